@@ -1,0 +1,157 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes front end of oracle/cpu_ref.cpp (liboracle.so).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "liboracle.so")
+
+KEYPOINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                           ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "cpu_ref.cpp")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "liboracle.so"], stdout=subprocess.DEVNULL)
+    return _SO
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_SO)
+        _lib.ora_extractor_create.restype = C.c_void_p
+        _lib.ora_extractor_create.argtypes = [C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int]
+        _lib.ora_extractor_destroy.argtypes = [C.c_void_p]
+        _lib.ora_fast_atan2.restype = C.c_float
+        _lib.ora_fast_atan2.argtypes = [C.c_float, C.c_float]
+        _lib.ora_stereo_frames.restype = C.c_long
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class Extractor:
+    """Mirror of FeatureExtractor (reference include/FeatureExtractor.h:52-97)."""
+
+    def __init__(self, nFeatures=2000, nLevels=8, imScale=1.2, edgeThreshold=19, patchSize=31,
+                 maxFastThreshold=20, minFastThreshold=7):
+        self.params = (int(nFeatures), int(nLevels), float(imScale), int(edgeThreshold), int(patchSize),
+                       int(maxFastThreshold), int(minFastThreshold))
+        self.nFeatures, self.nLevels = int(nFeatures), int(nLevels)
+        self.h = C.c_void_p(lib().ora_extractor_create(*self.params))
+        L = self.nLevels
+        self.scalePyramid = np.zeros(L, np.float32)
+        self.scaleInvPyramid = np.zeros(L, np.float32)
+        self.sigmaFactor = np.zeros(L, np.float32)
+        self.InvSigmaFactor = np.zeros(L, np.float32)
+        self.scaledPatchSize = np.zeros(L, np.int32)
+        self.featurePerLevel = np.zeros(L, np.int32)
+        self.umax = np.zeros(16, np.int32)
+        lib().ora_extractor_tables(self.h, _p(self.scalePyramid), _p(self.scaleInvPyramid), _p(self.sigmaFactor),
+                                   _p(self.InvSigmaFactor), _p(self.scaledPatchSize), _p(self.featurePerLevel),
+                                   _p(self.umax))
+
+    def __del__(self):
+        try:
+            lib().ora_extractor_destroy(self.h)
+        except Exception:
+            pass
+
+    def extractKeysNew(self, image: np.ndarray):
+        image = np.ascontiguousarray(image, np.uint8)
+        h, w = image.shape
+        cap = max(4 * self.nFeatures, 1024)
+        kp = np.zeros(cap, KEYPOINT_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n = lib().ora_extract(self.h, _p(image), w, h, w, _p(kp), _p(desc), cap)
+        assert n >= 0
+        return kp[:n].copy(), desc[:n].copy()
+
+    def level_image(self, level: int, blurred: bool = False) -> np.ndarray:
+        w, h = C.c_int(), C.c_int()
+        lib().ora_level_size(self.h, level, C.byref(w), C.byref(h))
+        out = np.zeros((h.value, w.value), np.uint8)
+        lib().ora_level_image(self.h, level, int(blurred), _p(out))
+        return out
+
+    def level_keys(self, level: int, kept: bool):
+        n = lib().ora_level_count(self.h, level, int(kept))
+        x = np.zeros(n, np.int32); y = np.zeros(n, np.int32); r = np.zeros(n, np.float32)
+        a = np.zeros(n, np.float32); m10 = np.zeros(n, np.int32); m01 = np.zeros(n, np.int32)
+        lib().ora_level_keys(self.h, level, int(kept), _p(x), _p(y), _p(r), _p(a), _p(m10), _p(m01))
+        return dict(x=x, y=y, response=r, angle=a, m10=m10, m01=m01)
+
+    def ssc_passes(self, level: int) -> int:
+        return lib().ora_level_ssc_passes(self.h, level)
+
+
+def stereo_match(feL: Extractor, feR: Extractor, fx: float, baseline: float, imageHeight: int, kl, dl, kr, dr):
+    """findStereoMatchesORB2R (reference src/FeatureMatcher.cpp:528-708) on the pyramids of the last extract."""
+    NL, NR = len(kl), len(kr)
+    ridx = np.zeros(NL, np.int32); lidx = np.zeros(NR, np.int32)
+    dep = np.zeros(NL, np.float32); close = np.zeros(NL, np.uint8)
+    stats = np.zeros(2, np.int32)
+    kl = np.ascontiguousarray(kl); kr = np.ascontiguousarray(kr)
+    dl = np.ascontiguousarray(dl); dr = np.ascontiguousarray(dr)
+    lib().ora_stereo_match(feL.h, feR.h, C.c_double(fx), C.c_float(baseline), imageHeight, _p(kl), _p(dl), NL,
+                           _p(kr), _p(dr), NR, _p(ridx), _p(lidx), _p(dep), _p(close), _p(stats))
+    return dict(rightIdxs=ridx, leftIdxs=lidx, estimatedDepth=dep, close=close.astype(bool),
+                hamming_tests=int(stats[0]), accepted=int(stats[1]))
+
+
+def assign_grid(kps, width: int, height: int):
+    """assignKeysToGrids (reference src/FeatureTracker.cpp:28-54) in CSR form."""
+    kps = np.ascontiguousarray(kps)
+    n = len(kps)
+    start = np.zeros(64 * 64 + 1, np.int32)
+    items = np.zeros(max(n, 1), np.int32)
+    xm, ym = C.c_float(), C.c_float()
+    yg = lib().ora_assign_grid(_p(kps), n, width, height, _p(start), _p(items), C.byref(xm), C.byref(ym))
+    return dict(xGrids=64, yGrids=yg, xMult=xm.value, yMult=ym.value, start=start[:yg * 64 + 1].copy(), items=items[:n].copy())
+
+
+def match_projection(fe: Extractor, mode: int, mps: dict, kl, dl, kr, dr, leftIdxs, rightIdxs, width, height, rad,
+                     matchedL, matchedR, matches):
+    """mode 0/1/2 = matchByProjectionRPred / matchByProjectionMono / matchByRadius
+    (reference src/FeatureMatcher.cpp:254-389 / 391-456 / 458-526).  Updates matchedL/R, matches in place."""
+    M = len(mps["desc"])
+    f = lambda k, dt: np.ascontiguousarray(mps[k], dt) if k in mps and mps[k] is not None else None
+    desc = f("desc", np.uint8); pL = f("predL", np.float32); pR = f("predR", np.float32)
+    lL = f("scaleLevelL", np.int32); lR = f("scaleLevelR", np.int32)
+    iF = f("inFrame", np.uint8); iR = f("inFrameR", np.uint8)
+    kl = np.ascontiguousarray(kl); dl = np.ascontiguousarray(dl)
+    NR = 0 if kr is None else len(kr)
+    if kr is not None:
+        kr = np.ascontiguousarray(kr); dr = np.ascontiguousarray(dr)
+    li = None if leftIdxs is None else np.ascontiguousarray(leftIdxs, np.int32)
+    ri = None if rightIdxs is None else np.ascontiguousarray(rightIdxs, np.int32)
+    assert matchedL.dtype == np.int32 and matches.dtype == np.int32 and matches.shape == (M, 2)
+    return lib().ora_match_projection(fe.h, mode, M, _p(desc), _p(pL), _p(pR), _p(lL), _p(lR), _p(iF), _p(iR),
+                                      _p(kl), _p(dl), len(kl), _p(kr), _p(dr), NR, _p(li), _p(ri), width, height,
+                                      C.c_float(rad), _p(matchedL), _p(matchedR), _p(matches))
+
+
+def stereo_frames(params, fx, baseline, L: np.ndarray, R: np.ndarray, shape: int, threads: int):
+    """CPU baseline: run F stereo frames; returns (total matches, per-frame left key counts)."""
+    L = np.ascontiguousarray(L, np.uint8); R = np.ascontiguousarray(R, np.uint8)
+    F, h, w = L.shape
+    nk = np.zeros(F, np.int32)
+    nF, nL, s, e, p, mx, mn = params
+    tot = lib().ora_stereo_frames(nF, nL, C.c_float(s), e, p, mx, mn, C.c_double(fx), C.c_float(baseline),
+                                  _p(L), _p(R), F, w, h, shape, threads, _p(nk))
+    return tot, nk
