@@ -1,0 +1,391 @@
+"""Host-side mirror of the reference's feature layer on top of the C ABI (include/gvs.h, libgvs.so).
+
+Class and method names follow the reference (include/FeatureExtractor.h:52-97, include/FeatureMatcher.h:22-65,
+src/FeatureTracker.cpp:28-70) so that parity tests read like the reference's call sites.  Everything here is
+ctypes plumbing: all computation happens in the CUDA kernels behind the C ABI, and every call fails loudly
+(GvsError) when the extension or a CUDA device is missing -- there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgvs.so")
+
+KEYPOINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                           ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+assert KEYPOINT_DTYPE.itemsize == 28
+
+GVS_MATCH_STEREO_PRED, GVS_MATCH_MONO, GVS_MATCH_RADIUS = 0, 1, 2
+
+# every symbol include/gvs.h declares (tests check that the library exports all of them)
+SYMBOLS = [
+    "gvs_last_error", "gvs_version", "gvs_default_params", "gvs_device_count",
+    "gvs_extractor_create", "gvs_extractor_destroy", "gvs_extractor_tables", "gvs_extractor_level_size",
+    "gvs_extract", "gvs_extract_batch_host", "gvs_extractor_input", "gvs_extract_batch_resident",
+    "gvs_extractor_sync", "gvs_extract_offsets", "gvs_extract_download", "gvs_extractor_set_stream",
+    "gvs_debug_level_image", "gvs_debug_level_candidates", "gvs_debug_level_kept",
+    "gvs_matcher_create", "gvs_matcher_destroy", "gvs_stereo_match_batch", "gvs_stereo_download",
+    "gvs_assign_grids_batch", "gvs_grid_download", "gvs_track_stereo_batch_host",
+    "gvs_track_stereo_batch_resident", "gvs_matcher_sync", "gvs_match_projection", "gvs_descriptor_distance",
+    "gvs_extractor_enable_timing", "gvs_extractor_stage_times", "gvs_matcher_launch_count",
+    "gvs_extractor_launch_count",
+]
+
+
+class GvsError(RuntimeError):
+    pass
+
+
+class _Params(C.Structure):
+    _fields_ = [("n_features", C.c_int32), ("n_levels", C.c_int32), ("im_scale", C.c_float),
+                ("edge_threshold", C.c_int32), ("patch_size", C.c_int32), ("max_fast_threshold", C.c_int32),
+                ("min_fast_threshold", C.c_int32)]
+
+
+class _MapPoints(C.Structure):
+    _fields_ = [("count", C.c_int32), ("desc", C.c_void_p), ("pred_l", C.c_void_p), ("pred_r", C.c_void_p),
+                ("scale_level_l", C.c_void_p), ("scale_level_r", C.c_void_p), ("in_frame", C.c_void_p),
+                ("in_frame_r", C.c_void_p)]
+
+
+class StageTimes(C.Structure):
+    _fields_ = [("pyramid_ms", C.c_float), ("fast_ms", C.c_float), ("select_ms", C.c_float), ("blur_ms", C.c_float),
+                ("describe_ms", C.c_float), ("stereo_ms", C.c_float), ("grid_ms", C.c_float), ("launches", C.c_int32)]
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Load libgvs.so.  Raises GvsError if it has not been built (python __graft_entry__.py build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise GvsError(f"{LIB_PATH} is missing: build the CUDA extension first (there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    lib.gvs_last_error.restype = C.c_char_p
+    for name in SYMBOLS:
+        getattr(lib, name)  # AttributeError if the header and the library disagree
+    vp, i32, f32 = C.c_void_p, C.c_int, C.c_float
+    lib.gvs_extractor_create.argtypes = [C.POINTER(vp), C.POINTER(_Params), i32, i32, i32, i32]
+    lib.gvs_extractor_destroy.argtypes = [vp]
+    lib.gvs_extractor_tables.argtypes = [vp] + [vp] * 6
+    lib.gvs_extractor_level_size.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32)]
+    lib.gvs_extract.argtypes = [vp, vp, i32, i32, i32, vp, vp, i32, C.POINTER(i32)]
+    lib.gvs_extract_batch_host.argtypes = [vp, vp, C.c_size_t, i32, i32]
+    lib.gvs_extractor_input.argtypes = [vp, C.POINTER(vp), C.POINTER(i32), C.POINTER(C.c_size_t)]
+    lib.gvs_extract_batch_resident.argtypes = [vp, i32]
+    lib.gvs_extractor_sync.argtypes = [vp]
+    lib.gvs_extract_offsets.argtypes = [vp, vp]
+    lib.gvs_extract_download.argtypes = [vp, i32, i32, vp, vp, i32]
+    lib.gvs_extractor_set_stream.argtypes = [vp, vp]
+    lib.gvs_debug_level_image.argtypes = [vp, i32, i32, i32, vp]
+    lib.gvs_debug_level_candidates.argtypes = [vp, i32, i32, vp, vp, vp, i32, C.POINTER(i32)]
+    lib.gvs_debug_level_kept.argtypes = [vp, i32, i32, vp, vp, vp, i32, C.POINTER(i32)]
+    lib.gvs_matcher_create.argtypes = [C.POINTER(vp), vp, vp, C.c_double, f32, i32]
+    lib.gvs_matcher_destroy.argtypes = [vp]
+    lib.gvs_stereo_match_batch.argtypes = [vp, i32]
+    lib.gvs_stereo_download.argtypes = [vp, i32, i32, vp, vp, vp, vp]
+    lib.gvs_assign_grids_batch.argtypes = [vp, i32, i32, i32]
+    lib.gvs_grid_download.argtypes = [vp, i32, i32, vp, vp, C.POINTER(i32), C.POINTER(f32), C.POINTER(f32)]
+    lib.gvs_track_stereo_batch_host.argtypes = [vp, vp, vp, C.c_size_t, i32, i32, i32, i32]
+    lib.gvs_track_stereo_batch_resident.argtypes = [vp, i32, i32, i32]
+    lib.gvs_matcher_sync.argtypes = [vp]
+    lib.gvs_match_projection.argtypes = [vp, i32, i32, C.POINTER(_MapPoints), f32, vp, vp, vp, C.POINTER(i32)]
+    lib.gvs_descriptor_distance.argtypes = [vp, vp, vp, i32, vp]
+    lib.gvs_extractor_enable_timing.argtypes = [vp, i32]
+    lib.gvs_extractor_stage_times.argtypes = [vp, C.POINTER(StageTimes)]
+    lib.gvs_matcher_launch_count.argtypes = [vp, C.POINTER(C.c_int64)]
+    lib.gvs_extractor_launch_count.argtypes = [vp, C.POINTER(C.c_int64)]
+    _lib = lib
+    return lib
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise GvsError(f"gvs error {rc}: {load_library().gvs_last_error().decode()}")
+
+
+def _p(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def device_count() -> int:
+    return load_library().gvs_device_count()
+
+
+@dataclass
+class TrackedKeys:
+    """include/FeatureExtractor.h:18-50.  Grids are CSR (cell_start, items) instead of vector<vector<vector<int>>>."""
+    keyPoints: np.ndarray = None
+    rightKeyPoints: np.ndarray = None
+    Desc: np.ndarray = None
+    rightDesc: np.ndarray = None
+    lkeyGrid: dict = field(default_factory=dict)
+    rkeyGrid: dict = field(default_factory=dict)
+    rightIdxs: np.ndarray = None
+    leftIdxs: np.ndarray = None
+    estimatedDepth: np.ndarray = None
+    close: np.ndarray = None
+    xMult: float = 0.0
+    yMult: float = 0.0
+    xGrids: int = 0
+    yGrids: int = 0
+
+
+class FeatureExtractor:
+    """include/FeatureExtractor.h:52-97 with `max_images` image slots (batch of independent images)."""
+
+    def __init__(self, nFeatures=2000, nLevels=8, imScale=1.2, edgeThreshold=19, patchSize=31, maxFastThreshold=20,
+                 minFastThreshold=7, *, width: int, height: int, max_images: int = 1, device: int = 0):
+        lib = load_library()
+        self._lib = lib
+        self.nFeatures, self.nLevels, self.imScale = int(nFeatures), int(nLevels), float(imScale)
+        self.edgeThreshold, self.patchSize = int(edgeThreshold), int(patchSize)
+        self.maxFastThreshold, self.minFastThreshold = int(maxFastThreshold), int(minFastThreshold)
+        self.width, self.height, self.max_images, self.device = int(width), int(height), int(max_images), int(device)
+        p = _Params(self.nFeatures, self.nLevels, self.imScale, self.edgeThreshold, self.patchSize,
+                    self.maxFastThreshold, self.minFastThreshold)
+        self.h = C.c_void_p()
+        _check(lib.gvs_extractor_create(C.byref(self.h), C.byref(p), self.width, self.height, self.max_images, self.device))
+        L = self.nLevels
+        self.scalePyramid = np.zeros(L, np.float32)
+        self.scaleInvPyramid = np.zeros(L, np.float32)
+        self.sigmaFactor = np.zeros(L, np.float32)
+        self.InvSigmaFactor = np.zeros(L, np.float32)
+        self.scaledPatchSize = np.zeros(L, np.int32)
+        self.featurePerLevel = np.zeros(L, np.int32)
+        _check(lib.gvs_extractor_tables(self.h, _p(self.scalePyramid), _p(self.scaleInvPyramid), _p(self.sigmaFactor),
+                                        _p(self.InvSigmaFactor), _p(self.scaledPatchSize), _p(self.featurePerLevel)))
+        self.cap_per_image = int(2 * self.featurePerLevel.sum() + 64 * L)
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self._lib.gvs_extractor_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- FeatureExtractor::extractKeysNew (src/FeatureExtractor.cpp:481-533)
+    def extractKeysNew(self, image: np.ndarray):
+        image = np.ascontiguousarray(image, np.uint8)
+        h, w = image.shape
+        cap = self.cap_per_image
+        kp = np.zeros(cap, KEYPOINT_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n = C.c_int(0)
+        _check(self._lib.gvs_extract(self.h, _p(image), w, h, w, _p(kp), _p(desc), cap, C.byref(n)))
+        return kp[:n.value].copy(), desc[:n.value].copy()
+
+    # -- batched
+    def extract_batch(self, images: np.ndarray) -> None:
+        """images: (n, H, W) uint8 host array (pinned or pageable).  Asynchronous."""
+        assert images.dtype == np.uint8 and images.ndim == 3 and images.flags.c_contiguous
+        n, h, w = images.shape
+        assert (h, w) == (self.height, self.width)
+        self._keep = images
+        _check(self._lib.gvs_extract_batch_host(self.h, _p(images), h * w, w, n))
+
+    def input_layout(self):
+        dev, pitch, stride = C.c_void_p(), C.c_int(), C.c_size_t()
+        _check(self._lib.gvs_extractor_input(self.h, C.byref(dev), C.byref(pitch), C.byref(stride)))
+        return dev.value, pitch.value, stride.value
+
+    def extract_batch_resident(self, n: int) -> None:
+        _check(self._lib.gvs_extract_batch_resident(self.h, n))
+
+    def sync(self) -> None:
+        _check(self._lib.gvs_extractor_sync(self.h))
+
+    def offsets(self, n: int) -> np.ndarray:
+        off = np.zeros(n + 1, np.int32)
+        _check(self._lib.gvs_extract_offsets(self.h, _p(off)))
+        return off
+
+    def download(self, first: int, count: int, total: int):
+        kp = np.zeros(max(total, 1), KEYPOINT_DTYPE)
+        desc = np.zeros((max(total, 1), 32), np.uint8)
+        _check(self._lib.gvs_extract_download(self.h, first, count, _p(kp), _p(desc), total))
+        return kp[:total], desc[:total]
+
+    def set_stream(self, cuda_stream: int | None) -> None:
+        _check(self._lib.gvs_extractor_set_stream(self.h, C.c_void_p(cuda_stream or 0)))
+
+    def level_size(self, level: int):
+        w, h = C.c_int(), C.c_int()
+        _check(self._lib.gvs_extractor_level_size(self.h, level, C.byref(w), C.byref(h)))
+        return w.value, h.value
+
+    # -- parity taps
+    def level_image(self, image: int, level: int, blurred: bool = False) -> np.ndarray:
+        w, h = self.level_size(level)
+        out = np.zeros((h, w), np.uint8)
+        _check(self._lib.gvs_debug_level_image(self.h, image, level, int(blurred), _p(out)))
+        return out
+
+    def _level_keys(self, fn, image: int, level: int):
+        cap = 1 << 20
+        x = np.zeros(cap, np.int32); y = np.zeros(cap, np.int32); s = np.zeros(cap, np.int32)
+        n = C.c_int(0)
+        _check(fn(self.h, image, level, _p(x), _p(y), _p(s), cap, C.byref(n)))
+        return x[:n.value].copy(), y[:n.value].copy(), s[:n.value].copy()
+
+    def level_candidates(self, image: int, level: int):
+        return self._level_keys(self._lib.gvs_debug_level_candidates, image, level)
+
+    def level_kept(self, image: int, level: int):
+        return self._level_keys(self._lib.gvs_debug_level_kept, image, level)
+
+    def enable_timing(self, on: bool = True) -> None:
+        _check(self._lib.gvs_extractor_enable_timing(self.h, int(on)))
+
+    def stage_times(self) -> StageTimes:
+        t = StageTimes()
+        _check(self._lib.gvs_extractor_stage_times(self.h, C.byref(t)))
+        return t
+
+    def launch_count(self) -> int:
+        v = C.c_int64(0)
+        _check(self._lib.gvs_extractor_launch_count(self.h, C.byref(v)))
+        return v.value
+
+
+class FeatureMatcher:
+    """include/FeatureMatcher.h:22-65.  zedptr is reduced to the three values the path reads: fx, baseline, height."""
+
+    def __init__(self, fx: float, baseline: float, feLeft: FeatureExtractor, feRight: FeatureExtractor | None,
+                 imageHeight: int = 360):
+        self._lib = load_library()
+        self.feLeft, self.feRight = feLeft, feRight if feRight is not None else feLeft
+        self.fx, self.baseline, self.imageHeight = float(fx), float(baseline), int(imageHeight)
+        self.closeNumber = 40
+        self.h = C.c_void_p()
+        _check(self._lib.gvs_matcher_create(C.byref(self.h), feLeft.h, self.feRight.h, self.fx, self.baseline, self.imageHeight))
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self._lib.gvs_matcher_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _dense(fe: FeatureExtractor, first: int, count: int):
+        off = fe.offsets(first + count)
+        return off, int(off[first]), int(off[first + count] - off[first])
+
+    # -- findStereoMatchesORB2R (src/FeatureMatcher.cpp:528-708) over the last extracted batch
+    def stereo_match_batch(self, n_frames: int) -> None:
+        _check(self._lib.gvs_stereo_match_batch(self.h, n_frames))
+
+    def stereo_download(self, first: int, count: int):
+        _, _, nl = self._dense(self.feLeft, first, count)
+        _, _, nr = self._dense(self.feRight, first, count)
+        ridx = np.zeros(max(nl, 1), np.int32); dep = np.zeros(max(nl, 1), np.float32); cl = np.zeros(max(nl, 1), np.uint8)
+        lidx = np.zeros(max(nr, 1), np.int32)
+        _check(self._lib.gvs_stereo_download(self.h, first, count, _p(ridx), _p(lidx), _p(dep), _p(cl)))
+        return ridx[:nl], lidx[:nr], dep[:nl], cl[:nl].astype(bool)
+
+    def assign_grids_batch(self, n_frames: int, width: int, height: int) -> None:
+        _check(self._lib.gvs_assign_grids_batch(self.h, n_frames, width, height))
+
+    def grid_download(self, frame: int, side: int):
+        fe = self.feRight if side else self.feLeft
+        off = fe.offsets(frame + 1)
+        n = int(off[frame + 1] - off[frame])
+        start = np.zeros(64 * 64 + 1, np.int32); items = np.zeros(max(n, 1), np.int32)
+        yg, xm, ym = C.c_int(), C.c_float(), C.c_float()
+        _check(self._lib.gvs_grid_download(self.h, frame, side, _p(start), _p(items), C.byref(yg), C.byref(xm), C.byref(ym)))
+        return dict(xGrids=64, yGrids=yg.value, xMult=xm.value, yMult=ym.value, start=start[:64 * yg.value + 1].copy(),
+                    items=items[:n].copy())
+
+    def track_stereo_batch(self, left: np.ndarray, right: np.ndarray) -> None:
+        """FeatureTracker::extractORBAndStereoMatch (src/FeatureTracker.cpp:56-70) for a batch of host frames."""
+        assert left.shape == right.shape and left.dtype == np.uint8 and left.flags.c_contiguous and right.flags.c_contiguous
+        n, h, w = left.shape
+        self._keep = (left, right)
+        _check(self._lib.gvs_track_stereo_batch_host(self.h, _p(left), _p(right), h * w, w, n, w, h))
+
+    def track_stereo_batch_resident(self, n_frames: int, width: int, height: int) -> None:
+        _check(self._lib.gvs_track_stereo_batch_resident(self.h, n_frames, width, height))
+
+    def sync(self) -> None:
+        _check(self._lib.gvs_matcher_sync(self.h))
+
+    def launch_count(self) -> int:
+        v = C.c_int64(0)
+        _check(self._lib.gvs_matcher_launch_count(self.h, C.byref(v)))
+        return v.value
+
+    # -- matchByProjectionRPred / matchByProjectionMono / matchByRadius (src/FeatureMatcher.cpp:254-526)
+    def _project(self, frame, mode, mps, rad, matchedL, matchedR, matches):
+        M = len(mps["desc"])
+        keep = []
+
+        def arr(key, dt):
+            v = mps.get(key)
+            if v is None:
+                return None
+            a = np.ascontiguousarray(v, dt)
+            keep.append(a)
+            return a.ctypes.data
+
+        s = _MapPoints(M, arr("desc", np.uint8), arr("predL", np.float32), arr("predR", np.float32),
+                       arr("scaleLevelL", np.int32), arr("scaleLevelR", np.int32), arr("inFrame", np.uint8),
+                       arr("inFrameR", np.uint8))
+        assert matchedL.dtype == np.int32 and matches.dtype == np.int32 and matches.shape == (M, 2) and matches.flags.c_contiguous
+        n = C.c_int(0)
+        _check(self._lib.gvs_match_projection(self.h, frame, mode, C.byref(s), float(rad), _p(matchedL),
+                                              _p(matchedR) if matchedR is not None else None, _p(matches), C.byref(n)))
+        return n.value
+
+    def matchByProjectionRPred(self, mps, frame, matchedIdxsL, matchedIdxsR, matchesIdxs, rad):
+        return self._project(frame, GVS_MATCH_STEREO_PRED, mps, rad, matchedIdxsL, matchedIdxsR, matchesIdxs)
+
+    def matchByProjectionMono(self, mps, frame, matchedIdxsL, matchesIdxs, rad):
+        return self._project(frame, GVS_MATCH_MONO, mps, rad, matchedIdxsL, None, matchesIdxs)
+
+    def matchByRadius(self, mps, frame, matchedIdxsL, matchesIdxs, rad):
+        return self._project(frame, GVS_MATCH_RADIUS, mps, rad, matchedIdxsL, None, matchesIdxs)
+
+    def DescriptorDistance(self, a: np.ndarray, b: np.ndarray) -> np.ndarray:
+        a = np.ascontiguousarray(a, np.uint8).reshape(-1, 32); b = np.ascontiguousarray(b, np.uint8).reshape(-1, 32)
+        out = np.zeros(len(a), np.int32)
+        _check(self._lib.gvs_descriptor_distance(self.h, _p(a), _p(b), len(a), _p(out)))
+        return out
+
+
+def extractORBAndStereoMatch(fm: FeatureMatcher, leftIm: np.ndarray, rightIm: np.ndarray) -> TrackedKeys:
+    """FeatureTracker::extractORBAndStereoMatch (src/FeatureTracker.cpp:56-70) for one stereo pair."""
+    h, w = leftIm.shape
+    fm.track_stereo_batch(np.ascontiguousarray(leftIm[None]), np.ascontiguousarray(rightIm[None]))
+    return tracked_keys(fm, 0, w, h)
+
+
+def tracked_keys(fm: FeatureMatcher, frame: int, width: int, height: int) -> TrackedKeys:
+    """Assemble the TrackedKeys of one frame of the last batch from the device-resident results."""
+    k = TrackedKeys()
+    offL = fm.feLeft.offsets(frame + 1); offR = fm.feRight.offsets(frame + 1)
+    nl = int(offL[frame + 1] - offL[frame]); nr = int(offR[frame + 1] - offR[frame])
+    k.keyPoints, k.Desc = fm.feLeft.download(frame, 1, nl)
+    k.rightKeyPoints, k.rightDesc = fm.feRight.download(frame, 1, nr)
+    k.rightIdxs, k.leftIdxs, k.estimatedDepth, k.close = fm.stereo_download(frame, 1)
+    k.lkeyGrid = fm.grid_download(frame, 0)
+    k.rkeyGrid = fm.grid_download(frame, 1)
+    k.xGrids, k.yGrids = 64, k.lkeyGrid["yGrids"]
+    k.xMult, k.yMult = k.lkeyGrid["xMult"], k.lkeyGrid["yMult"]
+    return k

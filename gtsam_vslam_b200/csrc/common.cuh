@@ -1,0 +1,185 @@
+// Shared declarations of the sm_100a frontend kernels (internal; the public surface is include/gvs.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/gvs.h"
+
+namespace gvs {
+
+constexpr int kMaxLevels = GVS_MAX_LEVELS;
+constexpr int kHalfPatch = 15;  // FeatureExtractor::halfPatchSize, include/FeatureExtractor.h:67
+constexpr int kFastEdge = 3;    // computeKeypointsORBNew, src/FeatureExtractor.cpp:538
+constexpr int kCellW = 35;      // W, :542
+
+// Geometry and quotas of one pyramid level.  Lives in kernel parameter space (__grid_constant__).
+struct LevelGeom {
+    int w, h, pitch;         // pitch: bytes per row in the slab (multiple of 64)
+    unsigned off;            // byte offset of the level inside one image's slab
+    int nCols, nRows;        // FAST cell grid (src/FeatureExtractor.cpp:555-556)
+    int gridW, gridH;        // cell pitch (:558-559)
+    int cellBase;            // first entry of this level in the per-image cell-count array
+    int quota, kmin, kmax;   // featurePerLevel, SSC tolerance band (:405-406)
+    int sscHigh;             // closed-form upper bracket (:382-395)
+    int candOff, candCap;    // candidate records of this level inside one image's record buffer
+    int keptOff, keptCap;    // kept keys of this level inside one image's staging buffer
+    int tabX, tabY;          // offsets of the resize tables of this level (dst level), in entries
+    int xmax;                // first dst column whose source column is clamped (cv::resize)
+    float scale, invScale;   // scalePyramid, scaleInvPyramid
+    int scaledPatch;         // scaledPatchSize
+    int fastItemBase;        // first FAST work item of this level
+};
+
+struct Geometry {
+    int nLevels;
+    int width, height;
+    unsigned slabBytes;      // bytes per image in the pyramid slab
+    int cellsPerImage;
+    int candPerImage;        // records per image
+    int keptPerImage;        // staging keys per image
+    int tMin, tMax;          // minFastThreshold, maxFastThreshold
+    int edge;                // edgeThreshold: keypoints lie in [edge, w-edge) x [edge, h-edge)
+    int umax[kHalfPatch + 1];
+    LevelGeom lv[kMaxLevels];
+};
+
+// One FAST work item = a strip of up to kFastCellsPerItem consecutive cells of one cell row.
+constexpr int kFastCellsPerItem = 4;
+struct FastItem {
+    short level, iR, iC0, nC;
+};
+
+// Resize tables entry for one destination column / row (cv::resize INTER_LINEAR fixed point, 11 bits).
+struct ResizeTap {
+    short ofs, a0, a1, pad;
+};
+
+// 8-byte candidate record written by the FAST kernel in arbitrary order.
+//   w0 = x | y << 12 | score << 24 ; w1 = cell | rank << 16   (rank = position inside the cell's emission order)
+struct CandRec {
+    unsigned w0, w1;
+};
+
+// Kept key after selection (staging, per level region): x | y << 12 | score << 24
+typedef unsigned KeptKey;
+
+#define GVS_CUDA_OK(expr)                                                                     \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) return gvs::fail(GVS_ERR_CUDA, #expr, cudaGetErrorString(_e)); \
+    } while (0)
+
+int fail(int code, const char* what, const char* detail = nullptr);
+
+struct StageTimer;
+
+// ---- kernel launchers (one translation unit each) -------------------------------------------------
+void launchPyramid(const Geometry& g, uint8_t* slab, const ResizeTap* taps, int nImages, cudaStream_t s, int* launches);
+void launchFast(const Geometry& g, const uint8_t* slab, const FastItem* items, int nItems, int nImages, CandRec* recs,
+                int* nCand, unsigned short* cellCnt, int* status, cudaStream_t s, int* launches);
+void launchSelect(const Geometry& g, int nImages, const CandRec* recs, const int* nCand, const unsigned short* cellCnt,
+                  KeptKey* kept, int* keptCnt, unsigned* orderedDbg, uint8_t* scratch, size_t scratchPerCta, int nCtas,
+                  int* workCounter, int* status, cudaStream_t s, int* launches);
+size_t selectScratchBytes(const Geometry& g);
+int selectMaxCtas(int device);
+void launchOffsets(const Geometry& g, int nImages, const int* keptCnt, int* imgOff, int totalCap, int* status,
+                   cudaStream_t s, int* launches);
+struct BlurItem { short level, tx, ty, pad; };  // one 64x32 output tile
+constexpr int kBlurTW = 64, kBlurTH = 32;
+void launchBlur(const Geometry& g, const uint8_t* slab, uint8_t* blurSlab, const BlurItem* items, int nItems, int nImages,
+                cudaStream_t s, int* launches);
+void launchDescribe(const Geometry& g, const uint8_t* slab, const uint8_t* blurSlab, int nImages, const KeptKey* kept,
+                    const int* keptCnt, const int* imgOff, gvs_keypoint* kps, uint8_t* desc, int* momentsDbg,
+                    int totalCap, cudaStream_t s, int* launches);
+
+struct StereoArgs {
+    const uint8_t* slabL;
+    const uint8_t* slabR;
+    const gvs_keypoint* kpL;
+    const gvs_keypoint* kpR;
+    const uint8_t* descL;
+    const uint8_t* descR;
+    const int* offL;  // nFrames+1
+    const int* offR;
+    const int* keptCntL;  // per image per level counts (nImages x kMaxLevels)
+    const int* keptCntR;
+    int* rightIdxs;   // dense, left offsets
+    int* leftIdxs;    // dense, right offsets
+    float* depth;
+    uint8_t* close;
+    int* sadBest;     // dense, left offsets (scratch)
+    double fx;
+    float baseline;
+    int imageHeight;
+    int closeNumber;
+    int thDist;
+};
+void launchStereo(const Geometry& g, const StereoArgs& a, int nFrames, int maxKeysPerImage, cudaStream_t s, int* launches);
+
+struct GridArgs {
+    const gvs_keypoint* kps;
+    const int* off;     // nImages+1
+    int* cellStart;     // nImages x (maxCells+1)
+    int* items;         // dense, same offsets as kps
+    int xGrids, yGrids;
+    float xMult, yMult;
+    int maxCells;
+};
+void launchGrid(const GridArgs& a, int nImages, cudaStream_t s, int* launches);
+
+struct ProjArgs {
+    int mode;           // gvs_match_mode
+    int M;
+    const uint8_t* mpDesc;
+    const float* predL;
+    const float* predR;
+    const int* lvlL;
+    const int* lvlR;
+    const uint8_t* inFrame;
+    const uint8_t* inFrameR;
+    const gvs_keypoint* kpL;
+    const gvs_keypoint* kpR;
+    const uint8_t* descL;
+    const uint8_t* descR;
+    int NL, NR;
+    const int* cellStartL;
+    const int* itemsL;
+    const int* cellStartR;
+    const int* itemsR;
+    const int* leftIdxs;   // stereo partner arrays of the frame (mode 0)
+    const int* rightIdxs;
+    int xGrids, yGrids;
+    float xMult, yMult;
+    float rad;
+    float scalePyramid[kMaxLevels];
+    // candidate lists (phase 1 output / phase 2 input)
+    void* recs;            // 2*M ProjRec (project.cu)
+    int* poolTop;          // [2] list pool counters (left, right)
+    unsigned* candL;       // packed idx | dist << 16 | level << 25, see project.cu
+    unsigned* candR;
+    int candCap;           // entries per pool
+    // in/out
+    int* matchedL;
+    int* matchedR;
+    int* matches;          // M x 2
+    int* nMatches;
+    int* status;
+};
+void launchProject(const ProjArgs& a, cudaStream_t s, int* launches);
+void launchHamming(const uint8_t* a, const uint8_t* b, int n, int* out, cudaStream_t s, int* launches);
+
+// status bits written by kernels into a device int (checked on sync)
+enum : int { kStatCandOverflow = 1, kStatKeptOverflow = 2, kStatOutputOverflow = 4, kStatProjOverflow = 8 };
+
+// ---- small device helpers ----------------------------------------------------------------------------
+__device__ __forceinline__ const uint8_t* levelPtr(const uint8_t* slab, const Geometry& g, int img, int level) {
+    return slab + (size_t)img * g.slabBytes + g.lv[level].off;
+}
+__device__ __forceinline__ uint8_t* levelPtr(uint8_t* slab, const Geometry& g, int img, int level) {
+    return slab + (size_t)img * g.slabBytes + g.lv[level].off;
+}
+
+}  // namespace gvs

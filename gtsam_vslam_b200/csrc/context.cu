@@ -1,0 +1,937 @@
+// Host side of the C ABI (include/gvs.h): handle lifetime, level geometry and tables (the FeatureExtractor
+// constructor, reference src/FeatureExtractor.cpp:620-682), launch sequencing, transfers.  No CPU compute path:
+// every entry point either launches the CUDA kernels or fails.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace gvs {
+
+static thread_local std::string g_lastError;
+
+int fail(int code, const char* what, const char* detail) {
+    g_lastError = what ? what : "";
+    if (detail) { g_lastError += ": "; g_lastError += detail; }
+    return code;
+}
+
+static inline int cvRoundF(float v) { return (int)lrintf(v); }
+
+template <typename T>
+static cudaError_t devAlloc(T** p, size_t count) {
+    *p = nullptr;
+    return cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(count, 1) * sizeof(T));
+}
+
+}  // namespace gvs
+
+using namespace gvs;
+
+struct gvs_extractor {
+    int device = 0;
+    gvs_extractor_params params{};
+    int width = 0, height = 0, maxImages = 0;
+    Geometry g{};
+    std::vector<float> scale, invScale, sigma, invSigma;
+    std::vector<int> patch, quota;
+    cudaStream_t ownStream = nullptr, stream = nullptr;
+    cudaEvent_t doneEvent = nullptr;
+    // device
+    uint8_t* slab = nullptr;
+    uint8_t* blurSlab = nullptr;
+    ResizeTap* taps = nullptr;
+    FastItem* fastItems = nullptr;
+    int nFastItems = 0;
+    BlurItem* blurItems = nullptr;
+    int nBlurItems = 0;
+    CandRec* recs = nullptr;
+    int* nCand = nullptr;
+    unsigned short* cellCnt = nullptr;
+    KeptKey* kept = nullptr;
+    int* keptCnt = nullptr;
+    int* imgOff = nullptr;
+    unsigned* orderedDbg = nullptr;
+    int* momentsDbg = nullptr;
+    uint8_t* selScratch = nullptr;
+    size_t selScratchPerCta = 0;
+    int selCtas = 0;
+    int* workCounter = nullptr;
+    int* status = nullptr;
+    gvs_keypoint* kps = nullptr;
+    uint8_t* desc = nullptr;
+    int totalCap = 0;
+    // host (pinned)
+    int* hOff = nullptr;
+    int* hStatus = nullptr;
+    int lastN = 0;
+    bool pending = false;
+    int launches = 0;
+    int64_t launchesTotal = 0;
+    bool timing = false;
+    cudaEvent_t ev[8] = {};
+    gvs_stage_times times{};
+};
+
+struct gvs_matcher {
+    gvs_extractor* L = nullptr;
+    gvs_extractor* R = nullptr;
+    double fx = 0;
+    float baseline = 0;
+    int imageHeight = 0;
+    int* rightIdxs = nullptr;
+    int* leftIdxs = nullptr;
+    int* sadBest = nullptr;
+    float* depth = nullptr;
+    uint8_t* close = nullptr;
+    // grids
+    int* cellStartL = nullptr;
+    int* cellStartR = nullptr;
+    int* itemsL = nullptr;
+    int* itemsR = nullptr;
+    int maxCells = GVS_GRID_X * GVS_GRID_X;
+    int xGrids = 0, yGrids = 0;
+    float xMult = 0, yMult = 0;
+    bool gridsValid = false, stereoValid = false;
+    int lastFrames = 0;
+    cudaEvent_t evR = nullptr;
+    // projection scratch (grown on demand)
+    uint8_t* pj = nullptr;
+    size_t pjBytes = 0;
+    unsigned* pool = nullptr;
+    int poolCap = 0;
+    int* pjStatus = nullptr;
+    int launches = 0;
+    int64_t launchesTotal = 0;
+    cudaEvent_t ev[4] = {};
+    float stereoMs = 0, gridMs = 0;
+};
+
+namespace {
+
+int buildGeometry(gvs_extractor* fe) {
+    const gvs_extractor_params& p = fe->params;
+    const int L = p.n_levels;
+    Geometry& g = fe->g;
+    std::memset(&g, 0, sizeof(g));
+    g.nLevels = L;
+    g.width = fe->width;
+    g.height = fe->height;
+    g.tMin = p.min_fast_threshold;
+    g.tMax = p.max_fast_threshold;
+    g.edge = p.edge_threshold;
+    // ---- tables, float32 cumulative (src/FeatureExtractor.cpp:622-644)
+    fe->scale.assign(L, 1.f); fe->invScale.assign(L, 1.f); fe->sigma.assign(L, 1.f); fe->invSigma.assign(L, 1.f);
+    fe->patch.assign(L, p.patch_size); fe->quota.assign(L, 0);
+    for (int i = 1; i < L; i++) {
+        fe->scale[i] = fe->scale[i - 1] * p.im_scale;
+        fe->patch[i] = (int)(p.patch_size * fe->scale[i]);
+        fe->sigma[i] = fe->scale[i] * fe->scale[i];
+    }
+    for (int i = 0; i < L; i++) { fe->invScale[i] = 1.0f / fe->scale[i]; fe->invSigma[i] = 1.0f / fe->sigma[i]; }
+    // ---- per-level quota (:648-659)
+    {
+        const float factor = 1.0f / p.im_scale;
+        float nd = p.n_features * (1 - factor) / (1 - (float)std::pow((double)factor, (double)L));
+        int sum = 0;
+        for (int l = 0; l < L - 1; l++) { fe->quota[l] = cvRoundF(nd); sum += fe->quota[l]; nd *= factor; }
+        fe->quota[L - 1] = std::max(p.n_features - sum, 0);
+    }
+    // ---- umax (:666-680)
+    {
+        const int hp = kHalfPatch;
+        int v, v0, vmax = (int)std::floor(hp * std::sqrt(2.f) / 2 + 1), vmin = (int)std::ceil(hp * std::sqrt(2.f) / 2);
+        const double hp2 = hp * hp;
+        for (v = 0; v <= vmax; ++v) g.umax[v] = (int)lrint(std::sqrt(hp2 - v * v));
+        for (v = hp, v0 = 0; v >= vmin; --v) {
+            while (g.umax[v0] == g.umax[v0 + 1]) ++v0;
+            g.umax[v] = v0;
+            ++v0;
+        }
+    }
+    // ---- level geometry
+    unsigned off = 0;
+    int cellBase = 0, candOff = 0, keptOff = 0, tab = 0;
+    for (int l = 0; l < L; l++) {
+        LevelGeom& lv = g.lv[l];
+        lv.w = cvRoundF((float)fe->width * fe->invScale[l]);    // computePyramid :347
+        lv.h = cvRoundF((float)fe->height * fe->invScale[l]);
+        if (lv.w > 4095 || lv.h > 4095) return fail(GVS_ERR_INVALID, "image larger than 4095 px is not supported");
+        if (lv.w < 2 * p.edge_threshold + 8 || lv.h < 2 * p.edge_threshold + 8)
+            return fail(GVS_ERR_INVALID, "pyramid level smaller than the border: reduce n_levels");
+        lv.pitch = (lv.w + 63) & ~63;
+        lv.off = off;
+        off += (unsigned)lv.pitch * lv.h;
+        off = (off + 255u) & ~255u;
+        // FAST cells (computeKeypointsORBNew :544-559)
+        const int minB = p.edge_threshold - kFastEdge;
+        const int maxX = lv.w - p.edge_threshold + kFastEdge, maxY = lv.h - p.edge_threshold + kFastEdge;
+        const int wid = maxX - minB, hig = maxY - minB;
+        const float W = (float)kCellW;
+        lv.nCols = (int)(wid / W);
+        lv.nRows = (int)(hig / W);
+        lv.gridW = lv.nCols > 0 ? (int)std::ceil((float)wid / lv.nCols) : 0;
+        lv.gridH = lv.nRows > 0 ? (int)std::ceil((float)hig / lv.nRows) : 0;
+        if (lv.gridW > 255 || lv.gridH > 255) return fail(GVS_ERR_INVALID, "FAST cell larger than 255 px");
+        lv.cellBase = cellBase;
+        cellBase += lv.nCols * lv.nRows;
+        if (lv.nCols * lv.nRows > 65535) return fail(GVS_ERR_INVALID, "too many FAST cells in a level");
+        // quota and SSC constants (ssc :382-406, called with tolerance 0.1f, cols, rows :612)
+        lv.quota = fe->quota[l];
+        {
+            const int K = lv.quota, rows = lv.h, cols = lv.w;
+            const int exp1 = rows + cols + 2 * K;
+            const long long exp2 = ((long long)4 * cols + (long long)4 * K + (long long)4 * rows * K + (long long)rows * rows +
+                                    (long long)cols * cols - (long long)2 * rows * cols + (long long)4 * rows * cols * K);
+            const double exp3 = std::sqrt((double)exp2), exp4 = K - 1;
+            const double sol1 = -std::round((exp1 + exp3) / exp4), sol2 = -std::round((exp1 - exp3) / exp4);
+            lv.sscHigh = (int)((sol1 > sol2) ? sol1 : sol2);
+            const float tol = 0.1f;
+            const unsigned uK = (unsigned)K;
+            lv.kmin = (int)(unsigned)std::round(uK - (uK * tol));
+            lv.kmax = (int)(unsigned)std::round(uK + (uK * tol));
+        }
+        lv.candOff = candOff;
+        lv.candCap = std::min(((lv.w * lv.h) / 12 + 256 + 3) & ~3, 65535 * 16);
+        candOff += lv.candCap;
+        lv.keptOff = keptOff;
+        lv.keptCap = 2 * lv.quota + 64;
+        keptOff += lv.keptCap;
+        lv.scale = fe->scale[l];
+        lv.invScale = fe->invScale[l];
+        lv.scaledPatch = fe->patch[l];
+        if (l > 0) {
+            lv.tabX = tab; tab += (lv.w + 3) & ~3;
+            lv.tabY = tab; tab += (lv.h + 3) & ~3;
+        }
+    }
+    // whole rows of level 0 per image, so that a batch of host images is one strided 3-D copy
+    const unsigned unit = (unsigned)g.lv[0].pitch * 4u;
+    g.slabBytes = (off + unit - 1) / unit * unit;
+    g.cellsPerImage = cellBase;
+    g.candPerImage = candOff;
+    g.keptPerImage = keptOff;
+    if (g.keptPerImage > 65535) return fail(GVS_ERR_INVALID, "n_features too large (more than 65535 keys per image)");
+    return tab;
+}
+
+// cv::resize INTER_LINEAR coefficient tables, float32 exactly as OpenCV computes them
+void buildTaps(const gvs_extractor* fe, std::vector<ResizeTap>& taps, int nTaps) {
+    taps.assign(nTaps, ResizeTap{0, 0, 0, 0});
+    const Geometry& g = fe->g;
+    for (int l = 1; l < g.nLevels; l++) {
+        const LevelGeom& S = g.lv[l - 1];
+        const LevelGeom& D = g.lv[l];
+        const double scale_x = 1.0 / ((double)D.w / S.w), scale_y = 1.0 / ((double)D.h / S.h);
+        for (int dx = 0; dx < D.w; dx++) {
+            float fx = (float)((dx + 0.5) * scale_x - 0.5);
+            int sx = (int)std::floor(fx);
+            fx -= sx;
+            bool clampR = false;
+            if (sx < 0) { fx = 0; sx = 0; }
+            if (sx >= S.w - 1) { fx = 0; sx = S.w - 1; clampR = true; }
+            ResizeTap t;
+            t.ofs = (short)sx;
+            if (clampR) { t.a0 = 2048; t.a1 = 0; t.pad = (short)sx; }
+            else { t.a0 = (short)cvRoundF((1.f - fx) * 2048); t.a1 = (short)cvRoundF(fx * 2048); t.pad = (short)(sx + 1); }
+            taps[D.tabX + dx] = t;
+        }
+        for (int dy = 0; dy < D.h; dy++) {
+            float fy = (float)((dy + 0.5) * scale_y - 0.5);
+            int sy = (int)std::floor(fy);
+            fy -= sy;
+            ResizeTap t;
+            t.ofs = (short)std::min(std::max(sy, 0), S.h - 1);
+            t.pad = (short)std::min(std::max(sy + 1, 0), S.h - 1);
+            t.a0 = (short)cvRoundF((1.f - fy) * 2048);
+            t.a1 = (short)cvRoundF(fy * 2048);
+            taps[D.tabY + dy] = t;
+        }
+    }
+}
+
+void destroyExtractor(gvs_extractor* fe) {
+    if (!fe) return;
+    cudaSetDevice(fe->device);
+    if (fe->ownStream) cudaStreamSynchronize(fe->ownStream);
+    cudaFree(fe->slab); cudaFree(fe->blurSlab); cudaFree(fe->taps); cudaFree(fe->fastItems); cudaFree(fe->blurItems);
+    cudaFree(fe->recs); cudaFree(fe->nCand); cudaFree(fe->cellCnt); cudaFree(fe->kept); cudaFree(fe->keptCnt);
+    cudaFree(fe->imgOff); cudaFree(fe->orderedDbg); cudaFree(fe->momentsDbg); cudaFree(fe->selScratch);
+    cudaFree(fe->workCounter); cudaFree(fe->status); cudaFree(fe->kps); cudaFree(fe->desc);
+    if (fe->hOff) cudaFreeHost(fe->hOff);
+    if (fe->hStatus) cudaFreeHost(fe->hStatus);
+    if (fe->doneEvent) cudaEventDestroy(fe->doneEvent);
+    for (auto& e : fe->ev) if (e) cudaEventDestroy(e);
+    if (fe->ownStream) cudaStreamDestroy(fe->ownStream);
+    delete fe;
+}
+
+// the whole extraction pipeline for image slots [0, n) (src/FeatureExtractor.cpp:481-533 for each image)
+int runExtract(gvs_extractor* fe, int n) {
+    const Geometry& g = fe->g;
+    cudaStream_t s = fe->stream;
+    fe->launches = 0;
+    const bool T = fe->timing;
+    GVS_CUDA_OK(cudaMemsetAsync(fe->status, 0, sizeof(int), s));
+    if (T) cudaEventRecord(fe->ev[0], s);
+    launchPyramid(g, fe->slab, fe->taps, n, s, &fe->launches);
+    if (T) cudaEventRecord(fe->ev[1], s);
+    launchFast(g, fe->slab, fe->fastItems, fe->nFastItems, n, fe->recs, fe->nCand, fe->cellCnt, fe->status, s, &fe->launches);
+    if (T) cudaEventRecord(fe->ev[2], s);
+    launchSelect(g, n, fe->recs, fe->nCand, fe->cellCnt, fe->kept, fe->keptCnt, fe->orderedDbg, fe->selScratch,
+                 fe->selScratchPerCta, fe->selCtas, fe->workCounter, fe->status, s, &fe->launches);
+    launchOffsets(g, n, fe->keptCnt, fe->imgOff, fe->totalCap, fe->status, s, &fe->launches);
+    if (T) cudaEventRecord(fe->ev[3], s);
+    launchBlur(g, fe->slab, fe->blurSlab, fe->blurItems, fe->nBlurItems, n, s, &fe->launches);
+    if (T) cudaEventRecord(fe->ev[4], s);
+    launchDescribe(g, fe->slab, fe->blurSlab, n, fe->kept, fe->keptCnt, fe->imgOff, fe->kps, fe->desc, fe->momentsDbg,
+                   fe->totalCap, s, &fe->launches);
+    if (T) cudaEventRecord(fe->ev[5], s);
+    GVS_CUDA_OK(cudaMemcpyAsync(fe->hOff, fe->imgOff, sizeof(int) * (n + 1), cudaMemcpyDeviceToHost, s));
+    GVS_CUDA_OK(cudaMemcpyAsync(fe->hStatus, fe->status, sizeof(int), cudaMemcpyDeviceToHost, s));
+    GVS_CUDA_OK(cudaEventRecord(fe->doneEvent, s));
+    GVS_CUDA_OK(cudaGetLastError());
+    fe->lastN = n;
+    fe->pending = true;
+    fe->launchesTotal += fe->launches;
+    return GVS_OK;
+}
+
+int syncExtract(gvs_extractor* fe) {
+    GVS_CUDA_OK(cudaSetDevice(fe->device));
+    GVS_CUDA_OK(cudaStreamSynchronize(fe->stream));
+    if (fe->pending) {
+        fe->pending = false;
+        if (fe->timing) {
+            float* t[5] = {&fe->times.pyramid_ms, &fe->times.fast_ms, &fe->times.select_ms, &fe->times.blur_ms,
+                           &fe->times.describe_ms};
+            for (int i = 0; i < 5; i++) cudaEventElapsedTime(t[i], fe->ev[i], fe->ev[i + 1]);
+            fe->times.launches = fe->launches;
+        }
+    }
+    const int st = *fe->hStatus;
+    if (st & kStatCandOverflow) return fail(GVS_ERR_CAPACITY, "FAST candidate buffer overflow (image denser than 1 corner per 12 px)");
+    if (st & kStatKeptOverflow) return fail(GVS_ERR_CAPACITY, "kept-key staging overflow (ssc returned more than 2*quota+64 keys)");
+    if (st & kStatOutputOverflow) return fail(GVS_ERR_CAPACITY, "dense output overflow");
+    return GVS_OK;
+}
+
+int checkBatch(gvs_extractor* fe, int n) {
+    if (!fe) return fail(GVS_ERR_INVALID, "null extractor");
+    if (n < 1 || n > fe->maxImages) return fail(GVS_ERR_INVALID, "n_images out of range for this handle");
+    return GVS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* gvs_last_error(void) { return g_lastError.c_str(); }
+int gvs_version(void) { return 100; }
+void gvs_default_params(gvs_extractor_params* p) {
+    if (!p) return;
+    p->n_features = 2000; p->n_levels = 8; p->im_scale = 1.2f; p->edge_threshold = 19; p->patch_size = 31;
+    p->max_fast_threshold = 20; p->min_fast_threshold = 7;
+}
+int gvs_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int gvs_extractor_create(gvs_extractor** out, const gvs_extractor_params* params, int width, int height, int max_images,
+                         int device) {
+    if (!out || !params) return fail(GVS_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (params->n_levels < 1 || params->n_levels > kMaxLevels) return fail(GVS_ERR_INVALID, "n_levels must be in [1, 12]");
+    if (params->n_features < 2 || params->im_scale <= 1.0f) return fail(GVS_ERR_INVALID, "bad n_features / im_scale");
+    if (params->patch_size != 31) return fail(GVS_ERR_INVALID, "patch_size must be 31 (halfPatchSize is fixed to 15 in the reference)");
+    if (params->edge_threshold < 19) return fail(GVS_ERR_INVALID, "edge_threshold must be >= 19 (descriptor reach)");
+    if (params->min_fast_threshold < 1 || params->max_fast_threshold < params->min_fast_threshold || params->max_fast_threshold > 254)
+        return fail(GVS_ERR_INVALID, "bad FAST thresholds");
+    if (max_images < 1 || max_images > 65535) return fail(GVS_ERR_INVALID, "max_images must be in [1, 65535]");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(GVS_ERR_CUDA, "no CUDA device: this library has no CPU path");
+    }
+    if (device < 0 || device >= ndev) return fail(GVS_ERR_INVALID, "bad device index");
+    GVS_CUDA_OK(cudaSetDevice(device));
+    gvs_extractor* fe = new gvs_extractor();
+    fe->device = device; fe->params = *params; fe->width = width; fe->height = height; fe->maxImages = max_images;
+    const int nTaps = buildGeometry(fe);
+    if (nTaps < 0) { delete fe; return nTaps; }
+    const Geometry& g = fe->g;
+    const size_t B = (size_t)max_images;
+#define GVS_TRY(expr)                                                                \
+    do {                                                                             \
+        cudaError_t _e = (expr);                                                     \
+        if (_e != cudaSuccess) {                                                     \
+            int rc = fail(GVS_ERR_CUDA, #expr, cudaGetErrorString(_e));              \
+            destroyExtractor(fe);                                                    \
+            return rc;                                                               \
+        }                                                                            \
+    } while (0)
+    GVS_TRY(cudaStreamCreateWithFlags(&fe->ownStream, cudaStreamNonBlocking));
+    fe->stream = fe->ownStream;
+    GVS_TRY(cudaEventCreateWithFlags(&fe->doneEvent, cudaEventDisableTiming));
+    for (auto& e : fe->ev) GVS_TRY(cudaEventCreate(&e));
+    GVS_TRY(devAlloc(&fe->slab, B * g.slabBytes + 256));
+    GVS_TRY(devAlloc(&fe->blurSlab, B * g.slabBytes + 256));
+    GVS_TRY(cudaMemset(fe->slab, 0, B * g.slabBytes + 256));
+    {
+        std::vector<ResizeTap> taps;
+        buildTaps(fe, taps, std::max(nTaps, 4));
+        GVS_TRY(devAlloc(&fe->taps, taps.size()));
+        GVS_TRY(cudaMemcpy(fe->taps, taps.data(), taps.size() * sizeof(ResizeTap), cudaMemcpyHostToDevice));
+    }
+    {
+        std::vector<FastItem> items;
+        for (int l = 0; l < g.nLevels; l++) {
+            fe->g.lv[l].fastItemBase = (int)items.size();
+            for (int iR = 0; iR < g.lv[l].nRows; iR++)
+                for (int iC = 0; iC < g.lv[l].nCols; iC += kFastCellsPerItem)
+                    items.push_back(FastItem{(short)l, (short)iR, (short)iC, (short)std::min(kFastCellsPerItem, g.lv[l].nCols - iC)});
+        }
+        fe->nFastItems = (int)items.size();
+        GVS_TRY(devAlloc(&fe->fastItems, items.size()));
+        if (!items.empty()) GVS_TRY(cudaMemcpy(fe->fastItems, items.data(), items.size() * sizeof(FastItem), cudaMemcpyHostToDevice));
+        std::vector<BlurItem> bi;
+        for (int l = 0; l < g.nLevels; l++)
+            for (int ty = 0; ty * kBlurTH < g.lv[l].h; ty++)
+                for (int tx = 0; tx * kBlurTW < g.lv[l].w; tx++) bi.push_back(BlurItem{(short)l, (short)tx, (short)ty, 0});
+        fe->nBlurItems = (int)bi.size();
+        GVS_TRY(devAlloc(&fe->blurItems, bi.size()));
+        GVS_TRY(cudaMemcpy(fe->blurItems, bi.data(), bi.size() * sizeof(BlurItem), cudaMemcpyHostToDevice));
+    }
+    GVS_TRY(devAlloc(&fe->recs, B * g.candPerImage));
+    GVS_TRY(devAlloc(&fe->nCand, B * kMaxLevels));
+    GVS_TRY(devAlloc(&fe->cellCnt, B * std::max(g.cellsPerImage, 1)));
+    GVS_TRY(devAlloc(&fe->kept, B * g.keptPerImage));
+    GVS_TRY(devAlloc(&fe->keptCnt, B * kMaxLevels));
+    GVS_TRY(cudaMemset(fe->keptCnt, 0, B * kMaxLevels * sizeof(int)));
+    GVS_TRY(devAlloc(&fe->imgOff, B + 1));
+    GVS_TRY(devAlloc(&fe->workCounter, 2));
+    GVS_TRY(devAlloc(&fe->status, 1));
+    fe->selScratchPerCta = selectScratchBytes(g);
+    fe->selCtas = std::min(selectMaxCtas(device), (int)B * g.nLevels);
+    GVS_TRY(devAlloc(&fe->selScratch, fe->selScratchPerCta * fe->selCtas));
+    fe->totalCap = (int)std::min<size_t>(B * g.keptPerImage, (size_t)1 << 30);
+    GVS_TRY(devAlloc(&fe->kps, (size_t)fe->totalCap));
+    GVS_TRY(devAlloc(&fe->desc, (size_t)fe->totalCap * 32));
+    GVS_TRY(cudaMallocHost(reinterpret_cast<void**>(&fe->hOff), sizeof(int) * (B + 1)));
+    GVS_TRY(cudaMallocHost(reinterpret_cast<void**>(&fe->hStatus), sizeof(int)));
+    *fe->hStatus = 0;
+    std::memset(fe->hOff, 0, sizeof(int) * (B + 1));
+#undef GVS_TRY
+    *out = fe;
+    return GVS_OK;
+}
+
+int gvs_extractor_destroy(gvs_extractor* fe) {
+    destroyExtractor(fe);
+    return GVS_OK;
+}
+
+int gvs_extractor_tables(const gvs_extractor* fe, float* scale, float* inv_scale, float* sigma, float* inv_sigma,
+                         int32_t* scaled_patch, int32_t* feature_per_level) {
+    if (!fe) return fail(GVS_ERR_INVALID, "null extractor");
+    for (int i = 0; i < fe->g.nLevels; i++) {
+        if (scale) scale[i] = fe->scale[i];
+        if (inv_scale) inv_scale[i] = fe->invScale[i];
+        if (sigma) sigma[i] = fe->sigma[i];
+        if (inv_sigma) inv_sigma[i] = fe->invSigma[i];
+        if (scaled_patch) scaled_patch[i] = fe->patch[i];
+        if (feature_per_level) feature_per_level[i] = fe->quota[i];
+    }
+    return GVS_OK;
+}
+
+int gvs_extractor_level_size(const gvs_extractor* fe, int level, int* width, int* height) {
+    if (!fe || level < 0 || level >= fe->g.nLevels) return fail(GVS_ERR_INVALID, "bad level");
+    if (width) *width = fe->g.lv[level].w;
+    if (height) *height = fe->g.lv[level].h;
+    return GVS_OK;
+}
+
+int gvs_extractor_set_stream(gvs_extractor* fe, void* cuda_stream) {
+    if (!fe) return fail(GVS_ERR_INVALID, "null extractor");
+    GVS_CUDA_OK(cudaSetDevice(fe->device));
+    GVS_CUDA_OK(cudaStreamSynchronize(fe->stream));
+    fe->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : fe->ownStream;
+    return GVS_OK;
+}
+
+int gvs_extractor_input(gvs_extractor* fe, uint8_t** dev, int* pitch, size_t* image_stride) {
+    if (!fe) return fail(GVS_ERR_INVALID, "null extractor");
+    if (dev) *dev = fe->slab + fe->g.lv[0].off;
+    if (pitch) *pitch = fe->g.lv[0].pitch;
+    if (image_stride) *image_stride = fe->g.slabBytes;
+    return GVS_OK;
+}
+
+int gvs_extract_batch_resident(gvs_extractor* fe, int n_images) {
+    int rc = checkBatch(fe, n_images);
+    if (rc) return rc;
+    GVS_CUDA_OK(cudaSetDevice(fe->device));
+    return runExtract(fe, n_images);
+}
+
+int gvs_extract_batch_host(gvs_extractor* fe, const uint8_t* images, size_t image_stride, int row_stride, int n_images) {
+    int rc = checkBatch(fe, n_images);
+    if (rc) return rc;
+    if (!images || row_stride < fe->width) return fail(GVS_ERR_INVALID, "bad image pointer / stride");
+    GVS_CUDA_OK(cudaSetDevice(fe->device));
+    const LevelGeom& l0 = fe->g.lv[0];
+    if (image_stride == (size_t)row_stride * fe->height) {
+        // one strided 3-D copy: rows of all images are `row_stride` apart in the source
+        cudaMemcpy3DParms p{};
+        p.srcPtr = make_cudaPitchedPtr(const_cast<uint8_t*>(images), row_stride, fe->width, fe->height);
+        p.dstPtr = make_cudaPitchedPtr(fe->slab + l0.off, l0.pitch, fe->width, fe->g.slabBytes / l0.pitch);
+        p.extent = make_cudaExtent(fe->width, fe->height, n_images);
+        p.kind = cudaMemcpyHostToDevice;
+        if (fe->g.slabBytes % l0.pitch == 0) {
+            GVS_CUDA_OK(cudaMemcpy3DAsync(&p, fe->stream));
+            return runExtract(fe, n_images);
+        }
+    }
+    for (int i = 0; i < n_images; i++)
+        GVS_CUDA_OK(cudaMemcpy2DAsync(fe->slab + (size_t)i * fe->g.slabBytes + l0.off, l0.pitch, images + (size_t)i * image_stride,
+                                      row_stride, fe->width, fe->height, cudaMemcpyHostToDevice, fe->stream));
+    return runExtract(fe, n_images);
+}
+
+int gvs_extractor_sync(gvs_extractor* fe) {
+    if (!fe) return fail(GVS_ERR_INVALID, "null extractor");
+    return syncExtract(fe);
+}
+
+int gvs_extract_offsets(gvs_extractor* fe, int32_t* offsets) {
+    if (!fe || !offsets) return fail(GVS_ERR_INVALID, "null argument");
+    if (fe->lastN <= 0) return fail(GVS_ERR_STATE, "no batch has been extracted");
+    int rc = syncExtract(fe);
+    if (rc) return rc;
+    std::memcpy(offsets, fe->hOff, sizeof(int) * (fe->lastN + 1));
+    return GVS_OK;
+}
+
+int gvs_extract_download(gvs_extractor* fe, int first, int count, gvs_keypoint* kps, uint8_t* desc, int cap) {
+    if (!fe) return fail(GVS_ERR_INVALID, "null extractor");
+    if (fe->lastN <= 0) return fail(GVS_ERR_STATE, "no batch has been extracted");
+    if (first < 0 || count < 0 || first + count > fe->lastN) return fail(GVS_ERR_INVALID, "image range out of the last batch");
+    int rc = syncExtract(fe);
+    if (rc) return rc;
+    const int o0 = fe->hOff[first], n = fe->hOff[first + count] - o0;
+    if (n > cap) return fail(GVS_ERR_CAPACITY, "caller buffer too small for the keypoints of this range");
+    if (n > 0) {
+        if (kps) GVS_CUDA_OK(cudaMemcpyAsync(kps, fe->kps + o0, (size_t)n * sizeof(gvs_keypoint), cudaMemcpyDeviceToHost, fe->stream));
+        if (desc) GVS_CUDA_OK(cudaMemcpyAsync(desc, fe->desc + (size_t)o0 * 32, (size_t)n * 32, cudaMemcpyDeviceToHost, fe->stream));
+        GVS_CUDA_OK(cudaStreamSynchronize(fe->stream));
+    }
+    return GVS_OK;
+}
+
+int gvs_extract(gvs_extractor* fe, const uint8_t* gray, int width, int height, int stride, gvs_keypoint* out, uint8_t* desc,
+                int cap, int* n) {
+    if (!fe || !gray || !n) return fail(GVS_ERR_INVALID, "null argument");
+    if (width != fe->width || height != fe->height) return fail(GVS_ERR_INVALID, "image size differs from the handle's");
+    int rc = gvs_extract_batch_host(fe, gray, (size_t)stride * height, stride, 1);
+    if (rc) return rc;
+    int off[2];
+    rc = gvs_extract_offsets(fe, off);
+    if (rc) return rc;
+    *n = off[1];
+    if (*n == 0) return GVS_OK;  // outputs untouched (src/FeatureExtractor.cpp:498-499)
+    return gvs_extract_download(fe, 0, 1, out, desc, cap);
+}
+
+int gvs_extractor_enable_timing(gvs_extractor* fe, int on) {
+    if (!fe) return fail(GVS_ERR_INVALID, "null extractor");
+    fe->timing = on != 0;
+    return GVS_OK;
+}
+int gvs_extractor_stage_times(gvs_extractor* fe, gvs_stage_times* t) {
+    if (!fe || !t) return fail(GVS_ERR_INVALID, "null argument");
+    *t = fe->times;
+    return GVS_OK;
+}
+int gvs_extractor_launch_count(gvs_extractor* fe, int64_t* launches) {
+    if (!fe || !launches) return fail(GVS_ERR_INVALID, "null argument");
+    *launches = fe->launchesTotal;
+    return GVS_OK;
+}
+
+// ---- parity taps
+int gvs_debug_level_image(gvs_extractor* fe, int image, int level, int blurred, uint8_t* out) {
+    if (!fe || !out || level < 0 || level >= fe->g.nLevels || image < 0 || image >= fe->maxImages)
+        return fail(GVS_ERR_INVALID, "bad argument");
+    GVS_CUDA_OK(cudaSetDevice(fe->device));
+    const LevelGeom& lv = fe->g.lv[level];
+    const uint8_t* src = (blurred ? fe->blurSlab : fe->slab) + (size_t)image * fe->g.slabBytes + lv.off;
+    GVS_CUDA_OK(cudaStreamSynchronize(fe->stream));
+    GVS_CUDA_OK(cudaMemcpy2D(out, lv.w, src, lv.pitch, lv.w, lv.h, cudaMemcpyDeviceToHost));
+    return GVS_OK;
+}
+
+static int unpackKeys(const std::vector<unsigned>& v, int n, int32_t* x, int32_t* y, int32_t* score) {
+    for (int i = 0; i < n; i++) {
+        if (x) x[i] = v[i] & 0xfff;
+        if (y) y[i] = (v[i] >> 12) & 0xfff;
+        if (score) score[i] = v[i] >> 24;
+    }
+    return GVS_OK;
+}
+
+int gvs_debug_level_candidates(gvs_extractor* fe, int image, int level, int32_t* x, int32_t* y, int32_t* score, int cap, int* n) {
+    if (!fe || !n || level < 0 || level >= fe->g.nLevels || image < 0 || image >= fe->lastN) return fail(GVS_ERR_INVALID, "bad argument");
+    GVS_CUDA_OK(cudaSetDevice(fe->device));
+    if (!fe->orderedDbg) {
+        // first use: allocate the tap and re-run the last batch so that it gets filled
+        GVS_CUDA_OK(cudaStreamSynchronize(fe->stream));
+        GVS_CUDA_OK(devAlloc(&fe->orderedDbg, (size_t)fe->maxImages * fe->g.candPerImage));
+        int rc = runExtract(fe, fe->lastN);
+        if (rc) return rc;
+    }
+    int rc = syncExtract(fe);
+    if (rc) return rc;
+    const LevelGeom& lv = fe->g.lv[level];
+    int cnt = 0;
+    GVS_CUDA_OK(cudaMemcpy(&cnt, fe->nCand + image * kMaxLevels + level, sizeof(int), cudaMemcpyDeviceToHost));
+    *n = cnt;
+    if (cnt > cap) return fail(GVS_ERR_CAPACITY, "caller buffer too small");
+    std::vector<unsigned> v(std::max(cnt, 1));
+    GVS_CUDA_OK(cudaMemcpy(v.data(), fe->orderedDbg + (size_t)image * fe->g.candPerImage + lv.candOff, sizeof(unsigned) * cnt,
+                           cudaMemcpyDeviceToHost));
+    return unpackKeys(v, cnt, x, y, score);
+}
+
+int gvs_debug_level_kept(gvs_extractor* fe, int image, int level, int32_t* x, int32_t* y, int32_t* score, int cap, int* n) {
+    if (!fe || !n || level < 0 || level >= fe->g.nLevels || image < 0 || image >= fe->lastN) return fail(GVS_ERR_INVALID, "bad argument");
+    GVS_CUDA_OK(cudaSetDevice(fe->device));
+    int rc = syncExtract(fe);
+    if (rc) return rc;
+    const LevelGeom& lv = fe->g.lv[level];
+    int cnt = 0;
+    GVS_CUDA_OK(cudaMemcpy(&cnt, fe->keptCnt + image * kMaxLevels + level, sizeof(int), cudaMemcpyDeviceToHost));
+    *n = cnt;
+    if (cnt > cap) return fail(GVS_ERR_CAPACITY, "caller buffer too small");
+    std::vector<unsigned> v(std::max(cnt, 1));
+    GVS_CUDA_OK(cudaMemcpy(v.data(), fe->kept + (size_t)image * fe->g.keptPerImage + lv.keptOff, sizeof(unsigned) * cnt,
+                           cudaMemcpyDeviceToHost));
+    return unpackKeys(v, cnt, x, y, score);
+}
+
+// ------------------------------------------------------------------ matcher
+int gvs_matcher_create(gvs_matcher** out, gvs_extractor* feL, gvs_extractor* feR, double fx, float baseline, int image_height) {
+    if (!out || !feL) return fail(GVS_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (!feR) feR = feL;  // mono: System::InitializeMonocular passes the left extractor twice (src/System.cpp:32)
+    if (feL->device != feR->device) return fail(GVS_ERR_INVALID, "extractors live on different devices");
+    if (feL->g.nLevels != feR->g.nLevels || feL->width != feR->width || feL->height != feR->height)
+        return fail(GVS_ERR_INVALID, "left and right extractors differ in geometry");
+    if (image_height < 1) return fail(GVS_ERR_INVALID, "bad image_height");
+    GVS_CUDA_OK(cudaSetDevice(feL->device));
+    gvs_matcher* m = new gvs_matcher();
+    m->L = feL; m->R = feR; m->fx = fx; m->baseline = baseline; m->imageHeight = image_height;
+    const size_t B = (size_t)std::min(feL->maxImages, feR->maxImages);
+    bool ok = devAlloc(&m->rightIdxs, (size_t)feL->totalCap) == cudaSuccess && devAlloc(&m->depth, (size_t)feL->totalCap) == cudaSuccess &&
+              devAlloc(&m->close, (size_t)feL->totalCap) == cudaSuccess && devAlloc(&m->sadBest, (size_t)feL->totalCap) == cudaSuccess &&
+              devAlloc(&m->leftIdxs, (size_t)feR->totalCap) == cudaSuccess &&
+              devAlloc(&m->cellStartL, B * (m->maxCells + 1)) == cudaSuccess && devAlloc(&m->cellStartR, B * (m->maxCells + 1)) == cudaSuccess &&
+              devAlloc(&m->itemsL, (size_t)feL->totalCap) == cudaSuccess && devAlloc(&m->itemsR, (size_t)feR->totalCap) == cudaSuccess &&
+              devAlloc(&m->pjStatus, 2) == cudaSuccess && cudaEventCreateWithFlags(&m->evR, cudaEventDisableTiming) == cudaSuccess;
+    for (auto& e : m->ev) ok = ok && cudaEventCreate(&e) == cudaSuccess;
+    if (!ok) {
+        int rc = fail(GVS_ERR_CUDA, "matcher allocation", cudaGetErrorString(cudaGetLastError()));
+        gvs_matcher_destroy(m);
+        return rc;
+    }
+    *out = m;
+    return GVS_OK;
+}
+
+int gvs_matcher_destroy(gvs_matcher* m) {
+    if (!m) return GVS_OK;
+    cudaSetDevice(m->L->device);
+    cudaStreamSynchronize(m->L->stream);
+    cudaFree(m->rightIdxs); cudaFree(m->leftIdxs); cudaFree(m->sadBest); cudaFree(m->depth); cudaFree(m->close);
+    cudaFree(m->cellStartL); cudaFree(m->cellStartR); cudaFree(m->itemsL); cudaFree(m->itemsR); cudaFree(m->pj);
+    cudaFree(m->pool); cudaFree(m->pjStatus);
+    if (m->evR) cudaEventDestroy(m->evR);
+    for (auto& e : m->ev) if (e) cudaEventDestroy(e);
+    delete m;
+    return GVS_OK;
+}
+
+static int joinRight(gvs_matcher* m) {  // make L's stream wait for R's last batch
+    if (m->R != m->L && m->R->stream != m->L->stream) {
+        GVS_CUDA_OK(cudaEventRecord(m->evR, m->R->stream));
+        GVS_CUDA_OK(cudaStreamWaitEvent(m->L->stream, m->evR, 0));
+    }
+    return GVS_OK;
+}
+
+int gvs_stereo_match_batch(gvs_matcher* m, int n_frames) {
+    if (!m) return fail(GVS_ERR_INVALID, "null matcher");
+    if (n_frames < 1 || n_frames > m->L->lastN || n_frames > m->R->lastN) return fail(GVS_ERR_STATE, "extract both sides first");
+    GVS_CUDA_OK(cudaSetDevice(m->L->device));
+    int rc = joinRight(m);
+    if (rc) return rc;
+    cudaStream_t s = m->L->stream;
+    StereoArgs a{};
+    a.slabL = m->L->slab; a.slabR = m->R->slab; a.kpL = m->L->kps; a.kpR = m->R->kps; a.descL = m->L->desc; a.descR = m->R->desc;
+    a.offL = m->L->imgOff; a.offR = m->R->imgOff; a.keptCntL = m->L->keptCnt; a.keptCntR = m->R->keptCnt;
+    a.rightIdxs = m->rightIdxs; a.leftIdxs = m->leftIdxs; a.depth = m->depth; a.close = m->close; a.sadBest = m->sadBest;
+    a.fx = m->fx; a.baseline = m->baseline; a.imageHeight = m->imageHeight; a.closeNumber = 40; a.thDist = 75;
+    m->launches = 0;
+    if (m->L->timing) cudaEventRecord(m->ev[0], s);
+    GVS_CUDA_OK(cudaMemsetAsync(m->leftIdxs, 0xff, sizeof(int) * (size_t)std::min<size_t>((size_t)n_frames * m->R->g.keptPerImage, m->R->totalCap), s));
+    launchStereo(m->L->g, a, n_frames, m->L->g.keptPerImage, s, &m->launches);
+    if (m->L->timing) cudaEventRecord(m->ev[1], s);
+    GVS_CUDA_OK(cudaGetLastError());
+    m->launchesTotal += m->launches;
+    m->stereoValid = true;
+    m->lastFrames = n_frames;
+    return GVS_OK;
+}
+
+int gvs_matcher_sync(gvs_matcher* m) {
+    if (!m) return fail(GVS_ERR_INVALID, "null matcher");
+    int rc = syncExtract(m->L);
+    if (rc) return rc;
+    if (m->R != m->L) rc = syncExtract(m->R);
+    if (rc) return rc;
+    if (m->L->timing && m->stereoValid) {
+        cudaEventElapsedTime(&m->stereoMs, m->ev[0], m->ev[1]);
+        if (m->gridsValid) cudaEventElapsedTime(&m->gridMs, m->ev[2], m->ev[3]);
+        m->L->times.stereo_ms = m->stereoMs;
+        m->L->times.grid_ms = m->gridMs;
+    }
+    return GVS_OK;
+}
+
+int gvs_stereo_download(gvs_matcher* m, int first, int count, int32_t* right_idxs, int32_t* left_idxs, float* depth, uint8_t* close) {
+    if (!m) return fail(GVS_ERR_INVALID, "null matcher");
+    if (!m->stereoValid) return fail(GVS_ERR_STATE, "no stereo batch has been matched");
+    if (first < 0 || count < 0 || first + count > m->lastFrames) return fail(GVS_ERR_INVALID, "frame range out of the last batch");
+    int rc = gvs_matcher_sync(m);
+    if (rc) return rc;
+    cudaStream_t s = m->L->stream;
+    const int l0 = m->L->hOff[first], nl = m->L->hOff[first + count] - l0;
+    const int r0 = m->R->hOff[first], nr = m->R->hOff[first + count] - r0;
+    if (nl > 0) {
+        if (right_idxs) GVS_CUDA_OK(cudaMemcpyAsync(right_idxs, m->rightIdxs + l0, sizeof(int) * nl, cudaMemcpyDeviceToHost, s));
+        if (depth) GVS_CUDA_OK(cudaMemcpyAsync(depth, m->depth + l0, sizeof(float) * nl, cudaMemcpyDeviceToHost, s));
+        if (close) GVS_CUDA_OK(cudaMemcpyAsync(close, m->close + l0, (size_t)nl, cudaMemcpyDeviceToHost, s));
+    }
+    if (nr > 0 && left_idxs) GVS_CUDA_OK(cudaMemcpyAsync(left_idxs, m->leftIdxs + r0, sizeof(int) * nr, cudaMemcpyDeviceToHost, s));
+    GVS_CUDA_OK(cudaStreamSynchronize(s));
+    return GVS_OK;
+}
+
+int gvs_assign_grids_batch(gvs_matcher* m, int n_frames, int width, int height) {
+    if (!m) return fail(GVS_ERR_INVALID, "null matcher");
+    if (n_frames < 1 || n_frames > m->L->lastN) return fail(GVS_ERR_STATE, "extract first");
+    if (width < 1 || height < 1) return fail(GVS_ERR_INVALID, "bad size");
+    GVS_CUDA_OK(cudaSetDevice(m->L->device));
+    // src/FeatureTracker.cpp:30-34 (float32)
+    const float imageRatio = (float)width / (float)height;
+    m->xGrids = GVS_GRID_X;
+    m->yGrids = (int)std::ceil((float)m->xGrids / imageRatio);
+    if (m->xGrids * m->yGrids > m->maxCells) return fail(GVS_ERR_INVALID, "image taller than wide by more than 64x is not supported");
+    m->xMult = (float)m->xGrids / (float)width;
+    m->yMult = (float)m->yGrids / (float)height;
+    int rc = joinRight(m);
+    if (rc) return rc;
+    cudaStream_t s = m->L->stream;
+    int launches = 0;
+    if (m->L->timing) cudaEventRecord(m->ev[2], s);
+    GridArgs a{};
+    a.xGrids = m->xGrids; a.yGrids = m->yGrids; a.xMult = m->xMult; a.yMult = m->yMult; a.maxCells = m->maxCells;
+    a.kps = m->L->kps; a.off = m->L->imgOff; a.cellStart = m->cellStartL; a.items = m->itemsL;
+    launchGrid(a, n_frames, s, &launches);
+    if (m->R != m->L && n_frames <= m->R->lastN) {
+        a.kps = m->R->kps; a.off = m->R->imgOff; a.cellStart = m->cellStartR; a.items = m->itemsR;
+        launchGrid(a, n_frames, s, &launches);
+    }
+    if (m->L->timing) cudaEventRecord(m->ev[3], s);
+    GVS_CUDA_OK(cudaGetLastError());
+    m->launchesTotal += launches;
+    m->launches += launches;
+    m->gridsValid = true;
+    if (m->lastFrames < n_frames) m->lastFrames = n_frames;
+    return GVS_OK;
+}
+
+int gvs_grid_download(gvs_matcher* m, int frame, int side, int32_t* cell_start, int32_t* items, int* y_grids, float* x_mult, float* y_mult) {
+    if (!m) return fail(GVS_ERR_INVALID, "null matcher");
+    if (!m->gridsValid) return fail(GVS_ERR_STATE, "grids have not been assigned");
+    gvs_extractor* fe = side ? m->R : m->L;
+    if (frame < 0 || frame >= fe->lastN) return fail(GVS_ERR_INVALID, "bad frame");
+    int rc = gvs_matcher_sync(m);
+    if (rc) return rc;
+    const int nc = m->xGrids * m->yGrids;
+    const int o0 = fe->hOff[frame], n = fe->hOff[frame + 1] - o0;
+    if (cell_start) GVS_CUDA_OK(cudaMemcpy(cell_start, (side ? m->cellStartR : m->cellStartL) + (size_t)frame * (m->maxCells + 1), sizeof(int) * (nc + 1), cudaMemcpyDeviceToHost));
+    if (items && n > 0) GVS_CUDA_OK(cudaMemcpy(items, (side ? m->itemsR : m->itemsL) + o0, sizeof(int) * n, cudaMemcpyDeviceToHost));
+    if (y_grids) *y_grids = m->yGrids;
+    if (x_mult) *x_mult = m->xMult;
+    if (y_mult) *y_mult = m->yMult;
+    return GVS_OK;
+}
+
+int gvs_track_stereo_batch_resident(gvs_matcher* m, int n_frames, int width, int height) {
+    if (!m) return fail(GVS_ERR_INVALID, "null matcher");
+    if (m->R == m->L) return fail(GVS_ERR_STATE, "stereo tracking needs two extractors");
+    int rc = gvs_extract_batch_resident(m->L, n_frames);
+    if (rc) return rc;
+    rc = gvs_extract_batch_resident(m->R, n_frames);
+    if (rc) return rc;
+    rc = gvs_stereo_match_batch(m, n_frames);
+    if (rc) return rc;
+    return gvs_assign_grids_batch(m, n_frames, width, height);
+}
+
+int gvs_track_stereo_batch_host(gvs_matcher* m, const uint8_t* left, const uint8_t* right, size_t image_stride, int row_stride,
+                                int n_frames, int width, int height) {
+    if (!m) return fail(GVS_ERR_INVALID, "null matcher");
+    if (m->R == m->L) return fail(GVS_ERR_STATE, "stereo tracking needs two extractors");
+    int rc = gvs_extract_batch_host(m->L, left, image_stride, row_stride, n_frames);
+    if (rc) return rc;
+    rc = gvs_extract_batch_host(m->R, right, image_stride, row_stride, n_frames);
+    if (rc) return rc;
+    rc = gvs_stereo_match_batch(m, n_frames);
+    if (rc) return rc;
+    return gvs_assign_grids_batch(m, n_frames, width, height);
+}
+
+int gvs_matcher_launch_count(gvs_matcher* m, int64_t* launches) {
+    if (!m || !launches) return fail(GVS_ERR_INVALID, "null argument");
+    *launches = m->launchesTotal;
+    return GVS_OK;
+}
+
+int gvs_match_projection(gvs_matcher* m, int frame, int mode, const gvs_mappoints* mps, float rad, int32_t* matched_l,
+                         int32_t* matched_r, int32_t* matches, int* n_matches) {
+    if (!m || !mps || !matched_l || !matches || !n_matches) return fail(GVS_ERR_INVALID, "null argument");
+    if (mode < 0 || mode > 2) return fail(GVS_ERR_INVALID, "bad mode");
+    if (!m->gridsValid) return fail(GVS_ERR_STATE, "call gvs_assign_grids_batch first");
+    if (mode == GVS_MATCH_STEREO_PRED && (!m->stereoValid || !matched_r || !mps->pred_r || !mps->scale_level_r))
+        return fail(GVS_ERR_STATE, "stereo-pred matching needs a stereo batch, matched_r, pred_r and scale_level_r");
+    if (frame < 0 || frame >= m->lastFrames) return fail(GVS_ERR_INVALID, "bad frame");
+    if (!mps->desc || !mps->pred_l || !mps->scale_level_l) return fail(GVS_ERR_INVALID, "map point arrays missing");
+    int rc = gvs_matcher_sync(m);
+    if (rc) return rc;
+    GVS_CUDA_OK(cudaSetDevice(m->L->device));
+    cudaStream_t s = m->L->stream;
+    const int M = mps->count;
+    *n_matches = 0;
+    if (M <= 0) return GVS_OK;
+    const int oL = m->L->hOff[frame], NL = m->L->hOff[frame + 1] - oL;
+    const bool two = mode == GVS_MATCH_STEREO_PRED;
+    const int oR = two ? m->R->hOff[frame] : 0, NR = two ? m->R->hOff[frame + 1] - oR : 0;
+    for (int i = 0; i < M; i++) {
+        const int l = mps->scale_level_l[i];
+        if (l < 0 || l >= m->L->g.nLevels || (two && (mps->scale_level_r[i] < 0 || mps->scale_level_r[i] >= m->L->g.nLevels)))
+            return fail(GVS_ERR_INVALID, "map point scale level out of range");
+    }
+    // scratch layout
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    size_t o = 0;
+    const size_t oDesc = o; o += al((size_t)M * 32);
+    const size_t oPL = o; o += al((size_t)M * 8);
+    const size_t oPR = o; o += al((size_t)M * 8);
+    const size_t oLL = o; o += al((size_t)M * 4);
+    const size_t oLR = o; o += al((size_t)M * 4);
+    const size_t oIF = o; o += al((size_t)M);
+    const size_t oIR = o; o += al((size_t)M);
+    const size_t oML = o; o += al((size_t)std::max(NL, 1) * 4);
+    const size_t oMR = o; o += al((size_t)std::max(NR, 1) * 4);
+    const size_t oMt = o; o += al((size_t)M * 8);
+    const size_t oRec = o; o += al((size_t)M * 2 * 20);
+    const size_t oCnt = o; o += al(16);
+    if (o > m->pjBytes) {
+        cudaFree(m->pj); m->pj = nullptr; m->pjBytes = 0;
+        GVS_CUDA_OK(devAlloc(&m->pj, o));
+        m->pjBytes = o;
+    }
+    // candidate pools: every map point can list every key of its side at most once
+    const long long need = std::min<long long>((long long)M * std::max(NL, NR), (long long)1 << 28);
+    if (need > m->poolCap) {
+        cudaFree(m->pool); m->pool = nullptr; m->poolCap = 0;
+        GVS_CUDA_OK(devAlloc(&m->pool, (size_t)need * 2));
+        m->poolCap = (int)need;
+    }
+    uint8_t* b = m->pj;
+    auto up = [&](size_t off, const void* src, size_t bytes) -> cudaError_t {
+        return src ? cudaMemcpyAsync(b + off, src, bytes, cudaMemcpyHostToDevice, s) : cudaSuccess;
+    };
+    GVS_CUDA_OK(up(oDesc, mps->desc, (size_t)M * 32));
+    GVS_CUDA_OK(up(oPL, mps->pred_l, (size_t)M * 8));
+    GVS_CUDA_OK(up(oLL, mps->scale_level_l, (size_t)M * 4));
+    GVS_CUDA_OK(up(oIF, mps->in_frame, (size_t)M));
+    if (two) {
+        GVS_CUDA_OK(up(oPR, mps->pred_r, (size_t)M * 8));
+        GVS_CUDA_OK(up(oLR, mps->scale_level_r, (size_t)M * 4));
+        GVS_CUDA_OK(up(oIR, mps->in_frame_r, (size_t)M));
+        GVS_CUDA_OK(up(oMR, matched_r, (size_t)NR * 4));
+    }
+    GVS_CUDA_OK(up(oML, matched_l, (size_t)NL * 4));
+    GVS_CUDA_OK(up(oMt, matches, (size_t)M * 8));
+    GVS_CUDA_OK(cudaMemsetAsync(m->pjStatus, 0, 2 * sizeof(int), s));
+    ProjArgs a{};
+    a.mode = mode; a.M = M;
+    a.mpDesc = b + oDesc; a.predL = reinterpret_cast<float*>(b + oPL); a.predR = reinterpret_cast<float*>(b + oPR);
+    a.lvlL = reinterpret_cast<int*>(b + oLL); a.lvlR = reinterpret_cast<int*>(b + oLR);
+    a.inFrame = mps->in_frame ? b + oIF : nullptr; a.inFrameR = mps->in_frame_r ? b + oIR : nullptr;
+    a.kpL = m->L->kps + oL; a.descL = m->L->desc + (size_t)oL * 32; a.NL = NL;
+    a.kpR = two ? m->R->kps + oR : nullptr; a.descR = two ? m->R->desc + (size_t)oR * 32 : nullptr; a.NR = NR;
+    a.cellStartL = m->cellStartL + (size_t)frame * (m->maxCells + 1); a.itemsL = m->itemsL + oL;
+    a.cellStartR = two ? m->cellStartR + (size_t)frame * (m->maxCells + 1) : nullptr; a.itemsR = two ? m->itemsR + oR : nullptr;
+    a.leftIdxs = two ? m->leftIdxs + oR : nullptr; a.rightIdxs = two ? m->rightIdxs + oL : nullptr;
+    a.xGrids = m->xGrids; a.yGrids = m->yGrids; a.xMult = m->xMult; a.yMult = m->yMult; a.rad = rad;
+    for (int i = 0; i < kMaxLevels; i++) a.scalePyramid[i] = i < m->L->g.nLevels ? m->L->scale[i] : 1.f;
+    a.recs = b + oRec; a.poolTop = reinterpret_cast<int*>(b + oCnt);
+    a.candL = m->pool; a.candR = m->pool + m->poolCap; a.candCap = m->poolCap;
+    a.matchedL = reinterpret_cast<int*>(b + oML); a.matchedR = reinterpret_cast<int*>(b + oMR);
+    a.matches = reinterpret_cast<int*>(b + oMt); a.nMatches = m->pjStatus + 1; a.status = m->pjStatus;
+    int launches = 0;
+    launchProject(a, s, &launches);
+    m->launchesTotal += launches;
+    int st[2] = {0, 0};
+    GVS_CUDA_OK(cudaMemcpyAsync(matched_l, b + oML, (size_t)NL * 4, cudaMemcpyDeviceToHost, s));
+    if (two) GVS_CUDA_OK(cudaMemcpyAsync(matched_r, b + oMR, (size_t)NR * 4, cudaMemcpyDeviceToHost, s));
+    GVS_CUDA_OK(cudaMemcpyAsync(matches, b + oMt, (size_t)M * 8, cudaMemcpyDeviceToHost, s));
+    GVS_CUDA_OK(cudaMemcpyAsync(st, m->pjStatus, sizeof(st), cudaMemcpyDeviceToHost, s));
+    GVS_CUDA_OK(cudaStreamSynchronize(s));
+    GVS_CUDA_OK(cudaGetLastError());
+    if (st[0] & kStatProjOverflow) return fail(GVS_ERR_CAPACITY, "projection candidate pool overflow");
+    *n_matches = st[1];
+    return GVS_OK;
+}
+
+int gvs_descriptor_distance(gvs_matcher* m, const uint8_t* a, const uint8_t* b, int n, int32_t* dist) {
+    if (!m || !a || !b || !dist || n < 0) return fail(GVS_ERR_INVALID, "bad argument");
+    if (n == 0) return GVS_OK;
+    GVS_CUDA_OK(cudaSetDevice(m->L->device));
+    cudaStream_t s = m->L->stream;
+    uint8_t *da = nullptr, *db = nullptr;
+    int* dd = nullptr;
+    cudaError_t e = devAlloc(&da, (size_t)n * 32);
+    if (e == cudaSuccess) e = devAlloc(&db, (size_t)n * 32);
+    if (e == cudaSuccess) e = devAlloc(&dd, (size_t)n);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(da, a, (size_t)n * 32, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(db, b, (size_t)n * 32, cudaMemcpyHostToDevice, s);
+    int launches = 0;
+    if (e == cudaSuccess) { launchHamming(da, db, n, dd, s, &launches); e = cudaMemcpyAsync(dist, dd, sizeof(int) * n, cudaMemcpyDeviceToHost, s); }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(da); cudaFree(db); cudaFree(dd);
+    m->launchesTotal += launches;
+    if (e != cudaSuccess) return fail(GVS_ERR_CUDA, "gvs_descriptor_distance", cudaGetErrorString(e));
+    return GVS_OK;
+}
+
+}  // extern "C"

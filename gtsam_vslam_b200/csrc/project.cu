@@ -1,0 +1,285 @@
+// K10 proj_match: windowed, projection-guided descriptor matching of map points against one frame.
+// Replaces FeatureMatcher::getMatchIdxs (reference src/FeatureMatcher.cpp:13-64), matchByProjectionRPred
+// (:254-389), matchByProjectionMono (:391-456) and matchByRadius (:458-526).
+//
+// The reference is greedy over map points in index order: a key point matched by map point j is skipped by
+// every later map point.  Two phases keep that order while doing the heavy work in parallel:
+//
+// phase 1 (proj_candidates, one warp per (map point, side)): enumerate the grid window in the reference's
+//   order (grid row, grid column, insertion order = one contiguous CSR range per grid row), apply the octave
+//   and |dx|,|dy| < radius tests (and the pixel-parallax test of matchByRadius), compute the 256-bit Hamming
+//   distances with __popc, and store the ordered list {idx, dist, level}.  It also reduces the list to the
+//   only three candidates the best/second-best rule can depend on (App. A.9): the first minimum p, the first
+//   minimum of the prefix [0,p) and the first minimum of the suffix (p,end).
+// phase 2 (proj_resolve, one warp per call): walks the map points in order, 32 at a time.  If none of a map
+//   point's three deciding candidates is already matched, the phase-1 result stands (skipping any other
+//   candidate cannot change best, second or their levels); otherwise the warp rescans the stored list with the
+//   skip test.  matchedIdxsL/R live in shared memory for the duration of the walk.
+#include "common.cuh"
+
+namespace gvs {
+
+// list entry: idx (16 bits) | dist (9 bits) << 16 | level (4 bits) << 25 ; 0xffffffff = none
+__device__ __forceinline__ unsigned packCand(int idx, int dist, int lev) { return (unsigned)idx | ((unsigned)dist << 16) | ((unsigned)lev << 25); }
+__device__ __forceinline__ int candIdx(unsigned e) { return (int)(e & 0xffff); }
+__device__ __forceinline__ int candDist(unsigned e) { return (int)((e >> 16) & 0x1ff); }
+__device__ __forceinline__ int candLev(unsigned e) { return (int)((e >> 25) & 0xf); }
+constexpr unsigned kNone = 0xffffffffu;
+
+struct ProjRec {  // per (map point, side)
+    int start, len;
+    unsigned eBest, ePre, eSuf;
+};
+
+__device__ __forceinline__ unsigned warpMin(unsigned v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Reduce an ordered candidate list (optionally skipping matched keys) to (eBest, ePre, eSuf).  Warp-wide.
+__device__ void reduceList(const unsigned* list, int len, const int* matched, int lane, unsigned& eBest, unsigned& ePre,
+                           unsigned& eSuf) {
+    // key = dist << 20 | position  (len < 2^20)
+    unsigned kb = kNone;
+    for (int p = lane; p < len; p += 32) {
+        const unsigned e = list[p];
+        if (matched && matched[candIdx(e)] >= 0) continue;
+        kb = min(kb, ((unsigned)candDist(e) << 20) | (unsigned)p);
+    }
+    kb = warpMin(kb);
+    if (kb == kNone) { eBest = ePre = eSuf = kNone; return; }
+    const int pBest = (int)(kb & 0xfffff);
+    unsigned kp = kNone, ks = kNone;
+    for (int p = lane; p < len; p += 32) {
+        if (p == pBest) continue;
+        const unsigned e = list[p];
+        if (matched && matched[candIdx(e)] >= 0) continue;
+        const unsigned k = ((unsigned)candDist(e) << 20) | (unsigned)p;
+        if (p < pBest) kp = min(kp, k); else ks = min(ks, k);
+    }
+    kp = warpMin(kp);
+    ks = warpMin(ks);
+    eBest = list[pBest];
+    ePre = kp == kNone ? kNone : list[kp & 0xfffff];
+    eSuf = ks == kNone ? kNone : list[ks & 0xfffff];
+}
+
+__global__ void __launch_bounds__(256)
+proj_candidates_kernel(const ProjArgs a, ProjRec* __restrict__ recs) {
+    const int lane = threadIdx.x & 31;
+    const int nSides = a.mode == GVS_MATCH_STEREO_PRED ? 2 : 1;
+    const int warpsPerGrid = gridDim.x * (blockDim.x >> 5);
+    unsigned lt;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt));
+    for (int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < a.M * nSides; w += warpsPerGrid) {
+        const int mp = w / nSides, side = w - mp * nSides;
+        ProjRec rec;
+        rec.start = 0; rec.len = 0; rec.eBest = rec.ePre = rec.eSuf = kNone;
+        const float* pred = side ? a.predR : a.predL;
+        const int lvl = side ? a.lvlR[mp] : a.lvlL[mp];
+        const bool inFrame = a.mode == GVS_MATCH_RADIUS ? true : (side ? (a.inFrameR ? a.inFrameR[mp] != 0 : true)
+                                                                       : (a.inFrame ? a.inFrame[mp] != 0 : true));
+        const gvs_keypoint* kps = side ? a.kpR : a.kpL;
+        const uint8_t* descs = side ? a.descR : a.descL;
+        const int* cellStart = side ? a.cellStartR : a.cellStartL;
+        const int* items = side ? a.itemsR : a.itemsL;
+        const float trackX = pred[2 * mp], trackY = pred[2 * mp + 1];
+        const float radius = __fmul_rn(a.scalePyramid[min(max(lvl, 0), kMaxLevels - 1)], a.rad);
+        // getMatchIdxs window (src/FeatureMatcher.cpp:18-30)
+        const int minX = max(0, (int)floorf(__fmul_rn(__fsub_rn(trackX, radius), a.xMult)));
+        const int maxX = min(a.xGrids - 1, (int)ceilf(__fmul_rn(__fadd_rn(trackX, radius), a.xMult)));
+        const int minY = max(0, (int)floorf(__fmul_rn(__fsub_rn(trackY, radius), a.yMult)));
+        const int maxY = min(a.yGrids - 1, (int)ceilf(__fmul_rn(__fadd_rn(trackY, radius), a.yMult)));
+        const bool window = inFrame && !(minX >= a.xGrids || minY >= a.yGrids || maxX < 0 || maxY < 0) && minX <= maxX;
+        if (window) {
+            const uint4* dq = reinterpret_cast<const uint4*>(a.mpDesc + (size_t)mp * 32);
+            const uint4 q0 = __ldg(dq), q1 = __ldg(dq + 1);
+            auto passes = [&](int idx) {
+                const gvs_keypoint k = kps[idx];
+                if (k.octave > lvl + 1 || k.octave < lvl - 1) return -1;
+                const float dx = __fsub_rn(k.x, trackX), dy = __fsub_rn(k.y, trackY);
+                if (!(fabsf(dx) < radius && fabsf(dy) < radius)) return -1;
+                if (a.mode == GVS_MATCH_RADIUS) {  // Converter::checkPixelParallax (include/Conversions.h:140-144)
+                    const double ex = (double)trackX - (double)k.x, ey = (double)trackY - (double)k.y;
+                    if (!(sqrt(ex * ex + ey * ey) > 10.0)) return -1;
+                }
+                return k.octave;
+            };
+            // pass 1: count
+            int cnt = 0;
+            for (int row = minY; row <= maxY; row++) {
+                const int p0 = cellStart[row * a.xGrids + minX], p1 = cellStart[row * a.xGrids + maxX + 1];
+                for (int p = p0 + lane; p < p1; p += 32) cnt += passes(items[p]) >= 0;
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+            int start = 0;
+            if (lane == 0 && cnt > 0) start = atomicAdd(a.poolTop + side, cnt);
+            start = __shfl_sync(0xffffffffu, start, 0);
+            if (cnt > 0 && start + cnt > a.candCap) {
+                if (lane == 0) atomicOr(a.status, kStatProjOverflow);
+                cnt = 0;
+            }
+            // pass 2: distances, ordered write
+            if (cnt > 0) {
+                unsigned* list = (side ? a.candR : a.candL) + start;
+                int run = 0;
+                for (int row = minY; row <= maxY; row++) {
+                    const int p0 = cellStart[row * a.xGrids + minX], p1 = cellStart[row * a.xGrids + maxX + 1];
+                    for (int base = p0; base < p1; base += 32) {
+                        const int p = base + lane;
+                        int idx = -1, lev = -1;
+                        if (p < p1) { idx = items[p]; lev = passes(idx); }
+                        const unsigned m = __ballot_sync(0xffffffffu, lev >= 0);
+                        if (lev >= 0) {
+                            const uint4* dk = reinterpret_cast<const uint4*>(descs + (size_t)idx * 32);
+                            const uint4 k0 = __ldg(dk), k1 = __ldg(dk + 1);
+                            const int dist = __popc(q0.x ^ k0.x) + __popc(q0.y ^ k0.y) + __popc(q0.z ^ k0.z) + __popc(q0.w ^ k0.w) +
+                                             __popc(q1.x ^ k1.x) + __popc(q1.y ^ k1.y) + __popc(q1.z ^ k1.z) + __popc(q1.w ^ k1.w);
+                            list[run + __popc(m & lt)] = packCand(idx, dist, lev);
+                        }
+                        run += __popc(m);
+                    }
+                }
+                __syncwarp();
+                rec.start = start; rec.len = cnt;
+                reduceList(list, cnt, nullptr, lane, rec.eBest, rec.ePre, rec.eSuf);
+            }
+        }
+        if (lane == 0) recs[w] = rec;
+    }
+}
+
+struct Decision { int bestDist, bestIdx, bestLev, bestLev2, secDist; };
+__device__ __forceinline__ Decision decide(unsigned eBest, unsigned ePre, unsigned eSuf) {
+    Decision d{256, -1, -1, -1, 256};
+    if (eBest == kNone) return d;
+    d.bestDist = candDist(eBest); d.bestIdx = candIdx(eBest); d.bestLev = candLev(eBest);
+    if (ePre != kNone) { d.secDist = candDist(ePre); d.bestLev2 = candLev(ePre); }
+    if (eSuf != kNone && candDist(eSuf) < d.secDist) { d.secDist = candDist(eSuf); d.bestLev2 = candLev(eSuf); }
+    return d;
+}
+
+__global__ void __launch_bounds__(32)
+proj_resolve_kernel(const ProjArgs a, const ProjRec* __restrict__ recs) {
+    extern __shared__ int sMatched[];  // NL + NR
+    int* mL = sMatched;
+    int* mR = sMatched + a.NL;
+    const int lane = threadIdx.x;
+    for (int i = lane; i < a.NL; i += 32) mL[i] = a.matchedL[i];
+    if (a.mode == GVS_MATCH_STEREO_PRED) for (int i = lane; i < a.NR; i += 32) mR[i] = a.matchedR[i];
+    __syncwarp();
+    const int nSides = a.mode == GVS_MATCH_STEREO_PRED ? 2 : 1;
+    int nMatches = 0;
+    for (int base = 0; base < a.M; base += 32) {
+        const int mp = base + lane;
+        ProjRec rl, rr;
+        rl.start = rl.len = 0; rl.eBest = rl.ePre = rl.eSuf = kNone;
+        rr = rl;
+        bool skipMP = true;
+        if (mp < a.M) {
+            rl = recs[mp * nSides];
+            if (nSides == 2) rr = recs[mp * nSides + 1];
+            skipMP = a.mode != GVS_MATCH_RADIUS && (a.matches[2 * mp] >= 0 || a.matches[2 * mp + 1] >= 0);
+        }
+        const int chunk = min(32, a.M - base);
+        for (int k = 0; k < chunk; k++) {
+            // lane k's turn; every lane follows the same control flow with lane k's data
+            const bool skipK = __shfl_sync(0xffffffffu, (int)skipMP, k) != 0;
+            if (skipK) continue;
+            unsigned eb = __shfl_sync(0xffffffffu, rl.eBest, k), ep = __shfl_sync(0xffffffffu, rl.ePre, k),
+                     es = __shfl_sync(0xffffffffu, rl.eSuf, k);
+            const int lstart = __shfl_sync(0xffffffffu, rl.start, k), llen = __shfl_sync(0xffffffffu, rl.len, k);
+            auto taken = [&](unsigned e, const int* m) { return e != kNone && m[candIdx(e)] >= 0; };
+            if (taken(eb, mL) || taken(ep, mL) || taken(es, mL)) reduceList(a.candL + lstart, llen, mL, lane, eb, ep, es);
+            Decision d = decide(eb, ep, es);
+            bool right = false;
+            int bestIdxR = -1;
+            if (nSides == 2) {
+                unsigned rb = __shfl_sync(0xffffffffu, rr.eBest, k), rp = __shfl_sync(0xffffffffu, rr.ePre, k),
+                         rs = __shfl_sync(0xffffffffu, rr.eSuf, k);
+                const int rstart = __shfl_sync(0xffffffffu, rr.start, k), rlen = __shfl_sync(0xffffffffu, rr.len, k);
+                if (taken(rb, mR) || taken(rp, mR) || taken(rs, mR)) reduceList(a.candR + rstart, rlen, mR, lane, rb, rp, rs);
+                const Decision dr = decide(rb, rp, rs);
+                bestIdxR = dr.bestIdx;
+                if (d.bestDist > dr.bestDist) {
+                    d.bestDist = dr.bestDist; d.secDist = dr.secDist; d.bestLev = dr.bestLev; d.bestLev2 = dr.bestLev2;
+                    right = true;
+                }
+            }
+            bool accept;
+            if (a.mode == GVS_MATCH_MONO) {
+                // (ratioProj + 0.1) * secDist is evaluated in double (float + double), threshold 100 + 50
+                const double thr = ((double)0.8f + 0.1) * (double)d.secDist;
+                accept = d.bestDist <= 150 && !(d.bestLev == d.bestLev2 && (double)d.bestDist >= thr) &&
+                         (d.bestLev != d.bestLev2 || (double)d.bestDist < thr);
+            } else {
+                const float thr = __fmul_rn(0.8f, (float)d.secDist);
+                accept = d.bestDist <= 100 && !(d.bestLev == d.bestLev2 && (float)d.bestDist >= thr) &&
+                         (d.bestLev != d.bestLev2 || (float)d.bestDist < thr);
+            }
+            if (accept) {
+                nMatches++;
+                const int i = base + k;
+                if (lane == 0) {
+                    if (a.mode != GVS_MATCH_STEREO_PRED) {
+                        mL[d.bestIdx] = i;
+                        a.matches[2 * i] = d.bestIdx;
+                    } else if (right) {
+                        mR[bestIdxR] = i;
+                        a.matches[2 * i + 1] = bestIdxR;
+                        const int li = a.leftIdxs[bestIdxR];
+                        if (li >= 0) { a.matches[2 * i] = li; mL[li] = i; }
+                    } else {
+                        mL[d.bestIdx] = i;
+                        a.matches[2 * i] = d.bestIdx;
+                        const int ri = a.rightIdxs[d.bestIdx];
+                        if (ri >= 0) { a.matches[2 * i + 1] = ri; mR[ri] = i; }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
+    __syncwarp();
+    for (int i = lane; i < a.NL; i += 32) a.matchedL[i] = mL[i];
+    if (a.mode == GVS_MATCH_STEREO_PRED) for (int i = lane; i < a.NR; i += 32) a.matchedR[i] = mR[i];
+    if (lane == 0) *a.nMatches = nMatches;
+}
+
+void launchProject(const ProjArgs& a, cudaStream_t s, int* launches) {
+    ProjRec* recs = reinterpret_cast<ProjRec*>(a.recs);
+    cudaMemsetAsync(a.poolTop, 0, 2 * sizeof(int), s);
+    if (a.M <= 0) { cudaMemsetAsync(a.nMatches, 0, sizeof(int), s); return; }
+    const int nSides = a.mode == GVS_MATCH_STEREO_PRED ? 2 : 1;
+    const int warps = a.M * nSides;
+    proj_candidates_kernel<<<(warps + 7) / 8, 256, 0, s>>>(a, recs);
+    ++*launches;
+    const size_t sm = (size_t)(a.NL + a.NR) * sizeof(int);
+    static size_t configured = 0;
+    if (sm > 48 * 1024 && configured < sm) {
+        cudaFuncSetAttribute(proj_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        configured = sm;
+    }
+    proj_resolve_kernel<<<1, 32, sm, s>>>(a, recs);
+    ++*launches;
+}
+
+__global__ void hamming_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, int n, int* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4* pa = reinterpret_cast<const uint4*>(a + (size_t)i * 32);
+    const uint4* pb = reinterpret_cast<const uint4*>(b + (size_t)i * 32);
+    const uint4 a0 = pa[0], a1 = pa[1], b0 = pb[0], b1 = pb[1];
+    out[i] = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+             __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+void launchHamming(const uint8_t* a, const uint8_t* b, int n, int* out, cudaStream_t s, int* launches) {
+    if (n <= 0) return;
+    hamming_kernel<<<(n + 255) / 256, 256, 0, s>>>(a, b, n, out);
+    ++*launches;
+}
+
+}  // namespace gvs

@@ -1,0 +1,671 @@
+// K3+K4 select: per (image, level): restore the reference's candidate order, sort by response exactly like
+// cv::sortIdx (libstdc++ introsort, unstable: the tie order is data dependent), and run the SSC binary search
+// (Suppression via Square Covering).  Replaces the ordered emplace_back of computeKeypointsORBNew
+// (reference src/FeatureExtractor.cpp:596-603) and FeatureExtractor::ssc (:368-468).
+//
+// One persistent CTA per resident slot, problems (level-major, biggest first) taken from an atomic counter.
+//
+// (a) order:   exclusive scan of the per-cell counts (cell-row-major) + rank inside the cell gives each
+//              record's position in the reference's emission order; keys and coordinates are scattered
+//              into shared memory in that order.
+// (b) sort:    std::sort(idx, by key[a] < key[b]) followed by array reversal is emulated
+//              exactly but in parallel:
+//              * __unguarded_partition is a two-pointer sweep that swaps the k-th element >= pivot from
+//                the left with the k-th element <= pivot from the right until the pointers cross; the set
+//                of swaps and the cut are closed-form in prefix/suffix ranks, so a partition is three
+//                data-parallel passes (count, rank+assign, swap).  Segments >= 1024 are partitioned by the
+//                whole CTA, smaller ones breadth-first by one warp each; median-of-3, the depth limit
+//                2*floor(log2 n) and the heapsort fallback (one lane, rare) follow libstdc++ literally.
+//              * __final_insertion_sort moves each element left past strictly greater ones, i.e. it is a
+//                stable sort of the partitioned array, done here as a stable counting sort on the 8-bit
+//                score; the descending order is the reversed array.
+//              Validated against cv2.sortIdx / std::sort in tests (including median-of-3 killer inputs).
+// (c) ssc:     a pass keeps a point iff its cell (side width/2) is not covered by an earlier kept point, and
+//              a kept point covers the 5x5 cells around it.  Hence at most the first point of a cell can be
+//              kept and a cell "fires" iff no neighbouring cell (+-2) with a smaller first rank fired: an
+//              exact greedy independent set on the cell grid, resolved in parallel rounds (a decision is
+//              final once made).  Kept points are compacted in sorted order by a block scan.
+//              floor(y / c) with c = width / 2.0 equals (2*y) / width in integers (exact).
+#include "common.cuh"
+
+namespace gvs {
+
+constexpr int kSelThreads = 256;
+constexpr int kSelWarps = kSelThreads / 32;
+constexpr int kSmallMax = 6144;    // problems with n <= kSmallMax run entirely in shared memory
+constexpr int kBigSeg = 1024;      // segments at least this long are partitioned by the whole CTA
+constexpr int kSmemCells = 4096;   // SSC cell grid entries kept in shared memory
+constexpr unsigned kCellEmpty = 0x3fffffffu;
+constexpr unsigned kRankMask = 0x3fffffffu;
+constexpr unsigned kFired = 1u << 30, kDropped = 2u << 30;
+
+template <typename IdxT>
+struct SelArrays {
+    uint8_t* key;    // [n]   score, emission order
+    unsigned* xy;    // [n]   x | y << 12 | score << 24, emission order
+    IdxT* idx;       // [n]   permutation
+    IdxT* tmp;       // [n]   scratch / sorted order
+    int* cellOff;    // [cells + 1]
+    int* seg;        // small-segment frontiers 2 x segCap x 3
+    int segCap;
+    int* hist;       // kSelWarps x 256 counting-sort counters
+    unsigned* cells; // SSC grid
+    int cellCap;
+    unsigned* cellsGlobal;  // fallback hash grid in global scratch (2 * pow2ceil(2n) words)
+};
+
+struct SelShared {
+    int prob;
+    int bigTop;
+    int bigSeg[64][3];
+    int nSeg[2];
+    int wA[kSelWarps], wB[kSelWarps], wM[kSelWarps], wMin[kSelWarps];
+    int cut, pv, m, any;
+    int scan[kSelWarps];
+    int keptTotal;
+};
+
+__device__ __forceinline__ unsigned lanemaskLt() { unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
+__device__ __forceinline__ unsigned lanemaskLe() { unsigned m; asm("mov.u32 %0, %%lanemask_le;" : "=r"(m)); return m; }
+
+// ---- libstdc++ pieces executed by a single lane -----------------------------------------------------
+template <typename IdxT>
+__device__ void moveMedianToFirst(const uint8_t* key, IdxT* idx, int result, int a, int b, int c) {
+    auto lt = [&](int i, int j) { return key[idx[i]] < key[idx[j]]; };
+    auto sw = [&](int i, int j) { IdxT t = idx[i]; idx[i] = idx[j]; idx[j] = t; };
+    if (lt(a, b)) {
+        if (lt(b, c)) sw(result, b);
+        else if (lt(a, c)) sw(result, c);
+        else sw(result, a);
+    } else if (lt(a, c)) sw(result, a);
+    else if (lt(b, c)) sw(result, c);
+    else sw(result, b);
+}
+
+template <typename IdxT>
+__device__ void adjustHeap(const uint8_t* key, IdxT* first, int hole, int len, IdxT value) {
+    const int top = hole;
+    int second = hole;
+    while (second < (len - 1) / 2) {
+        second = 2 * (second + 1);
+        if (key[first[second]] < key[first[second - 1]]) second--;
+        first[hole] = first[second];
+        hole = second;
+    }
+    if ((len & 1) == 0 && second == (len - 2) / 2) {
+        second = 2 * (second + 1);
+        first[hole] = first[second - 1];
+        hole = second - 1;
+    }
+    int parent = (hole - 1) / 2;
+    while (hole > top && key[first[parent]] < key[value]) {
+        first[hole] = first[parent];
+        hole = parent;
+        parent = (hole - 1) / 2;
+    }
+    first[hole] = value;
+}
+
+template <typename IdxT>
+__device__ void heapSort(const uint8_t* key, IdxT* first, int len) {  // std::__partial_sort(first, last, last)
+    if (len >= 2) {
+        int parent = (len - 2) / 2;
+        while (true) {
+            IdxT v = first[parent];
+            adjustHeap(key, first, parent, len, v);
+            if (parent == 0) break;
+            parent--;
+        }
+    }
+    int last = len;
+    while (last > 1) {
+        --last;
+        IdxT v = first[last];
+        first[last] = first[0];
+        adjustHeap(key, first, 0, last, v);
+    }
+}
+
+// ---- warp-level pieces of the parallel partition ----------------------------------------------------
+// count of (key >= pv) and (key <= pv) over positions [a, b)
+template <typename IdxT>
+__device__ __forceinline__ void countAB(const uint8_t* key, const IdxT* idx, int a, int b, int pv, int lane, int& cA, int& cB) {
+    int na = 0, nb = 0;
+    for (int p = a + lane; p < b; p += 32) {
+        const int k = key[idx[p]];
+        na += k >= pv;
+        nb += k <= pv;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { na += __shfl_xor_sync(0xffffffffu, na, o); nb += __shfl_xor_sync(0xffffffffu, nb, o); }
+    cA = na; cB = nb;
+}
+
+// rank + assign over [a, b): runA/runB = counts before a; totalB = count of B over the whole partition range.
+// Writes posA[k] / posB[k] for swapped elements; returns number swapped (A side) and the smallest unswapped A position.
+template <typename IdxT>
+__device__ __forceinline__ void assignAB(const uint8_t* key, const IdxT* idx, int a, int b, int pv, int lane, int runA,
+                                         int runB, int totalB, IdxT* posA, IdxT* posB, int& mOut, int& minUnsw) {
+    int m = 0, mn = 0x7fffffff;
+    const unsigned lt = lanemaskLt(), le = lanemaskLe();
+    for (int base = a; base < b; base += 32) {
+        const int p = base + lane;
+        const bool valid = p < b;
+        const int k = valid ? (int)key[idx[p]] : -1;
+        const bool fa = valid && k >= pv, fb = valid && k <= pv;
+        const unsigned ba = __ballot_sync(0xffffffffu, fa), bb = __ballot_sync(0xffffffffu, fb);
+        const int ra = runA + __popc(ba & lt);
+        const int rbx = totalB - (runB + __popc(bb & le));
+        const bool swA = fa && rbx > ra, swB = fb && ra > rbx;
+        if (swA) posA[ra] = (IdxT)p;
+        if (swB) posB[rbx] = (IdxT)p;
+        if (fa && !swA) mn = min(mn, p);
+        m += __popc(__ballot_sync(0xffffffffu, swA));
+        runA += __popc(ba);
+        runB += __popc(bb);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mOut = m; minUnsw = mn;
+}
+
+// Partition [first, last) with one warp; returns cut.
+template <typename IdxT>
+__device__ int partitionWarp(const uint8_t* key, IdxT* idx, IdxT* tmp, int first, int last, int lane) {
+    if (lane == 0) moveMedianToFirst(key, idx, first, first + 1, first + (last - first) / 2, last - 1);
+    __syncwarp();
+    const int pv = key[idx[first]];
+    const int lo = first + 1, len = last - first;
+    int cA, cB;
+    countAB(key, idx, lo, last, pv, lane, cA, cB);
+    IdxT* posA = tmp + first;
+    IdxT* posB = tmp + first + (len + 1) / 2;
+    int m, mn;
+    assignAB(key, idx, lo, last, pv, lane, 0, 0, cB, posA, posB, m, mn);
+    __syncwarp();
+    const int bm1 = m > 0 ? (int)posB[m - 1] : 0x7fffffff;
+    for (int k = lane; k < m; k += 32) {
+        const int a = posA[k], b = posB[k];
+        const IdxT t = idx[a]; idx[a] = idx[b]; idx[b] = t;
+    }
+    __syncwarp();
+    return min(mn, bm1);
+}
+
+template <typename IdxT>
+__device__ void sortDescending(const SelArrays<IdxT>& A, SelShared& S, int n) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint8_t* key = A.key;
+    IdxT* idx = A.idx;
+    IdxT* tmp = A.tmp;
+    for (int i = tid; i < n; i += kSelThreads) idx[i] = (IdxT)i;
+    if (tid == 0) {
+        S.bigTop = 0; S.nSeg[0] = 0; S.nSeg[1] = 0;
+        if (n > 16) {
+            const int depth = 2 * (31 - __clz(n));
+            if (n >= kBigSeg) { S.bigSeg[0][0] = 0; S.bigSeg[0][1] = n; S.bigSeg[0][2] = depth; S.bigTop = 1; }
+            else { A.seg[0] = 0; A.seg[1] = n; A.seg[2] = depth; S.nSeg[0] = 1; }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 1: big segments, whole CTA per partition
+    while (S.bigTop > 0) {
+        const int top = S.bigTop - 1;
+        const int first = S.bigSeg[top][0], last = S.bigSeg[top][1], depth = S.bigSeg[top][2];
+        __syncthreads();
+        if (depth == 0) {
+            if (tid == 0) { heapSort(key, idx + first, last - first); S.bigTop = top; }
+            __syncthreads();
+            continue;
+        }
+        if (tid == 0) {
+            moveMedianToFirst(key, idx, first, first + 1, first + (last - first) / 2, last - 1);
+            S.pv = key[idx[first]];
+        }
+        __syncthreads();
+        const int pv = S.pv, lo = first + 1, len = last - first;
+        const int chunk = (((last - lo) + kSelWarps - 1) / kSelWarps + 31) & ~31;
+        const int a = min(lo + warp * chunk, last), b = min(a + chunk, last);
+        int cA, cB;
+        countAB(key, idx, a, b, pv, lane, cA, cB);
+        if (lane == 0) { S.wA[warp] = cA; S.wB[warp] = cB; }
+        __syncthreads();
+        int runA = 0, runB = 0, totalB = 0;
+#pragma unroll
+        for (int w = 0; w < kSelWarps; w++) {
+            if (w < warp) { runA += S.wA[w]; runB += S.wB[w]; }
+            totalB += S.wB[w];
+        }
+        IdxT* posA = tmp + first;
+        IdxT* posB = tmp + first + (len + 1) / 2;
+        int m, mn;
+        assignAB(key, idx, a, b, pv, lane, runA, runB, totalB, posA, posB, m, mn);
+        if (lane == 0) { S.wM[warp] = m; S.wMin[warp] = mn; }
+        __syncthreads();
+        int mTot = 0, mnAll = 0x7fffffff;
+#pragma unroll
+        for (int w = 0; w < kSelWarps; w++) { mTot += S.wM[w]; mnAll = min(mnAll, S.wMin[w]); }
+        const int bm1 = mTot > 0 ? (int)posB[mTot - 1] : 0x7fffffff;
+        const int cut = min(mnAll, bm1);
+        __syncthreads();  // everyone has read posB[mTot-1] before tmp is reused by children
+        for (int k = tid; k < mTot; k += kSelThreads) {
+            const int pa = posA[k], pb = posB[k];
+            const IdxT t = idx[pa]; idx[pa] = idx[pb]; idx[pb] = t;
+        }
+        if (tid == 0) {
+            int t2 = top;
+            const int d = depth - 1;
+            auto push = [&](int f, int l) {
+                if (l - f >= kBigSeg) { S.bigSeg[t2][0] = f; S.bigSeg[t2][1] = l; S.bigSeg[t2][2] = d; t2++; }
+                else if (l - f > 16) { int s = S.nSeg[0]++; A.seg[3 * s] = f; A.seg[3 * s + 1] = l; A.seg[3 * s + 2] = d; }
+            };
+            push(cut, last);
+            push(first, cut);
+            S.bigTop = t2;
+        }
+        __syncthreads();
+    }
+
+    // ---- phase 2: small segments, breadth first, one warp per segment
+    int cur = 0;
+    while (true) {
+        const int ns = S.nSeg[cur];
+        if (ns == 0) break;
+        int* segIn = A.seg + cur * 3 * A.segCap;
+        int* segOut = A.seg + (cur ^ 1) * 3 * A.segCap;
+        for (int s = warp; s < ns; s += kSelWarps) {
+            const int first = segIn[3 * s], last = segIn[3 * s + 1], depth = segIn[3 * s + 2];
+            if (depth == 0) {
+                if (lane == 0) heapSort(key, idx + first, last - first);
+                continue;
+            }
+            const int cut = partitionWarp(key, idx, tmp, first, last, lane);
+            if (lane == 0) {
+                if (last - cut > 16) { int o = atomicAdd(&S.nSeg[cur ^ 1], 1); segOut[3 * o] = cut; segOut[3 * o + 1] = last; segOut[3 * o + 2] = depth - 1; }
+                if (cut - first > 16) { int o = atomicAdd(&S.nSeg[cur ^ 1], 1); segOut[3 * o] = first; segOut[3 * o + 1] = cut; segOut[3 * o + 2] = depth - 1; }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) S.nSeg[cur] = 0;
+        cur ^= 1;
+        __syncthreads();
+    }
+
+    // ---- final insertion sort == stable sort by key; reversed -> tmp holds the descending order
+    int* hist = A.hist;
+    for (int i = tid; i < kSelWarps * 256; i += kSelThreads) hist[i] = 0;
+    __syncthreads();
+    const int chunk = ((n + kSelWarps - 1) / kSelWarps + 31) & ~31;
+    const int a = min(warp * chunk, n), b = min(a + chunk, n);
+    for (int base = a; base < b; base += 32) {
+        const int p = base + lane;
+        const int k = p < b ? (int)key[idx[p]] : 256 + lane;  // inactive lanes get unique keys
+        const unsigned peers = __match_any_sync(0xffffffffu, k);
+        if (p < b && (peers & lanemaskLt()) == 0) hist[warp * 256 + k] += __popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+    {   // exclusive scan in (key, warp) order; thread k owns key k
+        int tot = 0;
+        for (int w = 0; w < kSelWarps; w++) tot += hist[w * 256 + tid];
+        int incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        if (lane == 31) S.scan[warp] = incl;
+        __syncthreads();
+        int base = incl - tot;
+        for (int w = 0; w < warp; w++) base += S.scan[w];
+        for (int w = 0; w < kSelWarps; w++) { const int c = hist[w * 256 + tid]; hist[w * 256 + tid] = base; base += c; }
+    }
+    __syncthreads();
+    for (int base = a; base < b; base += 32) {
+        const int p = base + lane;
+        const IdxT v = p < b ? idx[p] : (IdxT)0;
+        const int k = p < b ? (int)key[v] : 256 + lane;
+        const unsigned peers = __match_any_sync(0xffffffffu, k);
+        if (p < b) {
+            const int pos = hist[warp * 256 + k] + __popc(peers & lanemaskLt());
+            tmp[n - 1 - pos] = v;
+        }
+        __syncwarp();
+        if (p < b && (peers & lanemaskLt()) == 0) hist[warp * 256 + k] += __popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+}
+
+// SSC cell grid storage: dense array in shared memory when the grid fits, otherwise an open-addressing hash
+// table in global scratch whose size depends on n only (at most n cells are non-empty).
+struct DenseGrid {
+    unsigned* v;
+    int ncell;
+    __device__ __forceinline__ int slots() const { return ncell; }
+    __device__ __forceinline__ void clear(int s) const { v[s] = kCellEmpty; }
+    __device__ __forceinline__ int insert(unsigned cid) const { return (int)cid; }
+    __device__ __forceinline__ int find(unsigned cid) const { return (int)cid; }
+    __device__ __forceinline__ unsigned cellOf(int s) const { return (unsigned)s; }
+    __device__ __forceinline__ bool used(int s) const { return true; }
+};
+struct HashGrid {
+    unsigned* v;     // value per slot
+    unsigned* k;     // cell id per slot (0xffffffff = free)
+    int mask;        // slots - 1 (power of two)
+    __device__ __forceinline__ int slots() const { return mask + 1; }
+    __device__ __forceinline__ void clear(int s) const { v[s] = kCellEmpty; k[s] = 0xffffffffu; }
+    __device__ __forceinline__ int insert(unsigned cid) const {
+        int s = (int)((cid * 2654435761u) >> 7) & mask;
+        while (true) {
+            const unsigned o = atomicCAS(&k[s], 0xffffffffu, cid);
+            if (o == 0xffffffffu || o == cid) return s;
+            s = (s + 1) & mask;
+        }
+    }
+    __device__ __forceinline__ int find(unsigned cid) const {
+        int s = (int)((cid * 2654435761u) >> 7) & mask;
+        while (true) {
+            const unsigned o = *(volatile unsigned*)&k[s];
+            if (o == cid) return s;
+            if (o == 0xffffffffu) return -1;
+            s = (s + 1) & mask;
+        }
+    }
+    __device__ __forceinline__ unsigned cellOf(int s) const { return k[s]; }
+    __device__ __forceinline__ bool used(int s) const { return k[s] != 0xffffffffu; }
+};
+
+// One SSC pass at `width` over the sorted order `sorted`; writes the kept sorted-positions (ascending) to `res`
+// and returns their number.  `flag` is an n-byte scratch array.
+template <typename IdxT, typename Grid>
+__device__ int sscPassT(const Grid G, const unsigned* xy, SelShared& S, const IdxT* sorted, IdxT* res, uint8_t* flag,
+                        int n, int width, int ncc, int ncr) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned magic = (unsigned)(0x100000000ull / (unsigned)width) + 1u;  // exact while 2*coord*width < 2^32
+    const int nslot = G.slots();
+    for (int i = tid; i < nslot; i += kSelThreads) G.clear(i);
+    for (int i = tid; i < n; i += kSelThreads) flag[i] = 0;
+    __syncthreads();
+    // first (smallest) sorted rank per cell
+    for (int i = tid; i < n; i += kSelThreads) {
+        const unsigned q = xy[sorted[i]];
+        const unsigned x = q & 0xfff, y = (q >> 12) & 0xfff;
+        const unsigned col = __umulhi(2 * x, magic), row = __umulhi(2 * y, magic);
+        atomicMin(&G.v[G.insert(row * (unsigned)ncc + col)], (unsigned)i);
+    }
+    __syncthreads();
+    // exact greedy independent set on the cell grid: a cell fires iff no neighbour (+-2) with a smaller first
+    // rank fired.  Chaotic rounds: every decision is final when taken.
+    while (true) {
+        int undecided = 0;
+        for (int s = tid; s < nslot; s += kSelThreads) {
+            const unsigned v = *(volatile unsigned*)&G.v[s];
+            if (v >= kCellEmpty) continue;  // empty, fired or dropped
+            const unsigned cid = G.cellOf(s);
+            const int row = (int)(cid / (unsigned)ncc), col = (int)(cid - (unsigned)row * ncc);
+            const int r0 = max(row - 2, 0), r1 = min(row + 2, ncr - 1), c0 = max(col - 2, 0), c1 = min(col + 2, ncc - 1);
+            bool drop = false, wait = false;
+            for (int r = r0; r <= r1; r++)
+                for (int c = c0; c <= c1; c++) {
+                    const int t = G.find((unsigned)r * ncc + c);
+                    if (t < 0) continue;
+                    const unsigned o = *(volatile unsigned*)&G.v[t];
+                    if ((o >> 30) == 1) drop = true;
+                    else if ((o >> 30) == 0 && o < v) wait = true;  // undecided neighbour with a smaller first rank
+                }
+            if (drop) G.v[s] = v | kDropped;
+            else if (!wait) { G.v[s] = v | kFired; flag[v] = 1; }
+            else undecided = 1;
+        }
+        if (!__syncthreads_or(undecided)) break;
+    }
+    // ordered compaction of the flags (each thread owns a contiguous strip of sorted positions)
+    const int per = (n + kSelThreads - 1) / kSelThreads;
+    const int a = min(tid * per, n), b = min(a + per, n);
+    int cnt = 0;
+    for (int i = a; i < b; i++) cnt += flag[i];
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) S.scan[warp] = incl;
+    __syncthreads();
+    int base = incl - cnt, total = 0;
+    for (int w = 0; w < kSelWarps; w++) { if (w < warp) base += S.scan[w]; total += S.scan[w]; }
+    for (int i = a; i < b; i++) if (flag[i]) res[base++] = (IdxT)i;
+    __syncthreads();
+    return total;
+}
+
+template <typename IdxT>
+__device__ int sscPass(const SelArrays<IdxT>& A, SelShared& S, const IdxT* sorted, IdxT* res, int n, int width, int cols,
+                       int rows) {
+    const int ncc = (2 * cols) / width + 1, ncr = (2 * rows) / width + 1;  // numCellCols + 1, numCellRows + 1
+    if ((long long)ncc * ncr <= A.cellCap) {
+        DenseGrid G{A.cells, ncc * ncr};
+        return sscPassT<IdxT>(G, A.xy, S, sorted, res, A.key, n, width, ncc, ncr);
+    }
+    int slots = 64;
+    while (slots < 2 * n) slots <<= 1;
+    HashGrid G{A.cellsGlobal, A.cellsGlobal + slots, slots - 1};
+    return sscPassT<IdxT>(G, A.xy, S, sorted, res, A.key, n, width, ncc, ncr);
+}
+
+template <typename IdxT, bool kSmall>
+__global__ void __launch_bounds__(kSelThreads)
+select_kernel(const __grid_constant__ Geometry g, int nImages, const CandRec* __restrict__ recs,
+              const int* __restrict__ nCand, const unsigned short* __restrict__ cellCnt, KeptKey* __restrict__ kept,
+              int* __restrict__ keptCnt, unsigned* __restrict__ orderedDbg, uint8_t* __restrict__ scratch,
+              size_t scratchPerCta, int* __restrict__ workCounter, int* __restrict__ status, int maxCells, int segCap,
+              int nMaxGlobal) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ SelShared S;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    SelArrays<IdxT> A;
+    uint8_t* myScratch = scratch + (size_t)blockIdx.x * scratchPerCta;
+    {
+        // shared layout: cellOff | union(seg + hist, cells) | [small only] xy | idx | tmp | key
+        uint8_t* p = smem;
+        A.cellOff = reinterpret_cast<int*>(p); p += ((maxCells + 1) * 4 + 15) & ~15;
+        const size_t segBytes = (size_t)2 * 3 * segCap * 4, histBytes = kSelWarps * 256 * 4;
+        A.seg = reinterpret_cast<int*>(p);
+        A.hist = reinterpret_cast<int*>(p + segBytes);
+        A.cells = reinterpret_cast<unsigned*>(p);
+        A.segCap = segCap;
+        const size_t unionBytes = segBytes + histBytes > (size_t)kSmemCells * 4 ? segBytes + histBytes : (size_t)kSmemCells * 4;
+        A.cellCap = (int)(unionBytes / 4);
+        p += (unionBytes + 15) & ~15;
+        if (kSmall) {
+            A.xy = reinterpret_cast<unsigned*>(p); p += (size_t)kSmallMax * 4;
+            A.idx = reinterpret_cast<IdxT*>(p); p += (size_t)kSmallMax * sizeof(IdxT);
+            A.tmp = reinterpret_cast<IdxT*>(p); p += (size_t)kSmallMax * sizeof(IdxT);
+            A.key = p;
+            A.cellsGlobal = reinterpret_cast<unsigned*>(myScratch);
+        } else {
+            // global class: seg frontiers do not fit the shared union for large n -> global as well
+            uint8_t* q = myScratch;
+            A.xy = reinterpret_cast<unsigned*>(q); q += (size_t)nMaxGlobal * 4;
+            A.idx = reinterpret_cast<IdxT*>(q); q += (size_t)nMaxGlobal * sizeof(IdxT);
+            A.tmp = reinterpret_cast<IdxT*>(q); q += (size_t)nMaxGlobal * sizeof(IdxT);
+            A.seg = reinterpret_cast<int*>(q); A.segCap = nMaxGlobal / 17 + 2; q += (size_t)2 * 3 * A.segCap * 4;
+            A.key = q; q += ((size_t)nMaxGlobal + 15) & ~(size_t)15;
+            A.cellsGlobal = reinterpret_cast<unsigned*>(q);
+            A.hist = reinterpret_cast<int*>(p - ((unionBytes + 15) & ~15));  // hist alone at the start of the union
+            A.cellCap = (int)(unionBytes / 4);
+        }
+    }
+
+    const int nProb = nImages * g.nLevels;
+    while (true) {
+        __syncthreads();
+        if (tid == 0) S.prob = atomicAdd(workCounter, 1);
+        __syncthreads();
+        const int prob = S.prob;
+        if (prob >= nProb) break;
+        const int level = prob / nImages, img = prob - level * nImages;
+        const LevelGeom& lv = g.lv[level];
+        int n = nCand[img * kMaxLevels + level];
+        if (n > lv.candCap) n = lv.candCap;  // overflow already flagged by the FAST kernel
+        if ((n <= kSmallMax) != kSmall) continue;
+        int* keptCntOut = keptCnt + img * kMaxLevels + level;
+        KeptKey* keptOut = kept + (size_t)img * g.keptPerImage + lv.keptOff;
+        if (n == 0) { if (tid == 0) *keptCntOut = 0; continue; }
+
+        // ---- (a) order: scan cell counts, scatter records
+        const int nCells = lv.nCols * lv.nRows;
+        const unsigned short* cc = cellCnt + (size_t)img * g.cellsPerImage + lv.cellBase;
+        if (warp == 0) {
+            int run = 0;
+            for (int base = 0; base < nCells; base += 32) {
+                const int i = base + lane;
+                const int c = i < nCells ? (int)cc[i] : 0;
+                int incl = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+                if (i < nCells) A.cellOff[i] = run + incl - c;
+                run += __shfl_sync(0xffffffffu, incl, 31);
+            }
+        }
+        __syncthreads();
+        const CandRec* rin = recs + (size_t)img * g.candPerImage + lv.candOff;
+        for (int i = tid; i < n; i += kSelThreads) {
+            const CandRec r = rin[i];
+            const int pos = A.cellOff[r.w1 & 0xffff] + (int)(r.w1 >> 16);
+            if (pos < n) { A.xy[pos] = r.w0; A.key[pos] = (uint8_t)(r.w0 >> 24); }
+        }
+        __syncthreads();
+        if (orderedDbg) {
+            unsigned* o = orderedDbg + (size_t)img * g.candPerImage + lv.candOff;
+            for (int i = tid; i < n; i += kSelThreads) o[i] = A.xy[i];
+        }
+        if (n <= lv.quota) {  // no ssc (src/FeatureExtractor.cpp:610): keys stay in emission order
+            for (int i = tid; i < n; i += kSelThreads) keptOut[i] = A.xy[i];
+            if (tid == 0) *keptCntOut = n;
+            continue;
+        }
+
+        // ---- (b) sort
+        sortDescending(A, S, n);
+        const IdxT* sorted = A.tmp;
+        IdxT* res = A.idx;
+
+        // ---- (c) ssc binary search (src/FeatureExtractor.cpp:396-461)
+        const int K = lv.quota;
+        int high = lv.sscHigh;
+        int low = (int)floor(sqrt((double)n / (double)K));
+        low = max(1, low);
+        int prevWidth = -1, count = 0;
+        while (true) {
+            const int width = low + (high - low) / 2;
+            if (width == prevWidth || low > high) break;
+            count = sscPass(A, S, sorted, res, n, width, lv.w, lv.h);
+            if (count >= lv.kmin && count <= lv.kmax) break;
+            else if (count < lv.kmin) high = width - 1;
+            else low = width + 1;
+            prevWidth = width;
+        }
+        if (count > lv.keptCap) { if (tid == 0) atomicOr(status, kStatKeptOverflow); count = lv.keptCap; }
+        for (int i = tid; i < count; i += kSelThreads) keptOut[i] = A.xy[sorted[res[i]]];
+        if (tid == 0) *keptCntOut = count;
+    }
+}
+
+static size_t selectSmemBytes(bool small, int maxCells, int segCap) {
+    size_t b = ((size_t)(maxCells + 1) * 4 + 15) & ~(size_t)15;
+    const size_t segBytes = (size_t)2 * 3 * segCap * 4, histBytes = kSelWarps * 256 * 4;
+    size_t u = std::max(segBytes + histBytes, (size_t)kSmemCells * 4);
+    b += (u + 15) & ~(size_t)15;
+    if (small) b += (size_t)kSmallMax * (4 + 2 + 2 + 1);
+    return b;
+}
+
+static int maxCandCap(const Geometry& g) {
+    int m = 0;
+    for (int l = 0; l < g.nLevels; l++) m = std::max(m, g.lv[l].candCap);
+    return m;
+}
+
+size_t selectScratchBytes(const Geometry& g) {
+    // global class arrays (xy, idx, tmp, seg frontiers, key) + the hash grid (value + key per slot)
+    const size_t nMax = (size_t)std::max(maxCandCap(g), kSmallMax);
+    size_t b = nMax * (4 + 4 + 4) + (size_t)2 * 3 * (nMax / 17 + 2) * 4 + ((nMax + 15) & ~(size_t)15);
+    size_t slots = 64;
+    while (slots < 2 * nMax) slots <<= 1;
+    b += slots * 8;
+    return (b + 255) & ~(size_t)255;
+}
+
+int selectMaxCtas(int device) {
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    return sms > 0 ? sms * 3 : 148 * 3;
+}
+
+void launchSelect(const Geometry& g, int nImages, const CandRec* recs, const int* nCand, const unsigned short* cellCnt,
+                  KeptKey* kept, int* keptCnt, unsigned* orderedDbg, uint8_t* scratch, size_t scratchPerCta, int nCtas,
+                  int* workCounter, int* status, cudaStream_t s, int* launches) {
+    int maxCells = 0;
+    for (int l = 0; l < g.nLevels; l++) maxCells = std::max(maxCells, g.lv[l].nCols * g.lv[l].nRows);
+    const int segCapSmall = kSmallMax / 17 + 2;
+    const size_t smSmall = selectSmemBytes(true, maxCells, segCapSmall);
+    const size_t smBig = selectSmemBytes(false, maxCells, 1);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(select_kernel<unsigned short, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(select_kernel<unsigned, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        configured = true;
+    }
+    const int nProb = nImages * g.nLevels;
+    const int grid = std::min(nCtas, nProb);
+    cudaMemsetAsync(workCounter, 0, 2 * sizeof(int), s);
+    select_kernel<unsigned short, true><<<grid, kSelThreads, smSmall, s>>>(
+        g, nImages, recs, nCand, cellCnt, kept, keptCnt, orderedDbg, scratch, scratchPerCta, workCounter, status, maxCells,
+        segCapSmall, maxCandCap(g));
+    ++*launches;
+    bool needBig = false;
+    for (int l = 0; l < g.nLevels; l++) needBig |= g.lv[l].candCap > kSmallMax;
+    if (needBig) {
+        select_kernel<unsigned, false><<<grid, kSelThreads, smBig, s>>>(
+            g, nImages, recs, nCand, cellCnt, kept, keptCnt, orderedDbg, scratch, scratchPerCta, workCounter + 1, status,
+            maxCells, 1, maxCandCap(g));
+        ++*launches;
+    }
+}
+
+// exclusive scan of per-image totals -> dense output offsets (one CTA; nImages is small)
+__global__ void offsets_kernel(int nLevels, int nImages, const int* __restrict__ keptCnt, int* __restrict__ imgOff,
+                               int totalCap, int* __restrict__ status) {
+    __shared__ int sRun;
+    __shared__ int sW[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) sRun = 0;
+    __syncthreads();
+    for (int base = 0; base < nImages; base += blockDim.x) {
+        const int i = base + tid;
+        int c = 0;
+        if (i < nImages)
+            for (int l = 0; l < nLevels; l++) c += keptCnt[i * kMaxLevels + l];
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        if (lane == 31) sW[warp] = incl;
+        __syncthreads();
+        int add = sRun;
+        for (int w = 0; w < warp; w++) add += sW[w];
+        if (i < nImages) imgOff[i] = add + incl - c;
+        __syncthreads();
+        if (tid == blockDim.x - 1) sRun = add + incl;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        imgOff[nImages] = sRun;
+        if (sRun > totalCap) atomicOr(status, kStatOutputOverflow);
+    }
+}
+
+void launchOffsets(const Geometry& g, int nImages, const int* keptCnt, int* imgOff, int totalCap, int* status,
+                   cudaStream_t s, int* launches) {
+    offsets_kernel<<<1, 256, 0, s>>>(g.nLevels, nImages, keptCnt, imgOff, totalCap, status);
+    ++*launches;
+}
+
+}  // namespace gvs

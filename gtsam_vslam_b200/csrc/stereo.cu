@@ -1,0 +1,287 @@
+// K8 stereo_match + K8b stereo_finalize + K9 grid_assign.
+// Replaces FeatureMatcher::findStereoMatchesORB2R and destributeRightKeys (reference src/FeatureMatcher.cpp:528-708,
+// :728-752) and FeatureTracker::assignKeysToGrids (src/FeatureTracker.cpp:28-54) for a batch of frames.
+//
+// stereo_match: one warp per left key.
+//   * the row buckets of destributeRightKeys are never materialised: right key j is in bucket[yKeyL] iff
+//     floor(yKeyR - r) <= yKeyL <= ceil(yKeyR + r), r = 2*scalePyramid[octR] (float32), and buckets hold
+//     indices in ascending order, so "first minimum in bucket order" is the minimum of (distance, j).
+//     Right keys are stored level by level, so only the levels octL-1..octL+1 are scanned.
+//   * the reference's "u" test uses pt.y (sic): yL - fx <= yR <= yL.
+//   * Hamming distance: 8 x __popc on 32-bit words, warp-shuffle argmin on (dist << 20 | j).
+//   * SAD refinement on the unblurred level octL of both pyramids: 22 lanes = 11 shifts x 2 row halves,
+//     skipped shifts keep 0.0 (App. B.3); float32 parabola and depth with explicit round-to-nearest ops.
+//   * leftIdxs[j] is last-writer-wins in left-index order (App. B.4) = atomicMax over the accepted left indices.
+// stereo_finalize: one CTA per frame; bitonic sorts of (depth, idx) and (SAD, idx) give the lowest floor(1%)
+//   depths and the median SAD; both outlier passes are then order independent.
+// Bound: integer pipe / L2 latency; the HBM traffic of this stage is negligible (descriptors + keypoints).
+#include "common.cuh"
+
+namespace gvs {
+
+__device__ __forceinline__ int hamming256(const uint4& a0, const uint4& a1, const uint4& b0, const uint4& b1) {
+    return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+           __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+__global__ void __launch_bounds__(256)
+stereo_match_kernel(const __grid_constant__ Geometry g, const StereoArgs a) {
+    const int frame = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int offL = a.offL[frame], nL = a.offL[frame + 1] - offL;
+    const int offR = a.offR[frame], nR = a.offR[frame + 1] - offR;
+    __shared__ int sLvlStart[kMaxLevels + 1];
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int l = 0; l < kMaxLevels; l++) { sLvlStart[l] = run; run += l < g.nLevels ? a.keptCntR[frame * kMaxLevels + l] : 0; }
+        sLvlStart[kMaxLevels] = run;
+    }
+    __syncthreads();
+    const float maxD = (float)a.fx;
+    const int warpsPerGrid = gridDim.x * (blockDim.x >> 5);
+    for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < nL; i += warpsPerGrid) {
+        const gvs_keypoint kl = a.kpL[offL + i];
+        int rIdx = -1, sad = 0;
+        float depth = -1.f;
+        bool close = false;
+        const int yKey = __float2int_rn(kl.y);
+        const float uL = kl.y;
+        const int octL = kl.octave;
+        const float minU = __fsub_rn(uL, maxD), maxU = uL;
+        if (!(maxU < 0.f) && yKey >= 0 && yKey < a.imageHeight) {
+            const uint4* dl = reinterpret_cast<const uint4*>(a.descL + (size_t)(offL + i) * 32);
+            const uint4 l0 = __ldg(dl), l1 = __ldg(dl + 1);
+            const int j0 = sLvlStart[max(octL - 1, 0)], j1 = sLvlStart[min(octL + 2, kMaxLevels)];
+            unsigned best = 0xffffffffu;
+            for (int j = j0 + lane; j < min(j1, nR); j += 32) {
+                const gvs_keypoint kr = a.kpR[offR + j];
+                const int yKeyR = __float2int_rn(kr.y);
+                const float r = __fmul_rn(2.0f, g.lv[kr.octave].scale);
+                const int mn = (int)floorf(__fsub_rn((float)yKeyR, r)), mx = (int)ceilf(__fadd_rn((float)yKeyR, r));
+                if (yKey < mn || yKey > mx) continue;
+                if (!(kr.y >= minU && kr.y <= maxU)) continue;
+                const uint4* dr = reinterpret_cast<const uint4*>(a.descR + (size_t)(offR + j) * 32);
+                const int dist = hamming256(l0, l1, __ldg(dr), __ldg(dr + 1));
+                best = min(best, ((unsigned)dist << 20) | (unsigned)j);
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+            const int bestDist = best == 0xffffffffu ? 256 : (int)(best >> 20);
+            if (bestDist <= a.thDist) {
+                const int bestIdx = (int)(best & 0xfffff);
+                const float kRx = a.kpR[offR + bestIdx].x;
+                const LevelGeom& lv = g.lv[octL];
+                const float scale = lv.invScale;
+                const int scuL = (int)roundf(__fmul_rn(kl.x, scale)), scvL = (int)roundf(__fmul_rn(kl.y, scale));
+                const int scuR = (int)roundf(__fmul_rn(kRx, scale));
+                const uint8_t* imL = levelPtr(a.slabL, g, frame, octL);
+                const uint8_t* imR = levelPtr(a.slabR, g, frame, octL);
+                // 22 lanes: shift s = lane % 11 (xMov = s - 5), rows half*6 .. half*6+5 (second half has 5 rows)
+                int part = 0;
+                const int s = lane % 11, half = lane / 11;
+                const int startW = scuR + (s - 5) - 5, endW = scuR + (s - 5) + 6;
+                const bool skip = startW < 0 || endW >= lv.w;
+                if (lane < 22 && !skip) {
+                    const int rEnd = half ? 11 : 6;
+                    for (int r = half * 6; r < rEnd; r++) {
+                        const uint8_t* pl = imL + (size_t)(scvL - 5 + r) * lv.pitch + (scuL - 5);
+                        const uint8_t* pr = imR + (size_t)(scvL - 5 + r) * lv.pitch + startW;
+#pragma unroll
+                        for (int c = 0; c < 11; c++) part += abs((int)pl[c] - (int)pr[c]);
+                    }
+                }
+                part += __shfl_down_sync(0xffffffffu, part, 11);  // lanes 0..10 now hold the full SAD of shift s
+                const unsigned skipMask = __ballot_sync(0xffffffffu, skip);
+                int bestDistW = 0x7fffffff, bestX = 0;
+                float d[11];
+#pragma unroll
+                for (int t = 0; t < 11; t++) {
+                    const int v = __shfl_sync(0xffffffffu, part, t);
+                    const bool sk = (skipMask >> t) & 1;
+                    d[t] = sk ? 0.0f : (float)v;
+                    if (!sk && (float)bestDistW > (float)v) { bestX = t - 5; bestDistW = v; }
+                }
+                if (bestX != -5 && bestX != 5) {
+                    float dist1 = 0.f, dist2 = 0.f, dist3 = 0.f;
+#pragma unroll
+                    for (int t = 1; t < 10; t++)
+                        if (t == bestX + 5) { dist1 = d[t - 1]; dist2 = d[t]; dist3 = d[t + 1]; }
+                    const float delta = __fdiv_rn(__fsub_rn(dist1, dist3),
+                                                  __fmul_rn(2.0f, __fsub_rn(__fadd_rn(dist1, dist3), __fmul_rn(2.0f, dist2))));
+                    if (!(delta > 1.f || delta < -1.f)) {
+                        const float newuR = __fmul_rn(lv.scale, __fadd_rn(__fadd_rn((float)scuR, (float)bestX), delta));
+                        const float disparity = __fsub_rn(kl.x, newuR);
+                        if (disparity > 0.0f && (double)disparity < a.fx) {
+                            depth = __fdiv_rn(__fmul_rn((float)a.fx, a.baseline), disparity);
+                            rIdx = bestIdx;
+                            sad = bestDistW;
+                            close = depth < __fmul_rn(a.baseline, (float)a.closeNumber);
+                        }
+                    }
+                }
+            }
+        }
+        if (lane == 0) {
+            a.rightIdxs[offL + i] = rIdx;
+            a.depth[offL + i] = depth;
+            a.close[offL + i] = close ? 1 : 0;
+            a.sadBest[offL + i] = sad;
+            if (rIdx >= 0) atomicMax(&a.leftIdxs[offR + rIdx], i);
+        }
+    }
+}
+
+// ascending bitonic sort of n 64-bit keys (n a power of two) in shared memory
+__device__ void bitonicSort(unsigned long long* k, int n) {
+    for (int size = 2; size <= n; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int t = threadIdx.x; t < n / 2; t += blockDim.x) {
+                const int lo = 2 * t - (t & (stride - 1));
+                const int hi = lo + stride;
+                const bool up = (lo & size) == 0;
+                const unsigned long long x = k[lo], y = k[hi];
+                if ((x > y) == up) { k[lo] = y; k[hi] = x; }
+            }
+        }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+stereo_finalize_kernel(const StereoArgs a, int sortCap) {
+    extern __shared__ unsigned long long sKeys[];
+    __shared__ int sCount;
+    __shared__ float sMed;
+    const int frame = blockIdx.x, tid = threadIdx.x;
+    const int offL = a.offL[frame], nL = a.offL[frame + 1] - offL;
+    const int offR = a.offR[frame];
+    if (tid == 0) sCount = 0;
+    __syncthreads();
+    // pass A: (depth, idx) ascending -> lowest floor(1%) depths
+    for (int i = tid; i < nL; i += blockDim.x)
+        if (a.rightIdxs[offL + i] >= 0) {
+            const int s = atomicAdd(&sCount, 1);
+            if (s < sortCap) sKeys[s] = ((unsigned long long)__float_as_uint(a.depth[offL + i]) << 32) | (unsigned)i;
+        }
+    __syncthreads();
+    const int V = min(sCount, sortCap);
+    if (V <= 0) return;
+    int n2 = 1;
+    while (n2 < V) n2 <<= 1;
+    for (int i = V + tid; i < n2; i += blockDim.x) sKeys[i] = ~0ull;
+    bitonicSort(sKeys, n2);
+    const int endDe = (int)floor((double)V * 0.01);
+    // remember which left keys pass A removes (apply after pass B has read the SADs: the passes commute)
+    unsigned dropA = 0xffffffffu;  // each thread remembers at most a few; endDe is small -> loop
+    __syncthreads();
+    // pass B needs the SAD keys: build them before overwriting anything
+    // stash pass-A victims in the tail of the key array (n2 .. n2+endDe) is not possible without extra room,
+    // so mark them through the close[] byte: 2 = "drop" (close is rewritten below)
+    for (int i = tid; i < endDe; i += blockDim.x) a.close[offL + (int)(sKeys[i] & 0xffffffffu)] = 2;
+    (void)dropA;
+    __syncthreads();
+    if (tid == 0) sCount = 0;
+    __syncthreads();
+    for (int i = tid; i < nL; i += blockDim.x)
+        if (a.rightIdxs[offL + i] >= 0) {
+            const int s = atomicAdd(&sCount, 1);
+            if (s < sortCap) sKeys[s] = ((unsigned long long)(unsigned)a.sadBest[offL + i] << 32) | (unsigned)i;
+        }
+    __syncthreads();
+    for (int i = V + tid; i < n2; i += blockDim.x) sKeys[i] = ~0ull;
+    bitonicSort(sKeys, n2);
+    if (tid == 0) {
+        const int medianD = (int)(sKeys[V / 2] >> 32);
+        sMed = __fmul_rn((float)medianD, __fmul_rn(1.5f, 1.4f));
+    }
+    __syncthreads();
+    const float medDistD = sMed;
+    for (int i = tid; i < nL; i += blockDim.x) {
+        const int r = a.rightIdxs[offL + i];
+        if (r < 0) continue;
+        const bool drop = a.close[offL + i] == 2 || !((float)a.sadBest[offL + i] < medDistD);
+        if (drop) {
+            a.leftIdxs[offR + r] = -1;
+            a.rightIdxs[offL + i] = -1;
+            a.depth[offL + i] = -1.f;
+            a.close[offL + i] = 0;
+        }
+    }
+}
+
+void launchStereo(const Geometry& g, const StereoArgs& a, int nFrames, int maxKeysPerImage, cudaStream_t s, int* launches) {
+    if (nFrames <= 0) return;
+    const int warpsPerCta = 8;
+    int gx = (maxKeysPerImage / 2 + 4 * warpsPerCta - 1) / (4 * warpsPerCta);  // ~4 left keys per warp at typical fill
+    if (gx < 1) gx = 1;
+    stereo_match_kernel<<<dim3(gx, nFrames), 32 * warpsPerCta, 0, s>>>(g, a);
+    ++*launches;
+    int n2 = 1;
+    while (n2 < maxKeysPerImage) n2 <<= 1;
+    const size_t sm = (size_t)n2 * 8;
+    static size_t configured = 0;
+    if (sm > 48 * 1024 && configured < sm) {
+        cudaFuncSetAttribute(stereo_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        configured = sm;
+    }
+    stereo_finalize_kernel<<<nFrames, 256, sm, s>>>(a, n2);
+    ++*launches;
+}
+
+// ------------------------------------------------------------------ K9 grid_assign
+// One warp per image: bin = cvRound(pt * mult) clamped (src/FeatureTracker.cpp:40-49); CSR with insertion
+// (= index) order inside a cell: counting pass, exclusive scan, stable fill in chunks of 32 keys.
+__global__ void __launch_bounds__(32)
+grid_assign_kernel(const GridArgs a) {
+    extern __shared__ int sCell[];  // maxCells + 1
+    const int img = blockIdx.x, lane = threadIdx.x;
+    const int off = a.off[img], n = a.off[img + 1] - off;
+    const int nCells = a.xGrids * a.yGrids;
+    for (int c = lane; c <= nCells; c += 32) sCell[c] = 0;
+    __syncwarp();
+    auto cellOf = [&](int i) {
+        const gvs_keypoint k = a.kps[off + i];
+        int xPos = __float2int_rn(__fmul_rn(k.x, a.xMult)), yPos = __float2int_rn(__fmul_rn(k.y, a.yMult));
+        xPos = min(max(xPos, 0), a.xGrids - 1);
+        yPos = min(max(yPos, 0), a.yGrids - 1);
+        return yPos * a.xGrids + xPos;
+    };
+    for (int i = lane; i < n; i += 32) atomicAdd(&sCell[cellOf(i)], 1);
+    __syncwarp();
+    // exclusive scan over cells
+    int run = 0;
+    for (int base = 0; base < nCells; base += 32) {
+        const int c = base + lane;
+        const int v = c < nCells ? sCell[c] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (c < nCells) sCell[c] = run + incl - v;
+        run += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) sCell[nCells] = run;
+    __syncwarp();
+    int* cs = a.cellStart + (size_t)img * (a.maxCells + 1);
+    for (int c = lane; c <= nCells; c += 32) cs[c] = sCell[c];
+    __syncwarp();
+    // stable fill
+    unsigned lt;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt));
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        const int c = i < n ? cellOf(i) : -1 - lane;
+        const unsigned peers = __match_any_sync(0xffffffffu, c);
+        if (i < n) a.items[off + sCell[c] + __popc(peers & lt)] = i;
+        __syncwarp();
+        if (i < n && (peers & lt) == 0) sCell[c] += __popc(peers);
+        __syncwarp();
+    }
+}
+
+void launchGrid(const GridArgs& a, int nImages, cudaStream_t s, int* launches) {
+    if (nImages <= 0) return;
+    grid_assign_kernel<<<nImages, 32, (a.maxCells + 1) * sizeof(int), s>>>(a);
+    ++*launches;
+}
+
+}  // namespace gvs

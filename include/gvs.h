@@ -1,0 +1,198 @@
+/*
+ * gvs.h -- C ABI of the B200-native frontend hot path of gtsam-vSLAM.
+ *
+ * The reference (christoskokas/gtsam-vSLAM) has no FFI / plugin layer: its boundary for this path is the
+ * public C++ surface of FeatureExtractor, FeatureMatcher and two FeatureTracker helpers.  Every entry point
+ * below names the reference interface it replaces (file:line under the reference tree).  The C++ adapter
+ * classes in include/gvs_adapter.hpp keep the reference's class and member names on top of this ABI.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; all functions return 0 (GVS_OK) or a negative gvs_status;
+ *    gvs_last_error() gives the text for the calling thread.  The reference itself has no error channel
+ *    (void returns, unchecked indexing); conditions that are UB there are GVS_ERR_* here.
+ *  - there is NO CPU fallback: without a CUDA device every compute call fails with GVS_ERR_CUDA.
+ *  - a gvs_extractor is one FeatureExtractor instance with `max_images` image slots, so that a batch of
+ *    independent frames runs as one set of launches.  Handles own their CUDA stream; two handles may be
+ *    driven from two host threads concurrently (as reference src/FeatureTracker.cpp:58-61 does).
+ *  - results of the last extract stay resident on the device (pyramids, keypoints, descriptors) and are what
+ *    the matcher calls read, exactly like FeatureMatcher reads feLeft->imagePyramid (src/FeatureMatcher.cpp:606).
+ */
+#ifndef GVS_H_
+#define GVS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GVS_MAX_LEVELS 12
+#define GVS_GRID_X 64 /* FeatureTracker::assignKeysToGrids xGrids, src/FeatureTracker.cpp:31 */
+
+typedef enum gvs_status {
+    GVS_OK = 0,
+    GVS_ERR_INVALID = -1,  /* bad argument */
+    GVS_ERR_CUDA = -2,     /* CUDA runtime / driver error, or no device */
+    GVS_ERR_CAPACITY = -3, /* an internal or caller buffer was too small; nothing was silently dropped */
+    GVS_ERR_STATE = -4     /* call order violated (e.g. match before extract) */
+} gvs_status;
+
+/* Same memory layout as cv::KeyPoint (28 bytes): the adapter memcpy's into std::vector<cv::KeyPoint>. */
+typedef struct gvs_keypoint {
+    float x, y;     /* pt, level coordinates times scalePyramid[octave] (src/FeatureExtractor.cpp:523-524) */
+    float size;     /* (float)scaledPatchSize[octave] (:601) */
+    float angle;    /* degrees in [0,360), cv::fastAtan2 of the intensity centroid (:338) */
+    float response; /* FAST score (integer valued) */
+    int32_t octave; /* pyramid level */
+    int32_t class_id; /* -1 */
+} gvs_keypoint;
+
+/* FeatureExtractor constructor arguments, include/FeatureExtractor.h:80 (defaults in gvs_default_params). */
+typedef struct gvs_extractor_params {
+    int32_t n_features;
+    int32_t n_levels;
+    float im_scale;
+    int32_t edge_threshold;
+    int32_t patch_size;
+    int32_t max_fast_threshold;
+    int32_t min_fast_threshold;
+} gvs_extractor_params;
+
+typedef struct gvs_extractor gvs_extractor; /* replaces class FeatureExtractor, include/FeatureExtractor.h:52-97 */
+typedef struct gvs_matcher gvs_matcher;     /* replaces class FeatureMatcher,  include/FeatureMatcher.h:22-65 */
+
+const char* gvs_last_error(void);
+int gvs_version(void);
+void gvs_default_params(gvs_extractor_params* p); /* 2000, 8, 1.2f, 19, 31, 20, 7 */
+int gvs_device_count(void);
+
+/* ------------------------------------------------------------------ FeatureExtractor ---------------- */
+
+/* FeatureExtractor::FeatureExtractor, src/FeatureExtractor.cpp:620-682.  Image size is fixed per handle
+ * (the reference re-derives level sizes per call from image.cols/rows, :347; cameras do not change size). */
+int gvs_extractor_create(gvs_extractor** out, const gvs_extractor_params* params, int width, int height,
+                         int max_images, int device);
+int gvs_extractor_destroy(gvs_extractor* fe);
+
+/* Public tables read by KeyFrame / pose optimisation (include/FeatureExtractor.h:71-77;
+ * src/FeatureTracker.cpp:75-79).  Each array has n_levels entries; any pointer may be NULL. */
+int gvs_extractor_tables(const gvs_extractor* fe, float* scale_pyramid, float* scale_inv_pyramid, float* sigma_factor,
+                         float* inv_sigma_factor, int32_t* scaled_patch_size, int32_t* feature_per_level);
+/* imagePyramid[level].cols / .rows (computePyramid, src/FeatureExtractor.cpp:346-347) */
+int gvs_extractor_level_size(const gvs_extractor* fe, int level, int* width, int* height);
+
+/* FeatureExtractor::extractKeysNew, src/FeatureExtractor.cpp:481-533, one image (slot 0).
+ * gray: host pointer, u8, `stride` bytes per row.  out/desc: caller arrays of `cap` keypoints / cap*32 bytes.
+ * Zero keypoints leaves out/desc untouched and sets *n = 0 (:498-499). */
+int gvs_extract(gvs_extractor* fe, const uint8_t* gray, int width, int height, int stride, gvs_keypoint* out,
+                uint8_t* desc, int cap, int* n);
+
+/* Batched form of extractKeysNew over n_images independent images (throughput path).
+ * Host images: image i starts at images + i*image_stride, rows are row_stride bytes apart.  Asynchronous on
+ * the handle's stream; gvs_extractor_sync / the download calls wait. */
+int gvs_extract_batch_host(gvs_extractor* fe, const uint8_t* images, size_t image_stride, int row_stride, int n_images);
+/* Device-resident input: the caller fills the handle's own pitched level-0 store (device pointer *dev,
+ * rows *pitch bytes apart, images *image_stride bytes apart), then runs n_images slots. */
+int gvs_extractor_input(gvs_extractor* fe, uint8_t** dev, int* pitch, size_t* image_stride);
+int gvs_extract_batch_resident(gvs_extractor* fe, int n_images);
+int gvs_extractor_sync(gvs_extractor* fe);
+
+/* Per-image results of the last batch.  offsets has n_images+1 entries: image i owns [offsets[i], offsets[i+1])
+ * of the dense keypoint / descriptor arrays.  Waits for the batch. */
+int gvs_extract_offsets(gvs_extractor* fe, int32_t* offsets);
+/* Copy keypoints / descriptors of images [first, first+count) (dense, in image order) to the host. */
+int gvs_extract_download(gvs_extractor* fe, int first, int count, gvs_keypoint* kps, uint8_t* desc, int cap);
+
+/* Use an externally owned CUDA stream (cudaStream_t as void*) for all work of this handle; NULL restores the
+ * handle's own stream. */
+int gvs_extractor_set_stream(gvs_extractor* fe, void* cuda_stream);
+
+/* Parity taps (tests only; they stall the stream).  imagePyramid[level] / its blurred clone
+ * (src/FeatureExtractor.cpp:512-515), tightly packed w*h bytes. */
+int gvs_debug_level_image(gvs_extractor* fe, int image, int level, int blurred, uint8_t* out);
+/* Ordered FAST candidates of a level before ssc (computeKeypointsORBNew, :563-608): returns count in *n. */
+int gvs_debug_level_candidates(gvs_extractor* fe, int image, int level, int32_t* x, int32_t* y, int32_t* score, int cap,
+                               int* n);
+/* Keys of a level after ssc (:609-613) in output order, with the integer moments of computeOrientation. */
+int gvs_debug_level_kept(gvs_extractor* fe, int image, int level, int32_t* x, int32_t* y, int32_t* score, int cap, int* n);
+
+/* ------------------------------------------------------------------ FeatureMatcher ------------------ */
+
+/* FeatureMatcher::FeatureMatcher, src/FeatureMatcher.cpp:8.  fx = zedptr->mCameraLeft->fx (double,
+ * include/Camera.h:72), baseline = zedptr->mBaseline (float, :86), image_height sizes the row buckets (:732). */
+int gvs_matcher_create(gvs_matcher** out, gvs_extractor* fe_left, gvs_extractor* fe_right, double fx, float baseline,
+                       int image_height);
+int gvs_matcher_destroy(gvs_matcher* fm);
+
+/* FeatureMatcher::findStereoMatchesORB2R, src/FeatureMatcher.cpp:528-708, for frames [0,n_frames): frame f
+ * matches image slot f of fe_left against slot f of fe_right (device resident, last batch).  Asynchronous. */
+int gvs_stereo_match_batch(gvs_matcher* fm, int n_frames);
+/* rightIdxs / estimatedDepth / close are indexed like the left keypoints of frames [first,first+count)
+ * (dense, left offsets); leftIdxs like the right keypoints (right offsets).  Any pointer may be NULL. */
+int gvs_stereo_download(gvs_matcher* fm, int first, int count, int32_t* right_idxs, int32_t* left_idxs,
+                        float* estimated_depth, uint8_t* close);
+
+/* FeatureTracker::assignKeysToGrids, src/FeatureTracker.cpp:28-54, for both sides of frames [0,n_frames)
+ * (device resident CSR: the grids feed gvs_match_projection).  width/height = zedPtr->mWidth/mHeight. */
+int gvs_assign_grids_batch(gvs_matcher* fm, int n_frames, int width, int height);
+/* CSR download for one frame and side (0 left, 1 right): cell_start has y_grids*64+1 entries, items n. */
+int gvs_grid_download(gvs_matcher* fm, int frame, int side, int32_t* cell_start, int32_t* items, int* y_grids,
+                      float* x_mult, float* y_mult);
+
+/* FeatureTracker::extractORBAndStereoMatch, src/FeatureTracker.cpp:56-70, for n_frames host frames:
+ * extract left and right (two streams, like the two std::threads), stereo match, assign both grids. */
+int gvs_track_stereo_batch_host(gvs_matcher* fm, const uint8_t* left, const uint8_t* right, size_t image_stride,
+                                int row_stride, int n_frames, int width, int height);
+int gvs_track_stereo_batch_resident(gvs_matcher* fm, int n_frames, int width, int height);
+int gvs_matcher_sync(gvs_matcher* fm);
+
+/* Map points as a structure of arrays: the fields of MapPoint that the projection matchers read
+ * (include/Map.h; src/FeatureMatcher.cpp:264-267,307-310). */
+typedef struct gvs_mappoints {
+    int32_t count;
+    const uint8_t* desc;          /* count x 32, MapPoint::desc */
+    const float* pred_l;          /* count x 2, MapPoint::predL */
+    const float* pred_r;          /* count x 2, MapPoint::predR (NULL for mono / radius) */
+    const int32_t* scale_level_l; /* MapPoint::scaleLevelL */
+    const int32_t* scale_level_r; /* MapPoint::scaleLevelR (NULL for mono / radius) */
+    const uint8_t* in_frame;      /* MapPoint::inFrame  (NULL = all true) */
+    const uint8_t* in_frame_r;    /* MapPoint::inFrameR (NULL = all true) */
+} gvs_mappoints;
+
+typedef enum gvs_match_mode {
+    GVS_MATCH_STEREO_PRED = 0, /* FeatureMatcher::matchByProjectionRPred, src/FeatureMatcher.cpp:254-389 */
+    GVS_MATCH_MONO = 1,        /* FeatureMatcher::matchByProjectionMono,  :391-456 */
+    GVS_MATCH_RADIUS = 2       /* FeatureMatcher::matchByRadius,          :458-526 (map points = last keyframe's
+                                  keys: pred_l = pt, scale_level_l = octave, desc = Desc rows) */
+} gvs_match_mode;
+
+/* One call of matchByProjection* / matchByRadius against frame `frame` of the last batch (host arrays in,
+ * host arrays out).  matched_l (n_left) / matched_r (n_right) / matches (count x 2, pair<int,int>) are
+ * in-out exactly as in the reference (callers pre-fill them with -1 or with earlier matches).  For
+ * GVS_MATCH_RADIUS matches[i][0] receives the matched key index (the reference appends (KeyFrame*, idx)
+ * to keyframeIdxMatchs[i], :522).  *n_matches = the reference's return value.  Requires
+ * gvs_assign_grids_batch (and gvs_stereo_match_batch for mode 0). */
+int gvs_match_projection(gvs_matcher* fm, int frame, int mode, const gvs_mappoints* mps, float rad, int32_t* matched_l,
+                         int32_t* matched_r, int32_t* matches, int* n_matches);
+
+/* FeatureMatcher::DescriptorDistance, src/FeatureMatcher.cpp:710-726, for n pairs of 32-byte descriptors
+ * (host arrays; computed on the device). */
+int gvs_descriptor_distance(gvs_matcher* fm, const uint8_t* a, const uint8_t* b, int n, int32_t* dist);
+
+/* ------------------------------------------------------------------ measurement --------------------- */
+
+/* Launch counters and device timings of the last batch, for bench.py (gpu_launches, per-stage ms). */
+typedef struct gvs_stage_times {
+    float pyramid_ms, fast_ms, select_ms, blur_ms, describe_ms, stereo_ms, grid_ms;
+    int32_t launches;
+} gvs_stage_times;
+int gvs_extractor_enable_timing(gvs_extractor* fe, int on);
+int gvs_extractor_stage_times(gvs_extractor* fe, gvs_stage_times* t);
+int gvs_matcher_launch_count(gvs_matcher* fm, int64_t* launches); /* kernels launched since creation */
+int gvs_extractor_launch_count(gvs_extractor* fe, int64_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GVS_H_ */
