@@ -28,7 +28,7 @@ SYMBOLS = [
     "gvs_extractor_create", "gvs_extractor_destroy", "gvs_extractor_tables", "gvs_extractor_level_size",
     "gvs_extract", "gvs_extract_batch_host", "gvs_extractor_input", "gvs_extract_batch_resident",
     "gvs_extractor_sync", "gvs_extract_offsets", "gvs_extract_download", "gvs_extractor_set_stream",
-    "gvs_debug_level_image", "gvs_debug_level_candidates", "gvs_debug_level_kept",
+    "gvs_debug_level_image", "gvs_debug_level_candidates", "gvs_debug_level_kept", "gvs_debug_select",
     "gvs_matcher_create", "gvs_matcher_destroy", "gvs_stereo_match_batch", "gvs_stereo_download",
     "gvs_assign_grids_batch", "gvs_grid_download", "gvs_track_stereo_batch_host",
     "gvs_track_stereo_batch_resident", "gvs_matcher_sync", "gvs_match_projection", "gvs_descriptor_distance",
@@ -88,6 +88,7 @@ def load_library() -> C.CDLL:
     lib.gvs_debug_level_image.argtypes = [vp, i32, i32, i32, vp]
     lib.gvs_debug_level_candidates.argtypes = [vp, i32, i32, vp, vp, vp, i32, C.POINTER(i32)]
     lib.gvs_debug_level_kept.argtypes = [vp, i32, i32, vp, vp, vp, i32, C.POINTER(i32)]
+    lib.gvs_debug_select.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, i32, C.POINTER(i32)]
     lib.gvs_matcher_create.argtypes = [C.POINTER(vp), vp, vp, C.c_double, f32, i32]
     lib.gvs_matcher_destroy.argtypes = [vp]
     lib.gvs_stereo_match_batch.argtypes = [vp, i32]
@@ -245,6 +246,15 @@ class FeatureExtractor:
 
     def level_kept(self, image: int, level: int):
         return self._level_keys(self._lib.gvs_debug_level_kept, image, level)
+
+    def debug_select(self, level: int, x, y, score):
+        """Selection stage alone on a caller-made candidate list: (sorted permutation or None, kept input indices)."""
+        x = np.ascontiguousarray(x, np.int32); y = np.ascontiguousarray(y, np.int32); s = np.ascontiguousarray(score, np.int32)
+        n = len(x)
+        sidx = np.zeros(max(n, 1), np.int32); kept = np.zeros(max(n, 1), np.int32)
+        nk = C.c_int(0)
+        _check(self._lib.gvs_debug_select(self.h, level, n, _p(x), _p(y), _p(s), _p(sidx), _p(kept), max(n, 1), C.byref(nk)))
+        return (sidx[:n] if n and sidx[0] >= 0 else None), kept[:nk.value].copy()
 
     def enable_timing(self, on: bool = True) -> None:
         _check(self._lib.gvs_extractor_enable_timing(self.h, int(on)))

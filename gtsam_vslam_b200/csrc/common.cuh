@@ -81,8 +81,8 @@ void launchPyramid(const Geometry& g, uint8_t* slab, const ResizeTap* taps, int 
 void launchFast(const Geometry& g, const uint8_t* slab, const FastItem* items, int nItems, int nImages, CandRec* recs,
                 int* nCand, unsigned short* cellCnt, int* status, cudaStream_t s, int* launches);
 void launchSelect(const Geometry& g, int nImages, const CandRec* recs, const int* nCand, const unsigned short* cellCnt,
-                  KeptKey* kept, int* keptCnt, unsigned* orderedDbg, uint8_t* scratch, size_t scratchPerCta, int nCtas,
-                  int* workCounter, int* status, cudaStream_t s, int* launches);
+                  KeptKey* kept, int* keptCnt, unsigned* orderedDbg, unsigned* sortedDbg, uint8_t* scratch,
+                  size_t scratchPerCta, int nCtas, int* workCounter, int* status, cudaStream_t s, int* launches);
 size_t selectScratchBytes(const Geometry& g);
 int selectMaxCtas(int device);
 void launchOffsets(const Geometry& g, int nImages, const int* keptCnt, int* imgOff, int totalCap, int* status,

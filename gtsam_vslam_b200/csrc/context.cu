@@ -55,6 +55,7 @@ struct gvs_extractor {
     int* keptCnt = nullptr;
     int* imgOff = nullptr;
     unsigned* orderedDbg = nullptr;
+    unsigned* sortedDbg = nullptr;
     int* momentsDbg = nullptr;
     uint8_t* selScratch = nullptr;
     size_t selScratchPerCta = 0;
@@ -259,7 +260,7 @@ void destroyExtractor(gvs_extractor* fe) {
     if (fe->ownStream) cudaStreamSynchronize(fe->ownStream);
     cudaFree(fe->slab); cudaFree(fe->blurSlab); cudaFree(fe->taps); cudaFree(fe->fastItems); cudaFree(fe->blurItems);
     cudaFree(fe->recs); cudaFree(fe->nCand); cudaFree(fe->cellCnt); cudaFree(fe->kept); cudaFree(fe->keptCnt);
-    cudaFree(fe->imgOff); cudaFree(fe->orderedDbg); cudaFree(fe->momentsDbg); cudaFree(fe->selScratch);
+    cudaFree(fe->imgOff); cudaFree(fe->orderedDbg); cudaFree(fe->sortedDbg); cudaFree(fe->momentsDbg); cudaFree(fe->selScratch);
     cudaFree(fe->workCounter); cudaFree(fe->status); cudaFree(fe->kps); cudaFree(fe->desc);
     if (fe->hOff) cudaFreeHost(fe->hOff);
     if (fe->hStatus) cudaFreeHost(fe->hStatus);
@@ -281,7 +282,7 @@ int runExtract(gvs_extractor* fe, int n) {
     if (T) cudaEventRecord(fe->ev[1], s);
     launchFast(g, fe->slab, fe->fastItems, fe->nFastItems, n, fe->recs, fe->nCand, fe->cellCnt, fe->status, s, &fe->launches);
     if (T) cudaEventRecord(fe->ev[2], s);
-    launchSelect(g, n, fe->recs, fe->nCand, fe->cellCnt, fe->kept, fe->keptCnt, fe->orderedDbg, fe->selScratch,
+    launchSelect(g, n, fe->recs, fe->nCand, fe->cellCnt, fe->kept, fe->keptCnt, fe->orderedDbg, nullptr, fe->selScratch,
                  fe->selScratchPerCta, fe->selCtas, fe->workCounter, fe->status, s, &fe->launches);
     launchOffsets(g, n, fe->keptCnt, fe->imgOff, fe->totalCap, fe->status, s, &fe->launches);
     if (T) cudaEventRecord(fe->ev[3], s);
@@ -622,6 +623,61 @@ int gvs_debug_level_kept(gvs_extractor* fe, int image, int level, int32_t* x, in
     GVS_CUDA_OK(cudaMemcpy(v.data(), fe->kept + (size_t)image * fe->g.keptPerImage + lv.keptOff, sizeof(unsigned) * cnt,
                            cudaMemcpyDeviceToHost));
     return unpackKeys(v, cnt, x, y, score);
+}
+
+int gvs_debug_select(gvs_extractor* fe, int level, int n, const int32_t* x, const int32_t* y, const int32_t* score,
+                     int32_t* sorted_idx, int32_t* kept_idx, int cap, int* n_kept) {
+    if (!fe || !x || !y || !score || !kept_idx || !n_kept || level < 0 || level >= fe->g.nLevels) return fail(GVS_ERR_INVALID, "bad argument");
+    const LevelGeom& lv = fe->g.lv[level];
+    if (n < 0 || n > lv.candCap || n > 65535) return fail(GVS_ERR_CAPACITY, "more candidates than the level's record buffer (or 65535)");
+    GVS_CUDA_OK(cudaSetDevice(fe->device));
+    cudaStream_t s = fe->stream;
+    GVS_CUDA_OK(cudaStreamSynchronize(s));
+    const Geometry& g = fe->g;
+    if (!fe->sortedDbg) GVS_CUDA_OK(devAlloc(&fe->sortedDbg, (size_t)fe->maxImages * g.candPerImage));
+    if (!fe->orderedDbg) GVS_CUDA_OK(devAlloc(&fe->orderedDbg, (size_t)fe->maxImages * g.candPerImage));
+    // all candidates in cell 0 with rank = input position, every other cell / level empty
+    std::vector<CandRec> recs(std::max(n, 1));
+    for (int i = 0; i < n; i++) {
+        if (x[i] < 0 || x[i] >= lv.w || y[i] < 0 || y[i] >= lv.h || score[i] < 1 || score[i] > 254) return fail(GVS_ERR_INVALID, "candidate out of range");
+        recs[i].w0 = (unsigned)x[i] | ((unsigned)y[i] << 12) | ((unsigned)score[i] << 24);
+        recs[i].w1 = (unsigned)i << 16;
+    }
+    std::vector<unsigned short> cells(std::max(g.cellsPerImage, 1), 0);
+    if (lv.nCols * lv.nRows < 1) return fail(GVS_ERR_INVALID, "level has no FAST cells");
+    cells[lv.cellBase] = (unsigned short)n;
+    std::vector<int> nc(kMaxLevels, 0);
+    nc[level] = n;
+    GVS_CUDA_OK(cudaMemcpyAsync(fe->recs + lv.candOff, recs.data(), sizeof(CandRec) * n, cudaMemcpyHostToDevice, s));
+    GVS_CUDA_OK(cudaMemcpyAsync(fe->cellCnt, cells.data(), sizeof(unsigned short) * cells.size(), cudaMemcpyHostToDevice, s));
+    GVS_CUDA_OK(cudaMemcpyAsync(fe->nCand, nc.data(), sizeof(int) * kMaxLevels, cudaMemcpyHostToDevice, s));
+    GVS_CUDA_OK(cudaMemsetAsync(fe->status, 0, sizeof(int), s));
+    int launches = 0;
+    launchSelect(g, 1, fe->recs, fe->nCand, fe->cellCnt, fe->kept, fe->keptCnt, fe->orderedDbg, fe->sortedDbg, fe->selScratch,
+                 fe->selScratchPerCta, fe->selCtas, fe->workCounter, fe->status, s, &launches);
+    fe->launchesTotal += launches;
+    int cnt = 0, st = 0;
+    GVS_CUDA_OK(cudaMemcpyAsync(&cnt, fe->keptCnt + level, sizeof(int), cudaMemcpyDeviceToHost, s));
+    GVS_CUDA_OK(cudaMemcpyAsync(&st, fe->status, sizeof(int), cudaMemcpyDeviceToHost, s));
+    GVS_CUDA_OK(cudaStreamSynchronize(s));
+    GVS_CUDA_OK(cudaGetLastError());
+    fe->lastN = 0;  // the batch state of the handle is gone
+    if (st) return fail(GVS_ERR_CAPACITY, "selection overflow");
+    *n_kept = cnt;
+    if (cnt > cap) return fail(GVS_ERR_CAPACITY, "caller buffer too small");
+    std::vector<unsigned> sorted(std::max(n, 1)), kept(std::max(cnt, 1));
+    GVS_CUDA_OK(cudaMemcpy(kept.data(), fe->kept + lv.keptOff, sizeof(unsigned) * cnt, cudaMemcpyDeviceToHost));
+    if (n > lv.quota) {
+        GVS_CUDA_OK(cudaMemcpy(sorted.data(), fe->sortedDbg + lv.candOff, sizeof(unsigned) * n, cudaMemcpyDeviceToHost));
+        if (sorted_idx) for (int i = 0; i < n; i++) sorted_idx[i] = (int)sorted[i];
+    } else if (sorted_idx) {
+        for (int i = 0; i < n; i++) sorted_idx[i] = -1;  // the reference does not sort when n <= quota
+    }
+    // map kept keys back to input indices (x, y are unique per candidate in FAST output; fall back to first match)
+    std::vector<int> lut((size_t)lv.w * lv.h, -1);
+    for (int i = n - 1; i >= 0; i--) lut[(size_t)y[i] * lv.w + x[i]] = i;
+    for (int i = 0; i < cnt; i++) kept_idx[i] = lut[(size_t)((kept[i] >> 12) & 0xfff) * lv.w + (kept[i] & 0xfff)];
+    return GVS_OK;
 }
 
 // ------------------------------------------------------------------ matcher

@@ -453,7 +453,8 @@ template <typename IdxT, bool kSmall>
 __global__ void __launch_bounds__(kSelThreads)
 select_kernel(const __grid_constant__ Geometry g, int nImages, const CandRec* __restrict__ recs,
               const int* __restrict__ nCand, const unsigned short* __restrict__ cellCnt, KeptKey* __restrict__ kept,
-              int* __restrict__ keptCnt, unsigned* __restrict__ orderedDbg, uint8_t* __restrict__ scratch,
+              int* __restrict__ keptCnt, unsigned* __restrict__ orderedDbg, unsigned* __restrict__ sortedDbg,
+              uint8_t* __restrict__ scratch,
               size_t scratchPerCta, int* __restrict__ workCounter, int* __restrict__ status, int maxCells, int segCap,
               int nMaxGlobal) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -547,6 +548,10 @@ select_kernel(const __grid_constant__ Geometry g, int nImages, const CandRec* __
         sortDescending(A, S, n);
         const IdxT* sorted = A.tmp;
         IdxT* res = A.idx;
+        if (sortedDbg) {  // parity tap: the permutation itself and, after ssc, the kept positions
+            unsigned* o = sortedDbg + (size_t)img * g.candPerImage + lv.candOff;
+            for (int i = tid; i < n; i += kSelThreads) o[i] = (unsigned)sorted[i];
+        }
 
         // ---- (c) ssc binary search (src/FeatureExtractor.cpp:396-461)
         const int K = lv.quota;
@@ -601,8 +606,8 @@ int selectMaxCtas(int device) {
 }
 
 void launchSelect(const Geometry& g, int nImages, const CandRec* recs, const int* nCand, const unsigned short* cellCnt,
-                  KeptKey* kept, int* keptCnt, unsigned* orderedDbg, uint8_t* scratch, size_t scratchPerCta, int nCtas,
-                  int* workCounter, int* status, cudaStream_t s, int* launches) {
+                  KeptKey* kept, int* keptCnt, unsigned* orderedDbg, unsigned* sortedDbg, uint8_t* scratch,
+                  size_t scratchPerCta, int nCtas, int* workCounter, int* status, cudaStream_t s, int* launches) {
     int maxCells = 0;
     for (int l = 0; l < g.nLevels; l++) maxCells = std::max(maxCells, g.lv[l].nCols * g.lv[l].nRows);
     const int segCapSmall = kSmallMax / 17 + 2;
@@ -618,15 +623,15 @@ void launchSelect(const Geometry& g, int nImages, const CandRec* recs, const int
     const int grid = std::min(nCtas, nProb);
     cudaMemsetAsync(workCounter, 0, 2 * sizeof(int), s);
     select_kernel<unsigned short, true><<<grid, kSelThreads, smSmall, s>>>(
-        g, nImages, recs, nCand, cellCnt, kept, keptCnt, orderedDbg, scratch, scratchPerCta, workCounter, status, maxCells,
-        segCapSmall, maxCandCap(g));
+        g, nImages, recs, nCand, cellCnt, kept, keptCnt, orderedDbg, sortedDbg, scratch, scratchPerCta, workCounter, status,
+        maxCells, segCapSmall, maxCandCap(g));
     ++*launches;
     bool needBig = false;
     for (int l = 0; l < g.nLevels; l++) needBig |= g.lv[l].candCap > kSmallMax;
     if (needBig) {
         select_kernel<unsigned, false><<<grid, kSelThreads, smBig, s>>>(
-            g, nImages, recs, nCand, cellCnt, kept, keptCnt, orderedDbg, scratch, scratchPerCta, workCounter + 1, status,
-            maxCells, 1, maxCandCap(g));
+            g, nImages, recs, nCand, cellCnt, kept, keptCnt, orderedDbg, sortedDbg, scratch, scratchPerCta, workCounter + 1,
+            status, maxCells, 1, maxCandCap(g));
         ++*launches;
     }
 }

@@ -117,6 +117,14 @@ int gvs_debug_level_candidates(gvs_extractor* fe, int image, int level, int32_t*
 /* Keys of a level after ssc (:609-613) in output order, with the integer moments of computeOrientation. */
 int gvs_debug_level_kept(gvs_extractor* fe, int image, int level, int32_t* x, int32_t* y, int32_t* score, int cap, int* n);
 
+/* Run the selection stage alone (ordering + cv::sortIdx emulation + ssc, src/FeatureExtractor.cpp:368-468) on a
+ * caller-made candidate list of pyramid level `level` (n candidates in emission order, x/y inside the level,
+ * score in [1,254]).  Outputs: sorted_idx (n entries, may be NULL) = the permutation cv::sortIdx(SORT_DESCENDING)
+ * returns for these scores; kept_idx (cap entries) = indices into the input list of the keys ssc keeps, in
+ * output order (all n in input order when n <= featurePerLevel[level]).  Overwrites the handle's last batch. */
+int gvs_debug_select(gvs_extractor* fe, int level, int n, const int32_t* x, const int32_t* y, const int32_t* score,
+                     int32_t* sorted_idx, int32_t* kept_idx, int cap, int* n_kept);
+
 /* ------------------------------------------------------------------ FeatureMatcher ------------------ */
 
 /* FeatureMatcher::FeatureMatcher, src/FeatureMatcher.cpp:8.  fx = zedptr->mCameraLeft->fx (double,

@@ -96,6 +96,14 @@ class Extractor:
         lib().ora_level_keys(self.h, level, int(kept), _p(x), _p(y), _p(r), _p(a), _p(m10), _p(m01))
         return dict(x=x, y=y, response=r, angle=a, m10=m10, m01=m01)
 
+    def ssc(self, numRetPoints: int, cols: int, rows: int, x, y, resp):
+        """FeatureExtractor::ssc (reference src/FeatureExtractor.cpp:368-468): (sorted permutation, kept input indices)."""
+        x = np.ascontiguousarray(x, np.int32); y = np.ascontiguousarray(y, np.int32); r = np.ascontiguousarray(resp, np.float32)
+        n = len(x)
+        out = np.zeros(max(n, 1), np.int32); srt = np.zeros(max(n, 1), np.int32)
+        k = lib().ora_ssc(self.h, numRetPoints, cols, rows, n, _p(x), _p(y), _p(r), _p(out), _p(srt))
+        return srt[:n].copy(), out[:k].copy()
+
     def ssc_passes(self, level: int) -> int:
         return lib().ora_level_ssc_passes(self.h, level)
 

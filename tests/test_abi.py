@@ -1,0 +1,59 @@
+"""CPU: the C-ABI library loads and exports every symbol include/gvs.h declares; compute calls fail loudly
+without a CUDA device (there is no CPU fallback)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import gtsam_vslam_b200 as gvs
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "gvs.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(gvs_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = gvs.load_library()
+    names = _header_functions()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), f"{n} is declared in include/gvs.h but not exported by libgvs.so"
+    assert sorted(gvs.SYMBOLS) == names  # the python binding list is complete too
+
+
+def test_keypoint_layout_is_cv_keypoint():
+    assert gvs.KEYPOINT_DTYPE.itemsize == 28
+    assert [gvs.KEYPOINT_DTYPE.fields[n][1] for n in ("x", "y", "size", "angle", "response", "octave", "class_id")] == [0, 4, 8, 12, 16, 20, 24]
+
+
+def test_no_cpu_fallback():
+    if gvs.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(gvs.GvsError, match="no CUDA device"):
+        gvs.FeatureExtractor(width=752, height=480)
+
+
+def test_product_does_not_import_oracle():
+    """The product path must never route through oracle/ (only tests, smoke and the bench baseline may)."""
+    pkg = os.path.join(ROOT, "gtsam_vslam_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")) or f == "Makefile":
+                txt = open(os.path.join(dp, f), errors="ignore").read()
+                assert "oracle" not in txt.replace("oracle/ (", ""), f"{f} mentions oracle"
+    for f in ("gvs.h", "gvs_adapter.hpp"):
+        p = os.path.join(ROOT, "include", f)
+        if os.path.exists(p):
+            assert "cpu_ref" not in open(p).read()
+
+
+def test_bad_arguments_are_reported():
+    lib = gvs.load_library()
+    assert lib.gvs_extractor_destroy(None) == 0
+    assert lib.gvs_extractor_sync(None) != 0
+    assert b"null" in lib.gvs_last_error()

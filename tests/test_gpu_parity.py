@@ -1,0 +1,321 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI, against the oracle and the golden fixtures.
+
+Bars: keypoint coordinates, FAST scores, octaves, descriptors, match indices, grids: bit exact.  Orientation,
+sub-pixel disparity -> depth: the kernels use the same un-fused float32 operation order as the oracle, so they
+are compared bit exact as well; the stated tolerances of the north star (1e-4 rad, 1e-3 px) are asserted too so
+that a future relaxation has a written bound.
+"""
+import hashlib
+import math
+import os
+
+import numpy as np
+import pytest
+
+import gtsam_vslam_b200 as gvs
+from gtsam_vslam_b200 import synth
+from oracle import cpu_ref
+
+pytestmark = pytest.mark.gpu
+
+ANGLE_TOL_DEG = math.degrees(1e-4)
+DEPTH_REL_TOL = 1e-5
+
+
+def _handles(cfg, n, **kw):
+    w, h = cfg["width"], cfg["height"]
+    args = dict(nFeatures=cfg["n_features"], nLevels=cfg["n_levels"], width=w, height=h, max_images=n)
+    args.update(kw)
+    feL, feR = gvs.FeatureExtractor(**args), gvs.FeatureExtractor(**args)
+    return feL, feR, gvs.FeatureMatcher(cfg["fx"], cfg["baseline"], feL, feR, h)
+
+
+def _oracle_frame(cfg, L, R):
+    args = dict(nFeatures=cfg["n_features"], nLevels=cfg["n_levels"])
+    oL, oR = cpu_ref.Extractor(**args), cpu_ref.Extractor(**args)
+    kl, dl = oL.extractKeysNew(L); kr, dr = oR.extractKeysNew(R)
+    s = cpu_ref.stereo_match(oL, oR, cfg["fx"], cfg["baseline"], cfg["height"], kl, dl, kr, dr)
+    return oL, oR, kl, dl, kr, dr, s
+
+
+def _assert_keys(gk, gd, ok, od):
+    assert len(gk) == len(ok)
+    for f in ("x", "y", "size", "response", "octave", "class_id"):
+        assert np.array_equal(gk[f], ok[f]), f
+    assert np.max(np.abs(gk["angle"] - ok["angle"]), initial=0) <= ANGLE_TOL_DEG
+    assert np.array_equal(gk["angle"], ok["angle"])
+    assert np.array_equal(gd, od)
+
+
+def _assert_frame(fm, f, cfg, kl, dl, kr, dr, s):
+    w, h = cfg["width"], cfg["height"]
+    k = gvs.tracked_keys(fm, f, w, h)
+    _assert_keys(k.keyPoints, k.Desc, kl, dl)
+    _assert_keys(k.rightKeyPoints, k.rightDesc, kr, dr)
+    assert np.array_equal(k.rightIdxs, s["rightIdxs"]) and np.array_equal(k.leftIdxs, s["leftIdxs"])
+    m = s["rightIdxs"] >= 0
+    assert np.all(np.abs(k.estimatedDepth[m] - s["estimatedDepth"][m]) <= DEPTH_REL_TOL * s["estimatedDepth"][m])
+    assert np.array_equal(k.estimatedDepth, s["estimatedDepth"]) and np.array_equal(k.close, s["close"])
+    for side, kk, gg in ((0, kl, k.lkeyGrid), (1, kr, k.rkeyGrid)):
+        o = cpu_ref.assign_grid(kk, w, h)
+        assert gg["yGrids"] == o["yGrids"] and gg["xMult"] == o["xMult"] and gg["yMult"] == o["yMult"]
+        assert np.array_equal(gg["start"], o["start"]) and np.array_equal(gg["items"], o["items"])
+    return k
+
+
+@pytest.mark.parametrize("name", ["small_s0", "small_s1_ramp", "euroc_s0", "kitti_s0"])
+def test_golden_fixture(name, golden_dir):
+    """CUDA path vs the committed fixtures (made with cv2 under the reference's control flow)."""
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    cfg = synth.CONFIGS[str(g["cfg"])]
+    L, R = synth.stereo_pair(cfg["width"], cfg["height"], cfg["disparity"], int(g["seed"]), ramp=bool(g["ramp"]))
+    assert hashlib.sha256(L.tobytes()).hexdigest() == str(g["sha_left"])
+    feL, feR, fm = _handles(cfg, 1)
+    k = gvs.extractORBAndStereoMatch(fm, L, R)
+    _assert_keys(k.keyPoints, k.Desc, g["kpL"], g["descL"])
+    _assert_keys(k.rightKeyPoints, k.rightDesc, g["kpR"], g["descR"])
+    assert np.array_equal(k.rightIdxs, g["rightIdxs"]) and np.array_equal(k.leftIdxs, g["leftIdxs"])
+    assert np.array_equal(k.estimatedDepth, g["depth"]) and np.array_equal(k.close, g["close"])
+    assert np.array_equal(k.lkeyGrid["start"], g["gridL_start"]) and np.array_equal(k.lkeyGrid["items"], g["gridL_items"])
+    assert np.array_equal(k.rkeyGrid["start"], g["gridR_start"]) and np.array_equal(k.rkeyGrid["items"], g["gridR_items"])
+    for l in range(cfg["n_levels"]):
+        assert hashlib.sha256(feL.level_image(0, l).tobytes()).hexdigest() == str(g["pyr_sha"][l])
+    assert np.array_equal(feL.scalePyramid, g["scalePyramid"]) and np.array_equal(feL.featurePerLevel, g["featurePerLevel"])
+
+
+@pytest.mark.parametrize("cfgname,seeds", [("small", [20, 21, 22, 23]), ("euroc", [5, 6]), ("kitti", [7])])
+def test_stages_against_oracle(cfgname, seeds):
+    """Stage by stage on fresh seeds: pyramid, blur, ordered FAST candidates, SSC selection, then everything."""
+    cfg = synth.CONFIGS[cfgname]
+    w, h = cfg["width"], cfg["height"]
+    Ls, Rs = synth.stereo_batch(w, h, cfg["disparity"], seeds)
+    feL, feR, fm = _handles(cfg, len(seeds))
+    fm.track_stereo_batch(Ls, Rs)
+    for f in range(len(seeds)):
+        oL, oR, kl, dl, kr, dr, s = _oracle_frame(cfg, Ls[f], Rs[f])
+        for fe, o in ((feL, oL), (feR, oR)):
+            for l in range(cfg["n_levels"]):
+                assert np.array_equal(fe.level_image(f, l), o.level_image(l)), ("pyramid", l)
+                assert np.array_equal(fe.level_image(f, l, True), o.level_image(l, True)), ("blur", l)
+                x, y, sc = fe.level_candidates(f, l); c = o.level_keys(l, False)
+                assert np.array_equal(x, c["x"]) and np.array_equal(y, c["y"]) and np.array_equal(sc, c["response"].astype(np.int32)), ("cand", l)
+                x, y, sc = fe.level_kept(f, l); c = o.level_keys(l, True)
+                assert np.array_equal(x, c["x"]) and np.array_equal(y, c["y"]) and np.array_equal(sc, c["response"].astype(np.int32)), ("kept", l)
+        _assert_frame(fm, f, cfg, kl, dl, kr, dr, s)
+
+
+def test_single_image_api_and_tables():
+    """gvs_extract == FeatureExtractor::extractKeysNew; public tables == the reference constructor's."""
+    cfg = synth.CONFIGS["euroc"]
+    L, _ = synth.stereo_pair(cfg["width"], cfg["height"], cfg["disparity"], 9)
+    fe = gvs.FeatureExtractor(nFeatures=2000, width=cfg["width"], height=cfg["height"])  # mono default ctor (System.cpp:31)
+    o = cpu_ref.Extractor(2000)
+    kp, d = fe.extractKeysNew(L)
+    ok, od = o.extractKeysNew(L)
+    _assert_keys(kp, d, ok, od)
+    for a in ("scalePyramid", "scaleInvPyramid", "sigmaFactor", "InvSigmaFactor", "scaledPatchSize", "featurePerLevel"):
+        assert np.array_equal(getattr(fe, a), getattr(o, a)), a
+    assert fe.featurePerLevel.tolist() == [434, 362, 302, 251, 209, 175, 145, 122]
+
+
+def test_edge_cases_blank_and_sparse_images():
+    cfg = synth.CONFIGS["small"]
+    w, h = cfg["width"], cfg["height"]
+    fe = gvs.FeatureExtractor(nFeatures=300, nLevels=4, width=w, height=h)
+    o = cpu_ref.Extractor(300, 4)
+    # blank image: no corner anywhere -> zero keypoints, outputs untouched (src/FeatureExtractor.cpp:498-499)
+    kp, d = fe.extractKeysNew(np.full((h, w), 77, np.uint8))
+    assert len(kp) == 0 and len(d) == 0
+    # sparse image: fewer candidates than the quota on every level -> no ssc, emission order is kept (:610)
+    img = np.full((h, w), 40, np.uint8)
+    rng = np.random.default_rng(1)
+    for _ in range(12):
+        x, y = int(rng.integers(30, w - 60)), int(rng.integers(30, h - 60))
+        img[y:y + 17, x:x + 23] = 200
+    kp, d = fe.extractKeysNew(img)
+    ok, od = o.extractKeysNew(img)
+    assert 0 < len(ok) < 300
+    _assert_keys(kp, d, ok, od)
+    # weak corners only: every cell falls back to the min threshold (cv::FAST(.., 7), :592-593)
+    img2 = (40 + 12 * ((np.add.outer(np.arange(h) // 9, np.arange(w) // 9) % 2))).astype(np.uint8)
+    kp, d = fe.extractKeysNew(img2)
+    ok, od = o.extractKeysNew(img2)
+    assert len(ok) > 0 and ok["response"].max() < 20
+    _assert_keys(kp, d, ok, od)
+    # saturated noise: maximum corner density
+    img3 = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    kp, d = fe.extractKeysNew(img3)
+    ok, od = o.extractKeysNew(img3)
+    _assert_keys(kp, d, ok, od)
+
+
+def _killer(n):
+    k = n // 2
+    a = [0] * n
+    for i in range(1, k + 1):
+        if i % 2 == 1:
+            a[i - 1] = i; a[i] = k + i
+        a[k + i - 1] = 2 * i
+    return np.array(a)
+
+
+@pytest.mark.parametrize("case", ["ties2", "ties8", "wide", "sorted", "reversed", "equal", "organ", "killer", "tiny", "big"])
+def test_sort_and_ssc_emulation(case):
+    """The device emulation of cv::sortIdx (libstdc++ introsort incl. median-of-3, depth limit, heapsort) and of ssc
+    on crafted candidate lists, against std::sort / the oracle's ssc."""
+    cfg = synth.CONFIGS["kitti"]
+    fe = gvs.FeatureExtractor(nFeatures=2000, width=cfg["width"], height=cfg["height"])
+    o = cpu_ref.Extractor(2000)
+    lw, lh = fe.level_size(0)
+    rng = np.random.default_rng(abs(hash(case)) % 1000)
+    n = {"tiny": 500, "big": 20000, "killer": 6000}.get(case, 5000)
+    if case == "ties2": s = rng.integers(20, 22, n)
+    elif case == "ties8": s = rng.integers(7, 15, n)
+    elif case == "wide": s = rng.integers(7, 200, n)
+    elif case == "sorted": s = np.sort(rng.integers(7, 120, n))
+    elif case == "reversed": s = np.sort(rng.integers(7, 120, n))[::-1].copy()
+    elif case == "equal": s = np.full(n, 33)
+    elif case == "organ": s = np.concatenate([np.arange(n // 2), np.arange(n // 2)[::-1]]) % 200 + 7
+    elif case == "killer": s = _killer(n) * 240 // n + 7      # median-of-3 killer: exercises the heapsort fallback
+    else: s = rng.integers(7, 60, n)
+    s = np.clip(s, 1, 254).astype(np.int32)
+    n = len(s)
+    pos = rng.permutation((lw - 40) * (lh - 40))[:n]
+    x = (pos % (lw - 40) + 20).astype(np.int32); y = (pos // (lw - 40) + 20).astype(np.int32)
+    sidx, kept = fe.debug_select(0, x, y, s)
+    osrt, okept = o.ssc(int(fe.featurePerLevel[0]), lw, lh, x, y, s.astype(np.float32))
+    if n > fe.featurePerLevel[0]:
+        assert np.array_equal(sidx, osrt)
+        assert np.array_equal(kept, okept)
+    else:
+        assert np.array_equal(kept, np.arange(n))
+
+
+def test_ssc_small_widths_use_hash_grid():
+    """Few candidates above the quota force the binary search down to tiny widths (cell grid larger than shared memory)."""
+    cfg = synth.CONFIGS["kitti"]
+    fe = gvs.FeatureExtractor(nFeatures=2000, width=cfg["width"], height=cfg["height"])
+    o = cpu_ref.Extractor(2000)
+    lw, lh = fe.level_size(0)
+    rng = np.random.default_rng(3)
+    for n in (440, 480, 700):
+        pos = rng.permutation((lw - 40) * (lh - 40))[:n]
+        x = (pos % (lw - 40) + 20).astype(np.int32); y = (pos // (lw - 40) + 20).astype(np.int32)
+        s = rng.integers(7, 90, n).astype(np.int32)
+        sidx, kept = fe.debug_select(0, x, y, s)
+        osrt, okept = o.ssc(int(fe.featurePerLevel[0]), lw, lh, x, y, s.astype(np.float32))
+        assert np.array_equal(sidx, osrt) and np.array_equal(kept, okept), n
+
+
+def test_projection_matchers_against_golden_and_oracle(golden_dir):
+    g = np.load(os.path.join(golden_dir, "small_s0.npz")); p = np.load(os.path.join(golden_dir, "small_s0_proj.npz"))
+    cfg = synth.CONFIGS["small"]
+    w, h = cfg["width"], cfg["height"]
+    feL, feR, fm = _handles(cfg, 1)
+    gvs.extractORBAndStereoMatch(fm, g["left"], g["right"])
+    mps = {k[3:]: p[k] for k in p.files if k.startswith("mp_")}
+    nl, nr, M = len(g["kpL"]), len(g["kpR"]), len(mps["desc"])
+    for rad in (4, 10, 120):
+        mL = np.full(nl, -1, np.int32); mR = np.full(nr, -1, np.int32); mt = np.full((M, 2), -1, np.int32); mt[::17] = [3, -1]
+        n = fm.matchByProjectionRPred(mps, 0, mL, mR, mt, float(rad))
+        assert n == int(p[f"rpred_{rad}_n"]) and np.array_equal(mL, p[f"rpred_{rad}_mL"]) and np.array_equal(mR, p[f"rpred_{rad}_mR"])
+        assert np.array_equal(mt, p[f"rpred_{rad}_mt"])
+        mL = np.full(nl, -1, np.int32); mt = np.full((M, 2), -1, np.int32)
+        n = fm.matchByProjectionMono(mps, 0, mL, mt, float(rad))
+        assert n == int(p[f"mono_{rad}_n"]) and np.array_equal(mL, p[f"mono_{rad}_mL"]) and np.array_equal(mt, p[f"mono_{rad}_mt"])
+    last = dict(desc=g["descR"], predL=np.stack([g["kpR"]["x"], g["kpR"]["y"]], 1), scaleLevelL=g["kpR"]["octave"])
+    mL = np.full(nl, -1, np.int32); mt = np.full((nr, 2), -1, np.int32)
+    n = fm.matchByRadius(last, 0, mL, mt, 120.0)
+    assert n == int(p["radius_n"]) and np.array_equal(mL, p["radius_mL"]) and np.array_equal(mt[:, 0], p["radius_match"])
+
+
+def test_mono_temporal_config4():
+    """BASELINE config 4: 752x480 mono, default ctor (2000 features), M = previous frame's keys, rad 1200 and 10."""
+    cfg = synth.CONFIGS["mono"]
+    w, h = cfg["width"], cfg["height"]
+    seq = synth.shifted_sequence(w, h, 2, seed=4)
+    fe = gvs.FeatureExtractor(nFeatures=2000, width=w, height=h, max_images=2)
+    fm = gvs.FeatureMatcher(cfg["fx"], cfg["baseline"], fe, None, h)
+    fe.extract_batch(seq)
+    fm.assign_grids_batch(2, w, h)
+    off = fe.offsets(2)
+    k0, d0 = fe.download(0, 1, int(off[1]))
+    k1, d1 = fe.download(1, 1, int(off[2] - off[1]))
+    o = cpu_ref.Extractor(2000)
+    ok1, od1 = o.extractKeysNew(seq[1])
+    _assert_keys(k1, d1, ok1, od1)
+    rng = np.random.default_rng(0)
+    M = len(k0)
+    mps = dict(desc=d0, predL=np.stack([k0["x"] - 2, k0["y"] - 1], 1).astype(np.float32) + rng.normal(0, 1, (M, 2)).astype(np.float32),
+               scaleLevelL=k0["octave"].astype(np.int32), inFrame=np.ones(M, np.uint8))
+    for rad in (10.0, 1200.0):
+        mL = np.full(len(k1), -1, np.int32); mt = np.full((M, 2), -1, np.int32)
+        n = fm.matchByProjectionMono(mps, 1, mL, mt, rad)
+        oL = np.full(len(k1), -1, np.int32); ot = np.full((M, 2), -1, np.int32)
+        on = cpu_ref.match_projection(o, 1, mps, ok1, od1, None, None, None, None, w, h, rad, oL, None, ot)
+        assert n == on and np.array_equal(mL, oL) and np.array_equal(mt, ot), rad
+        assert n > 0.5 * M
+
+
+def test_descriptor_distance():
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, 256, (1000, 32), dtype=np.uint8); b = rng.integers(0, 256, (1000, 32), dtype=np.uint8)
+    b[:10] = a[:10]
+    cfg = synth.CONFIGS["small"]
+    feL, feR, fm = _handles(cfg, 1)
+    d = fm.DescriptorDistance(a, b)
+    assert np.array_equal(d, np.unpackbits(a ^ b, axis=1).sum(axis=1))
+
+
+def test_batch_invariance_and_idempotence_full_size():
+    """BASELINE configs[1] at its full batch size: a 256-frame batch gives, frame by frame, exactly what single-frame
+    calls give (frames are independent), twice in a row (idempotence), with sorted responses inside each level."""
+    cfg = synth.CONFIGS["euroc"]
+    w, h = cfg["width"], cfg["height"]
+    F = 256
+    base = synth.stereo_batch(w, h, cfg["disparity"], range(100, 108))
+    Ls = np.ascontiguousarray(np.tile(base[0], (F // 8, 1, 1))); Rs = np.ascontiguousarray(np.tile(base[1], (F // 8, 1, 1)))
+    feL, feR, fm = _handles(cfg, F)
+    digests = []
+    for _ in range(2):
+        fm.track_stereo_batch(Ls, Rs)
+        offL, offR = feL.offsets(F), feR.offsets(F)
+        kl, dl = feL.download(0, F, int(offL[F])); kr, dr = feR.download(0, F, int(offR[F]))
+        ridx, lidx, dep, cl = fm.stereo_download(0, F)
+        digests.append(hashlib.sha256(b"".join(a.tobytes() for a in (offL, offR, kl, dl, kr, dr, ridx, lidx, dep, cl))).hexdigest())
+    assert digests[0] == digests[1]
+    # frames f and f+8 are the same image: identical slices
+    for f in range(8):
+        a = slice(offL[f], offL[f + 1])
+        for rep in range(1, F // 8):
+            b = slice(offL[f + 8 * rep], offL[f + 8 * rep + 1])
+            assert kl[a].tobytes() == kl[b].tobytes() and dl[a].tobytes() == dl[b].tobytes()
+            assert ridx[a].tobytes() == ridx[b].tobytes() and dep[a].tobytes() == dep[b].tobytes()
+    # against the oracle on the 8 distinct frames
+    for f in range(8):
+        oL, oR, okl, odl, okr, odr, s = _oracle_frame(cfg, base[0][f], base[1][f])
+        _assert_keys(kl[offL[f]:offL[f + 1]], dl[offL[f]:offL[f + 1]], okl, odl)
+        assert np.array_equal(ridx[offL[f]:offL[f + 1]], s["rightIdxs"]) and np.array_equal(lidx[offR[f]:offR[f + 1]], s["leftIdxs"])
+    # size-independent properties: per level, responses of SSC-selected keys are non-increasing; octaves ascend
+    for f in range(0, F, 37):
+        k = kl[offL[f]:offL[f + 1]]
+        assert np.all(np.diff(k["octave"]) >= 0)
+        for l in range(cfg["n_levels"]):
+            r = k["response"][k["octave"] == l]
+            assert np.all(np.diff(r) <= 0)
+        m = ridx[offL[f]:offL[f + 1]]
+        li = lidx[offR[f]:offR[f + 1]]
+        # leftIdxs / rightIdxs are mutually consistent where both are set
+        j = np.nonzero(li >= 0)[0]
+        assert np.all(m[li[j]] == j)
+
+
+def test_errors_are_loud():
+    cfg = synth.CONFIGS["small"]
+    feL, feR, fm = _handles(cfg, 1)
+    with pytest.raises(gvs.GvsError):
+        fm.stereo_match_batch(1)  # nothing extracted yet
+    with pytest.raises(gvs.GvsError):
+        feL.extractKeysNew(np.zeros((10, 10), np.uint8))  # wrong size
+    with pytest.raises(gvs.GvsError):
+        gvs.FeatureExtractor(width=64, height=64)  # pyramid level smaller than the border

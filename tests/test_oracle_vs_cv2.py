@@ -1,0 +1,174 @@
+"""CPU: the scalar C++ oracle (oracle/cpu_ref.cpp) against the real OpenCV primitives (cv2) and against the
+committed golden fixtures made by oracle/ref_cv2.py.  This is what pins the oracle (the reference has no tests)."""
+import ctypes as C
+import hashlib
+import os
+
+import cv2
+import numpy as np
+import pytest
+
+from gtsam_vslam_b200 import synth
+from oracle import cpu_ref, ref_cv2
+
+cv2.setNumThreads(1)
+lib = cpu_ref.lib()
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+@pytest.mark.parametrize("shape", [(376, 1241), (480, 752), (105, 346), (61, 83), (240, 320)])
+def test_resize_linear_matches_cv2(shape):
+    rng = np.random.default_rng(shape[0])
+    src = rng.integers(0, 256, shape, dtype=np.uint8)
+    dh, dw = int(round(shape[0] / 1.2)), int(round(shape[1] / 1.2))
+    ref = cv2.resize(src, (dw, dh), interpolation=cv2.INTER_LINEAR)
+    out = np.zeros((dh, dw), np.uint8)
+    lib.ora_resize_linear(_p(src), shape[1], shape[0], _p(out), dw, dh)
+    assert np.array_equal(out, ref)
+
+
+@pytest.mark.parametrize("shape", [(313, 1034), (134, 210), (47, 53), (480, 752)])
+def test_gaussian_blur_matches_cv2(shape):
+    rng = np.random.default_rng(shape[1])
+    src = rng.integers(0, 256, shape, dtype=np.uint8)
+    ref = cv2.GaussianBlur(src.copy(), (7, 7), 2, None, 2, cv2.BORDER_REFLECT_101)
+    out = np.zeros(shape, np.uint8)
+    lib.ora_gaussian_blur7(_p(src), shape[1], shape[0], _p(out))
+    assert np.array_equal(out, ref)
+
+
+def test_fast_atan2_matches_cv2():
+    rng = np.random.default_rng(0)
+    ys = rng.integers(-1300000, 1300000, 20000); xs = rng.integers(-1300000, 1300000, 20000)
+    ys[:4] = [0, 0, 5, -5]; xs[:4] = [0, 7, 0, 0]
+    for y, x in zip(ys, xs):
+        assert lib.ora_fast_atan2(float(y), float(x)) == np.float32(cv2.fastAtan2(float(y), float(x)))
+
+
+@pytest.mark.parametrize("n,hi", [(1, 5), (16, 3), (17, 3), (100, 4), (5000, 60), (20000, 12)])
+def test_sort_idx_matches_cv2(n, hi):
+    rng = np.random.default_rng(n)
+    key = rng.integers(7, 7 + hi, n).astype(np.float32)
+    ref = cv2.sortIdx(key.reshape(1, -1), cv2.SORT_DESCENDING + cv2.SORT_EVERY_ROW)[0]
+    out = np.zeros(n, np.int32)
+    lib.ora_sort_idx_desc(_p(key), n, _p(out))
+    assert np.array_equal(out, ref)
+
+
+@pytest.mark.parametrize("t", [20, 7])
+def test_fast_detect_matches_cv2(t):
+    L, _ = synth.stereo_pair(320, 240, 8, 5)
+    det = cv2.FastFeatureDetector_create(t, True, cv2.FAST_FEATURE_DETECTOR_TYPE_9_16)
+    for (y0, y1, x0, x1) in [(0, 240, 0, 320), (16, 61, 16, 58), (100, 107, 30, 90), (50, 95, 200, 245)]:
+        sub = np.ascontiguousarray(L[y0:y1, x0:x1])
+        kps = det.detect(sub)
+        ref = [(int(k.pt[0]), int(k.pt[1]), int(k.response)) for k in kps]
+        cap = 100000
+        xs = np.zeros(cap, np.int32); ys = np.zeros(cap, np.int32); sc = np.zeros(cap, np.int32)
+        n = lib.ora_fast_detect(_p(sub), sub.shape[1], sub.shape[0], t, _p(xs), _p(ys), _p(sc), cap)
+        assert n == len(ref)
+        assert list(zip(xs[:n].tolist(), ys[:n].tolist(), sc[:n].tolist())) == ref  # same points, scores and order
+
+
+def test_constructor_tables():
+    # the only intrinsic known answers of the reference
+    e = cpu_ref.Extractor(2000)
+    assert e.umax.tolist() == [15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3]
+    assert e.featurePerLevel.tolist() == [434, 362, 302, 251, 209, 175, 145, 122]
+    assert cpu_ref.Extractor(1000).featurePerLevel.tolist() == [217, 181, 151, 126, 105, 87, 73, 60]
+    assert cpu_ref.Extractor(8000).featurePerLevel.tolist() == [1737, 1448, 1207, 1005, 838, 698, 582, 485]
+    r = ref_cv2.FeatureExtractor(2000)
+    assert np.array_equal(e.scalePyramid, r.scalePyramid) and np.array_equal(e.scaledPatchSize, r.scaledPatchSize)
+    assert np.array_equal(e.sigmaFactor, r.sigmaFactor) and np.array_equal(e.InvSigmaFactor, r.InvSigmaFactor)
+
+
+def _run_cpp(cfg, L, R):
+    args = dict(nFeatures=cfg["n_features"], nLevels=cfg["n_levels"])
+    oL, oR = cpu_ref.Extractor(**args), cpu_ref.Extractor(**args)
+    kl, dl = oL.extractKeysNew(L); kr, dr = oR.extractKeysNew(R)
+    s = cpu_ref.stereo_match(oL, oR, cfg["fx"], cfg["baseline"], cfg["height"], kl, dl, kr, dr)
+    return oL, oR, kl, dl, kr, dr, s
+
+
+def _check_against_golden(g, kl, dl, kr, dr, s, w, h):
+    for f in kl.dtype.names:
+        assert np.array_equal(kl[f], g["kpL"][f]), f
+        assert np.array_equal(kr[f], g["kpR"][f]), f
+    assert np.array_equal(dl, g["descL"]) and np.array_equal(dr, g["descR"])
+    assert np.array_equal(s["rightIdxs"], g["rightIdxs"]) and np.array_equal(s["leftIdxs"], g["leftIdxs"])
+    assert np.array_equal(s["estimatedDepth"], g["depth"]) and np.array_equal(s["close"], g["close"])
+    gl = cpu_ref.assign_grid(kl, w, h)
+    assert gl["yGrids"] == int(g["yGrids"]) and np.array_equal(gl["start"], g["gridL_start"]) and np.array_equal(gl["items"], g["gridL_items"])
+    gr = cpu_ref.assign_grid(kr, w, h)
+    assert np.array_equal(gr["start"], g["gridR_start"]) and np.array_equal(gr["items"], g["gridR_items"])
+    assert np.float32(gl["xMult"]) == g["xMult"] and np.float32(gl["yMult"]) == g["yMult"]
+
+
+@pytest.mark.parametrize("name", ["small_s0", "small_s1_ramp", "euroc_s0", "kitti_s0"])
+def test_cpp_oracle_matches_golden(name, golden_dir):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    cfg = synth.CONFIGS[str(g["cfg"])]
+    L, R = synth.stereo_pair(cfg["width"], cfg["height"], cfg["disparity"], int(g["seed"]), ramp=bool(g["ramp"]))
+    assert hashlib.sha256(L.tobytes()).hexdigest() == str(g["sha_left"])  # the generator is deterministic
+    assert hashlib.sha256(R.tobytes()).hexdigest() == str(g["sha_right"])
+    if "left" in g:
+        assert np.array_equal(L, g["left"]) and np.array_equal(R, g["right"])
+    oL, oR, kl, dl, kr, dr, s = _run_cpp(cfg, L, R)
+    for l in range(cfg["n_levels"]):
+        im = oL.level_image(l)
+        assert im.shape[::-1] == tuple(g["level_sizes"][l])
+        assert hashlib.sha256(im.tobytes()).hexdigest() == str(g["pyr_sha"][l])
+        assert len(oL.level_keys(l, False)["x"]) == int(g["candidates"][l])
+    _check_against_golden(g, kl, dl, kr, dr, s, cfg["width"], cfg["height"])
+
+
+def test_cpp_oracle_matches_cv2_oracle_live():
+    """End to end on a fresh seed (not a fixture): both oracles run here and must agree bit for bit."""
+    cfg = synth.CONFIGS["small"]
+    L, R = synth.stereo_pair(cfg["width"], cfg["height"], cfg["disparity"], 11)
+    feL = ref_cv2.FeatureExtractor(cfg["n_features"], cfg["n_levels"]); feR = ref_cv2.FeatureExtractor(cfg["n_features"], cfg["n_levels"])
+    fm = ref_cv2.FeatureMatcher(cfg["fx"], cfg["baseline"], feL, feR, cfg["height"])
+    k = ref_cv2.extractORBAndStereoMatch(feL, feR, fm, L, R, cfg["width"], cfg["height"])
+    oL, oR, kl, dl, kr, dr, s = _run_cpp(cfg, L, R)
+    for f in kl.dtype.names:
+        assert np.array_equal(kl[f], k.keyPoints[f]) and np.array_equal(kr[f], k.rightKeyPoints[f])
+    assert np.array_equal(dl, k.Desc) and np.array_equal(dr, k.rightDesc)
+    assert np.array_equal(s["rightIdxs"], k.rightIdxs) and np.array_equal(s["leftIdxs"], k.leftIdxs)
+    assert np.array_equal(s["estimatedDepth"], k.estimatedDepth) and np.array_equal(s["close"], k.close)
+    for l in range(cfg["n_levels"]):
+        assert np.array_equal(oL.level_image(l, True), cv2.GaussianBlur(feL.imagePyramid[l].copy(), (7, 7), 2, None, 2, cv2.BORDER_REFLECT_101))
+
+
+def test_cpp_projection_matchers_match_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "small_s0.npz")); p = np.load(os.path.join(golden_dir, "small_s0_proj.npz"))
+    cfg = synth.CONFIGS["small"]
+    w, h = cfg["width"], cfg["height"]
+    fe = cpu_ref.Extractor(nFeatures=cfg["n_features"], nLevels=cfg["n_levels"])
+    mps = {k[3:]: p[k] for k in p.files if k.startswith("mp_")}
+    nl, nr, M = len(g["kpL"]), len(g["kpR"]), len(mps["desc"])
+    for rad in (4, 10, 120):
+        mL = np.full(nl, -1, np.int32); mR = np.full(nr, -1, np.int32); mt = np.full((M, 2), -1, np.int32); mt[::17] = [3, -1]
+        n = cpu_ref.match_projection(fe, 0, mps, g["kpL"], g["descL"], g["kpR"], g["descR"], g["leftIdxs"], g["rightIdxs"], w, h,
+                                     float(rad), mL, mR, mt)
+        assert n == int(p[f"rpred_{rad}_n"]) and np.array_equal(mL, p[f"rpred_{rad}_mL"]) and np.array_equal(mR, p[f"rpred_{rad}_mR"])
+        assert np.array_equal(mt, p[f"rpred_{rad}_mt"])
+        mL = np.full(nl, -1, np.int32); mt = np.full((M, 2), -1, np.int32)
+        n = cpu_ref.match_projection(fe, 1, mps, g["kpL"], g["descL"], None, None, None, None, w, h, float(rad), mL, None, mt)
+        assert n == int(p[f"mono_{rad}_n"]) and np.array_equal(mL, p[f"mono_{rad}_mL"]) and np.array_equal(mt, p[f"mono_{rad}_mt"])
+    last = dict(desc=g["descR"], predL=np.stack([g["kpR"]["x"], g["kpR"]["y"]], 1), scaleLevelL=g["kpR"]["octave"])
+    mL = np.full(nl, -1, np.int32); mt = np.full((nr, 2), -1, np.int32)
+    n = cpu_ref.match_projection(fe, 2, last, g["kpL"], g["descL"], None, None, None, None, w, h, 120.0, mL, None, mt)
+    assert n == int(p["radius_n"]) and np.array_equal(mL, p["radius_mL"]) and np.array_equal(mt[:, 0], p["radius_match"])
+
+
+def test_analytic_depth():
+    """Constant-disparity pair: median depth = fx*b/d."""
+    g = synth.CONFIGS["kitti"]
+    L, R = synth.stereo_pair(g["width"], g["height"], 24, 2)
+    *_, s = _run_cpp(g, L, R)
+    m = s["rightIdxs"] >= 0
+    assert m.sum() > 500
+    assert abs(np.median(s["estimatedDepth"][m]) - g["fx"] * g["baseline"] / 24) < 0.05
