@@ -31,7 +31,7 @@ SYMBOLS = [
     "gvs_debug_level_image", "gvs_debug_level_candidates", "gvs_debug_level_kept", "gvs_debug_select",
     "gvs_matcher_create", "gvs_matcher_destroy", "gvs_stereo_match_batch", "gvs_stereo_download",
     "gvs_assign_grids_batch", "gvs_grid_download", "gvs_track_stereo_batch_host",
-    "gvs_track_stereo_batch_resident", "gvs_matcher_sync", "gvs_match_projection", "gvs_descriptor_distance",
+    "gvs_track_stereo_batch_resident", "gvs_matcher_sync", "gvs_matcher_set_stream", "gvs_match_projection", "gvs_descriptor_distance",
     "gvs_extractor_enable_timing", "gvs_extractor_stage_times", "gvs_matcher_launch_count",
     "gvs_extractor_launch_count",
 ]
@@ -98,6 +98,7 @@ def load_library() -> C.CDLL:
     lib.gvs_track_stereo_batch_host.argtypes = [vp, vp, vp, C.c_size_t, i32, i32, i32, i32]
     lib.gvs_track_stereo_batch_resident.argtypes = [vp, i32, i32, i32]
     lib.gvs_matcher_sync.argtypes = [vp]
+    lib.gvs_matcher_set_stream.argtypes = [vp, vp]
     lib.gvs_match_projection.argtypes = [vp, i32, i32, C.POINTER(_MapPoints), f32, vp, vp, vp, C.POINTER(i32)]
     lib.gvs_descriptor_distance.argtypes = [vp, vp, vp, i32, vp]
     lib.gvs_extractor_enable_timing.argtypes = [vp, i32]
@@ -219,6 +220,14 @@ class FeatureExtractor:
         _check(self._lib.gvs_extract_download(self.h, first, count, _p(kp), _p(desc), total))
         return kp[:total], desc[:total]
 
+    def download_into(self, first: int, count: int, kp: np.ndarray, desc: np.ndarray) -> int:
+        """Like download() but into caller arrays (use pinned memory for full PCIe speed); returns the key count."""
+        off = self.offsets(first + count)
+        total = int(off[first + count] - off[first])
+        assert kp.dtype == KEYPOINT_DTYPE and len(kp) >= total and desc.dtype == np.uint8 and desc.size >= total * 32
+        _check(self._lib.gvs_extract_download(self.h, first, count, _p(kp), _p(desc), len(kp)))
+        return total
+
     def set_stream(self, cuda_stream: int | None) -> None:
         _check(self._lib.gvs_extractor_set_stream(self.h, C.c_void_p(cuda_stream or 0)))
 
@@ -310,6 +319,9 @@ class FeatureMatcher:
         _check(self._lib.gvs_stereo_download(self.h, first, count, _p(ridx), _p(lidx), _p(dep), _p(cl)))
         return ridx[:nl], lidx[:nr], dep[:nl], cl[:nl].astype(bool)
 
+    def stereo_download_into(self, first: int, count: int, ridx, lidx, dep, cl) -> None:
+        _check(self._lib.gvs_stereo_download(self.h, first, count, _p(ridx), _p(lidx), _p(dep), _p(cl)))
+
     def assign_grids_batch(self, n_frames: int, width: int, height: int) -> None:
         _check(self._lib.gvs_assign_grids_batch(self.h, n_frames, width, height))
 
@@ -335,6 +347,9 @@ class FeatureMatcher:
 
     def sync(self) -> None:
         _check(self._lib.gvs_matcher_sync(self.h))
+
+    def set_stream(self, cuda_stream: int | None) -> None:
+        _check(self._lib.gvs_matcher_set_stream(self.h, C.c_void_p(cuda_stream or 0)))
 
     def launch_count(self) -> int:
         v = C.c_int64(0)

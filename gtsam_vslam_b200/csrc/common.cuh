@@ -78,6 +78,7 @@ struct StageTimer;
 
 // ---- kernel launchers (one translation unit each) -------------------------------------------------
 void launchPyramid(const Geometry& g, uint8_t* slab, const ResizeTap* taps, int nImages, cudaStream_t s, int* launches);
+void launchRepack(const Geometry& g, const uint8_t* tight, uint8_t* slab, int nImages, cudaStream_t s, int* launches);
 void launchFast(const Geometry& g, const uint8_t* slab, const FastItem* items, int nItems, int nImages, CandRec* recs,
                 int* nCand, unsigned short* cellCnt, int* status, cudaStream_t s, int* launches);
 void launchSelect(const Geometry& g, int nImages, const CandRec* recs, const int* nCand, const unsigned short* cellCnt,

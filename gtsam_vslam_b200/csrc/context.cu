@@ -39,10 +39,12 @@ struct gvs_extractor {
     std::vector<float> scale, invScale, sigma, invSigma;
     std::vector<int> patch, quota;
     cudaStream_t ownStream = nullptr, stream = nullptr;
-    cudaEvent_t doneEvent = nullptr;
+    cudaStream_t auxStream = nullptr;  // blur runs here, concurrently with FAST + selection
+    cudaEvent_t doneEvent = nullptr, evPyr = nullptr, evBlur = nullptr;
     // device
     uint8_t* slab = nullptr;
     uint8_t* blurSlab = nullptr;
+    uint8_t* tight = nullptr;   // staging for tightly packed host batches (one contiguous DMA, then repack)
     ResizeTap* taps = nullptr;
     FastItem* fastItems = nullptr;
     int nFastItems = 0;
@@ -98,7 +100,8 @@ struct gvs_matcher {
     float xMult = 0, yMult = 0;
     bool gridsValid = false, stereoValid = false;
     int lastFrames = 0;
-    cudaEvent_t evR = nullptr;
+    cudaEvent_t evR = nullptr, evFork = nullptr, evJoin = nullptr;
+    cudaStream_t callerStream = nullptr;  // optional: work is forked from / joined into this stream
     // projection scratch (grown on demand)
     uint8_t* pj = nullptr;
     size_t pjBytes = 0;
@@ -258,13 +261,16 @@ void destroyExtractor(gvs_extractor* fe) {
     if (!fe) return;
     cudaSetDevice(fe->device);
     if (fe->ownStream) cudaStreamSynchronize(fe->ownStream);
-    cudaFree(fe->slab); cudaFree(fe->blurSlab); cudaFree(fe->taps); cudaFree(fe->fastItems); cudaFree(fe->blurItems);
+    cudaFree(fe->slab); cudaFree(fe->blurSlab); cudaFree(fe->tight); cudaFree(fe->taps); cudaFree(fe->fastItems); cudaFree(fe->blurItems);
     cudaFree(fe->recs); cudaFree(fe->nCand); cudaFree(fe->cellCnt); cudaFree(fe->kept); cudaFree(fe->keptCnt);
     cudaFree(fe->imgOff); cudaFree(fe->orderedDbg); cudaFree(fe->sortedDbg); cudaFree(fe->momentsDbg); cudaFree(fe->selScratch);
     cudaFree(fe->workCounter); cudaFree(fe->status); cudaFree(fe->kps); cudaFree(fe->desc);
     if (fe->hOff) cudaFreeHost(fe->hOff);
     if (fe->hStatus) cudaFreeHost(fe->hStatus);
     if (fe->doneEvent) cudaEventDestroy(fe->doneEvent);
+    if (fe->evPyr) cudaEventDestroy(fe->evPyr);
+    if (fe->evBlur) cudaEventDestroy(fe->evBlur);
+    if (fe->auxStream) cudaStreamDestroy(fe->auxStream);
     for (auto& e : fe->ev) if (e) cudaEventDestroy(e);
     if (fe->ownStream) cudaStreamDestroy(fe->ownStream);
     delete fe;
@@ -280,14 +286,26 @@ int runExtract(gvs_extractor* fe, int n) {
     if (T) cudaEventRecord(fe->ev[0], s);
     launchPyramid(g, fe->slab, fe->taps, n, s, &fe->launches);
     if (T) cudaEventRecord(fe->ev[1], s);
+    // blur depends on the pyramid only: fork it onto the aux stream so that it overlaps FAST and selection.
+    // In timing mode every stage runs in order on the main stream so that the stage times are clean.
+    if (!T) {
+        GVS_CUDA_OK(cudaEventRecord(fe->evPyr, s));
+        GVS_CUDA_OK(cudaStreamWaitEvent(fe->auxStream, fe->evPyr, 0));
+        launchBlur(g, fe->slab, fe->blurSlab, fe->blurItems, fe->nBlurItems, n, fe->auxStream, &fe->launches);
+        GVS_CUDA_OK(cudaEventRecord(fe->evBlur, fe->auxStream));
+    }
     launchFast(g, fe->slab, fe->fastItems, fe->nFastItems, n, fe->recs, fe->nCand, fe->cellCnt, fe->status, s, &fe->launches);
     if (T) cudaEventRecord(fe->ev[2], s);
     launchSelect(g, n, fe->recs, fe->nCand, fe->cellCnt, fe->kept, fe->keptCnt, fe->orderedDbg, nullptr, fe->selScratch,
                  fe->selScratchPerCta, fe->selCtas, fe->workCounter, fe->status, s, &fe->launches);
     launchOffsets(g, n, fe->keptCnt, fe->imgOff, fe->totalCap, fe->status, s, &fe->launches);
-    if (T) cudaEventRecord(fe->ev[3], s);
-    launchBlur(g, fe->slab, fe->blurSlab, fe->blurItems, fe->nBlurItems, n, s, &fe->launches);
-    if (T) cudaEventRecord(fe->ev[4], s);
+    if (T) {
+        cudaEventRecord(fe->ev[3], s);
+        launchBlur(g, fe->slab, fe->blurSlab, fe->blurItems, fe->nBlurItems, n, s, &fe->launches);
+        cudaEventRecord(fe->ev[4], s);
+    } else {
+        GVS_CUDA_OK(cudaStreamWaitEvent(s, fe->evBlur, 0));
+    }
     launchDescribe(g, fe->slab, fe->blurSlab, n, fe->kept, fe->keptCnt, fe->imgOff, fe->kps, fe->desc, fe->momentsDbg,
                    fe->totalCap, s, &fe->launches);
     if (T) cudaEventRecord(fe->ev[5], s);
@@ -378,7 +396,10 @@ int gvs_extractor_create(gvs_extractor** out, const gvs_extractor_params* params
     } while (0)
     GVS_TRY(cudaStreamCreateWithFlags(&fe->ownStream, cudaStreamNonBlocking));
     fe->stream = fe->ownStream;
+    GVS_TRY(cudaStreamCreateWithFlags(&fe->auxStream, cudaStreamNonBlocking));
     GVS_TRY(cudaEventCreateWithFlags(&fe->doneEvent, cudaEventDisableTiming));
+    GVS_TRY(cudaEventCreateWithFlags(&fe->evPyr, cudaEventDisableTiming));
+    GVS_TRY(cudaEventCreateWithFlags(&fe->evBlur, cudaEventDisableTiming));
     for (auto& e : fe->ev) GVS_TRY(cudaEventCreate(&e));
     GVS_TRY(devAlloc(&fe->slab, B * g.slabBytes + 256));
     GVS_TRY(devAlloc(&fe->blurSlab, B * g.slabBytes + 256));
@@ -487,17 +508,14 @@ int gvs_extract_batch_host(gvs_extractor* fe, const uint8_t* images, size_t imag
     if (!images || row_stride < fe->width) return fail(GVS_ERR_INVALID, "bad image pointer / stride");
     GVS_CUDA_OK(cudaSetDevice(fe->device));
     const LevelGeom& l0 = fe->g.lv[0];
-    if (image_stride == (size_t)row_stride * fe->height) {
-        // one strided 3-D copy: rows of all images are `row_stride` apart in the source
-        cudaMemcpy3DParms p{};
-        p.srcPtr = make_cudaPitchedPtr(const_cast<uint8_t*>(images), row_stride, fe->width, fe->height);
-        p.dstPtr = make_cudaPitchedPtr(fe->slab + l0.off, l0.pitch, fe->width, fe->g.slabBytes / l0.pitch);
-        p.extent = make_cudaExtent(fe->width, fe->height, n_images);
-        p.kind = cudaMemcpyHostToDevice;
-        if (fe->g.slabBytes % l0.pitch == 0) {
-            GVS_CUDA_OK(cudaMemcpy3DAsync(&p, fe->stream));
-            return runExtract(fe, n_images);
-        }
+    if (row_stride == fe->width && image_stride == (size_t)fe->width * fe->height) {
+        // tightly packed batch: one contiguous DMA into a staging buffer, then a repack kernel into the pitched store
+        if (!fe->tight) GVS_CUDA_OK(devAlloc(&fe->tight, (size_t)fe->maxImages * fe->width * fe->height + 16));
+        GVS_CUDA_OK(cudaMemcpyAsync(fe->tight, images, (size_t)n_images * image_stride, cudaMemcpyHostToDevice, fe->stream));
+        int launches = 0;
+        launchRepack(fe->g, fe->tight, fe->slab, n_images, fe->stream, &launches);
+        fe->launchesTotal += launches;
+        return runExtract(fe, n_images);
     }
     for (int i = 0; i < n_images; i++)
         GVS_CUDA_OK(cudaMemcpy2DAsync(fe->slab + (size_t)i * fe->g.slabBytes + l0.off, l0.pitch, images + (size_t)i * image_stride,
@@ -698,7 +716,9 @@ int gvs_matcher_create(gvs_matcher** out, gvs_extractor* feL, gvs_extractor* feR
               devAlloc(&m->leftIdxs, (size_t)feR->totalCap) == cudaSuccess &&
               devAlloc(&m->cellStartL, B * (m->maxCells + 1)) == cudaSuccess && devAlloc(&m->cellStartR, B * (m->maxCells + 1)) == cudaSuccess &&
               devAlloc(&m->itemsL, (size_t)feL->totalCap) == cudaSuccess && devAlloc(&m->itemsR, (size_t)feR->totalCap) == cudaSuccess &&
-              devAlloc(&m->pjStatus, 2) == cudaSuccess && cudaEventCreateWithFlags(&m->evR, cudaEventDisableTiming) == cudaSuccess;
+              devAlloc(&m->pjStatus, 2) == cudaSuccess && cudaEventCreateWithFlags(&m->evR, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&m->evFork, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&m->evJoin, cudaEventDisableTiming) == cudaSuccess;
     for (auto& e : m->ev) ok = ok && cudaEventCreate(&e) == cudaSuccess;
     if (!ok) {
         int rc = fail(GVS_ERR_CUDA, "matcher allocation", cudaGetErrorString(cudaGetLastError()));
@@ -717,6 +737,8 @@ int gvs_matcher_destroy(gvs_matcher* m) {
     cudaFree(m->cellStartL); cudaFree(m->cellStartR); cudaFree(m->itemsL); cudaFree(m->itemsR); cudaFree(m->pj);
     cudaFree(m->pool); cudaFree(m->pjStatus);
     if (m->evR) cudaEventDestroy(m->evR);
+    if (m->evFork) cudaEventDestroy(m->evFork);
+    if (m->evJoin) cudaEventDestroy(m->evJoin);
     for (auto& e : m->ev) if (e) cudaEventDestroy(e);
     delete m;
     return GVS_OK;
@@ -727,6 +749,26 @@ static int joinRight(gvs_matcher* m) {  // make L's stream wait for R's last bat
         GVS_CUDA_OK(cudaEventRecord(m->evR, m->R->stream));
         GVS_CUDA_OK(cudaStreamWaitEvent(m->L->stream, m->evR, 0));
     }
+    return GVS_OK;
+}
+
+static int forkFromCaller(gvs_matcher* m) {
+    if (!m->callerStream) return GVS_OK;
+    GVS_CUDA_OK(cudaEventRecord(m->evFork, m->callerStream));
+    if (m->L->stream != m->callerStream) GVS_CUDA_OK(cudaStreamWaitEvent(m->L->stream, m->evFork, 0));
+    if (m->R != m->L && m->R->stream != m->callerStream) GVS_CUDA_OK(cudaStreamWaitEvent(m->R->stream, m->evFork, 0));
+    return GVS_OK;
+}
+static int joinIntoCaller(gvs_matcher* m) {
+    if (!m->callerStream || m->L->stream == m->callerStream) return GVS_OK;
+    GVS_CUDA_OK(cudaEventRecord(m->evJoin, m->L->stream));
+    GVS_CUDA_OK(cudaStreamWaitEvent(m->callerStream, m->evJoin, 0));
+    return GVS_OK;
+}
+
+int gvs_matcher_set_stream(gvs_matcher* m, void* cuda_stream) {
+    if (!m) return fail(GVS_ERR_INVALID, "null matcher");
+    m->callerStream = reinterpret_cast<cudaStream_t>(cuda_stream);
     return GVS_OK;
 }
 
@@ -842,26 +884,36 @@ int gvs_grid_download(gvs_matcher* m, int frame, int side, int32_t* cell_start, 
 int gvs_track_stereo_batch_resident(gvs_matcher* m, int n_frames, int width, int height) {
     if (!m) return fail(GVS_ERR_INVALID, "null matcher");
     if (m->R == m->L) return fail(GVS_ERR_STATE, "stereo tracking needs two extractors");
-    int rc = gvs_extract_batch_resident(m->L, n_frames);
+    GVS_CUDA_OK(cudaSetDevice(m->L->device));
+    int rc = forkFromCaller(m);
+    if (rc) return rc;
+    rc = gvs_extract_batch_resident(m->L, n_frames);
     if (rc) return rc;
     rc = gvs_extract_batch_resident(m->R, n_frames);
     if (rc) return rc;
     rc = gvs_stereo_match_batch(m, n_frames);
     if (rc) return rc;
-    return gvs_assign_grids_batch(m, n_frames, width, height);
+    rc = gvs_assign_grids_batch(m, n_frames, width, height);
+    if (rc) return rc;
+    return joinIntoCaller(m);
 }
 
 int gvs_track_stereo_batch_host(gvs_matcher* m, const uint8_t* left, const uint8_t* right, size_t image_stride, int row_stride,
                                 int n_frames, int width, int height) {
     if (!m) return fail(GVS_ERR_INVALID, "null matcher");
     if (m->R == m->L) return fail(GVS_ERR_STATE, "stereo tracking needs two extractors");
-    int rc = gvs_extract_batch_host(m->L, left, image_stride, row_stride, n_frames);
+    GVS_CUDA_OK(cudaSetDevice(m->L->device));
+    int rc = forkFromCaller(m);
+    if (rc) return rc;
+    rc = gvs_extract_batch_host(m->L, left, image_stride, row_stride, n_frames);
     if (rc) return rc;
     rc = gvs_extract_batch_host(m->R, right, image_stride, row_stride, n_frames);
     if (rc) return rc;
     rc = gvs_stereo_match_batch(m, n_frames);
     if (rc) return rc;
-    return gvs_assign_grids_batch(m, n_frames, width, height);
+    rc = gvs_assign_grids_batch(m, n_frames, width, height);
+    if (rc) return rc;
+    return joinIntoCaller(m);
 }
 
 int gvs_matcher_launch_count(gvs_matcher* m, int64_t* launches) {

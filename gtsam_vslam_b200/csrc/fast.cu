@@ -26,33 +26,83 @@
 namespace gvs {
 
 // ring offsets, OpenCV order
-__constant__ int8_t kRingDx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
-__constant__ int8_t kRingDy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+#define GVS_RING_DX {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1}
+#define GVS_RING_DY {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3}
 
 struct FastSmemLayout {
-    int tilePitch, tileRows;    // image tile (bytes per row, rows)
-    int scorePitch, scoreRows;  // score tile including a 1-px zero frame
+    int tileWords, tileRows;    // image tile: words per row, rows
+    int scoreWords, scoreRows;  // score tile: words per row (1 zero word each side), rows (1 zero row each side)
     int listCap;                // entries per cell list
-    int tileOff, scoreOff, listOff, total;
+    int tileOff, scoreOff, listOff, maskOff, total;
 };
 
 __host__ __device__ inline FastSmemLayout fastLayout(int maxGW, int maxGH) {
     FastSmemLayout L;
-    L.tilePitch = ((kFastCellsPerItem * maxGW + 6 + 3 + 3) / 4) * 4 + 4;
+    const int maxUnits = (kFastCellsPerItem * maxGW + 3 + 3) / 4 + 1;  // unit words covering [X0, X1)
+    L.tileWords = maxUnits + 2;
     L.tileRows = maxGH + 6;
-    L.scorePitch = ((kFastCellsPerItem * maxGW + 2 + 3) / 4) * 4;
+    L.scoreWords = maxUnits + 2;
     L.scoreRows = maxGH + 2;
     L.listCap = ((maxGW + 1) / 2) * ((maxGH + 1) / 2);
     L.tileOff = 0;
-    L.scoreOff = L.tileOff + L.tilePitch * L.tileRows;
-    L.listOff = ((L.scoreOff + L.scorePitch * L.scoreRows + 15) / 16) * 16;
+    L.scoreOff = L.tileOff + L.tileWords * L.tileRows * 4;
+    L.maskOff = L.scoreOff + L.scoreWords * L.scoreRows * 4;
+    L.listOff = ((L.maskOff + maxUnits * 12 + 15) / 16) * 16;
     L.total = L.listOff + kFastCellsPerItem * L.listCap * 4;
     return L;
 }
 
-__device__ __forceinline__ unsigned pair16(const uint8_t* p) { return (unsigned)p[0] | ((unsigned)p[1] << 16); }
+// u16x2 lanes = 257 * (byte q, byte q+1) of the 12-byte window {w0, w1, w2}; q is a compile-time constant
+template <int Q>
+__device__ __forceinline__ unsigned pairAt(unsigned w0, unsigned w1, unsigned w2) {
+    if (Q + 1 <= 7) return __byte_perm(w0, w1, Q | (Q << 4) | ((Q + 1) << 8) | ((Q + 1) << 12));
+    return __byte_perm(w1, w2, (Q - 4) | ((Q - 4) << 4) | ((Q - 3) << 8) | ((Q - 3) << 12));
+}
 
-__global__ void __launch_bounds__(256)
+// B = max over the 16 arcs of min of 9 consecutive, D = min over arcs of max of 9 consecutive (u16x2 lanes)
+__device__ __forceinline__ void arcMinMax(const unsigned (&r)[16], unsigned& B, unsigned& D) {
+    unsigned mn3[16], mx3[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        mn3[k] = __vimin3_u16x2(r[k], r[(k + 1) & 15], r[(k + 2) & 15]);
+        mx3[k] = __vimax3_u16x2(r[k], r[(k + 1) & 15], r[(k + 2) & 15]);
+    }
+    unsigned mn9[16], mx9[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        mn9[k] = __vimin3_u16x2(mn3[k], mn3[(k + 3) & 15], mn3[(k + 6) & 15]);
+        mx9[k] = __vimax3_u16x2(mx3[k], mx3[(k + 3) & 15], mx3[(k + 6) & 15]);
+    }
+    unsigned b5[6], d5[6];
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        b5[k] = __vimax3_u16x2(mn9[3 * k], mn9[3 * k + 1], mn9[3 * k + 2]);
+        d5[k] = __vimin3_u16x2(mx9[3 * k], mx9[3 * k + 1], mx9[3 * k + 2]);
+    }
+    b5[5] = mn9[15]; d5[5] = mx9[15];
+    B = __vmaxu2(__vimax3_u16x2(b5[0], b5[1], b5[2]), __vimax3_u16x2(b5[3], b5[4], b5[5]));
+    D = __vminu2(__vimin3_u16x2(d5[0], d5[1], d5[2]), __vimin3_u16x2(d5[3], d5[4], d5[5]));
+}
+
+template <int P>  // pair P of the unit word: pixels 2P, 2P+1
+__device__ __forceinline__ unsigned scorePair(const unsigned (&W)[7][3], int tMin) {
+    constexpr int dx[16] = GVS_RING_DX, dy[16] = GVS_RING_DY;
+    unsigned r[16];
+#define GVS_R(k) r[k] = pairAt<4 + 2 * P + dx[k]>(W[3 + dy[k]][0], W[3 + dy[k]][1], W[3 + dy[k]][2]);
+    GVS_R(0) GVS_R(1) GVS_R(2) GVS_R(3) GVS_R(4) GVS_R(5) GVS_R(6) GVS_R(7)
+    GVS_R(8) GVS_R(9) GVS_R(10) GVS_R(11) GVS_R(12) GVS_R(13) GVS_R(14) GVS_R(15)
+#undef GVS_R
+    unsigned B, D;
+    arcMinMax(r, B, D);
+    const unsigned c = W[3][1];
+    const int v0 = (c >> (16 * P)) & 0xff, v1 = (c >> (16 * P + 8)) & 0xff;
+    const int best0 = max((int)((B >> 8) & 0xff) - v0, v0 - (int)((D >> 8) & 0xff));
+    const int best1 = max((int)(B >> 24) - v1, v1 - (int)(D >> 24));
+    const unsigned s0 = best0 > tMin ? (unsigned)(best0 - 1) : 0u, s1 = best1 > tMin ? (unsigned)(best1 - 1) : 0u;
+    return s0 | (s1 << 8);
+}
+
+__global__ void __launch_bounds__(256, 3)
 fast_cells_kernel(const __grid_constant__ Geometry g, const uint8_t* __restrict__ slab,
                   const FastItem* __restrict__ items, int maxGW, int maxGH, CandRec* __restrict__ recs,
                   int* __restrict__ nCand, unsigned short* __restrict__ cellCnt, int* __restrict__ status) {
@@ -63,8 +113,9 @@ fast_cells_kernel(const __grid_constant__ Geometry g, const uint8_t* __restrict_
     const int img = blockIdx.y;
     const LevelGeom& lv = g.lv[it.level];
     const FastSmemLayout L = fastLayout(maxGW, maxGH);
-    uint8_t* tile = smem + L.tileOff;
-    uint8_t* score = smem + L.scoreOff;
+    unsigned* tile = reinterpret_cast<unsigned*>(smem + L.tileOff);
+    unsigned* score = reinterpret_cast<unsigned*>(smem + L.scoreOff);
+    unsigned* masks = reinterpret_cast<unsigned*>(smem + L.maskOff);  // per unit: in-range, has-left, has-right byte masks
     unsigned* lists = reinterpret_cast<unsigned*>(smem + L.listOff);
 
     const int edge = g.edge;  // (edgeThreshold - fastEdge) + 3: first tested pixel of the first cell
@@ -77,71 +128,76 @@ fast_cells_kernel(const __grid_constant__ Geometry g, const uint8_t* __restrict_
         if (tid < it.nC) cellCnt[(size_t)img * g.cellsPerImage + lv.cellBase + it.iR * lv.nCols + it.iC0 + tid] = 0;
         return;
     }
-
-    // ---- 1. stage the image tile: x in [xa, xa + 4*tw), y in [y0-3, y1+3)
-    const uint8_t* src = levelPtr(slab, g, img, it.level);
-    const int xa = (X0 - 3) & ~3;
-    const int tw = (X1 + 3 - xa + 3) >> 2;  // words per row
-    const int th = rows + 6;
-    for (int i = tid; i < tw * th; i += 256) {
-        const int r = i / tw, c = i - r * tw;
-        const unsigned v = __ldg(reinterpret_cast<const unsigned*>(src + (size_t)(y0 - 3 + r) * lv.pitch + xa) + c);
-        *reinterpret_cast<unsigned*>(tile + r * L.tilePitch + 4 * c) = v;
-    }
-    // zero the score tile (frame included)
-    for (int i = tid; i < (L.scorePitch * (rows + 2)) >> 2; i += 256) reinterpret_cast<unsigned*>(score)[i] = 0;
-    __syncthreads();
-
-    // ---- 2. scores, two horizontally adjacent pixels per step
-    const int pairsPerRow = (cols + 1) >> 1;
-    const int tMin = g.tMin;
-    for (int i = tid; i < pairsPerRow * rows; i += 256) {
-        const int ry = i / pairsPerRow, px = (i - ry * pairsPerRow) * 2;
-        const uint8_t* c = tile + (ry + 3) * L.tilePitch + (X0 - xa) + px;
-        unsigned r[16];
-#pragma unroll
-        for (int k = 0; k < 16; k++) r[k] = pair16(c + kRingDy[k] * L.tilePitch + kRingDx[k]);
-        unsigned mn3[16], mx3[16];
-#pragma unroll
-        for (int k = 0; k < 16; k++) {
-            mn3[k] = __vimin3_u16x2(r[k], r[(k + 1) & 15], r[(k + 2) & 15]);
-            mx3[k] = __vimax3_u16x2(r[k], r[(k + 1) & 15], r[(k + 2) & 15]);
-        }
-        unsigned B = 0, D = 0xffffffffu;
-#pragma unroll
-        for (int k = 0; k < 16; k++) {
-            const unsigned mn9 = __vimin3_u16x2(mn3[k], mn3[(k + 3) & 15], mn3[(k + 6) & 15]);
-            const unsigned mx9 = __vimax3_u16x2(mx3[k], mx3[(k + 3) & 15], mx3[(k + 6) & 15]);
-            B = __vmaxu2(B, mn9);
-            D = __vminu2(D, mx9);
-        }
-        const int v0 = c[0], v1 = c[1];
-        const int best0 = max((int)(B & 0xffff) - v0, v0 - (int)(D & 0xffff));
-        const int best1 = max((int)(B >> 16) - v1, v1 - (int)(D >> 16));
-        uint8_t* sp = score + (ry + 1) * L.scorePitch + 1 + px;
-        if (best0 > tMin) sp[0] = (uint8_t)(best0 - 1);
-        if (best1 > tMin && px + 1 < cols) sp[1] = (uint8_t)(best1 - 1);
-    }
-    __syncthreads();
-
-    // ---- 3. strict local maxima inside each cell -> per-cell lists
     const int gW = lv.gridW;
-    for (int i = tid; i < cols * rows; i += 256) {
-        const int ry = i / cols, lx = i - ry * cols;
-        const uint8_t* sp = score + (ry + 1) * L.scorePitch + 1 + lx;
-        const int s = sp[0];
-        if (s == 0) continue;
-        const int cl = (lx >= gW) + (lx >= 2 * gW) + (lx >= 3 * gW);
-        const int cx0 = cl * gW, cx1 = min(cx0 + gW, cols);
-        const bool hasL = lx > cx0, hasR = lx + 1 < cx1;
-        const int P = L.scorePitch;
-        bool ok = s > sp[-P] && s > sp[P];
-        if (hasL) ok = ok && s > sp[-1] && s > sp[-P - 1] && s > sp[P - 1];
-        if (hasR) ok = ok && s > sp[1] && s > sp[-P + 1] && s > sp[P + 1];
-        if (!ok) continue;
-        const int slot = atomicAdd(&sCnt[cl], 1);
-        lists[cl * L.listCap + slot] = ((unsigned)ry << 16) | ((unsigned)(lx - cx0) << 8) | (unsigned)s;
-        atomicMax(&sMax[cl], s);
+    // unit words: 4-px aligned words covering [X0, X1); tile word 0 is the word left of unit 0
+    const int xu = X0 & ~3;                 // x of unit 0
+    const int nW = (X1 - xu + 3) >> 2;      // number of unit words
+    const int tw = nW + 2, th = rows + 6;   // tile words per row / rows
+    const unsigned magicT = 0xffffffffu / (unsigned)tw + 1u, magicU = 0xffffffffu / (unsigned)nW + 1u;
+
+    // ---- 1. stage the image tile (x from xu-4, y from y0-3), zero the score tile, build the per-unit byte masks
+    const uint8_t* src = levelPtr(slab, g, img, it.level) + (size_t)(y0 - 3) * lv.pitch + (xu - 4);
+    for (int i = tid; i < tw * th; i += 256) {
+        const int r = (int)__umulhi((unsigned)i, magicT), c = i - r * tw;
+        tile[r * L.tileWords + c] = __ldg(reinterpret_cast<const unsigned*>(src + (size_t)r * lv.pitch) + c);
+    }
+    for (int i = tid; i < L.scoreWords * (rows + 2); i += 256) score[i] = 0;
+    for (int j = tid; j < nW; j += 256) {
+        unsigned inr = 0, hasL = 0, hasR = 0;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int lx = xu + 4 * j + b - X0;  // position inside the strip
+            if (lx < 0 || lx >= cols) continue;
+            const int cl = (lx >= gW) + (lx >= 2 * gW) + (lx >= 3 * gW);
+            const int cx0 = cl * gW, cx1 = min(cx0 + gW, cols);
+            inr |= 0xffu << (8 * b);
+            if (lx > cx0) hasL |= 0xffu << (8 * b);
+            if (lx + 1 < cx1) hasR |= 0xffu << (8 * b);
+        }
+        masks[3 * j] = inr; masks[3 * j + 1] = hasL; masks[3 * j + 2] = hasR;
+    }
+    __syncthreads();
+
+    // ---- 2. scores: one unit word (4 px = 2 pairs) per step, 21 word loads, ring pairs by PRMT
+    const int tMin = g.tMin;
+    for (int i = tid; i < nW * rows; i += 256) {
+        const int ry = (int)__umulhi((unsigned)i, magicU), j = i - ry * nW;
+        unsigned W[7][3];
+#pragma unroll
+        for (int r = 0; r < 7; r++) {
+            const unsigned* p = tile + (ry + r) * L.tileWords + j;
+            W[r][0] = p[0]; W[r][1] = p[1]; W[r][2] = p[2];
+        }
+        const unsigned s = (scorePair<0>(W, tMin) | (scorePair<1>(W, tMin) << 16)) & masks[3 * j];
+        score[(ry + 1) * L.scoreWords + j + 1] = s;
+    }
+    __syncthreads();
+
+    // ---- 3. strict local maxima inside each cell, four pixels at a time -> per-cell lists
+    for (int i = tid; i < nW * rows; i += 256) {
+        const int ry = (int)__umulhi((unsigned)i, magicU), j = i - ry * nW;
+        const unsigned* sp = score + (ry + 1) * L.scoreWords + j + 1;
+        const unsigned c = sp[0];
+        if (c == 0) continue;
+        const unsigned hasL = masks[3 * j + 1], hasR = masks[3 * j + 2];
+        const int P = L.scoreWords;
+        const unsigned up = sp[-P], dn = sp[P];
+        unsigned lm = __vcmpgtu4(c, up) & __vcmpgtu4(c, dn);
+        const unsigned l0 = __funnelshift_r(sp[-1], c, 24) & hasL, l1 = __funnelshift_r(sp[-P - 1], up, 24) & hasL,
+                       l2 = __funnelshift_r(sp[P - 1], dn, 24) & hasL;
+        lm &= __vcmpgtu4(c, l0) & __vcmpgtu4(c, l1) & __vcmpgtu4(c, l2);
+        const unsigned r0 = __funnelshift_r(c, sp[1], 8) & hasR, r1 = __funnelshift_r(up, sp[-P + 1], 8) & hasR,
+                       r2 = __funnelshift_r(dn, sp[P + 1], 8) & hasR;
+        lm &= __vcmpgtu4(c, r0) & __vcmpgtu4(c, r1) & __vcmpgtu4(c, r2);
+        while (lm) {
+            const int b = (__ffs(lm) - 1) >> 3;
+            lm &= ~(0xffu << (8 * b));
+            const int lx = xu + 4 * j + b - X0, s = (c >> (8 * b)) & 0xff;
+            const int cl = (lx >= gW) + (lx >= 2 * gW) + (lx >= 3 * gW);
+            const int slot = atomicAdd(&sCnt[cl], 1);
+            lists[cl * L.listCap + slot] = ((unsigned)ry << 16) | ((unsigned)(lx - cl * gW) << 8) | (unsigned)s;
+            atomicMax(&sMax[cl], s);
+        }
     }
     __syncthreads();
 

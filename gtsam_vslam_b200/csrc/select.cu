@@ -34,10 +34,7 @@ constexpr int kSelThreads = 256;
 constexpr int kSelWarps = kSelThreads / 32;
 constexpr int kSmallMax = 6144;    // problems with n <= kSmallMax run entirely in shared memory
 constexpr int kBigSeg = 1024;      // segments at least this long are partitioned by the whole CTA
-constexpr int kSmemCells = 4096;   // SSC cell grid entries kept in shared memory
-constexpr unsigned kCellEmpty = 0x3fffffffu;
-constexpr unsigned kRankMask = 0x3fffffffu;
-constexpr unsigned kFired = 1u << 30, kDropped = 2u << 30;
+constexpr int kSscWarps = 7;       // widths evaluated speculatively per super-round
 
 template <typename IdxT>
 struct SelArrays {
@@ -49,9 +46,10 @@ struct SelArrays {
     int* seg;        // small-segment frontiers 2 x segCap x 3
     int segCap;
     int* hist;       // kSelWarps x 256 counting-sort counters
-    unsigned* cells; // SSC grid
-    int cellCap;
-    unsigned* cellsGlobal;  // fallback hash grid in global scratch (2 * pow2ceil(2n) words)
+    unsigned* bitmaps;      // kSscWarps x kSscBitmapWords coverage bitmaps (shared)
+    void* lists;            // kSscWarps x listCap kept positions (shared)
+    int listCap;
+    unsigned* globalBitmap; // fallback bitmap for tiny widths (global scratch)
 };
 
 struct SelShared {
@@ -335,118 +333,113 @@ __device__ void sortDescending(const SelArrays<IdxT>& A, SelShared& S, int n) {
     __syncthreads();
 }
 
-// SSC cell grid storage: dense array in shared memory when the grid fits, otherwise an open-addressing hash
-// table in global scratch whose size depends on n only (at most n cells are non-empty).
-struct DenseGrid {
-    unsigned* v;
-    int ncell;
-    __device__ __forceinline__ int slots() const { return ncell; }
-    __device__ __forceinline__ void clear(int s) const { v[s] = kCellEmpty; }
-    __device__ __forceinline__ int insert(unsigned cid) const { return (int)cid; }
-    __device__ __forceinline__ int find(unsigned cid) const { return (int)cid; }
-    __device__ __forceinline__ unsigned cellOf(int s) const { return (unsigned)s; }
-    __device__ __forceinline__ bool used(int s) const { return true; }
-};
-struct HashGrid {
-    unsigned* v;     // value per slot
-    unsigned* k;     // cell id per slot (0xffffffff = free)
-    int mask;        // slots - 1 (power of two)
-    __device__ __forceinline__ int slots() const { return mask + 1; }
-    __device__ __forceinline__ void clear(int s) const { v[s] = kCellEmpty; k[s] = 0xffffffffu; }
-    __device__ __forceinline__ int insert(unsigned cid) const {
-        int s = (int)((cid * 2654435761u) >> 7) & mask;
-        while (true) {
-            const unsigned o = atomicCAS(&k[s], 0xffffffffu, cid);
-            if (o == 0xffffffffu || o == cid) return s;
-            s = (s + 1) & mask;
-        }
-    }
-    __device__ __forceinline__ int find(unsigned cid) const {
-        int s = (int)((cid * 2654435761u) >> 7) & mask;
-        while (true) {
-            const unsigned o = *(volatile unsigned*)&k[s];
-            if (o == cid) return s;
-            if (o == 0xffffffffu) return -1;
-            s = (s + 1) & mask;
-        }
-    }
-    __device__ __forceinline__ unsigned cellOf(int s) const { return k[s]; }
-    __device__ __forceinline__ bool used(int s) const { return k[s] != 0xffffffffu; }
-};
-
-// One SSC pass at `width` over the sorted order `sorted`; writes the kept sorted-positions (ascending) to `res`
-// and returns their number.  `flag` is an n-byte scratch array.
-template <typename IdxT, typename Grid>
-__device__ int sscPassT(const Grid G, const unsigned* xy, SelShared& S, const IdxT* sorted, IdxT* res, uint8_t* flag,
-                        int n, int width, int ncc, int ncr) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// ---- SSC (src/FeatureExtractor.cpp:410-461) --------------------------------------------------------------
+// One pass at `width`, executed by ONE warp over all n points in sorted order with a coverage bitmap
+// (1 bit per cell of side width/2).  32 points are tested against the bitmap at once; the uncovered ones are
+// resolved in order inside the chunk with ballots (the first uncovered lane is kept, covers its 5x5 cells and
+// knocks out the later lanes that fall inside), so the result is exactly the sequential greedy cover.
+// floor(y / c), c = width / 2.0  ==  (2*y) / width in integers (exact: a non-integer quotient is at least
+// 1/width away from an integer, far more than the double rounding error; an integer quotient is exact).
+template <typename IdxT>
+__device__ int sscPassWarp(const unsigned* xy, const IdxT* sorted, int n, int width, int ncc, int ncr, unsigned* bitmap,
+                           IdxT* list, int listCap, int lane) {
+    const int bmWords = (ncc * ncr + 31) >> 5;
+    for (int i = lane; i < bmWords; i += 32) bitmap[i] = 0;
+    __syncwarp();
     const unsigned magic = (unsigned)(0x100000000ull / (unsigned)width) + 1u;  // exact while 2*coord*width < 2^32
-    const int nslot = G.slots();
-    for (int i = tid; i < nslot; i += kSelThreads) G.clear(i);
-    for (int i = tid; i < n; i += kSelThreads) flag[i] = 0;
-    __syncthreads();
-    // first (smallest) sorted rank per cell
-    for (int i = tid; i < n; i += kSelThreads) {
-        const unsigned q = xy[sorted[i]];
-        const unsigned x = q & 0xfff, y = (q >> 12) & 0xfff;
-        const unsigned col = __umulhi(2 * x, magic), row = __umulhi(2 * y, magic);
-        atomicMin(&G.v[G.insert(row * (unsigned)ncc + col)], (unsigned)i);
-    }
-    __syncthreads();
-    // exact greedy independent set on the cell grid: a cell fires iff no neighbour (+-2) with a smaller first
-    // rank fired.  Chaotic rounds: every decision is final when taken.
-    while (true) {
-        int undecided = 0;
-        for (int s = tid; s < nslot; s += kSelThreads) {
-            const unsigned v = *(volatile unsigned*)&G.v[s];
-            if (v >= kCellEmpty) continue;  // empty, fired or dropped
-            const unsigned cid = G.cellOf(s);
-            const int row = (int)(cid / (unsigned)ncc), col = (int)(cid - (unsigned)row * ncc);
-            const int r0 = max(row - 2, 0), r1 = min(row + 2, ncr - 1), c0 = max(col - 2, 0), c1 = min(col + 2, ncc - 1);
-            bool drop = false, wait = false;
-            for (int r = r0; r <= r1; r++)
-                for (int c = c0; c <= c1; c++) {
-                    const int t = G.find((unsigned)r * ncc + c);
-                    if (t < 0) continue;
-                    const unsigned o = *(volatile unsigned*)&G.v[t];
-                    if ((o >> 30) == 1) drop = true;
-                    else if ((o >> 30) == 0 && o < v) wait = true;  // undecided neighbour with a smaller first rank
-                }
-            if (drop) G.v[s] = v | kDropped;
-            else if (!wait) { G.v[s] = v | kFired; flag[v] = 1; }
-            else undecided = 1;
-        }
-        if (!__syncthreads_or(undecided)) break;
-    }
-    // ordered compaction of the flags (each thread owns a contiguous strip of sorted positions)
-    const int per = (n + kSelThreads - 1) / kSelThreads;
-    const int a = min(tid * per, n), b = min(a + per, n);
     int cnt = 0;
-    for (int i = a; i < b; i++) cnt += flag[i];
-    int incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-    if (lane == 31) S.scan[warp] = incl;
-    __syncthreads();
-    int base = incl - cnt, total = 0;
-    for (int w = 0; w < kSelWarps; w++) { if (w < warp) base += S.scan[w]; total += S.scan[w]; }
-    for (int i = a; i < b; i++) if (flag[i]) res[base++] = (IdxT)i;
-    __syncthreads();
-    return total;
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        int row = 0, col = 0;
+        bool active = false;
+        if (i < n) {
+            const unsigned q = xy[sorted[i]];
+            col = (int)__umulhi(2 * (q & 0xfff), magic);
+            row = (int)__umulhi(2 * ((q >> 12) & 0xfff), magic);
+            const int bit = row * ncc + col;
+            active = !((bitmap[bit >> 5] >> (bit & 31)) & 1);
+        }
+        unsigned mask = __ballot_sync(0xffffffffu, active);
+        while (mask) {
+            const int f = __ffs(mask) - 1;
+            const int fr = __shfl_sync(0xffffffffu, row, f), fc = __shfl_sync(0xffffffffu, col, f);
+            if (lane == 0 && cnt < listCap) list[cnt] = (IdxT)(base + f);
+            cnt++;
+            if (lane < 5) {  // cover rows fr-2 .. fr+2, columns fc-2 .. fc+2 (clamped to the grid)
+                const int r = fr - 2 + lane;
+                if (r >= 0 && r < ncr) {
+                    const int c0 = max(fc - 2, 0), c1 = min(fc + 2, ncc - 1);
+                    const int sbit = r * ncc + c0, len = c1 - c0 + 1, sh = sbit & 31;
+                    const unsigned m = (1u << len) - 1u;
+                    atomicOr(&bitmap[sbit >> 5], m << sh);
+                    if (sh + len > 32) atomicOr(&bitmap[(sbit >> 5) + 1], m >> (32 - sh));
+                }
+            }
+            if (active && abs(row - fr) <= 2 && abs(col - fc) <= 2) active = false;
+            mask = __ballot_sync(0xffffffffu, active);
+        }
+        __syncwarp();
+    }
+    return cnt;
 }
 
+// The reference's binary search over the width.  The widths it can visit form a binary tree; three levels of
+// the tree (7 nodes) are evaluated speculatively by 7 warps at once, then the path is walked with the counts.
+// Returns the kept count; `outList` (shared, listCap entries) receives the kept sorted-positions.
+constexpr int kSscBitmapWords = 512;  // per-warp shared bitmap: 16384 cells
 template <typename IdxT>
-__device__ int sscPass(const SelArrays<IdxT>& A, SelShared& S, const IdxT* sorted, IdxT* res, int n, int width, int cols,
-                       int rows) {
-    const int ncc = (2 * cols) / width + 1, ncr = (2 * rows) / width + 1;  // numCellCols + 1, numCellRows + 1
-    if ((long long)ncc * ncr <= A.cellCap) {
-        DenseGrid G{A.cells, ncc * ncr};
-        return sscPassT<IdxT>(G, A.xy, S, sorted, res, A.key, n, width, ncc, ncr);
+__device__ int sscSearch(const SelArrays<IdxT>& A, SelShared& S, const IdxT* sorted, int n, const LevelGeom& lv,
+                         unsigned* bitmaps, IdxT* lists, int listCap, unsigned* globalBitmap, const IdxT** outList) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int K = lv.quota, cols = lv.w, rows = lv.h;
+    int high = lv.sscHigh;
+    int low = max(1, (int)floor(sqrt((double)n / (double)K)));
+    int finalNode = -1, finalCount = 0;
+    while (true) {
+        if (low > high) break;  // (width == prevWidth cannot occur once low <= high: the bracket always shrinks)
+        // node k of the 3-level tree: bracket [nl, nh], width nw; children 2k+1 (count < Kmin) and 2k+2 (count > Kmax)
+        int nl[7], nh[7], nw[7];
+        nl[0] = low; nh[0] = high;
+#pragma unroll
+        for (int k = 0; k < 7; k++) {
+            nw[k] = nl[k] + (nh[k] - nl[k]) / 2;
+            if (k < 3) { nl[2 * k + 1] = nl[k]; nh[2 * k + 1] = nw[k] - 1; nl[2 * k + 2] = nw[k] + 1; nh[2 * k + 2] = nh[k]; }
+        }
+        auto fits = [&](int k) { return nl[k] <= nh[k] && ((2 * cols) / nw[k] + 1) * ((2 * rows) / nw[k] + 1) <= kSscBitmapWords * 32; };
+        const bool rootFits = fits(0);
+        if (warp < 7) {
+            bool valid = true;  // all ancestors must be valid brackets as well
+            for (int k = warp; valid; k = (k - 1) / 2) { valid = nl[k] <= nh[k]; if (k == 0) break; }
+            int c = -1;
+            if (rootFits) {
+                if (valid && fits(warp))
+                    c = sscPassWarp(A.xy, sorted, n, nw[warp], (2 * cols) / nw[warp] + 1, (2 * rows) / nw[warp] + 1,
+                                    bitmaps + warp * kSscBitmapWords, lists + warp * listCap, listCap, lane);
+            } else if (warp == 0) {  // tiny width: one pass, bitmap in global scratch
+                c = sscPassWarp(A.xy, sorted, n, nw[0], (2 * cols) / nw[0] + 1, (2 * rows) / nw[0] + 1, globalBitmap, lists,
+                                listCap, lane);
+            }
+            if (lane == 0) S.wA[warp] = c;
+        }
+        __syncthreads();
+        // walk (every thread does the same walk on the shared counts)
+        int k = 0;
+        bool done = false;
+        while (true) {
+            const int c = S.wA[k];
+            finalNode = k; finalCount = c;
+            if (c >= lv.kmin && c <= lv.kmax) { done = true; break; }
+            const int child = c < lv.kmin ? 2 * k + 1 : 2 * k + 2;
+            const int cl = c < lv.kmin ? nl[k] : nw[k] + 1, ch = c < lv.kmin ? nw[k] - 1 : nh[k];
+            if (cl > ch) { done = true; break; }          // the reference stops and returns the last computed pass
+            if (child >= 7 || S.wA[child] < 0) { low = cl; high = ch; break; }  // not evaluated: next super-round
+            k = child;
+        }
+        __syncthreads();
+        if (done) break;
     }
-    int slots = 64;
-    while (slots < 2 * n) slots <<= 1;
-    HashGrid G{A.cellsGlobal, A.cellsGlobal + slots, slots - 1};
-    return sscPassT<IdxT>(G, A.xy, S, sorted, res, A.key, n, width, ncc, ncr);
+    *outList = finalNode >= 0 ? lists + finalNode * listCap : lists;
+    return finalNode >= 0 ? finalCount : 0;
 }
 
 template <typename IdxT, bool kSmall>
@@ -456,7 +449,7 @@ select_kernel(const __grid_constant__ Geometry g, int nImages, const CandRec* __
               int* __restrict__ keptCnt, unsigned* __restrict__ orderedDbg, unsigned* __restrict__ sortedDbg,
               uint8_t* __restrict__ scratch,
               size_t scratchPerCta, int* __restrict__ workCounter, int* __restrict__ status, int maxCells, int segCap,
-              int nMaxGlobal) {
+              int nMaxGlobal, int listCap) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ SelShared S;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -464,34 +457,35 @@ select_kernel(const __grid_constant__ Geometry g, int nImages, const CandRec* __
     SelArrays<IdxT> A;
     uint8_t* myScratch = scratch + (size_t)blockIdx.x * scratchPerCta;
     {
-        // shared layout: cellOff | union(seg + hist, cells) | [small only] xy | idx | tmp | key
+        // shared layout: cellOff | union(sort: seg + hist ; ssc: bitmaps + lists) | [small only] xy | idx | tmp | key
         uint8_t* p = smem;
         A.cellOff = reinterpret_cast<int*>(p); p += ((maxCells + 1) * 4 + 15) & ~15;
         const size_t segBytes = (size_t)2 * 3 * segCap * 4, histBytes = kSelWarps * 256 * 4;
+        const size_t bmBytes = (size_t)kSscWarps * kSscBitmapWords * 4, listBytes = (size_t)kSscWarps * listCap * sizeof(IdxT);
         A.seg = reinterpret_cast<int*>(p);
         A.hist = reinterpret_cast<int*>(p + segBytes);
-        A.cells = reinterpret_cast<unsigned*>(p);
         A.segCap = segCap;
-        const size_t unionBytes = segBytes + histBytes > (size_t)kSmemCells * 4 ? segBytes + histBytes : (size_t)kSmemCells * 4;
-        A.cellCap = (int)(unionBytes / 4);
+        A.bitmaps = reinterpret_cast<unsigned*>(p);
+        A.lists = p + bmBytes;
+        A.listCap = listCap;
+        const size_t unionBytes = segBytes + histBytes > bmBytes + listBytes ? segBytes + histBytes : bmBytes + listBytes;
         p += (unionBytes + 15) & ~15;
         if (kSmall) {
             A.xy = reinterpret_cast<unsigned*>(p); p += (size_t)kSmallMax * 4;
             A.idx = reinterpret_cast<IdxT*>(p); p += (size_t)kSmallMax * sizeof(IdxT);
             A.tmp = reinterpret_cast<IdxT*>(p); p += (size_t)kSmallMax * sizeof(IdxT);
             A.key = p;
-            A.cellsGlobal = reinterpret_cast<unsigned*>(myScratch);
+            A.globalBitmap = reinterpret_cast<unsigned*>(myScratch);
         } else {
-            // global class: seg frontiers do not fit the shared union for large n -> global as well
+            // global class: all per-candidate arrays and the segment frontiers live in global scratch
             uint8_t* q = myScratch;
             A.xy = reinterpret_cast<unsigned*>(q); q += (size_t)nMaxGlobal * 4;
             A.idx = reinterpret_cast<IdxT*>(q); q += (size_t)nMaxGlobal * sizeof(IdxT);
             A.tmp = reinterpret_cast<IdxT*>(q); q += (size_t)nMaxGlobal * sizeof(IdxT);
             A.seg = reinterpret_cast<int*>(q); A.segCap = nMaxGlobal / 17 + 2; q += (size_t)2 * 3 * A.segCap * 4;
             A.key = q; q += ((size_t)nMaxGlobal + 15) & ~(size_t)15;
-            A.cellsGlobal = reinterpret_cast<unsigned*>(q);
-            A.hist = reinterpret_cast<int*>(p - ((unionBytes + 15) & ~15));  // hist alone at the start of the union
-            A.cellCap = (int)(unionBytes / 4);
+            A.globalBitmap = reinterpret_cast<unsigned*>(q);
+            A.hist = reinterpret_cast<int*>(A.bitmaps);  // the union holds only hist during the sort
         }
     }
 
@@ -547,37 +541,24 @@ select_kernel(const __grid_constant__ Geometry g, int nImages, const CandRec* __
         // ---- (b) sort
         sortDescending(A, S, n);
         const IdxT* sorted = A.tmp;
-        IdxT* res = A.idx;
         if (sortedDbg) {  // parity tap: the permutation itself and, after ssc, the kept positions
             unsigned* o = sortedDbg + (size_t)img * g.candPerImage + lv.candOff;
             for (int i = tid; i < n; i += kSelThreads) o[i] = (unsigned)sorted[i];
         }
 
         // ---- (c) ssc binary search (src/FeatureExtractor.cpp:396-461)
-        const int K = lv.quota;
-        int high = lv.sscHigh;
-        int low = (int)floor(sqrt((double)n / (double)K));
-        low = max(1, low);
-        int prevWidth = -1, count = 0;
-        while (true) {
-            const int width = low + (high - low) / 2;
-            if (width == prevWidth || low > high) break;
-            count = sscPass(A, S, sorted, res, n, width, lv.w, lv.h);
-            if (count >= lv.kmin && count <= lv.kmax) break;
-            else if (count < lv.kmin) high = width - 1;
-            else low = width + 1;
-            prevWidth = width;
-        }
-        if (count > lv.keptCap) { if (tid == 0) atomicOr(status, kStatKeptOverflow); count = lv.keptCap; }
+        const IdxT* res = nullptr;
+        int count = sscSearch<IdxT>(A, S, sorted, n, lv, A.bitmaps, reinterpret_cast<IdxT*>(A.lists), A.listCap, A.globalBitmap, &res);
+        if (count > lv.keptCap || count > A.listCap) { if (tid == 0) atomicOr(status, kStatKeptOverflow); count = min(lv.keptCap, A.listCap); }
         for (int i = tid; i < count; i += kSelThreads) keptOut[i] = A.xy[sorted[res[i]]];
         if (tid == 0) *keptCntOut = count;
     }
 }
 
-static size_t selectSmemBytes(bool small, int maxCells, int segCap) {
+static size_t selectSmemBytes(bool small, int maxCells, int segCap, int listCap) {
     size_t b = ((size_t)(maxCells + 1) * 4 + 15) & ~(size_t)15;
     const size_t segBytes = (size_t)2 * 3 * segCap * 4, histBytes = kSelWarps * 256 * 4;
-    size_t u = std::max(segBytes + histBytes, (size_t)kSmemCells * 4);
+    size_t u = std::max(segBytes + histBytes, (size_t)kSscWarps * kSscBitmapWords * 4 + (size_t)kSscWarps * listCap * (small ? 2 : 4));
     b += (u + 15) & ~(size_t)15;
     if (small) b += (size_t)kSmallMax * (4 + 2 + 2 + 1);
     return b;
@@ -590,12 +571,11 @@ static int maxCandCap(const Geometry& g) {
 }
 
 size_t selectScratchBytes(const Geometry& g) {
-    // global class arrays (xy, idx, tmp, seg frontiers, key) + the hash grid (value + key per slot)
+    // global class arrays (xy, idx, tmp, seg frontiers, key) + the fallback SSC bitmap for width 1:
+    // (2h+1) x (2w+1) cells, one bit each
     const size_t nMax = (size_t)std::max(maxCandCap(g), kSmallMax);
     size_t b = nMax * (4 + 4 + 4) + (size_t)2 * 3 * (nMax / 17 + 2) * 4 + ((nMax + 15) & ~(size_t)15);
-    size_t slots = 64;
-    while (slots < 2 * nMax) slots <<= 1;
-    b += slots * 8;
+    b += ((size_t)(2 * g.lv[0].h + 1) * (2 * g.lv[0].w + 1) + 31) / 32 * 4 + 16;
     return (b + 255) & ~(size_t)255;
 }
 
@@ -611,8 +591,10 @@ void launchSelect(const Geometry& g, int nImages, const CandRec* recs, const int
     int maxCells = 0;
     for (int l = 0; l < g.nLevels; l++) maxCells = std::max(maxCells, g.lv[l].nCols * g.lv[l].nRows);
     const int segCapSmall = kSmallMax / 17 + 2;
-    const size_t smSmall = selectSmemBytes(true, maxCells, segCapSmall);
-    const size_t smBig = selectSmemBytes(false, maxCells, 1);
+    int listCap = 0;
+    for (int l = 0; l < g.nLevels; l++) listCap = std::max(listCap, g.lv[l].keptCap);
+    const size_t smSmall = selectSmemBytes(true, maxCells, segCapSmall, listCap);
+    const size_t smBig = selectSmemBytes(false, maxCells, 1, listCap);
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(select_kernel<unsigned short, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -624,14 +606,14 @@ void launchSelect(const Geometry& g, int nImages, const CandRec* recs, const int
     cudaMemsetAsync(workCounter, 0, 2 * sizeof(int), s);
     select_kernel<unsigned short, true><<<grid, kSelThreads, smSmall, s>>>(
         g, nImages, recs, nCand, cellCnt, kept, keptCnt, orderedDbg, sortedDbg, scratch, scratchPerCta, workCounter, status,
-        maxCells, segCapSmall, maxCandCap(g));
+        maxCells, segCapSmall, maxCandCap(g), listCap);
     ++*launches;
     bool needBig = false;
     for (int l = 0; l < g.nLevels; l++) needBig |= g.lv[l].candCap > kSmallMax;
     if (needBig) {
         select_kernel<unsigned, false><<<grid, kSelThreads, smBig, s>>>(
             g, nImages, recs, nCand, cellCnt, kept, keptCnt, orderedDbg, sortedDbg, scratch, scratchPerCta, workCounter + 1,
-            status, maxCells, 1, maxCandCap(g));
+            status, maxCells, 1, maxCandCap(g), listCap);
         ++*launches;
     }
 }

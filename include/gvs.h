@@ -154,6 +154,11 @@ int gvs_track_stereo_batch_host(gvs_matcher* fm, const uint8_t* left, const uint
                                 int row_stride, int n_frames, int width, int height);
 int gvs_track_stereo_batch_resident(gvs_matcher* fm, int n_frames, int width, int height);
 int gvs_matcher_sync(gvs_matcher* fm);
+/* Fork/join the two track calls above from/into an externally owned CUDA stream (cudaStream_t as void*): the
+ * extractors keep running concurrently on their own streams (like the reference's two extraction threads), but
+ * everything is ordered after the work already queued on `cuda_stream`, and work queued on it afterwards waits
+ * for the batch.  NULL detaches. */
+int gvs_matcher_set_stream(gvs_matcher* fm, void* cuda_stream);
 
 /* Map points as a structure of arrays: the fields of MapPoint that the projection matchers read
  * (include/Map.h; src/FeatureMatcher.cpp:264-267,307-310). */
