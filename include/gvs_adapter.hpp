@@ -1,0 +1,244 @@
+// Drop-in C++ adapter: the reference's FeatureExtractor / FeatureMatcher / TrackedKeys (same namespace, class,
+// member and method names, same argument meaning) implemented on the C ABI of include/gvs.h.
+//
+// A maintainer of gtsam-vSLAM replaces include/FeatureExtractor.h + src/FeatureExtractor.cpp and
+// include/FeatureMatcher.h + src/FeatureMatcher.cpp by this header and links libgvs.so;
+// System, FeatureTracker, KeyFrame, Map and LocalMapper compile against it unchanged apart from the two
+// constructor calls that now also pass the image size.
+//
+//   reference                                                       here
+//   FeatureExtractor::FeatureExtractor   src/FeatureExtractor.cpp:620   FeatureExtractor(..., width, height)
+//   FeatureExtractor::extractKeysNew     src/FeatureExtractor.cpp:481   extractKeysNew(image, keypoints, descriptors)
+//   public tables                        include/FeatureExtractor.h:71  scalePyramid, scaleInvPyramid, sigmaFactor, ...
+//   FeatureMatcher::findStereoMatchesORB2R src/FeatureMatcher.cpp:528   findStereoMatchesORB2R(lImage, rImage, rightDesc, rightKeys, keysLeft)
+//   FeatureMatcher::matchByProjectionRPred src/FeatureMatcher.cpp:254   matchByProjectionRPred(activeMapPoints, keysLeft, ...)
+//   FeatureMatcher::matchByProjectionMono  src/FeatureMatcher.cpp:391   matchByProjectionMono(...)
+//   FeatureMatcher::matchByRadius          src/FeatureMatcher.cpp:458   matchByRadius(...)
+//   FeatureMatcher::DescriptorDistance     src/FeatureMatcher.cpp:710   DescriptorDistance(a, b)
+//   FeatureTracker::assignKeysToGrids      src/FeatureTracker.cpp:28    FeatureMatcher::assignKeysToGrids(keysLeft, width, height)
+//   FeatureTracker::extractORBAndStereoMatch src/FeatureTracker.cpp:56  FeatureMatcher::extractORBAndStereoMatch(leftIm, rightIm, keysLeft)
+//
+// Error behaviour: the reference returns void and never reports errors; here a failing C-ABI call throws
+// std::runtime_error with gvs_last_error() (there is no CPU fallback to fall through to).
+#pragma once
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#ifdef GVS_HAVE_OPENCV
+#include <opencv2/core.hpp>
+#else
+#include "gvs_cv_shim.hpp"
+#endif
+#include "gvs.h"
+
+namespace GTSAM_VIOSLAM {
+
+static_assert(sizeof(cv::KeyPoint) == sizeof(gvs_keypoint), "cv::KeyPoint must be the 28-byte POD the ABI copies");
+
+inline void gvsCheck(int rc) {
+    if (rc != GVS_OK) throw std::runtime_error(std::string("gvs: ") + gvs_last_error());
+}
+
+struct TrackedKeys {  // include/FeatureExtractor.h:18-50
+    std::vector<cv::KeyPoint> keyPoints, rightKeyPoints;
+    std::vector<std::vector<std::vector<int>>> lkeyGrid, rkeyGrid;
+    std::vector<int> rightIdxs, leftIdxs;
+    std::vector<float> estimatedDepth;
+    std::vector<bool> close;
+    cv::Mat Desc, rightDesc;
+    float xMult = 0, yMult = 0;
+    int xGrids = 0, yGrids = 0;
+    void getKeys(const TrackedKeys& k) {
+        keyPoints = k.keyPoints; rightKeyPoints = k.rightKeyPoints; lkeyGrid = k.lkeyGrid; rkeyGrid = k.rkeyGrid;
+        rightIdxs = k.rightIdxs; leftIdxs = k.leftIdxs; Desc = k.Desc.clone(); rightDesc = k.rightDesc.clone();
+        close = k.close; estimatedDepth = k.estimatedDepth; xMult = k.xMult; yMult = k.yMult; xGrids = k.xGrids; yGrids = k.yGrids;
+    }
+};
+
+class FeatureExtractor {
+  public:
+    const int nFeatures;
+    const size_t nLevels;
+    const float imScale;
+    const int edgeThreshold, patchSize;
+    const int halfPatchSize{15};
+    const int maxFastThreshold, minFastThreshold;
+    std::vector<int> scaledPatchSize, featurePerLevel;
+    std::vector<float> scalePyramid, scaleInvPyramid, sigmaFactor, InvSigmaFactor;
+    // imagePyramid stays on the device: only findStereoMatchesORB2R reads it (src/FeatureMatcher.cpp:606-623)
+
+    FeatureExtractor(int _nfeatures, int _nLevels, float _imScale, int _edgeThreshold, int _patchSize, int _maxFastThreshold,
+                     int _minFastThreshold, int width, int height, int device = 0)
+        : nFeatures(_nfeatures), nLevels(_nLevels), imScale(_imScale), edgeThreshold(_edgeThreshold), patchSize(_patchSize),
+          maxFastThreshold(_maxFastThreshold), minFastThreshold(_minFastThreshold), width_(width), height_(height) {
+        gvs_extractor_params p{_nfeatures, _nLevels, _imScale, _edgeThreshold, _patchSize, _maxFastThreshold, _minFastThreshold};
+        gvsCheck(gvs_extractor_create(&h_, &p, width, height, 1, device));
+        scalePyramid.resize(nLevels); scaleInvPyramid.resize(nLevels); sigmaFactor.resize(nLevels); InvSigmaFactor.resize(nLevels);
+        scaledPatchSize.resize(nLevels); featurePerLevel.resize(nLevels);
+        gvsCheck(gvs_extractor_tables(h_, scalePyramid.data(), scaleInvPyramid.data(), sigmaFactor.data(), InvSigmaFactor.data(),
+                                      scaledPatchSize.data(), featurePerLevel.data()));
+    }
+    FeatureExtractor(int width, int height) : FeatureExtractor(2000, 8, 1.2f, 19, 31, 20, 7, width, height) {}
+    ~FeatureExtractor() { gvs_extractor_destroy(h_); }
+    FeatureExtractor(const FeatureExtractor&) = delete;
+    FeatureExtractor& operator=(const FeatureExtractor&) = delete;
+
+    // src/FeatureExtractor.cpp:481-533.  Zero keypoints leaves both outputs untouched (:498-499).
+    void extractKeysNew(cv::Mat& image, std::vector<cv::KeyPoint>& keypoints, cv::Mat& descriptors) {
+        const int cap = 2 * nFeatures + 64 * (int)nLevels;
+        std::vector<cv::KeyPoint> k(cap);
+        cv::Mat d(cap, 32, cv::CV_8U);
+        int n = 0;
+        gvsCheck(gvs_extract(h_, image.data, image.cols, image.rows, (int)image.step, reinterpret_cast<gvs_keypoint*>(k.data()),
+                             d.data, cap, &n));
+        if (n <= 0) return;
+        k.resize(n);
+        keypoints = std::move(k);
+        descriptors = cv::Mat(n, 32, cv::CV_8U);
+        std::memcpy(descriptors.data, d.data, (size_t)n * 32);
+    }
+    gvs_extractor* handle() const { return h_; }
+    int width() const { return width_; }
+    int height() const { return height_; }
+
+  private:
+    gvs_extractor* h_ = nullptr;
+    int width_, height_;
+};
+
+class FeatureMatcher {
+  public:
+    const int closeNumber{40};
+    std::shared_ptr<FeatureExtractor> feLeft, feRight;
+    const int imageHeight;
+
+    // zedptr is reduced to the values the path reads: mCameraLeft->fx (double), mBaseline (float) (include/Camera.h:72,86)
+    FeatureMatcher(double fx, float baseline, std::shared_ptr<FeatureExtractor> _feLeft, std::shared_ptr<FeatureExtractor> _feRight,
+                   int _imageHeight = 360)
+        : feLeft(std::move(_feLeft)), feRight(std::move(_feRight)), imageHeight(_imageHeight) {
+        gvsCheck(gvs_matcher_create(&h_, feLeft->handle(), feRight ? feRight->handle() : nullptr, fx, baseline, _imageHeight));
+    }
+    ~FeatureMatcher() { gvs_matcher_destroy(h_); }
+    FeatureMatcher(const FeatureMatcher&) = delete;
+    FeatureMatcher& operator=(const FeatureMatcher&) = delete;
+
+    // src/FeatureMatcher.cpp:528-708.  The images and rightDesc/rightKeys arguments are kept for signature parity: the
+    // device already holds the pyramids, keys and descriptors of the two extractKeysNew calls that precede this call.
+    void findStereoMatchesORB2R(const cv::Mat&, const cv::Mat&, const cv::Mat&, std::vector<cv::KeyPoint>& rightKeys, TrackedKeys& keysLeft) {
+        gvsCheck(gvs_stereo_match_batch(h_, 1));
+        const size_t nl = keysLeft.keyPoints.size(), nr = rightKeys.size();
+        keysLeft.rightIdxs.assign(nl, -1); keysLeft.leftIdxs.assign(nr, -1); keysLeft.estimatedDepth.assign(nl, -1.0f);
+        std::vector<uint8_t> cl(nl + 1);
+        gvsCheck(gvs_stereo_download(h_, 0, 1, keysLeft.rightIdxs.data(), keysLeft.leftIdxs.data(), keysLeft.estimatedDepth.data(), cl.data()));
+        keysLeft.close.assign(nl, false);
+        for (size_t i = 0; i < nl; i++) keysLeft.close[i] = cl[i] != 0;
+    }
+
+    // FeatureTracker::assignKeysToGrids for both sides (src/FeatureTracker.cpp:28-54, :67-68)
+    void assignKeysToGrids(TrackedKeys& keysLeft, int width, int height) {
+        gvsCheck(gvs_assign_grids_batch(h_, 1, width, height));
+        for (int side = 0; side < 2; side++) {
+            const size_t n = side ? keysLeft.rightKeyPoints.size() : keysLeft.keyPoints.size();
+            std::vector<int> start(GVS_GRID_X * GVS_GRID_X + 1), items(n + 1);
+            int yg = 0;
+            gvsCheck(gvs_grid_download(h_, 0, side, start.data(), items.data(), &yg, &keysLeft.xMult, &keysLeft.yMult));
+            keysLeft.xGrids = GVS_GRID_X; keysLeft.yGrids = yg;
+            auto& grid = side ? keysLeft.rkeyGrid : keysLeft.lkeyGrid;
+            grid.assign(yg, std::vector<std::vector<int>>(GVS_GRID_X));
+            for (int r = 0; r < yg; r++)
+                for (int c = 0; c < GVS_GRID_X; c++)
+                    grid[r][c].assign(items.begin() + start[r * GVS_GRID_X + c], items.begin() + start[r * GVS_GRID_X + c + 1]);
+        }
+    }
+
+    // FeatureTracker::extractORBAndStereoMatch (src/FeatureTracker.cpp:56-70): the two extractions run concurrently on the
+    // two handles' streams (the reference uses two std::threads), then stereo matching and both grids.
+    void extractORBAndStereoMatch(cv::Mat& leftIm, cv::Mat& rightIm, TrackedKeys& keysLeft) {
+        gvsCheck(gvs_extract_batch_host(feLeft->handle(), leftIm.data, leftIm.step * leftIm.rows, (int)leftIm.step, 1));
+        gvsCheck(gvs_extract_batch_host(feRight->handle(), rightIm.data, rightIm.step * rightIm.rows, (int)rightIm.step, 1));
+        fetch(*feLeft, keysLeft.keyPoints, keysLeft.Desc);
+        fetch(*feRight, keysLeft.rightKeyPoints, keysLeft.rightDesc);
+        findStereoMatchesORB2R(leftIm, rightIm, keysLeft.rightDesc, keysLeft.rightKeyPoints, keysLeft);
+        assignKeysToGrids(keysLeft, leftIm.cols, leftIm.rows);
+    }
+
+    // src/FeatureMatcher.cpp:254-389 / :391-456.  MapPointT needs: cv::Mat desc; cv::Point2f predL, predR; int scaleLevelL,
+    // scaleLevelR; bool inFrame, inFrameR (include/Map.h).  Runs against the frame of the last extractORBAndStereoMatch.
+    template <class MapPointT>
+    int matchByProjectionRPred(std::vector<MapPointT*>& activeMapPoints, TrackedKeys& keysLeft, std::vector<int>& matchedIdxsL,
+                               std::vector<int>& matchedIdxsR, std::vector<std::pair<int, int>>& matchesIdxs, const float rad) {
+        return project(GVS_MATCH_STEREO_PRED, activeMapPoints, keysLeft, matchedIdxsL, &matchedIdxsR, matchesIdxs, rad);
+    }
+    template <class MapPointT>
+    int matchByProjectionMono(std::vector<MapPointT*>& activeMapPoints, TrackedKeys& keysLeft, std::vector<int>& matchedIdxsL,
+                              std::vector<std::pair<int, int>>& matchesIdxs, const float rad) {
+        return project(GVS_MATCH_MONO, activeMapPoints, keysLeft, matchedIdxsL, nullptr, matchesIdxs, rad);
+    }
+    // src/FeatureMatcher.cpp:458-526: matches[i].first receives the index matched by lastKeys.keyPoints[i] (or stays -1); the
+    // caller appends (actKeyFrame, idx) to keyframeIdxMatchs[i] as :522 does.  actKeys must be the last extracted frame.
+    int matchByRadius(TrackedKeys& lastKeys, TrackedKeys& actKeys, std::vector<int>& matchedIdxsL, std::vector<std::pair<int, int>>& matches,
+                      const float rad) {
+        const int M = (int)lastKeys.keyPoints.size();
+        std::vector<float> pred(2 * (size_t)M);
+        std::vector<int32_t> lvl(M);
+        std::vector<uint8_t> desc((size_t)M * 32);
+        for (int i = 0; i < M; i++) {
+            pred[2 * i] = lastKeys.keyPoints[i].pt.x; pred[2 * i + 1] = lastKeys.keyPoints[i].pt.y; lvl[i] = lastKeys.keyPoints[i].octave;
+            std::memcpy(&desc[(size_t)i * 32], lastKeys.Desc.ptr(i), 32);
+        }
+        gvs_mappoints mp{M, desc.data(), pred.data(), nullptr, lvl.data(), nullptr, nullptr, nullptr};
+        matches.assign(M, std::make_pair(-1, -1));
+        int n = 0;
+        (void)actKeys;
+        gvsCheck(gvs_match_projection(h_, 0, GVS_MATCH_RADIUS, &mp, rad, matchedIdxsL.data(), nullptr,
+                                      reinterpret_cast<int32_t*>(matches.data()), &n));
+        return n;
+    }
+
+    // src/FeatureMatcher.cpp:710-726
+    static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b) {
+        const uint32_t* pa = reinterpret_cast<const uint32_t*>(a.ptr(0));
+        const uint32_t* pb = reinterpret_cast<const uint32_t*>(b.ptr(0));
+        int d = 0;
+        for (int i = 0; i < 8; i++) d += __builtin_popcount(pa[i] ^ pb[i]);  // one 32-byte pair: not worth a launch
+        return d;
+    }
+    gvs_matcher* handle() const { return h_; }
+
+  private:
+    static void fetch(FeatureExtractor& fe, std::vector<cv::KeyPoint>& k, cv::Mat& d) {
+        int off[2] = {0, 0};
+        gvsCheck(gvs_extract_offsets(fe.handle(), off));
+        const int n = off[1];
+        if (n <= 0) return;
+        k.assign(n, cv::KeyPoint());
+        d = cv::Mat(n, 32, cv::CV_8U);
+        gvsCheck(gvs_extract_download(fe.handle(), 0, 1, reinterpret_cast<gvs_keypoint*>(k.data()), d.data, n));
+    }
+    template <class MapPointT>
+    int project(int mode, std::vector<MapPointT*>& mps, TrackedKeys&, std::vector<int>& mL, std::vector<int>* mR,
+                std::vector<std::pair<int, int>>& matches, float rad) {
+        const int M = (int)mps.size();
+        std::vector<float> pl(2 * (size_t)M), pr(2 * (size_t)M);
+        std::vector<int32_t> ll(M), lr(M);
+        std::vector<uint8_t> inl(M), inr(M), desc((size_t)M * 32);
+        for (int i = 0; i < M; i++) {
+            const MapPointT* mp = mps[i];
+            pl[2 * i] = mp->predL.x; pl[2 * i + 1] = mp->predL.y; pr[2 * i] = mp->predR.x; pr[2 * i + 1] = mp->predR.y;
+            ll[i] = mp->scaleLevelL; lr[i] = mp->scaleLevelR; inl[i] = mp->inFrame; inr[i] = mp->inFrameR;
+            std::memcpy(&desc[(size_t)i * 32], mp->desc.ptr(0), 32);
+        }
+        gvs_mappoints s{M, desc.data(), pl.data(), pr.data(), ll.data(), lr.data(), inl.data(), inr.data()};
+        static_assert(sizeof(std::pair<int, int>) == 8, "pair<int,int> must be two packed ints");
+        int n = 0;
+        gvsCheck(gvs_match_projection(h_, 0, mode, &s, rad, mL.data(), mR ? mR->data() : nullptr,
+                                      reinterpret_cast<int32_t*>(matches.data()), &n));
+        return n;
+    }
+    gvs_matcher* h_ = nullptr;
+};
+
+}  // namespace GTSAM_VIOSLAM
