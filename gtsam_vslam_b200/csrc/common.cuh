@@ -96,6 +96,10 @@ void launchDescribe(const Geometry& g, const uint8_t* slab, const uint8_t* blurS
                     const int* keptCnt, const int* imgOff, gvs_keypoint* kps, uint8_t* desc, int* momentsDbg,
                     int totalCap, cudaStream_t s, int* launches);
 
+void launchDescribeFused(const Geometry& g, const uint8_t* slab, int nImages, const KeptKey* kept, const int* keptCnt,
+                         const int* imgOff, gvs_keypoint* kps, uint8_t* desc, int* momentsDbg, int totalCap, cudaStream_t s,
+                         int* launches);
+
 struct StereoArgs {
     const uint8_t* slabL;
     const uint8_t* slabR;

@@ -72,6 +72,7 @@ struct gvs_extractor {
     int* hStatus = nullptr;
     int lastN = 0;
     bool pending = false;
+    bool blurValid = false;   // the blurred slab is only materialised on demand (parity tap)
     int launches = 0;
     int64_t launchesTotal = 0;
     bool timing = false;
@@ -286,29 +287,17 @@ int runExtract(gvs_extractor* fe, int n) {
     if (T) cudaEventRecord(fe->ev[0], s);
     launchPyramid(g, fe->slab, fe->taps, n, s, &fe->launches);
     if (T) cudaEventRecord(fe->ev[1], s);
-    // blur depends on the pyramid only: fork it onto the aux stream so that it overlaps FAST and selection.
-    // In timing mode every stage runs in order on the main stream so that the stage times are clean.
-    if (!T) {
-        GVS_CUDA_OK(cudaEventRecord(fe->evPyr, s));
-        GVS_CUDA_OK(cudaStreamWaitEvent(fe->auxStream, fe->evPyr, 0));
-        launchBlur(g, fe->slab, fe->blurSlab, fe->blurItems, fe->nBlurItems, n, fe->auxStream, &fe->launches);
-        GVS_CUDA_OK(cudaEventRecord(fe->evBlur, fe->auxStream));
-    }
     launchFast(g, fe->slab, fe->fastItems, fe->nFastItems, n, fe->recs, fe->nCand, fe->cellCnt, fe->status, s, &fe->launches);
     if (T) cudaEventRecord(fe->ev[2], s);
     launchSelect(g, n, fe->recs, fe->nCand, fe->cellCnt, fe->kept, fe->keptCnt, fe->orderedDbg, nullptr, fe->selScratch,
                  fe->selScratchPerCta, fe->selCtas, fe->workCounter, fe->status, s, &fe->launches);
     launchOffsets(g, n, fe->keptCnt, fe->imgOff, fe->totalCap, fe->status, s, &fe->launches);
-    if (T) {
-        cudaEventRecord(fe->ev[3], s);
-        launchBlur(g, fe->slab, fe->blurSlab, fe->blurItems, fe->nBlurItems, n, s, &fe->launches);
-        cudaEventRecord(fe->ev[4], s);
-    } else {
-        GVS_CUDA_OK(cudaStreamWaitEvent(s, fe->evBlur, 0));
-    }
-    launchDescribe(g, fe->slab, fe->blurSlab, n, fe->kept, fe->keptCnt, fe->imgOff, fe->kps, fe->desc, fe->momentsDbg,
-                   fe->totalCap, s, &fe->launches);
+    // the 7x7 blur is fused into the descriptor kernel (evaluated only at the sample positions of the kept keys)
+    if (T) { cudaEventRecord(fe->ev[3], s); cudaEventRecord(fe->ev[4], s); }
+    launchDescribeFused(g, fe->slab, n, fe->kept, fe->keptCnt, fe->imgOff, fe->kps, fe->desc, fe->momentsDbg, fe->totalCap, s,
+                        &fe->launches);
     if (T) cudaEventRecord(fe->ev[5], s);
+    fe->blurValid = false;
     GVS_CUDA_OK(cudaMemcpyAsync(fe->hOff, fe->imgOff, sizeof(int) * (n + 1), cudaMemcpyDeviceToHost, s));
     GVS_CUDA_OK(cudaMemcpyAsync(fe->hStatus, fe->status, sizeof(int), cudaMemcpyDeviceToHost, s));
     GVS_CUDA_OK(cudaEventRecord(fe->doneEvent, s));
@@ -589,6 +578,12 @@ int gvs_debug_level_image(gvs_extractor* fe, int image, int level, int blurred, 
         return fail(GVS_ERR_INVALID, "bad argument");
     GVS_CUDA_OK(cudaSetDevice(fe->device));
     const LevelGeom& lv = fe->g.lv[level];
+    if (blurred && !fe->blurValid && fe->lastN > 0) {  // cv::GaussianBlur of every level, dense (src/FeatureExtractor.cpp:512-515)
+        int launches = 0;
+        launchBlur(fe->g, fe->slab, fe->blurSlab, fe->blurItems, fe->nBlurItems, fe->lastN, fe->stream, &launches);
+        fe->launchesTotal += launches;
+        fe->blurValid = true;
+    }
     const uint8_t* src = (blurred ? fe->blurSlab : fe->slab) + (size_t)image * fe->g.slabBytes + lv.off;
     GVS_CUDA_OK(cudaStreamSynchronize(fe->stream));
     GVS_CUDA_OK(cudaMemcpy2D(out, lv.w, src, lv.pitch, lv.w, lv.h, cudaMemcpyDeviceToHost));

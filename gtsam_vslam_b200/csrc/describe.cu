@@ -40,6 +40,162 @@ __device__ __forceinline__ float fastAtan2Deg(float y, float x) {
     return a;
 }
 
+// Fused form (default): the 7x7 sigma-2 blur (same Q8 taps and rounding as blur7_kernel) is evaluated
+// only where a key needs it.  Per key the warp stages the 43 x 52-byte source patch (reach 18 + 3 taps, reflect-101 at
+// the image border) in shared memory, runs the horizontal pass for the 43 rows (two dp4a per pixel, u16 results in shared
+// memory) and evaluates the vertical pass at the 512 sample positions only.  The blurred slab is neither written nor read.
+constexpr int kPR = 21, kPRows = 2 * kPR + 1, kPWords = 13, kHCols = 44;
+constexpr int kPBytes = (kPRows * kPWords * 4 + 15) & ~15;                       // 2240
+constexpr int kWarpSmemBytes = kPBytes + ((kPRows * kHCols * 2 + 15) & ~15);     // + 3792 = 6032
+
+__device__ __forceinline__ int reflect101i(int p, int n) {
+    while (p < 0 || p >= n) p = p < 0 ? -p : 2 * n - 2 - p;
+    return p;
+}
+
+__global__ void __launch_bounds__(256)
+describe_fused_kernel(const __grid_constant__ Geometry g, const uint8_t* __restrict__ slab, const KeptKey* __restrict__ kept,
+                      const int* __restrict__ keptCnt, const int* __restrict__ imgOff, gvs_keypoint* __restrict__ kps,
+                      uint8_t* __restrict__ desc, int* __restrict__ momentsDbg, int totalCap) {
+    extern __shared__ __align__(16) uint8_t dsm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int img = blockIdx.y;
+    unsigned* P = reinterpret_cast<unsigned*>(dsm + warp * kWarpSmemBytes);
+    unsigned short* H = reinterpret_cast<unsigned short*>(dsm + warp * kWarpSmemBytes + kPBytes);
+    const uint8_t* Pb = reinterpret_cast<const uint8_t*>(P);
+    unsigned pat[8];
+    {
+        const uint4* p = reinterpret_cast<const uint4*>(kPatternDev + lane * 32);
+        const uint4 a = p[0], b = p[1];
+        pat[0] = a.x; pat[1] = a.y; pat[2] = a.z; pat[3] = a.w; pat[4] = b.x; pat[5] = b.y; pat[6] = b.z; pat[7] = b.w;
+    }
+    __shared__ int cnt[kMaxLevels];
+    if (threadIdx.x < kMaxLevels) cnt[threadIdx.x] = threadIdx.x < g.nLevels ? keptCnt[img * kMaxLevels + threadIdx.x] : 0;
+    __syncthreads();
+    const int outBase = imgOff[img];
+    const int warpsPerGrid = gridDim.x * (blockDim.x >> 5);
+    for (int slot = blockIdx.x * (blockDim.x >> 5) + warp; slot < g.keptPerImage; slot += warpsPerGrid) {
+        int level = 0, pre = 0;
+        while (level + 1 < g.nLevels && slot >= g.lv[level + 1].keptOff) { pre += cnt[level]; level++; }
+        const LevelGeom& lv = g.lv[level];
+        const int i = slot - lv.keptOff;
+        if (i >= cnt[level]) continue;
+        const int o = outBase + pre + i;
+        if (o >= totalCap) continue;
+        const unsigned q = kept[(size_t)img * g.keptPerImage + slot];
+        const int x = q & 0xfff, y = (q >> 12) & 0xfff, score = q >> 24;
+        const uint8_t* src = levelPtr(slab, g, img, level);
+        const int xs = ((x - kPR) & ~3) - 4, ys = y - kPR, ox = x - xs;  // ox in [25, 28]
+
+        // ---- stage the patch
+        __syncwarp();
+        if (x - kPR >= 4 && x + kPR + 8 <= lv.w && ys >= 0 && ys + kPRows <= lv.h) {
+            for (int t = lane; t < kPRows * kPWords; t += 32) {
+                const int r = t / kPWords, c = t - r * kPWords;
+                P[t] = __ldg(reinterpret_cast<const unsigned*>(src + (size_t)(ys + r) * lv.pitch + xs) + c);
+            }
+        } else {  // within 21 px of the image border: reflect-101, byte by byte
+            for (int t = lane; t < kPRows * kPWords; t += 32) {
+                const int r = t / kPWords, c = t - r * kPWords;
+                const uint8_t* row = src + (size_t)reflect101i(ys + r, lv.h) * lv.pitch;
+                unsigned v = 0;
+#pragma unroll
+                for (int b = 0; b < 4; b++) v |= (unsigned)row[reflect101i(xs + 4 * c + b, lv.w)] << (8 * b);
+                P[t] = v;
+            }
+        }
+        __syncwarp();
+
+        // ---- orientation: lane = row of the radius-15 disc
+        int m10 = 0, m01 = 0;
+        if (lane < 2 * kHalfPatch + 1) {
+            const int v = lane - kHalfPatch;
+            const int d = g.umax[v < 0 ? -v : v];
+            const uint8_t* row = Pb + (kPR + v) * (kPWords * 4) + ox;
+            int s0 = 0, s1 = 0;
+            for (int u = -d; u <= d; u++) { const int val = row[u]; s0 += val; s1 += u * val; }
+            m10 = s1;
+            m01 = v * s0;
+        }
+#pragma unroll
+        for (int off = 16; off; off >>= 1) { m10 += __shfl_xor_sync(0xffffffffu, m10, off); m01 += __shfl_xor_sync(0xffffffffu, m01, off); }
+        const float angle = fastAtan2Deg((float)m01, (float)m10);
+
+        // ---- horizontal blur pass on the patch: unit = (row, word m in 1..11) -> 4 u16 results
+        const unsigned tLo = 0x38302212u, tHi = 0x00122230u;  // {18,34,48,56}, {48,34,18,0}
+        for (int t = lane; t < kPRows * 11; t += 32) {
+            const int r = t / 11, m = 1 + (t - r * 11);
+            const unsigned* w = P + r * kPWords + m;
+            const unsigned w0 = w[-1], w1 = w[0], w2 = w[1];
+            unsigned h[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const unsigned a = j == 3 ? w1 : __funnelshift_r(w0, w1, 8 * (1 + j));
+                const unsigned b = j == 3 ? w2 : __funnelshift_r(w1, w2, 8 * (1 + j));
+                h[j] = __dp4a(a, tLo, __dp4a(b, tHi, 0u));
+            }
+            *reinterpret_cast<uint2*>(H + r * kHCols + 4 * (m - 1)) = make_uint2(h[0] | (h[1] << 16), h[2] | (h[3] << 16));
+        }
+        __syncwarp();
+
+        // ---- rotated BRIEF on vertically blurred samples
+        const float factorPI = (float)(3.14159265358979323846 / 180.0);
+        const float ang = __fmul_rn(angle, factorPI);
+        const float a = (float)cos((double)ang), b = (float)sin((double)ang);
+        const unsigned short* Hc = H + kPR * kHCols + (ox - 4);  // H[row of the key][column of the key]
+        auto sample = [&](float px, float py) {
+            const int iy = __float2int_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)));
+            const int ix = __float2int_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)));
+            const unsigned short* c = Hc + iy * kHCols + ix;
+            const unsigned acc = 32768u + 18u * (c[-3 * kHCols] + c[3 * kHCols]) + 34u * (c[-2 * kHCols] + c[2 * kHCols]) +
+                                 48u * (c[-kHCols] + c[kHCols]) + 56u * c[0];
+            return (int)(acc >> 16);
+        };
+        unsigned byte = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const unsigned w = pat[j];
+            const int t0 = sample((float)(int8_t)(w & 0xff), (float)(int8_t)((w >> 8) & 0xff));
+            const int t1 = sample((float)(int8_t)((w >> 16) & 0xff), (float)(int8_t)(w >> 24));
+            byte |= (unsigned)(t0 < t1) << j;
+        }
+        desc[(size_t)o * 32 + lane] = (uint8_t)byte;
+
+        if (lane < 7) {
+            float fx = (float)x, fy = (float)y;
+            if (level != 0) { fx = __fmul_rn(fx, lv.scale); fy = __fmul_rn(fy, lv.scale); }
+            unsigned wv;
+            switch (lane) {
+                case 0: wv = __float_as_uint(fx); break;
+                case 1: wv = __float_as_uint(fy); break;
+                case 2: wv = __float_as_uint((float)lv.scaledPatch); break;
+                case 3: wv = __float_as_uint(angle); break;
+                case 4: wv = __float_as_uint((float)score); break;
+                case 5: wv = (unsigned)level; break;
+                default: wv = 0xffffffffu; break;
+            }
+            reinterpret_cast<unsigned*>(kps + o)[lane] = wv;
+        }
+        if (momentsDbg && lane == 0) { momentsDbg[2 * o] = m10; momentsDbg[2 * o + 1] = m01; }
+    }
+}
+
+void launchDescribeFused(const Geometry& g, const uint8_t* slab, int nImages, const KeptKey* kept, const int* keptCnt,
+                         const int* imgOff, gvs_keypoint* kps, uint8_t* desc, int* momentsDbg, int totalCap, cudaStream_t s,
+                         int* launches) {
+    const int warpsPerCta = 8;
+    const int smem = warpsPerCta * kWarpSmemBytes;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(describe_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        configured = true;
+    }
+    int gx = (g.keptPerImage + 2 * warpsPerCta - 1) / (2 * warpsPerCta);
+    if (gx < 1) gx = 1;
+    describe_fused_kernel<<<dim3(gx, nImages), 32 * warpsPerCta, smem, s>>>(g, slab, kept, keptCnt, imgOff, kps, desc, momentsDbg, totalCap);
+    ++*launches;
+}
+
 __global__ void __launch_bounds__(256)
 describe_kernel(const __grid_constant__ Geometry g, const uint8_t* __restrict__ slab, const uint8_t* __restrict__ blurSlab,
                 const KeptKey* __restrict__ kept, const int* __restrict__ keptCnt, const int* __restrict__ imgOff,

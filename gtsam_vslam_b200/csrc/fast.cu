@@ -14,13 +14,16 @@
 //
 // Work item = up to 4 consecutive cells of one cell row (about 150 x 40 px); CTA = 256 threads.
 //   1. the (rows+6) x (cols+6) u8 tile is staged in shared memory with 4-byte loads;
-//   2. scores are computed two pixels at a time in u16x2 lanes with the native VIMNMX3.U16x2 min/max
-//      (9-wide circular min/max as min3 of min3: 32 + 8 instructions per polarity per pixel pair);
-//   3. local maxima are appended to a per-cell list in shared memory, filtered by T_cell, ranked in
-//      row-major order inside the cell (k^2/2 compares on ~20 entries) and written as 8-byte records
-//      {x, y, score, cell, rank} to a per-(image, level) buffer; K3/K4 (select.cu) restores the reference's
-//      emission order from (cell, rank).
-// Bound: integer ALU (about 50 lane-ops per pixel), not HBM: see DESIGN.md.
+//   2a. a pre-test on 4 pixels per instruction (VABSDIFF4 on the up/down and left/right ring pairs) discards pixels that
+//      cannot be corners at the minimum threshold; survivors are compacted pair-wise into shared-memory queues;
+//   2b. exact scores of the surviving pairs in u16x2 lanes: 21 word loads, ring pairs extracted with PRMT
+//      (lane = 257 * pixel), 9-wide circular min/max as min3 of min3 with the native VIMNMX3.U16x2
+//      (78 instructions per pair for both polarities);
+//   3. strict local maxima, four pixels at a time (vcmpgtu4 against the 8 shifted neighbour words, masked at cell
+//      borders), are appended to a per-cell list in shared memory, filtered by T_cell, ranked in row-major order
+//      inside the cell and written as 8-byte records {x, y, score, cell, rank} to a per-(image, level) buffer;
+//      K3/K4 (select.cu) restores the reference's emission order from (cell, rank).
+// Bound: integer ALU, not HBM: see DESIGN.md.
 #include "common.cuh"
 
 namespace gvs {
@@ -33,7 +36,7 @@ struct FastSmemLayout {
     int tileWords, tileRows;    // image tile: words per row, rows
     int scoreWords, scoreRows;  // score tile: words per row (1 zero word each side), rows (1 zero row each side)
     int listCap;                // entries per cell list
-    int tileOff, scoreOff, listOff, maskOff, total;
+    int tileOff, scoreOff, listOff, maskOff, queueOff, queueCap, total;
 };
 
 __host__ __device__ inline FastSmemLayout fastLayout(int maxGW, int maxGH) {
@@ -48,7 +51,9 @@ __host__ __device__ inline FastSmemLayout fastLayout(int maxGW, int maxGH) {
     L.scoreOff = L.tileOff + L.tileWords * L.tileRows * 4;
     L.maskOff = L.scoreOff + L.scoreWords * L.scoreRows * 4;
     L.listOff = ((L.maskOff + maxUnits * 12 + 15) / 16) * 16;
-    L.total = L.listOff + kFastCellsPerItem * L.listCap * 4;
+    L.queueOff = L.listOff + kFastCellsPerItem * L.listCap * 4;
+    L.queueCap = maxUnits * maxGH;                       // per pair parity
+    L.total = L.queueOff + 2 * L.queueCap * 2;
     return L;
 }
 
@@ -158,9 +163,52 @@ fast_cells_kernel(const __grid_constant__ Geometry g, const uint8_t* __restrict_
     }
     __syncthreads();
 
-    // ---- 2. scores: one unit word (4 px = 2 pairs) per step, 21 word loads, ring pairs by PRMT
+    // ---- 2a. pre-test on 4 pixels at once (native VABSDIFF4): a 9-arc contains ring pixel k or k+8 for every k, so a
+    // corner at threshold t needs |I(ring_k) - I(p)| > t for k in {0 or 8} and for k in {4 or 12}.  ">" is relaxed to
+    // "some bit at or above floor(log2(t+1)) set" (exact for t = 2^m - 1, e.g. the reference's 7; conservative otherwise).
+    // Surviving pixel pairs are compacted into two queues (one per pair position, so that 2b has no divergent code).
+    unsigned short* queue = reinterpret_cast<unsigned short*>(smem + L.queueOff);
+    __shared__ int sQ[2];
+    if (tid < 2) sQ[tid] = 0;
+    __syncthreads();
     const int tMin = g.tMin;
-    for (int i = tid; i < nW * rows; i += 256) {
+    const unsigned hiMask = (~((1u << (31 - __clz(tMin + 1))) - 1u) & 0xffu) * 0x01010101u;
+    const unsigned ltMask = (1u << (tid & 31)) - 1u;
+    const int nUnits = nW * rows;
+    for (int base = 0; base < nUnits; base += 256) {
+        const int i = base + tid;
+        bool p0 = false, p1 = false;
+        if (i < nUnits) {
+            const int ry = (int)__umulhi((unsigned)i, magicU), j = i - ry * nW;
+            const unsigned* p = tile + (ry + 3) * L.tileWords + j;
+            const unsigned c = p[1];
+            const unsigned up = p[1 - 3 * L.tileWords], dn = p[1 + 3 * L.tileWords];
+            const unsigned lf = __funnelshift_r(p[0], c, 8), rt = __funnelshift_r(c, p[2], 24);
+            const unsigned v = (__vabsdiffu4(up, c) | __vabsdiffu4(dn, c)) & hiMask;
+            const unsigned h = (__vabsdiffu4(lf, c) | __vabsdiffu4(rt, c)) & hiMask;
+            const unsigned nzv = (v | ((v | 0x80808080u) - 0x01010101u)), nzh = (h | ((h | 0x80808080u) - 0x01010101u));
+            const unsigned f = nzv & nzh & 0x80808080u & masks[3 * j];
+            p0 = (f & 0x0000ffffu) != 0;
+            p1 = (f & 0xffff0000u) != 0;
+        }
+        const unsigned b0 = __ballot_sync(0xffffffffu, p0), b1 = __ballot_sync(0xffffffffu, p1);
+        int o0 = 0, o1 = 0;
+        if ((tid & 31) == 0) {
+            if (b0) o0 = atomicAdd(&sQ[0], __popc(b0));
+            if (b1) o1 = atomicAdd(&sQ[1], __popc(b1));
+        }
+        o0 = __shfl_sync(0xffffffffu, o0, 0); o1 = __shfl_sync(0xffffffffu, o1, 0);
+        if (p0) queue[o0 + __popc(b0 & ltMask)] = (unsigned short)i;
+        if (p1) queue[L.queueCap + o1 + __popc(b1 & ltMask)] = (unsigned short)i;
+    }
+    __syncthreads();
+
+    // ---- 2b. exact scores of the surviving pairs: 21 word loads, ring pairs by PRMT, min3-of-min3 arcs
+    unsigned short* score16 = reinterpret_cast<unsigned short*>(score);
+    const int n0 = sQ[0], n1 = sQ[1];
+    for (int q = tid; q < n0 + n1; q += 256) {
+        const bool second = q >= n0;
+        const int i = second ? queue[L.queueCap + q - n0] : queue[q];
         const int ry = (int)__umulhi((unsigned)i, magicU), j = i - ry * nW;
         unsigned W[7][3];
 #pragma unroll
@@ -168,8 +216,9 @@ fast_cells_kernel(const __grid_constant__ Geometry g, const uint8_t* __restrict_
             const unsigned* p = tile + (ry + r) * L.tileWords + j;
             W[r][0] = p[0]; W[r][1] = p[1]; W[r][2] = p[2];
         }
-        const unsigned s = (scorePair<0>(W, tMin) | (scorePair<1>(W, tMin) << 16)) & masks[3 * j];
-        score[(ry + 1) * L.scoreWords + j + 1] = s;
+        const unsigned m = masks[3 * j];
+        if (!second) score16[2 * ((ry + 1) * L.scoreWords + j + 1)] = (unsigned short)(scorePair<0>(W, tMin) & m);
+        else score16[2 * ((ry + 1) * L.scoreWords + j + 1) + 1] = (unsigned short)(scorePair<1>(W, tMin) & (m >> 16));
     }
     __syncthreads();
 

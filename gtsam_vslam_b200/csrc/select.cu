@@ -340,9 +340,11 @@ __device__ void sortDescending(const SelArrays<IdxT>& A, SelShared& S, int n) {
 // knocks out the later lanes that fall inside), so the result is exactly the sequential greedy cover.
 // floor(y / c), c = width / 2.0  ==  (2*y) / width in integers (exact: a non-integer quotient is at least
 // 1/width away from an integer, far more than the double rounding error; an integer quotient is exact).
+// `limit`: a speculative pass may stop as soon as it has kept more than `limit` points (the search only needs to know
+// "more than Kmax" to choose its direction); it then returns limit + 1 and its list is incomplete.
 template <typename IdxT>
 __device__ int sscPassWarp(const unsigned* xy, const IdxT* sorted, int n, int width, int ncc, int ncr, unsigned* bitmap,
-                           IdxT* list, int listCap, int lane) {
+                           IdxT* list, int listCap, int lane, int limit) {
     const int bmWords = (ncc * ncr + 31) >> 5;
     for (int i = lane; i < bmWords; i += 32) bitmap[i] = 0;
     __syncwarp();
@@ -379,6 +381,7 @@ __device__ int sscPassWarp(const unsigned* xy, const IdxT* sorted, int n, int wi
             mask = __ballot_sync(0xffffffffu, active);
         }
         __syncwarp();
+        if (cnt > limit) return limit + 1;
     }
     return cnt;
 }
@@ -414,10 +417,10 @@ __device__ int sscSearch(const SelArrays<IdxT>& A, SelShared& S, const IdxT* sor
             if (rootFits) {
                 if (valid && fits(warp))
                     c = sscPassWarp(A.xy, sorted, n, nw[warp], (2 * cols) / nw[warp] + 1, (2 * rows) / nw[warp] + 1,
-                                    bitmaps + warp * kSscBitmapWords, lists + warp * listCap, listCap, lane);
+                                    bitmaps + warp * kSscBitmapWords, lists + warp * listCap, listCap, lane, lv.kmax);
             } else if (warp == 0) {  // tiny width: one pass, bitmap in global scratch
                 c = sscPassWarp(A.xy, sorted, n, nw[0], (2 * cols) / nw[0] + 1, (2 * rows) / nw[0] + 1, globalBitmap, lists,
-                                listCap, lane);
+                                listCap, lane, lv.kmax);
             }
             if (lane == 0) S.wA[warp] = c;
         }
@@ -436,7 +439,23 @@ __device__ int sscSearch(const SelArrays<IdxT>& A, SelShared& S, const IdxT* sor
             k = child;
         }
         __syncthreads();
-        if (done) break;
+        if (done) {
+            if (finalCount > lv.kmax) {
+                // bracket exhausted on a truncated pass: the reference returns that pass in full (:412-416) -> redo it
+                const int w = nw[finalNode];
+                const int ncc = (2 * cols) / w + 1, ncr = (2 * rows) / w + 1;
+                const bool fitsSmem = ncc * ncr <= kSscBitmapWords * 32;
+                if (warp == 0) {
+                    const int c = sscPassWarp(A.xy, sorted, n, w, ncc, ncr, fitsSmem ? bitmaps : globalBitmap, lists, listCap, lane,
+                                              0x7fffffff);
+                    if (lane == 0) S.wA[0] = c;
+                }
+                __syncthreads();
+                finalNode = 0; finalCount = S.wA[0];
+                __syncthreads();
+            }
+            break;
+        }
     }
     *outList = finalNode >= 0 ? lists + finalNode * listCap : lists;
     return finalNode >= 0 ? finalCount : 0;
