@@ -53,58 +53,103 @@ __device__ __forceinline__ int reflect101i(int p, int n) {
     return p;
 }
 
-__global__ void __launch_bounds__(256)
+constexpr int kDescWarpBytes = 2 * kPBytes + ((kPRows * kHCols * 2 + 15) & ~15);  // two patch buffers + H = 8272
+
+__device__ __forceinline__ void cpAsync4(void* smemDst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smemDst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc));
+}
+
+struct KeyRef { int level, x, y, score, xs, ys; };
+
+__global__ void __launch_bounds__(256, 3)
 describe_fused_kernel(const __grid_constant__ Geometry g, const uint8_t* __restrict__ slab, const KeptKey* __restrict__ kept,
                       const int* __restrict__ keptCnt, const int* __restrict__ imgOff, gvs_keypoint* __restrict__ kps,
                       uint8_t* __restrict__ desc, int* __restrict__ momentsDbg, int totalCap) {
     extern __shared__ __align__(16) uint8_t dsm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int img = blockIdx.y;
-    unsigned* P = reinterpret_cast<unsigned*>(dsm + warp * kWarpSmemBytes);
-    unsigned short* H = reinterpret_cast<unsigned short*>(dsm + warp * kWarpSmemBytes + kPBytes);
-    const uint8_t* Pb = reinterpret_cast<const uint8_t*>(P);
+    uint8_t* wbase = dsm + warp * kDescWarpBytes;
+    unsigned short* H = reinterpret_cast<unsigned short*>(wbase + 2 * kPBytes);
     unsigned pat[8];
     {
         const uint4* p = reinterpret_cast<const uint4*>(kPatternDev + lane * 32);
         const uint4 a = p[0], b = p[1];
         pat[0] = a.x; pat[1] = a.y; pat[2] = a.z; pat[3] = a.w; pat[4] = b.x; pat[5] = b.y; pat[6] = b.z; pat[7] = b.w;
     }
-    __shared__ int cnt[kMaxLevels];
-    if (threadIdx.x < kMaxLevels) cnt[threadIdx.x] = threadIdx.x < g.nLevels ? keptCnt[img * kMaxLevels + threadIdx.x] : 0;
+    __shared__ int pre[kMaxLevels + 1];  // keys of this image before level l (dense output order)
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int l = 0; l < kMaxLevels; l++) { pre[l] = run; run += l < g.nLevels ? keptCnt[img * kMaxLevels + l] : 0; }
+        pre[kMaxLevels] = run;
+    }
     __syncthreads();
-    const int outBase = imgOff[img];
+    const int outBase = imgOff[img], nKeys = pre[kMaxLevels];
     const int warpsPerGrid = gridDim.x * (blockDim.x >> 5);
-    for (int slot = blockIdx.x * (blockDim.x >> 5) + warp; slot < g.keptPerImage; slot += warpsPerGrid) {
-        int level = 0, pre = 0;
-        while (level + 1 < g.nLevels && slot >= g.lv[level + 1].keptOff) { pre += cnt[level]; level++; }
-        const LevelGeom& lv = g.lv[level];
-        const int i = slot - lv.keptOff;
-        if (i >= cnt[level]) continue;
-        const int o = outBase + pre + i;
-        if (o >= totalCap) continue;
-        const unsigned q = kept[(size_t)img * g.keptPerImage + slot];
-        const int x = q & 0xfff, y = (q >> 12) & 0xfff, score = q >> 24;
-        const uint8_t* src = levelPtr(slab, g, img, level);
-        const int xs = ((x - kPR) & ~3) - 4, ys = y - kPR, ox = x - xs;  // ox in [25, 28]
 
-        // ---- stage the patch
-        __syncwarp();
-        if (x - kPR >= 4 && x + kPR + 8 <= lv.w && ys >= 0 && ys + kPRows <= lv.h) {
-            for (int t = lane; t < kPRows * kPWords; t += 32) {
-                const int r = t / kPWords, c = t - r * kPWords;
-                P[t] = __ldg(reinterpret_cast<const unsigned*>(src + (size_t)(ys + r) * lv.pitch + xs) + c);
-            }
-        } else {  // within 21 px of the image border: reflect-101, byte by byte
-            for (int t = lane; t < kPRows * kPWords; t += 32) {
-                const int r = t / kPWords, c = t - r * kPWords;
-                const uint8_t* row = src + (size_t)reflect101i(ys + r, lv.h) * lv.pitch;
-                unsigned v = 0;
+    auto keyOf = [&](int k) {
+        KeyRef r;
+        int level = 0;
 #pragma unroll
-                for (int b = 0; b < 4; b++) v |= (unsigned)row[reflect101i(xs + 4 * c + b, lv.w)] << (8 * b);
+        for (int l = 1; l < kMaxLevels; l++) level += k >= pre[l] && l < g.nLevels;
+        const unsigned q = kept[(size_t)img * g.keptPerImage + g.lv[level].keptOff + (k - pre[level])];
+        r.level = level; r.x = q & 0xfff; r.y = (q >> 12) & 0xfff; r.score = q >> 24;
+        r.xs = ((r.x - kPR) & ~3) - 4; r.ys = r.y - kPR;
+        return r;
+    };
+    // stage the 43 x 13-word patch of a key into `P` asynchronously: aligned 4-byte cp.async for interior keys; keys whose
+    // patch touches the image border (they sit >= 19 px inside, the patch reaches 21 + alignment) use reflect-101 loads
+    auto stage = [&](const KeyRef& kr, unsigned* P) {
+        const LevelGeom& lv = g.lv[kr.level];
+        const uint8_t* src = levelPtr(slab, g, img, kr.level);
+        if (kr.xs >= 0 && kr.xs + 4 * kPWords <= lv.w && kr.ys >= 0 && kr.ys + kPRows <= lv.h) {
+            const uint8_t* base = src + (size_t)kr.ys * lv.pitch + kr.xs;
+#pragma unroll 6
+            for (int t = lane; t < kPRows * kPWords; t += 32) {
+                const int r = t / kPWords, c = t - r * kPWords;
+                cpAsync4(P + t, base + (size_t)r * lv.pitch + 4 * c);
+            }
+        } else {
+            for (int t = lane; t < kPRows * kPWords; t += 32) {
+                const int r = t / kPWords, c = t - r * kPWords;
+                int iy = kr.ys + r;
+                iy = iy < 0 ? -iy : (iy >= lv.h ? 2 * lv.h - 2 - iy : iy);
+                const uint8_t* row = src + (size_t)iy * lv.pitch;
+                const int gx = kr.xs + 4 * c;
+                unsigned v;
+                if (gx >= 0 && gx + 3 < lv.w) v = __ldg(reinterpret_cast<const unsigned*>(row + gx));
+                else {
+                    v = 0;
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        int xx = gx + b;
+                        xx = xx < 0 ? -xx : (xx >= lv.w ? 2 * lv.w - 2 - xx : xx);
+                        v |= (unsigned)row[xx] << (8 * b);
+                    }
+                }
                 P[t] = v;
             }
         }
+        asm volatile("cp.async.commit_group;\n" ::);
+    };
+
+    int k = blockIdx.x * (blockDim.x >> 5) + warp;
+    int buf = 0;
+    KeyRef cur{};
+    if (k < nKeys) { cur = keyOf(k); stage(cur, reinterpret_cast<unsigned*>(wbase)); }
+    for (; k < nKeys; k += warpsPerGrid, buf ^= 1) {
+        unsigned* P = reinterpret_cast<unsigned*>(wbase + buf * kPBytes);
+        const uint8_t* Pb = reinterpret_cast<const uint8_t*>(P);
+        const int level = cur.level, x = cur.x, y = cur.y, score = cur.score, ox = cur.x - cur.xs;  // ox in [25, 28]
+        const LevelGeom& lv = g.lv[level];
+        const int o = outBase + k;
+        // prefetch the next key's patch into the other buffer, then wait for this key's
+        KeyRef nxt{};
+        const bool more = k + warpsPerGrid < nKeys;
+        if (more) { nxt = keyOf(k + warpsPerGrid); stage(nxt, reinterpret_cast<unsigned*>(wbase + (buf ^ 1) * kPBytes)); }
+        if (more) asm volatile("cp.async.wait_group 1;\n" ::); else asm volatile("cp.async.wait_group 0;\n" ::);
         __syncwarp();
+        if (o >= totalCap) { cur = nxt; continue; }
 
         // ---- orientation: lane = row of the radius-15 disc
         int m10 = 0, m01 = 0;
@@ -177,6 +222,8 @@ describe_fused_kernel(const __grid_constant__ Geometry g, const uint8_t* __restr
             reinterpret_cast<unsigned*>(kps + o)[lane] = wv;
         }
         if (momentsDbg && lane == 0) { momentsDbg[2 * o] = m10; momentsDbg[2 * o + 1] = m01; }
+        cur = nxt;
+        __syncwarp();  // everyone is done with H and this patch buffer before they are refilled
     }
 }
 
@@ -184,13 +231,14 @@ void launchDescribeFused(const Geometry& g, const uint8_t* slab, int nImages, co
                          const int* imgOff, gvs_keypoint* kps, uint8_t* desc, int* momentsDbg, int totalCap, cudaStream_t s,
                          int* launches) {
     const int warpsPerCta = 8;
-    const int smem = warpsPerCta * kWarpSmemBytes;
+    const int smem = warpsPerCta * kDescWarpBytes;
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(describe_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         configured = true;
     }
-    int gx = (g.keptPerImage + 2 * warpsPerCta - 1) / (2 * warpsPerCta);
+    // keys per image are only known on the device (about keptPerImage / 2): 3 keys per warp on average, grid-stride loop
+    int gx = (g.keptPerImage / 2 + 3 * warpsPerCta - 1) / (3 * warpsPerCta);
     if (gx < 1) gx = 1;
     describe_fused_kernel<<<dim3(gx, nImages), 32 * warpsPerCta, smem, s>>>(g, slab, kept, keptCnt, imgOff, kps, desc, momentsDbg, totalCap);
     ++*launches;

@@ -389,7 +389,7 @@ __device__ int sscPassWarp(const unsigned* xy, const IdxT* sorted, int n, int wi
 // The reference's binary search over the width.  The widths it can visit form a binary tree; three levels of
 // the tree (7 nodes) are evaluated speculatively by 7 warps at once, then the path is walked with the counts.
 // Returns the kept count; `outList` (shared, listCap entries) receives the kept sorted-positions.
-constexpr int kSscBitmapWords = 512;  // per-warp shared bitmap: 16384 cells
+constexpr int kSscBitmapWords = 384;  // per-warp shared bitmap: 12288 cells (keeps the CTA at 3 per SM)
 template <typename IdxT>
 __device__ int sscSearch(const SelArrays<IdxT>& A, SelShared& S, const IdxT* sorted, int n, const LevelGeom& lv,
                          unsigned* bitmaps, IdxT* lists, int listCap, unsigned* globalBitmap, const IdxT** outList) {
