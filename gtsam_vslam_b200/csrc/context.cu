@@ -46,6 +46,9 @@ struct gvs_extractor {
     uint8_t* blurSlab = nullptr;
     uint8_t* tight = nullptr;   // staging for tightly packed host batches (one contiguous DMA, then repack)
     ResizeTap* taps = nullptr;
+    uint4* xWeights = nullptr;        // per group of 4 destination columns: a0 | a1 << 16 of each column
+    uint4* xSelectors = nullptr;      // ... PRMT selector (| 1 << 16 when the pair sits in the upper 8 bytes of the window)
+    unsigned short* xBase = nullptr;  // ... 4-byte aligned source offset of the 12-byte window
     FastItem* fastItems = nullptr;
     int nFastItems = 0;
     BlurItem* blurItems = nullptr;
@@ -262,7 +265,7 @@ void destroyExtractor(gvs_extractor* fe) {
     if (!fe) return;
     cudaSetDevice(fe->device);
     if (fe->ownStream) cudaStreamSynchronize(fe->ownStream);
-    cudaFree(fe->slab); cudaFree(fe->blurSlab); cudaFree(fe->tight); cudaFree(fe->taps); cudaFree(fe->fastItems); cudaFree(fe->blurItems);
+    cudaFree(fe->slab); cudaFree(fe->blurSlab); cudaFree(fe->tight); cudaFree(fe->xWeights); cudaFree(fe->xSelectors); cudaFree(fe->xBase); cudaFree(fe->taps); cudaFree(fe->fastItems); cudaFree(fe->blurItems);
     cudaFree(fe->recs); cudaFree(fe->nCand); cudaFree(fe->cellCnt); cudaFree(fe->kept); cudaFree(fe->keptCnt);
     cudaFree(fe->imgOff); cudaFree(fe->orderedDbg); cudaFree(fe->sortedDbg); cudaFree(fe->momentsDbg); cudaFree(fe->selScratch);
     cudaFree(fe->workCounter); cudaFree(fe->status); cudaFree(fe->kps); cudaFree(fe->desc);
@@ -285,7 +288,7 @@ int runExtract(gvs_extractor* fe, int n) {
     const bool T = fe->timing;
     GVS_CUDA_OK(cudaMemsetAsync(fe->status, 0, sizeof(int), s));
     if (T) cudaEventRecord(fe->ev[0], s);
-    launchPyramid(g, fe->slab, fe->taps, n, s, &fe->launches);
+    launchPyramid(g, fe->slab, fe->taps, fe->xWeights, fe->xSelectors, fe->xBase, n, s, &fe->launches);
     if (T) cudaEventRecord(fe->ev[1], s);
     launchFast(g, fe->slab, fe->fastItems, fe->nFastItems, n, fe->recs, fe->nCand, fe->cellCnt, fe->status, s, &fe->launches);
     if (T) cudaEventRecord(fe->ev[2], s);
@@ -398,6 +401,32 @@ int gvs_extractor_create(gvs_extractor** out, const gvs_extractor_params* params
         buildTaps(fe, taps, std::max(nTaps, 4));
         GVS_TRY(devAlloc(&fe->taps, taps.size()));
         GVS_TRY(cudaMemcpy(fe->taps, taps.data(), taps.size() * sizeof(ResizeTap), cudaMemcpyHostToDevice));
+        // horizontal taps regrouped for pyr_down_kernel: 4 destination columns share one 12-byte source window
+        const size_t nGroups = taps.size() / 4 + 1;
+        std::vector<unsigned> w(4 * nGroups, 0), sl(4 * nGroups, 0);
+        std::vector<unsigned short> base(nGroups, 0);
+        for (int l = 1; l < g.nLevels; l++) {
+            const LevelGeom& D = g.lv[l];
+            for (int dx0 = 0; dx0 < D.w; dx0 += 4) {
+                const size_t gi = (size_t)(D.tabX + dx0) / 4;
+                const int b = taps[D.tabX + dx0].ofs & ~3;
+                base[gi] = (unsigned short)b;
+                for (int i = 0; i < 4 && dx0 + i < D.w; i++) {
+                    const ResizeTap& t = taps[D.tabX + dx0 + i];
+                    const int o = t.ofs - b, o1 = t.pad - b;
+                    if (o < 0 || o1 > 11 || o1 < o) { int rc = fail(GVS_ERR_INVALID, "im_scale too large for the pyramid kernel's 12-byte source window"); destroyExtractor(fe); return rc; }
+                    const int hi = o >= 4;
+                    w[4 * gi + i] = (unsigned)(unsigned short)t.a0 | ((unsigned)(unsigned short)t.a1 << 16);
+                    sl[4 * gi + i] = (unsigned)(o - 4 * hi) | ((unsigned)(o1 - 4 * hi) << 4) | ((unsigned)hi << 16);
+                }
+            }
+        }
+        GVS_TRY(devAlloc(&fe->xWeights, nGroups));
+        GVS_TRY(devAlloc(&fe->xSelectors, nGroups));
+        GVS_TRY(devAlloc(&fe->xBase, nGroups));
+        GVS_TRY(cudaMemcpy(fe->xWeights, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
+        GVS_TRY(cudaMemcpy(fe->xSelectors, sl.data(), sl.size() * 4, cudaMemcpyHostToDevice));
+        GVS_TRY(cudaMemcpy(fe->xBase, base.data(), base.size() * 2, cudaMemcpyHostToDevice));
     }
     {
         std::vector<FastItem> items;

@@ -12,12 +12,17 @@
 
 namespace gvs {
 
+// Thread = 4 consecutive destination pixels of one row.  Their source bytes lie in a 12-byte window that starts at a
+// 4-byte aligned offset which is the same for every row, so the host stores, per group of 4 columns, the window offset
+// and per column {a0 | a1 << 16, PRMT selector of (S[sx], S[sx+1]) inside the window}.  Per pixel: 2 PRMT + 2 IDP2A for
+// the two horizontal interpolations, then the fixed-point vertical blend.  3 aligned word loads per source row.
 __global__ void __launch_bounds__(256)
 pyr_down_kernel(const __grid_constant__ Geometry g, uint8_t* __restrict__ slab, const ResizeTap* __restrict__ taps,
-                int level) {
+                const uint4* __restrict__ xw, const uint4* __restrict__ xs, const unsigned short* __restrict__ xbase, int level) {
     const LevelGeom& S = g.lv[level - 1];
     const LevelGeom& D = g.lv[level];
-    const int dx0 = (blockIdx.x * 32 + threadIdx.x) * 4;
+    const int grp = blockIdx.x * 32 + threadIdx.x;  // group of 4 destination columns
+    const int dx0 = grp * 4;
     const int dy = blockIdx.y * 8 + threadIdx.y;
     if (dx0 >= D.w || dy >= D.h) return;
     const int img = blockIdx.z;
@@ -25,23 +30,24 @@ pyr_down_kernel(const __grid_constant__ Geometry g, uint8_t* __restrict__ slab, 
     uint8_t* dst = levelPtr(slab, g, img, level);
 
     const ResizeTap ty = taps[D.tabY + dy];
-    const uint8_t* r0 = src + (size_t)ty.ofs * S.pitch;
-    const uint8_t* r1 = src + (size_t)ty.pad * S.pitch;
-    const int b0 = ty.a0, b1 = ty.a1;
-
-    // four column taps = 32 bytes, 16-byte aligned (tabX is a multiple of 4)
-    const uint4* tp = reinterpret_cast<const uint4*>(taps + D.tabX + dx0);
-    const uint4 t01 = __ldg(tp), t23 = __ldg(tp + 1);
-    const unsigned tw[8] = {t01.x, t01.y, t01.z, t01.w, t23.x, t23.y, t23.z, t23.w};
+    const int gi = D.tabX / 4 + grp;
+    const unsigned base = xbase[gi];
+    const unsigned* r0 = reinterpret_cast<const unsigned*>(src + (size_t)ty.ofs * S.pitch + base);
+    const unsigned* r1 = reinterpret_cast<const unsigned*>(src + (size_t)ty.pad * S.pitch + base);
+    const unsigned p0 = __ldg(r0), p1 = __ldg(r0 + 1), p2 = __ldg(r0 + 2);
+    const unsigned q0 = __ldg(r1), q1 = __ldg(r1 + 1), q2 = __ldg(r1 + 2);
+    const uint4 wv = __ldg(xw + gi), sv = __ldg(xs + gi);
+    const unsigned wts[4] = {wv.x, wv.y, wv.z, wv.w}, sel[4] = {sv.x, sv.y, sv.z, sv.w};
+    const unsigned b0 = (unsigned)ty.a0, b1 = (unsigned)ty.a1;
     unsigned out = 0;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        const int sx = (int)(tw[2 * i] & 0xffff), a0 = (int)(short)(tw[2 * i] >> 16);
-        const int a1 = (int)(short)(tw[2 * i + 1] & 0xffff), sx1 = (int)(tw[2 * i + 1] >> 16);
-        const int h0 = r0[sx] * a0 + r0[sx1] * a1;
-        const int h1 = r1[sx] * a0 + r1[sx1] * a1;
-        const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
-        out |= (unsigned)(v & 0xff) << (8 * i);
+        const bool hi = (sel[i] >> 16) != 0;
+        const unsigned s0 = __byte_perm(hi ? p1 : p0, hi ? p2 : p1, sel[i]);
+        const unsigned s1 = __byte_perm(hi ? q1 : q0, hi ? q2 : q1, sel[i]);
+        const unsigned h0 = __dp2a_lo(wts[i], s0, 0u), h1 = __dp2a_lo(wts[i], s1, 0u);
+        const unsigned v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+        out |= (v & 0xff) << (8 * i);
     }
     *reinterpret_cast<unsigned*>(dst + (size_t)dy * D.pitch + dx0) = out;
 }
@@ -75,11 +81,12 @@ void launchRepack(const Geometry& g, const uint8_t* tight, uint8_t* slab, int nI
     ++*launches;
 }
 
-void launchPyramid(const Geometry& g, uint8_t* slab, const ResizeTap* taps, int nImages, cudaStream_t s, int* launches) {
+void launchPyramid(const Geometry& g, uint8_t* slab, const ResizeTap* taps, const uint4* xw, const uint4* xs,
+                   const unsigned short* xbase, int nImages, cudaStream_t s, int* launches) {
     for (int l = 1; l < g.nLevels; l++) {
         dim3 block(32, 8);
         dim3 grid((g.lv[l].w + 127) / 128, (g.lv[l].h + 7) / 8, nImages);
-        pyr_down_kernel<<<grid, block, 0, s>>>(g, slab, taps, l);
+        pyr_down_kernel<<<grid, block, 0, s>>>(g, slab, taps, xw, xs, xbase, l);
         ++*launches;
     }
 }
