@@ -32,7 +32,7 @@ SYMBOLS = [
     "gvs_matcher_create", "gvs_matcher_destroy", "gvs_stereo_match_batch", "gvs_stereo_download",
     "gvs_assign_grids_batch", "gvs_grid_download", "gvs_track_stereo_batch_host",
     "gvs_track_stereo_batch_resident", "gvs_matcher_sync", "gvs_matcher_set_stream", "gvs_match_projection", "gvs_descriptor_distance",
-    "gvs_extractor_enable_timing", "gvs_extractor_stage_times", "gvs_matcher_launch_count",
+    "gvs_match_projection_lba", "gvs_median_descriptor", "gvs_extractor_enable_timing", "gvs_extractor_stage_times", "gvs_matcher_launch_count",
     "gvs_extractor_launch_count",
 ]
 
@@ -51,6 +51,17 @@ class _MapPoints(C.Structure):
     _fields_ = [("count", C.c_int32), ("desc", C.c_void_p), ("pred_l", C.c_void_p), ("pred_r", C.c_void_p),
                 ("scale_level_l", C.c_void_p), ("scale_level_r", C.c_void_p), ("in_frame", C.c_void_p),
                 ("in_frame_r", C.c_void_p)]
+
+
+class _LbaFrame(C.Structure):
+    _fields_ = [("n_left", C.c_int32), ("n_right", C.c_int32), ("kp_left", C.c_void_p), ("desc_left", C.c_void_p),
+                ("kp_right", C.c_void_p), ("desc_right", C.c_void_p), ("left_idxs", C.c_void_p), ("right_idxs", C.c_void_p),
+                ("unmatched_f", C.c_void_p), ("unmatched_fr", C.c_void_p), ("width", C.c_int32), ("height", C.c_int32)]
+
+
+class _LbaPoints(C.Structure):
+    _fields_ = [("count", C.c_int32), ("desc", C.c_void_p), ("pred_l", C.c_void_p), ("pred_r", C.c_void_p),
+                ("pred_scale", C.c_void_p), ("last_l", C.c_void_p), ("last_r", C.c_void_p)]
 
 
 class StageTimes(C.Structure):
@@ -101,6 +112,8 @@ def load_library() -> C.CDLL:
     lib.gvs_matcher_set_stream.argtypes = [vp, vp]
     lib.gvs_match_projection.argtypes = [vp, i32, i32, C.POINTER(_MapPoints), f32, vp, vp, vp, C.POINTER(i32)]
     lib.gvs_descriptor_distance.argtypes = [vp, vp, vp, i32, vp]
+    lib.gvs_match_projection_lba.argtypes = [vp, C.POINTER(_LbaFrame), C.POINTER(_LbaPoints), f32, vp, C.POINTER(i32)]
+    lib.gvs_median_descriptor.argtypes = [vp, vp, vp, i32, vp]
     lib.gvs_extractor_enable_timing.argtypes = [vp, i32]
     lib.gvs_extractor_stage_times.argtypes = [vp, C.POINTER(StageTimes)]
     lib.gvs_matcher_launch_count.argtypes = [vp, C.POINTER(C.c_int64)]
@@ -386,6 +399,29 @@ class FeatureMatcher:
 
     def matchByRadius(self, mps, frame, matchedIdxsL, matchesIdxs, rad):
         return self._project(frame, GVS_MATCH_RADIUS, mps, rad, matchedIdxsL, None, matchesIdxs)
+
+    # -- matchByProjectionRPredLBA (src/FeatureMatcher.cpp:66-252); flattened inputs, see include/gvs.h
+    def matchByProjectionRPredLBA(self, pts: dict, kl, dl, kr, dr, leftIdxs, rightIdxs, unMatchedF, unMatchedFR, width, height, rad):
+        c = lambda a, dt: np.ascontiguousarray(a, dt)
+        kl = np.ascontiguousarray(kl); kr = np.ascontiguousarray(kr)
+        keep = [kl, c(dl, np.uint8), kr, c(dr, np.uint8), c(leftIdxs, np.int32), c(rightIdxs, np.int32), c(unMatchedF, np.int32),
+                c(unMatchedFR, np.int32)]
+        f = _LbaFrame(len(kl), len(kr), *[a.ctypes.data for a in keep], width, height)
+        M = len(pts["desc"])
+        pk = [c(pts["desc"], np.uint8), c(pts["predL"], np.float32), c(pts["predR"], np.float32), c(pts["predScale"], np.int32),
+              c(pts["lastL"], np.float32), c(pts["lastR"], np.float32)]
+        p = _LbaPoints(M, *[a.ctypes.data for a in pk])
+        out = np.zeros((M, 2), np.int32)
+        n = C.c_int(0)
+        _check(self._lib.gvs_match_projection_lba(self.h, C.byref(f), C.byref(p), float(rad), _p(out), C.byref(n)))
+        return n.value, out
+
+    # -- MapPoint::calcDescriptor (src/Map.cpp:145-210), batched over map points
+    def median_descriptor(self, descs: np.ndarray, offsets: np.ndarray) -> np.ndarray:
+        descs = np.ascontiguousarray(descs, np.uint8); offsets = np.ascontiguousarray(offsets, np.int32)
+        out = np.zeros(len(offsets) - 1, np.int32)
+        _check(self._lib.gvs_median_descriptor(self.h, _p(descs), _p(offsets), len(out), _p(out)))
+        return out
 
     def DescriptorDistance(self, a: np.ndarray, b: np.ndarray) -> np.ndarray:
         a = np.ascontiguousarray(a, np.uint8).reshape(-1, 32); b = np.ascontiguousarray(b, np.uint8).reshape(-1, 32)

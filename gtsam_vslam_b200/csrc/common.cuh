@@ -175,6 +175,8 @@ struct ProjArgs {
     int* status;
 };
 void launchProject(const ProjArgs& a, cudaStream_t s, int* launches);
+void launchProjectLBA(const ProjArgs& a, const float* lastL, const float* lastR, int* out, cudaStream_t s, int* launches);
+void launchMedianDescriptor(const uint8_t* descs, const int* offsets, int P, int* bestIdx, cudaStream_t s, int* launches);
 void launchHamming(const uint8_t* a, const uint8_t* b, int n, int* out, cudaStream_t s, int* launches);
 
 // status bits written by kernels into a device int (checked on sync)

@@ -1045,6 +1045,129 @@ int gvs_match_projection(gvs_matcher* m, int frame, int mode, const gvs_mappoint
     return GVS_OK;
 }
 
+int gvs_match_projection_lba(gvs_matcher* m, const gvs_lba_frame* kf, const gvs_lba_points* pts, float rad, int32_t* out_pairs,
+                             int* n_matches) {
+    if (!m || !kf || !pts || !out_pairs || !n_matches) return fail(GVS_ERR_INVALID, "null argument");
+    const int M = pts->count, NL = kf->n_left, NR = kf->n_right;
+    *n_matches = 0;
+    if (M <= 0) return GVS_OK;
+    if (NL < 0 || NR < 0 || NL > 65535 || NR > 65535 || kf->width < 1 || kf->height < 1) return fail(GVS_ERR_INVALID, "bad key frame");
+    if (!pts->desc || !pts->pred_l || !pts->pred_r || !pts->pred_scale || !pts->last_l || !pts->last_r)
+        return fail(GVS_ERR_INVALID, "candidate point arrays missing");
+    if ((NL && (!kf->kp_left || !kf->desc_left || !kf->right_idxs || !kf->unmatched_f)) ||
+        (NR && (!kf->kp_right || !kf->desc_right || !kf->left_idxs || !kf->unmatched_fr)))
+        return fail(GVS_ERR_INVALID, "key frame arrays missing");
+    for (int i = 0; i < M; i++)
+        if (pts->pred_scale[i] < 0 || pts->pred_scale[i] >= m->L->g.nLevels) return fail(GVS_ERR_INVALID, "pred_scale out of range");
+    GVS_CUDA_OK(cudaSetDevice(m->L->device));
+    cudaStream_t s = m->L->stream;
+    const float imageRatio = (float)kf->width / (float)kf->height;
+    const int xGrids = GVS_GRID_X, yGrids = (int)std::ceil((float)xGrids / imageRatio);
+    if (xGrids * yGrids > m->maxCells) return fail(GVS_ERR_INVALID, "image taller than wide by more than 64x is not supported");
+    const float xMult = (float)xGrids / (float)kf->width, yMult = (float)yGrids / (float)kf->height;
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    size_t o = 0;
+    auto take = [&](size_t bytes) { const size_t r = o; o += al(std::max<size_t>(bytes, 4)); return r; };
+    const size_t oDesc = take((size_t)M * 32), oPL = take((size_t)M * 8), oPR = take((size_t)M * 8), oLv = take((size_t)M * 4),
+                 oLL = take((size_t)M * 8), oLR = take((size_t)M * 8), oIF = take(M), oIR = take(M), oOut = take((size_t)M * 8),
+                 oRec = take((size_t)M * 2 * 20), oCnt = take(16), oKL = take((size_t)NL * 28), oKR = take((size_t)NR * 28),
+                 oDL = take((size_t)NL * 32), oDR = take((size_t)NR * 32), oLI = take((size_t)NR * 4), oRI = take((size_t)NL * 4),
+                 oUF = take((size_t)NL * 4), oUR = take((size_t)NR * 4), oCSL = take((size_t)(m->maxCells + 1) * 4),
+                 oCSR = take((size_t)(m->maxCells + 1) * 4), oItL = take((size_t)NL * 4), oItR = take((size_t)NR * 4), oOff = take(32);
+    if (o > m->pjBytes) {
+        GVS_CUDA_OK(cudaStreamSynchronize(s));
+        cudaFree(m->pj); m->pj = nullptr; m->pjBytes = 0;
+        GVS_CUDA_OK(devAlloc(&m->pj, o));
+        m->pjBytes = o;
+    }
+    const long long need = std::min<long long>((long long)M * std::max(std::max(NL, NR), 1), (long long)1 << 28);
+    if (need > m->poolCap) {
+        GVS_CUDA_OK(cudaStreamSynchronize(s));
+        cudaFree(m->pool); m->pool = nullptr; m->poolCap = 0;
+        GVS_CUDA_OK(devAlloc(&m->pool, (size_t)need * 2));
+        m->poolCap = (int)need;
+    }
+    uint8_t* b = m->pj;
+    std::vector<uint8_t> inL(M), inR(M);
+    for (int i = 0; i < M; i++) {
+        inL[i] = pts->pred_l[2 * i] > 0 && pts->pred_l[2 * i + 1] > 0;   // :104
+        inR[i] = pts->pred_r[2 * i] > 0 && pts->pred_r[2 * i + 1] > 0;   // :153
+    }
+    const int offs[4] = {0, NL, 0, NR};
+    auto up = [&](size_t off, const void* src, size_t bytes) -> cudaError_t {
+        return bytes ? cudaMemcpyAsync(b + off, src, bytes, cudaMemcpyHostToDevice, s) : cudaSuccess;
+    };
+    GVS_CUDA_OK(up(oDesc, pts->desc, (size_t)M * 32)); GVS_CUDA_OK(up(oPL, pts->pred_l, (size_t)M * 8));
+    GVS_CUDA_OK(up(oPR, pts->pred_r, (size_t)M * 8)); GVS_CUDA_OK(up(oLv, pts->pred_scale, (size_t)M * 4));
+    GVS_CUDA_OK(up(oLL, pts->last_l, (size_t)M * 8)); GVS_CUDA_OK(up(oLR, pts->last_r, (size_t)M * 8));
+    GVS_CUDA_OK(up(oIF, inL.data(), M)); GVS_CUDA_OK(up(oIR, inR.data(), M));
+    GVS_CUDA_OK(up(oKL, kf->kp_left, (size_t)NL * 28)); GVS_CUDA_OK(up(oKR, kf->kp_right, (size_t)NR * 28));
+    GVS_CUDA_OK(up(oDL, kf->desc_left, (size_t)NL * 32)); GVS_CUDA_OK(up(oDR, kf->desc_right, (size_t)NR * 32));
+    GVS_CUDA_OK(up(oLI, kf->left_idxs, (size_t)NR * 4)); GVS_CUDA_OK(up(oRI, kf->right_idxs, (size_t)NL * 4));
+    GVS_CUDA_OK(up(oUF, kf->unmatched_f, (size_t)NL * 4)); GVS_CUDA_OK(up(oUR, kf->unmatched_fr, (size_t)NR * 4));
+    GVS_CUDA_OK(up(oOff, offs, sizeof(offs)));
+    GVS_CUDA_OK(cudaMemsetAsync(m->pjStatus, 0, 2 * sizeof(int), s));
+    int launches = 0;
+    GridArgs ga{};
+    ga.xGrids = xGrids; ga.yGrids = yGrids; ga.xMult = xMult; ga.yMult = yMult; ga.maxCells = m->maxCells;
+    ga.kps = reinterpret_cast<gvs_keypoint*>(b + oKL); ga.off = reinterpret_cast<int*>(b + oOff); ga.cellStart = reinterpret_cast<int*>(b + oCSL);
+    ga.items = reinterpret_cast<int*>(b + oItL);
+    launchGrid(ga, 1, s, &launches);
+    ga.kps = reinterpret_cast<gvs_keypoint*>(b + oKR); ga.off = reinterpret_cast<int*>(b + oOff) + 2; ga.cellStart = reinterpret_cast<int*>(b + oCSR);
+    ga.items = reinterpret_cast<int*>(b + oItR);
+    launchGrid(ga, 1, s, &launches);
+    ProjArgs a{};
+    a.mode = 3; a.M = M;
+    a.mpDesc = b + oDesc; a.predL = reinterpret_cast<float*>(b + oPL); a.predR = reinterpret_cast<float*>(b + oPR);
+    a.lvlL = reinterpret_cast<int*>(b + oLv); a.lvlR = reinterpret_cast<int*>(b + oLv);
+    a.inFrame = b + oIF; a.inFrameR = b + oIR;
+    a.kpL = reinterpret_cast<gvs_keypoint*>(b + oKL); a.descL = b + oDL; a.NL = NL;
+    a.kpR = reinterpret_cast<gvs_keypoint*>(b + oKR); a.descR = b + oDR; a.NR = NR;
+    a.cellStartL = reinterpret_cast<int*>(b + oCSL); a.itemsL = reinterpret_cast<int*>(b + oItL);
+    a.cellStartR = reinterpret_cast<int*>(b + oCSR); a.itemsR = reinterpret_cast<int*>(b + oItR);
+    a.leftIdxs = reinterpret_cast<int*>(b + oLI); a.rightIdxs = reinterpret_cast<int*>(b + oRI);
+    a.xGrids = xGrids; a.yGrids = yGrids; a.xMult = xMult; a.yMult = yMult; a.rad = rad;
+    for (int i = 0; i < kMaxLevels; i++) a.scalePyramid[i] = i < m->L->g.nLevels ? m->L->scale[i] : 1.f;
+    a.recs = b + oRec; a.poolTop = reinterpret_cast<int*>(b + oCnt);
+    a.candL = m->pool; a.candR = m->pool + m->poolCap; a.candCap = m->poolCap;
+    a.matchedL = reinterpret_cast<int*>(b + oUF); a.matchedR = reinterpret_cast<int*>(b + oUR);  // static exclusion arrays
+    a.matches = nullptr; a.nMatches = m->pjStatus + 1; a.status = m->pjStatus;
+    launchProjectLBA(a, reinterpret_cast<float*>(b + oLL), reinterpret_cast<float*>(b + oLR), reinterpret_cast<int*>(b + oOut), s, &launches);
+    m->launchesTotal += launches;
+    int st[2] = {0, 0};
+    GVS_CUDA_OK(cudaMemcpyAsync(out_pairs, b + oOut, (size_t)M * 8, cudaMemcpyDeviceToHost, s));
+    GVS_CUDA_OK(cudaMemcpyAsync(st, m->pjStatus, sizeof(st), cudaMemcpyDeviceToHost, s));
+    GVS_CUDA_OK(cudaStreamSynchronize(s));
+    GVS_CUDA_OK(cudaGetLastError());
+    if (st[0] & kStatProjOverflow) return fail(GVS_ERR_CAPACITY, "projection candidate pool overflow");
+    *n_matches = st[1];
+    return GVS_OK;
+}
+
+int gvs_median_descriptor(gvs_matcher* m, const uint8_t* descs, const int32_t* offsets, int n_points, int32_t* best_idx) {
+    if (!m || !offsets || !best_idx || n_points < 0) return fail(GVS_ERR_INVALID, "bad argument");
+    if (n_points == 0) return GVS_OK;
+    const int total = offsets[n_points];
+    if (total < 0 || (total > 0 && !descs)) return fail(GVS_ERR_INVALID, "bad descriptor list");
+    for (int p = 0; p < n_points; p++)
+        if (offsets[p + 1] < offsets[p] || offsets[p + 1] - offsets[p] > 65535) return fail(GVS_ERR_INVALID, "bad offsets");
+    GVS_CUDA_OK(cudaSetDevice(m->L->device));
+    cudaStream_t s = m->L->stream;
+    uint8_t* dd = nullptr; int* doff = nullptr; int* dbest = nullptr;
+    cudaError_t e = devAlloc(&dd, (size_t)std::max(total, 1) * 32);
+    if (e == cudaSuccess) e = devAlloc(&doff, (size_t)n_points + 1);
+    if (e == cudaSuccess) e = devAlloc(&dbest, (size_t)n_points);
+    if (e == cudaSuccess && total) e = cudaMemcpyAsync(dd, descs, (size_t)total * 32, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(doff, offsets, sizeof(int) * (n_points + 1), cudaMemcpyHostToDevice, s);
+    int launches = 0;
+    if (e == cudaSuccess) { launchMedianDescriptor(dd, doff, n_points, dbest, s, &launches); e = cudaMemcpyAsync(best_idx, dbest, sizeof(int) * n_points, cudaMemcpyDeviceToHost, s); }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(dd); cudaFree(doff); cudaFree(dbest);
+    m->launchesTotal += launches;
+    if (e != cudaSuccess) return fail(GVS_ERR_CUDA, "gvs_median_descriptor", cudaGetErrorString(e));
+    return GVS_OK;
+}
+
 int gvs_descriptor_distance(gvs_matcher* m, const uint8_t* a, const uint8_t* b, int n, int32_t* dist) {
     if (!m || !a || !b || !dist || n < 0) return fail(GVS_ERR_INVALID, "bad argument");
     if (n == 0) return GVS_OK;

@@ -26,6 +26,8 @@ __device__ __forceinline__ int candDist(unsigned e) { return (int)((e >> 16) & 0
 __device__ __forceinline__ int candLev(unsigned e) { return (int)((e >> 25) & 0xf); }
 constexpr unsigned kNone = 0xffffffffu;
 
+constexpr int kModeLBA = 3;  // internal: FeatureMatcher::matchByProjectionRPredLBA
+
 struct ProjRec {  // per (map point, side)
     int start, len;
     unsigned eBest, ePre, eSuf;
@@ -68,7 +70,7 @@ __device__ void reduceList(const unsigned* list, int len, const int* matched, in
 __global__ void __launch_bounds__(256)
 proj_candidates_kernel(const ProjArgs a, ProjRec* __restrict__ recs) {
     const int lane = threadIdx.x & 31;
-    const int nSides = a.mode == GVS_MATCH_STEREO_PRED ? 2 : 1;
+    const int nSides = (a.mode == GVS_MATCH_STEREO_PRED || a.mode == kModeLBA) ? 2 : 1;
     const int warpsPerGrid = gridDim.x * (blockDim.x >> 5);
     unsigned lt;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt));
@@ -84,6 +86,9 @@ proj_candidates_kernel(const ProjArgs a, ProjRec* __restrict__ recs) {
         const uint8_t* descs = side ? a.descR : a.descL;
         const int* cellStart = side ? a.cellStartR : a.cellStartL;
         const int* items = side ? a.itemsR : a.itemsL;
+        // LBA: keys already owned by a map point are excluded up front (newKF->unMatchedF/FR, src/FeatureMatcher.cpp:118,167);
+        // the arrays are not modified by the call, so map points are independent
+        const int* excl = a.mode == kModeLBA ? (side ? a.matchedR : a.matchedL) : nullptr;
         const float trackX = pred[2 * mp], trackY = pred[2 * mp + 1];
         const float radius = __fmul_rn(a.scalePyramid[min(max(lvl, 0), kMaxLevels - 1)], a.rad);
         // getMatchIdxs window (src/FeatureMatcher.cpp:18-30)
@@ -98,6 +103,7 @@ proj_candidates_kernel(const ProjArgs a, ProjRec* __restrict__ recs) {
             auto passes = [&](int idx) {
                 const gvs_keypoint k = kps[idx];
                 if (k.octave > lvl + 1 || k.octave < lvl - 1) return -1;
+                if (excl && excl[idx] >= 0) return -1;
                 const float dx = __fsub_rn(k.x, trackX), dy = __fsub_rn(k.y, trackY);
                 if (!(fabsf(dx) < radius && fabsf(dy) < radius)) return -1;
                 if (a.mode == GVS_MATCH_RADIUS) {  // Converter::checkPixelParallax (include/Conversions.h:140-144)
@@ -263,6 +269,106 @@ void launchProject(const ProjArgs& a, cudaStream_t s, int* launches) {
         configured = sm;
     }
     proj_resolve_kernel<<<1, 32, sm, s>>>(a, recs);
+    ++*launches;
+}
+
+// FeatureMatcher::matchByProjectionRPredLBA decision (src/FeatureMatcher.cpp:191-249), one thread per candidate point.
+// Left branch quirk (:132-136): a later second-best takes the *best* key's level.
+__global__ void lba_resolve_kernel(const ProjArgs a, const ProjRec* __restrict__ recs, const float* __restrict__ lastL,
+                                   const float* __restrict__ lastR, int* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < a.M;
+    bool accept = false;
+    int o0 = -2, o1 = -2;
+    if (valid) {
+        const ProjRec rl = recs[2 * i], rr = recs[2 * i + 1];
+        Decision d{256, -1, -1, -1, 256};
+        if (rl.eBest != kNone) {
+            d.bestDist = candDist(rl.eBest); d.bestIdx = candIdx(rl.eBest); d.bestLev = candLev(rl.eBest);
+            if (rl.ePre != kNone) { d.secDist = candDist(rl.ePre); d.bestLev2 = candLev(rl.ePre); }
+            if (rl.eSuf != kNone && candDist(rl.eSuf) < d.secDist) { d.secDist = candDist(rl.eSuf); d.bestLev2 = d.bestLev; }
+        }
+        const Decision dr = decide(rr.eBest, rr.ePre, rr.eSuf);
+        bool right = false;
+        if (d.bestDist > dr.bestDist) { d.bestDist = dr.bestDist; d.secDist = dr.secDist; d.bestLev = dr.bestLev; d.bestLev2 = dr.bestLev2; right = true; }
+        const float thr = __fmul_rn(0.6f, (float)d.secDist);
+        bool ok = d.bestDist <= 50 && !(d.bestLev == d.bestLev2 && (float)d.bestDist >= thr) &&
+                  (d.bestLev != d.bestLev2 || (float)d.bestDist < thr);
+        if (ok) {
+            const float* last = right ? lastR + 2 * i : lastL + 2 * i;
+            const float* pred = right ? a.predR + 2 * i : a.predL + 2 * i;
+            const double dx = (double)pred[0] - (double)last[0], dy = (double)pred[1] - (double)last[1];
+            ok = sqrt(dx * dx + dy * dy) > 10.0;  // Converter::checkPixelParallax (include/Conversions.h:140-144)
+        }
+        if (ok) {
+            accept = true;
+            if (right) { const int li = a.leftIdxs[dr.bestIdx]; o0 = li >= 0 ? li : -1; o1 = dr.bestIdx; }
+            else { const int ri = a.rightIdxs[d.bestIdx]; o0 = d.bestIdx; o1 = ri >= 0 ? ri : -1; }
+        }
+        out[2 * i] = o0; out[2 * i + 1] = o1;
+    }
+    const int n = __syncthreads_count(accept);
+    if (threadIdx.x == 0 && n) atomicAdd(a.nMatches, n);
+}
+
+void launchProjectLBA(const ProjArgs& a, const float* lastL, const float* lastR, int* out, cudaStream_t s, int* launches) {
+    ProjRec* recs = reinterpret_cast<ProjRec*>(a.recs);
+    cudaMemsetAsync(a.poolTop, 0, 2 * sizeof(int), s);
+    cudaMemsetAsync(a.nMatches, 0, sizeof(int), s);
+    if (a.M <= 0) return;
+    proj_candidates_kernel<<<(2 * a.M + 7) / 8, 256, 0, s>>>(a, recs);
+    ++*launches;
+    lba_resolve_kernel<<<(a.M + 127) / 128, 128, 0, s>>>(a, recs, lastL, lastR, out);
+    ++*launches;
+}
+
+// MapPoint::calcDescriptor (src/Map.cpp:145-210): one CTA per map point, one warp per observation row; the median of the
+// row's distances (element int(0.5*(N-1)) of the sorted row, self distance 0 included) comes from a 257-bin histogram.
+__global__ void __launch_bounds__(128)
+median_descriptor_kernel(const uint8_t* __restrict__ descs, const int* __restrict__ offsets, int* __restrict__ bestIdx) {
+    __shared__ int hist[4][264];
+    __shared__ unsigned best[4];
+    const int p = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int o = offsets[p], N = offsets[p + 1] - o;
+    if (N <= 0) { if (threadIdx.x == 0) bestIdx[p] = -1; return; }
+    const int k = (int)(0.5 * (N - 1));
+    unsigned mine = 0xffffffffu;
+    for (int i = warp; i < N; i += 4) {
+        for (int b = lane; b < 264; b += 32) hist[warp][b] = 0;
+        __syncwarp();
+        const uint4* di = reinterpret_cast<const uint4*>(descs + (size_t)(o + i) * 32);
+        const uint4 a0 = __ldg(di), a1 = __ldg(di + 1);
+        for (int j = lane; j < N; j += 32) {
+            const uint4* dj = reinterpret_cast<const uint4*>(descs + (size_t)(o + j) * 32);
+            const uint4 b0 = __ldg(dj), b1 = __ldg(dj + 1);
+            const int d = i == j ? 0 : __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+                                       __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+            atomicAdd(&hist[warp][d], 1);
+        }
+        __syncwarp();
+        // k-th smallest: first bin whose inclusive prefix count exceeds k (lane owns 9 consecutive bins)
+        int c[9], tot = 0;
+#pragma unroll
+        for (int t = 0; t < 9; t++) { const int b = lane * 9 + t; c[t] = b < 257 ? hist[warp][b] : 0; tot += c[t]; }
+        int incl = tot;
+#pragma unroll
+        for (int s2 = 1; s2 < 32; s2 <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, s2); if (lane >= s2) incl += v; }
+        int run = incl - tot, med = 0x7fffffff;
+#pragma unroll
+        for (int t = 0; t < 9; t++) { run += c[t]; if (run > k && med == 0x7fffffff) med = lane * 9 + t; }
+#pragma unroll
+        for (int s2 = 16; s2; s2 >>= 1) med = min(med, __shfl_xor_sync(0xffffffffu, med, s2));
+        mine = min(mine, ((unsigned)med << 16) | (unsigned)i);  // least median, first index on ties (strict < in the reference)
+        __syncwarp();
+    }
+    if (lane == 0) best[warp] = mine;
+    __syncthreads();
+    if (threadIdx.x == 0) bestIdx[p] = (int)(min(min(best[0], best[1]), min(best[2], best[3])) & 0xffff);
+}
+
+void launchMedianDescriptor(const uint8_t* descs, const int* offsets, int P, int* bestIdx, cudaStream_t s, int* launches) {
+    if (P <= 0) return;
+    median_descriptor_kernel<<<P, 128, 0, s>>>(descs, offsets, bestIdx);
     ++*launches;
 }
 

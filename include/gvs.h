@@ -189,6 +189,40 @@ typedef enum gvs_match_mode {
 int gvs_match_projection(gvs_matcher* fm, int frame, int mode, const gvs_mappoints* mps, float rad, int32_t* matched_l,
                          int32_t* matched_r, int32_t* matches, int* n_matches);
 
+/* FeatureMatcher::matchByProjectionRPredLBA, src/FeatureMatcher.cpp:66-252 (LocalMapper::findNewPoints,
+ * src/OptimizationBA.cpp:367).  newKF is any stored key frame, so its keys come from the host: */
+typedef struct gvs_lba_frame {
+    int32_t n_left, n_right;
+    const gvs_keypoint* kp_left;   /* newKF->keys.keyPoints */
+    const uint8_t* desc_left;      /* newKF->keys.Desc, n_left x 32 */
+    const gvs_keypoint* kp_right;  /* newKF->keys.rightKeyPoints */
+    const uint8_t* desc_right;     /* newKF->keys.rightDesc */
+    const int32_t* left_idxs;      /* newKF->keys.leftIdxs, n_right */
+    const int32_t* right_idxs;     /* newKF->keys.rightIdxs, n_left */
+    const int32_t* unmatched_f;    /* newKF->unMatchedF, n_left (>= 0: the key already belongs to a map point) */
+    const int32_t* unmatched_fr;   /* newKF->unMatchedFR, n_right */
+    int32_t width, height;         /* image size the key grids were built with (src/FeatureTracker.cpp:67-68) */
+} gvs_lba_frame;
+/* The candidate points p4d[i] (:72-110), flattened by the caller exactly as the reference reads them: */
+typedef struct gvs_lba_points {
+    int32_t count;
+    const uint8_t* desc;        /* mp->desc, or lastKeys.Desc / rightDesc row (:76-86) */
+    const float* pred_l;        /* predPoints[i].first  (searched only if x > 0 && y > 0, :104) */
+    const float* pred_r;        /* predPoints[i].second (:153) */
+    const int32_t* pred_scale;  /* clamp(cvCeil(log(maxDistsScale[i]/dist)/logScale), 0, nScaleLev-1) (:88-95), host double math */
+    const float* last_l;        /* lastKFKeyPoint used by the left branch  (:231-235) */
+    const float* last_r;        /* lastKFKeyPoint used by the right branch (:211-215) */
+} gvs_lba_points;
+/* out_pairs: count x 2; (lIdx, rIdx) appended to matchedIdxs[i] (:226,:246) or (-2,-2) if nothing is appended.
+ * *n_matches = the reference's return value. */
+int gvs_match_projection_lba(gvs_matcher* fm, const gvs_lba_frame* new_kf, const gvs_lba_points* pts, float rad,
+                             int32_t* out_pairs, int* n_matches);
+
+/* MapPoint::calcDescriptor, src/Map.cpp:145-210, for n_points map points at once: descs = the observation descriptors
+ * of all points back to back (32 bytes each), offsets[n_points + 1]; best_idx[p] = index inside point p's own list of
+ * the descriptor with the least median Hamming distance to the others (-1 for an empty list). */
+int gvs_median_descriptor(gvs_matcher* fm, const uint8_t* descs, const int32_t* offsets, int n_points, int32_t* best_idx);
+
 /* FeatureMatcher::DescriptorDistance, src/FeatureMatcher.cpp:710-726, for n pairs of 32-byte descriptors
  * (host arrays; computed on the device). */
 int gvs_descriptor_distance(gvs_matcher* fm, const uint8_t* a, const uint8_t* b, int n, int32_t* dist);

@@ -14,6 +14,8 @@
 //   FeatureMatcher::matchByProjectionRPred src/FeatureMatcher.cpp:254   matchByProjectionRPred(activeMapPoints, keysLeft, ...)
 //   FeatureMatcher::matchByProjectionMono  src/FeatureMatcher.cpp:391   matchByProjectionMono(...)
 //   FeatureMatcher::matchByRadius          src/FeatureMatcher.cpp:458   matchByRadius(...)
+//   FeatureMatcher::matchByProjectionRPredLBA src/FeatureMatcher.cpp:66 matchByProjectionRPredLBA(lastKF, newKF, ...) (template)
+//   MapPoint::calcDescriptor               src/Map.cpp:145              FeatureMatcher::medianDescriptor(vDescriptors)
 //   FeatureMatcher::DescriptorDistance     src/FeatureMatcher.cpp:710   DescriptorDistance(a, b)
 //   FeatureTracker::assignKeysToGrids      src/FeatureTracker.cpp:28    FeatureMatcher::assignKeysToGrids(keysLeft, width, height)
 //   FeatureTracker::extractORBAndStereoMatch src/FeatureTracker.cpp:56  FeatureMatcher::extractORBAndStereoMatch(leftIm, rightIm, keysLeft)
@@ -21,6 +23,8 @@
 // Error behaviour: the reference returns void and never reports errors; here a failing C-ABI call throws
 // std::runtime_error with gvs_last_error() (there is no CPU fallback to fall through to).
 #pragma once
+#include <cmath>
+#include <cstring>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -196,6 +200,67 @@ class FeatureMatcher {
         gvsCheck(gvs_match_projection(h_, 0, GVS_MATCH_RADIUS, &mp, rad, matchedIdxsL.data(), nullptr,
                                       reinterpret_cast<int32_t*>(matches.data()), &n));
         return n;
+    }
+
+    // src/FeatureMatcher.cpp:66-252 (LocalMapper::findNewPoints, src/OptimizationBA.cpp:367).  KeyFrameT / the Eigen types are
+    // the reference's own (include/KeyFrame.h); this template is only instantiated inside the reference tree.  The scale
+    // prediction (:88-95) stays on the host in double precision exactly as the reference computes it.
+    template <class KeyFrameT, class Vec4>
+    int matchByProjectionRPredLBA(const KeyFrameT* lastKF, KeyFrameT* newKF,
+                                  std::vector<std::vector<std::pair<KeyFrameT*, std::pair<int, int>>>>& matchedIdxs, const float rad,
+                                  const std::vector<std::pair<cv::Point2f, cv::Point2f>>& predPoints,
+                                  const std::vector<float>& maxDistsScale, std::vector<std::pair<Vec4, std::pair<int, int>>>& p4d) {
+        const TrackedKeys& lastKeys = lastKF->keys;
+        const TrackedKeys& keys = newKF->keys;
+        const auto toFindPose = newKF->pose.pose;
+        const int M = (int)p4d.size();
+        std::vector<uint8_t> desc((size_t)M * 32);
+        std::vector<float> pl(2 * (size_t)M), pr(2 * (size_t)M), ll(2 * (size_t)M), lr(2 * (size_t)M);
+        std::vector<int32_t> ps(M);
+        for (int i = 0; i < M; i++) {
+            const auto& wPos = p4d[i].first;
+            const std::pair<int, int>& kp = p4d[i].second;
+            const cv::Mat* d;
+            if (kp.first >= 0) {
+                const auto* mp = lastKF->localMapPoints[kp.first];
+                d = mp ? &mp->desc : nullptr;
+                std::memcpy(&desc[(size_t)i * 32], d ? d->ptr(0) : lastKeys.Desc.ptr(kp.first), 32);
+            } else std::memcpy(&desc[(size_t)i * 32], lastKeys.rightDesc.ptr(kp.second), 32);
+            const double px = wPos(0) - toFindPose(0, 3), py = wPos(1) - toFindPose(1, 3), pz = wPos(2) - toFindPose(2, 3);
+            const float dist = (float)std::sqrt(px * px + py * py + pz * pz);
+            const float dif = maxDistsScale[i] / dist;
+            int predScale = (int)std::ceil(std::log(dif) / lastKF->logScale);
+            if (predScale < 0) predScale = 0; else if (predScale >= lastKF->nScaleLev) predScale = lastKF->nScaleLev - 1;
+            ps[i] = predScale;
+            pl[2 * i] = predPoints[i].first.x; pl[2 * i + 1] = predPoints[i].first.y;
+            pr[2 * i] = predPoints[i].second.x; pr[2 * i + 1] = predPoints[i].second.y;
+            const cv::Point2f kl = kp.first >= 0 ? lastKeys.keyPoints[kp.first].pt : lastKeys.rightKeyPoints[kp.second].pt;   // :231-235
+            const cv::Point2f kr = kp.second >= 0 ? lastKeys.rightKeyPoints[kp.second].pt : lastKeys.keyPoints[kp.first].pt;  // :211-215
+            ll[2 * i] = kl.x; ll[2 * i + 1] = kl.y; lr[2 * i] = kr.x; lr[2 * i + 1] = kr.y;
+        }
+        gvs_lba_frame f{(int32_t)keys.keyPoints.size(), (int32_t)keys.rightKeyPoints.size(),
+                        reinterpret_cast<const gvs_keypoint*>(keys.keyPoints.data()), keys.Desc.data,
+                        reinterpret_cast<const gvs_keypoint*>(keys.rightKeyPoints.data()), keys.rightDesc.data, keys.leftIdxs.data(),
+                        keys.rightIdxs.data(), newKF->unMatchedF.data(), newKF->unMatchedFR.data(), feLeft->width(), feLeft->height()};
+        gvs_lba_points p{M, desc.data(), pl.data(), pr.data(), ps.data(), ll.data(), lr.data()};
+        std::vector<int32_t> out(2 * (size_t)M);
+        int n = 0;
+        gvsCheck(gvs_match_projection_lba(h_, &f, &p, rad, out.data(), &n));
+        for (int i = 0; i < M; i++)
+            if (out[2 * i] != -2) matchedIdxs[i].emplace_back(std::make_pair(newKF, std::make_pair(out[2 * i], out[2 * i + 1])));
+        return n;
+    }
+
+    // MapPoint::calcDescriptor (src/Map.cpp:145-210) for one observation list: index of the chosen descriptor
+    int medianDescriptor(const std::vector<cv::Mat>& vDescriptors) {
+        const int N = (int)vDescriptors.size();
+        if (N == 0) return -1;
+        std::vector<uint8_t> d((size_t)N * 32);
+        for (int i = 0; i < N; i++) std::memcpy(&d[(size_t)i * 32], vDescriptors[i].ptr(0), 32);
+        const int32_t off[2] = {0, N};
+        int32_t best = -1;
+        gvsCheck(gvs_median_descriptor(h_, d.data(), off, 1, &best));
+        return best;
     }
 
     // src/FeatureMatcher.cpp:710-726

@@ -154,6 +154,28 @@ def match_projection(fe: Extractor, mode: int, mps: dict, kl, dl, kr, dr, leftId
                                       C.c_float(rad), _p(matchedL), _p(matchedR), _p(matches))
 
 
+def match_lba(fe: Extractor, pts: dict, kl, dl, kr, dr, leftIdxs, rightIdxs, unMatchedF, unMatchedFR, width, height, rad):
+    """matchByProjectionRPredLBA (reference src/FeatureMatcher.cpp:66-252), flattened inputs: (nMatches, out (M,2))."""
+    c = lambda a, dt: np.ascontiguousarray(a, dt)
+    M = len(pts["desc"])
+    out = np.zeros((M, 2), np.int32)
+    kl = np.ascontiguousarray(kl); kr = np.ascontiguousarray(kr)
+    args = [c(pts["desc"], np.uint8), c(pts["predL"], np.float32), c(pts["predR"], np.float32), c(pts["predScale"], np.int32),
+            c(pts["lastL"], np.float32), c(pts["lastR"], np.float32)]
+    n = lib().ora_match_lba(fe.h, M, *[_p(a) for a in args], _p(kl), _p(c(dl, np.uint8)), len(kl), _p(kr), _p(c(dr, np.uint8)), len(kr),
+                            _p(c(leftIdxs, np.int32)), _p(c(rightIdxs, np.int32)), _p(c(unMatchedF, np.int32)),
+                            _p(c(unMatchedFR, np.int32)), width, height, C.c_float(rad), _p(out))
+    return n, out
+
+
+def median_descriptor(descs: np.ndarray, offsets: np.ndarray) -> np.ndarray:
+    """MapPoint::calcDescriptor (reference src/Map.cpp:145-210) for len(offsets)-1 map points."""
+    descs = np.ascontiguousarray(descs, np.uint8); offsets = np.ascontiguousarray(offsets, np.int32)
+    out = np.zeros(len(offsets) - 1, np.int32)
+    lib().ora_median_descriptor(_p(descs), _p(offsets), len(out), _p(out))
+    return out
+
+
 def stereo_frames(params, fx, baseline, L: np.ndarray, R: np.ndarray, shape: int, threads: int):
     """CPU baseline: run F stereo frames; returns (total matches, per-frame left key counts)."""
     L = np.ascontiguousarray(L, np.uint8); R = np.ascontiguousarray(R, np.uint8)

@@ -625,6 +625,87 @@ class FeatureMatcher:
         return nMatches, out
 
 
+    # src/FeatureMatcher.cpp:66-252 (LocalMapper's matcher).  The KeyFrame / MapPoint / Eigen inputs are flattened:
+    #   pts: desc (M,32) = mp->desc or the last keyframe's descriptor row (:76-86); predL/predR (M,2) = predPoints;
+    #        predScale (M,) = the clamped cvCeil(log(dif)/logScale) of :88-95; lastL/lastR (M,2) = lastKFKeyPoint of the
+    #        left / right branch (:231-235 / :211-215)
+    #   newKeys: TrackedKeys of newKF; unMatchedF / unMatchedFR = newKF->unMatchedF / unMatchedFR
+    # Returns (nMatches, out) with out[i] = (lIdx, rIdx) appended to matchedIdxs[i], or (-2, -2) if nothing was appended.
+    def matchByProjectionRPredLBA(self, pts: dict, newKeys: TrackedKeys, unMatchedF, unMatchedFR, rad):
+        matchDistLBA, ratioLBA = 50, _F32(0.6)
+        rad = _F32(rad)
+        M = len(pts["desc"])
+        out = np.full((M, 2), -2, np.int32)
+        nMatches = 0
+        for i in range(M):
+            mpDesc = pts["desc"][i]
+            predScale = int(pts["predScale"][i])
+            bestDist, bestIdx, bestLev, bestLev2, secDist = 256, -1, -1, -1, 256
+            pLeft = pts["predL"][i]
+            radius = _F32(self.feLeft.scalePyramid[predScale] * rad)
+            if pLeft[0] > 0 and pLeft[1] > 0:
+                for idx in self.getMatchIdxs(pLeft, newKeys, predScale, radius, False):
+                    if unMatchedF[idx] >= 0:
+                        continue
+                    lev = int(newKeys.keyPoints["octave"][idx])
+                    dist = DescriptorDistance(mpDesc, newKeys.Desc[idx])
+                    if dist < bestDist:
+                        secDist, bestLev2 = bestDist, bestLev
+                        bestDist, bestLev, bestIdx = dist, lev, idx
+                        continue
+                    if dist < secDist:
+                        secDist, bestLev2 = dist, bestLev   # sic (:132-136): the best key's level, not this key's
+            pRight = pts["predR"][i]
+            bestDistR, bestIdxR, bestLevR, bestLevR2, secDistR = 256, -1, -1, -1, 256
+            if pRight[0] > 0 and pRight[1] > 0:
+                for idx in self.getMatchIdxs(pRight, newKeys, predScale, radius, True):
+                    if unMatchedFR[idx] >= 0:
+                        continue
+                    lev = int(newKeys.rightKeyPoints["octave"][idx])
+                    dist = DescriptorDistance(mpDesc, newKeys.rightDesc[idx])
+                    if dist < bestDistR:
+                        secDistR, bestLevR2 = bestDistR, bestLevR
+                        bestDistR, bestLevR, bestIdxR = dist, lev, idx
+                        continue
+                    if dist < secDistR:
+                        secDistR, bestLevR2 = dist, lev
+            right = False
+            if bestDist > bestDistR:
+                bestDist, secDist, bestLev, bestLev2, right = bestDistR, secDistR, bestLevR, bestLevR2, True
+            if bestDist > matchDistLBA:
+                continue
+            thr = _F32(ratioLBA * _F32(secDist))
+            if bestLev == bestLev2 and _F32(bestDist) >= thr:
+                continue
+            if bestLev != bestLev2 or _F32(bestDist) < thr:
+                last = pts["lastR"][i] if right else pts["lastL"][i]
+                pred = pRight if right else pLeft
+                dx, dy = float(pred[0]) - float(last[0]), float(pred[1]) - float(last[1])
+                if not (math.sqrt(dx * dx + dy * dy) > 10.0):   # Converter::checkPixelParallax, include/Conversions.h:140-144
+                    continue
+                if right:
+                    out[i] = (newKeys.leftIdxs[bestIdxR] if newKeys.leftIdxs[bestIdxR] >= 0 else -1, bestIdxR)
+                else:
+                    out[i] = (bestIdx, newKeys.rightIdxs[bestIdx] if newKeys.rightIdxs[bestIdx] >= 0 else -1)
+                nMatches += 1
+        return nMatches, out
+
+
+def calcDescriptor(descs: np.ndarray) -> int:
+    """MapPoint::calcDescriptor (src/Map.cpp:145-210): index of the descriptor with the least median distance to the rest."""
+    N = len(descs)
+    D = np.zeros((N, N), np.int32)
+    for i in range(N):
+        for j in range(i + 1, N):
+            D[i, j] = D[j, i] = DescriptorDistance(descs[i], descs[j])
+    best, bestIdx = 2 ** 31 - 1, 0
+    for i in range(N):
+        median = int(np.sort(D[i])[int(0.5 * (N - 1))])
+        if median < best:
+            best, bestIdx = median, i
+    return bestIdx
+
+
 # ----------------------------------------------------------------------------------------------
 # FeatureTracker glue (src/FeatureTracker.cpp:28-70)
 # ----------------------------------------------------------------------------------------------

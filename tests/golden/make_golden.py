@@ -95,9 +95,59 @@ def projection_cases(cfg, feL, feR, fm, k, name):
     print(name, {kk: int(v) for kk, v in out.items() if kk.endswith("_n")})
 
 
+def lba_inputs(cfg, k, seed=11):
+    """Candidate points for matchByProjectionRPredLBA: this frame's keys seen from a 'last key frame' shifted by ~14 px."""
+    rng = np.random.default_rng(seed)
+    nl, nr = len(k.keyPoints), len(k.rightKeyPoints)
+    M = min(nl, 350)
+    sel = rng.permutation(nl)[:M]
+    desc = k.Desc[sel].copy()
+    flip = rng.integers(0, 256, (M, 2))
+    for i in range(M):
+        for b in flip[i]:
+            desc[i, b // 8] ^= np.uint8(1 << (b % 8))
+    predL = np.stack([k.keyPoints["x"][sel], k.keyPoints["y"][sel]], 1).astype(np.float32) + rng.normal(0, 0.8, (M, 2)).astype(np.float32)
+    ridx = k.rightIdxs[sel]
+    predR = np.full((M, 2), -1.0, np.float32)           # not visible in the right image unless stereo matched
+    has = ridx >= 0
+    predR[has, 0] = k.rightKeyPoints["x"][ridx[has]]; predR[has, 1] = k.rightKeyPoints["y"][ridx[has]]
+    predR[has] += rng.normal(0, 0.8, (int(has.sum()), 2)).astype(np.float32)
+    predL[rng.random(M) < 0.1] = -5.0                   # some points project outside the left image
+    shift = np.where(rng.random((M, 1)) < 0.8, 14.0, 3.0).astype(np.float32)   # 20 % fail the 10-px parallax test
+    lastL = predL + shift * np.array([[0.8, 0.6]], np.float32)
+    lastR = predR + shift * np.array([[0.6, -0.8]], np.float32)
+    predScale = np.clip(k.keyPoints["octave"][sel] + rng.integers(-1, 2, M), 0, cfg["n_levels"] - 1).astype(np.int32)
+    unF = np.where(rng.random(nl) < 0.15, 7, -1).astype(np.int32)
+    unFR = np.where(rng.random(nr) < 0.15, 9, -1).astype(np.int32)
+    return dict(desc=desc, predL=predL, predR=predR, predScale=predScale, lastL=lastL, lastR=lastR), unF, unFR
+
+
+def lba_case(cfg, feL, feR, fm, k, name):
+    pts, unF, unFR = lba_inputs(cfg, k)
+    out = dict(**{"pt_" + kk: v for kk, v in pts.items()}, unF=unF, unFR=unFR)
+    for rad in (4.0, 15.0):
+        n, o = fm.matchByProjectionRPredLBA(pts, k, unF, unFR, rad)
+        out[f"lba_{int(rad)}_n"] = n; out[f"lba_{int(rad)}_out"] = o
+    # MapPoint::calcDescriptor on random observation sets built from real descriptors
+    rng = np.random.default_rng(5)
+    sizes = [1, 2, 3, 4, 7, 10, 33, 64]
+    descs, offs, best = [], [0], []
+    for sz in sizes:
+        base = k.Desc[rng.integers(0, len(k.Desc))]
+        d = np.repeat(base[None], sz, 0).copy()
+        for r in range(sz):
+            for b in rng.integers(0, 256, rng.integers(0, 40)):
+                d[r, b // 8] ^= np.uint8(1 << (b % 8))
+        descs.append(d); offs.append(offs[-1] + sz); best.append(R.calcDescriptor(d))
+    out["med_descs"] = np.concatenate(descs); out["med_offsets"] = np.array(offs, np.int32); out["med_best"] = np.array(best, np.int32)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, {kk: int(v) for kk, v in out.items() if kk.endswith("_n")}, best)
+
+
 if __name__ == "__main__":
     c = stereo_case("small_s0", "small", 0, True)
     projection_cases(*c, "small_s0_proj")
+    lba_case(*c, "small_s0_lba")
     stereo_case("small_s1_ramp", "small", 1, True, ramp=True)
     stereo_case("euroc_s0", "euroc", 0, False)
     stereo_case("kitti_s0", "kitti", 0, False)

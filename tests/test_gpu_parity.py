@@ -319,3 +319,23 @@ def test_errors_are_loud():
         feL.extractKeysNew(np.zeros((10, 10), np.uint8))  # wrong size
     with pytest.raises(gvs.GvsError):
         gvs.FeatureExtractor(width=64, height=64)  # pyramid level smaller than the border
+
+
+def test_lba_matcher_and_median_descriptor(golden_dir):
+    """SURVEY 8(f) rank 1 (the backend's matcher): gvs_match_projection_lba and gvs_median_descriptor."""
+    g = np.load(os.path.join(golden_dir, "small_s0.npz")); p = np.load(os.path.join(golden_dir, "small_s0_lba.npz"))
+    cfg = synth.CONFIGS["small"]
+    feL, feR, fm = _handles(cfg, 1)
+    pts = {k[3:]: p[k] for k in p.files if k.startswith("pt_")}
+    for rad in (4, 15):
+        n, out = fm.matchByProjectionRPredLBA(pts, g["kpL"], g["descL"], g["kpR"], g["descR"], g["leftIdxs"], g["rightIdxs"], p["unF"],
+                                             p["unFR"], cfg["width"], cfg["height"], float(rad))
+        assert n == int(p[f"lba_{rad}_n"]) and np.array_equal(out, p[f"lba_{rad}_out"])
+    assert np.array_equal(fm.median_descriptor(p["med_descs"], p["med_offsets"]), p["med_best"])
+    # larger random case against the C++ oracle
+    rng = np.random.default_rng(2)
+    sizes = rng.integers(1, 120, 40)
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    descs = rng.integers(0, 256, (int(offs[-1]), 32), dtype=np.uint8)
+    descs[:, 8:] = descs[0, 8:]   # make distances small enough to tie often
+    assert np.array_equal(fm.median_descriptor(descs, offs), cpu_ref.median_descriptor(descs, offs))

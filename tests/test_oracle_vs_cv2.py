@@ -172,3 +172,17 @@ def test_analytic_depth():
     m = s["rightIdxs"] >= 0
     assert m.sum() > 500
     assert abs(np.median(s["estimatedDepth"][m]) - g["fx"] * g["baseline"] / 24) < 0.05
+
+
+def test_cpp_lba_matcher_and_median_descriptor_match_golden(golden_dir):
+    """SURVEY 8(f) rank 1: matchByProjectionRPredLBA (incl. the bestLev2 quirk of the left branch) and MapPoint::calcDescriptor."""
+    g = np.load(os.path.join(golden_dir, "small_s0.npz")); p = np.load(os.path.join(golden_dir, "small_s0_lba.npz"))
+    cfg = synth.CONFIGS["small"]
+    fe = cpu_ref.Extractor(nFeatures=cfg["n_features"], nLevels=cfg["n_levels"])
+    pts = {k[3:]: p[k] for k in p.files if k.startswith("pt_")}
+    for rad in (4, 15):
+        n, out = cpu_ref.match_lba(fe, pts, g["kpL"], g["descL"], g["kpR"], g["descR"], g["leftIdxs"], g["rightIdxs"], p["unF"], p["unFR"],
+                                   cfg["width"], cfg["height"], float(rad))
+        assert n == int(p[f"lba_{rad}_n"]) and np.array_equal(out, p[f"lba_{rad}_out"])
+        assert 0 < n < len(pts["desc"])
+    assert np.array_equal(cpu_ref.median_descriptor(p["med_descs"], p["med_offsets"]), p["med_best"])
