@@ -47,7 +47,7 @@ struct Geometry {
 };
 
 // One FAST work item = a strip of up to kFastCellsPerItem consecutive cells of one cell row.
-constexpr int kFastCellsPerItem = 4;
+constexpr int kFastCellsPerItem = 8;
 struct FastItem {
     short level, iR, iC0, nC;
 };
@@ -73,6 +73,18 @@ typedef unsigned KeptKey;
     } while (0)
 
 int fail(int code, const char* what, const char* detail = nullptr);
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remember the largest request per (kernel, device)
+template <typename K>
+inline void ensureDynamicSmem(K kernel, size_t bytes, size_t* cache /* [64] zero-initialised, one per call site */) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (bytes > 48 * 1024 && cache[dev] < bytes) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        cache[dev] = bytes;
+    }
+}
 
 struct StageTimer;
 
@@ -117,6 +129,7 @@ struct StereoArgs {
     float* depth;
     uint8_t* close;
     int* sadBest;     // dense, left offsets (scratch)
+    void* sortScratch; // nFrames x pow2ceil(keys per image) x 8 bytes, only when the sort does not fit shared memory
     double fx;
     float baseline;
     int imageHeight;

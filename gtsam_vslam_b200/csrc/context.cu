@@ -92,6 +92,7 @@ struct gvs_matcher {
     int* rightIdxs = nullptr;
     int* leftIdxs = nullptr;
     int* sadBest = nullptr;
+    void* sortScratch = nullptr;
     float* depth = nullptr;
     uint8_t* close = nullptr;
     // grids
@@ -757,7 +758,7 @@ int gvs_matcher_destroy(gvs_matcher* m) {
     if (!m) return GVS_OK;
     cudaSetDevice(m->L->device);
     cudaStreamSynchronize(m->L->stream);
-    cudaFree(m->rightIdxs); cudaFree(m->leftIdxs); cudaFree(m->sadBest); cudaFree(m->depth); cudaFree(m->close);
+    cudaFree(m->rightIdxs); cudaFree(m->leftIdxs); cudaFree(m->sadBest); cudaFree(m->sortScratch); cudaFree(m->depth); cudaFree(m->close);
     cudaFree(m->cellStartL); cudaFree(m->cellStartR); cudaFree(m->itemsL); cudaFree(m->itemsR); cudaFree(m->pj);
     cudaFree(m->pool); cudaFree(m->pjStatus);
     if (m->evR) cudaEventDestroy(m->evR);
@@ -808,6 +809,16 @@ int gvs_stereo_match_batch(gvs_matcher* m, int n_frames) {
     a.offL = m->L->imgOff; a.offR = m->R->imgOff; a.keptCntL = m->L->keptCnt; a.keptCntR = m->R->keptCnt;
     a.rightIdxs = m->rightIdxs; a.leftIdxs = m->leftIdxs; a.depth = m->depth; a.close = m->close; a.sadBest = m->sadBest;
     a.fx = m->fx; a.baseline = m->baseline; a.imageHeight = m->imageHeight; a.closeNumber = 40; a.thDist = 75;
+    {
+        size_t n2 = 1;
+        while (n2 < (size_t)m->L->g.keptPerImage) n2 <<= 1;
+        if (n2 * 8 > 160 * 1024 && !m->sortScratch) {
+            uint8_t* p = nullptr;
+            GVS_CUDA_OK(devAlloc(&p, (size_t)std::min(m->L->maxImages, m->R->maxImages) * n2 * 8));
+            m->sortScratch = p;
+        }
+        a.sortScratch = m->sortScratch;
+    }
     m->launches = 0;
     if (m->L->timing) cudaEventRecord(m->ev[0], s);
     GVS_CUDA_OK(cudaMemsetAsync(m->leftIdxs, 0xff, sizeof(int) * (size_t)std::min<size_t>((size_t)n_frames * m->R->g.keptPerImage, m->R->totalCap), s));

@@ -232,11 +232,8 @@ void launchDescribeFused(const Geometry& g, const uint8_t* slab, int nImages, co
                          int* launches) {
     const int warpsPerCta = 8;
     const int smem = warpsPerCta * kDescWarpBytes;
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(describe_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        configured = true;
-    }
+    static size_t cfg[64];
+    ensureDynamicSmem(describe_fused_kernel, (size_t)smem, cfg);
     // keys per image are only known on the device (about keptPerImage / 2): 3 keys per warp on average, grid-stride loop
     int gx = (g.keptPerImage / 2 + 3 * warpsPerCta - 1) / (3 * warpsPerCta);
     if (gx < 1) gx = 1;

@@ -57,6 +57,14 @@ __host__ __device__ inline FastSmemLayout fastLayout(int maxGW, int maxGH) {
     return L;
 }
 
+// index of the cell (inside the strip) that owns strip column lx
+__device__ __forceinline__ int cellOfStrip(int lx, int gW) {
+    int c = 0;
+#pragma unroll
+    for (int k = 1; k < kFastCellsPerItem; k++) c += lx >= k * gW;
+    return c;
+}
+
 // u16x2 lanes = 257 * (byte q, byte q+1) of the 12-byte window {w0, w1, w2}; q is a compile-time constant
 template <int Q>
 __device__ __forceinline__ unsigned pairAt(unsigned w0, unsigned w1, unsigned w2) {
@@ -153,7 +161,7 @@ fast_cells_kernel(const __grid_constant__ Geometry g, const uint8_t* __restrict_
         for (int b = 0; b < 4; b++) {
             const int lx = xu + 4 * j + b - X0;  // position inside the strip
             if (lx < 0 || lx >= cols) continue;
-            const int cl = (lx >= gW) + (lx >= 2 * gW) + (lx >= 3 * gW);
+            const int cl = cellOfStrip(lx, gW);
             const int cx0 = cl * gW, cx1 = min(cx0 + gW, cols);
             inr |= 0xffu << (8 * b);
             if (lx > cx0) hasL |= 0xffu << (8 * b);
@@ -242,7 +250,7 @@ fast_cells_kernel(const __grid_constant__ Geometry g, const uint8_t* __restrict_
             const int b = (__ffs(lm) - 1) >> 3;
             lm &= ~(0xffu << (8 * b));
             const int lx = xu + 4 * j + b - X0, s = (c >> (8 * b)) & 0xff;
-            const int cl = (lx >= gW) + (lx >= 2 * gW) + (lx >= 3 * gW);
+            const int cl = cellOfStrip(lx, gW);
             const int slot = atomicAdd(&sCnt[cl], 1);
             lists[cl * L.listCap + slot] = ((unsigned)ry << 16) | ((unsigned)(lx - cl * gW) << 8) | (unsigned)s;
             atomicMax(&sMax[cl], s);
@@ -300,11 +308,8 @@ void launchFast(const Geometry& g, const uint8_t* slab, const FastItem* items, i
     int maxGW = 0, maxGH = 0;
     for (int l = 0; l < g.nLevels; l++) { maxGW = std::max(maxGW, g.lv[l].gridW); maxGH = std::max(maxGH, g.lv[l].gridH); }
     const FastSmemLayout L = fastLayout(maxGW, maxGH);
-    static int configured = 0;
-    if (L.total > 48 * 1024 && configured < L.total) {
-        cudaFuncSetAttribute(fast_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
-        configured = L.total;
-    }
+    static size_t cfg[64];
+    ensureDynamicSmem(fast_cells_kernel, (size_t)L.total, cfg);
     cudaMemsetAsync(nCand, 0, sizeof(int) * (size_t)nImages * kMaxLevels, s);
     if (nItems > 0) {
         fast_cells_kernel<<<dim3(nItems, nImages), 256, L.total, s>>>(g, slab, items, maxGW, maxGH, recs, nCand, cellCnt, status);

@@ -263,11 +263,8 @@ void launchProject(const ProjArgs& a, cudaStream_t s, int* launches) {
     proj_candidates_kernel<<<(warps + 7) / 8, 256, 0, s>>>(a, recs);
     ++*launches;
     const size_t sm = (size_t)(a.NL + a.NR) * sizeof(int);
-    static size_t configured = 0;
-    if (sm > 48 * 1024 && configured < sm) {
-        cudaFuncSetAttribute(proj_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        configured = sm;
-    }
+    static size_t cfg[64];
+    ensureDynamicSmem(proj_resolve_kernel, sm, cfg);
     proj_resolve_kernel<<<1, 32, sm, s>>>(a, recs);
     ++*launches;
 }

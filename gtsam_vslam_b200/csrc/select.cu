@@ -26,6 +26,8 @@
 //              exact greedy independent set on the cell grid, resolved in parallel rounds (a decision is
 //              final once made).  Kept points are compacted in sorted order by a block scan.
 //              floor(y / c) with c = width / 2.0 equals (2*y) / width in integers (exact).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace gvs {
@@ -601,7 +603,9 @@ size_t selectScratchBytes(const Geometry& g) {
 int selectMaxCtas(int device) {
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    return sms > 0 ? sms * 3 : 148 * 3;
+    int per = 3;
+    if (const char* e = getenv("GVS_SELECT_CTAS_PER_SM")) per = std::max(1, atoi(e));  // tuning knob (default 3 = shared-memory limit)
+    return (sms > 0 ? sms : 148) * per;
 }
 
 void launchSelect(const Geometry& g, int nImages, const CandRec* recs, const int* nCand, const unsigned short* cellCnt,
@@ -614,12 +618,9 @@ void launchSelect(const Geometry& g, int nImages, const CandRec* recs, const int
     for (int l = 0; l < g.nLevels; l++) listCap = std::max(listCap, g.lv[l].keptCap);
     const size_t smSmall = selectSmemBytes(true, maxCells, segCapSmall, listCap);
     const size_t smBig = selectSmemBytes(false, maxCells, 1, listCap);
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(select_kernel<unsigned short, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(select_kernel<unsigned, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        configured = true;
-    }
+    static size_t cfgS[64], cfgB[64];
+    ensureDynamicSmem(select_kernel<unsigned short, true>, smSmall, cfgS);
+    ensureDynamicSmem(select_kernel<unsigned, false>, smBig, cfgB);
     const int nProb = nImages * g.nLevels;
     const int grid = std::min(nCtas, nProb);
     cudaMemsetAsync(workCounter, 0, 2 * sizeof(int), s);

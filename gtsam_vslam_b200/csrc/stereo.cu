@@ -148,8 +148,10 @@ __device__ void bitonicSort(unsigned long long* k, int n) {
 }
 
 __global__ void __launch_bounds__(256)
-stereo_finalize_kernel(const StereoArgs a, int sortCap) {
-    extern __shared__ unsigned long long sKeys[];
+stereo_finalize_kernel(const StereoArgs a, int sortCap, unsigned long long* __restrict__ gKeys) {
+    extern __shared__ unsigned long long smKeys[];
+    // sort keys live in shared memory when the per-image key capacity fits, in global scratch otherwise (very large nFeatures)
+    unsigned long long* sKeys = gKeys ? gKeys + (size_t)blockIdx.x * sortCap : smKeys;
     __shared__ int sCount;
     __shared__ float sMed;
     const int frame = blockIdx.x, tid = threadIdx.x;
@@ -218,13 +220,12 @@ void launchStereo(const Geometry& g, const StereoArgs& a, int nFrames, int maxKe
     ++*launches;
     int n2 = 1;
     while (n2 < maxKeysPerImage) n2 <<= 1;
-    const size_t sm = (size_t)n2 * 8;
-    static size_t configured = 0;
-    if (sm > 48 * 1024 && configured < sm) {
-        cudaFuncSetAttribute(stereo_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        configured = sm;
-    }
-    stereo_finalize_kernel<<<nFrames, 256, sm, s>>>(a, n2);
+    size_t sm = (size_t)n2 * 8;
+    unsigned long long* gKeys = nullptr;
+    if (sm > 160 * 1024) { gKeys = reinterpret_cast<unsigned long long*>(a.sortScratch); sm = 0; }
+    static size_t cfg[64];
+    ensureDynamicSmem(stereo_finalize_kernel, sm, cfg);
+    stereo_finalize_kernel<<<nFrames, 256, sm, s>>>(a, n2, gKeys);
     ++*launches;
 }
 

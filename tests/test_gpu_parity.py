@@ -339,3 +339,15 @@ def test_lba_matcher_and_median_descriptor(golden_dir):
     descs = rng.integers(0, 256, (int(offs[-1]), 32), dtype=np.uint8)
     descs[:, 8:] = descs[0, 8:]   # make distances small enough to tie often
     assert np.array_equal(fm.median_descriptor(descs, offs), cpu_ref.median_descriptor(descs, offs))
+
+
+def test_hires_stress_config5():
+    """BASELINE config 5: 2048x1536, 8 levels, 8000 features -- the largest sizes: more than 6144 candidates per level
+    (global-memory class of the selection kernel, 32-bit indices) and more keys per image than the shared-memory sort holds."""
+    cfg = synth.CONFIGS["hires"]
+    L, R = synth.stereo_pair(cfg["width"], cfg["height"], cfg["disparity"], 1)
+    feL, feR, fm = _handles(cfg, 1)
+    fm.track_stereo_batch(L[None].copy(), R[None].copy())
+    oL, oR, kl, dl, kr, dr, s = _oracle_frame(cfg, L, R)
+    assert len(kl) > 7000 and max(len(oL.level_keys(l, False)["x"]) for l in range(8)) > 6144
+    _assert_frame(fm, 0, cfg, kl, dl, kr, dr, s)
