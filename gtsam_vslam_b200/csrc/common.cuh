@@ -47,7 +47,7 @@ struct Geometry {
 };
 
 // One FAST work item = a strip of up to kFastCellsPerItem consecutive cells of one cell row.
-constexpr int kFastCellsPerItem = 8;
+constexpr int kFastCellsPerItem = 4;
 struct FastItem {
     short level, iR, iC0, nC;
 };
@@ -110,8 +110,8 @@ void launchDescribe(const Geometry& g, const uint8_t* slab, const uint8_t* blurS
                     int totalCap, cudaStream_t s, int* launches);
 
 void launchDescribeFused(const Geometry& g, const uint8_t* slab, int nImages, const KeptKey* kept, const int* keptCnt,
-                         const int* imgOff, gvs_keypoint* kps, uint8_t* desc, int* momentsDbg, int totalCap, cudaStream_t s,
-                         int* launches);
+                         const int* imgOff, gvs_keypoint* kps, uint8_t* desc, uint2* auxKey, int* momentsDbg, int totalCap,
+                         cudaStream_t s, int* launches);
 
 struct StereoArgs {
     const uint8_t* slabL;
@@ -124,6 +124,7 @@ struct StereoArgs {
     const int* offR;
     const int* keptCntL;  // per image per level counts (nImages x kMaxLevels)
     const int* keptCntR;
+    const uint2* auxR; // per right key: bucket row range (mn | mx << 16) and pt.y, written by the descriptor kernel
     int* rightIdxs;   // dense, left offsets
     int* leftIdxs;    // dense, right offsets
     float* depth;

@@ -69,6 +69,7 @@ struct gvs_extractor {
     int* status = nullptr;
     gvs_keypoint* kps = nullptr;
     uint8_t* desc = nullptr;
+    uint2* auxKey = nullptr;   // per key: stereo bucket row range + pt.y (compact copy for the matcher's scan)
     int totalCap = 0;
     // host (pinned)
     int* hOff = nullptr;
@@ -269,7 +270,7 @@ void destroyExtractor(gvs_extractor* fe) {
     cudaFree(fe->slab); cudaFree(fe->blurSlab); cudaFree(fe->tight); cudaFree(fe->xWeights); cudaFree(fe->xSelectors); cudaFree(fe->xBase); cudaFree(fe->taps); cudaFree(fe->fastItems); cudaFree(fe->blurItems);
     cudaFree(fe->recs); cudaFree(fe->nCand); cudaFree(fe->cellCnt); cudaFree(fe->kept); cudaFree(fe->keptCnt);
     cudaFree(fe->imgOff); cudaFree(fe->orderedDbg); cudaFree(fe->sortedDbg); cudaFree(fe->momentsDbg); cudaFree(fe->selScratch);
-    cudaFree(fe->workCounter); cudaFree(fe->status); cudaFree(fe->kps); cudaFree(fe->desc);
+    cudaFree(fe->workCounter); cudaFree(fe->status); cudaFree(fe->kps); cudaFree(fe->desc); cudaFree(fe->auxKey);
     if (fe->hOff) cudaFreeHost(fe->hOff);
     if (fe->hStatus) cudaFreeHost(fe->hStatus);
     if (fe->doneEvent) cudaEventDestroy(fe->doneEvent);
@@ -298,8 +299,8 @@ int runExtract(gvs_extractor* fe, int n) {
     launchOffsets(g, n, fe->keptCnt, fe->imgOff, fe->totalCap, fe->status, s, &fe->launches);
     // the 7x7 blur is fused into the descriptor kernel (evaluated only at the sample positions of the kept keys)
     if (T) { cudaEventRecord(fe->ev[3], s); cudaEventRecord(fe->ev[4], s); }
-    launchDescribeFused(g, fe->slab, n, fe->kept, fe->keptCnt, fe->imgOff, fe->kps, fe->desc, fe->momentsDbg, fe->totalCap, s,
-                        &fe->launches);
+    launchDescribeFused(g, fe->slab, n, fe->kept, fe->keptCnt, fe->imgOff, fe->kps, fe->desc, fe->auxKey, fe->momentsDbg,
+                        fe->totalCap, s, &fe->launches);
     if (T) cudaEventRecord(fe->ev[5], s);
     fe->blurValid = false;
     GVS_CUDA_OK(cudaMemcpyAsync(fe->hOff, fe->imgOff, sizeof(int) * (n + 1), cudaMemcpyDeviceToHost, s));
@@ -463,6 +464,7 @@ int gvs_extractor_create(gvs_extractor** out, const gvs_extractor_params* params
     fe->totalCap = (int)std::min<size_t>(B * g.keptPerImage, (size_t)1 << 30);
     GVS_TRY(devAlloc(&fe->kps, (size_t)fe->totalCap));
     GVS_TRY(devAlloc(&fe->desc, (size_t)fe->totalCap * 32));
+    GVS_TRY(devAlloc(&fe->auxKey, (size_t)fe->totalCap));
     GVS_TRY(cudaMallocHost(reinterpret_cast<void**>(&fe->hOff), sizeof(int) * (B + 1)));
     GVS_TRY(cudaMallocHost(reinterpret_cast<void**>(&fe->hStatus), sizeof(int)));
     *fe->hStatus = 0;
@@ -807,6 +809,7 @@ int gvs_stereo_match_batch(gvs_matcher* m, int n_frames) {
     StereoArgs a{};
     a.slabL = m->L->slab; a.slabR = m->R->slab; a.kpL = m->L->kps; a.kpR = m->R->kps; a.descL = m->L->desc; a.descR = m->R->desc;
     a.offL = m->L->imgOff; a.offR = m->R->imgOff; a.keptCntL = m->L->keptCnt; a.keptCntR = m->R->keptCnt;
+    a.auxR = m->R->auxKey;
     a.rightIdxs = m->rightIdxs; a.leftIdxs = m->leftIdxs; a.depth = m->depth; a.close = m->close; a.sadBest = m->sadBest;
     a.fx = m->fx; a.baseline = m->baseline; a.imageHeight = m->imageHeight; a.closeNumber = 40; a.thDist = 75;
     {

@@ -65,7 +65,7 @@ struct KeyRef { int level, x, y, score, xs, ys; };
 __global__ void __launch_bounds__(256, 3)
 describe_fused_kernel(const __grid_constant__ Geometry g, const uint8_t* __restrict__ slab, const KeptKey* __restrict__ kept,
                       const int* __restrict__ keptCnt, const int* __restrict__ imgOff, gvs_keypoint* __restrict__ kps,
-                      uint8_t* __restrict__ desc, int* __restrict__ momentsDbg, int totalCap) {
+                      uint8_t* __restrict__ desc, uint2* __restrict__ auxKey, int* __restrict__ momentsDbg, int totalCap) {
     extern __shared__ __align__(16) uint8_t dsm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int img = blockIdx.y;
@@ -221,6 +221,16 @@ describe_fused_kernel(const __grid_constant__ Geometry g, const uint8_t* __restr
             }
             reinterpret_cast<unsigned*>(kps + o)[lane] = wv;
         }
+        if (lane == 7) {
+            // compact record for the stereo matcher: the row bucket range of destributeRightKeys
+            // (src/FeatureMatcher.cpp:741-744: floor(yKey - r) .. ceil(yKey + r), r = 2*scalePyramid[octave]) and pt.y
+            float fy = (float)y;
+            if (level != 0) fy = __fmul_rn(fy, lv.scale);
+            const int yKey = __float2int_rn(fy);
+            const float r = __fmul_rn(2.0f, lv.scale);
+            const int mn = (int)floorf(__fsub_rn((float)yKey, r)), mx = (int)ceilf(__fadd_rn((float)yKey, r));
+            auxKey[o] = make_uint2(((unsigned)mn & 0xffffu) | ((unsigned)mx << 16), __float_as_uint(fy));
+        }
         if (momentsDbg && lane == 0) { momentsDbg[2 * o] = m10; momentsDbg[2 * o + 1] = m01; }
         cur = nxt;
         __syncwarp();  // everyone is done with H and this patch buffer before they are refilled
@@ -228,8 +238,8 @@ describe_fused_kernel(const __grid_constant__ Geometry g, const uint8_t* __restr
 }
 
 void launchDescribeFused(const Geometry& g, const uint8_t* slab, int nImages, const KeptKey* kept, const int* keptCnt,
-                         const int* imgOff, gvs_keypoint* kps, uint8_t* desc, int* momentsDbg, int totalCap, cudaStream_t s,
-                         int* launches) {
+                         const int* imgOff, gvs_keypoint* kps, uint8_t* desc, uint2* auxKey, int* momentsDbg, int totalCap,
+                         cudaStream_t s, int* launches) {
     const int warpsPerCta = 8;
     const int smem = warpsPerCta * kDescWarpBytes;
     static size_t cfg[64];
@@ -237,7 +247,7 @@ void launchDescribeFused(const Geometry& g, const uint8_t* slab, int nImages, co
     // keys per image are only known on the device (about keptPerImage / 2): 3 keys per warp on average, grid-stride loop
     int gx = (g.keptPerImage / 2 + 3 * warpsPerCta - 1) / (3 * warpsPerCta);
     if (gx < 1) gx = 1;
-    describe_fused_kernel<<<dim3(gx, nImages), 32 * warpsPerCta, smem, s>>>(g, slab, kept, keptCnt, imgOff, kps, desc, momentsDbg, totalCap);
+    describe_fused_kernel<<<dim3(gx, nImages), 32 * warpsPerCta, smem, s>>>(g, slab, kept, keptCnt, imgOff, kps, desc, auxKey, momentsDbg, totalCap);
     ++*launches;
 }
 

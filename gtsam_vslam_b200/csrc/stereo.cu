@@ -54,12 +54,11 @@ stereo_match_kernel(const __grid_constant__ Geometry g, const StereoArgs a) {
             const int j0 = sLvlStart[max(octL - 1, 0)], j1 = sLvlStart[min(octL + 2, kMaxLevels)];
             unsigned best = 0xffffffffu;
             for (int j = j0 + lane; j < min(j1, nR); j += 32) {
-                const gvs_keypoint kr = a.kpR[offR + j];
-                const int yKeyR = __float2int_rn(kr.y);
-                const float r = __fmul_rn(2.0f, g.lv[kr.octave].scale);
-                const int mn = (int)floorf(__fsub_rn((float)yKeyR, r)), mx = (int)ceilf(__fadd_rn((float)yKeyR, r));
+                const uint2 ar = __ldg(a.auxR + offR + j);  // bucket rows [mn, mx] of this right key, and its pt.y
+                const int mn = (int)(ar.x & 0xffffu), mx = (int)(ar.x >> 16);
                 if (yKey < mn || yKey > mx) continue;
-                if (!(kr.y >= minU && kr.y <= maxU)) continue;
+                const float yR = __uint_as_float(ar.y);
+                if (!(yR >= minU && yR <= maxU)) continue;
                 const uint4* dr = reinterpret_cast<const uint4*>(a.descR + (size_t)(offR + j) * 32);
                 const int dist = hamming256(l0, l1, __ldg(dr), __ldg(dr + 1));
                 best = min(best, ((unsigned)dist << 20) | (unsigned)j);
