@@ -355,7 +355,7 @@ def main():
     }
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        sample = min(F, max(cores, 8 * cores))  # about 10-30 core-seconds of CPU work
+        sample = F  # the whole batch: about 10-30 core-seconds of CPU work
         v_all, dt_all, _ = cpu_reference_rate(cfg, L[:sample], R[:sample], cores, shape=1)
         s2 = min(sample, 6)
         v_ref, dt_ref, _ = cpu_reference_rate(cfg, L[:s2], R[:s2], 2, shape=0)

@@ -27,7 +27,7 @@ SYMBOLS = [
     "gvs_last_error", "gvs_version", "gvs_default_params", "gvs_device_count",
     "gvs_extractor_create", "gvs_extractor_destroy", "gvs_extractor_tables", "gvs_extractor_level_size",
     "gvs_extract", "gvs_extract_batch_host", "gvs_extractor_input", "gvs_extract_batch_resident",
-    "gvs_extractor_sync", "gvs_extract_offsets", "gvs_extract_download", "gvs_extractor_set_stream",
+    "gvs_extractor_sync", "gvs_extractor_set_rectify_maps", "gvs_extract_batch_host_raw", "gvs_extract_offsets", "gvs_extract_download", "gvs_extractor_set_stream",
     "gvs_debug_level_image", "gvs_debug_level_candidates", "gvs_debug_level_kept", "gvs_debug_select",
     "gvs_matcher_create", "gvs_matcher_destroy", "gvs_stereo_match_batch", "gvs_stereo_download",
     "gvs_assign_grids_batch", "gvs_grid_download", "gvs_track_stereo_batch_host",
@@ -93,6 +93,8 @@ def load_library() -> C.CDLL:
     lib.gvs_extractor_input.argtypes = [vp, C.POINTER(vp), C.POINTER(i32), C.POINTER(C.c_size_t)]
     lib.gvs_extract_batch_resident.argtypes = [vp, i32]
     lib.gvs_extractor_sync.argtypes = [vp]
+    lib.gvs_extractor_set_rectify_maps.argtypes = [vp, vp, vp]
+    lib.gvs_extract_batch_host_raw.argtypes = [vp, vp, i32, i32]
     lib.gvs_extract_offsets.argtypes = [vp, vp]
     lib.gvs_extract_download.argtypes = [vp, i32, i32, vp, vp, i32]
     lib.gvs_extractor_set_stream.argtypes = [vp, vp]
@@ -210,6 +212,22 @@ class FeatureExtractor:
         assert (h, w) == (self.height, self.width)
         self._keep = images
         _check(self._lib.gvs_extract_batch_host(self.h, _p(images), h * w, w, n))
+
+    def set_rectify_maps(self, mapx: np.ndarray | None, mapy: np.ndarray | None) -> None:
+        """cv::initUndistortRectifyMap outputs (CV_32FC1), or None/None for already rectified cameras."""
+        if mapx is None:
+            _check(self._lib.gvs_extractor_set_rectify_maps(self.h, None, None))
+            return
+        mx = np.ascontiguousarray(mapx, np.float32); my = np.ascontiguousarray(mapy, np.float32)
+        assert mx.shape == (self.height, self.width) and my.shape == mx.shape
+        _check(self._lib.gvs_extractor_set_rectify_maps(self.h, _p(mx), _p(my)))
+
+    def extract_batch_raw(self, images: np.ndarray) -> None:
+        """Raw camera frames (n, H, W, 3) BGR or (n, H, W) gray: remap + BGR2GRAY on the device, then extraction."""
+        assert images.dtype == np.uint8 and images.flags.c_contiguous and images.shape[1:3] == (self.height, self.width)
+        ch = 1 if images.ndim == 3 else images.shape[3]
+        self._keep = images
+        _check(self._lib.gvs_extract_batch_host_raw(self.h, _p(images), ch, images.shape[0]))
 
     def input_layout(self):
         dev, pitch, stride = C.c_void_p(), C.c_int(), C.c_size_t()

@@ -91,6 +91,8 @@ struct StageTimer;
 // ---- kernel launchers (one translation unit each) -------------------------------------------------
 void launchPyramid(const Geometry& g, uint8_t* slab, const ResizeTap* taps, const uint4* xw, const uint4* xs,
                    const unsigned short* xbase, int nImages, cudaStream_t s, int* launches);
+void launchPrepare(const Geometry& g, const uint8_t* src, int channels, const float* mapx, const float* mapy, uint8_t* slab,
+                   int nImages, cudaStream_t s, int* launches);
 void launchRepack(const Geometry& g, const uint8_t* tight, uint8_t* slab, int nImages, cudaStream_t s, int* launches);
 void launchFast(const Geometry& g, const uint8_t* slab, const FastItem* items, int nItems, int nImages, CandRec* recs,
                 int* nCand, unsigned short* cellCnt, int* status, cudaStream_t s, int* launches);

@@ -45,6 +45,9 @@ struct gvs_extractor {
     uint8_t* slab = nullptr;
     uint8_t* blurSlab = nullptr;
     uint8_t* tight = nullptr;   // staging for tightly packed host batches (one contiguous DMA, then repack)
+    size_t tightBytes = 0;
+    float* mapX = nullptr;      // rectification maps of cv::remap (optional, gvs_extractor_set_rectify_maps)
+    float* mapY = nullptr;
     ResizeTap* taps = nullptr;
     uint4* xWeights = nullptr;        // per group of 4 destination columns: a0 | a1 << 16 of each column
     uint4* xSelectors = nullptr;      // ... PRMT selector (| 1 << 16 when the pair sits in the upper 8 bytes of the window)
@@ -267,7 +270,7 @@ void destroyExtractor(gvs_extractor* fe) {
     if (!fe) return;
     cudaSetDevice(fe->device);
     if (fe->ownStream) cudaStreamSynchronize(fe->ownStream);
-    cudaFree(fe->slab); cudaFree(fe->blurSlab); cudaFree(fe->tight); cudaFree(fe->xWeights); cudaFree(fe->xSelectors); cudaFree(fe->xBase); cudaFree(fe->taps); cudaFree(fe->fastItems); cudaFree(fe->blurItems);
+    cudaFree(fe->slab); cudaFree(fe->blurSlab); cudaFree(fe->tight); cudaFree(fe->mapX); cudaFree(fe->mapY); cudaFree(fe->xWeights); cudaFree(fe->xSelectors); cudaFree(fe->xBase); cudaFree(fe->taps); cudaFree(fe->fastItems); cudaFree(fe->blurItems);
     cudaFree(fe->recs); cudaFree(fe->nCand); cudaFree(fe->cellCnt); cudaFree(fe->kept); cudaFree(fe->keptCnt);
     cudaFree(fe->imgOff); cudaFree(fe->orderedDbg); cudaFree(fe->sortedDbg); cudaFree(fe->momentsDbg); cudaFree(fe->selScratch);
     cudaFree(fe->workCounter); cudaFree(fe->status); cudaFree(fe->kps); cudaFree(fe->desc); cudaFree(fe->auxKey);
@@ -396,7 +399,6 @@ int gvs_extractor_create(gvs_extractor** out, const gvs_extractor_params* params
     GVS_TRY(cudaEventCreateWithFlags(&fe->evBlur, cudaEventDisableTiming));
     for (auto& e : fe->ev) GVS_TRY(cudaEventCreate(&e));
     GVS_TRY(devAlloc(&fe->slab, B * g.slabBytes + 256));
-    GVS_TRY(devAlloc(&fe->blurSlab, B * g.slabBytes + 256));
     GVS_TRY(cudaMemset(fe->slab, 0, B * g.slabBytes + 256));
     {
         std::vector<ResizeTap> taps;
@@ -531,7 +533,13 @@ int gvs_extract_batch_host(gvs_extractor* fe, const uint8_t* images, size_t imag
     const LevelGeom& l0 = fe->g.lv[0];
     if (row_stride == fe->width && image_stride == (size_t)fe->width * fe->height) {
         // tightly packed batch: one contiguous DMA into a staging buffer, then a repack kernel into the pitched store
-        if (!fe->tight) GVS_CUDA_OK(devAlloc(&fe->tight, (size_t)fe->maxImages * fe->width * fe->height + 16));
+        const size_t need = (size_t)fe->maxImages * fe->width * fe->height + 16;
+        if (fe->tightBytes < need) {
+            GVS_CUDA_OK(cudaStreamSynchronize(fe->stream));
+            cudaFree(fe->tight); fe->tight = nullptr; fe->tightBytes = 0;
+            GVS_CUDA_OK(devAlloc(&fe->tight, need));
+            fe->tightBytes = need;
+        }
         GVS_CUDA_OK(cudaMemcpyAsync(fe->tight, images, (size_t)n_images * image_stride, cudaMemcpyHostToDevice, fe->stream));
         int launches = 0;
         launchRepack(fe->g, fe->tight, fe->slab, n_images, fe->stream, &launches);
@@ -541,6 +549,43 @@ int gvs_extract_batch_host(gvs_extractor* fe, const uint8_t* images, size_t imag
     for (int i = 0; i < n_images; i++)
         GVS_CUDA_OK(cudaMemcpy2DAsync(fe->slab + (size_t)i * fe->g.slabBytes + l0.off, l0.pitch, images + (size_t)i * image_stride,
                                       row_stride, fe->width, fe->height, cudaMemcpyHostToDevice, fe->stream));
+    return runExtract(fe, n_images);
+}
+
+int gvs_extractor_set_rectify_maps(gvs_extractor* fe, const float* map_x, const float* map_y) {
+    if (!fe) return fail(GVS_ERR_INVALID, "null extractor");
+    GVS_CUDA_OK(cudaSetDevice(fe->device));
+    GVS_CUDA_OK(cudaStreamSynchronize(fe->stream));
+    if (!map_x || !map_y) {
+        cudaFree(fe->mapX); cudaFree(fe->mapY);
+        fe->mapX = fe->mapY = nullptr;
+        return GVS_OK;
+    }
+    const size_t n = (size_t)fe->width * fe->height;
+    if (!fe->mapX) GVS_CUDA_OK(devAlloc(&fe->mapX, n));
+    if (!fe->mapY) GVS_CUDA_OK(devAlloc(&fe->mapY, n));
+    GVS_CUDA_OK(cudaMemcpy(fe->mapX, map_x, n * sizeof(float), cudaMemcpyHostToDevice));
+    GVS_CUDA_OK(cudaMemcpy(fe->mapY, map_y, n * sizeof(float), cudaMemcpyHostToDevice));
+    return GVS_OK;
+}
+
+int gvs_extract_batch_host_raw(gvs_extractor* fe, const uint8_t* images, int channels, int n_images) {
+    int rc = checkBatch(fe, n_images);
+    if (rc) return rc;
+    if (!images || (channels != 1 && channels != 3)) return fail(GVS_ERR_INVALID, "raw images must be tightly packed, 1 or 3 channels");
+    GVS_CUDA_OK(cudaSetDevice(fe->device));
+    const size_t per = (size_t)fe->width * fe->height * channels;
+    const size_t need = (size_t)fe->maxImages * fe->width * fe->height * 3 + 16;
+    if (fe->tightBytes < need) {
+        GVS_CUDA_OK(cudaStreamSynchronize(fe->stream));
+        cudaFree(fe->tight); fe->tight = nullptr; fe->tightBytes = 0;
+        GVS_CUDA_OK(devAlloc(&fe->tight, need));
+        fe->tightBytes = need;
+    }
+    GVS_CUDA_OK(cudaMemcpyAsync(fe->tight, images, per * n_images, cudaMemcpyHostToDevice, fe->stream));
+    int launches = 0;
+    launchPrepare(fe->g, fe->tight, channels, fe->mapX, fe->mapY, fe->slab, n_images, fe->stream, &launches);
+    fe->launchesTotal += launches;
     return runExtract(fe, n_images);
 }
 
@@ -611,11 +656,13 @@ int gvs_debug_level_image(gvs_extractor* fe, int image, int level, int blurred, 
     GVS_CUDA_OK(cudaSetDevice(fe->device));
     const LevelGeom& lv = fe->g.lv[level];
     if (blurred && !fe->blurValid && fe->lastN > 0) {  // cv::GaussianBlur of every level, dense (src/FeatureExtractor.cpp:512-515)
+        if (!fe->blurSlab) GVS_CUDA_OK(devAlloc(&fe->blurSlab, (size_t)fe->maxImages * fe->g.slabBytes + 256));
         int launches = 0;
         launchBlur(fe->g, fe->slab, fe->blurSlab, fe->blurItems, fe->nBlurItems, fe->lastN, fe->stream, &launches);
         fe->launchesTotal += launches;
         fe->blurValid = true;
     }
+    if (blurred && !fe->blurSlab) return fail(GVS_ERR_STATE, "no batch has been extracted");
     const uint8_t* src = (blurred ? fe->blurSlab : fe->slab) + (size_t)image * fe->g.slabBytes + lv.off;
     GVS_CUDA_OK(cudaStreamSynchronize(fe->stream));
     GVS_CUDA_OK(cudaMemcpy2D(out, lv.w, src, lv.pitch, lv.w, lv.h, cudaMemcpyDeviceToHost));

@@ -81,6 +81,65 @@ void launchRepack(const Geometry& g, const uint8_t* tight, uint8_t* slab, int nI
     ++*launches;
 }
 
+// Upstream image preparation: cv::remap(INTER_LINEAR, BORDER_CONSTANT 0) with the CV_32FC1 rectification maps
+// (reference src/VIOSlam.cpp:282-301) fused with cvtColor BGR2GRAY (src/FeatureTracker.cpp:1131-1135), written straight into the
+// pitched level-0 store.  OpenCV arithmetic: sx = cvRound(mapx * 32) (float32), 5 fractional bits, weights (32-fx)(32-fy)*32 etc.
+// (the first one saturated to short), channel = (sum + 2^14) >> 15; gray = (3735 B + 19235 G + 9798 R + 2^14) >> 15.
+// Thread = 4 destination pixels of one row (one 4-byte store).  HBM/L2 gather bound: 8 map bytes + 4 taps per pixel.
+template <int CH>
+__global__ void __launch_bounds__(256)
+prepare_level0_kernel(const __grid_constant__ Geometry g, const uint8_t* __restrict__ srcImgs, const float* __restrict__ mapx,
+                      const float* __restrict__ mapy, uint8_t* __restrict__ slab) {
+    const LevelGeom& lv = g.lv[0];
+    const int img = blockIdx.z, y = blockIdx.y * 4 + threadIdx.y;
+    const int x0 = (blockIdx.x * 64 + threadIdx.x) * 4;
+    if (x0 >= lv.w || y >= lv.h) return;
+    const uint8_t* src = srcImgs + (size_t)img * lv.w * lv.h * CH;
+    unsigned out = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int x = x0 + i;
+        int v[CH];
+#pragma unroll
+        for (int c = 0; c < CH; c++) v[c] = 0;
+        if (x < lv.w) {
+            if (mapx) {
+                const size_t m = (size_t)y * lv.w + x;
+                const int sx = __float2int_rn(__fmul_rn(__ldg(mapx + m), 32.f)), sy = __float2int_rn(__fmul_rn(__ldg(mapy + m), 32.f));
+                const int fx = sx & 31, fy = sy & 31;
+                const int ix = min(max(sx >> 5, -32768), 32767), iy = min(max(sy >> 5, -32768), 32767);
+                const int wt[4] = {min((32 - fx) * (32 - fy) * 32, 32767), fx * (32 - fy) * 32, (32 - fx) * fy * 32, fx * fy * 32};
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    const int px = ix + (t & 1), py = iy + (t >> 1);
+                    if (px >= 0 && px < lv.w && py >= 0 && py < lv.h) {
+                        const uint8_t* p = src + ((size_t)py * lv.w + px) * CH;
+#pragma unroll
+                        for (int c = 0; c < CH; c++) v[c] += (int)p[c] * wt[t];
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < CH; c++) v[c] = min(max((v[c] + 16384) >> 15, 0), 255);
+            } else {
+                const uint8_t* p = src + ((size_t)y * lv.w + x) * CH;
+#pragma unroll
+                for (int c = 0; c < CH; c++) v[c] = p[c];
+            }
+        }
+        const int gray = CH == 3 ? (v[0] * 3735 + v[CH > 1 ? 1 : 0] * 19235 + v[CH > 2 ? 2 : 0] * 9798 + 16384) >> 15 : v[0];
+        out |= (unsigned)(gray & 0xff) << (8 * i);
+    }
+    *reinterpret_cast<unsigned*>(slab + (size_t)img * g.slabBytes + lv.off + (size_t)y * lv.pitch + x0) = out;
+}
+
+void launchPrepare(const Geometry& g, const uint8_t* src, int channels, const float* mapx, const float* mapy, uint8_t* slab,
+                   int nImages, cudaStream_t s, int* launches) {
+    dim3 grid((g.lv[0].w + 255) / 256, (g.lv[0].h + 3) / 4, nImages);
+    if (channels == 3) prepare_level0_kernel<3><<<grid, dim3(64, 4), 0, s>>>(g, src, mapx, mapy, slab);
+    else prepare_level0_kernel<1><<<grid, dim3(64, 4), 0, s>>>(g, src, mapx, mapy, slab);
+    ++*launches;
+}
+
 void launchPyramid(const Geometry& g, uint8_t* slab, const ResizeTap* taps, const uint4* xw, const uint4* xs,
                    const unsigned short* xbase, int nImages, cudaStream_t s, int* launches) {
     for (int l = 1; l < g.nLevels; l++) {

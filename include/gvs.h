@@ -96,6 +96,12 @@ int gvs_extract_batch_host(gvs_extractor* fe, const uint8_t* images, size_t imag
  * rows *pitch bytes apart, images *image_stride bytes apart), then runs n_images slots. */
 int gvs_extractor_input(gvs_extractor* fe, uint8_t** dev, int* pitch, size_t* image_stride);
 int gvs_extract_batch_resident(gvs_extractor* fe, int n_images);
+/* Upstream image preparation on the device, so that raw camera frames go straight to the GPU:
+ * cv::remap(INTER_LINEAR) with the CV_32FC1 maps of cv::initUndistortRectifyMap (src/VIOSlam.cpp:282-301) followed by
+ * cvtColor(BGR2GRAY) (src/FeatureTracker.cpp:1131-1135).  Maps: width*height floats each, NULL/NULL = images are already
+ * rectified (Camera.rectified).  Raw images: tightly packed, `channels` = 3 (BGR, what cv::imread(IMREAD_COLOR) returns) or 1. */
+int gvs_extractor_set_rectify_maps(gvs_extractor* fe, const float* map_x, const float* map_y);
+int gvs_extract_batch_host_raw(gvs_extractor* fe, const uint8_t* images, int channels, int n_images);
 int gvs_extractor_sync(gvs_extractor* fe);
 
 /* Per-image results of the last batch.  offsets has n_images+1 entries: image i owns [offsets[i], offsets[i+1])

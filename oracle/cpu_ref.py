@@ -176,6 +176,18 @@ def median_descriptor(descs: np.ndarray, offsets: np.ndarray) -> np.ndarray:
     return out
 
 
+def prepare_image(image: np.ndarray, mapx=None, mapy=None) -> np.ndarray:
+    """cv::remap(INTER_LINEAR) + cvtColor(BGR2GRAY) restated (reference src/VIOSlam.cpp:282-301, src/FeatureTracker.cpp:1131-1135)."""
+    image = np.ascontiguousarray(image, np.uint8)
+    h, w = image.shape[:2]
+    ch = 1 if image.ndim == 2 else image.shape[2]
+    out = np.zeros((h, w), np.uint8)
+    mx = None if mapx is None else np.ascontiguousarray(mapx, np.float32)
+    my = None if mapy is None else np.ascontiguousarray(mapy, np.float32)
+    lib().ora_prepare_image(_p(image), w, h, ch, _p(mx), _p(my), _p(out))
+    return out
+
+
 def stereo_frames(params, fx, baseline, L: np.ndarray, R: np.ndarray, shape: int, threads: int):
     """CPU baseline: run F stereo frames; returns (total matches, per-frame left key counts)."""
     L = np.ascontiguousarray(L, np.uint8); R = np.ascontiguousarray(R, np.uint8)

@@ -691,6 +691,16 @@ class FeatureMatcher:
         return nMatches, out
 
 
+def prepareImage(image: np.ndarray, mapx: np.ndarray | None = None, mapy: np.ndarray | None = None) -> np.ndarray:
+    """Upstream image preparation (SURVEY 8(f) rank 2): cv::remap(INTER_LINEAR) with the CV_32F rectification maps
+    (src/VIOSlam.cpp:282-301), then cvtColor BGR2GRAY (src/FeatureTracker.cpp:1131-1135)."""
+    if mapx is not None:
+        image = cv2.remap(image, mapx, mapy, cv2.INTER_LINEAR)
+    if image.ndim == 3:
+        image = cv2.cvtColor(image, cv2.COLOR_BGR2GRAY)
+    return image
+
+
 def calcDescriptor(descs: np.ndarray) -> int:
     """MapPoint::calcDescriptor (src/Map.cpp:145-210): index of the descriptor with the least median distance to the rest."""
     N = len(descs)

@@ -351,3 +351,65 @@ def test_hires_stress_config5():
     oL, oR, kl, dl, kr, dr, s = _oracle_frame(cfg, L, R)
     assert len(kl) > 7000 and max(len(oL.level_keys(l, False)["x"]) for l in range(8)) > 6144
     _assert_frame(fm, 0, cfg, kl, dl, kr, dr, s)
+
+
+def test_raw_frames_remap_and_gray_on_device():
+    """BGR frames + rectification maps in, same keys as remap + cvtColor + extractKeysNew on the CPU."""
+    cfg = synth.CONFIGS["small"]
+    w, h = cfg["width"], cfg["height"]
+    L, R = synth.stereo_pair(w, h, cfg["disparity"], 41)
+    rng = np.random.default_rng(0)
+    bgr = np.stack([L, R, np.clip(L.astype(int) + rng.integers(-9, 10, L.shape), 0, 255).astype(np.uint8)], axis=-1)  # B, G, R planes
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    r2 = ((xx - w / 2) ** 2 + (yy - h / 2) ** 2) / np.float32(w * w)
+    mx = (xx + (xx - w / 2) * np.float32(0.12) * r2 + np.float32(0.8)).astype(np.float32)
+    my = (yy + (yy - h / 2) * np.float32(0.12) * r2 - np.float32(0.4)).astype(np.float32)
+    fe = gvs.FeatureExtractor(nFeatures=cfg["n_features"], nLevels=cfg["n_levels"], width=w, height=h, max_images=2)
+    o = cpu_ref.Extractor(cfg["n_features"], cfg["n_levels"])
+    batch = np.ascontiguousarray(np.stack([bgr, bgr[:, ::-1].copy()]))
+    for maps in ((mx, my), (None, None)):
+        fe.set_rectify_maps(*maps)
+        fe.extract_batch_raw(batch)
+        off = fe.offsets(2)
+        for i in range(2):
+            gray = cpu_ref.prepare_image(batch[i], *maps)
+            assert np.array_equal(fe.level_image(i, 0), gray)
+            ok, od = o.extractKeysNew(gray)
+            kp, d = fe.download(i, 1, int(off[i + 1] - off[i]))
+            _assert_keys(kp, d, ok, od)
+    # single-channel raw frames through the same entry point
+    fe.set_rectify_maps(mx, my)
+    fe.extract_batch_raw(np.ascontiguousarray(np.stack([L, R])))
+    assert np.array_equal(fe.level_image(1, 0), cpu_ref.prepare_image(R, mx, my))
+
+
+def test_strided_host_images_and_resident_input():
+    """Host images with a row stride (2-D copy path) and the device-resident input path give the same keys as the tight path."""
+    import torch
+    cfg = synth.CONFIGS["small"]
+    w, h = cfg["width"], cfg["height"]
+    Ls, _ = synth.stereo_batch(w, h, cfg["disparity"], [50, 51, 52])
+    fe = gvs.FeatureExtractor(nFeatures=cfg["n_features"], nLevels=cfg["n_levels"], width=w, height=h, max_images=3)
+    fe.extract_batch(Ls)
+    off = fe.offsets(3)
+    ref = fe.download(0, 3, int(off[3]))
+    ref = (ref[0].copy(), ref[1].copy())
+    padded = np.zeros((3, h + 2, w + 24), np.uint8)
+    padded[:, :h, :w] = Ls
+    lib = gvs.load_library()
+    assert lib.gvs_extract_batch_host(fe.h, padded.ctypes.data, padded.strides[0], padded.strides[1], 3) == 0
+    off2 = fe.offsets(3)
+    got = fe.download(0, 3, int(off2[3]))
+    assert np.array_equal(off, off2) and got[0].tobytes() == ref[0].tobytes() and np.array_equal(got[1], ref[1])
+    dev, pitch, stride = fe.input_layout()
+
+    class _Ext:
+        __cuda_array_interface__ = {"shape": (3, stride // pitch, pitch), "typestr": "|u1", "data": (dev, False), "version": 2}
+    store = torch.as_tensor(_Ext(), device="cuda")
+    store.zero_()
+    store[:, :h, :w].copy_(torch.from_numpy(Ls).cuda())
+    torch.cuda.synchronize()
+    fe.extract_batch_resident(3)
+    off3 = fe.offsets(3)
+    got = fe.download(0, 3, int(off3[3]))
+    assert np.array_equal(off, off3) and got[0].tobytes() == ref[0].tobytes() and np.array_equal(got[1], ref[1])

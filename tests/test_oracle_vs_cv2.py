@@ -186,3 +186,23 @@ def test_cpp_lba_matcher_and_median_descriptor_match_golden(golden_dir):
         assert n == int(p[f"lba_{rad}_n"]) and np.array_equal(out, p[f"lba_{rad}_out"])
         assert 0 < n < len(pts["desc"])
     assert np.array_equal(cpu_ref.median_descriptor(p["med_descs"], p["med_offsets"]), p["med_best"])
+
+
+def _distortion_maps(w, h, k=0.15, dx=1.3, dy=-0.7):
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    r2 = ((xx - w / 2) ** 2 + (yy - h / 2) ** 2) / np.float32(w * w)
+    return (xx + (xx - w / 2) * np.float32(k) * r2 + np.float32(dx)).astype(np.float32), \
+           (yy + (yy - h / 2) * np.float32(k) * r2 + np.float32(dy)).astype(np.float32)
+
+
+def test_image_preparation_matches_cv2():
+    """SURVEY 8(f) rank 2: cv::remap(INTER_LINEAR, CV_32F maps) + cvtColor(BGR2GRAY) restated, against cv2."""
+    rng = np.random.default_rng(3)
+    for (h, w) in ((240, 320), (97, 131)):
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        mx, my = _distortion_maps(w, h)
+        mx[0, :6] = [-5, -0.5, 0.0, w - 1.01, w - 0.5, w + 3]; my[0, :6] = [3, 3, 0.0, h - 1.01, 20, 5]   # border cases
+        assert np.array_equal(cpu_ref.prepare_image(img, mx, my), ref_cv2.prepareImage(img, mx, my))
+        assert np.array_equal(cpu_ref.prepare_image(img), cv2.cvtColor(img, cv2.COLOR_BGR2GRAY))
+        g = np.ascontiguousarray(img[..., 1])
+        assert np.array_equal(cpu_ref.prepare_image(g, mx, my), cv2.remap(g, mx, my, cv2.INTER_LINEAR))
