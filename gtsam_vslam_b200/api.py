@@ -32,7 +32,7 @@ SYMBOLS = [
     "gvs_matcher_create", "gvs_matcher_destroy", "gvs_stereo_match_batch", "gvs_stereo_download",
     "gvs_assign_grids_batch", "gvs_grid_download", "gvs_track_stereo_batch_host",
     "gvs_track_stereo_batch_resident", "gvs_matcher_sync", "gvs_matcher_set_stream", "gvs_match_projection", "gvs_descriptor_distance",
-    "gvs_match_projection_lba", "gvs_median_descriptor", "gvs_extractor_enable_timing", "gvs_extractor_stage_times", "gvs_matcher_launch_count",
+    "gvs_match_projection_lba", "gvs_median_descriptor", "gvs_project_mappoints", "gvs_extractor_enable_timing", "gvs_extractor_stage_times", "gvs_matcher_launch_count",
     "gvs_extractor_launch_count",
 ]
 
@@ -116,6 +116,8 @@ def load_library() -> C.CDLL:
     lib.gvs_descriptor_distance.argtypes = [vp, vp, vp, i32, vp]
     lib.gvs_match_projection_lba.argtypes = [vp, C.POINTER(_LbaFrame), C.POINTER(_LbaPoints), f32, vp, C.POINTER(i32)]
     lib.gvs_median_descriptor.argtypes = [vp, vp, vp, i32, vp]
+    dbl = C.c_double
+    lib.gvs_project_mappoints.argtypes = [vp, vp, dbl, dbl, dbl, dbl, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
     lib.gvs_extractor_enable_timing.argtypes = [vp, i32]
     lib.gvs_extractor_stage_times.argtypes = [vp, C.POINTER(StageTimes)]
     lib.gvs_matcher_launch_count.argtypes = [vp, C.POINTER(C.c_int64)]
@@ -440,6 +442,17 @@ class FeatureMatcher:
         out = np.zeros(len(offsets) - 1, np.int32)
         _check(self._lib.gvs_median_descriptor(self.h, _p(descs), _p(offsets), len(out), _p(out)))
         return out
+
+    # -- FeatureTracker::worldToFrame + MapPoint::predictScale (src/FeatureTracker.cpp:685-741, src/Map.cpp:13-23), batched
+    def worldToFrame(self, poseInv, fx, fy, cx, cy, width, height, wPos, maxScaleDist, logScale, nScaleLev, pred, scaleLevel):
+        c = lambda a, dt: np.ascontiguousarray(a, dt)
+        M = len(wPos)
+        inF = np.zeros(max(M, 1), np.uint8)
+        assert pred.dtype == np.float32 and scaleLevel.dtype == np.int32 and pred.flags.c_contiguous
+        keep = [c(poseInv, np.float64), c(wPos, np.float64), c(maxScaleDist, np.float32), c(logScale, np.float32), c(nScaleLev, np.int32)]
+        _check(self._lib.gvs_project_mappoints(self.h, _p(keep[0]), fx, fy, cx, cy, width, height, M, _p(keep[1]), _p(keep[2]), _p(keep[3]),
+                                               _p(keep[4]), _p(pred), _p(scaleLevel), _p(inF)))
+        return inF[:M]
 
     def DescriptorDistance(self, a: np.ndarray, b: np.ndarray) -> np.ndarray:
         a = np.ascontiguousarray(a, np.uint8).reshape(-1, 32); b = np.ascontiguousarray(b, np.uint8).reshape(-1, 32)

@@ -107,10 +107,6 @@ struct BlurItem { short level, tx, ty, pad; };  // one 64x32 output tile
 constexpr int kBlurTW = 64, kBlurTH = 32;
 void launchBlur(const Geometry& g, const uint8_t* slab, uint8_t* blurSlab, const BlurItem* items, int nItems, int nImages,
                 cudaStream_t s, int* launches);
-void launchDescribe(const Geometry& g, const uint8_t* slab, const uint8_t* blurSlab, int nImages, const KeptKey* kept,
-                    const int* keptCnt, const int* imgOff, gvs_keypoint* kps, uint8_t* desc, int* momentsDbg,
-                    int totalCap, cudaStream_t s, int* launches);
-
 void launchDescribeFused(const Geometry& g, const uint8_t* slab, int nImages, const KeptKey* kept, const int* keptCnt,
                          const int* imgOff, gvs_keypoint* kps, uint8_t* desc, uint2* auxKey, int* momentsDbg, int totalCap,
                          cudaStream_t s, int* launches);
@@ -193,6 +189,9 @@ struct ProjArgs {
 void launchProject(const ProjArgs& a, cudaStream_t s, int* launches);
 void launchProjectLBA(const ProjArgs& a, const float* lastL, const float* lastR, int* out, cudaStream_t s, int* launches);
 void launchMedianDescriptor(const uint8_t* descs, const int* offsets, int P, int* bestIdx, cudaStream_t s, int* launches);
+void launchWorldToFrame(int M, const double* poseInv, double fx, double fy, double cx, double cy, int width, int height,
+                        const double* wPos, const float* maxScaleDist, const float* logScale, const int* nScaleLev, float* pred,
+                        int* scaleLevel, uint8_t* inFrame, cudaStream_t s, int* launches);
 void launchHamming(const uint8_t* a, const uint8_t* b, int n, int* out, cudaStream_t s, int* launches);
 
 // status bits written by kernels into a device int (checked on sync)

@@ -1205,6 +1205,45 @@ int gvs_match_projection_lba(gvs_matcher* m, const gvs_lba_frame* kf, const gvs_
     return GVS_OK;
 }
 
+int gvs_project_mappoints(gvs_matcher* m, const double* pose_inv, double fx, double fy, double cx, double cy, int width, int height,
+                          int count, const double* world_pos, const float* max_scale_dist, const float* log_scale,
+                          const int32_t* n_scale_lev, float* pred, int32_t* scale_level, uint8_t* in_frame) {
+    if (!m || !pose_inv || count < 0) return fail(GVS_ERR_INVALID, "bad argument");
+    if (count == 0) return GVS_OK;
+    if (!world_pos || !max_scale_dist || !log_scale || !n_scale_lev || !pred || !scale_level || !in_frame) return fail(GVS_ERR_INVALID, "null array");
+    GVS_CUDA_OK(cudaSetDevice(m->L->device));
+    cudaStream_t s = m->L->stream;
+    const size_t M = (size_t)count;
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t oPose = 0, oW = al(128), oMs = oW + al(M * 32), oLs = oMs + al(M * 4), oNl = oLs + al(M * 4), oPr = oNl + al(M * 4),
+                 oSl = oPr + al(M * 8), oIf = oSl + al(M * 4), total = oIf + al(M);
+    if (total > m->pjBytes) {
+        GVS_CUDA_OK(cudaStreamSynchronize(s));
+        cudaFree(m->pj); m->pj = nullptr; m->pjBytes = 0;
+        GVS_CUDA_OK(devAlloc(&m->pj, total));
+        m->pjBytes = total;
+    }
+    uint8_t* b = m->pj;
+    GVS_CUDA_OK(cudaMemcpyAsync(b + oPose, pose_inv, 128, cudaMemcpyHostToDevice, s));
+    GVS_CUDA_OK(cudaMemcpyAsync(b + oW, world_pos, M * 32, cudaMemcpyHostToDevice, s));
+    GVS_CUDA_OK(cudaMemcpyAsync(b + oMs, max_scale_dist, M * 4, cudaMemcpyHostToDevice, s));
+    GVS_CUDA_OK(cudaMemcpyAsync(b + oLs, log_scale, M * 4, cudaMemcpyHostToDevice, s));
+    GVS_CUDA_OK(cudaMemcpyAsync(b + oNl, n_scale_lev, M * 4, cudaMemcpyHostToDevice, s));
+    GVS_CUDA_OK(cudaMemcpyAsync(b + oPr, pred, M * 8, cudaMemcpyHostToDevice, s));        // in-out: untouched when not in frame
+    GVS_CUDA_OK(cudaMemcpyAsync(b + oSl, scale_level, M * 4, cudaMemcpyHostToDevice, s));
+    int launches = 0;
+    launchWorldToFrame(count, reinterpret_cast<double*>(b + oPose), fx, fy, cx, cy, width, height, reinterpret_cast<double*>(b + oW),
+                       reinterpret_cast<float*>(b + oMs), reinterpret_cast<float*>(b + oLs), reinterpret_cast<int*>(b + oNl),
+                       reinterpret_cast<float*>(b + oPr), reinterpret_cast<int*>(b + oSl), b + oIf, s, &launches);
+    m->launchesTotal += launches;
+    GVS_CUDA_OK(cudaMemcpyAsync(pred, b + oPr, M * 8, cudaMemcpyDeviceToHost, s));
+    GVS_CUDA_OK(cudaMemcpyAsync(scale_level, b + oSl, M * 4, cudaMemcpyDeviceToHost, s));
+    GVS_CUDA_OK(cudaMemcpyAsync(in_frame, b + oIf, M, cudaMemcpyDeviceToHost, s));
+    GVS_CUDA_OK(cudaStreamSynchronize(s));
+    GVS_CUDA_OK(cudaGetLastError());
+    return GVS_OK;
+}
+
 int gvs_median_descriptor(gvs_matcher* m, const uint8_t* descs, const int32_t* offsets, int n_points, int32_t* best_idx) {
     if (!m || !offsets || !best_idx || n_points < 0) return fail(GVS_ERR_INVALID, "bad argument");
     if (n_points == 0) return GVS_OK;

@@ -1,5 +1,6 @@
-// K5+K7 describe: intensity-centroid orientation on the unblurred level, rotated BRIEF-256 on the blurred level,
-// and assembly of the final cv::KeyPoint records at their dense output position.  One warp per kept key.
+// K5+K6+K7 describe: intensity-centroid orientation on the unblurred level, rotated BRIEF-256 on the 7x7-blurred level
+// (the blur is evaluated inside the kernel, only where a key samples it), and assembly of the final cv::KeyPoint records at
+// their dense output position.  One warp per kept key.
 // Replaces FeatureExtractor::computeOrientation / computeAllOrientations (reference src/FeatureExtractor.cpp:315-340,
 // :471-479), computeOrbDescriptor / computeDescriptors (:268-313) and the scale-up + concatenation loop of
 // extractKeysNew (:518-530).
@@ -40,7 +41,7 @@ __device__ __forceinline__ float fastAtan2Deg(float y, float x) {
     return a;
 }
 
-// Fused form (default): the 7x7 sigma-2 blur (same Q8 taps and rounding as blur7_kernel) is evaluated
+// The 7x7 sigma-2 blur (same Q8 taps and rounding as blur7_kernel) is evaluated
 // only where a key needs it.  Per key the warp stages the 43 x 52-byte source patch (reach 18 + 3 taps, reflect-101 at
 // the image border) in shared memory, runs the horizontal pass for the 43 rows (two dp4a per pixel, u16 results in shared
 // memory) and evaluates the vertical pass at the 512 sample positions only.  The blurred slab is neither written nor read.
@@ -186,7 +187,9 @@ describe_fused_kernel(const __grid_constant__ Geometry g, const uint8_t* __restr
         // ---- rotated BRIEF on vertically blurred samples
         const float factorPI = (float)(3.14159265358979323846 / 180.0);
         const float ang = __fmul_rn(angle, factorPI);
-        const float a = (float)cos((double)ang), b = (float)sin((double)ang);
+        double sd, cd;
+        sincos((double)ang, &sd, &cd);  // one shared range reduction; same results as separate sin() / cos() (parity-tested)
+        const float a = (float)cd, b = (float)sd;
         const unsigned short* Hc = H + kPR * kHCols + (ox - 4);  // H[row of the key][column of the key]
         auto sample = [&](float px, float py) {
             const int iy = __float2int_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)));
@@ -248,104 +251,6 @@ void launchDescribeFused(const Geometry& g, const uint8_t* slab, int nImages, co
     int gx = (g.keptPerImage / 2 + 3 * warpsPerCta - 1) / (3 * warpsPerCta);
     if (gx < 1) gx = 1;
     describe_fused_kernel<<<dim3(gx, nImages), 32 * warpsPerCta, smem, s>>>(g, slab, kept, keptCnt, imgOff, kps, desc, auxKey, momentsDbg, totalCap);
-    ++*launches;
-}
-
-__global__ void __launch_bounds__(256)
-describe_kernel(const __grid_constant__ Geometry g, const uint8_t* __restrict__ slab, const uint8_t* __restrict__ blurSlab,
-                const KeptKey* __restrict__ kept, const int* __restrict__ keptCnt, const int* __restrict__ imgOff,
-                gvs_keypoint* __restrict__ kps, uint8_t* __restrict__ desc, int* __restrict__ momentsDbg, int totalCap) {
-    const int lane = threadIdx.x & 31;
-    const int img = blockIdx.y;
-    // this lane's 8 tests = 32 pattern bytes
-    unsigned pat[8];
-    {
-        const uint4* p = reinterpret_cast<const uint4*>(kPatternDev + lane * 32);
-        const uint4 a = p[0], b = p[1];
-        pat[0] = a.x; pat[1] = a.y; pat[2] = a.z; pat[3] = a.w; pat[4] = b.x; pat[5] = b.y; pat[6] = b.z; pat[7] = b.w;
-    }
-    __shared__ int cnt[kMaxLevels];
-    if (threadIdx.x < kMaxLevels) cnt[threadIdx.x] = threadIdx.x < g.nLevels ? keptCnt[img * kMaxLevels + threadIdx.x] : 0;
-    __syncthreads();
-    const int outBase = imgOff[img];
-    const int warpsPerGrid = gridDim.x * (blockDim.x >> 5);
-    for (int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); slot < g.keptPerImage; slot += warpsPerGrid) {
-        // staging slot -> (level, i)
-        int level = 0, pre = 0;
-        while (level + 1 < g.nLevels && slot >= g.lv[level + 1].keptOff) { pre += cnt[level]; level++; }
-        const LevelGeom& lv = g.lv[level];
-        const int i = slot - lv.keptOff;
-        if (i >= cnt[level]) continue;
-        const int o = outBase + pre + i;
-        if (o >= totalCap) continue;  // flagged by offsets_kernel
-        const unsigned q = kept[(size_t)img * g.keptPerImage + slot];
-        const int x = q & 0xfff, y = (q >> 12) & 0xfff, score = q >> 24;
-
-        // ---- orientation
-        const uint8_t* src = levelPtr(slab, g, img, level);
-        int m10 = 0, m01 = 0;
-        if (lane < 2 * kHalfPatch + 1) {
-            const int v = lane - kHalfPatch;
-            const int d = g.umax[v < 0 ? -v : v];
-            const uint8_t* row = src + (size_t)(y + v) * lv.pitch + x;
-            int s0 = 0, s1 = 0;
-            for (int u = -d; u <= d; u++) { const int val = row[u]; s0 += val; s1 += u * val; }
-            m10 = s1;
-            m01 = v * s0;
-        }
-#pragma unroll
-        for (int off = 16; off; off >>= 1) { m10 += __shfl_xor_sync(0xffffffffu, m10, off); m01 += __shfl_xor_sync(0xffffffffu, m01, off); }
-        const float angle = fastAtan2Deg((float)m01, (float)m10);
-
-        // ---- rotated BRIEF
-        const float factorPI = (float)(3.14159265358979323846 / 180.0);
-        const float ang = __fmul_rn(angle, factorPI);
-        const float a = (float)cos((double)ang), b = (float)sin((double)ang);
-        const uint8_t* bl = levelPtr(blurSlab, g, img, level) + (size_t)y * lv.pitch + x;
-        unsigned byte = 0;
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const unsigned w = pat[j];
-            const float x0 = (float)(int8_t)(w & 0xff), y0 = (float)(int8_t)((w >> 8) & 0xff);
-            const float x1 = (float)(int8_t)((w >> 16) & 0xff), y1 = (float)(int8_t)(w >> 24);
-            const int iy0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
-            const int ix0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
-            const int iy1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
-            const int ix1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
-            const int t0 = bl[iy0 * lv.pitch + ix0], t1 = bl[iy1 * lv.pitch + ix1];
-            byte |= (unsigned)(t0 < t1) << j;
-        }
-        desc[(size_t)o * 32 + lane] = (uint8_t)byte;
-
-        // ---- keypoint record (7 x 4 bytes), lanes 0..6
-        if (lane < 7) {
-            float fx = (float)x, fy = (float)y;
-            if (level != 0) { fx = __fmul_rn(fx, lv.scale); fy = __fmul_rn(fy, lv.scale); }
-            unsigned wv;
-            switch (lane) {
-                case 0: wv = __float_as_uint(fx); break;
-                case 1: wv = __float_as_uint(fy); break;
-                case 2: wv = __float_as_uint((float)lv.scaledPatch); break;
-                case 3: wv = __float_as_uint(angle); break;
-                case 4: wv = __float_as_uint((float)score); break;
-                case 5: wv = (unsigned)level; break;
-                default: wv = 0xffffffffu; break;
-            }
-            reinterpret_cast<unsigned*>(kps + o)[lane] = wv;
-        }
-        if (momentsDbg && lane == 0) { momentsDbg[2 * o] = m10; momentsDbg[2 * o + 1] = m01; }
-    }
-}
-
-void launchDescribe(const Geometry& g, const uint8_t* slab, const uint8_t* blurSlab, int nImages, const KeptKey* kept,
-                    const int* keptCnt, const int* imgOff, gvs_keypoint* kps, uint8_t* desc, int* momentsDbg,
-                    int totalCap, cudaStream_t s, int* launches) {
-    const int warpsPerCta = 8;
-    // about half of the staging slots are occupied; 2 slots per warp keeps the pattern registers amortised
-    int gx = (g.keptPerImage + 2 * warpsPerCta - 1) / (2 * warpsPerCta);
-    if (gx < 1) gx = 1;
-    describe_kernel<<<dim3(gx, nImages), 32 * warpsPerCta, 0, s>>>(g, slab, blurSlab, kept, keptCnt, imgOff, kps, desc,
-                                                                  momentsDbg, totalCap);
     ++*launches;
 }
 

@@ -369,6 +369,40 @@ void launchMedianDescriptor(const uint8_t* descs, const int* offsets, int P, int
     ++*launches;
 }
 
+// FeatureTracker::worldToFrame + MapPoint::predictScale (src/FeatureTracker.cpp:685-741, src/Map.cpp:13-23), thread per map
+// point.  Double precision, explicit round-to-nearest operations in the reference's left-to-right order (no FMA).
+__global__ void world_to_frame_kernel(int M, const double* __restrict__ poseInv, double fx, double fy, double cx, double cy, int width,
+                                      int height, const double* __restrict__ wPos, const float* __restrict__ maxScaleDist,
+                                      const float* __restrict__ logScale, const int* __restrict__ nScaleLev, float* __restrict__ pred,
+                                      int* __restrict__ scaleLevel, uint8_t* __restrict__ inFrame) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    const double w0 = wPos[4 * i], w1 = wPos[4 * i + 1], w2 = wPos[4 * i + 2], w3 = wPos[4 * i + 3];
+    double pt[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+        pt[r] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(poseInv[4 * r], w0), __dmul_rn(poseInv[4 * r + 1], w1)), __dmul_rn(poseInv[4 * r + 2], w2)),
+                          __dmul_rn(poseInv[4 * r + 3], w3));
+    if (pt[2] <= 0.0) { inFrame[i] = 0; return; }
+    const double invZ = __ddiv_rn(1.0, pt[2]);
+    const double u = __dadd_rn(__dmul_rn(__dmul_rn(fx, pt[0]), invZ), cx), v = __dadd_rn(__dmul_rn(__dmul_rn(fy, pt[1]), invZ), cy);
+    if (u < 0 || v < 0 || u >= width || v >= height) { inFrame[i] = 0; return; }
+    const float dist = (float)__dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(pt[0], pt[0]), __dmul_rn(pt[1], pt[1])), __dmul_rn(pt[2], pt[2])));
+    const float dif = __fdiv_rn(maxScaleDist[i], dist);
+    int scale = (int)ceil(__ddiv_rn(log((double)dif), (double)logScale[i]));
+    if (scale < 0) scale = 0; else if (scale >= nScaleLev[i]) scale = nScaleLev[i] - 1;
+    scaleLevel[i] = scale; inFrame[i] = 1; pred[2 * i] = (float)u; pred[2 * i + 1] = (float)v;
+}
+
+void launchWorldToFrame(int M, const double* poseInv, double fx, double fy, double cx, double cy, int width, int height,
+                        const double* wPos, const float* maxScaleDist, const float* logScale, const int* nScaleLev, float* pred,
+                        int* scaleLevel, uint8_t* inFrame, cudaStream_t s, int* launches) {
+    if (M <= 0) return;
+    world_to_frame_kernel<<<(M + 127) / 128, 128, 0, s>>>(M, poseInv, fx, fy, cx, cy, width, height, wPos, maxScaleDist, logScale,
+                                                          nScaleLev, pred, scaleLevel, inFrame);
+    ++*launches;
+}
+
 __global__ void hamming_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, int n, int* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;

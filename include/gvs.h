@@ -224,6 +224,15 @@ typedef struct gvs_lba_points {
 int gvs_match_projection_lba(gvs_matcher* fm, const gvs_lba_frame* new_kf, const gvs_lba_points* pts, float rad,
                              int32_t* out_pairs, int* n_matches);
 
+/* FeatureTracker::worldToFrame (src/FeatureTracker.cpp:685-741) with MapPoint::predictScale (src/Map.cpp:13-23) for `count`
+ * map points and one camera (it produces predL/predR, scaleLevelL/R, inFrame/inFrameR, the inputs of
+ * gvs_match_projection).  pose_inv: predPoseInv, 16 doubles row-major; world_pos: count x 4 doubles (MapPoint::wp);
+ * max_scale_dist: MapPoint::maxScaleDist; log_scale / n_scale_lev: lastObsKF->logScale / nScaleLev per point.
+ * pred (count x 2) and scale_level are in-out: a point that is not in the frame only gets in_frame = 0 (:697-718). */
+int gvs_project_mappoints(gvs_matcher* fm, const double* pose_inv, double fx, double fy, double cx, double cy, int width, int height,
+                          int count, const double* world_pos, const float* max_scale_dist, const float* log_scale,
+                          const int32_t* n_scale_lev, float* pred, int32_t* scale_level, uint8_t* in_frame);
+
 /* MapPoint::calcDescriptor, src/Map.cpp:145-210, for n_points map points at once: descs = the observation descriptors
  * of all points back to back (32 bytes each), offsets[n_points + 1]; best_idx[p] = index inside point p's own list of
  * the descriptor with the least median Hamming distance to the others (-1 for an empty list). */

@@ -188,6 +188,18 @@ def prepare_image(image: np.ndarray, mapx=None, mapy=None) -> np.ndarray:
     return out
 
 
+def world_to_frame(poseInv, fx, fy, cx, cy, width, height, wPos, maxScaleDist, logScale, nScaleLev, pred, scaleLevel):
+    """worldToFrame + predictScale (reference src/FeatureTracker.cpp:685-741, src/Map.cpp:13-23); pred/scaleLevel in-out."""
+    c = lambda a, dt: np.ascontiguousarray(a, dt)
+    M = len(wPos)
+    inF = np.zeros(M, np.uint8)
+    assert pred.dtype == np.float32 and scaleLevel.dtype == np.int32
+    lib().ora_world_to_frame(_p(c(poseInv, np.float64)), C.c_double(fx), C.c_double(fy), C.c_double(cx), C.c_double(cy), width, height, M,
+                             _p(c(wPos, np.float64)), _p(c(maxScaleDist, np.float32)), _p(c(logScale, np.float32)),
+                             _p(c(nScaleLev, np.int32)), _p(pred), _p(scaleLevel), _p(inF))
+    return inF
+
+
 def stereo_frames(params, fx, baseline, L: np.ndarray, R: np.ndarray, shape: int, threads: int):
     """CPU baseline: run F stereo frames; returns (total matches, per-frame left key counts)."""
     L = np.ascontiguousarray(L, np.uint8); R = np.ascontiguousarray(R, np.uint8)

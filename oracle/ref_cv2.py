@@ -701,6 +701,36 @@ def prepareImage(image: np.ndarray, mapx: np.ndarray | None = None, mapy: np.nda
     return image
 
 
+def worldToFrame(wPos: np.ndarray, predPoseInv: np.ndarray, fx, fy, cx, cy, width, height, maxScaleDist, logScale, nScaleLev,
+                 pred: np.ndarray, scaleLevel: np.ndarray, inFrame: np.ndarray) -> np.ndarray:
+    """FeatureTracker::worldToFrame (src/FeatureTracker.cpp:685-741) + MapPoint::predictScale (src/Map.cpp:13-23) for a batch of
+    map points and one camera.  pred / scaleLevel are in-out (untouched when the point is not in the frame); returns the bools."""
+    M = len(wPos)
+    ok = np.zeros(M, bool)
+    for i in range(M):
+        w = [float(v) for v in wPos[i]]
+        pt = [((float(predPoseInv[r, 0]) * w[0] + float(predPoseInv[r, 1]) * w[1]) + float(predPoseInv[r, 2]) * w[2]) + float(predPoseInv[r, 3]) * w[3]
+              for r in range(4)]
+        if pt[2] <= 0.0:
+            inFrame[i] = 0
+            continue
+        invZ = 1.0 / pt[2]
+        u = fx * pt[0] * invZ + cx
+        v = fy * pt[1] * invZ + cy
+        if u < 0 or v < 0 or u >= width or v >= height:
+            inFrame[i] = 0
+            continue
+        dist = _F32(math.sqrt(pt[0] * pt[0] + pt[1] * pt[1] + pt[2] * pt[2]))
+        dif = _F32(_F32(maxScaleDist[i]) / dist)
+        scale = int(math.ceil(math.log(float(dif)) / float(_F32(logScale[i]))))
+        scale = 0 if scale < 0 else min(scale, int(nScaleLev[i]) - 1)
+        scaleLevel[i] = scale
+        inFrame[i] = 1
+        pred[i] = (_F32(u), _F32(v))
+        ok[i] = True
+    return ok
+
+
 def calcDescriptor(descs: np.ndarray) -> int:
     """MapPoint::calcDescriptor (src/Map.cpp:145-210): index of the descriptor with the least median distance to the rest."""
     N = len(descs)

@@ -413,3 +413,19 @@ def test_strided_host_images_and_resident_input():
     off3 = fe.offsets(3)
     got = fe.download(0, 3, int(off3[3]))
     assert np.array_equal(off, off3) and got[0].tobytes() == ref[0].tobytes() and np.array_equal(got[1], ref[1])
+
+
+def test_world_to_frame_projection():
+    """SURVEY 8(f) rank 3: batched FeatureTracker::worldToFrame + MapPoint::predictScale (double precision) against the oracle."""
+    from test_oracle_vs_cv2 import _projection_case
+    Pinv, wPos, msd, ls, nl = _projection_case(seed=3, M=20000)
+    M = len(wPos)
+    cam = (435.2047, 435.2047, 367.4517, 252.2008, 752, 480)
+    cfg = synth.CONFIGS["small"]
+    feL, feR, fm = _handles(cfg, 1)
+    pa = np.full((M, 2), -7, np.float32); sa = np.full(M, -7, np.int32)
+    fa = fm.worldToFrame(Pinv, *cam, wPos, msd, ls, nl, pa, sa)
+    pb = np.full((M, 2), -7, np.float32); sb = np.full(M, -7, np.int32)
+    fb = cpu_ref.world_to_frame(Pinv, *cam, wPos, msd, ls, nl, pb, sb)
+    assert np.array_equal(fa, fb) and np.array_equal(sa, sb)
+    assert np.max(np.abs(pa - pb), initial=0) <= 1e-3 and np.array_equal(pa, pb)   # tolerance of the north star, and bit exact

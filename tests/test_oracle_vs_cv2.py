@@ -2,6 +2,7 @@
 committed golden fixtures made by oracle/ref_cv2.py.  This is what pins the oracle (the reference has no tests)."""
 import ctypes as C
 import hashlib
+import math
 import os
 
 import cv2
@@ -206,3 +207,28 @@ def test_image_preparation_matches_cv2():
         assert np.array_equal(cpu_ref.prepare_image(img), cv2.cvtColor(img, cv2.COLOR_BGR2GRAY))
         g = np.ascontiguousarray(img[..., 1])
         assert np.array_equal(cpu_ref.prepare_image(g, mx, my), cv2.remap(g, mx, my, cv2.INTER_LINEAR))
+
+
+def _projection_case(seed=0, M=3000):
+    rng = np.random.default_rng(seed)
+    ang = 0.1
+    Rm = np.array([[math.cos(ang), 0, math.sin(ang)], [0, 1, 0], [-math.sin(ang), 0, math.cos(ang)]])
+    T = np.eye(4); T[:3, :3] = Rm; T[:3, 3] = [0.3, -0.1, 0.5]
+    wPos = np.concatenate([rng.uniform(-8, 8, (M, 2)), rng.uniform(-2, 30, (M, 1)), np.ones((M, 1))], axis=1)
+    maxScaleDist = rng.uniform(5, 60, M).astype(np.float32)
+    logScale = np.full(M, np.float32(math.log(np.float32(1.2))), np.float32)
+    nScaleLev = np.full(M, 8, np.int32)
+    return np.linalg.inv(T), wPos, maxScaleDist, logScale, nScaleLev
+
+
+def test_world_to_frame_cpp_matches_python_restatement():
+    """SURVEY 8(f) rank 3: FeatureTracker::worldToFrame + MapPoint::predictScale, C++ oracle vs the Python restatement."""
+    Pinv, wPos, msd, ls, nl = _projection_case()
+    M = len(wPos)
+    cam = (435.2047, 435.2047, 367.4517, 252.2008, 752, 480)
+    pa = np.full((M, 2), -7, np.float32); sa = np.full(M, -7, np.int32); fa = np.zeros(M, np.uint8)
+    ref_cv2.worldToFrame(wPos, Pinv, *cam, msd, ls, nl, pa, sa, fa)
+    pb = np.full((M, 2), -7, np.float32); sb = np.full(M, -7, np.int32)
+    fb = cpu_ref.world_to_frame(Pinv, *cam, wPos, msd, ls, nl, pb, sb)
+    assert np.array_equal(fa, fb) and np.array_equal(pa, pb) and np.array_equal(sa, sb)
+    assert 0.1 < fa.mean() < 0.9 and len(np.unique(sa[fa > 0])) >= 5
