@@ -54,7 +54,9 @@ __device__ __forceinline__ int reflect101i(int p, int n) {
     return p;
 }
 
-constexpr int kDescWarpBytes = 2 * kPBytes + ((kPRows * kHCols * 2 + 15) & ~15);  // two patch buffers + H = 8272
+constexpr int kHtRows = 44;  // H is stored column-major (column = image x, 44 u16 per column incl. 1 pad) so that the 7 vertical
+                             // taps of a sample are contiguous: 4 word loads instead of 7 scattered u16 loads
+constexpr int kDescWarpBytes = 2 * kPBytes + ((kHCols * kHtRows * 2 + 15) & ~15);  // two patch buffers + H^T = 8352
 
 __device__ __forceinline__ void cpAsync4(void* smemDst, const void* gsrc) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smemDst);
@@ -167,20 +169,19 @@ describe_fused_kernel(const __grid_constant__ Geometry g, const uint8_t* __restr
         for (int off = 16; off; off >>= 1) { m10 += __shfl_xor_sync(0xffffffffu, m10, off); m01 += __shfl_xor_sync(0xffffffffu, m01, off); }
         const float angle = fastAtan2Deg((float)m01, (float)m10);
 
-        // ---- horizontal blur pass on the patch: unit = (row, word m in 1..11) -> 4 u16 results
+        // ---- horizontal blur pass on the patch: unit = (word m in 1..11, row), consecutive lanes = consecutive rows
+        // (conflict-free: patch rows are 13 words apart, H^T columns hold consecutive rows) -> 4 u16 results
         const unsigned tLo = 0x38302212u, tHi = 0x00122230u;  // {18,34,48,56}, {48,34,18,0}
         for (int t = lane; t < kPRows * 11; t += 32) {
-            const int r = t / 11, m = 1 + (t - r * 11);
+            const int m = 1 + t / kPRows, r = t - (m - 1) * kPRows;
             const unsigned* w = P + r * kPWords + m;
             const unsigned w0 = w[-1], w1 = w[0], w2 = w[1];
-            unsigned h[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const unsigned a = j == 3 ? w1 : __funnelshift_r(w0, w1, 8 * (1 + j));
                 const unsigned b = j == 3 ? w2 : __funnelshift_r(w1, w2, 8 * (1 + j));
-                h[j] = __dp4a(a, tLo, __dp4a(b, tHi, 0u));
+                H[(4 * (m - 1) + j) * kHtRows + r] = (unsigned short)__dp4a(a, tLo, __dp4a(b, tHi, 0u));
             }
-            *reinterpret_cast<uint2*>(H + r * kHCols + 4 * (m - 1)) = make_uint2(h[0] | (h[1] << 16), h[2] | (h[3] << 16));
         }
         __syncwarp();
 
@@ -190,13 +191,19 @@ describe_fused_kernel(const __grid_constant__ Geometry g, const uint8_t* __restr
         double sd, cd;
         sincos((double)ang, &sd, &cd);  // one shared range reduction; same results as separate sin() / cos() (parity-tested)
         const float a = (float)cd, b = (float)sd;
-        const unsigned short* Hc = H + kPR * kHCols + (ox - 4);  // H[row of the key][column of the key]
+        // H^T as words: column c starts at word c * 22; the taps of a sample at (ix, iy) are rows 18 + iy .. 24 + iy of column ox - 4 + ix
+        const unsigned* Hw = reinterpret_cast<const unsigned*>(H);
         auto sample = [&](float px, float py) {
             const int iy = __float2int_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)));
             const int ix = __float2int_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)));
-            const unsigned short* c = Hc + iy * kHCols + ix;
-            const unsigned acc = 32768u + 18u * (c[-3 * kHCols] + c[3 * kHCols]) + 34u * (c[-2 * kHCols] + c[2 * kHCols]) +
-                                 48u * (c[-kHCols] + c[kHCols]) + 56u * c[0];
+            const int r0 = kPR - 3 + iy;
+            const unsigned* c = Hw + (ox - 4 + ix) * (kHtRows / 2) + (r0 >> 1);
+            const unsigned sh = (r0 & 1) * 16;
+            const unsigned w0 = c[0], w1 = c[1], w2 = c[2], w3 = c[3];
+            const unsigned x0 = __funnelshift_r(w0, w1, sh), x1 = __funnelshift_r(w1, w2, sh), x2 = __funnelshift_r(w2, w3, sh),
+                           x3 = (w3 >> sh) & 0xffffu;
+            // taps {18,34 | 48,56 | 48,34 | 18} on (v0,v1 | v2,v3 | v4,v5 | v6): exact u32 sums, order is irrelevant
+            const unsigned acc = __dp2a_lo(x0, 0x2212u, __dp2a_lo(x1, 0x3830u, __dp2a_lo(x2, 0x2230u, 32768u + 18u * x3)));
             return (int)(acc >> 16);
         };
         unsigned byte = 0;
