@@ -14,8 +14,10 @@ data path; the only collective is the timing reduction).  Prints ONE JSON line o
             arrays back on the host inside the timed region
   roofline  the dominant kernel stage against the measured HBM peak (MEASURED_PEAKS.json), algorithmic bytes
             per SURVEY.md section 8(d)
-  cpu_baseline / --impl reference: the CPU restatement of the reference path (oracle/cpu_ref.cpp) on the
-            host cores of the same box, on a bounded sample of the same workload
+  cpu_baseline / --impl reference: the reference's own FeatureExtractor.cpp / FeatureMatcher.cpp (oracle/_ref, compiled
+            unmodified in the build container against a stand-in OpenCV; kind "reference"), or, when that library is
+            absent, the C++ restatement oracle/cpu_ref.cpp (kind "port"), on the host cores of the same box, on a
+            bounded sample of the same workload
 """
 from __future__ import annotations
 
@@ -113,20 +115,31 @@ def make_frames(cfg, n, seed0):
     return synth.stereo_batch(cfg["width"], cfg["height"], cfg["disparity"], range(seed0, seed0 + n))
 
 
+def cpu_arm():
+    """(module, kind, description) of the CPU implementation timed as the baseline (oracle/: checker + baseline only)."""
+    from oracle import cpu_ref, ref_build
+    if os.path.exists(ref_build._SO):
+        return ref_build, "reference", ("oracle/_ref/libref_frontend.so = the reference's own src/FeatureExtractor.cpp + "
+                                        "src/FeatureMatcher.cpp compiled unmodified (-O3) against a stand-in OpenCV whose resize / FAST / "
+                                        "GaussianBlur / sortIdx / fastAtan2 are scalar restatements (no SIMD OpenCV in this image)")
+    return cpu_ref, "port", "oracle/cpu_ref.cpp (scalar C++ restatement; oracle/_ref was not built)"
+
+
 def cpu_reference_rate(cfg, L, R, threads, shape=1):
-    """frames/s of the CPU restatement of the reference path on this box (oracle: checker + baseline only)."""
-    from oracle import cpu_ref
+    """frames/s of the reference's CPU path on this box."""
+    mod, _, _ = cpu_arm()
     params = (cfg["n_features"], cfg["n_levels"], 1.2, 19, 31, 20, 7)
     t = time.perf_counter()
-    tot, _ = cpu_ref.stereo_frames(params, cfg["fx"], cfg["baseline"], L, R, shape, threads)
+    tot, _ = mod.stereo_frames(params, cfg["fx"], cfg["baseline"], L, R, shape, threads)
     dt = time.perf_counter() - t
     return len(L) / dt, dt, tot
 
 
 def run_reference(args, cfg, rank, world):
-    """--impl reference: the reference's own CPU algorithm (C++ restatement) on all host cores; rank 0 only."""
+    """--impl reference: the reference's own CPU implementation of the path on all host cores; rank 0 only."""
     if rank != 0:
         return
+    _, kind, what = cpu_arm()
     cores = os.cpu_count() or 1
     sample = max(cores, min(4 * cores, 64))
     L, R = make_frames(cfg, sample, 0)
@@ -143,9 +156,8 @@ def run_reference(args, cfg, rank, world):
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
         "config": {"workload": workload_name(args, cfg), "frames_per_step": sample, "host_threads": cores},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample} frames per step, frame-parallel over {cores} host threads, oracle/cpu_ref.cpp "
-                                   "(scalar C++ restatement; the reference itself needs C++ OpenCV/GTSAM and does not build here)"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{sample} frames per step, frame-parallel over {cores} host threads; {what}"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
@@ -359,9 +371,10 @@ def main():
         v_all, dt_all, _ = cpu_reference_rate(cfg, L[:sample], R[:sample], cores, shape=1)
         s2 = min(sample, 6)
         v_ref, dt_ref, _ = cpu_reference_rate(cfg, L[:s2], R[:s2], 2, shape=0)
-        out["cpu_baseline"] = {"value": v_all, "unit": UNIT, "cores": cores, "kind": "port",
+        _, kind, what = cpu_arm()
+        out["cpu_baseline"] = {"value": v_all, "unit": UNIT, "cores": cores, "kind": kind,
                                "sample": f"first {sample} frames of the same batch, frame-parallel over {cores} host threads "
-                                         f"({dt_all:.1f} s), oracle/cpu_ref.cpp",
+                                         f"({dt_all:.1f} s); {what}",
                                "reference_shaped_2_threads": {"value": v_ref, "sample": f"{s2} frames, 2 extraction threads + serial matcher"}}
     print(json.dumps(out), flush=True)
     if world > 1:

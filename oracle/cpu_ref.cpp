@@ -4,11 +4,13 @@
 // Nothing under gtsam_vslam_b200/ links, loads or calls this file.  Only tests/, __graft_entry__.smoke()
 // and bench.py's cpu_baseline / --impl reference legs do.
 //
-// Parity status: the reference holds no tests or golden vectors and does not compile
-// here (C++ OpenCV / Eigen / GTSAM are absent), so parity is "unpinned by the reference's own tests".
-// This file is pinned instead against (a) oracle/ref_cv2.py, which runs the same control flow on the
-// real OpenCV primitives through cv2 4.13.0, primitive by primitive and end to end
-// (tests/test_oracle_vs_cv2.py), and (b) the committed fixtures tests/golden/*.npz generated by it.
+// Parity status: PINNED against outputs of the reference itself run here.  The reference's own
+// FeatureExtractor.cpp / FeatureMatcher.cpp are compiled unmodified into oracle/_ref (oracle/Makefile target
+// `ref`, against the stand-ins of oracle/shim) and, with the real OpenCV 4.13.0 primitives hooked in through
+// cv2, reproduce this file bit for bit (tests/test_reference_build.py).  It is also pinned against
+// (a) oracle/ref_cv2.py, which runs the same control flow on the real OpenCV primitives, primitive by
+// primitive and end to end (tests/test_oracle_vs_cv2.py), and (b) the committed fixtures tests/golden/*.npz.
+// The reference holds no tests or golden vectors of its own.
 //
 // Third-party dependency restated here: OpenCV (requested as 4.2.0 else 3.2, reference
 // CMakeLists.txt:27-33, un-vendored).  Restated primitives: cv::resize INTER_LINEAR u8, cv::FAST 9/16

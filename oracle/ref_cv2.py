@@ -4,9 +4,10 @@ real OpenCV primitives (Python cv2), function by function.
 Nothing under gtsam_vslam_b200/ may import this file; only tests/, __graft_entry__.smoke() and the
 cpu_baseline / --impl reference legs of bench.py do.
 
-Parity status: the reference (/root/reference) has no tests, golden vectors or fixtures of its own
- and cannot be compiled in this image (no C++ OpenCV/Eigen/GTSAM), so parity
-is "unpinned by the reference's own tests".  What pins it instead is this file: every arithmetic
+Parity status: PINNED.  The reference (/root/reference) has no tests, golden vectors or fixtures of its own
+(SURVEY.md section 4), but its two source files on the path compile here against stand-in headers
+(oracle/_ref, see oracle/ref_build.py) and reproduce this file's fixtures bit for bit when their OpenCV
+primitives are hooked to cv2 (tests/test_reference_build.py).  In this file every arithmetic
 primitive on the path (cv::resize, cv::FAST, cv::sortIdx, cv::fastAtan2, cv::GaussianBlur, cv::norm)
 is executed by the same OpenCV code the reference links (cv2 4.13.0 here; the reference asks for
 >= 4.2), and the control flow around them follows the cited reference lines.  oracle/cpu_ref.cpp

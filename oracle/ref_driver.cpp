@@ -1,0 +1,319 @@
+// oracle/ref_driver.cpp — TEST INFRASTRUCTURE ONLY.
+//
+// C entry points around the reference's OWN FeatureExtractor and FeatureMatcher (compiled unmodified from
+// /root/reference/src/FeatureExtractor.cpp and src/FeatureMatcher.cpp against oracle/shim, see oracle/Makefile target
+// `ref`), so that python tests can run them next to the restatement (oracle/cpu_ref.cpp) and generate golden vectors.
+// Only objects and members the reference declares public are touched.  The reference's Map.cpp / KeyFrame.cpp /
+// Camera.cpp are not on the path and not compiled; the few constructors of their classes that this driver needs in order
+// to hand objects to the matcher are defined at the bottom of this file as plain member initialisations.
+#include <atomic>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "FeatureMatcher.h"   // reference header: pulls Settings.h, Camera.h, Map.h, KeyFrame.h, FeatureExtractor.h
+#include "ref_hooks.h"
+
+// default primitives: the cv2-pinned restatements exported by liboracle.so (oracle/cpu_ref.cpp)
+extern "C" {
+void ora_resize_linear(const uint8_t* src, int sw, int sh, uint8_t* dst, int dw, int dh);
+void ora_gaussian_blur7(const uint8_t* src, int w, int h, uint8_t* dst);
+float ora_fast_atan2(float y, float x);
+void ora_sort_idx_desc(const float* key, int n, int* idx);
+int ora_fast_detect(const uint8_t* img, int w, int h, int threshold, int* xs, int* ys, int* scores, int cap);
+int ora_assign_grid(const void* kps, int n, int width, int height, int* start, int* items, float* xMult, float* yMult);
+}
+
+namespace {
+const gvs_ref_hooks kDefaults = {ora_resize_linear, ora_fast_detect, ora_gaussian_blur7, ora_sort_idx_desc, ora_fast_atan2};
+gvs_ref_hooks gHooks = kDefaults;
+using namespace GTSAM_VIOSLAM;
+typedef std::shared_ptr<FeatureExtractor> ExtractorPtr;
+inline FeatureExtractor* FE(void* h) { return ((ExtractorPtr*)h)->get(); }
+
+struct Matcher {
+    std::shared_ptr<StereoCamera> zed;
+    std::shared_ptr<FeatureMatcher> fm;
+};
+
+std::vector<cv::KeyPoint> keyVector(const void* kps, int n) {
+    const cv::KeyPoint* k = (const cv::KeyPoint*)kps;
+    return std::vector<cv::KeyPoint>(k, k + n);
+}
+cv::Mat descMat(const uint8_t* d, int n) {
+    cv::Mat m(n, 32, CV_8U);
+    if (n) std::memcpy(m.data, d, (size_t)n * 32);
+    return m;
+}
+// CSR (start[yGrids*xGrids+1], items) -> TrackedKeys grid (FeatureTracker::assignKeysToGrids' output layout)
+std::vector<std::vector<std::vector<int>>> gridFromCsr(const int* start, const int* items, int yGrids, int xGrids) {
+    std::vector<std::vector<std::vector<int>>> g(yGrids, std::vector<std::vector<int>>(xGrids));
+    for (int r = 0; r < yGrids; ++r)
+        for (int c = 0; c < xGrids; ++c) g[r][c].assign(items + start[r * xGrids + c], items + start[r * xGrids + c + 1]);
+    return g;
+}
+// TrackedKeys of one frame from flat arrays (+ CSR grids)
+void fillKeys(TrackedKeys& k, const void* kpL, const uint8_t* descL, int NL, const void* kpR, const uint8_t* descR, int NR,
+              const int* leftIdxs, const int* rightIdxs, const int* gridLStart, const int* gridLItems, const int* gridRStart,
+              const int* gridRItems, int yGrids, int xGrids, float xMult, float yMult) {
+    k.keyPoints = keyVector(kpL, NL); k.Desc = descMat(descL, NL);
+    if (kpR) { k.rightKeyPoints = keyVector(kpR, NR); k.rightDesc = descMat(descR, NR); }
+    if (leftIdxs) k.leftIdxs.assign(leftIdxs, leftIdxs + NR);
+    if (rightIdxs) k.rightIdxs.assign(rightIdxs, rightIdxs + NL);
+    k.xGrids = xGrids; k.yGrids = yGrids; k.xMult = xMult; k.yMult = yMult;
+    k.lkeyGrid = gridFromCsr(gridLStart, gridLItems, yGrids, xGrids);
+    if (gridRStart) k.rkeyGrid = gridFromCsr(gridRStart, gridRItems, yGrids, xGrids);
+}
+}  // namespace
+
+extern "C" {
+
+const gvs_ref_hooks* gvs_ref_get_hooks(void) { return &gHooks; }
+
+void gvs_ref_set_hooks(const gvs_ref_hooks* h) {
+    gHooks = kDefaults;
+    if (!h) return;
+    if (h->resize_linear) gHooks.resize_linear = h->resize_linear;
+    if (h->fast_nms) gHooks.fast_nms = h->fast_nms;
+    if (h->gaussian_blur7) gHooks.gaussian_blur7 = h->gaussian_blur7;
+    if (h->sort_idx_desc) gHooks.sort_idx_desc = h->sort_idx_desc;
+    if (h->fast_atan2) gHooks.fast_atan2 = h->fast_atan2;
+}
+
+void* ref_extractor_create(int nFeatures, int nLevels, float imScale, int edgeThreshold, int patchSize, int maxFast,
+                           int minFast) {
+    return new ExtractorPtr(std::make_shared<FeatureExtractor>(nFeatures, nLevels, imScale, edgeThreshold, patchSize, maxFast, minFast));
+}
+void ref_extractor_destroy(void* h) { delete (ExtractorPtr*)h; }
+
+// public tables (include/FeatureExtractor.h:71-77)
+void ref_extractor_tables(void* h, float* scale, float* invScale, float* sigma, float* invSigma, int* patchSz, int* quota) {
+    FeatureExtractor* fe = FE(h);
+    for (size_t i = 0; i < fe->nLevels; ++i) {
+        scale[i] = fe->scalePyramid[i]; invScale[i] = fe->scaleInvPyramid[i]; sigma[i] = fe->sigmaFactor[i];
+        invSigma[i] = fe->InvSigmaFactor[i]; patchSz[i] = fe->scaledPatchSize[i]; quota[i] = fe->featurePerLevel[i];
+    }
+}
+
+// FeatureExtractor::extractKeysNew; kps = cv::KeyPoint[cap] (28 bytes each), desc = cap x 32 bytes.  Returns n or -1.
+int ref_extract(void* h, const uint8_t* img, int w, int hgt, void* kps, uint8_t* desc, int cap) {
+    FeatureExtractor* fe = FE(h);
+    cv::Mat image(hgt, w, CV_8UC1, (void*)img);
+    std::vector<cv::KeyPoint> keys;
+    cv::Mat d;
+    fe->extractKeysNew(image, keys, d);
+    if ((int)keys.size() > cap) return -1;
+    if (!keys.empty()) std::memcpy(kps, keys.data(), keys.size() * sizeof(cv::KeyPoint));
+    for (size_t i = 0; i < keys.size(); ++i) std::memcpy(desc + i * 32, d.ptr((int)i), 32);
+    return (int)keys.size();
+}
+
+// pyramid level of the last extract (FeatureExtractor::imagePyramid, public)
+void ref_level_size(void* h, int level, int* w, int* hgt) {
+    FeatureExtractor* fe = FE(h);
+    *w = fe->imagePyramid[level].cols; *hgt = fe->imagePyramid[level].rows;
+}
+void ref_level_image(void* h, int level, uint8_t* out) {
+    const cv::Mat& m = FE(h)->imagePyramid[level];
+    for (int y = 0; y < m.rows; ++y) std::memcpy(out + (size_t)y * m.cols, m.ptr(y), (size_t)m.cols);
+}
+
+// FeatureExtractor::ssc on explicit points (public member): returns the kept count, out = indices into the input
+int ref_ssc(void* h, int numRetPoints, int cols, int rows, int n, const int* x, const int* y, const float* resp, int* out) {
+    FeatureExtractor* fe = FE(h);
+    std::vector<cv::KeyPoint> in(n);
+    for (int i = 0; i < n; ++i) { in[i] = cv::KeyPoint((float)x[i], (float)y[i], 7.f, -1.f, resp[i]); in[i].class_id = i; }
+    std::vector<cv::KeyPoint> kept = fe->ssc(in, numRetPoints, 0.1f, cols, rows);
+    for (size_t i = 0; i < kept.size(); ++i) out[i] = kept[i].class_id;
+    return (int)kept.size();
+}
+
+// ---- FeatureMatcher (reference include/FeatureMatcher.h:21-60) ------------------------------------------------------
+
+void* ref_matcher_create(void* feL, void* feR, double fx, float baseline, int imageHeight) {
+    Matcher* m = new Matcher;
+    m->zed = std::make_shared<StereoCamera>();
+    m->zed->mBaseline = baseline;
+    m->zed->mCameraLeft = std::make_shared<Camera>(nullptr, std::string());
+    m->zed->mCameraLeft->fx = fx;
+    m->fm = std::make_shared<FeatureMatcher>(m->zed, *(ExtractorPtr*)feL, *(ExtractorPtr*)feR, imageHeight);
+    return m;
+}
+void ref_matcher_destroy(void* h) { delete (Matcher*)h; }
+
+// FeatureMatcher::findStereoMatchesORB2R on the pyramids of the last extractKeysNew of the two extractors
+void ref_stereo_match(void* h, const void* kl, const uint8_t* dl, int NL, const void* kr, const uint8_t* dr, int NR,
+                      int* rightIdxs, int* leftIdxs, float* depth, uint8_t* close) {
+    Matcher* m = (Matcher*)h;
+    TrackedKeys keys;
+    keys.keyPoints = keyVector(kl, NL); keys.Desc = descMat(dl, NL);
+    std::vector<cv::KeyPoint> rightKeys = keyVector(kr, NR);
+    cv::Mat rightDesc = descMat(dr, NR), none;
+    m->fm->findStereoMatchesORB2R(none, none, rightDesc, rightKeys, keys);
+    for (int i = 0; i < NL; ++i) { rightIdxs[i] = keys.rightIdxs[i]; depth[i] = keys.estimatedDepth[i]; close[i] = keys.close[i]; }
+    for (int i = 0; i < NR; ++i) leftIdxs[i] = keys.leftIdxs[i];
+}
+
+// mode 0/1/2 = matchByProjectionRPred / matchByProjectionMono / matchByRadius; same flattened arguments as
+// ora_match_projection (oracle/cpu_ref.cpp) except that the key grids are passed in (FeatureTracker.cpp is not compiled).
+int ref_match_projection(void* h, int mode, int M, const uint8_t* mpDesc, const float* predL, const float* predR,
+                         const int* lvlL, const int* lvlR, const uint8_t* inFrame, const uint8_t* inFrameR, const void* kpL,
+                         const uint8_t* descL, int NL, const void* kpR, const uint8_t* descR, int NR, const int* leftIdxs,
+                         const int* rightIdxs, const int* gridLStart, const int* gridLItems, const int* gridRStart,
+                         const int* gridRItems, int yGrids, int xGrids, float xMult, float yMult, float rad,
+                         int* matchedIdxsL, int* matchedIdxsR, int* matchesIdxs /* M x 2 */) {
+    Matcher* m = (Matcher*)h;
+    TrackedKeys keys;
+    fillKeys(keys, kpL, descL, NL, kpR, descR, NR, leftIdxs, rightIdxs, gridLStart, gridLItems, gridRStart, gridRItems, yGrids,
+             xGrids, xMult, yMult);
+    std::vector<int> mL(matchedIdxsL, matchedIdxsL + NL), mR;
+    if (matchedIdxsR) mR.assign(matchedIdxsR, matchedIdxsR + NR);
+    std::vector<std::pair<int, int>> pairs(M);
+    for (int i = 0; i < M; ++i) pairs[i] = {matchesIdxs[2 * i], matchesIdxs[2 * i + 1]};
+    int n = 0;
+    if (mode == 2) {
+        // "map points" are the previous frame's keys: predL = pt, lvlL = octave, mpDesc = Desc rows
+        TrackedKeys last;
+        last.keyPoints.resize(M);
+        for (int i = 0; i < M; ++i) { last.keyPoints[i].pt = cv::Point2f(predL[2 * i], predL[2 * i + 1]); last.keyPoints[i].octave = lvlL[i]; }
+        last.Desc = descMat(mpDesc, M);
+        std::vector<std::vector<std::pair<KeyFrame*, int>>> kfMatches(M);
+        n = m->fm->matchByRadius(last, keys, mL, pairs, rad, kfMatches, nullptr);
+        for (int i = 0; i < M; ++i)
+            if (!kfMatches[i].empty()) pairs[i].first = kfMatches[i].back().second;
+    } else {
+        std::vector<MapPoint*> mps(M);
+        cv::KeyPoint obs;
+        for (int i = 0; i < M; ++i) {
+            MapPoint* mp = new MapPoint(Eigen::Vector4d(0, 0, 0, 1), descMat(mpDesc + (size_t)i * 32, 1), obs, 0, (unsigned long)i);
+            mp->predL = cv::Point2f(predL[2 * i], predL[2 * i + 1]);
+            if (predR) mp->predR = cv::Point2f(predR[2 * i], predR[2 * i + 1]);
+            mp->scaleLevelL = lvlL[i];
+            if (lvlR) mp->scaleLevelR = lvlR[i];
+            if (inFrame) mp->inFrame = inFrame[i] != 0;
+            if (inFrameR) mp->inFrameR = inFrameR[i] != 0;
+            mps[i] = mp;
+        }
+        n = mode == 0 ? m->fm->matchByProjectionRPred(mps, keys, mL, mR, pairs, rad)
+                      : m->fm->matchByProjectionMono(mps, keys, mL, pairs, rad);
+        for (MapPoint* mp : mps) delete mp;
+    }
+    std::memcpy(matchedIdxsL, mL.data(), (size_t)NL * sizeof(int));
+    if (matchedIdxsR) std::memcpy(matchedIdxsR, mR.data(), (size_t)NR * sizeof(int));
+    for (int i = 0; i < M; ++i) { matchesIdxs[2 * i] = pairs[i].first; matchesIdxs[2 * i + 1] = pairs[i].second; }
+    return n;
+}
+
+// FeatureMatcher::matchByProjectionRPredLBA with the flattened inputs of ora_match_lba.  The KeyFrame inputs are rebuilt
+// so that the reference code sees exactly these values: map point i is key pair (i, i) of a synthetic last key frame whose
+// left / right key i sits at lastL[i] / lastR[i] with descriptor mpDesc[i]; the new key frame's pose is the identity, every
+// world point is at distance 1 and maxDistsScale[i] = 1.2^(predScale[i] - 0.5), which makes
+// ceil(log(maxDist / dist) / logScale) = predScale[i] (src/FeatureMatcher.cpp:88-95).
+int ref_match_lba(void* h, int M, const uint8_t* mpDesc, const float* predL, const float* predR, const int* predScale,
+                  const float* lastL, const float* lastR, const void* kpL, const uint8_t* descL, int NL, const void* kpR,
+                  const uint8_t* descR, int NR, const int* leftIdxs, const int* rightIdxs, const int* unMatchedF,
+                  const int* unMatchedFR, const int* gridLStart, const int* gridLItems, const int* gridRStart,
+                  const int* gridRItems, int yGrids, int xGrids, float xMult, float yMult, float rad, int* out /* M x 2 */) {
+    Matcher* m = (Matcher*)h;
+    cv::Mat noIm;
+    KeyFrame lastKF(Eigen::Matrix4d::Identity(), noIm, noIm, 0, 0), newKF(Eigen::Matrix4d::Identity(), noIm, noIm, 1, 1);
+    const int nLev = (int)m->fm->feLeft->nLevels;
+    lastKF.logScale = std::log(m->fm->feLeft->imScale);
+    lastKF.nScaleLev = nLev;
+    lastKF.keys.keyPoints.resize(M); lastKF.keys.rightKeyPoints.resize(M);
+    for (int i = 0; i < M; ++i) {
+        lastKF.keys.keyPoints[i].pt = cv::Point2f(lastL[2 * i], lastL[2 * i + 1]);
+        lastKF.keys.rightKeyPoints[i].pt = cv::Point2f(lastR[2 * i], lastR[2 * i + 1]);
+    }
+    lastKF.keys.Desc = descMat(mpDesc, M);
+    lastKF.keys.rightDesc = descMat(mpDesc, M);
+    lastKF.localMapPoints.assign(M, nullptr);
+    fillKeys(newKF.keys, kpL, descL, NL, kpR, descR, NR, leftIdxs, rightIdxs, gridLStart, gridLItems, gridRStart, gridRItems,
+             yGrids, xGrids, xMult, yMult);
+    newKF.unMatchedF.assign(unMatchedF, unMatchedF + NL);
+    newKF.unMatchedFR.assign(unMatchedFR, unMatchedFR + NR);
+    std::vector<std::vector<std::pair<KeyFrame*, std::pair<int, int>>>> matched(M);
+    std::vector<std::pair<cv::Point2f, cv::Point2f>> pred(M);
+    std::vector<float> maxDists(M);
+    std::vector<std::pair<Eigen::Vector4d, std::pair<int, int>>> p4d(M);
+    for (int i = 0; i < M; ++i) {
+        pred[i] = {cv::Point2f(predL[2 * i], predL[2 * i + 1]), cv::Point2f(predR[2 * i], predR[2 * i + 1])};
+        maxDists[i] = (float)std::exp((double)lastKF.logScale * ((double)predScale[i] - 0.5));
+        p4d[i] = {Eigen::Vector4d(0, 0, 1, 1), {i, i}};
+    }
+    int n = m->fm->matchByProjectionRPredLBA(&lastKF, &newKF, matched, rad, pred, maxDists, p4d);
+    for (int i = 0; i < M; ++i) {
+        out[2 * i] = out[2 * i + 1] = -2;
+        if (!matched[i].empty()) { out[2 * i] = matched[i].back().second.first; out[2 * i + 1] = matched[i].back().second.second; }
+    }
+    return n;
+}
+
+// CPU baseline on the reference's own code: F stereo frames = extractKeysNew x2 + findStereoMatchesORB2R (+ the two key
+// grids through the restated assignKeysToGrids of liboracle.so: FeatureTracker.cpp is not compiled), i.e.
+// FeatureTracker::extractORBAndStereoMatch (src/FeatureTracker.cpp:56-70).  Same contract as ora_stereo_frames:
+// shape 0 = reference-shaped (frames in sequence, two extraction threads per frame, serial matcher), shape 1 = frame-parallel
+// over `threads` workers.  Uses whatever hook table is installed (default: restated scalar primitives, thread safe).
+long ref_stereo_frames(int nF, int nL, float s, int edge, int patch, int maxF, int minF, double fx, float baseline,
+                       const uint8_t* L, const uint8_t* R, int frames, int w, int h, int shape, int threads, int* nKeysOut) {
+    std::atomic<long> total{0};
+    auto one = [&](int f, bool twoThreads) {
+        ExtractorPtr feL = std::make_shared<FeatureExtractor>(nF, nL, s, edge, patch, maxF, minF);
+        ExtractorPtr feR = std::make_shared<FeatureExtractor>(nF, nL, s, edge, patch, maxF, minF);
+        Matcher* m = (Matcher*)ref_matcher_create(&feL, &feR, fx, baseline, h);
+        cv::Mat li(h, w, CV_8UC1, (void*)(L + (size_t)f * w * h)), ri(h, w, CV_8UC1, (void*)(R + (size_t)f * w * h));
+        TrackedKeys keys;
+        std::vector<cv::KeyPoint> rightKeys;
+        cv::Mat rightDesc;
+        if (twoThreads) {
+            std::thread a([&] { feL->extractKeysNew(li, keys.keyPoints, keys.Desc); });
+            std::thread b([&] { feR->extractKeysNew(ri, rightKeys, rightDesc); });
+            a.join(); b.join();
+        } else {
+            feL->extractKeysNew(li, keys.keyPoints, keys.Desc);
+            feR->extractKeysNew(ri, rightKeys, rightDesc);
+        }
+        m->fm->findStereoMatchesORB2R(li, ri, rightDesc, rightKeys, keys);
+        const int nl = (int)keys.keyPoints.size(), nr = (int)rightKeys.size();
+        std::vector<int> start(64 * 64 + 1), items(std::max(1, std::max(nl, nr)));
+        float xm, ym;
+        ora_assign_grid(keys.keyPoints.data(), nl, w, h, start.data(), items.data(), &xm, &ym);
+        ora_assign_grid(rightKeys.data(), nr, w, h, start.data(), items.data(), &xm, &ym);
+        long matched = 0;
+        for (int v : keys.rightIdxs) matched += v >= 0;
+        total += matched;
+        if (nKeysOut) nKeysOut[f] = nl;
+        ref_matcher_destroy(m);
+    };
+    if (shape == 0) {
+        for (int f = 0; f < frames; f++) one(f, true);
+    } else {
+        std::atomic<int> next{0};
+        std::vector<std::thread> pool;
+        for (int t = 0; t < std::max(1, threads); t++)
+            pool.emplace_back([&] { for (int f; (f = next++) < frames;) one(f, false); });
+        for (auto& t : pool) t.join();
+    }
+    return total.load();
+}
+
+int ref_descriptor_distance(const uint8_t* a, const uint8_t* b) {
+    return FeatureMatcher::DescriptorDistance(descMat(a, 1), descMat(b, 1));
+}
+
+}  // extern "C"
+
+// ---- link stubs -----------------------------------------------------------------------------------------------------
+// Constructors that the reference defines in files which are not on the path (src/Map.cpp, src/KeyFrame.cpp,
+// src/Camera.cpp) and which this driver needs to create the objects the matcher reads.  They only initialise members; no
+// behaviour of the reference is restated here.
+namespace GTSAM_VIOSLAM {
+CameraPose::CameraPose(Eigen::Matrix4d _pose, std::chrono::time_point<std::chrono::high_resolution_clock> _timestamp)
+    : pose(_pose), timestamp(_timestamp) {}
+Camera::Camera(std::shared_ptr<ConfigFile> configFile, const std::string&) : mConfigFile(configFile) {}
+MapPoint::MapPoint(const Eigen::Vector4d& p, const cv::Mat& _desc, const cv::KeyPoint& obsK, const unsigned long _kdx,
+                   const unsigned long _idx)
+    : wp(p), lastObsL(obsK), lastObsKF(nullptr), desc(_desc), kdx(_kdx), idx(_idx) {}
+KeyFrame::KeyFrame(Eigen::Matrix4d _pose, cv::Mat& _leftIm, cv::Mat& rLIm, const int _numb, const int _frameIdx)
+    : pose(_pose), leftIm(_leftIm), rLeftIm(rLIm), numb(_numb), frameIdx(_frameIdx) {}
+}  // namespace GTSAM_VIOSLAM

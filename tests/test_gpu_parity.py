@@ -429,3 +429,32 @@ def test_world_to_frame_projection():
     fb = cpu_ref.world_to_frame(Pinv, *cam, wPos, msd, ls, nl, pb, sb)
     assert np.array_equal(fa, fb) and np.array_equal(sa, sb)
     assert np.max(np.abs(pa - pb), initial=0) <= 1e-3 and np.array_equal(pa, pb)   # tolerance of the north star, and bit exact
+
+
+def test_cuda_against_the_compiled_reference():
+    """The CUDA path against the reference's OWN source (oracle/_ref/libref_frontend.so: FeatureExtractor.cpp and
+    FeatureMatcher.cpp compiled unmodified; built in the CPU container, the .so travels), on fresh seeds; with the real
+    OpenCV primitives (cv2 hooks) when cv2 is importable on this box."""
+    from oracle import ref_build
+    if not ref_build.available():
+        pytest.skip("oracle/_ref/libref_frontend.so was not built (needs the reference sources in the build container)")
+    try:
+        import cv2  # noqa: F401
+        ref_build.use_cv2_hooks()
+    except Exception:
+        ref_build.use_default_hooks()
+    try:
+        for cfgname, seeds in (("small", [40, 41, 42]), ("euroc", [43, 44]), ("kitti", [45])):
+            cfg = synth.CONFIGS[cfgname]
+            w, h = cfg["width"], cfg["height"]
+            L, R = synth.stereo_batch(w, h, cfg["disparity"], seeds)
+            feL, feR, fm = _handles(cfg, len(seeds))
+            fm.track_stereo_batch(L, R)
+            for f in range(len(seeds)):
+                rL = ref_build.RefExtractor(cfg["n_features"], cfg["n_levels"]); rR = ref_build.RefExtractor(cfg["n_features"], cfg["n_levels"])
+                kl, dl = rL.extractKeysNew(L[f]); kr, dr = rR.extractKeysNew(R[f])
+                s = ref_build.RefMatcher(cfg["fx"], cfg["baseline"], rL, rR, h).findStereoMatchesORB2R(kl, dl, kr, dr)
+                assert (s["rightIdxs"] >= 0).sum() > 0.3 * len(kl)
+                _assert_frame(fm, f, cfg, kl, dl, kr, dr, s)
+    finally:
+        ref_build.use_default_hooks()
