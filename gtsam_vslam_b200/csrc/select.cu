@@ -350,7 +350,8 @@ __device__ int sscPassWarp(const unsigned* xy, const IdxT* sorted, int n, int wi
     const int bmWords = (ncc * ncr + 31) >> 5;
     for (int i = lane; i < bmWords; i += 32) bitmap[i] = 0;
     __syncwarp();
-    const unsigned magic = (unsigned)(0x100000000ull / (unsigned)width) + 1u;  // exact while 2*coord*width < 2^32
+    // exact while 2*coord*width < 2^32; width 1 has no 32-bit magic number (2^32 + 1) and is handled apart below
+    const unsigned magic = (unsigned)(0x100000000ull / (unsigned)max(width, 2)) + 1u;
     int cnt = 0;
     for (int base = 0; base < n; base += 32) {
         const int i = base + lane;
@@ -358,8 +359,9 @@ __device__ int sscPassWarp(const unsigned* xy, const IdxT* sorted, int n, int wi
         bool active = false;
         if (i < n) {
             const unsigned q = xy[sorted[i]];
-            col = (int)__umulhi(2 * (q & 0xfff), magic);
-            row = (int)__umulhi(2 * ((q >> 12) & 0xfff), magic);
+            const unsigned x2 = 2 * (q & 0xfff), y2 = 2 * ((q >> 12) & 0xfff);
+            col = width == 1 ? (int)x2 : (int)__umulhi(x2, magic);
+            row = width == 1 ? (int)y2 : (int)__umulhi(y2, magic);
             const int bit = row * ncc + col;
             active = !((bitmap[bit >> 5] >> (bit & 31)) & 1);
         }

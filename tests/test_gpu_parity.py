@@ -205,6 +205,16 @@ def test_ssc_small_widths_use_hash_grid():
         sidx, kept = fe.debug_select(0, x, y, s)
         osrt, okept = o.ssc(int(fe.featurePerLevel[0]), lw, lh, x, y, s.astype(np.float32))
         assert np.array_equal(sidx, osrt) and np.array_equal(kept, okept), n
+    # pairs of points 2 px apart: width 2 merges each pair (count < Kmin), so the search ends at width 1 (cell = half a pixel)
+    for pairs in (225, 235):      # 450 keys: inside [Kmin, Kmax] at width 1; 470: above Kmax -> bracket exhausted, last pass returned
+        pos = rng.permutation(((lw - 60) // 8) * ((lh - 60) // 8))[:pairs]
+        px = (pos % ((lw - 60) // 8) * 8 + 24).astype(np.int32); py = (pos // ((lw - 60) // 8) * 8 + 24).astype(np.int32)
+        x = np.concatenate([px, px + 2]); y = np.concatenate([py, py])
+        s = rng.integers(7, 60, 2 * pairs).astype(np.int32)
+        sidx, kept = fe.debug_select(0, x, y, s)
+        osrt, okept = o.ssc(int(fe.featurePerLevel[0]), lw, lh, x, y, s.astype(np.float32))
+        assert len(okept) == 2 * pairs
+        assert np.array_equal(sidx, osrt) and np.array_equal(kept, okept), pairs
 
 
 def test_projection_matchers_against_golden_and_oracle(golden_dir):
@@ -458,3 +468,33 @@ def test_cuda_against_the_compiled_reference():
                 _assert_frame(fm, f, cfg, kl, dl, kr, dr, s)
     finally:
         ref_build.use_default_hooks()
+
+
+@pytest.mark.parametrize("w,h,nF,nL,scale,edge,maxF,minF,seed", [
+    (640, 480, 500, 6, 1.5, 19, 20, 7, 50),      # coarse pyramid
+    (401, 303, 800, 5, 1.3, 19, 30, 10, 51),     # odd sizes, other thresholds
+    (1280, 720, 1500, 8, 1.2, 19, 20, 7, 52),    # 720p
+    (752, 480, 1000, 12, 1.1, 19, 20, 7, 53),    # 12 fine levels
+    (320, 240, 300, 4, 1.2, 25, 40, 5, 54),      # wider edge, far-apart thresholds
+    (512, 384, 4000, 3, 2.0, 19, 12, 3, 55),     # many features, factor 2, low thresholds
+    (333, 257, 150, 2, 1.2, 19, 20, 20, 56),     # max == min threshold
+])
+def test_parameter_sweep(w, h, nF, nL, scale, edge, maxF, minF, seed):
+    """Non-default constructor parameters and image sizes: CUDA == oracle (== compiled reference when it is present)."""
+    from oracle import ref_build
+    L, R = synth.stereo_pair(w, h, 10, seed)
+    feL = gvs.FeatureExtractor(nF, nL, scale, edge, 31, maxF, minF, width=w, height=h, max_images=1)
+    feR = gvs.FeatureExtractor(nF, nL, scale, edge, 31, maxF, minF, width=w, height=h, max_images=1)
+    fm = gvs.FeatureMatcher(300.0, 0.2, feL, feR, h)
+    fm.track_stereo_batch(L[None], R[None])
+    cfg = dict(width=w, height=h)
+    oL, oR = cpu_ref.Extractor(nF, nL, scale, edge, 31, maxF, minF), cpu_ref.Extractor(nF, nL, scale, edge, 31, maxF, minF)
+    kl, dl = oL.extractKeysNew(L); kr, dr = oR.extractKeysNew(R)
+    assert len(kl) > 0.5 * min(nF, 1500)
+    s = cpu_ref.stereo_match(oL, oR, 300.0, 0.2, h, kl, dl, kr, dr)
+    _assert_frame(fm, 0, cfg, kl, dl, kr, dr, s)
+    if ref_build.available():
+        rL, rR = ref_build.RefExtractor(nF, nL, scale, edge, 31, maxF, minF), ref_build.RefExtractor(nF, nL, scale, edge, 31, maxF, minF)
+        kl2, dl2 = rL.extractKeysNew(L); kr2, dr2 = rR.extractKeysNew(R)
+        s2 = ref_build.RefMatcher(300.0, 0.2, rL, rR, h).findStereoMatchesORB2R(kl2, dl2, kr2, dr2)
+        _assert_frame(fm, 0, cfg, kl2, dl2, kr2, dr2, s2)
