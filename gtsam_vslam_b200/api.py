@@ -362,8 +362,9 @@ class FeatureMatcher:
         fe = self.feRight if side else self.feLeft
         off = fe.offsets(frame + 1)
         n = int(off[frame + 1] - off[frame])
-        start = np.zeros(64 * 64 + 1, np.int32); items = np.zeros(max(n, 1), np.int32)
         yg, xm, ym = C.c_int(), C.c_float(), C.c_float()
+        _check(self._lib.gvs_grid_download(self.h, frame, side, None, None, C.byref(yg), C.byref(xm), C.byref(ym)))  # sizes first
+        start = np.zeros(64 * yg.value + 1, np.int32); items = np.zeros(max(n, 1), np.int32)
         _check(self._lib.gvs_grid_download(self.h, frame, side, _p(start), _p(items), C.byref(yg), C.byref(xm), C.byref(ym)))
         return dict(xGrids=64, yGrids=yg.value, xMult=xm.value, yMult=ym.value, start=start[:64 * yg.value + 1].copy(),
                     items=items[:n].copy())

@@ -104,7 +104,8 @@ struct gvs_matcher {
     int* cellStartR = nullptr;
     int* itemsL = nullptr;
     int* itemsR = nullptr;
-    int maxCells = GVS_GRID_X * GVS_GRID_X;
+    int maxCells = GVS_GRID_X * GVS_GRID_X;   // set at creation from the image shape
+    static constexpr int kMaxGridRows = 512;   // 64 x 512 cells: the counting sort of grid_assign_kernel keeps them in shared memory
     int xGrids = 0, yGrids = 0;
     float xMult = 0, yMult = 0;
     bool gridsValid = false, stereoValid = false;
@@ -208,7 +209,7 @@ int buildGeometry(gvs_extractor* fe) {
             lv.kmax = (int)(unsigned)std::round(uK + (uK * tol));
         }
         lv.candOff = candOff;
-        lv.candCap = std::min(((lv.w * lv.h) / 12 + 256 + 3) & ~3, 65535 * 16);
+        lv.candCap = std::min(((lv.w * lv.h) / 8 + 256 + 3) & ~3, 65535 * 16);  // iid noise at a low threshold keeps ~1 px in 9 after the 3x3 NMS
         candOff += lv.candCap;
         lv.keptOff = keptOff;
         lv.keptCap = 2 * lv.quota + 64;
@@ -329,7 +330,7 @@ int syncExtract(gvs_extractor* fe) {
         }
     }
     const int st = *fe->hStatus;
-    if (st & kStatCandOverflow) return fail(GVS_ERR_CAPACITY, "FAST candidate buffer overflow (image denser than 1 corner per 12 px)");
+    if (st & kStatCandOverflow) return fail(GVS_ERR_CAPACITY, "FAST candidate buffer overflow (image denser than 1 corner per 8 px)");
     if (st & kStatKeptOverflow) return fail(GVS_ERR_CAPACITY, "kept-key staging overflow (ssc returned more than 2*quota+64 keys)");
     if (st & kStatOutputOverflow) return fail(GVS_ERR_CAPACITY, "dense output overflow");
     return GVS_OK;
@@ -784,6 +785,11 @@ int gvs_matcher_create(gvs_matcher** out, gvs_extractor* feL, gvs_extractor* feR
     GVS_CUDA_OK(cudaSetDevice(feL->device));
     gvs_matcher* m = new gvs_matcher();
     m->L = feL; m->R = feR; m->fx = fx; m->baseline = baseline; m->imageHeight = image_height;
+    {   // key grid: 64 columns, ceil(64 / (w/h)) rows (src/FeatureTracker.cpp:30-34); sized for this handle's image shape
+        const int yG = (int)std::ceil((float)GVS_GRID_X / ((float)feL->width / (float)feL->height));
+        if (yG > gvs_matcher::kMaxGridRows) { delete m; return fail(GVS_ERR_INVALID, "image taller than 8x its width is not supported"); }
+        m->maxCells = GVS_GRID_X * std::max(GVS_GRID_X, yG);
+    }
     const size_t B = (size_t)std::min(feL->maxImages, feR->maxImages);
     bool ok = devAlloc(&m->rightIdxs, (size_t)feL->totalCap) == cudaSuccess && devAlloc(&m->depth, (size_t)feL->totalCap) == cudaSuccess &&
               devAlloc(&m->close, (size_t)feL->totalCap) == cudaSuccess && devAlloc(&m->sadBest, (size_t)feL->totalCap) == cudaSuccess &&
@@ -924,7 +930,7 @@ int gvs_assign_grids_batch(gvs_matcher* m, int n_frames, int width, int height) 
     const float imageRatio = (float)width / (float)height;
     m->xGrids = GVS_GRID_X;
     m->yGrids = (int)std::ceil((float)m->xGrids / imageRatio);
-    if (m->xGrids * m->yGrids > m->maxCells) return fail(GVS_ERR_INVALID, "image taller than wide by more than 64x is not supported");
+    if (m->xGrids * m->yGrids > m->maxCells) return fail(GVS_ERR_INVALID, "key grid larger than the one this matcher was created for (image shape differs from the extractors')");
     m->xMult = (float)m->xGrids / (float)width;
     m->yMult = (float)m->yGrids / (float)height;
     int rc = joinRight(m);
@@ -1124,7 +1130,7 @@ int gvs_match_projection_lba(gvs_matcher* m, const gvs_lba_frame* kf, const gvs_
     cudaStream_t s = m->L->stream;
     const float imageRatio = (float)kf->width / (float)kf->height;
     const int xGrids = GVS_GRID_X, yGrids = (int)std::ceil((float)xGrids / imageRatio);
-    if (xGrids * yGrids > m->maxCells) return fail(GVS_ERR_INVALID, "image taller than wide by more than 64x is not supported");
+    if (xGrids * yGrids > m->maxCells) return fail(GVS_ERR_INVALID, "key grid larger than the one this matcher was created for (image shape differs from the extractors')");
     const float xMult = (float)xGrids / (float)kf->width, yMult = (float)yGrids / (float)kf->height;
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
     size_t o = 0;

@@ -394,6 +394,8 @@ __device__ int sscPassWarp(const unsigned* xy, const IdxT* sorted, int n, int wi
 // the tree (7 nodes) are evaluated speculatively by 7 warps at once, then the path is walked with the counts.
 // Returns the kept count; `outList` (shared, listCap entries) receives the kept sorted-positions.
 constexpr int kSscBitmapWords = 384;  // per-warp shared bitmap: 12288 cells (keeps the CTA at 3 per SM)
+constexpr size_t kSscListSmemBudget = 16 * 1024;  // 7 kept lists of u16: in shared memory up to this size (quota <= ~550 per level)
+__host__ __device__ inline size_t sscListScratchBytes(int listCap) { return ((size_t)kSscWarps * listCap * 4 + 255) & ~(size_t)255; }
 template <typename IdxT>
 __device__ int sscSearch(const SelArrays<IdxT>& A, SelShared& S, const IdxT* sorted, int n, const LevelGeom& lv,
                          unsigned* bitmaps, IdxT* lists, int listCap, unsigned* globalBitmap, const IdxT** outList) {
@@ -472,7 +474,7 @@ select_kernel(const __grid_constant__ Geometry g, int nImages, const CandRec* __
               int* __restrict__ keptCnt, unsigned* __restrict__ orderedDbg, unsigned* __restrict__ sortedDbg,
               uint8_t* __restrict__ scratch,
               size_t scratchPerCta, int* __restrict__ workCounter, int* __restrict__ status, int maxCells, int segCap,
-              int nMaxGlobal, int listCap) {
+              int nMaxGlobal, int listCap, int listsGlobal) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ SelShared S;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -484,12 +486,14 @@ select_kernel(const __grid_constant__ Geometry g, int nImages, const CandRec* __
         uint8_t* p = smem;
         A.cellOff = reinterpret_cast<int*>(p); p += ((maxCells + 1) * 4 + 15) & ~15;
         const size_t segBytes = (size_t)2 * 3 * segCap * 4, histBytes = kSelWarps * 256 * 4;
-        const size_t bmBytes = (size_t)kSscWarps * kSscBitmapWords * 4, listBytes = (size_t)kSscWarps * listCap * sizeof(IdxT);
+        // the 7 speculative kept lists live in shared memory unless the per-level quota is large (listsGlobal)
+        const size_t bmBytes = (size_t)kSscWarps * kSscBitmapWords * 4;
+        const size_t listBytes = listsGlobal ? 0 : (size_t)kSscWarps * listCap * sizeof(IdxT);
         A.seg = reinterpret_cast<int*>(p);
         A.hist = reinterpret_cast<int*>(p + segBytes);
         A.segCap = segCap;
         A.bitmaps = reinterpret_cast<unsigned*>(p);
-        A.lists = p + bmBytes;
+        A.lists = listsGlobal ? myScratch + scratchPerCta - sscListScratchBytes(listCap) : p + bmBytes;
         A.listCap = listCap;
         const size_t unionBytes = segBytes + histBytes > bmBytes + listBytes ? segBytes + histBytes : bmBytes + listBytes;
         p += (unionBytes + 15) & ~15;
@@ -578,13 +582,19 @@ select_kernel(const __grid_constant__ Geometry g, int nImages, const CandRec* __
     }
 }
 
-static size_t selectSmemBytes(bool small, int maxCells, int segCap, int listCap) {
+static size_t selectSmemBytes(bool small, int maxCells, int segCap, int listCap /* 0: lists in global scratch */) {
     size_t b = ((size_t)(maxCells + 1) * 4 + 15) & ~(size_t)15;
     const size_t segBytes = (size_t)2 * 3 * segCap * 4, histBytes = kSelWarps * 256 * 4;
     size_t u = std::max(segBytes + histBytes, (size_t)kSscWarps * kSscBitmapWords * 4 + (size_t)kSscWarps * listCap * (small ? 2 : 4));
     b += (u + 15) & ~(size_t)15;
     if (small) b += (size_t)kSmallMax * (4 + 2 + 2 + 1);
     return b;
+}
+
+static int maxListCap(const Geometry& g) {
+    int m = 0;
+    for (int l = 0; l < g.nLevels; l++) m = std::max(m, g.lv[l].keptCap);
+    return m;
 }
 
 static int maxCandCap(const Geometry& g) {
@@ -599,7 +609,8 @@ size_t selectScratchBytes(const Geometry& g) {
     const size_t nMax = (size_t)std::max(maxCandCap(g), kSmallMax);
     size_t b = nMax * (4 + 4 + 4) + (size_t)2 * 3 * (nMax / 17 + 2) * 4 + ((nMax + 15) & ~(size_t)15);
     b += ((size_t)(2 * g.lv[0].h + 1) * (2 * g.lv[0].w + 1) + 31) / 32 * 4 + 16;
-    return (b + 255) & ~(size_t)255;
+    b = (b + 255) & ~(size_t)255;
+    return b + sscListScratchBytes(maxListCap(g));   // tail: the SSC kept lists when they do not fit shared memory
 }
 
 int selectMaxCtas(int device) {
@@ -616,10 +627,10 @@ void launchSelect(const Geometry& g, int nImages, const CandRec* recs, const int
     int maxCells = 0;
     for (int l = 0; l < g.nLevels; l++) maxCells = std::max(maxCells, g.lv[l].nCols * g.lv[l].nRows);
     const int segCapSmall = kSmallMax / 17 + 2;
-    int listCap = 0;
-    for (int l = 0; l < g.nLevels; l++) listCap = std::max(listCap, g.lv[l].keptCap);
-    const size_t smSmall = selectSmemBytes(true, maxCells, segCapSmall, listCap);
-    const size_t smBig = selectSmemBytes(false, maxCells, 1, listCap);
+    const int listCap = maxListCap(g);
+    const int listsGlobal = (size_t)kSscWarps * listCap * 2 > kSscListSmemBudget;
+    const size_t smSmall = selectSmemBytes(true, maxCells, segCapSmall, listsGlobal ? 0 : listCap);
+    const size_t smBig = selectSmemBytes(false, maxCells, 1, listsGlobal ? 0 : listCap);
     static size_t cfgS[64], cfgB[64];
     ensureDynamicSmem(select_kernel<unsigned short, true>, smSmall, cfgS);
     ensureDynamicSmem(select_kernel<unsigned, false>, smBig, cfgB);
@@ -628,14 +639,14 @@ void launchSelect(const Geometry& g, int nImages, const CandRec* recs, const int
     cudaMemsetAsync(workCounter, 0, 2 * sizeof(int), s);
     select_kernel<unsigned short, true><<<grid, kSelThreads, smSmall, s>>>(
         g, nImages, recs, nCand, cellCnt, kept, keptCnt, orderedDbg, sortedDbg, scratch, scratchPerCta, workCounter, status,
-        maxCells, segCapSmall, maxCandCap(g), listCap);
+        maxCells, segCapSmall, maxCandCap(g), listCap, listsGlobal);
     ++*launches;
     bool needBig = false;
     for (int l = 0; l < g.nLevels; l++) needBig |= g.lv[l].candCap > kSmallMax;
     if (needBig) {
         select_kernel<unsigned, false><<<grid, kSelThreads, smBig, s>>>(
             g, nImages, recs, nCand, cellCnt, kept, keptCnt, orderedDbg, sortedDbg, scratch, scratchPerCta, workCounter + 1,
-            status, maxCells, 1, maxCandCap(g), listCap);
+            status, maxCells, 1, maxCandCap(g), listCap, listsGlobal);
         ++*launches;
     }
 }

@@ -233,7 +233,7 @@ void launchStereo(const Geometry& g, const StereoArgs& a, int nFrames, int maxKe
 // (= index) order inside a cell: counting pass, exclusive scan, stable fill in chunks of 32 keys.
 __global__ void __launch_bounds__(32)
 grid_assign_kernel(const GridArgs a) {
-    extern __shared__ int sCell[];  // maxCells + 1
+    extern __shared__ int sCell[];  // xGrids * yGrids + 1
     const int img = blockIdx.x, lane = threadIdx.x;
     const int off = a.off[img], n = a.off[img + 1] - off;
     const int nCells = a.xGrids * a.yGrids;
@@ -280,7 +280,10 @@ grid_assign_kernel(const GridArgs a) {
 
 void launchGrid(const GridArgs& a, int nImages, cudaStream_t s, int* launches) {
     if (nImages <= 0) return;
-    grid_assign_kernel<<<nImages, 32, (a.maxCells + 1) * sizeof(int), s>>>(a);
+    const size_t sm = ((size_t)a.xGrids * a.yGrids + 1) * sizeof(int);
+    static size_t cfg[64];
+    ensureDynamicSmem(grid_assign_kernel, sm, cfg);
+    grid_assign_kernel<<<nImages, 32, sm, s>>>(a);
     ++*launches;
 }
 

@@ -150,7 +150,9 @@ int gvs_stereo_download(gvs_matcher* fm, int first, int count, int32_t* right_id
 /* FeatureTracker::assignKeysToGrids, src/FeatureTracker.cpp:28-54, for both sides of frames [0,n_frames)
  * (device resident CSR: the grids feed gvs_match_projection).  width/height = zedPtr->mWidth/mHeight. */
 int gvs_assign_grids_batch(gvs_matcher* fm, int n_frames, int width, int height);
-/* CSR download for one frame and side (0 left, 1 right): cell_start has y_grids*64+1 entries, items n. */
+/* CSR download for one frame and side (0 left, 1 right): cell_start has y_grids*64+1 entries, items n.
+ * y_grids = ceil(64 * height / width) (64 for landscape images up to square; at most 512): call with cell_start = items =
+ * NULL first to learn it.  Any pointer may be NULL. */
 int gvs_grid_download(gvs_matcher* fm, int frame, int side, int32_t* cell_start, int32_t* items, int* y_grids,
                       float* x_mult, float* y_mult);
 

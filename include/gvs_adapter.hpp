@@ -146,8 +146,9 @@ class FeatureMatcher {
         gvsCheck(gvs_assign_grids_batch(h_, 1, width, height));
         for (int side = 0; side < 2; side++) {
             const size_t n = side ? keysLeft.rightKeyPoints.size() : keysLeft.keyPoints.size();
-            std::vector<int> start(GVS_GRID_X * GVS_GRID_X + 1), items(n + 1);
             int yg = 0;
+            gvsCheck(gvs_grid_download(h_, 0, side, nullptr, nullptr, &yg, &keysLeft.xMult, &keysLeft.yMult));  // rows first
+            std::vector<int> start((size_t)GVS_GRID_X * yg + 1), items(n + 1);
             gvsCheck(gvs_grid_download(h_, 0, side, start.data(), items.data(), &yg, &keysLeft.xMult, &keysLeft.yMult));
             keysLeft.xGrids = GVS_GRID_X; keysLeft.yGrids = yg;
             auto& grid = side ? keysLeft.rkeyGrid : keysLeft.lkeyGrid;

@@ -1,0 +1,108 @@
+#!/usr/bin/env python3
+"""Differential fuzzing of the CUDA path against the oracle on random constructor parameters, image sizes and image
+kinds (run on a GPU box):  python tools/fuzz_parity.py [iterations] [seed]
+Every mismatch prints the parameter set that reproduces it; exit code 1 if any."""
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import gtsam_vslam_b200 as gvs  # noqa: E402
+from gtsam_vslam_b200 import synth  # noqa: E402
+from oracle import cpu_ref  # noqa: E402
+
+
+def box(img, k):
+    c = np.cumsum(np.cumsum(np.pad(img.astype(np.float64), ((k, 0), (k, 0))), 0), 1)
+    return (c[k:, k:] - c[:-k, k:] - c[k:, :-k] + c[:-k, :-k]) / (k * k)
+
+
+def make_image(rng, kind, w, h):
+    if kind == "rects":
+        return synth.stereo_pair(w, h, 0, int(rng.integers(1 << 30)))[0]
+    if kind == "noise":
+        return rng.integers(0, 256, (h, w), dtype=np.uint8)
+    if kind == "smooth":
+        k = int(rng.integers(2, 6))
+        b = box(rng.integers(0, 256, (h + k, w + k)).astype(np.float64), k)[:h, :w]
+        b = (b - b.min()) / max(b.max() - b.min(), 1e-9)
+        return (b * 255).astype(np.uint8)
+    if kind == "checker":
+        c = int(rng.integers(5, 40))
+        yy, xx = np.mgrid[0:h, 0:w]
+        lo, hi = sorted(rng.integers(0, 256, 2).tolist())
+        return np.where(((yy // c) + (xx // c)) % 2 == 0, lo, hi).astype(np.uint8)
+    if kind == "lowcontrast":
+        base = synth.stereo_pair(w, h, 0, int(rng.integers(1 << 30)))[0].astype(np.int32)
+        return (100 + (base - 128) // int(rng.integers(4, 12))).clip(0, 255).astype(np.uint8)
+    if kind == "dots":
+        img = np.full((h, w), int(rng.integers(20, 230)), np.uint8)
+        n = int(rng.integers(5, 400))
+        ys = rng.integers(0, h - 3, n); xs = rng.integers(0, w - 3, n)
+        for y, x in zip(ys, xs):
+            img[y:y + int(rng.integers(1, 4)), x:x + int(rng.integers(1, 4))] = int(rng.integers(0, 256))
+        return img
+    if kind == "saturated":
+        base = synth.stereo_pair(w, h, 0, int(rng.integers(1 << 30)))[0].astype(np.int32)
+        return ((base - 128) * 4 + 128).clip(0, 255).astype(np.uint8)
+    raise ValueError(kind)
+
+
+KINDS = ["rects", "noise", "smooth", "checker", "lowcontrast", "dots", "saturated"]
+
+
+def same_keys(a, b):
+    return len(a) == len(b) and all(np.array_equal(a[f], b[f]) for f in a.dtype.names)
+
+
+def main():
+    iters = int(sys.argv[1]) if len(sys.argv) > 1 else 100
+    rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+    bad = 0
+    t0 = time.time()
+    for it in range(iters):
+        w = int(rng.integers(120, 1400)); h = int(rng.integers(100, 900))
+        nL = int(rng.integers(1, 11)); scale = float(rng.choice([1.1, 1.2, 1.25, 1.3, 1.5, 2.0]))
+        while min(w, h) / scale ** (nL - 1) < 2 * 19 + 40:   # the coarsest level must keep a few cells
+            nL -= 1
+        nL = max(nL, 1)
+        nF = int(rng.choice([50, 200, 500, 1000, 2000, 5000]))
+        edge = int(rng.choice([19, 19, 19, 22, 31]))
+        maxF = int(rng.integers(5, 60)); minF = int(rng.integers(1, maxF + 1))
+        kind = str(rng.choice(KINDS)); disp = int(rng.integers(0, 40))
+        L = make_image(rng, kind, w + disp, h)
+        R = np.ascontiguousarray(L[:, disp:disp + w]) if disp else L.copy()
+        L = np.ascontiguousarray(L[:, :w])
+        if rng.random() < 0.5:
+            R = np.clip(R.astype(np.int32) + rng.integers(-2, 3, R.shape), 0, 255).astype(np.uint8)
+        tag = f"it {it}: {w}x{h} nF {nF} nL {nL} scale {scale} edge {edge} fast {maxF}/{minF} {kind} disp {disp}"
+        try:
+            feL = gvs.FeatureExtractor(nF, nL, scale, edge, 31, maxF, minF, width=w, height=h, max_images=1)
+            feR = gvs.FeatureExtractor(nF, nL, scale, edge, 31, maxF, minF, width=w, height=h, max_images=1)
+            fm = gvs.FeatureMatcher(300.0, 0.2, feL, feR, h)
+            fm.track_stereo_batch(L[None], R[None])
+            k = gvs.tracked_keys(fm, 0, w, h)
+        except gvs.GvsError as e:
+            if "capacity" in str(e).lower():
+                print("CAPACITY", tag, e, flush=True)
+                continue
+            print("ERROR", tag, e, flush=True); bad += 1
+            continue
+        oL, oR = cpu_ref.Extractor(nF, nL, scale, edge, 31, maxF, minF), cpu_ref.Extractor(nF, nL, scale, edge, 31, maxF, minF)
+        kl, dl = oL.extractKeysNew(L); kr, dr = oR.extractKeysNew(R)
+        s = cpu_ref.stereo_match(oL, oR, 300.0, 0.2, h, kl, dl, kr, dr)
+        ok = same_keys(k.keyPoints, kl) and same_keys(k.rightKeyPoints, kr) and np.array_equal(k.Desc, dl) and np.array_equal(k.rightDesc, dr)
+        ok2 = ok and all(np.array_equal(getattr(k, a), s[a]) for a in ("rightIdxs", "leftIdxs", "estimatedDepth", "close"))
+        if not ok2:
+            bad += 1
+            print("MISMATCH", "extract" if not ok else "stereo", tag, f"gpu {len(k.keyPoints)}/{len(k.rightKeyPoints)} oracle {len(kl)}/{len(kr)}", flush=True)
+        elif it % 10 == 0:
+            print("ok", tag, f"keys {len(kl)}/{len(kr)} matches {(s['rightIdxs'] >= 0).sum()}", flush=True)
+    print(f"{iters} cases, {bad} bad, {time.time() - t0:.0f} s")
+    sys.exit(1 if bad else 0)
+
+
+if __name__ == "__main__":
+    main()
