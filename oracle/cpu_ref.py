@@ -126,7 +126,7 @@ def assign_grid(kps, width: int, height: int):
     """assignKeysToGrids (reference src/FeatureTracker.cpp:28-54) in CSR form."""
     kps = np.ascontiguousarray(kps)
     n = len(kps)
-    start = np.zeros(64 * 64 + 1, np.int32)
+    start = np.zeros(64 * 513 + 1, np.int32)   # yGrids = ceil(64 * height / width): more than 64 rows for portrait images
     items = np.zeros(max(n, 1), np.int32)
     xm, ym = C.c_float(), C.c_float()
     yg = lib().ora_assign_grid(_p(kps), n, width, height, _p(start), _p(items), C.byref(xm), C.byref(ym))

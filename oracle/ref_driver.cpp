@@ -275,7 +275,7 @@ long ref_stereo_frames(int nF, int nL, float s, int edge, int patch, int maxF, i
         }
         m->fm->findStereoMatchesORB2R(li, ri, rightDesc, rightKeys, keys);
         const int nl = (int)keys.keyPoints.size(), nr = (int)rightKeys.size();
-        std::vector<int> start(64 * 64 + 1), items(std::max(1, std::max(nl, nr)));
+        std::vector<int> start(64 * (64 * h / w + 2) + 1), items(std::max(1, std::max(nl, nr)));
         float xm, ym;
         ora_assign_grid(keys.keyPoints.data(), nl, w, h, start.data(), items.data(), &xm, &ym);
         ora_assign_grid(rightKeys.data(), nr, w, h, start.data(), items.data(), &xm, &ym);

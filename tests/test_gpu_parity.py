@@ -478,6 +478,9 @@ def test_cuda_against_the_compiled_reference():
     (320, 240, 300, 4, 1.2, 25, 40, 5, 54),      # wider edge, far-apart thresholds
     (512, 384, 4000, 3, 2.0, 19, 12, 3, 55),     # many features, factor 2, low thresholds
     (333, 257, 150, 2, 1.2, 19, 20, 20, 56),     # max == min threshold
+    (1191, 360, 1000, 7, 1.1, 19, 19, 13, 57),   # last cell column 1 px wide and word aligned (found by tools/fuzz_parity.py)
+    (1054, 174, 2000, 4, 1.3, 22, 17, 10, 58),   # same, other alignment
+    (360, 700, 800, 5, 1.2, 19, 20, 7, 59),      # portrait: more than 64 key-grid rows
 ])
 def test_parameter_sweep(w, h, nF, nL, scale, edge, maxF, minF, seed):
     """Non-default constructor parameters and image sizes: CUDA == oracle (== compiled reference when it is present)."""
@@ -498,3 +501,20 @@ def test_parameter_sweep(w, h, nF, nL, scale, edge, maxF, minF, seed):
         kl2, dl2 = rL.extractKeysNew(L); kr2, dr2 = rR.extractKeysNew(R)
         s2 = ref_build.RefMatcher(300.0, 0.2, rL, rR, h).findStereoMatchesORB2R(kl2, dl2, kr2, dr2)
         _assert_frame(fm, 0, cfg, kl2, dl2, kr2, dr2, s2)
+
+
+def test_every_width_alignment_of_the_last_cell():
+    """Widths 300..371 at one level: the last cell column takes every width from 1 px up and every alignment against the
+    4-px words of the FAST kernel (a 1-px last cell that is one word wide once broke an index division)."""
+    rng = np.random.default_rng(9)
+    for w in range(300, 372):
+        h = 110 + (w % 7)
+        img = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        img[:, : w // 2] = synth.stereo_pair(w, h, 0, w)[0][:, : w // 2]
+        fe = gvs.FeatureExtractor(600, 1, 1.2, 19, 31, 20, 7, width=w, height=h, max_images=1)
+        o = cpu_ref.Extractor(600, 1, 1.2, 19, 31, 20, 7)
+        gk, gd = fe.extractKeysNew(img)
+        ok, od = o.extractKeysNew(img)
+        x, y, s = fe.level_candidates(0, 0); c = o.level_keys(0, False)
+        assert np.array_equal(x, c["x"]) and np.array_equal(y, c["y"]) and np.array_equal(s, c["response"].astype(np.int32)), w
+        _assert_keys(gk, gd, ok, od)

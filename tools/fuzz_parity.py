@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
 """Differential fuzzing of the CUDA path against the oracle on random constructor parameters, image sizes and image
-kinds (run on a GPU box):  python tools/fuzz_parity.py [iterations] [seed]
-Every mismatch prints the parameter set that reproduces it; exit code 1 if any."""
+kinds (run on a GPU box):  python tools/fuzz_parity.py [iterations] [seed] [only=it1,it2,...]
+Every mismatch prints the parameter set; `only=` replays the same random stream but runs (and diagnoses, level by level)
+just the listed iterations.  Exit code 1 if any mismatch."""
 import os
 import sys
 import time
@@ -57,9 +58,27 @@ def same_keys(a, b):
     return len(a) == len(b) and all(np.array_equal(a[f], b[f]) for f in a.dtype.names)
 
 
+def diagnose(fe, o, nL, side):
+    for l in range(nL):
+        a = fe.level_image(0, l); b = o.level_image(l)
+        x, y, s = fe.level_candidates(0, l); c = o.level_keys(l, False)
+        same_c = len(x) == len(c["x"]) and np.array_equal(x, c["x"]) and np.array_equal(y, c["y"]) and np.array_equal(s, c["response"].astype(np.int32))
+        xk, yk, sk = fe.level_kept(0, l); ck = o.level_keys(l, True)
+        same_k = len(xk) == len(ck["x"]) and np.array_equal(xk, ck["x"]) and np.array_equal(yk, ck["y"])
+        msg = f"   {side} L{l} {a.shape[1]}x{a.shape[0]} pyr {'ok' if np.array_equal(a, b) else 'DIFF ' + str(int((a != b).sum()))} cand {len(x)}/{len(c['x'])} {'ok' if same_c else 'DIFF'} kept {len(xk)}/{len(ck['x'])} {'ok' if same_k else 'DIFF'}"
+        if not same_c:
+            sa = set(zip(x.tolist(), y.tolist(), s.tolist())); sb = set(zip(c["x"].tolist(), c["y"].tolist(), c["response"].astype(int).tolist()))
+            msg += f" only-gpu {sorted(sa - sb)[:6]} only-oracle {sorted(sb - sa)[:6]}"
+        print(msg, flush=True)
+
+
 def main():
     iters = int(sys.argv[1]) if len(sys.argv) > 1 else 100
     rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+    only = None
+    for a in sys.argv[3:]:
+        if a.startswith("only="):
+            only = set(int(v) for v in a[5:].split(","))
     bad = 0
     t0 = time.time()
     for it in range(iters):
@@ -78,6 +97,8 @@ def main():
         if rng.random() < 0.5:
             R = np.clip(R.astype(np.int32) + rng.integers(-2, 3, R.shape), 0, 255).astype(np.uint8)
         tag = f"it {it}: {w}x{h} nF {nF} nL {nL} scale {scale} edge {edge} fast {maxF}/{minF} {kind} disp {disp}"
+        if only is not None and it not in only:
+            continue
         try:
             feL = gvs.FeatureExtractor(nF, nL, scale, edge, 31, maxF, minF, width=w, height=h, max_images=1)
             feR = gvs.FeatureExtractor(nF, nL, scale, edge, 31, maxF, minF, width=w, height=h, max_images=1)
@@ -98,6 +119,8 @@ def main():
         if not ok2:
             bad += 1
             print("MISMATCH", "extract" if not ok else "stereo", tag, f"gpu {len(k.keyPoints)}/{len(k.rightKeyPoints)} oracle {len(kl)}/{len(kr)}", flush=True)
+            if only is not None:
+                diagnose(feL, oL, nL, "L"); diagnose(feR, oR, nL, "R")
         elif it % 10 == 0:
             print("ok", tag, f"keys {len(kl)}/{len(kr)} matches {(s['rightIdxs'] >= 0).sum()}", flush=True)
     print(f"{iters} cases, {bad} bad, {time.time() - t0:.0f} s")
