@@ -72,6 +72,57 @@ def diagnose(fe, o, nL, side):
         print(msg, flush=True)
 
 
+def fuzz_matchers(rng, fm, oL, k, kl, dl, kr, dr, s, w, h, nL, tag):
+    """Random map points against the projection matchers (modes 0/1/2) and the LBA matcher; returns #mismatches."""
+    nl, nr = len(kl), len(kr)
+    if nl < 20 or nr < 20:
+        return 0
+    bad = 0
+    M = int(rng.integers(1, 600))
+    src = rng.integers(0, nl, M)
+    desc = dl[src].copy()
+    flip = rng.integers(0, 256, (M, 32)) < int(rng.integers(0, 40))
+    desc ^= (flip * rng.integers(1, 256, (M, 32))).astype(np.uint8)
+    jit = float(rng.choice([0.5, 2.0, 6.0]))
+    predL = (np.stack([kl["x"][src], kl["y"][src]], 1) + rng.normal(0, jit, (M, 2))).astype(np.float32)
+    predR = (predL - np.array([float(rng.integers(0, 30)), 0], np.float32)).astype(np.float32)
+    if rng.random() < 0.3:
+        predL[rng.random(M) < 0.1] = -5.0          # out-of-frame predictions
+    lv = lambda: np.clip(kl["octave"][src] + rng.integers(-1, 2, M), 0, nL - 1).astype(np.int32)
+    mps = dict(desc=desc, predL=predL, predR=predR, scaleLevelL=lv(), scaleLevelR=lv(),
+               inFrame=(rng.random(M) < 0.9).astype(np.uint8), inFrameR=(rng.random(M) < 0.8).astype(np.uint8))
+    rad = float(rng.choice([1.0, 3.0, 8.0, 20.0, 120.0]))
+    for mode in (0, 1, 2):
+        mL = np.full(nl, -1, np.int32); mR = np.full(nr, -1, np.int32); mt = np.full((M, 2), -1, np.int32)
+        pre = rng.random(nl) < 0.1
+        mL[pre] = 7
+        if mode != 2:
+            mt[rng.random(M) < 0.1] = [3, -1]
+        a = [mL.copy(), mR.copy(), mt.copy()]; b = [mL.copy(), mR.copy(), mt.copy()]
+        if mode == 0:
+            n1 = fm.matchByProjectionRPred(mps, 0, a[0], a[1], a[2], rad)
+            n2 = cpu_ref.match_projection(oL, 0, mps, kl, dl, kr, dr, s["leftIdxs"], s["rightIdxs"], w, h, rad, b[0], b[1], b[2])
+        elif mode == 1:
+            n1 = fm.matchByProjectionMono(mps, 0, a[0], a[2], rad)
+            n2 = cpu_ref.match_projection(oL, 1, mps, kl, dl, None, None, None, None, w, h, rad, b[0], None, b[2])
+        else:
+            last = dict(desc=desc, predL=predL, scaleLevelL=mps["scaleLevelL"])
+            n1 = fm.matchByRadius(last, 0, a[0], a[2], rad)
+            n2 = cpu_ref.match_projection(oL, 2, last, kl, dl, None, None, None, None, w, h, rad, b[0], None, b[2])
+        if n1 != n2 or not all(np.array_equal(x, y) for x, y in zip(a, b)):
+            bad += 1
+            print("MISMATCH matcher mode", mode, tag, f"M {M} rad {rad} n {n1}/{n2}", flush=True)
+    pts = dict(desc=desc, predL=predL, predR=predR, predScale=mps["scaleLevelL"],
+               lastL=(predL + rng.normal(0, 12, (M, 2))).astype(np.float32), lastR=(predR + rng.normal(0, 12, (M, 2))).astype(np.float32))
+    unF = np.where(rng.random(nl) < 0.2, 5, -1).astype(np.int32); unFR = np.where(rng.random(nr) < 0.2, 5, -1).astype(np.int32)
+    n1, o1 = fm.matchByProjectionRPredLBA(pts, kl, dl, kr, dr, s["leftIdxs"], s["rightIdxs"], unF, unFR, w, h, rad)
+    n2, o2 = cpu_ref.match_lba(oL, pts, kl, dl, kr, dr, s["leftIdxs"], s["rightIdxs"], unF, unFR, w, h, rad)
+    if n1 != n2 or not np.array_equal(o1, o2):
+        bad += 1
+        print("MISMATCH matcher LBA", tag, f"M {M} rad {rad} n {n1}/{n2}", flush=True)
+    return bad
+
+
 def main():
     iters = int(sys.argv[1]) if len(sys.argv) > 1 else 100
     rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
@@ -82,46 +133,60 @@ def main():
     bad = 0
     t0 = time.time()
     for it in range(iters):
-        w = int(rng.integers(120, 1400)); h = int(rng.integers(100, 900))
+        w = int(rng.integers(90, 1400)); h = int(rng.integers(80, 900))
         nL = int(rng.integers(1, 11)); scale = float(rng.choice([1.1, 1.2, 1.25, 1.3, 1.5, 2.0]))
-        while min(w, h) / scale ** (nL - 1) < 2 * 19 + 40:   # the coarsest level must keep a few cells
+        edge = int(rng.choice([19, 19, 19, 22, 31]))
+        while nL > 1 and min(w, h) / scale ** (nL - 1) < 2 * edge + 36:   # the coarsest level must keep one 35-px cell
             nL -= 1
         nL = max(nL, 1)
         nF = int(rng.choice([50, 200, 500, 1000, 2000, 5000]))
-        edge = int(rng.choice([19, 19, 19, 22, 31]))
         maxF = int(rng.integers(5, 60)); minF = int(rng.integers(1, maxF + 1))
         kind = str(rng.choice(KINDS)); disp = int(rng.integers(0, 40))
-        L = make_image(rng, kind, w + disp, h)
-        R = np.ascontiguousarray(L[:, disp:disp + w]) if disp else L.copy()
-        L = np.ascontiguousarray(L[:, :w])
-        if rng.random() < 0.5:
-            R = np.clip(R.astype(np.int32) + rng.integers(-2, 3, R.shape), 0, 255).astype(np.uint8)
-        tag = f"it {it}: {w}x{h} nF {nF} nL {nL} scale {scale} edge {edge} fast {maxF}/{minF} {kind} disp {disp}"
+        B = int(rng.choice([1, 1, 1, 2, 5]))
+        Ls, Rs = [], []
+        for f in range(B):
+            L = make_image(rng, kind if f == 0 else str(rng.choice(KINDS)), w + disp, h)
+            R = np.ascontiguousarray(L[:, disp:disp + w]) if disp else L.copy()
+            L = np.ascontiguousarray(L[:, :w])
+            if rng.random() < 0.5:
+                R = np.clip(R.astype(np.int32) + rng.integers(-2, 3, R.shape), 0, 255).astype(np.uint8)
+            Ls.append(L); Rs.append(R)
+        tag = f"it {it}: {w}x{h} x{B} nF {nF} nL {nL} scale {scale} edge {edge} fast {maxF}/{minF} {kind} disp {disp}"
         if only is not None and it not in only:
             continue
         try:
-            feL = gvs.FeatureExtractor(nF, nL, scale, edge, 31, maxF, minF, width=w, height=h, max_images=1)
-            feR = gvs.FeatureExtractor(nF, nL, scale, edge, 31, maxF, minF, width=w, height=h, max_images=1)
+            feL = gvs.FeatureExtractor(nF, nL, scale, edge, 31, maxF, minF, width=w, height=h, max_images=B)
+            feR = gvs.FeatureExtractor(nF, nL, scale, edge, 31, maxF, minF, width=w, height=h, max_images=B)
             fm = gvs.FeatureMatcher(300.0, 0.2, feL, feR, h)
-            fm.track_stereo_batch(L[None], R[None])
-            k = gvs.tracked_keys(fm, 0, w, h)
+            fm.track_stereo_batch(np.stack(Ls), np.stack(Rs))
+            ks = [gvs.tracked_keys(fm, f, w, h) for f in range(B)]
         except gvs.GvsError as e:
-            if "capacity" in str(e).lower():
-                print("CAPACITY", tag, e, flush=True)
+            if "overflow" in str(e).lower() or "taller than 8x" in str(e):   # documented limits, loud
+                print("LIMIT", tag, e, flush=True)
                 continue
             print("ERROR", tag, e, flush=True); bad += 1
             continue
-        oL, oR = cpu_ref.Extractor(nF, nL, scale, edge, 31, maxF, minF), cpu_ref.Extractor(nF, nL, scale, edge, 31, maxF, minF)
-        kl, dl = oL.extractKeysNew(L); kr, dr = oR.extractKeysNew(R)
-        s = cpu_ref.stereo_match(oL, oR, 300.0, 0.2, h, kl, dl, kr, dr)
-        ok = same_keys(k.keyPoints, kl) and same_keys(k.rightKeyPoints, kr) and np.array_equal(k.Desc, dl) and np.array_equal(k.rightDesc, dr)
-        ok2 = ok and all(np.array_equal(getattr(k, a), s[a]) for a in ("rightIdxs", "leftIdxs", "estimatedDepth", "close"))
-        if not ok2:
-            bad += 1
-            print("MISMATCH", "extract" if not ok else "stereo", tag, f"gpu {len(k.keyPoints)}/{len(k.rightKeyPoints)} oracle {len(kl)}/{len(kr)}", flush=True)
-            if only is not None:
-                diagnose(feL, oL, nL, "L"); diagnose(feR, oR, nL, "R")
-        elif it % 10 == 0:
+        ok2 = True
+        for f in range(B):
+            L, R, k = Ls[f], Rs[f], ks[f]
+            oL, oR = cpu_ref.Extractor(nF, nL, scale, edge, 31, maxF, minF), cpu_ref.Extractor(nF, nL, scale, edge, 31, maxF, minF)
+            kl, dl = oL.extractKeysNew(L); kr, dr = oR.extractKeysNew(R)
+            s = cpu_ref.stereo_match(oL, oR, 300.0, 0.2, h, kl, dl, kr, dr)
+            ok = same_keys(k.keyPoints, kl) and same_keys(k.rightKeyPoints, kr) and np.array_equal(k.Desc, dl) and np.array_equal(k.rightDesc, dr)
+            okf = ok and all(np.array_equal(getattr(k, a), s[a]) for a in ("rightIdxs", "leftIdxs", "estimatedDepth", "close"))
+            if okf:
+                gl = cpu_ref.assign_grid(kl, w, h); gr = cpu_ref.assign_grid(kr, w, h)
+                okf = all(np.array_equal(k.lkeyGrid[a], gl[a]) and np.array_equal(k.rkeyGrid[a], gr[a]) for a in ("start", "items"))
+                ok = okf or ok
+            if not okf:
+                ok2 = False
+                bad += 1
+                print("MISMATCH", "extract" if not ok else "stereo/grid", f"frame {f}", tag, f"gpu {len(k.keyPoints)}/{len(k.rightKeyPoints)} oracle {len(kl)}/{len(kr)}", flush=True)
+                if only is not None and B == 1:
+                    diagnose(feL, oL, nL, "L"); diagnose(feR, oR, nL, "R")
+            elif f == 0:
+                bad += fuzz_matchers(rng, fm, oL, k, kl, dl, kr, dr, s, w, h, nL, tag)
+        if ok2 and it % 10 == 0:
             print("ok", tag, f"keys {len(kl)}/{len(kr)} matches {(s['rightIdxs'] >= 0).sum()}", flush=True)
     print(f"{iters} cases, {bad} bad, {time.time() - t0:.0f} s")
     sys.exit(1 if bad else 0)
