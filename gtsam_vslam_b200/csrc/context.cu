@@ -24,7 +24,13 @@ static inline int cvRoundF(float v) { return (int)lrintf(v); }
 template <typename T>
 static cudaError_t devAlloc(T** p, size_t count) {
     *p = nullptr;
-    return cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(count, 1) * sizeof(T));
+    const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), bytes);
+    // debugging aid (compute-sanitizer's initcheck by other means): GVS_POISON=1 fills every fresh allocation with 0xA5 so that
+    // a kernel relying on cudaMalloc returning zeros shows up as a parity failure in the tests / tools/fuzz_parity.py
+    static const bool poison = getenv("GVS_POISON") != nullptr;
+    if (e == cudaSuccess && poison) { e = cudaMemset(*p, 0xA5, bytes); cudaDeviceSynchronize(); }  // (handles use non-blocking streams)
+    return e;
 }
 
 }  // namespace gvs
@@ -472,6 +478,8 @@ int gvs_extractor_create(gvs_extractor** out, const gvs_extractor_params* params
     GVS_TRY(cudaMallocHost(reinterpret_cast<void**>(&fe->hStatus), sizeof(int)));
     *fe->hStatus = 0;
     std::memset(fe->hOff, 0, sizeof(int) * (B + 1));
+    // the initialising memsets above ran on the legacy default stream, which the handle's non-blocking streams do not wait for
+    GVS_TRY(cudaDeviceSynchronize());
 #undef GVS_TRY
     *out = fe;
     return GVS_OK;
