@@ -144,13 +144,12 @@ fast_cells_kernel(const __grid_constant__ Geometry g, const uint8_t* __restrict_
     const int gW = lv.gridW;
     // unit words: 4-px aligned words covering [X0, X1); tile word 0 is the word left of unit 0
     const int xu = X0 & ~3;                 // x of unit 0
-    const int nW = (X1 - xu + 3) >> 2;      // number of unit words
+    // number of unit words; at least 2: i / 1 has no 32-bit magic number, and a narrow last cell can leave a single word (the
+    // extra word lies inside the row -- X1 <= w - edge -- and is fully masked out)
+    const int nW = max((X1 - xu + 3) >> 2, 2);
     const int tw = nW + 2, th = rows + 6;   // tile words per row / rows
-    // i / d = umulhi(i, 2^32 / d + 1) for the small i used here; d = 1 has no 32-bit magic number and a narrow last cell can
-    // leave a single unit word (nW == 1), which is handled apart (kOne)
-    const unsigned magicT = 0xffffffffu / (unsigned)tw + 1u;
-    const bool kOne = nW == 1;
-    const unsigned magicU = kOne ? 0u : 0xffffffffu / (unsigned)nW + 1u;
+    // i / d = umulhi(i, 2^32 / d + 1) for the small i used here (d >= 2)
+    const unsigned magicT = 0xffffffffu / (unsigned)tw + 1u, magicU = 0xffffffffu / (unsigned)nW + 1u;
 
     // ---- 1. stage the image tile (x from xu-4, y from y0-3), zero the score tile, build the per-unit byte masks
     const uint8_t* src = levelPtr(slab, g, img, it.level) + (size_t)(y0 - 3) * lv.pitch + (xu - 4);
@@ -191,7 +190,7 @@ fast_cells_kernel(const __grid_constant__ Geometry g, const uint8_t* __restrict_
         const int i = base + tid;
         bool p0 = false, p1 = false;
         if (i < nUnits) {
-            const int ry = kOne ? i : (int)__umulhi((unsigned)i, magicU), j = i - ry * nW;
+            const int ry = (int)__umulhi((unsigned)i, magicU), j = i - ry * nW;
             const unsigned* p = tile + (ry + 3) * L.tileWords + j;
             const unsigned c = p[1];
             const unsigned up = p[1 - 3 * L.tileWords], dn = p[1 + 3 * L.tileWords];
@@ -221,7 +220,7 @@ fast_cells_kernel(const __grid_constant__ Geometry g, const uint8_t* __restrict_
     for (int q = tid; q < n0 + n1; q += 256) {
         const bool second = q >= n0;
         const int i = second ? queue[L.queueCap + q - n0] : queue[q];
-        const int ry = kOne ? i : (int)__umulhi((unsigned)i, magicU), j = i - ry * nW;
+        const int ry = (int)__umulhi((unsigned)i, magicU), j = i - ry * nW;
         unsigned W[7][3];
 #pragma unroll
         for (int r = 0; r < 7; r++) {
@@ -236,7 +235,7 @@ fast_cells_kernel(const __grid_constant__ Geometry g, const uint8_t* __restrict_
 
     // ---- 3. strict local maxima inside each cell, four pixels at a time -> per-cell lists
     for (int i = tid; i < nW * rows; i += 256) {
-        const int ry = kOne ? i : (int)__umulhi((unsigned)i, magicU), j = i - ry * nW;
+        const int ry = (int)__umulhi((unsigned)i, magicU), j = i - ry * nW;
         const unsigned* sp = score + (ry + 1) * L.scoreWords + j + 1;
         const unsigned c = sp[0];
         if (c == 0) continue;

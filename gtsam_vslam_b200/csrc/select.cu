@@ -350,8 +350,9 @@ __device__ int sscPassWarp(const unsigned* xy, const IdxT* sorted, int n, int wi
     const int bmWords = (ncc * ncr + 31) >> 5;
     for (int i = lane; i < bmWords; i += 32) bitmap[i] = 0;
     __syncwarp();
-    // exact while 2*coord*width < 2^32; width 1 has no 32-bit magic number (2^32 + 1) and is handled apart below
-    const unsigned magic = (unsigned)(0x100000000ull / (unsigned)max(width, 2)) + 1u;
+    // floor(v / width) = umulhi(v + 1, floor((2^32 - 1) / width)) for every width >= 1 while (v + 1) * width < 2^32
+    // (round-down magic number; unlike the round-up form it also exists for width 1)
+    const unsigned magic = 0xffffffffu / (unsigned)width;
     int cnt = 0;
     for (int base = 0; base < n; base += 32) {
         const int i = base + lane;
@@ -359,9 +360,8 @@ __device__ int sscPassWarp(const unsigned* xy, const IdxT* sorted, int n, int wi
         bool active = false;
         if (i < n) {
             const unsigned q = xy[sorted[i]];
-            const unsigned x2 = 2 * (q & 0xfff), y2 = 2 * ((q >> 12) & 0xfff);
-            col = width == 1 ? (int)x2 : (int)__umulhi(x2, magic);
-            row = width == 1 ? (int)y2 : (int)__umulhi(y2, magic);
+            col = (int)__umulhi(2 * (q & 0xfff) + 1, magic);
+            row = (int)__umulhi(2 * ((q >> 12) & 0xfff) + 1, magic);
             const int bit = row * ncc + col;
             active = !((bitmap[bit >> 5] >> (bit & 31)) & 1);
         }
