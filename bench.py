@@ -276,35 +276,34 @@ def main():
     feL.set_stream(None); feR.set_stream(None)
 
     # ---- end to end through the public API: pinned host images in, all results back on the host
-    # The public API is used the way a throughput caller would: the batch is cut into `chunks` sub-batches, each on its own
-    # pair of extractor handles + matcher (own CUDA streams), all tracks are issued first and the downloads follow, so
-    # that the host->device copy of chunk k+1 and the device->host copy of chunk k-1 overlap the kernels of chunk k.
+    # The public API is used the way a throughput caller would: gvs_pipeline (include/gvs.h; api.StereoPipeline) with `chunks`
+    # slots, the batch cut into `chunks` tickets.  All tickets are submitted first and collected in order, so that the
+    # host->device copy of ticket k+1 and the device->host copy of ticket k-1 overlap the kernels of ticket k.
     chunks = max(1, min(args.e2e_chunks, F))
     while F % chunks:
         chunks -= 1
     Fc = F // chunks
     pin = lambda n, dt: torch.empty(n, dtype=dt).pin_memory().numpy()
-    pipes = []
-    for c in range(chunks):
-        ca = dict(fe_args, max_images=Fc)
-        cL, cR = gvs.FeatureExtractor(**ca), gvs.FeatureExtractor(**ca)
-        cm = gvs.FeatureMatcher(cfg["fx"], cfg["baseline"], cL, cR, h)
-        cap = Fc * cL.cap_per_image
-        pipes.append((cL, cR, cm, dict(kl=pin(cap * 28, torch.uint8).view(gvs.KEYPOINT_DTYPE), kr=pin(cap * 28, torch.uint8).view(gvs.KEYPOINT_DTYPE),
-                                       dl=pin(cap * 32, torch.uint8), dr=pin(cap * 32, torch.uint8), ri=pin(cap, torch.int32),
-                                       li=pin(cap, torch.int32), de=pin(cap, torch.float32), cl=pin(cap, torch.uint8))))
+    pipe = gvs.StereoPipeline(cfg["fx"], cfg["baseline"], width=w, height=h, frames_per_slot=Fc, n_slots=chunks,
+                              nFeatures=cfg["n_features"], nLevels=cfg["n_levels"])
+    cap = Fc * feL.cap_per_image
+    bufs = [dict(kl=pin(cap * 28, torch.uint8).view(gvs.KEYPOINT_DTYPE), kr=pin(cap * 28, torch.uint8).view(gvs.KEYPOINT_DTYPE),
+                 dl=pin(cap * 32, torch.uint8), dr=pin(cap * 32, torch.uint8), ri=pin(cap, torch.int32),
+                 li=pin(cap, torch.int32), de=pin(cap, torch.float32), cl=pin(cap, torch.uint8)) for _ in range(chunks)]
     npL, npR = hL.numpy(), hR.numpy()
+    e2e_launches = [0]
 
     def step_e2e():
-        for c, (cL, cR, cm, b) in enumerate(pipes):
-            cm.track_stereo_batch(npL[c * Fc:(c + 1) * Fc], npR[c * Fc:(c + 1) * Fc])
+        tickets = [pipe.submit(npL[c * Fc:(c + 1) * Fc], npR[c * Fc:(c + 1) * Fc]) for c in range(chunks)]
         nbytes, tl, tr, tm = 0, 0, 0, 0
-        for cL, cR, cm, b in pipes:
-            nl = cL.download_into(0, Fc, b["kl"], b["dl"])
-            nr = cR.download_into(0, Fc, b["kr"], b["dr"])
-            cm.stereo_download_into(0, Fc, b["ri"], b["li"], b["de"], b["cl"])
+        for t, b in zip(tickets, bufs):
+            offL, offR = pipe.wait(t, Fc)
+            nl, nr = int(offL[-1]), int(offR[-1])
+            pipe.download_into(t, b["kl"], b["dl"], b["kr"], b["dr"], b["ri"], b["li"], b["de"], b["cl"])
             nbytes += 2 * 4 * (Fc + 1) + (nl + nr) * 60 + nl * 9 + nr * 4
             tl += nl; tr += nr; tm += int((b["ri"][:nl] >= 0).sum())
+            e2e_launches[0] = pipe.slot_launch_count(t)
+            pipe.release(t)
         return nbytes, (tl, tr, tm)
 
     for _ in range(2):
@@ -350,8 +349,8 @@ def main():
                    "keypoints_per_frame": [counts[0] / F, counts[1] / F], "stereo_matches_per_frame": counts[2] / F},
         "e2e": {"value": world * F / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(2 * F * w * h), "d2h_bytes_per_step": int(d2h),
-                "how": f"pinned host images -> gvs_track_stereo_batch_host -> keypoints, descriptors, stereo arrays back in pinned host "
-                       f"memory; {chunks} sub-batches of {Fc} frames pipelined over separate handles; wall clock around the calls"},
+                "how": f"pinned host images -> gvs_pipeline_submit / wait / download ({chunks} tickets of {Fc} frames over {chunks} slots) -> "
+                       f"keypoints, descriptors, stereo arrays back in pinned host memory; wall clock around the calls"},
         "gpu_launches": int(n_launch),
         "stage_ms": {k: round(v, 4) for k, v in stage_acc.items()},
         "stage_ms_note": f"per step, left+right, each kernel alone on one stream (sum {serial_ms:.3f} ms); the timed region overlaps "

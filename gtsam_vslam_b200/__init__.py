@@ -3,8 +3,8 @@
 The product is the CUDA library csrc/ -> libgvs.so behind the C ABI of include/gvs.h; this package is the thin
 host-side mirror of the reference's FeatureExtractor / FeatureMatcher / FeatureTracker interfaces.
 """
-from .api import (FeatureExtractor, FeatureMatcher, GvsError, KEYPOINT_DTYPE, LIB_PATH, SYMBOLS, StageTimes, TrackedKeys,
+from .api import (FeatureExtractor, FeatureMatcher, GvsError, KEYPOINT_DTYPE, LIB_PATH, SYMBOLS, StageTimes, StereoPipeline, TrackedKeys,
                   device_count, extractORBAndStereoMatch, load_library, tracked_keys)
 
 __all__ = ["FeatureExtractor", "FeatureMatcher", "GvsError", "KEYPOINT_DTYPE", "LIB_PATH", "SYMBOLS", "StageTimes",
-           "TrackedKeys", "device_count", "extractORBAndStereoMatch", "load_library", "tracked_keys"]
+           "StereoPipeline", "TrackedKeys", "device_count", "extractORBAndStereoMatch", "load_library", "tracked_keys"]

@@ -34,6 +34,8 @@ SYMBOLS = [
     "gvs_track_stereo_batch_resident", "gvs_matcher_sync", "gvs_matcher_set_stream", "gvs_match_projection", "gvs_descriptor_distance",
     "gvs_match_projection_lba", "gvs_median_descriptor", "gvs_project_mappoints", "gvs_extractor_enable_timing", "gvs_extractor_stage_times", "gvs_matcher_launch_count",
     "gvs_extractor_launch_count",
+    "gvs_pipeline_create", "gvs_pipeline_destroy", "gvs_pipeline_submit", "gvs_pipeline_wait", "gvs_pipeline_download",
+    "gvs_pipeline_handles", "gvs_pipeline_release",
 ]
 
 
@@ -122,6 +124,14 @@ def load_library() -> C.CDLL:
     lib.gvs_extractor_stage_times.argtypes = [vp, C.POINTER(StageTimes)]
     lib.gvs_matcher_launch_count.argtypes = [vp, C.POINTER(C.c_int64)]
     lib.gvs_extractor_launch_count.argtypes = [vp, C.POINTER(C.c_int64)]
+    i64 = C.c_int64
+    lib.gvs_pipeline_create.argtypes = [C.POINTER(vp), C.POINTER(_Params), i32, i32, i32, i32, C.c_double, f32, i32]
+    lib.gvs_pipeline_destroy.argtypes = [vp]
+    lib.gvs_pipeline_submit.argtypes = [vp, vp, vp, C.c_size_t, i32, i32, C.POINTER(i64)]
+    lib.gvs_pipeline_wait.argtypes = [vp, i64, vp, vp]
+    lib.gvs_pipeline_download.argtypes = [vp, i64, vp, vp, i32, vp, vp, i32, vp, vp, vp, vp]
+    lib.gvs_pipeline_handles.argtypes = [vp, i64, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    lib.gvs_pipeline_release.argtypes = [vp, i64]
     _lib = lib
     return lib
 
@@ -460,6 +470,77 @@ class FeatureMatcher:
         out = np.zeros(len(a), np.int32)
         _check(self._lib.gvs_descriptor_distance(self.h, _p(a), _p(b), len(a), _p(out)))
         return out
+
+
+class StereoPipeline:
+    """gvs_pipeline (include/gvs.h): `n_slots` handle sets in a ring; `submit` is asynchronous, `wait` /
+    `download` collect a ticket, `release` frees its slot.  Ticket t uses slot t % n_slots."""
+
+    def __init__(self, fx: float, baseline: float, *, width: int, height: int, frames_per_slot: int = 1, n_slots: int = 2,
+                 nFeatures=2000, nLevels=8, imScale=1.2, edgeThreshold=19, patchSize=31, maxFastThreshold=20,
+                 minFastThreshold=7, device: int = 0):
+        self._lib = load_library()
+        self.width, self.height, self.frames_per_slot, self.n_slots = int(width), int(height), int(frames_per_slot), int(n_slots)
+        p = _Params(int(nFeatures), int(nLevels), float(imScale), int(edgeThreshold), int(patchSize), int(maxFastThreshold),
+                    int(minFastThreshold))
+        self.h = C.c_void_p()
+        _check(self._lib.gvs_pipeline_create(C.byref(self.h), C.byref(p), self.width, self.height, self.frames_per_slot,
+                                             self.n_slots, float(fx), float(baseline), int(device)))
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self._lib.gvs_pipeline_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def submit(self, left: np.ndarray, right: np.ndarray) -> int:
+        """left/right: (n, H, W) uint8, C-contiguous, ideally pinned; must stay alive until wait() returns."""
+        assert left.shape == right.shape and left.dtype == np.uint8 and left.flags.c_contiguous and right.flags.c_contiguous
+        n, h, w = left.shape
+        assert (h, w) == (self.height, self.width)
+        t = C.c_int64(-1)
+        _check(self._lib.gvs_pipeline_submit(self.h, _p(left), _p(right), w * h, w, n, C.byref(t)))
+        return t.value
+
+    def wait(self, ticket: int, n_frames: int):
+        offL = np.zeros(n_frames + 1, np.int32); offR = np.zeros(n_frames + 1, np.int32)
+        _check(self._lib.gvs_pipeline_wait(self.h, ticket, _p(offL), _p(offR)))
+        return offL, offR
+
+    def download_into(self, ticket: int, kl, dl, kr, dr, ridx, lidx, dep, cl) -> None:
+        """Dense results of the ticket into caller arrays (pinned for speed); capacities are taken from the arrays."""
+        _check(self._lib.gvs_pipeline_download(self.h, ticket, _p(kl), _p(dl), len(kl), _p(kr), _p(dr), len(kr),
+                                               _p(ridx), _p(lidx), _p(dep), _p(cl)))
+
+    def download(self, ticket: int, n_frames: int):
+        offL, offR = self.wait(ticket, n_frames)
+        nl, nr = int(offL[-1]), int(offR[-1])
+        kl = np.zeros(max(nl, 1), KEYPOINT_DTYPE); dl = np.zeros((max(nl, 1), 32), np.uint8)
+        kr = np.zeros(max(nr, 1), KEYPOINT_DTYPE); dr = np.zeros((max(nr, 1), 32), np.uint8)
+        ridx = np.zeros(max(nl, 1), np.int32); lidx = np.zeros(max(nr, 1), np.int32)
+        dep = np.zeros(max(nl, 1), np.float32); cl = np.zeros(max(nl, 1), np.uint8)
+        self.download_into(ticket, kl, dl, kr, dr, ridx, lidx, dep, cl)
+        return dict(offL=offL, offR=offR, kpL=kl[:nl], descL=dl[:nl], kpR=kr[:nr], descR=dr[:nr], rightIdxs=ridx[:nl],
+                    leftIdxs=lidx[:nr], estimatedDepth=dep[:nl], close=cl[:nl].astype(bool))
+
+    def release(self, ticket: int) -> None:
+        _check(self._lib.gvs_pipeline_release(self.h, ticket))
+
+    def slot_launch_count(self, ticket: int) -> int:
+        fl, fr, fm = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        _check(self._lib.gvs_pipeline_handles(self.h, ticket, C.byref(fl), C.byref(fr), C.byref(fm)))
+        tot = 0
+        for fn, hnd in ((self._lib.gvs_extractor_launch_count, fl), (self._lib.gvs_extractor_launch_count, fr),
+                        (self._lib.gvs_matcher_launch_count, fm)):
+            v = C.c_int64(0)
+            _check(fn(hnd, C.byref(v)))
+            tot += v.value
+        return tot
 
 
 def extractORBAndStereoMatch(fm: FeatureMatcher, leftIm: np.ndarray, rightIm: np.ndarray) -> TrackedKeys:

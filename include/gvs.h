@@ -244,6 +244,31 @@ int gvs_median_descriptor(gvs_matcher* fm, const uint8_t* descs, const int32_t* 
  * (host arrays; computed on the device). */
 int gvs_descriptor_distance(gvs_matcher* fm, const uint8_t* a, const uint8_t* b, int n, int32_t* dist);
 
+/* ---- frame pipeline ---------------------------------------------------------------------------
+ * The reference tracks one frame at a time, synchronously (System::trackNewImage -> FeatureTracker::TrackImageT ->
+ * extractORBAndStereoMatch, src/FeatureTracker.cpp:1120-1145 and :56-70).  A gvs_pipeline is a ring of n_slots independent
+ * handle sets (two extractors + one matcher, own CUDA streams), each taking up to frames_per_slot stereo frames per ticket:
+ * while the host collects ticket t, tickets t+1 ... upload and compute.  Ticket t uses slot t % n_slots; a slot is free again
+ * after gvs_pipeline_release.  Not thread safe (one submitting thread), like the reference's tracking thread. */
+typedef struct gvs_pipeline gvs_pipeline;
+int gvs_pipeline_create(gvs_pipeline** out, const gvs_extractor_params* params, int width, int height, int frames_per_slot,
+                        int n_slots, double fx, float baseline, int device);
+int gvs_pipeline_destroy(gvs_pipeline* p);
+/* Asynchronous gvs_track_stereo_batch_host on the next slot (host images should be pinned and must stay valid until
+ * gvs_pipeline_wait returns).  GVS_ERR_STATE if that slot still holds an unreleased ticket. */
+int gvs_pipeline_submit(gvs_pipeline* p, const uint8_t* left, const uint8_t* right, size_t image_stride, int row_stride,
+                        int n_frames, int64_t* ticket);
+/* Blocks until the ticket is computed; offsets (n_frames + 1 entries each, may be NULL) as gvs_extract_offsets.  Device-side
+ * failures of the ticket (GVS_ERR_CAPACITY ...) are returned here. */
+int gvs_pipeline_wait(gvs_pipeline* p, int64_t ticket, int32_t* left_offsets, int32_t* right_offsets);
+/* Results of all frames of the ticket, dense (as gvs_extract_download / gvs_stereo_download).  Any pointer may be NULL. */
+int gvs_pipeline_download(gvs_pipeline* p, int64_t ticket, gvs_keypoint* kp_left, uint8_t* desc_left, int cap_left,
+                          gvs_keypoint* kp_right, uint8_t* desc_right, int cap_right, int32_t* right_idxs, int32_t* left_idxs,
+                          float* estimated_depth, uint8_t* close);
+/* The slot's handles, e.g. for gvs_match_projection / gvs_grid_download against the ticket's frames (valid until release). */
+int gvs_pipeline_handles(gvs_pipeline* p, int64_t ticket, gvs_extractor** fe_left, gvs_extractor** fe_right, gvs_matcher** fm);
+int gvs_pipeline_release(gvs_pipeline* p, int64_t ticket);
+
 /* ------------------------------------------------------------------ measurement --------------------- */
 
 /* Launch counters and device timings of the last batch, for bench.py (gpu_launches, per-stage ms). */

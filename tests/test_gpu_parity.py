@@ -518,3 +518,41 @@ def test_every_width_alignment_of_the_last_cell():
         x, y, s = fe.level_candidates(0, 0); c = o.level_keys(0, False)
         assert np.array_equal(x, c["x"]) and np.array_equal(y, c["y"]) and np.array_equal(s, c["response"].astype(np.int32)), w
         _assert_keys(gk, gd, ok, od)
+
+
+def test_frame_pipeline_tickets_and_slots():
+    """more tickets than slots through gvs_pipeline; every ticket equals the oracle; slot discipline errors."""
+    cfg = synth.CONFIGS["small"]
+    w, h = cfg["width"], cfg["height"]
+    pipe = gvs.StereoPipeline(cfg["fx"], cfg["baseline"], width=w, height=h, frames_per_slot=2, n_slots=3,
+                              nFeatures=cfg["n_features"], nLevels=cfg["n_levels"])
+    batches = [synth.stereo_batch(w, h, cfg["disparity"], [60 + 2 * t, 61 + 2 * t][: 1 + t % 2]) for t in range(7)]
+    tickets = []
+
+    def collect(t):
+        L, R = batches[t]
+        n = len(L)
+        r = pipe.download(t, n)
+        for f in range(n):
+            _, _, kl, dl, kr, dr, s = _oracle_frame(cfg, L[f], R[f])
+            a, b = r["offL"][f], r["offL"][f + 1]; c, d = r["offR"][f], r["offR"][f + 1]
+            _assert_keys(r["kpL"][a:b], r["descL"][a:b], kl, dl)
+            _assert_keys(r["kpR"][c:d], r["descR"][c:d], kr, dr)
+            assert np.array_equal(r["rightIdxs"][a:b], s["rightIdxs"]) and np.array_equal(r["leftIdxs"][c:d], s["leftIdxs"])
+            assert np.array_equal(r["estimatedDepth"][a:b], s["estimatedDepth"]) and np.array_equal(r["close"][a:b], s["close"])
+        pipe.release(t)
+
+    for t in range(len(batches)):
+        if t >= 3:
+            collect(t - 3)                      # free the slot this ticket needs
+        assert pipe.submit(*batches[t]) == t
+        tickets.append(t)
+    with pytest.raises(gvs.GvsError):           # all three slots busy
+        pipe.submit(*batches[0])
+    for t in range(len(batches) - 3, len(batches)):
+        collect(t)
+    with pytest.raises(gvs.GvsError):           # released ticket
+        pipe.wait(0, 1)
+    with pytest.raises(gvs.GvsError):           # more frames than a slot holds
+        pipe.submit(*synth.stereo_batch(w, h, cfg["disparity"], [1, 2, 3]))
+    pipe.close()
