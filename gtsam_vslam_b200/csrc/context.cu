@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <mutex>
 
 #include "common.cuh"
@@ -60,6 +61,9 @@ struct gvs_extractor {
     unsigned short* xBase = nullptr;  // ... 4-byte aligned source offset of the 12-byte window
     FastItem* fastItems = nullptr;
     int nFastItems = 0;
+    // CUDA graphs of the extraction pipeline for small batches (latency mode): one instantiated graph per batch size
+    std::map<int, cudaGraphExec_t> graphs;
+    std::map<int, int> graphLaunches;
     BlurItem* blurItems = nullptr;
     int nBlurItems = 0;
     CandRec* recs = nullptr;
@@ -283,6 +287,7 @@ void destroyExtractor(gvs_extractor* fe) {
     cudaFree(fe->workCounter); cudaFree(fe->status); cudaFree(fe->kps); cudaFree(fe->desc); cudaFree(fe->auxKey);
     if (fe->hOff) cudaFreeHost(fe->hOff);
     if (fe->hStatus) cudaFreeHost(fe->hStatus);
+    for (auto& kv : fe->graphs) cudaGraphExecDestroy(kv.second);
     if (fe->doneEvent) cudaEventDestroy(fe->doneEvent);
     if (fe->evPyr) cudaEventDestroy(fe->evPyr);
     if (fe->evBlur) cudaEventDestroy(fe->evBlur);
@@ -292,10 +297,9 @@ void destroyExtractor(gvs_extractor* fe) {
     delete fe;
 }
 
-// the whole extraction pipeline for image slots [0, n) (src/FeatureExtractor.cpp:481-533 for each image)
-int runExtract(gvs_extractor* fe, int n) {
+// the whole extraction pipeline for image slots [0, n) (src/FeatureExtractor.cpp:481-533 for each image): stream work only
+static int enqueueExtract(gvs_extractor* fe, int n, cudaStream_t s) {
     const Geometry& g = fe->g;
-    cudaStream_t s = fe->stream;
     fe->launches = 0;
     const bool T = fe->timing;
     GVS_CUDA_OK(cudaMemsetAsync(fe->status, 0, sizeof(int), s));
@@ -312,9 +316,48 @@ int runExtract(gvs_extractor* fe, int n) {
     launchDescribeFused(g, fe->slab, n, fe->kept, fe->keptCnt, fe->imgOff, fe->kps, fe->desc, fe->auxKey, fe->momentsDbg,
                         fe->totalCap, s, &fe->launches);
     if (T) cudaEventRecord(fe->ev[5], s);
-    fe->blurValid = false;
     GVS_CUDA_OK(cudaMemcpyAsync(fe->hOff, fe->imgOff, sizeof(int) * (n + 1), cudaMemcpyDeviceToHost, s));
     GVS_CUDA_OK(cudaMemcpyAsync(fe->hStatus, fe->status, sizeof(int), cudaMemcpyDeviceToHost, s));
+    return GVS_OK;
+}
+
+// Captured graphs freeze the kernel arguments: drop them when a lazily allocated debug tap changes a pointer.
+static void invalidateGraphs(gvs_extractor* fe) {
+    for (auto& kv : fe->graphs) cudaGraphExecDestroy(kv.second);
+    fe->graphs.clear();
+    fe->graphLaunches.clear();
+}
+
+// Small batches are launch bound (13 launches per side for a frame that needs ~0.2 ms of kernels): the pipeline of a batch
+// size is captured once into a CUDA graph and replayed.  All kernel arguments are fixed per handle and batch size.
+constexpr int kGraphMaxImages = 8;
+
+int runExtract(gvs_extractor* fe, int n) {
+    cudaStream_t s = fe->stream;
+    static const bool noGraph = getenv("GVS_NO_GRAPH") != nullptr;
+    if (!fe->timing && !noGraph && n <= kGraphMaxImages) {
+        auto it = fe->graphs.find(n);
+        if (it == fe->graphs.end()) {
+            cudaGraph_t graph = nullptr;
+            GVS_CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+            const int rc = enqueueExtract(fe, n, s);
+            const cudaError_t e = cudaStreamEndCapture(s, &graph);
+            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+            GVS_CUDA_OK(e);
+            cudaGraphExec_t exec = nullptr;
+            const cudaError_t ei = cudaGraphInstantiate(&exec, graph, 0);
+            cudaGraphDestroy(graph);
+            GVS_CUDA_OK(ei);
+            it = fe->graphs.emplace(n, exec).first;
+            fe->graphLaunches[n] = fe->launches;
+        }
+        GVS_CUDA_OK(cudaGraphLaunch(it->second, s));
+        fe->launches = fe->graphLaunches[n];
+    } else {
+        const int rc = enqueueExtract(fe, n, s);
+        if (rc) return rc;
+    }
+    fe->blurValid = false;
     GVS_CUDA_OK(cudaEventRecord(fe->doneEvent, s));
     GVS_CUDA_OK(cudaGetLastError());
     fe->lastN = n;
@@ -694,6 +737,7 @@ int gvs_debug_level_candidates(gvs_extractor* fe, int image, int level, int32_t*
         // first use: allocate the tap and re-run the last batch so that it gets filled
         GVS_CUDA_OK(cudaStreamSynchronize(fe->stream));
         GVS_CUDA_OK(devAlloc(&fe->orderedDbg, (size_t)fe->maxImages * fe->g.candPerImage));
+        invalidateGraphs(fe);
         int rc = runExtract(fe, fe->lastN);
         if (rc) return rc;
     }
@@ -736,7 +780,10 @@ int gvs_debug_select(gvs_extractor* fe, int level, int n, const int32_t* x, cons
     GVS_CUDA_OK(cudaStreamSynchronize(s));
     const Geometry& g = fe->g;
     if (!fe->sortedDbg) GVS_CUDA_OK(devAlloc(&fe->sortedDbg, (size_t)fe->maxImages * g.candPerImage));
-    if (!fe->orderedDbg) GVS_CUDA_OK(devAlloc(&fe->orderedDbg, (size_t)fe->maxImages * g.candPerImage));
+    if (!fe->orderedDbg) {
+        GVS_CUDA_OK(devAlloc(&fe->orderedDbg, (size_t)fe->maxImages * g.candPerImage));
+        invalidateGraphs(fe);
+    }
     // all candidates in cell 0 with rank = input position, every other cell / level empty
     std::vector<CandRec> recs(std::max(n, 1));
     for (int i = 0; i < n; i++) {
