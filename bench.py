@@ -285,7 +285,7 @@ def main():
     Fc = F // chunks
     pin = lambda n, dt: torch.empty(n, dtype=dt).pin_memory().numpy()
     pipe = gvs.StereoPipeline(cfg["fx"], cfg["baseline"], width=w, height=h, frames_per_slot=Fc, n_slots=chunks,
-                              nFeatures=cfg["n_features"], nLevels=cfg["n_levels"])
+                              nFeatures=cfg["n_features"], nLevels=cfg["n_levels"], device=local)
     cap = Fc * feL.cap_per_image
     bufs = [dict(kl=pin(cap * 28, torch.uint8).view(gvs.KEYPOINT_DTYPE), kr=pin(cap * 28, torch.uint8).view(gvs.KEYPOINT_DTYPE),
                  dl=pin(cap * 32, torch.uint8), dr=pin(cap * 32, torch.uint8), ri=pin(cap, torch.int32),

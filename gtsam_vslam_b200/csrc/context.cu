@@ -20,6 +20,20 @@ int fail(int code, const char* what, const char* detail) {
     return code;
 }
 
+// Entry points run on the handle's device and leave the caller's current device as they found it (a caller such as PyTorch
+// resolves "cuda" to the current device).
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int device) {
+        int cur = -1;
+        if (cudaGetDevice(&cur) == cudaSuccess && cur != device) prev = cur;
+        cudaSetDevice(device);
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 static inline int cvRoundF(float v) { return (int)lrintf(v); }
 
 template <typename T>
@@ -279,7 +293,7 @@ void buildTaps(const gvs_extractor* fe, std::vector<ResizeTap>& taps, int nTaps)
 
 void destroyExtractor(gvs_extractor* fe) {
     if (!fe) return;
-    cudaSetDevice(fe->device);
+    DeviceGuard deviceGuard(fe->device);
     if (fe->ownStream) cudaStreamSynchronize(fe->ownStream);
     cudaFree(fe->slab); cudaFree(fe->blurSlab); cudaFree(fe->tight); cudaFree(fe->mapX); cudaFree(fe->mapY); cudaFree(fe->xWeights); cudaFree(fe->xSelectors); cudaFree(fe->xBase); cudaFree(fe->taps); cudaFree(fe->fastItems); cudaFree(fe->blurItems);
     cudaFree(fe->recs); cudaFree(fe->nCand); cudaFree(fe->cellCnt); cudaFree(fe->kept); cudaFree(fe->keptCnt);
@@ -367,7 +381,7 @@ int runExtract(gvs_extractor* fe, int n) {
 }
 
 int syncExtract(gvs_extractor* fe) {
-    GVS_CUDA_OK(cudaSetDevice(fe->device));
+    DeviceGuard deviceGuard(fe->device);
     GVS_CUDA_OK(cudaStreamSynchronize(fe->stream));
     if (fe->pending) {
         fe->pending = false;
@@ -425,7 +439,7 @@ int gvs_extractor_create(gvs_extractor** out, const gvs_extractor_params* params
         return fail(GVS_ERR_CUDA, "no CUDA device: this library has no CPU path");
     }
     if (device < 0 || device >= ndev) return fail(GVS_ERR_INVALID, "bad device index");
-    GVS_CUDA_OK(cudaSetDevice(device));
+    DeviceGuard deviceGuard(device);
     gvs_extractor* fe = new gvs_extractor();
     fe->device = device; fe->params = *params; fe->width = width; fe->height = height; fe->maxImages = max_images;
     const int nTaps = buildGeometry(fe);
@@ -556,7 +570,7 @@ int gvs_extractor_level_size(const gvs_extractor* fe, int level, int* width, int
 
 int gvs_extractor_set_stream(gvs_extractor* fe, void* cuda_stream) {
     if (!fe) return fail(GVS_ERR_INVALID, "null extractor");
-    GVS_CUDA_OK(cudaSetDevice(fe->device));
+    DeviceGuard deviceGuard(fe->device);
     GVS_CUDA_OK(cudaStreamSynchronize(fe->stream));
     fe->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : fe->ownStream;
     return GVS_OK;
@@ -573,7 +587,7 @@ int gvs_extractor_input(gvs_extractor* fe, uint8_t** dev, int* pitch, size_t* im
 int gvs_extract_batch_resident(gvs_extractor* fe, int n_images) {
     int rc = checkBatch(fe, n_images);
     if (rc) return rc;
-    GVS_CUDA_OK(cudaSetDevice(fe->device));
+    DeviceGuard deviceGuard(fe->device);
     return runExtract(fe, n_images);
 }
 
@@ -581,7 +595,7 @@ int gvs_extract_batch_host(gvs_extractor* fe, const uint8_t* images, size_t imag
     int rc = checkBatch(fe, n_images);
     if (rc) return rc;
     if (!images || row_stride < fe->width) return fail(GVS_ERR_INVALID, "bad image pointer / stride");
-    GVS_CUDA_OK(cudaSetDevice(fe->device));
+    DeviceGuard deviceGuard(fe->device);
     const LevelGeom& l0 = fe->g.lv[0];
     if (row_stride == fe->width && image_stride == (size_t)fe->width * fe->height) {
         // tightly packed batch: one contiguous DMA into a staging buffer, then a repack kernel into the pitched store
@@ -606,7 +620,7 @@ int gvs_extract_batch_host(gvs_extractor* fe, const uint8_t* images, size_t imag
 
 int gvs_extractor_set_rectify_maps(gvs_extractor* fe, const float* map_x, const float* map_y) {
     if (!fe) return fail(GVS_ERR_INVALID, "null extractor");
-    GVS_CUDA_OK(cudaSetDevice(fe->device));
+    DeviceGuard deviceGuard(fe->device);
     GVS_CUDA_OK(cudaStreamSynchronize(fe->stream));
     if (!map_x || !map_y) {
         cudaFree(fe->mapX); cudaFree(fe->mapY);
@@ -625,7 +639,7 @@ int gvs_extract_batch_host_raw(gvs_extractor* fe, const uint8_t* images, int cha
     int rc = checkBatch(fe, n_images);
     if (rc) return rc;
     if (!images || (channels != 1 && channels != 3)) return fail(GVS_ERR_INVALID, "raw images must be tightly packed, 1 or 3 channels");
-    GVS_CUDA_OK(cudaSetDevice(fe->device));
+    DeviceGuard deviceGuard(fe->device);
     const size_t per = (size_t)fe->width * fe->height * channels;
     const size_t need = (size_t)fe->maxImages * fe->width * fe->height * 3 + 16;
     if (fe->tightBytes < need) {
@@ -705,7 +719,7 @@ int gvs_extractor_launch_count(gvs_extractor* fe, int64_t* launches) {
 int gvs_debug_level_image(gvs_extractor* fe, int image, int level, int blurred, uint8_t* out) {
     if (!fe || !out || level < 0 || level >= fe->g.nLevels || image < 0 || image >= fe->maxImages)
         return fail(GVS_ERR_INVALID, "bad argument");
-    GVS_CUDA_OK(cudaSetDevice(fe->device));
+    DeviceGuard deviceGuard(fe->device);
     const LevelGeom& lv = fe->g.lv[level];
     if (blurred && !fe->blurValid && fe->lastN > 0) {  // cv::GaussianBlur of every level, dense (src/FeatureExtractor.cpp:512-515)
         if (!fe->blurSlab) GVS_CUDA_OK(devAlloc(&fe->blurSlab, (size_t)fe->maxImages * fe->g.slabBytes + 256));
@@ -732,7 +746,7 @@ static int unpackKeys(const std::vector<unsigned>& v, int n, int32_t* x, int32_t
 
 int gvs_debug_level_candidates(gvs_extractor* fe, int image, int level, int32_t* x, int32_t* y, int32_t* score, int cap, int* n) {
     if (!fe || !n || level < 0 || level >= fe->g.nLevels || image < 0 || image >= fe->lastN) return fail(GVS_ERR_INVALID, "bad argument");
-    GVS_CUDA_OK(cudaSetDevice(fe->device));
+    DeviceGuard deviceGuard(fe->device);
     if (!fe->orderedDbg) {
         // first use: allocate the tap and re-run the last batch so that it gets filled
         GVS_CUDA_OK(cudaStreamSynchronize(fe->stream));
@@ -756,7 +770,7 @@ int gvs_debug_level_candidates(gvs_extractor* fe, int image, int level, int32_t*
 
 int gvs_debug_level_kept(gvs_extractor* fe, int image, int level, int32_t* x, int32_t* y, int32_t* score, int cap, int* n) {
     if (!fe || !n || level < 0 || level >= fe->g.nLevels || image < 0 || image >= fe->lastN) return fail(GVS_ERR_INVALID, "bad argument");
-    GVS_CUDA_OK(cudaSetDevice(fe->device));
+    DeviceGuard deviceGuard(fe->device);
     int rc = syncExtract(fe);
     if (rc) return rc;
     const LevelGeom& lv = fe->g.lv[level];
@@ -775,7 +789,7 @@ int gvs_debug_select(gvs_extractor* fe, int level, int n, const int32_t* x, cons
     if (!fe || !x || !y || !score || !kept_idx || !n_kept || level < 0 || level >= fe->g.nLevels) return fail(GVS_ERR_INVALID, "bad argument");
     const LevelGeom& lv = fe->g.lv[level];
     if (n < 0 || n > lv.candCap || n > 65535) return fail(GVS_ERR_CAPACITY, "more candidates than the level's record buffer (or 65535)");
-    GVS_CUDA_OK(cudaSetDevice(fe->device));
+    DeviceGuard deviceGuard(fe->device);
     cudaStream_t s = fe->stream;
     GVS_CUDA_OK(cudaStreamSynchronize(s));
     const Geometry& g = fe->g;
@@ -837,7 +851,7 @@ int gvs_matcher_create(gvs_matcher** out, gvs_extractor* feL, gvs_extractor* feR
     if (feL->g.nLevels != feR->g.nLevels || feL->width != feR->width || feL->height != feR->height)
         return fail(GVS_ERR_INVALID, "left and right extractors differ in geometry");
     if (image_height < 1) return fail(GVS_ERR_INVALID, "bad image_height");
-    GVS_CUDA_OK(cudaSetDevice(feL->device));
+    DeviceGuard deviceGuard(feL->device);
     gvs_matcher* m = new gvs_matcher();
     m->L = feL; m->R = feR; m->fx = fx; m->baseline = baseline; m->imageHeight = image_height;
     {   // key grid: 64 columns, ceil(64 / (w/h)) rows (src/FeatureTracker.cpp:30-34); sized for this handle's image shape
@@ -866,7 +880,7 @@ int gvs_matcher_create(gvs_matcher** out, gvs_extractor* feL, gvs_extractor* feR
 
 int gvs_matcher_destroy(gvs_matcher* m) {
     if (!m) return GVS_OK;
-    cudaSetDevice(m->L->device);
+    DeviceGuard deviceGuard(m->L->device);
     cudaStreamSynchronize(m->L->stream);
     cudaFree(m->rightIdxs); cudaFree(m->leftIdxs); cudaFree(m->sadBest); cudaFree(m->sortScratch); cudaFree(m->depth); cudaFree(m->close);
     cudaFree(m->cellStartL); cudaFree(m->cellStartR); cudaFree(m->itemsL); cudaFree(m->itemsR); cudaFree(m->pj);
@@ -910,7 +924,7 @@ int gvs_matcher_set_stream(gvs_matcher* m, void* cuda_stream) {
 int gvs_stereo_match_batch(gvs_matcher* m, int n_frames) {
     if (!m) return fail(GVS_ERR_INVALID, "null matcher");
     if (n_frames < 1 || n_frames > m->L->lastN || n_frames > m->R->lastN) return fail(GVS_ERR_STATE, "extract both sides first");
-    GVS_CUDA_OK(cudaSetDevice(m->L->device));
+    DeviceGuard deviceGuard(m->L->device);
     int rc = joinRight(m);
     if (rc) return rc;
     cudaStream_t s = m->L->stream;
@@ -980,7 +994,7 @@ int gvs_assign_grids_batch(gvs_matcher* m, int n_frames, int width, int height) 
     if (!m) return fail(GVS_ERR_INVALID, "null matcher");
     if (n_frames < 1 || n_frames > m->L->lastN) return fail(GVS_ERR_STATE, "extract first");
     if (width < 1 || height < 1) return fail(GVS_ERR_INVALID, "bad size");
-    GVS_CUDA_OK(cudaSetDevice(m->L->device));
+    DeviceGuard deviceGuard(m->L->device);
     // src/FeatureTracker.cpp:30-34 (float32)
     const float imageRatio = (float)width / (float)height;
     m->xGrids = GVS_GRID_X;
@@ -1030,7 +1044,7 @@ int gvs_grid_download(gvs_matcher* m, int frame, int side, int32_t* cell_start, 
 int gvs_track_stereo_batch_resident(gvs_matcher* m, int n_frames, int width, int height) {
     if (!m) return fail(GVS_ERR_INVALID, "null matcher");
     if (m->R == m->L) return fail(GVS_ERR_STATE, "stereo tracking needs two extractors");
-    GVS_CUDA_OK(cudaSetDevice(m->L->device));
+    DeviceGuard deviceGuard(m->L->device);
     int rc = forkFromCaller(m);
     if (rc) return rc;
     rc = gvs_extract_batch_resident(m->L, n_frames);
@@ -1048,7 +1062,7 @@ int gvs_track_stereo_batch_host(gvs_matcher* m, const uint8_t* left, const uint8
                                 int n_frames, int width, int height) {
     if (!m) return fail(GVS_ERR_INVALID, "null matcher");
     if (m->R == m->L) return fail(GVS_ERR_STATE, "stereo tracking needs two extractors");
-    GVS_CUDA_OK(cudaSetDevice(m->L->device));
+    DeviceGuard deviceGuard(m->L->device);
     int rc = forkFromCaller(m);
     if (rc) return rc;
     rc = gvs_extract_batch_host(m->L, left, image_stride, row_stride, n_frames);
@@ -1079,7 +1093,7 @@ int gvs_match_projection(gvs_matcher* m, int frame, int mode, const gvs_mappoint
     if (!mps->desc || !mps->pred_l || !mps->scale_level_l) return fail(GVS_ERR_INVALID, "map point arrays missing");
     int rc = gvs_matcher_sync(m);
     if (rc) return rc;
-    GVS_CUDA_OK(cudaSetDevice(m->L->device));
+    DeviceGuard deviceGuard(m->L->device);
     cudaStream_t s = m->L->stream;
     const int M = mps->count;
     *n_matches = 0;
@@ -1181,7 +1195,7 @@ int gvs_match_projection_lba(gvs_matcher* m, const gvs_lba_frame* kf, const gvs_
         return fail(GVS_ERR_INVALID, "key frame arrays missing");
     for (int i = 0; i < M; i++)
         if (pts->pred_scale[i] < 0 || pts->pred_scale[i] >= m->L->g.nLevels) return fail(GVS_ERR_INVALID, "pred_scale out of range");
-    GVS_CUDA_OK(cudaSetDevice(m->L->device));
+    DeviceGuard deviceGuard(m->L->device);
     cudaStream_t s = m->L->stream;
     const float imageRatio = (float)kf->width / (float)kf->height;
     const int xGrids = GVS_GRID_X, yGrids = (int)std::ceil((float)xGrids / imageRatio);
@@ -1272,7 +1286,7 @@ int gvs_project_mappoints(gvs_matcher* m, const double* pose_inv, double fx, dou
     if (!m || !pose_inv || count < 0) return fail(GVS_ERR_INVALID, "bad argument");
     if (count == 0) return GVS_OK;
     if (!world_pos || !max_scale_dist || !log_scale || !n_scale_lev || !pred || !scale_level || !in_frame) return fail(GVS_ERR_INVALID, "null array");
-    GVS_CUDA_OK(cudaSetDevice(m->L->device));
+    DeviceGuard deviceGuard(m->L->device);
     cudaStream_t s = m->L->stream;
     const size_t M = (size_t)count;
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
@@ -1312,7 +1326,7 @@ int gvs_median_descriptor(gvs_matcher* m, const uint8_t* descs, const int32_t* o
     if (total < 0 || (total > 0 && !descs)) return fail(GVS_ERR_INVALID, "bad descriptor list");
     for (int p = 0; p < n_points; p++)
         if (offsets[p + 1] < offsets[p] || offsets[p + 1] - offsets[p] > 65535) return fail(GVS_ERR_INVALID, "bad offsets");
-    GVS_CUDA_OK(cudaSetDevice(m->L->device));
+    DeviceGuard deviceGuard(m->L->device);
     cudaStream_t s = m->L->stream;
     uint8_t* dd = nullptr; int* doff = nullptr; int* dbest = nullptr;
     cudaError_t e = devAlloc(&dd, (size_t)std::max(total, 1) * 32);
@@ -1332,7 +1346,7 @@ int gvs_median_descriptor(gvs_matcher* m, const uint8_t* descs, const int32_t* o
 int gvs_descriptor_distance(gvs_matcher* m, const uint8_t* a, const uint8_t* b, int n, int32_t* dist) {
     if (!m || !a || !b || !dist || n < 0) return fail(GVS_ERR_INVALID, "bad argument");
     if (n == 0) return GVS_OK;
-    GVS_CUDA_OK(cudaSetDevice(m->L->device));
+    DeviceGuard deviceGuard(m->L->device);
     cudaStream_t s = m->L->stream;
     uint8_t *da = nullptr, *db = nullptr;
     int* dd = nullptr;
