@@ -120,7 +120,7 @@ fast_cells_kernel(const __grid_constant__ Geometry g, const uint8_t* __restrict_
                   const FastItem* __restrict__ items, int maxGW, int maxGH, CandRec* __restrict__ recs,
                   int* __restrict__ nCand, unsigned short* __restrict__ cellCnt, int* __restrict__ status) {
     extern __shared__ __align__(16) uint8_t smem[];
-    __shared__ int sCnt[kFastCellsPerItem], sMax[kFastCellsPerItem], sEmit[kFastCellsPerItem], sBase[kFastCellsPerItem];
+    __shared__ int sCnt[kFastCellsPerItem], sBase[kFastCellsPerItem];
 
     const FastItem it = items[blockIdx.x];
     const int img = blockIdx.y;
@@ -135,7 +135,7 @@ fast_cells_kernel(const __grid_constant__ Geometry g, const uint8_t* __restrict_
     const int y0 = edge + it.iR * lv.gridH, y1 = min(y0 + lv.gridH, lv.h - edge);
     const int X0 = edge + it.iC0 * lv.gridW, X1 = min(X0 + it.nC * lv.gridW, lv.w - edge);
     const int tid = threadIdx.x;
-    if (tid < kFastCellsPerItem) { sCnt[tid] = 0; sMax[tid] = 0; sEmit[tid] = 0; }
+    if (tid < kFastCellsPerItem) sCnt[tid] = 0;
     const int rows = y1 - y0, cols = X1 - X0;
     if (rows <= 0 || cols <= 0) {  // empty strip: still publish zero counts for its cells
         if (tid < it.nC) cellCnt[(size_t)img * g.cellsPerImage + lv.cellBase + it.iR * lv.nCols + it.iC0 + tid] = 0;
@@ -174,113 +174,129 @@ fast_cells_kernel(const __grid_constant__ Geometry g, const uint8_t* __restrict_
     }
     __syncthreads();
 
-    // ---- 2a. pre-test on 4 pixels at once (native VABSDIFF4): a 9-arc contains ring pixel k or k+8 for every k, so a
-    // corner at threshold t needs |I(ring_k) - I(p)| > t for k in {0 or 8} and for k in {4 or 12}.  ">" is relaxed to
-    // "some bit at or above floor(log2(t+1)) set" (exact for t = 2^m - 1, e.g. the reference's 7; conservative otherwise).
-    // Surviving pixel pairs are compacted into two queues (one per pair position, so that 2b has no divergent code).
+    // The reference runs cv::FAST on a cell at maxFastThreshold and, only if that returns nothing, again at minFastThreshold
+    // (src/FeatureExtractor.cpp:591-593).  Same here: pass 0 works at tMax on every cell of the strip; pass 1 (rare on textured
+    // images) redoes the cells that produced no key at tMin.  A pass = 2a pre-test + compaction, 2b exact scores, 3 local maxima.
     unsigned short* queue = reinterpret_cast<unsigned short*>(smem + L.queueOff);
+    unsigned short* score16 = reinterpret_cast<unsigned short*>(score);
     __shared__ int sQ[2];
-    if (tid < 2) sQ[tid] = 0;
-    __syncthreads();
-    const int tMin = g.tMin;
-    const unsigned hiMask = (~((1u << (31 - __clz(tMin + 1))) - 1u) & 0xffu) * 0x01010101u;
+    const int tMin = g.tMin, tMax = g.tMax;
     const unsigned ltMask = (1u << (tid & 31)) - 1u;
     const int nUnits = nW * rows;
-    for (int base = 0; base < nUnits; base += 256) {
-        const int i = base + tid;
-        bool p0 = false, p1 = false;
-        if (i < nUnits) {
-            const int ry = (int)__umulhi((unsigned)i, magicU), j = i - ry * nW;
-            const unsigned* p = tile + (ry + 3) * L.tileWords + j;
-            const unsigned c = p[1];
-            const unsigned up = p[1 - 3 * L.tileWords], dn = p[1 + 3 * L.tileWords];
-            const unsigned lf = __funnelshift_r(p[0], c, 8), rt = __funnelshift_r(c, p[2], 24);
-            const unsigned v = (__vabsdiffu4(up, c) | __vabsdiffu4(dn, c)) & hiMask;
-            const unsigned h = (__vabsdiffu4(lf, c) | __vabsdiffu4(rt, c)) & hiMask;
-            const unsigned nzv = (v | ((v | 0x80808080u) - 0x01010101u)), nzh = (h | ((h | 0x80808080u) - 0x01010101u));
-            const unsigned f = nzv & nzh & 0x80808080u & masks[3 * j];
-            p0 = (f & 0x0000ffffu) != 0;
-            p1 = (f & 0xffff0000u) != 0;
-        }
-        const unsigned b0 = __ballot_sync(0xffffffffu, p0), b1 = __ballot_sync(0xffffffffu, p1);
-        int o0 = 0, o1 = 0;
-        if ((tid & 31) == 0) {
-            if (b0) o0 = atomicAdd(&sQ[0], __popc(b0));
-            if (b1) o1 = atomicAdd(&sQ[1], __popc(b1));
-        }
-        o0 = __shfl_sync(0xffffffffu, o0, 0); o1 = __shfl_sync(0xffffffffu, o1, 0);
-        if (p0) queue[o0 + __popc(b0 & ltMask)] = (unsigned short)i;
-        if (p1) queue[L.queueCap + o1 + __popc(b1 & ltMask)] = (unsigned short)i;
-    }
-    __syncthreads();
-
-    // ---- 2b. exact scores of the surviving pairs: 21 word loads, ring pairs by PRMT, min3-of-min3 arcs
-    unsigned short* score16 = reinterpret_cast<unsigned short*>(score);
-    const int n0 = sQ[0], n1 = sQ[1];
-    for (int q = tid; q < n0 + n1; q += 256) {
-        const bool second = q >= n0;
-        const int i = second ? queue[L.queueCap + q - n0] : queue[q];
-        const int ry = (int)__umulhi((unsigned)i, magicU), j = i - ry * nW;
-        unsigned W[7][3];
+    unsigned redo = 0;  // pass 1: bit c = cell c of the strip is redone
+    // bytes of unit word j that lie in a cell that is being redone
+    auto redoBytes = [&](int j) {
+        unsigned m = 0;
 #pragma unroll
-        for (int r = 0; r < 7; r++) {
-            const unsigned* p = tile + (ry + r) * L.tileWords + j;
-            W[r][0] = p[0]; W[r][1] = p[1]; W[r][2] = p[2];
+        for (int b = 0; b < 4; b++) {
+            const int lx = xu + 4 * j + b - X0;
+            if (lx >= 0 && lx < cols && ((redo >> cellOfStrip(lx, gW)) & 1u)) m |= 0xffu << (8 * b);
         }
-        const unsigned m = masks[3 * j];
-        if (!second) score16[2 * ((ry + 1) * L.scoreWords + j + 1)] = (unsigned short)(scorePair<0>(W, tMin) & m);
-        else score16[2 * ((ry + 1) * L.scoreWords + j + 1) + 1] = (unsigned short)(scorePair<1>(W, tMin) & (m >> 16));
-    }
-    __syncthreads();
+        return m;
+    };
+    for (int pass = 0; pass < 2; pass++) {
+        const int T = pass == 0 ? tMax : tMin;
+        if (tid < 2) sQ[tid] = 0;
+        __syncthreads();
 
-    // ---- 3. strict local maxima inside each cell, four pixels at a time -> per-cell lists
-    for (int i = tid; i < nW * rows; i += 256) {
-        const int ry = (int)__umulhi((unsigned)i, magicU), j = i - ry * nW;
-        const unsigned* sp = score + (ry + 1) * L.scoreWords + j + 1;
-        const unsigned c = sp[0];
-        if (c == 0) continue;
-        const unsigned hasL = masks[3 * j + 1], hasR = masks[3 * j + 2];
-        const int P = L.scoreWords;
-        const unsigned up = sp[-P], dn = sp[P];
-        unsigned lm = __vcmpgtu4(c, up) & __vcmpgtu4(c, dn);
-        const unsigned l0 = __funnelshift_r(sp[-1], c, 24) & hasL, l1 = __funnelshift_r(sp[-P - 1], up, 24) & hasL,
-                       l2 = __funnelshift_r(sp[P - 1], dn, 24) & hasL;
-        lm &= __vcmpgtu4(c, l0) & __vcmpgtu4(c, l1) & __vcmpgtu4(c, l2);
-        const unsigned r0 = __funnelshift_r(c, sp[1], 8) & hasR, r1 = __funnelshift_r(up, sp[-P + 1], 8) & hasR,
-                       r2 = __funnelshift_r(dn, sp[P + 1], 8) & hasR;
-        lm &= __vcmpgtu4(c, r0) & __vcmpgtu4(c, r1) & __vcmpgtu4(c, r2);
-        while (lm) {
-            const int b = (__ffs(lm) - 1) >> 3;
-            lm &= ~(0xffu << (8 * b));
-            const int lx = xu + 4 * j + b - X0, s = (c >> (8 * b)) & 0xff;
-            const int cl = cellOfStrip(lx, gW);
-            const int slot = atomicAdd(&sCnt[cl], 1);
-            lists[cl * L.listCap + slot] = ((unsigned)ry << 16) | ((unsigned)(lx - cl * gW) << 8) | (unsigned)s;
-            atomicMax(&sMax[cl], s);
+        // ---- 2a. pre-test on 4 pixels at once (native VABSDIFF4): a 9-arc contains ring pixel k or k+8 for every k, so a
+        // corner at threshold T needs |I(ring_k) - I(p)| > T for k in {0 or 8} and for k in {4 or 12}.  Per byte,
+        // d > T  <=>  bit 7 of ((d & 0x7f) + (127 - T)) | d   (T <= 127; above that the test degrades to d >= 128, still
+        // necessary).  Surviving pixel pairs are compacted into two queues (one per pair position: 2b has no divergent code).
+        const unsigned kT = (unsigned)max(127 - T, 0) * 0x01010101u;
+        auto gt = [&](unsigned d) { return ((d & 0x7f7f7f7fu) + kT) | d; };
+        for (int base = 0; base < nUnits; base += 256) {
+            const int i = base + tid;
+            bool p0 = false, p1 = false;
+            if (i < nUnits) {
+                const int ry = (int)__umulhi((unsigned)i, magicU), j = i - ry * nW;
+                const unsigned* p = tile + (ry + 3) * L.tileWords + j;
+                const unsigned c = p[1];
+                const unsigned up = p[1 - 3 * L.tileWords], dn = p[1 + 3 * L.tileWords];
+                const unsigned lf = __funnelshift_r(p[0], c, 8), rt = __funnelshift_r(c, p[2], 24);
+                const unsigned v = gt(__vabsdiffu4(up, c)) | gt(__vabsdiffu4(dn, c));
+                const unsigned h = gt(__vabsdiffu4(lf, c)) | gt(__vabsdiffu4(rt, c));
+                unsigned f = v & h & 0x80808080u & masks[3 * j];
+                if (pass) f &= redoBytes(j);
+                p0 = (f & 0x0000ffffu) != 0;
+                p1 = (f & 0xffff0000u) != 0;
+            }
+            const unsigned b0 = __ballot_sync(0xffffffffu, p0), b1 = __ballot_sync(0xffffffffu, p1);
+            int o0 = 0, o1 = 0;
+            if ((tid & 31) == 0) {
+                if (b0) o0 = atomicAdd(&sQ[0], __popc(b0));
+                if (b1) o1 = atomicAdd(&sQ[1], __popc(b1));
+            }
+            o0 = __shfl_sync(0xffffffffu, o0, 0); o1 = __shfl_sync(0xffffffffu, o1, 0);
+            if (p0) queue[o0 + __popc(b0 & ltMask)] = (unsigned short)i;
+            if (p1) queue[L.queueCap + o1 + __popc(b1 & ltMask)] = (unsigned short)i;
         }
-    }
-    __syncthreads();
+        __syncthreads();
 
-    // ---- 4. threshold per cell, count emitted, reserve, rank inside the cell (row-major), write
-    const int tMax = g.tMax;
+        // ---- 2b. exact scores of the surviving pairs: 21 word loads, ring pairs by PRMT, min3-of-min3 arcs; a score below
+        // the pass threshold is stored as 0, exactly like the score buffer of cv::FAST at that threshold
+        const int n0 = sQ[0], n1 = sQ[1];
+        for (int q = tid; q < n0 + n1; q += 256) {
+            const bool second = q >= n0;
+            const int i = second ? queue[L.queueCap + q - n0] : queue[q];
+            const int ry = (int)__umulhi((unsigned)i, magicU), j = i - ry * nW;
+            unsigned W[7][3];
+#pragma unroll
+            for (int r = 0; r < 7; r++) {
+                const unsigned* p = tile + (ry + r) * L.tileWords + j;
+                W[r][0] = p[0]; W[r][1] = p[1]; W[r][2] = p[2];
+            }
+            const unsigned m = masks[3 * j];
+            if (!second) score16[2 * ((ry + 1) * L.scoreWords + j + 1)] = (unsigned short)(scorePair<0>(W, T) & m);
+            else score16[2 * ((ry + 1) * L.scoreWords + j + 1) + 1] = (unsigned short)(scorePair<1>(W, T) & (m >> 16));
+        }
+        __syncthreads();
+
+        // ---- 3. strict local maxima inside each cell, four pixels at a time -> per-cell lists
+        for (int i = tid; i < nUnits; i += 256) {
+            const int ry = (int)__umulhi((unsigned)i, magicU), j = i - ry * nW;
+            const unsigned* sp = score + (ry + 1) * L.scoreWords + j + 1;
+            const unsigned c = sp[0];
+            if (c == 0) continue;
+            const unsigned hasL = masks[3 * j + 1], hasR = masks[3 * j + 2];
+            const int P = L.scoreWords;
+            const unsigned up = sp[-P], dn = sp[P];
+            unsigned lm = __vcmpgtu4(c, up) & __vcmpgtu4(c, dn);
+            const unsigned l0 = __funnelshift_r(sp[-1], c, 24) & hasL, l1 = __funnelshift_r(sp[-P - 1], up, 24) & hasL,
+                           l2 = __funnelshift_r(sp[P - 1], dn, 24) & hasL;
+            lm &= __vcmpgtu4(c, l0) & __vcmpgtu4(c, l1) & __vcmpgtu4(c, l2);
+            const unsigned r0 = __funnelshift_r(c, sp[1], 8) & hasR, r1 = __funnelshift_r(up, sp[-P + 1], 8) & hasR,
+                           r2 = __funnelshift_r(dn, sp[P + 1], 8) & hasR;
+            lm &= __vcmpgtu4(c, r0) & __vcmpgtu4(c, r1) & __vcmpgtu4(c, r2);
+            if (pass) lm &= redoBytes(j);   // the other cells were listed by pass 0
+            while (lm) {
+                const int b = (__ffs(lm) - 1) >> 3;
+                lm &= ~(0xffu << (8 * b));
+                const int lx = xu + 4 * j + b - X0, s = (c >> (8 * b)) & 0xff;
+                const int cl = cellOfStrip(lx, gW);
+                const int slot = atomicAdd(&sCnt[cl], 1);
+                lists[cl * L.listCap + slot] = ((unsigned)ry << 16) | ((unsigned)(lx - cl * gW) << 8) | (unsigned)s;
+            }
+        }
+        __syncthreads();
+        if (pass || tMin >= tMax) break;
+        for (int c = 0; c < it.nC; c++) redo |= (sCnt[c] == 0 ? 1u : 0u) << c;   // same value in every thread
+        if (!redo) break;
+    }
+
+    // ---- 4. reserve, rank inside the cell (row-major), write: every listed key is emitted (the lists already hold exactly the
+    // keys of the threshold that applies to their cell)
     int total = 0;
     for (int c = 0; c < it.nC; c++) total += sCnt[c];
-    for (int e = tid; e < total; e += 256) {
-        int c = 0, off = e;
-        while (off >= sCnt[c]) { off -= sCnt[c]; c++; }
-        const int T = sMax[c] >= tMax ? tMax : tMin;
-        if ((int)(lists[c * L.listCap + off] & 0xff) >= T) atomicAdd(&sEmit[c], 1);
-    }
-    __syncthreads();
     if (tid == 0) {
         int tot = 0;
-        for (int c = 0; c < it.nC; c++) { sBase[c] = tot; tot += sEmit[c]; }
+        for (int c = 0; c < it.nC; c++) { sBase[c] = tot; tot += sCnt[c]; }
         const int base = tot ? atomicAdd(&nCand[img * kMaxLevels + it.level], tot) : 0;
         if (base + tot > lv.candCap) atomicOr(status, kStatCandOverflow);
         for (int c = 0; c < it.nC; c++) sBase[c] += base;
     }
     if (tid < it.nC)
-        cellCnt[(size_t)img * g.cellsPerImage + lv.cellBase + it.iR * lv.nCols + it.iC0 + tid] = (unsigned short)sEmit[tid];
+        cellCnt[(size_t)img * g.cellsPerImage + lv.cellBase + it.iR * lv.nCols + it.iC0 + tid] = (unsigned short)sCnt[tid];
     __syncthreads();
     CandRec* out = recs + (size_t)img * g.candPerImage + lv.candOff;
     for (int e = tid; e < total; e += 256) {
@@ -288,14 +304,9 @@ fast_cells_kernel(const __grid_constant__ Geometry g, const uint8_t* __restrict_
         while (off >= sCnt[c]) { off -= sCnt[c]; c++; }
         const unsigned* lc = lists + c * L.listCap;
         const unsigned key = lc[off];
-        const int T = sMax[c] >= tMax ? tMax : tMin;
-        if ((int)(key & 0xff) < T) continue;
         int rank = 0;
         const int n = sCnt[c];
-        for (int j = 0; j < n; j++) {
-            const unsigned o = lc[j];
-            rank += ((int)(o & 0xff) >= T) && ((o >> 8) < (key >> 8));
-        }
+        for (int j = 0; j < n; j++) rank += (lc[j] >> 8) < (key >> 8);
         const int slot = sBase[c] + rank;
         if (slot >= lv.candCap) continue;
         const int x = X0 + c * gW + (int)((key >> 8) & 0xff), y = y0 + (int)(key >> 16);
