@@ -100,37 +100,44 @@ describe_fused_kernel(const __grid_constant__ Geometry g, const uint8_t* __restr
         r.xs = ((r.x - kPR) & ~3) - 4; r.ys = r.y - kPR;
         return r;
     };
-    // stage the 43 x 13-word patch of a key into `P` asynchronously: aligned 4-byte cp.async for interior keys; keys whose
-    // patch touches the image border (they sit >= 19 px inside, the patch reaches 21 + alignment) use reflect-101 loads
+    // stage the 43 x 13-word patch of a key into `P` asynchronously with aligned 4-byte cp.async.  Lane = (row parity, word
+    // column): 26 lanes copy two rows per step with nothing but pointer increments in the loop.  Keys whose patch touches the
+    // image border (they sit >= 19 px inside, the patch reaches 21 + alignment) reflect the row index (101) and gather the
+    // words that cross the left / right border byte by byte.
+    const int stSub = lane >= kPWords ? 1 : 0, stCol = lane - stSub * kPWords;   // lanes 26..31 idle
     auto stage = [&](const KeyRef& kr, unsigned* P) {
         const LevelGeom& lv = g.lv[kr.level];
         const uint8_t* src = levelPtr(slab, g, img, kr.level);
-        if (kr.xs >= 0 && kr.xs + 4 * kPWords <= lv.w && kr.ys >= 0 && kr.ys + kPRows <= lv.h) {
-            const uint8_t* base = src + (size_t)kr.ys * lv.pitch + kr.xs;
-#pragma unroll 6
-            for (int t = lane; t < kPRows * kPWords; t += 32) {
-                const int r = t / kPWords, c = t - r * kPWords;
-                cpAsync4(P + t, base + (size_t)r * lv.pitch + 4 * c);
-            }
-        } else {
-            for (int t = lane; t < kPRows * kPWords; t += 32) {
-                const int r = t / kPWords, c = t - r * kPWords;
-                int iy = kr.ys + r;
-                iy = iy < 0 ? -iy : (iy >= lv.h ? 2 * lv.h - 2 - iy : iy);
-                const uint8_t* row = src + (size_t)iy * lv.pitch;
-                const int gx = kr.xs + 4 * c;
-                unsigned v;
-                if (gx >= 0 && gx + 3 < lv.w) v = __ldg(reinterpret_cast<const unsigned*>(row + gx));
-                else {
-                    v = 0;
+        if (lane < 2 * kPWords) {
+            unsigned sp = (unsigned)__cvta_generic_to_shared(P + stSub * kPWords + stCol);
+            const int gx = kr.xs + 4 * stCol;
+            if (kr.xs >= 0 && kr.xs + 4 * kPWords <= lv.w && kr.ys >= 0 && kr.ys + kPRows <= lv.h) {
+                const uint8_t* gp = src + (size_t)(kr.ys + stSub) * lv.pitch + gx;
+                const size_t step = 2 * (size_t)lv.pitch;
+#pragma unroll 11
+                for (int r = stSub; r < kPRows; r += 2) {
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sp), "l"(gp));
+                    gp += step; sp += 2 * kPWords * 4;
+                }
+            } else {
+                const bool wordIn = gx >= 0 && gx + 3 < lv.w;
+                for (int r = stSub; r < kPRows; r += 2, sp += 2 * kPWords * 4) {
+                    int iy = kr.ys + r;
+                    iy = iy < 0 ? -iy : (iy >= lv.h ? 2 * lv.h - 2 - iy : iy);
+                    const uint8_t* row = src + (size_t)iy * lv.pitch;
+                    if (wordIn) {
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sp), "l"(row + gx));
+                    } else {
+                        unsigned v = 0;
 #pragma unroll
-                    for (int b = 0; b < 4; b++) {
-                        int xx = gx + b;
-                        xx = xx < 0 ? -xx : (xx >= lv.w ? 2 * lv.w - 2 - xx : xx);
-                        v |= (unsigned)row[xx] << (8 * b);
+                        for (int b = 0; b < 4; b++) {
+                            int xx = gx + b;
+                            xx = xx < 0 ? -xx : (xx >= lv.w ? 2 * lv.w - 2 - xx : xx);
+                            v |= (unsigned)row[xx] << (8 * b);
+                        }
+                        P[r * kPWords + stCol] = v;
                     }
                 }
-                P[t] = v;
             }
         }
         asm volatile("cp.async.commit_group;\n" ::);
