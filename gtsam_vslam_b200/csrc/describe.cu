@@ -81,6 +81,17 @@ describe_fused_kernel(const __grid_constant__ Geometry g, const uint8_t* __restr
         pat[0] = a.x; pat[1] = a.y; pat[2] = a.z; pat[3] = a.w; pat[4] = b.x; pat[5] = b.y; pat[6] = b.z; pat[7] = b.w;
     }
     __shared__ int pre[kMaxLevels + 1];  // keys of this image before level l (dense output order)
+    __shared__ unsigned oriW[8 * 32], oriO[8 * 32];  // orientation weights per (word, lane = disc row), see below
+    for (int t = threadIdx.x; t < 8 * 32; t += blockDim.x) {
+        const int i = t >> 5, v = (t & 31) - kHalfPatch;
+        const int d = (t & 31) <= 2 * kHalfPatch ? g.umax[v < 0 ? -v : v] : -1;
+        unsigned w = 0, o = 0;
+        for (int b = 0; b < 4; b++) {
+            const int u = 4 * i + b - kHalfPatch;
+            if (u >= -d && u <= d) { w |= (unsigned)(u + kHalfPatch) << (8 * b); o |= 1u << (8 * b); }
+        }
+        oriW[t] = w; oriO[t] = o;
+    }
     if (threadIdx.x == 0) {
         int run = 0;
         for (int l = 0; l < kMaxLevels; l++) { pre[l] = run; run += l < g.nLevels ? keptCnt[img * kMaxLevels + l] : 0; }
@@ -165,12 +176,22 @@ describe_fused_kernel(const __grid_constant__ Geometry g, const uint8_t* __restr
         int m10 = 0, m01 = 0;
         if (lane < 2 * kHalfPatch + 1) {
             const int v = lane - kHalfPatch;
-            const int d = g.umax[v < 0 ? -v : v];
-            const uint8_t* row = Pb + (kPR + v) * (kPWords * 4) + ox;
-            int s0 = 0, s1 = 0;
-            for (int u = -d; u <= d; u++) { const int val = row[u]; s0 += val; s1 += u * val; }
-            m10 = s1;
-            m01 = v * s0;
+            // row v of the disc: bytes u = -umax[|v|] .. umax[|v|] around the key column.  The 31 bytes u = -15 .. 15 are
+            // 8 words after a funnel shift; the disc extent is folded into per-lane weight tables (oriW = u + 15, oriO = 1,
+            // 0 outside the disc), so the two sums are 16 dp4a:  m10 row sum = sum (u + 15) I - 15 sum I.
+            const unsigned* rw = P + (kPR + v) * kPWords + ((ox - kHalfPatch) >> 2);
+            const unsigned sh = ((ox - kHalfPatch) & 3) * 8;
+            unsigned s0 = 0, s1 = 0, lo = rw[0];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const unsigned hi = rw[i + 1];
+                const unsigned xw = __funnelshift_r(lo, hi, sh);
+                s0 = __dp4a(xw, oriO[i * 32 + lane], s0);
+                s1 = __dp4a(xw, oriW[i * 32 + lane], s1);
+                lo = hi;
+            }
+            m10 = (int)s1 - kHalfPatch * (int)s0;
+            m01 = v * (int)s0;
         }
 #pragma unroll
         for (int off = 16; off; off >>= 1) { m10 += __shfl_xor_sync(0xffffffffu, m10, off); m01 += __shfl_xor_sync(0xffffffffu, m01, off); }
