@@ -65,54 +65,71 @@ struct SelShared {
     int keptTotal;
 };
 
+#ifdef GVS_SEL_PROFILE
+// phase clocks (thread 0 of every CTA): 0 order, 1 sort phase 1 (CTA-wide partitions), 2 sort phase 2 (warp partitions),
+// 3 final counting sort, 4 ssc, 5 output, 6 problems
+__device__ unsigned long long gSelProf[8];
+#define GVS_PROF_DECL long long profT = clock64();
+#define GVS_PROF_DECL2 profT = clock64();
+#define GVS_PROF(i) do { if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&gSelProf[i], (unsigned long long)(t_ - profT)); profT = t_; } } while (0)
+#else
+#define GVS_PROF_DECL
+#define GVS_PROF_DECL2
+#define GVS_PROF(i) do { } while (0)
+#endif
+
 __device__ __forceinline__ unsigned lanemaskLt() { unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
 __device__ __forceinline__ unsigned lanemaskLe() { unsigned m; asm("mov.u32 %0, %%lanemask_le;" : "=r"(m)); return m; }
 
 // ---- libstdc++ pieces executed by a single lane -----------------------------------------------------
+// The 8-bit keys are permuted together with idx (key[p] is the key of the element at position p), so no pass needs the
+// double indirection key[idx[p]] and key loads are contiguous.
 template <typename IdxT>
-__device__ void moveMedianToFirst(const uint8_t* key, IdxT* idx, int result, int a, int b, int c) {
-    auto lt = [&](int i, int j) { return key[idx[i]] < key[idx[j]]; };
-    auto sw = [&](int i, int j) { IdxT t = idx[i]; idx[i] = idx[j]; idx[j] = t; };
-    if (lt(a, b)) {
-        if (lt(b, c)) sw(result, b);
-        else if (lt(a, c)) sw(result, c);
-        else sw(result, a);
-    } else if (lt(a, c)) sw(result, a);
-    else if (lt(b, c)) sw(result, c);
-    else sw(result, b);
+__device__ __forceinline__ void swapPos(uint8_t* key, IdxT* idx, int i, int j) {
+    const IdxT t = idx[i]; idx[i] = idx[j]; idx[j] = t;
+    const uint8_t k = key[i]; key[i] = key[j]; key[j] = k;
 }
 
 template <typename IdxT>
-__device__ void adjustHeap(const uint8_t* key, IdxT* first, int hole, int len, IdxT value) {
+__device__ void moveMedianToFirst(uint8_t* key, IdxT* idx, int result, int a, int b, int c) {
+    const int ka = key[a], kb = key[b], kc = key[c];
+    int sel;
+    if (ka < kb) sel = kb < kc ? b : (ka < kc ? c : a);
+    else sel = ka < kc ? a : (kb < kc ? c : b);
+    swapPos(key, idx, result, sel);
+}
+
+template <typename IdxT>
+__device__ void adjustHeap(uint8_t* key, IdxT* idx, int hole, int len, IdxT value, uint8_t vkey) {
     const int top = hole;
     int second = hole;
     while (second < (len - 1) / 2) {
         second = 2 * (second + 1);
-        if (key[first[second]] < key[first[second - 1]]) second--;
-        first[hole] = first[second];
+        if (key[second] < key[second - 1]) second--;
+        idx[hole] = idx[second]; key[hole] = key[second];
         hole = second;
     }
     if ((len & 1) == 0 && second == (len - 2) / 2) {
         second = 2 * (second + 1);
-        first[hole] = first[second - 1];
+        idx[hole] = idx[second - 1]; key[hole] = key[second - 1];
         hole = second - 1;
     }
     int parent = (hole - 1) / 2;
-    while (hole > top && key[first[parent]] < key[value]) {
-        first[hole] = first[parent];
+    while (hole > top && key[parent] < vkey) {
+        idx[hole] = idx[parent]; key[hole] = key[parent];
         hole = parent;
         parent = (hole - 1) / 2;
     }
-    first[hole] = value;
+    idx[hole] = value; key[hole] = vkey;
 }
 
+// std::__partial_sort(first, last, last) on positions [0, len) of (idx, key)
 template <typename IdxT>
-__device__ void heapSort(const uint8_t* key, IdxT* first, int len) {  // std::__partial_sort(first, last, last)
+__device__ void heapSort(uint8_t* key, IdxT* idx, int len) {
     if (len >= 2) {
         int parent = (len - 2) / 2;
         while (true) {
-            IdxT v = first[parent];
-            adjustHeap(key, first, parent, len, v);
+            adjustHeap(key, idx, parent, len, idx[parent], key[parent]);
             if (parent == 0) break;
             parent--;
         }
@@ -120,19 +137,18 @@ __device__ void heapSort(const uint8_t* key, IdxT* first, int len) {  // std::__
     int last = len;
     while (last > 1) {
         --last;
-        IdxT v = first[last];
-        first[last] = first[0];
-        adjustHeap(key, first, 0, last, v);
+        const IdxT v = idx[last]; const uint8_t vk = key[last];
+        idx[last] = idx[0]; key[last] = key[0];
+        adjustHeap(key, idx, 0, last, v, vk);
     }
 }
 
 // ---- warp-level pieces of the parallel partition ----------------------------------------------------
 // count of (key >= pv) and (key <= pv) over positions [a, b)
-template <typename IdxT>
-__device__ __forceinline__ void countAB(const uint8_t* key, const IdxT* idx, int a, int b, int pv, int lane, int& cA, int& cB) {
+__device__ __forceinline__ void countAB(const uint8_t* key, int a, int b, int pv, int lane, int& cA, int& cB) {
     int na = 0, nb = 0;
     for (int p = a + lane; p < b; p += 32) {
-        const int k = key[idx[p]];
+        const int k = key[p];
         na += k >= pv;
         nb += k <= pv;
     }
@@ -144,50 +160,116 @@ __device__ __forceinline__ void countAB(const uint8_t* key, const IdxT* idx, int
 // rank + assign over [a, b): runA/runB = counts before a; totalB = count of B over the whole partition range.
 // Writes posA[k] / posB[k] for swapped elements; returns number swapped (A side) and the smallest unswapped A position.
 template <typename IdxT>
-__device__ __forceinline__ void assignAB(const uint8_t* key, const IdxT* idx, int a, int b, int pv, int lane, int runA,
+__device__ __forceinline__ void assignAB(const uint8_t* key, int a, int b, int pv, int lane, int runA,
                                          int runB, int totalB, IdxT* posA, IdxT* posB, int& mOut, int& minUnsw) {
     int m = 0, mn = 0x7fffffff;
     const unsigned lt = lanemaskLt(), le = lanemaskLe();
-    for (int base = a; base < b; base += 32) {
-        const int p = base + lane;
-        const bool valid = p < b;
-        const int k = valid ? (int)key[idx[p]] : -1;
-        const bool fa = valid && k >= pv, fb = valid && k <= pv;
-        const unsigned ba = __ballot_sync(0xffffffffu, fa), bb = __ballot_sync(0xffffffffu, fb);
-        const int ra = runA + __popc(ba & lt);
-        const int rbx = totalB - (runB + __popc(bb & le));
-        const bool swA = fa && rbx > ra, swB = fb && ra > rbx;
-        if (swA) posA[ra] = (IdxT)p;
-        if (swB) posB[rbx] = (IdxT)p;
-        if (fa && !swA) mn = min(mn, p);
-        m += __popc(__ballot_sync(0xffffffffu, swA));
-        runA += __popc(ba);
-        runB += __popc(bb);
+    for (int base4 = a; base4 < b; base4 += 128) {
+        int kk[4];  // the keys of four chunks are fetched before the (store-carrying) rank code: four loads in flight
+#pragma unroll
+        for (int j = 0; j < 4; j++) { const int p = base4 + 32 * j + lane; kk[j] = p < b ? (int)key[p] : -1; }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int base = base4 + 32 * j;
+            if (base >= b) break;
+            const int p = base + lane;
+            const int k = kk[j];
+            const bool fa = k >= pv, fb = k >= 0 && k <= pv;   // k = -1 marks a position past the end
+            const unsigned ba = __ballot_sync(0xffffffffu, fa), bb = __ballot_sync(0xffffffffu, fb);
+            const int ra = runA + __popc(ba & lt);
+            const int rbx = totalB - (runB + __popc(bb & le));
+            const bool swA = fa && rbx > ra, swB = fb && ra > rbx;
+            if (swA) posA[ra] = (IdxT)p;
+            if (swB) posB[rbx] = (IdxT)p;
+            if (fa && !swA) mn = min(mn, p);
+            m += __popc(__ballot_sync(0xffffffffu, swA));
+            runA += __popc(ba);
+            runB += __popc(bb);
+        }
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
     mOut = m; minUnsw = mn;
 }
 
+// Segments of at most 32 elements entirely in registers (lane = position): median-of-3, __unguarded_partition and the
+// descent into the one child that can still exceed 16 elements, with shuffles and ballots only -- one load and one store of
+// idx per element instead of several shared-memory round trips per partition.  Same swaps as partitionWarp: the swapped
+// "A" elements (key >= pivot, scanning up) are a prefix of the A lanes, the swapped "B" elements (key <= pivot, scanning
+// down) a suffix of the B lanes, the r-th of one is exchanged with the r-th of the other.
+template <typename IdxT>
+__device__ void sortSmallSegmentWarp(uint8_t* key, IdxT* idx, int first, int last, int depth, int lane) {
+    const int m0 = last - first;
+    IdxT e = lane < m0 ? idx[first + lane] : (IdxT)0;
+    int k = lane < m0 ? (int)key[first + lane] : 0;
+    int f = 0, l = m0;  // current sub-segment, lane relative
+    const unsigned ltm = lanemaskLt(), lem = lanemaskLe();
+    while (l - f > 16) {
+        if (depth == 0) {  // introsort's heapsort fallback: back to shared memory, one lane
+            if (lane < m0) { idx[first + lane] = e; key[first + lane] = (uint8_t)k; }
+            __syncwarp();
+            if (lane == 0) heapSort(key + first + f, idx + first + f, l - f);
+            __syncwarp();
+            return;
+        }
+        --depth;
+        // __move_median_to_first(f, f + 1, mid, l - 1)
+        const int ia = f + 1, ib = f + (l - f) / 2, ic = l - 1;
+        const int ka = __shfl_sync(0xffffffffu, k, ia), kb = __shfl_sync(0xffffffffu, k, ib), kc = __shfl_sync(0xffffffffu, k, ic);
+        int sel;
+        if (ka < kb) sel = kb < kc ? ib : (ka < kc ? ic : ia);
+        else sel = ka < kc ? ia : (kb < kc ? ic : ib);
+        {
+            const int src = lane == f ? sel : (lane == sel ? f : lane);
+            e = (IdxT)__shfl_sync(0xffffffffu, (int)e, src);
+            k = __shfl_sync(0xffffffffu, k, src);
+        }
+        const int pv = __shfl_sync(0xffffffffu, k, f);
+        // __unguarded_partition(f + 1, l, pivot at f)
+        const bool in = lane > f && lane < l;
+        const bool fa = in && k >= pv, fb = in && k <= pv;
+        const unsigned ba = __ballot_sync(0xffffffffu, fa), bb = __ballot_sync(0xffffffffu, fb);
+        const int ra = __popc(ba & ltm), rbx = __popc(bb) - __popc(bb & lem);
+        const bool swA = fa && rbx > ra, swB = fb && ra > rbx;
+        int src = lane;
+        if (swA) src = __fns(bb, 31, -(ra + 1));       // the (ra+1)-th B lane from the top
+        else if (swB) src = __fns(ba, 0, rbx + 1);     // the (rbx+1)-th A lane from the bottom
+        const unsigned unswA = __ballot_sync(0xffffffffu, fa && !swA), swBm = __ballot_sync(0xffffffffu, swB);
+        e = (IdxT)__shfl_sync(0xffffffffu, (int)e, src);
+        k = __shfl_sync(0xffffffffu, k, src);
+        const int cut = min(unswA ? __ffs(unswA) - 1 : 0x7fffffff, swBm ? __ffs(swBm) - 1 : 0x7fffffff);
+        // at most one child can still be larger than 16 (the two sizes add up to at most 32)
+        if (l - cut > 16) f = cut;
+        else l = cut;
+    }
+    if (lane < m0) { idx[first + lane] = e; key[first + lane] = (uint8_t)k; }
+    __syncwarp();
+}
+
 // Partition [first, last) with one warp; returns cut.
 template <typename IdxT>
-__device__ int partitionWarp(const uint8_t* key, IdxT* idx, IdxT* tmp, int first, int last, int lane) {
-    if (lane == 0) moveMedianToFirst(key, idx, first, first + 1, first + (last - first) / 2, last - 1);
+__device__ int partitionWarp(uint8_t* key, IdxT* idx, IdxT* tmp, int first, int last, int lane) {
+    const int len = last - first, lo = first + 1;
+    // __move_median_to_first(first, first + 1, mid, last - 1): three lanes fetch, every lane decides
+    const int ia = first + 1, ib = first + len / 2, ic = last - 1;
+    const int kq = key[lane == 0 ? ia : (lane == 1 ? ib : ic)];
+    const int ka = __shfl_sync(0xffffffffu, kq, 0), kb = __shfl_sync(0xffffffffu, kq, 1), kc = __shfl_sync(0xffffffffu, kq, 2);
+    int sel, pv;
+    if (ka < kb) { if (kb < kc) { sel = ib; pv = kb; } else if (ka < kc) { sel = ic; pv = kc; } else { sel = ia; pv = ka; } }
+    else if (ka < kc) { sel = ia; pv = ka; }
+    else if (kb < kc) { sel = ic; pv = kc; }
+    else { sel = ib; pv = kb; }
+    if (lane == 0) swapPos(key, idx, first, sel);
     __syncwarp();
-    const int pv = key[idx[first]];
-    const int lo = first + 1, len = last - first;
     int cA, cB;
-    countAB(key, idx, lo, last, pv, lane, cA, cB);
+    countAB(key, lo, last, pv, lane, cA, cB);
     IdxT* posA = tmp + first;
     IdxT* posB = tmp + first + (len + 1) / 2;
     int m, mn;
-    assignAB(key, idx, lo, last, pv, lane, 0, 0, cB, posA, posB, m, mn);
+    assignAB(key, lo, last, pv, lane, 0, 0, cB, posA, posB, m, mn);
     __syncwarp();
     const int bm1 = m > 0 ? (int)posB[m - 1] : 0x7fffffff;
-    for (int k = lane; k < m; k += 32) {
-        const int a = posA[k], b = posB[k];
-        const IdxT t = idx[a]; idx[a] = idx[b]; idx[b] = t;
-    }
+    for (int k = lane; k < m; k += 32) swapPos(key, idx, (int)posA[k], (int)posB[k]);
     __syncwarp();
     return min(mn, bm1);
 }
@@ -195,9 +277,10 @@ __device__ int partitionWarp(const uint8_t* key, IdxT* idx, IdxT* tmp, int first
 template <typename IdxT>
 __device__ void sortDescending(const SelArrays<IdxT>& A, SelShared& S, int n) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint8_t* key = A.key;
+    uint8_t* key = A.key;
     IdxT* idx = A.idx;
     IdxT* tmp = A.tmp;
+    GVS_PROF_DECL
     for (int i = tid; i < n; i += kSelThreads) idx[i] = (IdxT)i;
     if (tid == 0) {
         S.bigTop = 0; S.nSeg[0] = 0; S.nSeg[1] = 0;
@@ -215,20 +298,20 @@ __device__ void sortDescending(const SelArrays<IdxT>& A, SelShared& S, int n) {
         const int first = S.bigSeg[top][0], last = S.bigSeg[top][1], depth = S.bigSeg[top][2];
         __syncthreads();
         if (depth == 0) {
-            if (tid == 0) { heapSort(key, idx + first, last - first); S.bigTop = top; }
+            if (tid == 0) { heapSort(key + first, idx + first, last - first); S.bigTop = top; }
             __syncthreads();
             continue;
         }
         if (tid == 0) {
             moveMedianToFirst(key, idx, first, first + 1, first + (last - first) / 2, last - 1);
-            S.pv = key[idx[first]];
+            S.pv = key[first];
         }
         __syncthreads();
         const int pv = S.pv, lo = first + 1, len = last - first;
         const int chunk = (((last - lo) + kSelWarps - 1) / kSelWarps + 31) & ~31;
         const int a = min(lo + warp * chunk, last), b = min(a + chunk, last);
         int cA, cB;
-        countAB(key, idx, a, b, pv, lane, cA, cB);
+        countAB(key, a, b, pv, lane, cA, cB);
         if (lane == 0) { S.wA[warp] = cA; S.wB[warp] = cB; }
         __syncthreads();
         int runA = 0, runB = 0, totalB = 0;
@@ -240,7 +323,7 @@ __device__ void sortDescending(const SelArrays<IdxT>& A, SelShared& S, int n) {
         IdxT* posA = tmp + first;
         IdxT* posB = tmp + first + (len + 1) / 2;
         int m, mn;
-        assignAB(key, idx, a, b, pv, lane, runA, runB, totalB, posA, posB, m, mn);
+        assignAB(key, a, b, pv, lane, runA, runB, totalB, posA, posB, m, mn);
         if (lane == 0) { S.wM[warp] = m; S.wMin[warp] = mn; }
         __syncthreads();
         int mTot = 0, mnAll = 0x7fffffff;
@@ -249,10 +332,7 @@ __device__ void sortDescending(const SelArrays<IdxT>& A, SelShared& S, int n) {
         const int bm1 = mTot > 0 ? (int)posB[mTot - 1] : 0x7fffffff;
         const int cut = min(mnAll, bm1);
         __syncthreads();  // everyone has read posB[mTot-1] before tmp is reused by children
-        for (int k = tid; k < mTot; k += kSelThreads) {
-            const int pa = posA[k], pb = posB[k];
-            const IdxT t = idx[pa]; idx[pa] = idx[pb]; idx[pb] = t;
-        }
+        for (int k = tid; k < mTot; k += kSelThreads) swapPos(key, idx, (int)posA[k], (int)posB[k]);
         if (tid == 0) {
             int t2 = top;
             const int d = depth - 1;
@@ -267,6 +347,7 @@ __device__ void sortDescending(const SelArrays<IdxT>& A, SelShared& S, int n) {
         __syncthreads();
     }
 
+    GVS_PROF(1);
     // ---- phase 2: small segments, breadth first, one warp per segment
     int cur = 0;
     while (true) {
@@ -277,21 +358,29 @@ __device__ void sortDescending(const SelArrays<IdxT>& A, SelShared& S, int n) {
         for (int s = warp; s < ns; s += kSelWarps) {
             const int first = segIn[3 * s], last = segIn[3 * s + 1], depth = segIn[3 * s + 2];
             if (depth == 0) {
-                if (lane == 0) heapSort(key, idx + first, last - first);
+                if (lane == 0) heapSort(key + first, idx + first, last - first);
                 continue;
             }
+            if (last - first <= 32) { sortSmallSegmentWarp(key, idx, first, last, depth, lane); continue; }
             const int cut = partitionWarp(key, idx, tmp, first, last, lane);
-            if (lane == 0) {
-                if (last - cut > 16) { int o = atomicAdd(&S.nSeg[cur ^ 1], 1); segOut[3 * o] = cut; segOut[3 * o + 1] = last; segOut[3 * o + 2] = depth - 1; }
-                if (cut - first > 16) { int o = atomicAdd(&S.nSeg[cur ^ 1], 1); segOut[3 * o] = first; segOut[3 * o + 1] = cut; segOut[3 * o + 2] = depth - 1; }
-            }
+            // children of at most 32 elements are finished right away in registers, larger ones go to the next level
+            if (last - cut > 32) {
+                if (lane == 0) { int o = atomicAdd(&S.nSeg[cur ^ 1], 1); segOut[3 * o] = cut; segOut[3 * o + 1] = last; segOut[3 * o + 2] = depth - 1; }
+            } else if (last - cut > 16) sortSmallSegmentWarp(key, idx, cut, last, depth - 1, lane);
+            if (cut - first > 32) {
+                if (lane == 0) { int o = atomicAdd(&S.nSeg[cur ^ 1], 1); segOut[3 * o] = first; segOut[3 * o + 1] = cut; segOut[3 * o + 2] = depth - 1; }
+            } else if (cut - first > 16) sortSmallSegmentWarp(key, idx, first, cut, depth - 1, lane);
         }
         __syncthreads();
         if (tid == 0) S.nSeg[cur] = 0;
         cur ^= 1;
         __syncthreads();
+#ifdef GVS_SEL_PROFILE
+        if (tid == 0) atomicAdd(&gSelProf[7], 1ull);
+#endif
     }
 
+    GVS_PROF(2);
     // ---- final insertion sort == stable sort by key; reversed -> tmp holds the descending order
     int* hist = A.hist;
     for (int i = tid; i < kSelWarps * 256; i += kSelThreads) hist[i] = 0;
@@ -300,7 +389,7 @@ __device__ void sortDescending(const SelArrays<IdxT>& A, SelShared& S, int n) {
     const int a = min(warp * chunk, n), b = min(a + chunk, n);
     for (int base = a; base < b; base += 32) {
         const int p = base + lane;
-        const int k = p < b ? (int)key[idx[p]] : 256 + lane;  // inactive lanes get unique keys
+        const int k = p < b ? (int)key[p] : 256 + lane;  // inactive lanes get unique keys
         const unsigned peers = __match_any_sync(0xffffffffu, k);
         if (p < b && (peers & lanemaskLt()) == 0) hist[warp * 256 + k] += __popc(peers);
         __syncwarp();
@@ -322,7 +411,7 @@ __device__ void sortDescending(const SelArrays<IdxT>& A, SelShared& S, int n) {
     for (int base = a; base < b; base += 32) {
         const int p = base + lane;
         const IdxT v = p < b ? idx[p] : (IdxT)0;
-        const int k = p < b ? (int)key[v] : 256 + lane;
+        const int k = p < b ? (int)key[p] : 256 + lane;
         const unsigned peers = __match_any_sync(0xffffffffu, k);
         if (p < b) {
             const int pos = hist[warp * 256 + k] + __popc(peers & lanemaskLt());
@@ -333,6 +422,7 @@ __device__ void sortDescending(const SelArrays<IdxT>& A, SelShared& S, int n) {
         __syncwarp();
     }
     __syncthreads();
+    GVS_PROF(3);
 }
 
 // ---- SSC (src/FeatureExtractor.cpp:410-461) --------------------------------------------------------------
@@ -531,6 +621,7 @@ select_kernel(const __grid_constant__ Geometry g, int nImages, const CandRec* __
         int* keptCntOut = keptCnt + img * kMaxLevels + level;
         KeptKey* keptOut = kept + (size_t)img * g.keptPerImage + lv.keptOff;
         if (n == 0) { if (tid == 0) *keptCntOut = 0; continue; }
+        GVS_PROF_DECL
 
         // ---- (a) order: scan cell counts, scatter records
         const int nCells = lv.nCols * lv.nRows;
@@ -566,6 +657,7 @@ select_kernel(const __grid_constant__ Geometry g, int nImages, const CandRec* __
         }
 
         // ---- (b) sort
+        GVS_PROF(0);
         sortDescending(A, S, n);
         const IdxT* sorted = A.tmp;
         if (sortedDbg) {  // parity tap: the permutation itself and, after ssc, the kept positions
@@ -575,10 +667,16 @@ select_kernel(const __grid_constant__ Geometry g, int nImages, const CandRec* __
 
         // ---- (c) ssc binary search (src/FeatureExtractor.cpp:396-461)
         const IdxT* res = nullptr;
+        GVS_PROF_DECL2
         int count = sscSearch<IdxT>(A, S, sorted, n, lv, A.bitmaps, reinterpret_cast<IdxT*>(A.lists), A.listCap, A.globalBitmap, &res);
+        GVS_PROF(4);
         if (count > lv.keptCap || count > A.listCap) { if (tid == 0) atomicOr(status, kStatKeptOverflow); count = min(lv.keptCap, A.listCap); }
         for (int i = tid; i < count; i += kSelThreads) keptOut[i] = A.xy[sorted[res[i]]];
         if (tid == 0) *keptCntOut = count;
+        GVS_PROF(5);
+#ifdef GVS_SEL_PROFILE
+        if (tid == 0) atomicAdd(&gSelProf[6], 1ull);
+#endif
     }
 }
 
@@ -641,6 +739,20 @@ void launchSelect(const Geometry& g, int nImages, const CandRec* recs, const int
         g, nImages, recs, nCand, cellCnt, kept, keptCnt, orderedDbg, sortedDbg, scratch, scratchPerCta, workCounter, status,
         maxCells, segCapSmall, maxCandCap(g), listCap, listsGlobal);
     ++*launches;
+#ifdef GVS_SEL_PROFILE
+    {
+        static int calls = 0;
+        if (++calls % 40 == 0) {
+            cudaStreamSynchronize(s);
+            unsigned long long h[8];
+            cudaMemcpyFromSymbol(h, gSelProf, sizeof(h));
+            const double tot = (double)(h[0] + h[1] + h[2] + h[3] + h[4] + h[5]);
+            fprintf(stderr, "[select profile] problems %llu  order %.1f%%  sort-cta %.1f%%  sort-warp %.1f%%  sort-final %.1f%%  ssc %.1f%%  out %.1f%%  cycles/problem %.0f  bfs levels/problem %.1f  cycles/level %.0f\n",
+                    h[6], 100 * h[0] / tot, 100 * h[1] / tot, 100 * h[2] / tot, 100 * h[3] / tot, 100 * h[4] / tot, 100 * h[5] / tot, tot / (double)h[6],
+                    h[7] / (double)h[6], (double)h[2] / (double)h[7]);
+        }
+    }
+#endif
     bool needBig = false;
     for (int l = 0; l < g.nLevels; l++) needBig |= g.lv[l].candCap > kSmallMax;
     if (needBig) {
