@@ -375,9 +375,6 @@ __device__ void sortDescending(const SelArrays<IdxT>& A, SelShared& S, int n) {
         if (tid == 0) S.nSeg[cur] = 0;
         cur ^= 1;
         __syncthreads();
-#ifdef GVS_SEL_PROFILE
-        if (tid == 0) atomicAdd(&gSelProf[7], 1ull);
-#endif
     }
 
     GVS_PROF(2);
@@ -434,44 +431,47 @@ __device__ void sortDescending(const SelArrays<IdxT>& A, SelShared& S, int n) {
 // 1/width away from an integer, far more than the double rounding error; an integer quotient is exact).
 // `limit`: a speculative pass may stop as soon as it has kept more than `limit` points (the search only needs to know
 // "more than Kmax" to choose its direction); it then returns limit + 1 and its list is incomplete.
+// The bitmap carries a border of two cells on every side (row pitch ncc + 4), so that the 5 x 5 block of a kept point never
+// needs clamping: lane r < 5 sets the five bits starting at bit(point) + (r - 2) * pitch - 2.
+__host__ __device__ inline int sscBitmapCells(int cols, int rows, int width) {
+    return ((2 * cols) / width + 5) * ((2 * rows) / width + 5);
+}
+
 template <typename IdxT>
 __device__ int sscPassWarp(const unsigned* xy, const IdxT* sorted, int n, int width, int ncc, int ncr, unsigned* bitmap,
                            IdxT* list, int listCap, int lane, int limit) {
-    const int bmWords = (ncc * ncr + 31) >> 5;
+    const int pitch = ncc + 4;
+    const int bmWords = (pitch * (ncr + 4) + 31) >> 5;
     for (int i = lane; i < bmWords; i += 32) bitmap[i] = 0;
     __syncwarp();
     // floor(v / width) = umulhi(v + 1, floor((2^32 - 1) / width)) for every width >= 1 while (v + 1) * width < 2^32
     // (round-down magic number; unlike the round-up form it also exists for width 1)
     const unsigned magic = 0xffffffffu / (unsigned)width;
+    const int coverOff = (lane - 2) * pitch - 2;   // used by lanes 0..4
     int cnt = 0;
     for (int base = 0; base < n; base += 32) {
         const int i = base + lane;
-        int row = 0, col = 0;
+        int row = 0, col = 0, bit = 0;
         bool active = false;
         if (i < n) {
             const unsigned q = xy[sorted[i]];
             col = (int)__umulhi(2 * (q & 0xfff) + 1, magic);
             row = (int)__umulhi(2 * ((q >> 12) & 0xfff) + 1, magic);
-            const int bit = row * ncc + col;
+            bit = (row + 2) * pitch + col + 2;
             active = !((bitmap[bit >> 5] >> (bit & 31)) & 1);
         }
         unsigned mask = __ballot_sync(0xffffffffu, active);
+        const int rc = (row << 16) | col;
         while (mask) {
             const int f = __ffs(mask) - 1;
-            const int fr = __shfl_sync(0xffffffffu, row, f), fc = __shfl_sync(0xffffffffu, col, f);
-            if (lane == 0 && cnt < listCap) list[cnt] = (IdxT)(base + f);
+            const int frc = __shfl_sync(0xffffffffu, rc, f);
+            if (lane < 5) {  // cover rows fr-2 .. fr+2, columns fc-2 .. fc+2
+                const int sbit = ((frc >> 16) + 2) * pitch + (frc & 0xffff) + 2 + coverOff, sh = sbit & 31;
+                atomicOr(&bitmap[sbit >> 5], 0x1fu << sh);
+                if (sh > 27) atomicOr(&bitmap[(sbit >> 5) + 1], 0x1fu >> (32 - sh));
+            } else if (lane == 5 && cnt < listCap) list[cnt] = (IdxT)(base + f);
             cnt++;
-            if (lane < 5) {  // cover rows fr-2 .. fr+2, columns fc-2 .. fc+2 (clamped to the grid)
-                const int r = fr - 2 + lane;
-                if (r >= 0 && r < ncr) {
-                    const int c0 = max(fc - 2, 0), c1 = min(fc + 2, ncc - 1);
-                    const int sbit = r * ncc + c0, len = c1 - c0 + 1, sh = sbit & 31;
-                    const unsigned m = (1u << len) - 1u;
-                    atomicOr(&bitmap[sbit >> 5], m << sh);
-                    if (sh + len > 32) atomicOr(&bitmap[(sbit >> 5) + 1], m >> (32 - sh));
-                }
-            }
-            if (active && abs(row - fr) <= 2 && abs(col - fc) <= 2) active = false;
+            if ((unsigned)(row - (frc >> 16) + 2) <= 4u && (unsigned)(col - (frc & 0xffff) + 2) <= 4u) active = false;
             mask = __ballot_sync(0xffffffffu, active);
         }
         __syncwarp();
@@ -495,6 +495,9 @@ __device__ int sscSearch(const SelArrays<IdxT>& A, SelShared& S, const IdxT* sor
     int low = max(1, (int)floor(sqrt((double)n / (double)K)));
     int finalNode = -1, finalCount = 0;
     while (true) {
+#ifdef GVS_SEL_PROFILE
+        if (tid == 0) atomicAdd(&gSelProf[7], 1ull);
+#endif
         if (low > high) break;  // (width == prevWidth cannot occur once low <= high: the bracket always shrinks)
         // node k of the 3-level tree: bracket [nl, nh], width nw; children 2k+1 (count < Kmin) and 2k+2 (count > Kmax)
         int nl[7], nh[7], nw[7];
@@ -504,7 +507,7 @@ __device__ int sscSearch(const SelArrays<IdxT>& A, SelShared& S, const IdxT* sor
             nw[k] = nl[k] + (nh[k] - nl[k]) / 2;
             if (k < 3) { nl[2 * k + 1] = nl[k]; nh[2 * k + 1] = nw[k] - 1; nl[2 * k + 2] = nw[k] + 1; nh[2 * k + 2] = nh[k]; }
         }
-        auto fits = [&](int k) { return nl[k] <= nh[k] && ((2 * cols) / nw[k] + 1) * ((2 * rows) / nw[k] + 1) <= kSscBitmapWords * 32; };
+        auto fits = [&](int k) { return nl[k] <= nh[k] && sscBitmapCells(cols, rows, nw[k]) <= kSscBitmapWords * 32; };
         const bool rootFits = fits(0);
         if (warp < 7) {
             bool valid = true;  // all ancestors must be valid brackets as well
@@ -540,7 +543,7 @@ __device__ int sscSearch(const SelArrays<IdxT>& A, SelShared& S, const IdxT* sor
                 // bracket exhausted on a truncated pass: the reference returns that pass in full (:412-416) -> redo it
                 const int w = nw[finalNode];
                 const int ncc = (2 * cols) / w + 1, ncr = (2 * rows) / w + 1;
-                const bool fitsSmem = ncc * ncr <= kSscBitmapWords * 32;
+                const bool fitsSmem = sscBitmapCells(cols, rows, w) <= kSscBitmapWords * 32;
                 if (warp == 0) {
                     const int c = sscPassWarp(A.xy, sorted, n, w, ncc, ncr, fitsSmem ? bitmaps : globalBitmap, lists, listCap, lane,
                                               0x7fffffff);
@@ -706,7 +709,7 @@ size_t selectScratchBytes(const Geometry& g) {
     // (2h+1) x (2w+1) cells, one bit each
     const size_t nMax = (size_t)std::max(maxCandCap(g), kSmallMax);
     size_t b = nMax * (4 + 4 + 4) + (size_t)2 * 3 * (nMax / 17 + 2) * 4 + ((nMax + 15) & ~(size_t)15);
-    b += ((size_t)(2 * g.lv[0].h + 1) * (2 * g.lv[0].w + 1) + 31) / 32 * 4 + 16;
+    b += ((size_t)sscBitmapCells(g.lv[0].w, g.lv[0].h, 1) + 31) / 32 * 4 + 16;
     b = (b + 255) & ~(size_t)255;
     return b + sscListScratchBytes(maxListCap(g));   // tail: the SSC kept lists when they do not fit shared memory
 }
@@ -747,9 +750,9 @@ void launchSelect(const Geometry& g, int nImages, const CandRec* recs, const int
             unsigned long long h[8];
             cudaMemcpyFromSymbol(h, gSelProf, sizeof(h));
             const double tot = (double)(h[0] + h[1] + h[2] + h[3] + h[4] + h[5]);
-            fprintf(stderr, "[select profile] problems %llu  order %.1f%%  sort-cta %.1f%%  sort-warp %.1f%%  sort-final %.1f%%  ssc %.1f%%  out %.1f%%  cycles/problem %.0f  bfs levels/problem %.1f  cycles/level %.0f\n",
+            fprintf(stderr, "[select profile] problems %llu  order %.1f%%  sort-cta %.1f%%  sort-warp %.1f%%  sort-final %.1f%%  ssc %.1f%%  out %.1f%%  cycles/problem %.0f  ssc rounds/problem %.2f  ssc cycles/round %.0f\n",
                     h[6], 100 * h[0] / tot, 100 * h[1] / tot, 100 * h[2] / tot, 100 * h[3] / tot, 100 * h[4] / tot, 100 * h[5] / tot, tot / (double)h[6],
-                    h[7] / (double)h[6], (double)h[2] / (double)h[7]);
+                    h[7] / (double)h[6], (double)h[4] / (double)h[7]);
         }
     }
 #endif
