@@ -447,7 +447,6 @@ __device__ int sscPassWarp(const unsigned* xy, const IdxT* sorted, int n, int wi
     // floor(v / width) = umulhi(v + 1, floor((2^32 - 1) / width)) for every width >= 1 while (v + 1) * width < 2^32
     // (round-down magic number; unlike the round-up form it also exists for width 1)
     const unsigned magic = 0xffffffffu / (unsigned)width;
-    const int coverOff = (lane - 2) * pitch - 2;   // used by lanes 0..4
     int cnt = 0;
     for (int base = 0; base < n; base += 32) {
         const int i = base + lane;
@@ -462,16 +461,26 @@ __device__ int sscPassWarp(const unsigned* xy, const IdxT* sorted, int n, int wi
         }
         unsigned mask = __ballot_sync(0xffffffffu, active);
         const int rc = (row << 16) | col;
+        // Two uncovered lanes per step: the first one (f1) is always kept; the second one (f2) is kept in the same step unless
+        // f1 covers it, which every lane can tell from the two shuffled cells.  Lanes 0..4 / 8..12 set the two 5 x 5 blocks.
+        const int coverOff2 = ((lane & 7) - 2) * pitch - 2;
         while (mask) {
-            const int f = __ffs(mask) - 1;
-            const int frc = __shfl_sync(0xffffffffu, rc, f);
-            if (lane < 5) {  // cover rows fr-2 .. fr+2, columns fc-2 .. fc+2
-                const int sbit = ((frc >> 16) + 2) * pitch + (frc & 0xffff) + 2 + coverOff, sh = sbit & 31;
+            const int f1 = __ffs(mask) - 1;
+            const unsigned rest = mask & (mask - 1);
+            const int f2 = rest ? __ffs(rest) - 1 : f1;
+            const int c1 = __shfl_sync(0xffffffffu, rc, f1), c2 = __shfl_sync(0xffffffffu, rc, f2);
+            const int r1 = c1 >> 16, q1 = c1 & 0xffff, r2 = c2 >> 16, q2 = c2 & 0xffff;
+            const bool both = rest != 0 && !((unsigned)(r2 - r1 + 2) <= 4u && (unsigned)(q2 - q1 + 2) <= 4u);
+            const bool second = lane >= 8;
+            if ((lane & 7) < 5 && lane < 16 && (!second || both)) {
+                const int sbit = ((second ? r2 : r1) + 2) * pitch + (second ? q2 : q1) + 2 + coverOff2, sh = sbit & 31;
                 atomicOr(&bitmap[sbit >> 5], 0x1fu << sh);
                 if (sh > 27) atomicOr(&bitmap[(sbit >> 5) + 1], 0x1fu >> (32 - sh));
-            } else if (lane == 5 && cnt < listCap) list[cnt] = (IdxT)(base + f);
-            cnt++;
-            if ((unsigned)(row - (frc >> 16) + 2) <= 4u && (unsigned)(col - (frc & 0xffff) + 2) <= 4u) active = false;
+            } else if (lane == 5) { if (cnt < listCap) list[cnt] = (IdxT)(base + f1); }
+            else if (lane == 13 && both) { if (cnt + 1 < listCap) list[cnt + 1] = (IdxT)(base + f2); }
+            cnt += both ? 2 : 1;
+            if ((unsigned)(row - r1 + 2) <= 4u && (unsigned)(col - q1 + 2) <= 4u) active = false;
+            if (both && (unsigned)(row - r2 + 2) <= 4u && (unsigned)(col - q2 + 2) <= 4u) active = false;
             mask = __ballot_sync(0xffffffffu, active);
         }
         __syncwarp();
