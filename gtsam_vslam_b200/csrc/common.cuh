@@ -80,7 +80,8 @@ inline void ensureDynamicSmem(K kernel, size_t bytes, size_t* cache /* [64] zero
     int dev = 0;
     cudaGetDevice(&dev);
     dev &= 63;
-    if (bytes > 48 * 1024 && cache[dev] < bytes) {
+    // (opt in from 40 KB: a kernel's static shared memory counts against the 48 KB default as well)
+    if (bytes > 40 * 1024 && cache[dev] < bytes) {
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
         cache[dev] = bytes;
     }
