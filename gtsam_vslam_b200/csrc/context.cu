@@ -349,7 +349,10 @@ constexpr int kGraphMaxImages = 8;
 int runExtract(gvs_extractor* fe, int n) {
     cudaStream_t s = fe->stream;
     static const bool noGraph = getenv("GVS_NO_GRAPH") != nullptr;
-    if (!fe->timing && !noGraph && n <= kGraphMaxImages) {
+    // (a caller's stream that is itself being captured takes the plain launches: they become part of the caller's graph)
+    cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &capturing) != cudaSuccess) { cudaGetLastError(); capturing = cudaStreamCaptureStatusNone; }
+    if (!fe->timing && !noGraph && n <= kGraphMaxImages && capturing == cudaStreamCaptureStatusNone) {
         auto it = fe->graphs.find(n);
         if (it == fe->graphs.end()) {
             cudaGraph_t graph = nullptr;
