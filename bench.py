@@ -81,7 +81,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -90,16 +90,19 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Samples whose line arrived inside [t0, t1] (the timed region); all samples if that leaves none."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
+        inside = [r for t, r in self.rows if t0 is not None and t0 <= t <= t1 + 0.03]
+        rows = inside if inside else [r for _, r in self.rows]
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
                 for nm, v in zip(names, r[5:9]):
@@ -233,13 +236,14 @@ def main():
     def step_resident():
         fm.track_stereo_batch_resident(F, w, h)
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()   # (nvidia-smi needs ~0.1 s before its first line: started ahead of the warm-up, filtered by time below)
     for _ in range(args.warmup):
         step_resident()
     fm.sync()
-    sampler = ClockSampler(local)
     barrier()
-    if rank == 0:
-        sampler.start()
+    t_region0 = time.perf_counter()
     l0 = launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -248,9 +252,10 @@ def main():
     e1.record(stream)
     barrier()
     fm.sync()
+    t_region1 = time.perf_counter()
     dev_ms = e0.elapsed_time(e1) / args.steps
     n_launch = (launches() - l0) // args.steps
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_region0, t_region1) if rank == 0 else None
 
     # ---- per-stage device times: same work, same region length, but every kernel in order on ONE stream (timing mode
     # of the library) so that each stage's CUDA-event time is that kernel alone, not its overlap with the other side
