@@ -32,6 +32,8 @@ namespace gvs {
 #define GVS_RING_DX {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1}
 #define GVS_RING_DY {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3}
 
+constexpr int kFastWarps = 8;  // warps per CTA (256 threads)
+
 struct FastSmemLayout {
     int tileWords, tileRows;    // image tile: words per row, rows
     int scoreWords, scoreRows;  // score tile: words per row (1 zero word each side), rows (1 zero row each side)
@@ -52,7 +54,8 @@ __host__ __device__ inline FastSmemLayout fastLayout(int maxGW, int maxGH) {
     L.maskOff = L.scoreOff + L.scoreWords * L.scoreRows * 4;
     L.listOff = ((L.maskOff + maxUnits * 12 + 15) / 16) * 16;
     L.queueOff = L.listOff + kFastCellsPerItem * L.listCap * 4;
-    L.queueCap = maxUnits * maxGH;                       // per pair parity
+    // per pair parity; every warp owns a private region of `chunk` entries (chunk = its share of the unit words rounded up to 32)
+    L.queueCap = maxUnits * maxGH + kFastWarps * 32 + kFastWarps;
     L.total = L.queueOff + 2 * L.queueCap * 2;
     return L;
 }
@@ -115,7 +118,10 @@ __device__ __forceinline__ unsigned scorePair(const unsigned (&W)[7][3], int tMi
     return s0 | (s1 << 8);
 }
 
-__global__ void __launch_bounds__(256, 3)
+#ifndef GVS_FAST_CTAS
+#define GVS_FAST_CTAS 3
+#endif
+__global__ void __launch_bounds__(256, GVS_FAST_CTAS)
 fast_cells_kernel(const __grid_constant__ Geometry g, const uint8_t* __restrict__ slab,
                   const FastItem* __restrict__ items, int maxGW, int maxGH, CandRec* __restrict__ recs,
                   int* __restrict__ nCand, unsigned short* __restrict__ cellCnt, int* __restrict__ status) {
@@ -179,10 +185,16 @@ fast_cells_kernel(const __grid_constant__ Geometry g, const uint8_t* __restrict_
     // images) redoes the cells that produced no key at tMin.  A pass = 2a pre-test + compaction, 2b exact scores, 3 local maxima.
     unsigned short* queue = reinterpret_cast<unsigned short*>(smem + L.queueOff);
     unsigned short* score16 = reinterpret_cast<unsigned short*>(score);
-    __shared__ int sQ[2];
     const int tMin = g.tMin, tMax = g.tMax;
-    const unsigned ltMask = (1u << (tid & 31)) - 1u;
+    const int lane = tid & 31, warp = tid >> 5;
+    const unsigned ltMask = (1u << lane) - 1u;
     const int nUnits = nW * rows;
+    // Every warp owns a contiguous share of the unit words and private queue regions for it, so that compaction needs no
+    // shared counters or atomics and phase 2b follows 2a without a CTA barrier.
+    const int chunk = (((nUnits + kFastWarps - 1) / kFastWarps) + 31) & ~31;
+    const int u0 = min(warp * chunk, nUnits), u1 = min(u0 + chunk, nUnits);
+    unsigned short* q0 = queue + warp * chunk;                 // pair 0 of a unit / phase 3: units with a non-zero score
+    unsigned short* q1 = queue + L.queueCap + warp * chunk;    // pair 1 of a unit
     unsigned redo = 0;  // pass 1: bit c = cell c of the strip is redone
     // bytes of unit word j that lie in a cell that is being redone
     auto redoBytes = [&](int j) {
@@ -196,19 +208,19 @@ fast_cells_kernel(const __grid_constant__ Geometry g, const uint8_t* __restrict_
     };
     for (int pass = 0; pass < 2; pass++) {
         const int T = pass == 0 ? tMax : tMin;
-        if (tid < 2) sQ[tid] = 0;
-        __syncthreads();
 
         // ---- 2a. pre-test on 4 pixels at once (native VABSDIFF4): a 9-arc contains ring pixel k or k+8 for every k, so a
         // corner at threshold T needs |I(ring_k) - I(p)| > T for k in {0 or 8} and for k in {4 or 12}.  Per byte,
         // d > T  <=>  bit 7 of ((d & 0x7f) + (127 - T)) | d   (T <= 127; above that the test degrades to d >= 128, still
-        // necessary).  Surviving pixel pairs are compacted into two queues (one per pair position: 2b has no divergent code).
+        // necessary).  Surviving pixel pairs are compacted into the warp's two queues (one per pair position: 2b has no
+        // divergent code).
         const unsigned kT = (unsigned)max(127 - T, 0) * 0x01010101u;
         auto gt = [&](unsigned d) { return ((d & 0x7f7f7f7fu) + kT) | d; };
-        for (int base = 0; base < nUnits; base += 256) {
-            const int i = base + tid;
-            bool p0 = false, p1 = false;
-            if (i < nUnits) {
+        int n0 = 0, n1 = 0;
+        for (int base = u0; base < u1; base += 32) {
+            const int i = base + lane;
+            unsigned f = 0;  // bit 7 of byte b: pixel b of the unit passes the pre-test
+            if (i < u1) {
                 const int ry = (int)__umulhi((unsigned)i, magicU), j = i - ry * nW;
                 const unsigned* p = tile + (ry + 3) * L.tileWords + j;
                 const unsigned c = p[1];
@@ -216,29 +228,22 @@ fast_cells_kernel(const __grid_constant__ Geometry g, const uint8_t* __restrict_
                 const unsigned lf = __funnelshift_r(p[0], c, 8), rt = __funnelshift_r(c, p[2], 24);
                 const unsigned v = gt(__vabsdiffu4(up, c)) | gt(__vabsdiffu4(dn, c));
                 const unsigned h = gt(__vabsdiffu4(lf, c)) | gt(__vabsdiffu4(rt, c));
-                unsigned f = v & h & 0x80808080u & masks[3 * j];
+                f = v & h & 0x80808080u & masks[3 * j];
                 if (pass) f &= redoBytes(j);
-                p0 = (f & 0x0000ffffu) != 0;
-                p1 = (f & 0xffff0000u) != 0;
             }
+            const bool p0 = (f & 0x0000ffffu) != 0, p1 = (f & 0xffff0000u) != 0;
             const unsigned b0 = __ballot_sync(0xffffffffu, p0), b1 = __ballot_sync(0xffffffffu, p1);
-            int o0 = 0, o1 = 0;
-            if ((tid & 31) == 0) {
-                if (b0) o0 = atomicAdd(&sQ[0], __popc(b0));
-                if (b1) o1 = atomicAdd(&sQ[1], __popc(b1));
-            }
-            o0 = __shfl_sync(0xffffffffu, o0, 0); o1 = __shfl_sync(0xffffffffu, o1, 0);
-            if (p0) queue[o0 + __popc(b0 & ltMask)] = (unsigned short)i;
-            if (p1) queue[L.queueCap + o1 + __popc(b1 & ltMask)] = (unsigned short)i;
+            if (p0) q0[n0 + __popc(b0 & ltMask)] = (unsigned short)i;
+            if (p1) q1[n1 + __popc(b1 & ltMask)] = (unsigned short)i;
+            n0 += __popc(b0); n1 += __popc(b1);
         }
-        __syncthreads();
+        __syncwarp();
 
-        // ---- 2b. exact scores of the surviving pairs: 21 word loads, ring pairs by PRMT, min3-of-min3 arcs; a score below
-        // the pass threshold is stored as 0, exactly like the score buffer of cv::FAST at that threshold
-        const int n0 = sQ[0], n1 = sQ[1];
-        for (int q = tid; q < n0 + n1; q += 256) {
+        // ---- 2b. exact scores of the warp's surviving pairs: 21 word loads, ring pairs by PRMT, min3-of-min3 arcs; a score
+        // below the pass threshold is stored as 0, exactly like the score buffer of cv::FAST at that threshold
+        for (int q = lane; q < n0 + n1; q += 32) {
             const bool second = q >= n0;
-            const int i = second ? queue[L.queueCap + q - n0] : queue[q];
+            const int i = second ? q1[q - n0] : q0[q];
             const int ry = (int)__umulhi((unsigned)i, magicU), j = i - ry * nW;
             unsigned W[7][3];
 #pragma unroll
@@ -252,12 +257,28 @@ fast_cells_kernel(const __grid_constant__ Geometry g, const uint8_t* __restrict_
         }
         __syncthreads();
 
-        // ---- 3. strict local maxima inside each cell, four pixels at a time -> per-cell lists
-        for (int i = tid; i < nUnits; i += 256) {
+        // ---- 3. strict local maxima inside each cell, four pixels at a time -> per-cell lists.  The warp first compacts the
+        // unit words of its share that hold a non-zero score (about a third on textured images) and tests only those.
+        int nz = 0;
+        for (int base = u0; base < u1; base += 32) {
+            const int i = base + lane;
+            bool any = false;
+            if (i < u1) {
+                const int ry = (int)__umulhi((unsigned)i, magicU), j = i - ry * nW;
+                unsigned c = score[(ry + 1) * L.scoreWords + j + 1];
+                if (pass) c &= redoBytes(j);   // the other cells were listed by pass 0
+                any = c != 0;
+            }
+            const unsigned b = __ballot_sync(0xffffffffu, any);
+            if (any) q0[nz + __popc(b & ltMask)] = (unsigned short)i;
+            nz += __popc(b);
+        }
+        __syncwarp();
+        for (int q = lane; q < nz; q += 32) {
+            const int i = q0[q];
             const int ry = (int)__umulhi((unsigned)i, magicU), j = i - ry * nW;
             const unsigned* sp = score + (ry + 1) * L.scoreWords + j + 1;
             const unsigned c = sp[0];
-            if (c == 0) continue;
             const unsigned hasL = masks[3 * j + 1], hasR = masks[3 * j + 2];
             const int P = L.scoreWords;
             const unsigned up = sp[-P], dn = sp[P];
