@@ -32,7 +32,7 @@ SYMBOLS = [
     "gvs_matcher_create", "gvs_matcher_destroy", "gvs_stereo_match_batch", "gvs_stereo_download",
     "gvs_assign_grids_batch", "gvs_grid_download", "gvs_track_stereo_batch_host",
     "gvs_track_stereo_batch_resident", "gvs_matcher_sync", "gvs_matcher_set_stream", "gvs_match_projection", "gvs_descriptor_distance",
-    "gvs_match_projection_lba", "gvs_median_descriptor", "gvs_project_mappoints", "gvs_extractor_enable_timing", "gvs_extractor_stage_times", "gvs_matcher_launch_count",
+    "gvs_match_projection_lba", "gvs_median_descriptor", "gvs_project_mappoints", "gvs_find_outliers", "gvs_extractor_enable_timing", "gvs_extractor_stage_times", "gvs_matcher_launch_count",
     "gvs_extractor_launch_count",
     "gvs_pipeline_create", "gvs_pipeline_destroy", "gvs_pipeline_submit", "gvs_pipeline_wait", "gvs_pipeline_download",
     "gvs_pipeline_handles", "gvs_pipeline_release",
@@ -120,6 +120,7 @@ def load_library() -> C.CDLL:
     lib.gvs_median_descriptor.argtypes = [vp, vp, vp, i32, vp]
     dbl = C.c_double
     lib.gvs_project_mappoints.argtypes = [vp, vp, dbl, dbl, dbl, dbl, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
+    lib.gvs_find_outliers.argtypes = [vp, i32, i32, vp, vp, dbl, dbl, dbl, dbl, dbl, f32, i32] + [vp] * 10 + [C.POINTER(i32), C.POINTER(i32)]
     lib.gvs_extractor_enable_timing.argtypes = [vp, i32]
     lib.gvs_extractor_stage_times.argtypes = [vp, C.POINTER(StageTimes)]
     lib.gvs_matcher_launch_count.argtypes = [vp, C.POINTER(C.c_int64)]
@@ -464,6 +465,33 @@ class FeatureMatcher:
         _check(self._lib.gvs_project_mappoints(self.h, _p(keep[0]), fx, fy, cx, cy, width, height, M, _p(keep[1]), _p(keep[2]), _p(keep[3]),
                                                _p(keep[4]), _p(pred), _p(scaleLevel), _p(inF)))
         return inF[:M]
+
+    # -- FeatureTracker::findOutliersR / findOutliersMono (src/FeatureTracker.cpp:582-684) against frame `frame` of the last batch
+    def _find_outliers(self, mode, frame, estimPose, toCameraR, fx, fy, cx, cy, thres, closeDist, valid, wPos, inFrame, inFrameR,
+                       matches, outliers, keys=None):
+        c = lambda a, dt: None if a is None else np.ascontiguousarray(a, dt)
+        assert matches.dtype == np.int32 and matches.flags.c_contiguous and outliers.dtype == np.uint8
+        keep = [c(estimPose, np.float64), c(toCameraR, np.float64), c(valid, np.uint8), c(wPos, np.float64), c(inFrame, np.uint8),
+                c(inFrameR, np.uint8)]
+        st = [None] * 4
+        if keys is not None:  # the caller's TrackedKeys copies of the stereo arrays follow the device state
+            st = [keys.estimatedDepth, keys.close, keys.rightIdxs, keys.leftIdxs]
+            assert st[0].dtype == np.float32 and st[1].dtype in (np.uint8, np.bool_) and st[2].dtype == np.int32 and st[3].dtype == np.int32
+        nIn, nSt = C.c_int(0), C.c_int(0)
+        _check(self._lib.gvs_find_outliers(self.h, frame, mode, _p(keep[0]), _p(keep[1]), fx, fy, cx, cy, thres, closeDist, len(matches),
+                                           _p(keep[2]), _p(keep[3]), _p(keep[4]), _p(keep[5]), _p(matches), _p(outliers), _p(st[0]),
+                                           _p(st[1]), _p(st[2]), _p(st[3]), C.byref(nIn), C.byref(nSt)))
+        return nIn.value, nSt.value
+
+    def findOutliersR(self, frame, estimPose, toCameraR, fx, fy, cx, cy, thres, closeDist, valid, wPos, inFrame, inFrameR, matches,
+                      outliers, keys=None):
+        """Returns (number of nInliers increments, nStereo); matches / outliers (and keys' stereo arrays) are updated in place."""
+        return self._find_outliers(0, frame, estimPose, toCameraR, fx, fy, cx, cy, thres, closeDist, valid, wPos, inFrame, inFrameR,
+                                   matches, outliers, keys)
+
+    def findOutliersMono(self, frame, estimPose, fx, fy, cx, cy, thres, valid, wPos, inFrame, matches, outliers):
+        return self._find_outliers(1, frame, estimPose, None, fx, fy, cx, cy, thres, 0.0, valid, wPos, inFrame, None, matches,
+                                   outliers)[0]
 
     def DescriptorDistance(self, a: np.ndarray, b: np.ndarray) -> np.ndarray:
         a = np.ascontiguousarray(a, np.uint8).reshape(-1, 32); b = np.ascontiguousarray(b, np.uint8).reshape(-1, 32)

@@ -47,7 +47,10 @@ struct Geometry {
 };
 
 // One FAST work item = a strip of up to kFastCellsPerItem consecutive cells of one cell row.
-constexpr int kFastCellsPerItem = 4;
+#ifndef GVS_FAST_CELLS
+#define GVS_FAST_CELLS 4
+#endif
+constexpr int kFastCellsPerItem = GVS_FAST_CELLS;
 struct FastItem {
     short level, iR, iC0, nC;
 };
@@ -91,7 +94,7 @@ struct StageTimer;
 
 // ---- kernel launchers (one translation unit each) -------------------------------------------------
 void launchPyramid(const Geometry& g, uint8_t* slab, const ResizeTap* taps, const uint4* xw, const uint4* xs,
-                   const unsigned short* xbase, int nImages, cudaStream_t s, int* launches);
+                   const unsigned short* xbase, unsigned narrowMask, int nImages, cudaStream_t s, int* launches);
 void launchPrepare(const Geometry& g, const uint8_t* src, int channels, const float* mapx, const float* mapy, uint8_t* slab,
                    int nImages, cudaStream_t s, int* launches);
 void launchRepack(const Geometry& g, const uint8_t* tight, uint8_t* slab, int nImages, cudaStream_t s, int* launches);
@@ -193,6 +196,32 @@ void launchMedianDescriptor(const uint8_t* descs, const int* offsets, int P, int
 void launchWorldToFrame(int M, const double* poseInv, double fx, double fy, double cx, double cy, int width, int height,
                         const double* wPos, const float* maxScaleDist, const float* logScale, const int* nScaleLev, float* pred,
                         int* scaleLevel, uint8_t* inFrame, cudaStream_t s, int* launches);
+// FeatureTracker::findOutliersR / findOutliersMono
+struct OutlierArgs {
+    int mode;                  // 0 findOutliersR, 1 findOutliersMono
+    int M, NL, NR;
+    const double* pose;        // estimPose, row-major
+    const double* poseR;       // toCameraR (mode 0)
+    double fx, fy, cx, cy, thres;
+    float closeDist;           // zedPtr->mBaseline * fm.closeNumber
+    const float* invSigma;     // feLeft->InvSigmaFactor
+    const double* wPos;        // M x 4
+    const uint8_t* valid;      // mp != nullptr (NULL = all)
+    const uint8_t* inFrame;
+    const uint8_t* inFrameR;
+    int* matches;              // M x 2, in-out
+    uint8_t* outliers;         // M, in-out
+    const gvs_keypoint* kpL;   // the frame's keys
+    const gvs_keypoint* kpR;
+    float* depth;              // the frame's stereo arrays, in-out
+    uint8_t* close;
+    int* rightIdxs;
+    int* leftIdxs;
+    int* act;                  // M scratch
+    int* firstClear;           // NL scratch, preset to INT_MAX-like
+    int* counters;             // [0] inliers, [1] stereo
+};
+void launchFindOutliers(const OutlierArgs& a, cudaStream_t s, int* launches);
 void launchHamming(const uint8_t* a, const uint8_t* b, int n, int* out, cudaStream_t s, int* launches);
 
 // status bits written by kernels into a device int (checked on sync)

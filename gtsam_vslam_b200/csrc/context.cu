@@ -72,7 +72,9 @@ struct gvs_extractor {
     ResizeTap* taps = nullptr;
     uint4* xWeights = nullptr;        // per group of 4 destination columns: a0 | a1 << 16 of each column
     uint4* xSelectors = nullptr;      // ... PRMT selector (| 1 << 16 when the pair sits in the upper 8 bytes of the window)
-    unsigned short* xBase = nullptr;  // ... 4-byte aligned source offset of the 12-byte window
+    unsigned short* xBase = nullptr;  // ... source offset of the window: sx of the first column (narrow levels) or the 4-byte aligned
+                                      //     start of the 12-byte window (other levels)
+    unsigned pyrNarrowMask = 0;       // bit l: every column group of level l spans at most 8 source bytes (pyr_down_kernel<true>)
     FastItem* fastItems = nullptr;
     int nFastItems = 0;
     // CUDA graphs of the extraction pipeline for small batches (latency mode): one instantiated graph per batch size
@@ -318,7 +320,7 @@ static int enqueueExtract(gvs_extractor* fe, int n, cudaStream_t s) {
     const bool T = fe->timing;
     GVS_CUDA_OK(cudaMemsetAsync(fe->status, 0, sizeof(int), s));
     if (T) cudaEventRecord(fe->ev[0], s);
-    launchPyramid(g, fe->slab, fe->taps, fe->xWeights, fe->xSelectors, fe->xBase, n, s, &fe->launches);
+    launchPyramid(g, fe->slab, fe->taps, fe->xWeights, fe->xSelectors, fe->xBase, fe->pyrNarrowMask, n, s, &fe->launches);
     if (T) cudaEventRecord(fe->ev[1], s);
     launchFast(g, fe->slab, fe->fastItems, fe->nFastItems, n, fe->recs, fe->nCand, fe->cellCnt, fe->status, s, &fe->launches);
     if (T) cudaEventRecord(fe->ev[2], s);
@@ -478,15 +480,22 @@ int gvs_extractor_create(gvs_extractor** out, const gvs_extractor_params* params
         std::vector<unsigned short> base(nGroups, 0);
         for (int l = 1; l < g.nLevels; l++) {
             const LevelGeom& D = g.lv[l];
+            // narrow level: the pairs (sx, sx+1) of the 4 columns of every group lie within 8 bytes of the first column's sx
+            bool narrow = true;
+            for (int dx0 = 0; dx0 < D.w; dx0 += 4) {
+                const int last = std::min(dx0 + 3, D.w - 1);
+                if (taps[D.tabX + last].pad - taps[D.tabX + dx0].ofs > 7) narrow = false;
+            }
+            if (narrow) fe->pyrNarrowMask |= 1u << l;
             for (int dx0 = 0; dx0 < D.w; dx0 += 4) {
                 const size_t gi = (size_t)(D.tabX + dx0) / 4;
-                const int b = taps[D.tabX + dx0].ofs & ~3;
+                const int b = narrow ? taps[D.tabX + dx0].ofs : (taps[D.tabX + dx0].ofs & ~3);
                 base[gi] = (unsigned short)b;
                 for (int i = 0; i < 4 && dx0 + i < D.w; i++) {
                     const ResizeTap& t = taps[D.tabX + dx0 + i];
                     const int o = t.ofs - b, o1 = t.pad - b;
                     if (o < 0 || o1 > 11 || o1 < o) { int rc = fail(GVS_ERR_INVALID, "im_scale too large for the pyramid kernel's 12-byte source window"); destroyExtractor(fe); return rc; }
-                    const int hi = o >= 4;
+                    const int hi = narrow ? 0 : o >= 4;
                     w[4 * gi + i] = (unsigned)(unsigned short)t.a0 | ((unsigned)(unsigned short)t.a1 << 16);
                     sl[4 * gi + i] = (unsigned)(o - 4 * hi) | ((unsigned)(o1 - 4 * hi) << 4) | ((unsigned)hi << 16);
                 }
@@ -503,9 +512,13 @@ int gvs_extractor_create(gvs_extractor** out, const gvs_extractor_params* params
         std::vector<FastItem> items;
         for (int l = 0; l < g.nLevels; l++) {
             fe->g.lv[l].fastItemBase = (int)items.size();
+            // a cell row is cut into the fewest strips of at most kFastCellsPerItem cells, of equal length +- 1
+            const int nCols = g.lv[l].nCols, nStrips = (nCols + kFastCellsPerItem - 1) / kFastCellsPerItem;
             for (int iR = 0; iR < g.lv[l].nRows; iR++)
-                for (int iC = 0; iC < g.lv[l].nCols; iC += kFastCellsPerItem)
-                    items.push_back(FastItem{(short)l, (short)iR, (short)iC, (short)std::min(kFastCellsPerItem, g.lv[l].nCols - iC)});
+                for (int k = 0; k < nStrips; k++) {
+                    const int c0 = (int)((long long)k * nCols / nStrips), c1 = (int)((long long)(k + 1) * nCols / nStrips);
+                    items.push_back(FastItem{(short)l, (short)iR, (short)c0, (short)(c1 - c0)});
+                }
         }
         fe->nFastItems = (int)items.size();
         GVS_TRY(devAlloc(&fe->fastItems, items.size()));
@@ -1318,6 +1331,87 @@ int gvs_project_mappoints(gvs_matcher* m, const double* pose_inv, double fx, dou
     GVS_CUDA_OK(cudaMemcpyAsync(scale_level, b + oSl, M * 4, cudaMemcpyDeviceToHost, s));
     GVS_CUDA_OK(cudaMemcpyAsync(in_frame, b + oIf, M, cudaMemcpyDeviceToHost, s));
     GVS_CUDA_OK(cudaStreamSynchronize(s));
+    GVS_CUDA_OK(cudaGetLastError());
+    return GVS_OK;
+}
+
+int gvs_find_outliers(gvs_matcher* m, int frame, int mode, const double* pose, const double* pose_r, double fx, double fy,
+                      double cx, double cy, double thres, float close_dist, int count, const uint8_t* valid,
+                      const double* world_pos, const uint8_t* in_frame, const uint8_t* in_frame_r, int32_t* matches,
+                      uint8_t* outliers, float* est_depth, uint8_t* close, int32_t* right_idxs, int32_t* left_idxs,
+                      int* n_inliers, int* n_stereo) {
+    if (!m || !pose || !n_inliers || !n_stereo || count < 0) return fail(GVS_ERR_INVALID, "bad argument");
+    if (mode != 0 && mode != 1) return fail(GVS_ERR_INVALID, "bad mode");
+    if (mode == 0 && (!pose_r || !m->stereoValid)) return fail(GVS_ERR_STATE, "findOutliersR needs toCameraR and a stereo batch");
+    if (frame < 0 || frame >= m->L->lastN || (mode == 0 && frame >= m->lastFrames)) return fail(GVS_ERR_INVALID, "bad frame");
+    *n_inliers = 0; *n_stereo = 0;
+    int rc = gvs_matcher_sync(m);
+    if (rc) return rc;
+    const int oL = m->L->hOff[frame], NL = m->L->hOff[frame + 1] - oL;
+    const bool two = mode == 0;
+    const int oR = two ? m->R->hOff[frame] : 0, NR = two ? m->R->hOff[frame + 1] - oR : 0;
+    DeviceGuard deviceGuard(m->L->device);
+    cudaStream_t s = m->L->stream;
+    if (count > 0) {
+        if (!world_pos || !matches || !outliers) return fail(GVS_ERR_INVALID, "null array");
+        for (int i = 0; i < count; i++)
+            if (matches[2 * i] >= NL || (two && matches[2 * i + 1] >= NR))
+                return fail(GVS_ERR_INVALID, "match index outside the frame's keys");
+        const size_t M = (size_t)count;
+        auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+        const size_t oPose = 0, oSig = al(256), oW = oSig + al(kMaxLevels * 4), oVa = oW + al(M * 32), oIf = oVa + al(M), oIr = oIf + al(M),
+                     oMt = oIr + al(M), oOut = oMt + al(M * 8), oAct = oOut + al(M), oFc = oAct + al(M * 4),
+                     oCnt = oFc + al((size_t)std::max(NL, 1) * 4), total = oCnt + al(16);
+        if (total > m->pjBytes) {
+            cudaFree(m->pj); m->pj = nullptr; m->pjBytes = 0;
+            GVS_CUDA_OK(devAlloc(&m->pj, total));
+            m->pjBytes = total;
+        }
+        uint8_t* b = m->pj;
+        auto up = [&](size_t off, const void* src, size_t bytes) -> cudaError_t {
+            return src ? cudaMemcpyAsync(b + off, src, bytes, cudaMemcpyHostToDevice, s) : cudaSuccess;
+        };
+        GVS_CUDA_OK(up(oPose, pose, 128));
+        GVS_CUDA_OK(up(oPose + 128, pose_r, 128));
+        GVS_CUDA_OK(up(oSig, &m->L->invSigma[0], (size_t)m->L->g.nLevels * 4));
+        GVS_CUDA_OK(up(oW, world_pos, M * 32));
+        GVS_CUDA_OK(up(oVa, valid, M));
+        GVS_CUDA_OK(up(oIf, in_frame, M));
+        GVS_CUDA_OK(up(oIr, in_frame_r, M));
+        GVS_CUDA_OK(up(oMt, matches, M * 8));
+        GVS_CUDA_OK(up(oOut, outliers, M));
+        GVS_CUDA_OK(cudaMemsetAsync(b + oFc, 0x7f, (size_t)std::max(NL, 1) * 4, s));
+        GVS_CUDA_OK(cudaMemsetAsync(b + oCnt, 0, 16, s));
+        OutlierArgs a{};
+        a.mode = mode; a.M = count; a.NL = NL; a.NR = NR;
+        a.pose = reinterpret_cast<double*>(b + oPose); a.poseR = reinterpret_cast<double*>(b + oPose + 128);
+        a.fx = fx; a.fy = fy; a.cx = cx; a.cy = cy; a.thres = thres; a.closeDist = close_dist;
+        a.invSigma = reinterpret_cast<float*>(b + oSig);
+        a.wPos = reinterpret_cast<double*>(b + oW);
+        a.valid = valid ? b + oVa : nullptr; a.inFrame = in_frame ? b + oIf : nullptr; a.inFrameR = in_frame_r ? b + oIr : nullptr;
+        a.matches = reinterpret_cast<int*>(b + oMt); a.outliers = b + oOut;
+        a.kpL = m->L->kps + oL; a.kpR = two ? m->R->kps + oR : nullptr;
+        a.depth = two ? m->depth + oL : nullptr; a.close = two ? m->close + oL : nullptr;
+        a.rightIdxs = two ? m->rightIdxs + oL : nullptr; a.leftIdxs = two ? m->leftIdxs + oR : nullptr;
+        a.act = reinterpret_cast<int*>(b + oAct); a.firstClear = reinterpret_cast<int*>(b + oFc);
+        a.counters = reinterpret_cast<int*>(b + oCnt);
+        int launches = 0;
+        launchFindOutliers(a, s, &launches);
+        m->launchesTotal += launches;
+        int cnt[2] = {0, 0};
+        GVS_CUDA_OK(cudaMemcpyAsync(matches, b + oMt, M * 8, cudaMemcpyDeviceToHost, s));
+        GVS_CUDA_OK(cudaMemcpyAsync(outliers, b + oOut, M, cudaMemcpyDeviceToHost, s));
+        GVS_CUDA_OK(cudaMemcpyAsync(cnt, b + oCnt, 8, cudaMemcpyDeviceToHost, s));
+        GVS_CUDA_OK(cudaStreamSynchronize(s));
+        *n_inliers = cnt[0]; *n_stereo = cnt[1];
+    }
+    if (two) {
+        if (est_depth) GVS_CUDA_OK(cudaMemcpyAsync(est_depth, m->depth + oL, (size_t)NL * 4, cudaMemcpyDeviceToHost, s));
+        if (close) GVS_CUDA_OK(cudaMemcpyAsync(close, m->close + oL, (size_t)NL, cudaMemcpyDeviceToHost, s));
+        if (right_idxs) GVS_CUDA_OK(cudaMemcpyAsync(right_idxs, m->rightIdxs + oL, (size_t)NL * 4, cudaMemcpyDeviceToHost, s));
+        if (left_idxs) GVS_CUDA_OK(cudaMemcpyAsync(left_idxs, m->leftIdxs + oR, (size_t)NR * 4, cudaMemcpyDeviceToHost, s));
+        GVS_CUDA_OK(cudaStreamSynchronize(s));
+    }
     GVS_CUDA_OK(cudaGetLastError());
     return GVS_OK;
 }

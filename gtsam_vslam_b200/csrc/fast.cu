@@ -12,17 +12,20 @@
 //   thresholds: T_cell = maxFast if any local max has score >= maxFast, else minFast  (the reference falls
 //   back when the first call returns no keypoint *after* NMS, :592-593).
 //
-// Work item = up to 4 consecutive cells of one cell row (about 150 x 40 px); CTA = 256 threads.
+// Work item = up to kFastCellsPerItem consecutive cells of one cell row (about 150 x 40 px); CTA = 256 threads.
 //   1. the (rows+6) x (cols+6) u8 tile is staged in shared memory with 4-byte loads;
+//   Every warp then owns a contiguous share of the tile's 4-pixel unit words and private queue regions for it (no shared
+//   counters, no atomics, no CTA barrier between 2a and 2b):
 //   2a. a pre-test on 4 pixels per instruction (VABSDIFF4 on the up/down and left/right ring pairs) discards pixels that
-//      cannot be corners at the minimum threshold; survivors are compacted pair-wise into shared-memory queues;
+//      cannot be corners at the pass threshold; surviving pixel pairs are compacted into the warp's queues with ballots;
 //   2b. exact scores of the surviving pairs in u16x2 lanes: 21 word loads, ring pairs extracted with PRMT
 //      (lane = 257 * pixel), 9-wide circular min/max as min3 of min3 with the native VIMNMX3.U16x2
 //      (78 instructions per pair for both polarities);
-//   3. strict local maxima, four pixels at a time (vcmpgtu4 against the 8 shifted neighbour words, masked at cell
-//      borders), are appended to a per-cell list in shared memory, filtered by T_cell, ranked in row-major order
-//      inside the cell and written as 8-byte records {x, y, score, cell, rank} to a per-(image, level) buffer;
-//      K3/K4 (select.cu) restores the reference's emission order from (cell, rank).
+//   3. the unit words with a non-zero score are compacted the same way; strict local maxima, four pixels at a time (vcmpgtu4
+//      against the 8 shifted neighbour words, masked at cell borders), are appended to a per-cell list in shared memory, ranked
+//      in row-major order inside the cell and written as 8-byte records {x, y, score, cell, rank} to a per-(image, level)
+//      buffer; K3/K4 (select.cu) restores the reference's emission order from (cell, rank).
+//   Pass 0 runs 2a-3 at maxFastThreshold on every cell; pass 1 redoes the cells that listed no key at minFastThreshold.
 // Bound: integer ALU, not HBM: see DESIGN.md.
 #include "common.cuh"
 

@@ -460,6 +460,91 @@ void launchWorldToFrame(int M, const double* poseInv, double fx, double fy, doub
     ++*launches;
 }
 
+// FeatureTracker::findOutliersR / findOutliersMono (src/FeatureTracker.cpp:582-649, :651-684) with check2dError (:147-164).
+// The reference walks the matches in index order; everything a match computes is independent of the others except the
+// stereo-partner check, which reads keysLeft.close[nIdx] and clears it (with the depth and the stereo pair) when the right
+// observation is an outlier.  If several matches point at the same left key, only those up to and including the first one that
+// clears see close == true.  Hence two passes: pass 1 (thread per match) evaluates the reprojection tests against the
+// original `close` and records, per left key, the smallest match index that would clear it (atomicMin); pass 2 counts a
+// stereo inlier only before that index and applies the clearing at that index.  Double precision, explicit round-to-nearest
+// operations in the reference's left-to-right order (no FMA), like world_to_frame_kernel.
+__device__ __forceinline__ void mulPose(const double* __restrict__ P, const double* __restrict__ w, double (&pt)[3]) {
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+        pt[r] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P[4 * r], w[0]), __dmul_rn(P[4 * r + 1], w[1])), __dmul_rn(P[4 * r + 2], w[2])),
+                          __dmul_rn(P[4 * r + 3], w[3]));
+}
+
+// FeatureTracker::check2dError, :147-164
+__device__ __forceinline__ bool check2dError(const double (&p)[3], float ox, float oy, double fx, double fy, double cx, double cy,
+                                             double thres, double weight) {
+    if (p[2] <= 0) return true;
+    const double invZ = __ddiv_rn(1.0, p[2]);
+    const double u = __dadd_rn(__dmul_rn(__dmul_rn(fx, p[0]), invZ), cx), v = __dadd_rn(__dmul_rn(__dmul_rn(fy, p[1]), invZ), cy);
+    const double eU = __dsub_rn((double)ox, u), eV = __dsub_rn((double)oy, v);
+    const double error = __dmul_rn(__dadd_rn(__dmul_rn(eU, eU), __dmul_rn(eV, eV)), weight);
+    return error > thres;
+}
+
+__global__ void find_outliers_kernel(const OutlierArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.M) return;
+    a.act[i] = 0;
+    if (a.valid && !a.valid[i]) return;                     // if ( !mp ) continue;
+    const int first = a.matches[2 * i], second = a.matches[2 * i + 1];
+    const double* w = a.wPos + 4 * (size_t)i;
+    double p[3];
+    int nIdx;
+    bool right = false;
+    if (first >= 0) {
+        if (a.inFrame && !a.inFrame[i]) return;
+        mulPose(a.pose, w, p);
+        nIdx = first;
+    } else if (a.mode == 0 && second >= 0) {
+        if (a.inFrameR && !a.inFrameR[i]) return;
+        right = true;
+        mulPose(a.poseR, w, p);
+        nIdx = second;
+    } else return;
+    const gvs_keypoint k = right ? a.kpR[nIdx] : a.kpL[nIdx];
+    const bool outlier = check2dError(p, k.x, k.y, a.fx, a.fy, a.cx, a.cy, a.thres, (double)a.invSigma[k.octave]);
+    a.outliers[i] = outlier ? 1 : 0;
+    if (outlier) return;
+    atomicAdd(&a.counters[0], 1);                           // nInliers++
+    if (a.mode != 0 || right || !(p[2] < (double)a.closeDist) || !a.close[nIdx] || second < 0) return;
+    double pr[3];
+    mulPose(a.poseR, w, pr);
+    const gvs_keypoint kr = a.kpR[second];
+    if (!check2dError(pr, kr.x, kr.y, a.fx, a.fy, a.cx, a.cy, a.thres, (double)a.invSigma[kr.octave])) a.act[i] = 1;
+    else { a.act[i] = 2; atomicMin(&a.firstClear[nIdx], i); }
+}
+
+__global__ void find_outliers_apply_kernel(const OutlierArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.M) return;
+    const int act = a.act[i];
+    if (act == 0) return;
+    const int nIdx = a.matches[2 * i], fc = a.firstClear[nIdx];
+    if (act == 1) { if (i < fc) atomicAdd(&a.counters[1], 1); return; }   // nStereo++ while close[nIdx] is still set
+    if (i != fc) return;
+    a.depth[nIdx] = -1.f;
+    a.close[nIdx] = 0;
+    const int rIdx = a.rightIdxs[nIdx];
+    a.rightIdxs[nIdx] = -1;
+    if (rIdx >= 0 && rIdx < a.NR) a.leftIdxs[rIdx] = -1;   // close[nIdx] implies a stereo partner; the reference indexes unchecked
+    a.matches[2 * i + 1] = -1;
+}
+
+void launchFindOutliers(const OutlierArgs& a, cudaStream_t s, int* launches) {
+    if (a.M <= 0) return;
+    find_outliers_kernel<<<(a.M + 127) / 128, 128, 0, s>>>(a);
+    ++*launches;
+    if (a.mode == 0) {
+        find_outliers_apply_kernel<<<(a.M + 127) / 128, 128, 0, s>>>(a);
+        ++*launches;
+    }
+}
+
 __global__ void hamming_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, int n, int* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;

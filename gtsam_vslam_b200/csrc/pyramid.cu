@@ -12,10 +12,16 @@
 
 namespace gvs {
 
-// Thread = 4 consecutive destination pixels of one row.  Their source bytes lie in a 12-byte window that starts at a
-// 4-byte aligned offset which is the same for every row, so the host stores, per group of 4 columns, the window offset
-// and per column {a0 | a1 << 16, PRMT selector of (S[sx], S[sx+1]) inside the window}.  Per pixel: 2 PRMT + 2 IDP2A for
-// the two horizontal interpolations, then the fixed-point vertical blend.  3 aligned word loads per source row.
+// Thread = 4 consecutive destination pixels of two consecutive rows.  Their source bytes lie in a short window whose position
+// is the same for every row, so the host stores, per group of 4 columns, the window offset and per column
+// {a0 | a1 << 16, PRMT selector of (S[sx], S[sx+1]) inside the window}; both tables are shared by the two rows.
+// NARROW (every group of the level spans at most 8 source bytes: scale factors up to about 1.75): the window starts at the
+// first column's sx; two funnel shifts align the three loaded words to it and one PRMT per pixel picks the pair.
+// Otherwise the window is 12 bytes from the aligned offset and the selector carries which 8-byte half holds the pair.
+// Per pixel and source row: 1 PRMT + 1 IDP2A (a0*S[sx] + a1*S[sx+1]); the horizontal interpolation of a source row that
+// both destination rows need (sy(dy+1) = sy(dy) + 1, the common case at scale 1.2) is computed once.  The vertical blend
+// ((b*(H>>4))>>16 as a high multiply by b << 16) and the 4-byte store follow.  3 aligned word loads per source row.
+template <bool NARROW>
 __global__ void __launch_bounds__(256)
 pyr_down_kernel(const __grid_constant__ Geometry g, uint8_t* __restrict__ slab, const ResizeTap* __restrict__ taps,
                 const uint4* __restrict__ xw, const uint4* __restrict__ xs, const unsigned short* __restrict__ xbase, int level) {
@@ -23,33 +29,70 @@ pyr_down_kernel(const __grid_constant__ Geometry g, uint8_t* __restrict__ slab, 
     const LevelGeom& D = g.lv[level];
     const int grp = blockIdx.x * 32 + threadIdx.x;  // group of 4 destination columns
     const int dx0 = grp * 4;
-    const int dy = blockIdx.y * 8 + threadIdx.y;
+    const int dy = (blockIdx.y * 8 + threadIdx.y) * 2;
     if (dx0 >= D.w || dy >= D.h) return;
+    const bool two = dy + 1 < D.h;
     const int img = blockIdx.z;
     const uint8_t* src = levelPtr((const uint8_t*)slab, g, img, level - 1);
     uint8_t* dst = levelPtr(slab, g, img, level);
 
-    const ResizeTap ty = taps[D.tabY + dy];
+    const ResizeTap t0 = taps[D.tabY + dy], t1 = taps[D.tabY + dy + (two ? 1 : 0)];
     const int gi = D.tabX / 4 + grp;
     const unsigned base = xbase[gi];
-    const unsigned* r0 = reinterpret_cast<const unsigned*>(src + (size_t)ty.ofs * S.pitch + base);
-    const unsigned* r1 = reinterpret_cast<const unsigned*>(src + (size_t)ty.pad * S.pitch + base);
-    const unsigned p0 = __ldg(r0), p1 = __ldg(r0 + 1), p2 = __ldg(r0 + 2);
-    const unsigned q0 = __ldg(r1), q1 = __ldg(r1 + 1), q2 = __ldg(r1 + 2);
+    const unsigned al = NARROW ? (base & ~3u) : base, sh = (base & 3u) * 8u;
     const uint4 wv = __ldg(xw + gi), sv = __ldg(xs + gi);
     const unsigned wts[4] = {wv.x, wv.y, wv.z, wv.w}, sel[4] = {sv.x, sv.y, sv.z, sv.w};
-    const unsigned b0 = (unsigned)ty.a0, b1 = (unsigned)ty.a1;
-    unsigned out = 0;
+    // horizontal interpolation of one source row for the 4 columns, already shifted right by 4
+    auto hrow = [&](int row, unsigned (&h)[4]) {
+        const unsigned* r = reinterpret_cast<const unsigned*>(src + (size_t)row * S.pitch + al);
+        const unsigned p0 = __ldg(r), p1 = __ldg(r + 1), p2 = __ldg(r + 2);
+        if (NARROW) {
+            const unsigned lo = __funnelshift_r(p0, p1, sh), hi = __funnelshift_r(p1, p2, sh);
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const bool hi = (sel[i] >> 16) != 0;
-        const unsigned s0 = __byte_perm(hi ? p1 : p0, hi ? p2 : p1, sel[i]);
-        const unsigned s1 = __byte_perm(hi ? q1 : q0, hi ? q2 : q1, sel[i]);
-        const unsigned h0 = __dp2a_lo(wts[i], s0, 0u), h1 = __dp2a_lo(wts[i], s1, 0u);
-        const unsigned v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
-        out |= (v & 0xff) << (8 * i);
+            for (int i = 0; i < 4; i++) h[i] = __dp2a_lo(wts[i], __byte_perm(lo, hi, sel[i]), 0u) >> 4;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const bool up = (sel[i] >> 16) != 0;
+                h[i] = __dp2a_lo(wts[i], __byte_perm(up ? p1 : p0, up ? p2 : p1, sel[i]), 0u) >> 4;
+            }
+        }
+    };
+    auto blend = [&](const unsigned (&h0)[4], const unsigned (&h1)[4], const ResizeTap& t, int y) {
+        const unsigned b0 = (unsigned)t.a0 << 16, b1 = (unsigned)t.a1 << 16;   // (b*(h))>>16 == umulhi(b << 16, h), b <= 2048
+        unsigned out = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const unsigned v = (__umulhi(b0, h0[i]) + __umulhi(b1, h1[i]) + 2) >> 2;
+            out |= (v & 0xff) << (8 * i);
+        }
+        *reinterpret_cast<unsigned*>(dst + (size_t)y * D.pitch + dx0) = out;
+    };
+    unsigned hA0[4], hA1[4], hB0[4], hB1[4];
+    hrow(t0.ofs, hA0);
+    if (t0.pad != t0.ofs) hrow(t0.pad, hA1);
+    else {
+#pragma unroll
+        for (int i = 0; i < 4; i++) hA1[i] = hA0[i];
     }
-    *reinterpret_cast<unsigned*>(dst + (size_t)dy * D.pitch + dx0) = out;
+    blend(hA0, hA1, t0, dy);
+    if (!two) return;
+    // the rows of dy + 1 (uniform across the warp: all its threads share dy)
+    if (t1.ofs == t0.pad) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) hB0[i] = hA1[i];
+    } else if (t1.ofs == t0.ofs) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) hB0[i] = hA0[i];
+    } else hrow(t1.ofs, hB0);
+    if (t1.pad == t1.ofs) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) hB1[i] = hB0[i];
+    } else if (t1.pad == t0.pad) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) hB1[i] = hA1[i];
+    } else hrow(t1.pad, hB1);
+    blend(hB0, hB1, t1, dy + 1);
 }
 
 // Tightly packed host batches arrive with one contiguous DMA (about 55 GB/s over PCIe Gen5, against about 8 GB/s for a
@@ -141,11 +184,12 @@ void launchPrepare(const Geometry& g, const uint8_t* src, int channels, const fl
 }
 
 void launchPyramid(const Geometry& g, uint8_t* slab, const ResizeTap* taps, const uint4* xw, const uint4* xs,
-                   const unsigned short* xbase, int nImages, cudaStream_t s, int* launches) {
+                   const unsigned short* xbase, unsigned narrowMask, int nImages, cudaStream_t s, int* launches) {
     for (int l = 1; l < g.nLevels; l++) {
         dim3 block(32, 8);
-        dim3 grid((g.lv[l].w + 127) / 128, (g.lv[l].h + 7) / 8, nImages);
-        pyr_down_kernel<<<grid, block, 0, s>>>(g, slab, taps, xw, xs, xbase, l);
+        dim3 grid((g.lv[l].w + 127) / 128, (g.lv[l].h + 15) / 16, nImages);
+        if ((narrowMask >> l) & 1u) pyr_down_kernel<true><<<grid, block, 0, s>>>(g, slab, taps, xw, xs, xbase, l);
+        else pyr_down_kernel<false><<<grid, block, 0, s>>>(g, slab, taps, xw, xs, xbase, l);
         ++*launches;
     }
 }

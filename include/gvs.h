@@ -235,6 +235,28 @@ int gvs_project_mappoints(gvs_matcher* fm, const double* pose_inv, double fx, do
                           int count, const double* world_pos, const float* max_scale_dist, const float* log_scale,
                           const int32_t* n_scale_lev, float* pred, int32_t* scale_level, uint8_t* in_frame);
 
+/* FeatureTracker::findOutliersR (src/FeatureTracker.cpp:582-649; mode 0) and findOutliersMono (:651-684; mode 1) with
+ * check2dError (:147-164), for the `count` active map points against frame `frame` of the last batch (the
+ * outlier scoring that follows every pose estimate).  The frame's keys and stereo arrays are the device-resident ones, and the
+ * stereo arrays are UPDATED on the device when a stereo partner is rejected (:636-641), so the next gvs_match_projection call
+ * sees what the reference's next matchByProjectionRPred sees in keysLeft.
+ *   pose      estimPose, 16 doubles row-major;  pose_r  toCameraR = (estimPose^-1 * extrinsics)^-1 (:584-585; mode 0 only)
+ *   thres     chi-square threshold; close_dist = zedPtr->mBaseline * fm.closeNumber (:623)
+ *   valid     activeMapPoints[i] != nullptr (NULL = all valid); world_pos  count x 4 doubles (MapPoint::getWordPose4d)
+ *   in_frame / in_frame_r  MapPoint::inFrame / inFrameR (NULL = all true)
+ *   matches   count x 2 (pair<int,int>), in-out: .second is set to -1 where the right observation is rejected (:641);
+ *             indices must lie inside the frame's key arrays (the reference indexes unchecked)
+ *   outliers  count, in-out: written exactly where the reference writes MPsOutliers[i]
+ *   est_depth, close (n_left), right_idxs (n_left), left_idxs (n_right): optional host copies of the frame's stereo arrays
+ *             (TrackedKeys::estimatedDepth / close / rightIdxs / leftIdxs), refreshed from the device after the call
+ *   *n_inliers = number of nInliers++ executed (the reference increments its int& argument); *n_stereo = findOutliersR's
+ *             return value (0 in mode 1, where the reference returns nInliers). */
+int gvs_find_outliers(gvs_matcher* fm, int frame, int mode, const double* pose, const double* pose_r, double fx, double fy,
+                      double cx, double cy, double thres, float close_dist, int count, const uint8_t* valid,
+                      const double* world_pos, const uint8_t* in_frame, const uint8_t* in_frame_r, int32_t* matches,
+                      uint8_t* outliers, float* est_depth, uint8_t* close, int32_t* right_idxs, int32_t* left_idxs,
+                      int* n_inliers, int* n_stereo);
+
 /* MapPoint::calcDescriptor, src/Map.cpp:145-210, for n_points map points at once: descs = the observation descriptors
  * of all points back to back (32 bytes each), offsets[n_points + 1]; best_idx[p] = index inside point p's own list of
  * the descriptor with the least median Hamming distance to the others (-1 for an empty list). */

@@ -921,6 +921,63 @@ void ora_world_to_frame(const double* poseInv, double fx, double fy, double cx, 
     }
 }
 
+// FeatureTracker::check2dError (src/FeatureTracker.cpp:147-164), on the first three rows of pose * wp
+static bool check2dErrorRef(const double* P, const double* w, float ox, float oy, double fx, double fy, double cx, double cy, double thres,
+                            double weight, double* zOut) {
+    double p[3];
+    for (int r = 0; r < 3; r++) p[r] = ((P[4 * r] * w[0] + P[4 * r + 1] * w[1]) + P[4 * r + 2] * w[2]) + P[4 * r + 3] * w[3];
+    if (zOut) *zOut = p[2];
+    if (p[2] <= 0) return true;
+    const double invZ = 1.0f / p[2];
+    const double u = fx * p[0] * invZ + cx, v = fy * p[1] * invZ + cy;
+    const double errorU = (double)ox - u, errorV = (double)oy - v;
+    const double error = (errorU * errorU + errorV * errorV) * weight;
+    return error > thres;
+}
+
+// FeatureTracker::findOutliersR (src/FeatureTracker.cpp:582-649; mode 0) / findOutliersMono (:651-684; mode 1), the sequential
+// loop as written.  pose / poseR: estimPose / toCameraR, 16 doubles row-major (the two inverses of :584-585
+// are the caller's).  matches (M x 2), outliers, depth, close, rightIdxs, leftIdxs are in-out; counts[0] += nInliers++,
+// counts[1] = nStereo.  Restated, not compiled from the reference: FeatureTracker.cpp needs GTSAM.
+void ora_find_outliers(int mode, const double* pose, const double* poseR, double fx, double fy, double cx, double cy, double thres,
+                       float closeDist, const float* invSigma, int M, const uint8_t* valid, const double* wPos, const uint8_t* inFrame,
+                       const uint8_t* inFrameR, int* matches, uint8_t* outliers, const KeyPoint* kl, const KeyPoint* kr, float* depth,
+                       uint8_t* close, int* rightIdxs, int* leftIdxs, int* counts) {
+    int nStereo = 0;
+    for (int i = 0; i < M; i++) {
+        if (valid && !valid[i]) continue;
+        const double* w = wPos + 4 * i;
+        int nIdx; bool right = false; const double* P;
+        if (matches[2 * i] >= 0) {
+            if (inFrame && !inFrame[i]) continue;
+            P = pose; nIdx = matches[2 * i];
+        } else if (mode == 0 && matches[2 * i + 1] >= 0) {
+            if (inFrameR && !inFrameR[i]) continue;
+            right = true; P = poseR; nIdx = matches[2 * i + 1];
+        } else continue;
+        const KeyPoint& k = right ? kr[nIdx] : kl[nIdx];
+        double z = 0;
+        const bool outlier = check2dErrorRef(P, w, k.x, k.y, fx, fy, cx, cy, thres, (double)invSigma[k.octave], &z);
+        outliers[i] = outlier;
+        if (outlier) continue;
+        counts[0]++;
+        if (mode != 0) continue;
+        if (z < closeDist && close[nIdx] && !right) {
+            if (matches[2 * i + 1] < 0) continue;
+            const KeyPoint& k2 = kr[matches[2 * i + 1]];
+            if (!check2dErrorRef(poseR, w, k2.x, k2.y, fx, fy, cx, cy, thres, (double)invSigma[k2.octave], nullptr)) nStereo++;
+            else {
+                depth[nIdx] = -1; close[nIdx] = 0;
+                const int rIdx = rightIdxs[nIdx];
+                rightIdxs[nIdx] = -1;
+                if (rIdx >= 0) leftIdxs[rIdx] = -1;
+                matches[2 * i + 1] = -1;
+            }
+        }
+    }
+    counts[1] = nStereo;
+}
+
 int ora_descriptor_distance(const uint8_t* a, const uint8_t* b) { return descriptorDistance(a, b); }
 
 // ---- primitive-level entry points (pinned one by one against cv2 in tests/test_oracle_vs_cv2.py)

@@ -200,6 +200,23 @@ def world_to_frame(poseInv, fx, fy, cx, cy, width, height, wPos, maxScaleDist, l
     return inF
 
 
+def find_outliers(mode, pose, poseR, fx, fy, cx, cy, thres, closeDist, invSigma, valid, wPos, inFrame, inFrameR, matches, outliers,
+                  kl, kr, depth, close, rightIdxs, leftIdxs):
+    """findOutliersR (mode 0) / findOutliersMono (mode 1), reference src/FeatureTracker.cpp:582-684; matches, outliers and the
+    four stereo arrays are modified in place; returns (nInliers increments, nStereo)."""
+    c = lambda a, dt: None if a is None else np.ascontiguousarray(a, dt)
+    for a, dt in ((matches, np.int32), (outliers, np.uint8)):
+        assert a.dtype == dt and a.flags.c_contiguous
+    cnt = np.zeros(2, np.int32)
+    keep = [c(pose, np.float64), c(poseR, np.float64), c(invSigma, np.float32), c(valid, np.uint8), c(wPos, np.float64),
+            c(inFrame, np.uint8), c(inFrameR, np.uint8), np.ascontiguousarray(kl), None if kr is None else np.ascontiguousarray(kr)]
+    lib().ora_find_outliers(mode, _p(keep[0]), _p(keep[1]), C.c_double(fx), C.c_double(fy), C.c_double(cx), C.c_double(cy),
+                            C.c_double(thres), C.c_float(closeDist), _p(keep[2]), len(matches), _p(keep[3]), _p(keep[4]), _p(keep[5]),
+                            _p(keep[6]), _p(matches), _p(outliers), _p(keep[7]), _p(keep[8]), _p(depth), _p(close), _p(rightIdxs),
+                            _p(leftIdxs), _p(cnt))
+    return int(cnt[0]), int(cnt[1])
+
+
 def stereo_frames(params, fx, baseline, L: np.ndarray, R: np.ndarray, shape: int, threads: int):
     """CPU baseline: run F stereo frames; returns (total matches, per-frame left key counts)."""
     L = np.ascontiguousarray(L, np.uint8); R = np.ascontiguousarray(R, np.uint8)

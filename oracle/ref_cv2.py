@@ -732,6 +732,65 @@ def worldToFrame(wPos: np.ndarray, predPoseInv: np.ndarray, fx, fy, cx, cy, widt
     return ok
 
 
+def _check2dError(P, w, obs, fx, fy, cx, cy, thres, weight):
+    """FeatureTracker::check2dError (src/FeatureTracker.cpp:147-164); returns (outlier, z)."""
+    p = [((float(P[r, 0]) * w[0] + float(P[r, 1]) * w[1]) + float(P[r, 2]) * w[2]) + float(P[r, 3]) * w[3] for r in range(3)]
+    if p[2] <= 0:
+        return True, p[2]
+    invZ = 1.0 / p[2]
+    u = fx * p[0] * invZ + cx
+    v = fy * p[1] * invZ + cy
+    eU = float(obs[0]) - u
+    eV = float(obs[1]) - v
+    return (eU * eU + eV * eV) * weight > thres, p[2]
+
+
+def findOutliers(mode, estimPose, toCameraR, fx, fy, cx, cy, thres, closeDist, invSigma, valid, wPos, inFrame, inFrameR, matches,
+                 outliers, keysL, keysR, depth, close, rightIdxs, leftIdxs):
+    """FeatureTracker::findOutliersR (src/FeatureTracker.cpp:582-649; mode 0) / findOutliersMono (:651-684; mode 1).
+    keysL / keysR: structured keypoint arrays (x, y, octave); in-out arrays are modified; returns (nInliers increments, nStereo)."""
+    nIn = nStereo = 0
+    closeDist = float(_F32(closeDist))
+    for i in range(len(matches)):
+        if valid is not None and not valid[i]:
+            continue
+        w = [float(v) for v in wPos[i]]
+        right = False
+        if matches[i][0] >= 0:
+            if inFrame is not None and not inFrame[i]:
+                continue
+            P, nIdx = estimPose, int(matches[i][0])
+            k = keysL[nIdx]
+        elif mode == 0 and matches[i][1] >= 0:
+            if inFrameR is not None and not inFrameR[i]:
+                continue
+            right, P, nIdx = True, toCameraR, int(matches[i][1])
+            k = keysR[nIdx]
+        else:
+            continue
+        outlier, z = _check2dError(P, w, (k["x"], k["y"]), fx, fy, cx, cy, thres, float(invSigma[int(k["octave"])]))
+        outliers[i] = 1 if outlier else 0
+        if outlier:
+            continue
+        nIn += 1
+        if mode == 0 and z < closeDist and close[nIdx] and not right:
+            if matches[i][1] < 0:
+                continue
+            k2 = keysR[int(matches[i][1])]
+            outlierR, _ = _check2dError(toCameraR, w, (k2["x"], k2["y"]), fx, fy, cx, cy, thres, float(invSigma[int(k2["octave"])]))
+            if not outlierR:
+                nStereo += 1
+            else:
+                depth[nIdx] = -1
+                close[nIdx] = 0
+                rIdx = int(rightIdxs[nIdx])
+                rightIdxs[nIdx] = -1
+                if rIdx >= 0:
+                    leftIdxs[rIdx] = -1
+                matches[i][1] = -1
+    return nIn, nStereo
+
+
 def calcDescriptor(descs: np.ndarray) -> int:
     """MapPoint::calcDescriptor (src/Map.cpp:145-210): index of the descriptor with the least median distance to the rest."""
     N = len(descs)

@@ -441,6 +441,44 @@ def test_world_to_frame_projection():
     assert np.max(np.abs(pa - pb), initial=0) <= 1e-3 and np.array_equal(pa, pb)   # tolerance of the north star, and bit exact
 
 
+@pytest.mark.parametrize("mode", [0, 1])
+def test_find_outliers(mode):
+    """SURVEY 8(f) rank 3: FeatureTracker::findOutliersR / findOutliersMono on the device-resident frame against the oracle's
+    sequential loop: outlier flags, match pairs, counts and the cleared stereo arrays bit exact; the device-resident stereo
+    arrays follow (a second download sees the cleared pairs)."""
+    from test_oracle_vs_cv2 import _outlier_case, _run_outliers, _inv_sigma_factor
+    cfg = synth.CONFIGS["small"]
+    w, h = cfg["width"], cfg["height"]
+    L, R = synth.stereo_pair(w, h, cfg["disparity"], seed=5)
+    feL, feR, fm = _handles(cfg, 1)
+    k = gvs.extractORBAndStereoMatch(fm, L, R)
+    oL, oR, kl, dl, kr, dr, st = _oracle_frame(cfg, L, R)
+    assert np.array_equal(k.rightIdxs, st["rightIdxs"]) and np.array_equal(feL.InvSigmaFactor, _inv_sigma_factor(cfg["n_levels"]))
+    cam = (cfg["fx"], cfg["fx"], w / 2.0, h / 2.0)
+    for seed in (1, 2):
+        # the oracle starts from the stereo arrays the device currently holds (they change from call to call)
+        cur = dict(estimatedDepth=k.estimatedDepth.copy(), close=k.close.copy(), rightIdxs=k.rightIdxs.copy(), leftIdxs=k.leftIdxs.copy())
+        c = _outlier_case(kl, kr, cur, cfg["fx"], w / 2.0, h / 2.0, cfg["baseline"], seed=seed, M=2500)
+        ref = _run_outliers(cpu_ref.find_outliers, mode, c, cam, feL.InvSigmaFactor, kl, kr, cur)
+        m = c["matches"].copy(); out = np.full(len(m), 7, np.uint8)
+        if mode == 0:
+            cnt = fm.findOutliersR(0, c["pose"], c["poseR"], *cam, c["thres"], c["closeDist"], c["valid"], c["wPos"], c["inFrame"],
+                                   c["inFrameR"], m, out, keys=k)
+        else:
+            cnt = (fm.findOutliersMono(0, c["pose"], *cam, c["thres"], c["valid"], c["wPos"], c["inFrame"], m, out), 0)
+        assert tuple(cnt) == tuple(ref[0]), (cnt, ref[0])
+        assert np.array_equal(m, ref[1]) and np.array_equal(out, ref[2])
+        if mode == 0:
+            for got, want in zip((k.estimatedDepth, k.close, k.rightIdxs, k.leftIdxs), ref[3]):
+                assert np.array_equal(got, want)
+            r2, l2, d2, c2 = fm.stereo_download(0, 1)     # the device state itself
+            assert np.array_equal(r2, ref[3][2]) and np.array_equal(l2, ref[3][3]) and np.array_equal(d2, ref[3][0]) and np.array_equal(c2, ref[3][1])
+            assert (ref[3][2] != cur["rightIdxs"]).sum() > 0
+    with pytest.raises(gvs.GvsError):
+        bad = np.array([[10 ** 6, -1]], np.int32)
+        fm.findOutliersMono(0, np.eye(4), *cam, 7.815, None, np.ones((1, 4)), None, bad, np.zeros(1, np.uint8))
+
+
 def test_cuda_against_the_compiled_reference():
     """The CUDA path against the reference's OWN source (oracle/_ref/libref_frontend.so: FeatureExtractor.cpp and
     FeatureMatcher.cpp compiled unmodified; built in the CPU container, the .so travels), on fresh seeds; with the real

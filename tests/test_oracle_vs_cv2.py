@@ -232,3 +232,98 @@ def test_world_to_frame_cpp_matches_python_restatement():
     fb = cpu_ref.world_to_frame(Pinv, *cam, wPos, msd, ls, nl, pb, sb)
     assert np.array_equal(fa, fb) and np.array_equal(pa, pb) and np.array_equal(sa, sb)
     assert 0.1 < fa.mean() < 0.9 and len(np.unique(sa[fa > 0])) >= 5
+
+
+def _outlier_case(kl, kr, st, fx, cx, cy, baseline, seed=0, M=1500):
+    """Inputs for findOutliersR / findOutliersMono on the keys and stereo arrays of one frame: map points back-projected from the
+    keys they are matched to (small noise = inliers, large = outliers), stereo partners (true, wrong and missing ones), right-only
+    matches, duplicates of a left key, invalid / out-of-frame points and points behind the camera."""
+    rng = np.random.default_rng(seed)
+    nl, nr = len(kl), len(kr)
+    ang = 0.05
+    T = np.eye(4)
+    T[:3, :3] = [[math.cos(ang), 0, math.sin(ang)], [0, 1, 0], [-math.sin(ang), 0, math.cos(ang)]]
+    T[:3, 3] = [0.2, -0.05, 0.3]
+    Tr = np.eye(4); Tr[0, 3] = -baseline
+    TR = Tr @ T                                   # world -> right camera
+    Tinv = np.linalg.inv(T)
+    matches = np.full((M, 2), -1, np.int32)
+    wPos = np.zeros((M, 4))
+    for i in range(M):
+        u = rng.random()
+        first = int(rng.integers(0, nl))
+        if i > 0 and rng.random() < 0.1 and matches[i - 1, 0] >= 0:
+            first = int(matches[i - 1, 0])        # several map points on the same left key
+        z = float(st["estimatedDepth"][first]) if st["estimatedDepth"][first] > 0 else float(rng.uniform(1, 40))
+        if rng.random() < 0.05:
+            z = float(rng.uniform(0.5, 60))
+        pc = np.array([(kl["x"][first] - cx) / fx * z, (kl["y"][first] - cy) / fx * z, z, 1.0])
+        pc[:3] += rng.normal(0, 0.002 if rng.random() < 0.7 else 0.2, 3) * z
+        if rng.random() < 0.03:
+            pc[2] = -abs(pc[2])                   # behind the camera
+        wPos[i] = Tinv @ pc
+        if u < 0.8:
+            matches[i, 0] = first
+            r = rng.random()
+            if st["rightIdxs"][first] >= 0 and r < 0.7:
+                matches[i, 1] = st["rightIdxs"][first]
+            elif r < 0.85:
+                matches[i, 1] = int(rng.integers(0, nr))
+        elif u < 0.92:
+            matches[i, 1] = int(rng.integers(0, nr))   # right-only match
+            j = matches[i, 1]
+            z = float(rng.uniform(1, 40))
+            pr = np.array([(kr["x"][j] - cx) / fx * z, (kr["y"][j] - cy) / fx * z, z, 1.0])
+            pr[:3] += rng.normal(0, 0.002 if rng.random() < 0.7 else 0.2, 3) * z
+            wPos[i] = np.linalg.inv(TR) @ pr
+    valid = (rng.random(M) < 0.95).astype(np.uint8)
+    inF = (rng.random(M) < 0.95).astype(np.uint8)
+    inFR = (rng.random(M) < 0.9).astype(np.uint8)
+    return dict(pose=T, poseR=TR, wPos=wPos, matches=matches, valid=valid, inFrame=inF, inFrameR=inFR, thres=7.815,
+                closeDist=float(np.float32(baseline) * np.float32(40)))
+
+
+def _inv_sigma_factor(nLevels, imScale=1.2):
+    """FeatureExtractor::InvSigmaFactor (src/FeatureExtractor.cpp:628-646): cumulative float32 scale, squared, inverted."""
+    out, sc = [], np.float32(1)
+    for l in range(nLevels):
+        if l:
+            sc = np.float32(sc * np.float32(imScale))
+        out.append(np.float32(1) / np.float32(sc * sc))
+    return np.array(out, np.float32)
+
+
+def _run_outliers(fn, mode, c, cam, invSigma, kl, kr, st):
+    """fn(mode, pose, poseR, fx, fy, cx, cy, thres, closeDist, invSigma, valid, wPos, inFrame, inFrameR, matches, outliers, kl, kr,
+    depth, close, rightIdxs, leftIdxs) on fresh copies of the in-out arrays."""
+    m = c["matches"].copy(); out = np.full(len(m), 7, np.uint8)
+    arr = [st["estimatedDepth"].copy(), st["close"].astype(np.uint8).copy(), st["rightIdxs"].copy(), st["leftIdxs"].copy()]
+    cnt = fn(mode, c["pose"], c["poseR"], *cam, c["thres"], c["closeDist"], invSigma, c["valid"], c["wPos"], c["inFrame"],
+             c["inFrameR"], m, out, kl, kr, *arr)
+    return cnt, m, out, arr
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_find_outliers_cpp_matches_python_restatement(mode):
+    """SURVEY 8(f) rank 3: FeatureTracker::findOutliersR / findOutliersMono (src/FeatureTracker.cpp:582-684), C++ oracle vs the
+    Python restatement of the same sequential loop, on a frame's real keys and stereo arrays."""
+    cfg = synth.CONFIGS["small"]
+    w, h = cfg["width"], cfg["height"]
+    L, R = synth.stereo_pair(w, h, cfg["disparity"], seed=5)
+    args = dict(nFeatures=cfg["n_features"], nLevels=cfg["n_levels"])
+    oL, oR = cpu_ref.Extractor(**args), cpu_ref.Extractor(**args)
+    kl, dl = oL.extractKeysNew(L); kr, dr = oR.extractKeysNew(R)
+    st = cpu_ref.stereo_match(oL, oR, cfg["fx"], cfg["baseline"], h, kl, dl, kr, dr)
+    cam = (cfg["fx"], cfg["fx"], w / 2.0, h / 2.0)
+    c = _outlier_case(kl, kr, st, cfg["fx"], w / 2.0, h / 2.0, cfg["baseline"], seed=11 + mode)
+    invSigma = _inv_sigma_factor(cfg["n_levels"])
+    a = _run_outliers(ref_cv2.findOutliers, mode, c, cam, invSigma, kl, kr, st)
+    b = _run_outliers(cpu_ref.find_outliers, mode, c, cam, invSigma, kl, kr, st)
+    assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    for x, y in zip(a[3], b[3]):
+        assert np.array_equal(x, y)
+    nIn, nSt = b[0]
+    assert nIn > 100 and (b[2] == 1).sum() > 100 and (b[2] == 7).sum() > 10         # inliers, outliers and untouched entries
+    if mode == 0:
+        assert nSt > 20 and (b[1][:, 1] != c["matches"][:, 1]).sum() > 5           # stereo inliers and rejected partners
+        assert (b[3][1] != st["close"].astype(np.uint8)).sum() > 0

@@ -9,9 +9,11 @@ cp gtsam_vslam_b200/libgvs.so /tmp/libgvs_keep.so
 first=$1
 for v in "$@"; do
   cp variants/libgvs_$v.so gtsam_vslam_b200/libgvs.so
-  if [ "$v" = "$first" ] && [ "${SKIP_PARITY:-0}" != 1 ]; then
+  if { [ "$v" = "$first" ] || [ "${PARITY_ALL:-0}" = 1 ]; } && [ "${SKIP_PARITY:-0}" != 1 ]; then
     ( time timeout 420 python -m pytest tests -m gpu -x -q ) > gpurun_out/ab/pytest_$v.log 2>&1; echo "pytest $v rc=$?" | tee -a gpurun_out/ab/summary.txt
     tail -3 gpurun_out/ab/pytest_$v.log
+  fi
+  if [ "$v" = "$first" ] && [ "${SKIP_PARITY:-0}" != 1 ]; then
     ( time timeout 200 python tools/fuzz_parity.py ${FUZZ_N:-400} 777 ) > gpurun_out/ab/fuzz_$v.log 2>&1; echo "fuzz $v rc=$?" | tee -a gpurun_out/ab/summary.txt
     tail -2 gpurun_out/ab/fuzz_$v.log
   fi
