@@ -61,7 +61,8 @@ struct gvs_extractor {
     std::vector<int> patch, quota;
     cudaStream_t ownStream = nullptr, stream = nullptr;
     cudaStream_t auxStream = nullptr;  // blur runs here, concurrently with FAST + selection
-    cudaEvent_t doneEvent = nullptr, evPyr = nullptr, evBlur = nullptr;
+    cudaEvent_t doneEvent = nullptr, evPyr = nullptr, evBlur = nullptr;   // evPyr: recorded after the FAST kernel (recordAfterFast)
+    bool recordAfterFast = false;
     // device
     uint8_t* slab = nullptr;
     uint8_t* blurSlab = nullptr;
@@ -324,6 +325,7 @@ static int enqueueExtract(gvs_extractor* fe, int n, cudaStream_t s) {
     if (T) cudaEventRecord(fe->ev[1], s);
     launchFast(g, fe->slab, fe->fastItems, fe->nFastItems, n, fe->recs, fe->nCand, fe->cellCnt, fe->status, s, &fe->launches);
     if (T) cudaEventRecord(fe->ev[2], s);
+    if (fe->recordAfterFast) cudaEventRecord(fe->evPyr, s);   // the other side of a staggered stereo batch starts here
     launchSelect(g, n, fe->recs, fe->nCand, fe->cellCnt, fe->kept, fe->keptCnt, fe->orderedDbg, nullptr, fe->selScratch,
                  fe->selScratchPerCta, fe->selCtas, fe->workCounter, fe->status, s, &fe->launches);
     launchOffsets(g, n, fe->keptCnt, fe->imgOff, fe->totalCap, fe->status, s, &fe->launches);
@@ -1063,8 +1065,16 @@ int gvs_track_stereo_batch_resident(gvs_matcher* m, int n_frames, int width, int
     DeviceGuard deviceGuard(m->L->device);
     int rc = forkFromCaller(m);
     if (rc) return rc;
+    // Staggered sides (large batches): the right side starts when the left side's FAST kernel is done, so that the integer-bound
+    // pyramid / FAST kernels of one side share the SMs with the latency-bound selection / descriptor kernels of the other
+    // instead of with their own kind.
+    static const bool stagger = getenv("GVS_STAGGER") != nullptr && atoi(getenv("GVS_STAGGER")) != 0;
+    const bool st = stagger && n_frames > kGraphMaxImages && !m->L->timing && m->L->stream != m->R->stream;
+    m->L->recordAfterFast = st;
     rc = gvs_extract_batch_resident(m->L, n_frames);
+    m->L->recordAfterFast = false;
     if (rc) return rc;
+    if (st) GVS_CUDA_OK(cudaStreamWaitEvent(m->R->stream, m->L->evPyr, 0));
     rc = gvs_extract_batch_resident(m->R, n_frames);
     if (rc) return rc;
     rc = gvs_stereo_match_batch(m, n_frames);

@@ -198,18 +198,18 @@ describe_fused_kernel(const __grid_constant__ Geometry g, const uint8_t* __restr
         const float angle = fastAtan2Deg((float)m01, (float)m10);
 
         // ---- horizontal blur pass on the patch: unit = (word m in 1..11, row), consecutive lanes = consecutive rows
-        // (conflict-free: patch rows are 13 words apart, H^T columns hold consecutive rows) -> 4 u16 results
-        const unsigned tLo = 0x38302212u, tHi = 0x00122230u;  // {18,34,48,56}, {48,34,18,0}
+        // (conflict-free: patch rows are 13 words apart, H^T columns hold consecutive rows) -> 4 u16 results.  The 7-byte window
+        // of output 4m + j lies in the words (m-1, m, m+1); the taps {18,34,48,56,48,34,18} are laid out per word and per j as
+        // dp4a constants, so no byte shifts are needed (10 dp4a per unit; exact u32 sums, the order is irrelevant).
         for (int t = lane; t < kPRows * 11; t += 32) {
             const int m = 1 + t / kPRows, r = t - (m - 1) * kPRows;
             const unsigned* w = P + r * kPWords + m;
             const unsigned w0 = w[-1], w1 = w[0], w2 = w[1];
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const unsigned a = j == 3 ? w1 : __funnelshift_r(w0, w1, 8 * (1 + j));
-                const unsigned b = j == 3 ? w2 : __funnelshift_r(w1, w2, 8 * (1 + j));
-                H[(4 * (m - 1) + j) * kHtRows + r] = (unsigned short)__dp4a(a, tLo, __dp4a(b, tHi, 0u));
-            }
+            unsigned short* h = H + (4 * (m - 1)) * kHtRows + r;
+            h[0 * kHtRows] = (unsigned short)__dp4a(w0, 0x30221200u, __dp4a(w1, 0x12223038u, 0u));
+            h[1 * kHtRows] = (unsigned short)__dp4a(w0, 0x22120000u, __dp4a(w1, 0x22303830u, __dp4a(w2, 0x00000012u, 0u)));
+            h[2 * kHtRows] = (unsigned short)__dp4a(w0, 0x12000000u, __dp4a(w1, 0x30383022u, __dp4a(w2, 0x00001222u, 0u)));
+            h[3 * kHtRows] = (unsigned short)__dp4a(w1, 0x38302212u, __dp4a(w2, 0x00122230u, 0u));
         }
         __syncwarp();
 

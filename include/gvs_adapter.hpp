@@ -252,6 +252,26 @@ class FeatureMatcher {
         return n;
     }
 
+    // FeatureTracker::findOutliersR (src/FeatureTracker.cpp:582-649) with the reference's arguments (plus the camera members the
+    // tracker holds: fx, fy, cx, cy, zedPtr->extrinsics).  Mat4 / MapPointT are the reference's own Eigen::Matrix4d / MapPoint;
+    // the template is only instantiated inside the reference tree.  The two inverses (:584-585) stay on the host.
+    template <class Mat4, class MapPointT>
+    int findOutliersR(const Mat4& estimPose, const Mat4& extrinsics, double fx, double fy, double cx, double cy, float baseline,
+                      std::vector<MapPointT*>& activeMapPoints, TrackedKeys& keysLeft, std::vector<std::pair<int, int>>& matchesIdxs,
+                      const double thres, std::vector<bool>& MPsOutliers, int& nInliers) {
+        const Mat4 toCameraR = (estimPose.inverse() * extrinsics).inverse();
+        return findOutliersImpl(0, estimPose, &toCameraR, fx, fy, cx, cy, baseline * (float)closeNumber, activeMapPoints, &keysLeft,
+                                matchesIdxs, thres, MPsOutliers, nInliers);
+    }
+    // FeatureTracker::findOutliersMono (src/FeatureTracker.cpp:651-684); returns nInliers like the reference
+    template <class Mat4, class MapPointT>
+    int findOutliersMono(const Mat4& estimPose, double fx, double fy, double cx, double cy, std::vector<MapPointT*>& activeMapPoints,
+                         std::vector<std::pair<int, int>>& matchesIdxs, const double thres, std::vector<bool>& MPsOutliers, int& nInliers) {
+        findOutliersImpl(1, estimPose, (const Mat4*)nullptr, fx, fy, cx, cy, 0.f, activeMapPoints, (TrackedKeys*)nullptr, matchesIdxs, thres,
+                         MPsOutliers, nInliers);
+        return nInliers;
+    }
+
     // MapPoint::calcDescriptor (src/Map.cpp:145-210) for one observation list: index of the chosen descriptor
     int medianDescriptor(const std::vector<cv::Mat>& vDescriptors) {
         const int N = (int)vDescriptors.size();
@@ -275,6 +295,37 @@ class FeatureMatcher {
     gvs_matcher* handle() const { return h_; }
 
   private:
+    template <class Mat4, class MapPointT>
+    int findOutliersImpl(int mode, const Mat4& estimPose, const Mat4* toCameraR, double fx, double fy, double cx, double cy, float closeDist,
+                         std::vector<MapPointT*>& activeMapPoints, TrackedKeys* keys, std::vector<std::pair<int, int>>& matchesIdxs,
+                         const double thres, std::vector<bool>& MPsOutliers, int& nInliers) {
+        const int M = (int)matchesIdxs.size();
+        if (M == 0) return 0;
+        double pose[16], poseR[16];
+        for (int r = 0; r < 4; r++)
+            for (int c = 0; c < 4; c++) { pose[4 * r + c] = estimPose(r, c); poseR[4 * r + c] = toCameraR ? (*toCameraR)(r, c) : 0.0; }
+        std::vector<uint8_t> valid(M), inF(M), inFR(M), out(M);
+        std::vector<double> wp(4 * (size_t)M, 0.0);
+        for (int i = 0; i < M; i++) {
+            const MapPointT* mp = activeMapPoints[i];
+            valid[i] = mp != nullptr; out[i] = MPsOutliers[i];
+            if (!mp) continue;
+            inF[i] = mp->inFrame; inFR[i] = mp->inFrameR;
+            const auto w = mp->getWordPose4d();
+            for (int c = 0; c < 4; c++) wp[4 * (size_t)i + c] = w(c);
+        }
+        std::vector<uint8_t> close8;
+        if (keys) close8.assign(keys->close.begin(), keys->close.end());
+        int nIn = 0, nStereo = 0;
+        gvsCheck(gvs_find_outliers(h_, 0, mode, pose, toCameraR ? poseR : nullptr, fx, fy, cx, cy, thres, closeDist, M, valid.data(), wp.data(),
+                                   inF.data(), mode == 0 ? inFR.data() : nullptr, reinterpret_cast<int32_t*>(matchesIdxs.data()), out.data(),
+                                   keys ? keys->estimatedDepth.data() : nullptr, keys ? close8.data() : nullptr,
+                                   keys ? keys->rightIdxs.data() : nullptr, keys ? keys->leftIdxs.data() : nullptr, &nIn, &nStereo));
+        for (int i = 0; i < M; i++) MPsOutliers[i] = out[i] != 0;
+        if (keys) for (size_t i = 0; i < close8.size(); i++) keys->close[i] = close8[i] != 0;
+        nInliers += nIn;
+        return nStereo;
+    }
     static void fetch(FeatureExtractor& fe, std::vector<cv::KeyPoint>& k, cv::Mat& d) {
         int off[2] = {0, 0};
         gvsCheck(gvs_extract_offsets(fe.handle(), off));

@@ -1,6 +1,7 @@
 // Exercises include/gvs_adapter.hpp (the C++ drop-in with the reference's class names) end to end on one stereo pair read
 // from two raw u8 files; prints counts and FNV-1a checksums that tests/test_gpu_adapter.py compares with the ctypes path.
 #include <cstdio>
+#include <algorithm>
 #include <cstdlib>
 #include "../../include/gvs_adapter.hpp"
 
@@ -11,7 +12,19 @@ static uint64_t fnv(const void* p, size_t n, uint64_t h = 1469598103934665603ull
     for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ull; }
     return h;
 }
-struct MapPoint { cv::Mat desc; cv::Point2f predL, predR; int scaleLevelL = 0, scaleLevelR = 0; bool inFrame = true, inFrameR = true; };
+// stand-ins for the reference's Eigen::Vector4d / Eigen::Matrix4d (pure translations are enough here) and MapPoint
+struct Vec4 { double v[4]; double operator()(int i) const { return v[i]; } };
+struct Mat4 {
+    double t[3] = {0, 0, 0};
+    double operator()(int r, int c) const { return r == c ? 1.0 : (c == 3 && r < 3 ? t[r] : 0.0); }
+    Mat4 inverse() const { Mat4 m; for (int i = 0; i < 3; i++) m.t[i] = -t[i]; return m; }
+    Mat4 operator*(const Mat4& o) const { Mat4 m; for (int i = 0; i < 3; i++) m.t[i] = t[i] + o.t[i]; return m; }
+};
+struct MapPoint {
+    cv::Mat desc; cv::Point2f predL, predR; int scaleLevelL = 0, scaleLevelR = 0; bool inFrame = true, inFrameR = true;
+    Vec4 wp{{0, 0, 0, 1}};
+    Vec4 getWordPose4d() const { return wp; }
+};
 
 int main(int argc, char** argv) {
     if (argc < 7) { std::fprintf(stderr, "usage: left.raw right.raw w h nFeatures nLevels\n"); return 2; }
@@ -52,6 +65,25 @@ int main(int argc, char** argv) {
         std::vector<std::pair<int, int>> pairs(mps.size(), {-1, -1});
         int n = fm.matchByProjectionRPred(mps, k, mL, mR, pairs, 4.0f);
         std::printf("proj %d of %zu\n", n, mps.size());
+        // FeatureTracker::findOutliersR through the adapter: map point i = left key i back-projected with its stereo depth (5 m
+        // without one), matched to (i, rightIdxs[i]); every 5th stereo partner is replaced by its neighbour and must be rejected
+        const double fx = 200.0, cx = w / 2.0, cy = h / 2.0;
+        Mat4 estimPose, extrinsics; extrinsics.t[0] = 0.1f;
+        for (size_t i = 0; i < store.size(); i++) {
+            const double z = k.estimatedDepth[i] > 0 ? (double)k.estimatedDepth[i] : 5.0;
+            store[i].wp = Vec4{{((double)k.keyPoints[i].pt.x - cx) / fx * z, ((double)k.keyPoints[i].pt.y - cy) / fx * z, z, 1.0}};
+            store[i].inFrameR = true;
+            int second = k.rightIdxs[i];
+            if (second >= 0 && i % 5 == 0) second = (second + 1) % (int)k.rightKeyPoints.size();
+            pairs[i] = {(int)i, second};
+        }
+        std::vector<bool> outl(mps.size(), false);
+        int nIn = 0;
+        const int nStereo = fm.findOutliersR(estimPose, extrinsics, fx, fx, cx, cy, 0.1f, mps, k, pairs, 7.815, outl, nIn);
+        int nOut = 0, nCleared = 0;
+        for (size_t i = 0; i < outl.size(); i++) { nOut += outl[i]; nCleared += pairs[i].second < 0; }
+        std::printf("outliers in %d stereo %d out %d ridx %016llx close %d\n", nIn, nStereo, nOut,
+                    (unsigned long long)fnv(k.rightIdxs.data(), k.rightIdxs.size() * 4), (int)std::count(k.close.begin(), k.close.end(), true));
     } catch (const std::exception& e) { std::fprintf(stderr, "%s\n", e.what()); return 1; }
     return 0;
 }

@@ -49,3 +49,19 @@ def test_cpp_adapter_matches_oracle(tmp_path):
     # projecting a frame's own keys onto itself with a 4-px radius must match nearly all of them
     t = lines[3].split()
     assert int(t[1]) > 0.9 * int(t[3])
+    # findOutliersR through the adapter against the oracle's sequential loop on the same inputs
+    t = lines[4].split()
+    from test_oracle_vs_cv2 import _inv_sigma_factor
+    fx, cx, cy = 200.0, w / 2.0, h / 2.0
+    z = np.where(s["estimatedDepth"] > 0, s["estimatedDepth"].astype(np.float64), 5.0)
+    wp = np.stack([(kl["x"].astype(np.float64) - cx) / fx * z, (kl["y"].astype(np.float64) - cy) / fx * z, z, np.ones(len(kl))], 1)
+    m = np.stack([np.arange(len(kl)), s["rightIdxs"]], 1).astype(np.int32)
+    swap = (m[:, 1] >= 0) & (np.arange(len(kl)) % 5 == 0)
+    m[swap, 1] = (m[swap, 1] + 1) % len(kr)
+    T = np.eye(4); TR = np.eye(4); TR[0, 3] = -float(np.float32(0.1))
+    out = np.zeros(len(kl), np.uint8)
+    arr = [s["estimatedDepth"].copy(), s["close"].astype(np.uint8).copy(), s["rightIdxs"].copy(), s["leftIdxs"].copy()]
+    nIn, nSt = cpu_ref.find_outliers(0, T, TR, fx, fx, cx, cy, 7.815, float(np.float32(0.1) * np.float32(40)), _inv_sigma_factor(cfg["n_levels"]),
+                                     None, wp, None, None, m, out, kl, kr, *arr)
+    assert (int(t[2]), int(t[4]), int(t[6])) == (nIn, nSt, int(out.sum())) and nSt > 0
+    assert t[8] == fnv(arr[2].tobytes()) and int(t[10]) == int(arr[1].sum()) and (arr[2] != s["rightIdxs"]).sum() > 0
