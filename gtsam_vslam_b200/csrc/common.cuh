@@ -48,7 +48,7 @@ struct Geometry {
 
 // One FAST work item = a strip of up to kFastCellsPerItem consecutive cells of one cell row.
 #ifndef GVS_FAST_CELLS
-#define GVS_FAST_CELLS 4
+#define GVS_FAST_CELLS 6
 #endif
 constexpr int kFastCellsPerItem = GVS_FAST_CELLS;
 struct FastItem {

@@ -61,8 +61,7 @@ struct gvs_extractor {
     std::vector<int> patch, quota;
     cudaStream_t ownStream = nullptr, stream = nullptr;
     cudaStream_t auxStream = nullptr;  // blur runs here, concurrently with FAST + selection
-    cudaEvent_t doneEvent = nullptr, evPyr = nullptr, evBlur = nullptr;   // evPyr: recorded after the FAST kernel (recordAfterFast)
-    bool recordAfterFast = false;
+    cudaEvent_t doneEvent = nullptr, evPyr = nullptr, evBlur = nullptr;
     // device
     uint8_t* slab = nullptr;
     uint8_t* blurSlab = nullptr;
@@ -137,7 +136,7 @@ struct gvs_matcher {
     float xMult = 0, yMult = 0;
     bool gridsValid = false, stereoValid = false;
     int lastFrames = 0;
-    cudaEvent_t evR = nullptr, evFork = nullptr, evJoin = nullptr;
+    cudaEvent_t evR = nullptr, evFork = nullptr, evJoin = nullptr, evHold = nullptr;
     cudaStream_t callerStream = nullptr;  // optional: work is forked from / joined into this stream
     // projection scratch (grown on demand)
     uint8_t* pj = nullptr;
@@ -325,7 +324,6 @@ static int enqueueExtract(gvs_extractor* fe, int n, cudaStream_t s) {
     if (T) cudaEventRecord(fe->ev[1], s);
     launchFast(g, fe->slab, fe->fastItems, fe->nFastItems, n, fe->recs, fe->nCand, fe->cellCnt, fe->status, s, &fe->launches);
     if (T) cudaEventRecord(fe->ev[2], s);
-    if (fe->recordAfterFast) cudaEventRecord(fe->evPyr, s);   // the other side of a staggered stereo batch starts here
     launchSelect(g, n, fe->recs, fe->nCand, fe->cellCnt, fe->kept, fe->keptCnt, fe->orderedDbg, nullptr, fe->selScratch,
                  fe->selScratchPerCta, fe->selCtas, fe->workCounter, fe->status, s, &fe->launches);
     launchOffsets(g, n, fe->keptCnt, fe->imgOff, fe->totalCap, fe->status, s, &fe->launches);
@@ -885,7 +883,8 @@ int gvs_matcher_create(gvs_matcher** out, gvs_extractor* feL, gvs_extractor* feR
               devAlloc(&m->itemsL, (size_t)feL->totalCap) == cudaSuccess && devAlloc(&m->itemsR, (size_t)feR->totalCap) == cudaSuccess &&
               devAlloc(&m->pjStatus, 2) == cudaSuccess && cudaEventCreateWithFlags(&m->evR, cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&m->evFork, cudaEventDisableTiming) == cudaSuccess &&
-              cudaEventCreateWithFlags(&m->evJoin, cudaEventDisableTiming) == cudaSuccess;
+              cudaEventCreateWithFlags(&m->evJoin, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&m->evHold, cudaEventDisableTiming) == cudaSuccess;
     for (auto& e : m->ev) ok = ok && cudaEventCreate(&e) == cudaSuccess;
     if (!ok) {
         int rc = fail(GVS_ERR_CUDA, "matcher allocation", cudaGetErrorString(cudaGetLastError()));
@@ -906,6 +905,7 @@ int gvs_matcher_destroy(gvs_matcher* m) {
     if (m->evR) cudaEventDestroy(m->evR);
     if (m->evFork) cudaEventDestroy(m->evFork);
     if (m->evJoin) cudaEventDestroy(m->evJoin);
+    if (m->evHold) cudaEventDestroy(m->evHold);
     for (auto& e : m->ev) if (e) cudaEventDestroy(e);
     delete m;
     return GVS_OK;
@@ -915,6 +915,21 @@ static int joinRight(gvs_matcher* m) {  // make L's stream wait for R's last bat
     if (m->R != m->L && m->R->stream != m->L->stream) {
         GVS_CUDA_OK(cudaEventRecord(m->evR, m->R->stream));
         GVS_CUDA_OK(cudaStreamWaitEvent(m->L->stream, m->evR, 0));
+    }
+    return GVS_OK;
+}
+
+// The matcher's kernels run on L's stream and read R's keys, descriptors and pyramid: whatever is queued on R's stream afterwards
+// (the next batch's upload and extraction) must wait for them.
+static int holdRight(gvs_matcher* m) {
+    if (m->R != m->L && m->R->stream != m->L->stream) {
+        // (not while the caller captures L's stream into a graph: a fork that is never joined would invalidate the capture, and the
+        // caller's graph already orders whole batches)
+        cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(m->L->stream, &capturing) != cudaSuccess) { cudaGetLastError(); capturing = cudaStreamCaptureStatusNone; }
+        if (capturing != cudaStreamCaptureStatusNone) return GVS_OK;
+        GVS_CUDA_OK(cudaEventRecord(m->evHold, m->L->stream));
+        GVS_CUDA_OK(cudaStreamWaitEvent(m->R->stream, m->evHold, 0));
     }
     return GVS_OK;
 }
@@ -971,7 +986,7 @@ int gvs_stereo_match_batch(gvs_matcher* m, int n_frames) {
     m->launchesTotal += m->launches;
     m->stereoValid = true;
     m->lastFrames = n_frames;
-    return GVS_OK;
+    return holdRight(m);
 }
 
 int gvs_matcher_sync(gvs_matcher* m) {
@@ -1039,7 +1054,7 @@ int gvs_assign_grids_batch(gvs_matcher* m, int n_frames, int width, int height) 
     m->launches += launches;
     m->gridsValid = true;
     if (m->lastFrames < n_frames) m->lastFrames = n_frames;
-    return GVS_OK;
+    return holdRight(m);
 }
 
 int gvs_grid_download(gvs_matcher* m, int frame, int side, int32_t* cell_start, int32_t* items, int* y_grids, float* x_mult, float* y_mult) {
@@ -1065,16 +1080,8 @@ int gvs_track_stereo_batch_resident(gvs_matcher* m, int n_frames, int width, int
     DeviceGuard deviceGuard(m->L->device);
     int rc = forkFromCaller(m);
     if (rc) return rc;
-    // Staggered sides (large batches): the right side starts when the left side's FAST kernel is done, so that the integer-bound
-    // pyramid / FAST kernels of one side share the SMs with the latency-bound selection / descriptor kernels of the other
-    // instead of with their own kind.
-    static const bool stagger = getenv("GVS_STAGGER") != nullptr && atoi(getenv("GVS_STAGGER")) != 0;
-    const bool st = stagger && n_frames > kGraphMaxImages && !m->L->timing && m->L->stream != m->R->stream;
-    m->L->recordAfterFast = st;
     rc = gvs_extract_batch_resident(m->L, n_frames);
-    m->L->recordAfterFast = false;
     if (rc) return rc;
-    if (st) GVS_CUDA_OK(cudaStreamWaitEvent(m->R->stream, m->L->evPyr, 0));
     rc = gvs_extract_batch_resident(m->R, n_frames);
     if (rc) return rc;
     rc = gvs_stereo_match_batch(m, n_frames);
