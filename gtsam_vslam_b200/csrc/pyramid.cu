@@ -36,8 +36,8 @@ pyr_down_kernel(const __grid_constant__ Geometry g, uint8_t* __restrict__ slab, 
     const uint8_t* src = levelPtr((const uint8_t*)slab, g, img, level - 1);
     uint8_t* dst = levelPtr(slab, g, img, level);
 
-    const ResizeTap t0 = taps[D.tabY + dy], t1 = taps[D.tabY + dy + (two ? 1 : 0)];
     const int gi = D.tabX / 4 + grp;
+    const ResizeTap t0 = taps[D.tabY + dy], t1 = taps[D.tabY + dy + (two ? 1 : 0)];
     const unsigned base = xbase[gi];
     const unsigned al = NARROW ? (base & ~3u) : base, sh = (base & 3u) * 8u;
     const uint4 wv = __ldg(xw + gi), sv = __ldg(xs + gi);
