@@ -378,7 +378,7 @@ def main():
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": st_bytes[dom] * F,
                      "launch_ms": dom_ms / 2,
                      "note": "HBM is the roofline SURVEY 8(d) prescribes for this stage; ncu (profiles/README.md) shows the kernel bound by the "
-                             "integer ALU pipe instead (ALU 66 %, issue slots 77 %, DRAM 2.9 %, DRAM traffic = algorithmic bytes)",
+                             "integer ALU pipe instead (ALU 68 %, issue slots 71 %, DRAM 2.9 %, DRAM traffic = algorithmic bytes)",
                      "step": {"achieved": b_frame * F / (dev_ms * 1e-3) / 1e9, "frac": b_frame * F / (dev_ms * 1e-3) / 1e9 / peak,
                               "bytes_per_stereo_frame": b_frame}},
         "clocks": clocks,
