@@ -47,7 +47,6 @@ __device__ __forceinline__ float fastAtan2Deg(float y, float x) {
 // memory) and evaluates the vertical pass at the 512 sample positions only.  The blurred slab is neither written nor read.
 constexpr int kPR = 21, kPRows = 2 * kPR + 1, kPWords = 13, kHCols = 44;
 constexpr int kPBytes = (kPRows * kPWords * 4 + 15) & ~15;                       // 2240
-constexpr int kWarpSmemBytes = kPBytes + ((kPRows * kHCols * 2 + 15) & ~15);     // + 3792 = 6032
 
 __device__ __forceinline__ int reflect101i(int p, int n) {
     while (p < 0 || p >= n) p = p < 0 ? -p : 2 * n - 2 - p;
@@ -160,7 +159,6 @@ describe_fused_kernel(const __grid_constant__ Geometry g, const uint8_t* __restr
     if (k < nKeys) { cur = keyOf(k); stage(cur, reinterpret_cast<unsigned*>(wbase)); }
     for (; k < nKeys; k += warpsPerGrid, buf ^= 1) {
         unsigned* P = reinterpret_cast<unsigned*>(wbase + buf * kPBytes);
-        const uint8_t* Pb = reinterpret_cast<const uint8_t*>(P);
         const int level = cur.level, x = cur.x, y = cur.y, score = cur.score, ox = cur.x - cur.xs;  // ox in [25, 28]
         const LevelGeom& lv = g.lv[level];
         const int o = outBase + k;

@@ -172,14 +172,10 @@ stereo_finalize_kernel(const StereoArgs a, int sortCap, unsigned long long* __re
     for (int i = V + tid; i < n2; i += blockDim.x) sKeys[i] = ~0ull;
     bitonicSort(sKeys, n2);
     const int endDe = (int)floor((double)V * 0.01);
-    // remember which left keys pass A removes (apply after pass B has read the SADs: the passes commute)
-    unsigned dropA = 0xffffffffu;  // each thread remembers at most a few; endDe is small -> loop
+    // The left keys pass A removes are marked through the close[] byte (2 = "drop"; close is rewritten below) and applied after
+    // pass B has read the SADs: the two passes commute.
     __syncthreads();
-    // pass B needs the SAD keys: build them before overwriting anything
-    // stash pass-A victims in the tail of the key array (n2 .. n2+endDe) is not possible without extra room,
-    // so mark them through the close[] byte: 2 = "drop" (close is rewritten below)
     for (int i = tid; i < endDe; i += blockDim.x) a.close[offL + (int)(sKeys[i] & 0xffffffffu)] = 2;
-    (void)dropA;
     __syncthreads();
     if (tid == 0) sCount = 0;
     __syncthreads();
