@@ -32,7 +32,7 @@ SYMBOLS = [
     "gvs_matcher_create", "gvs_matcher_destroy", "gvs_stereo_match_batch", "gvs_stereo_download",
     "gvs_assign_grids_batch", "gvs_grid_download", "gvs_track_stereo_batch_host",
     "gvs_track_stereo_batch_resident", "gvs_matcher_sync", "gvs_matcher_set_stream", "gvs_match_projection", "gvs_descriptor_distance",
-    "gvs_match_projection_lba", "gvs_median_descriptor", "gvs_project_mappoints", "gvs_find_outliers", "gvs_extractor_enable_timing", "gvs_extractor_stage_times", "gvs_matcher_launch_count",
+    "gvs_match_projection_lba", "gvs_median_descriptor", "gvs_project_mappoints", "gvs_find_outliers", "gvs_predict_mappoints", "gvs_extractor_enable_timing", "gvs_extractor_stage_times", "gvs_matcher_launch_count",
     "gvs_extractor_launch_count",
     "gvs_pipeline_create", "gvs_pipeline_destroy", "gvs_pipeline_submit", "gvs_pipeline_wait", "gvs_pipeline_download",
     "gvs_pipeline_handles", "gvs_pipeline_release",
@@ -120,6 +120,7 @@ def load_library() -> C.CDLL:
     lib.gvs_median_descriptor.argtypes = [vp, vp, vp, i32, vp]
     dbl = C.c_double
     lib.gvs_project_mappoints.argtypes = [vp, vp, dbl, dbl, dbl, dbl, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
+    lib.gvs_predict_mappoints.argtypes = [vp, i32, vp, vp, dbl, dbl, dbl, dbl, i32, i32, i32] + [vp] * 14 + [i32, vp, i32, vp]
     lib.gvs_find_outliers.argtypes = [vp, i32, i32, vp, vp, dbl, dbl, dbl, dbl, dbl, f32, i32] + [vp] * 10 + [C.POINTER(i32), C.POINTER(i32)]
     lib.gvs_extractor_enable_timing.argtypes = [vp, i32]
     lib.gvs_extractor_stage_times.argtypes = [vp, C.POINTER(StageTimes)]
@@ -465,6 +466,25 @@ class FeatureMatcher:
         _check(self._lib.gvs_project_mappoints(self.h, _p(keep[0]), fx, fy, cx, cy, width, height, M, _p(keep[1]), _p(keep[2]), _p(keep[3]),
                                                _p(keep[4]), _p(pred), _p(scaleLevel), _p(inF)))
         return inF[:M]
+
+    # -- FeatureTracker::removeOutOfFrameMPs / removeOutOfFrameMPsMono / PredictMPsPosition (src/FeatureTracker.cpp:910-1013), batched
+    def predictMapPoints(self, mode, toCamera, toCameraR, fx, fy, cx, cy, width, height, valid, wPos, maxScaleDist, logScale, nScaleLev,
+                         predL, scaleLevelL, inFrame, predR=None, scaleLevelR=None, inFrameR=None, matches=None, matchedL=None,
+                         matchedR=None, outliers=None):
+        """mode 0 removeOutOfFrameMPs, 1 removeOutOfFrameMPsMono (returns keep), 2 PredictMPsPosition; in-out arrays updated in place."""
+        c = lambda a, dt: None if a is None else np.ascontiguousarray(a, dt)
+        M = len(wPos)
+        keep = np.zeros(max(M, 1), np.uint8)
+        for a, dt in ((predL, np.float32), (scaleLevelL, np.int32), (inFrame, np.uint8), (predR, np.float32), (scaleLevelR, np.int32),
+                      (inFrameR, np.uint8), (matches, np.int32), (matchedL, np.int32), (matchedR, np.int32), (outliers, np.uint8)):
+            assert a is None or (a.dtype == dt and a.flags.c_contiguous)
+        k = [c(toCamera, np.float64), c(toCameraR, np.float64), c(valid, np.uint8), c(wPos, np.float64), c(maxScaleDist, np.float32),
+             c(logScale, np.float32), c(nScaleLev, np.int32)]
+        _check(self._lib.gvs_predict_mappoints(self.h, mode, _p(k[0]), _p(k[1]), fx, fy, cx, cy, width, height, M, _p(k[2]), _p(k[3]), _p(k[4]),
+                                               _p(k[5]), _p(k[6]), _p(predL), _p(scaleLevelL), _p(inFrame), _p(predR), _p(scaleLevelR),
+                                               _p(inFrameR), _p(keep), _p(matches), _p(matchedL), 0 if matchedL is None else len(matchedL),
+                                               _p(matchedR), 0 if matchedR is None else len(matchedR), _p(outliers)))
+        return keep[:M] if mode != 2 else None
 
     # -- FeatureTracker::findOutliersR / findOutliersMono (src/FeatureTracker.cpp:582-684) against frame `frame` of the last batch
     def _find_outliers(self, mode, frame, estimPose, toCameraR, fx, fy, cx, cy, thres, closeDist, valid, wPos, inFrame, inFrameR,

@@ -196,6 +196,25 @@ void launchMedianDescriptor(const uint8_t* descs, const int* offsets, int P, int
 void launchWorldToFrame(int M, const double* poseInv, double fx, double fy, double cx, double cy, int width, int height,
                         const double* wPos, const float* maxScaleDist, const float* logScale, const int* nScaleLev, float* pred,
                         int* scaleLevel, uint8_t* inFrame, cudaStream_t s, int* launches);
+// FeatureTracker::removeOutOfFrameMPs / removeOutOfFrameMPsMono / PredictMPsPosition
+struct PredictArgs {
+    int mode, M;               // 0 removeOutOfFrameMPs, 1 ...Mono, 2 PredictMPsPosition
+    const double* toCamera;    // predNPose^-1, row-major
+    const double* toCameraR;   // (predNPose * extrinsics)^-1
+    double fx, fy, cx, cy;
+    int width, height;
+    const uint8_t* valid;
+    const double* wPos;
+    const float* maxScaleDist;
+    const float* logScale;
+    const int* nScaleLev;
+    float* predL; int* scaleLevelL; uint8_t* inFrame;      // in-out
+    float* predR; int* scaleLevelR; uint8_t* inFrameR;
+    uint8_t* keep;             // modes 0/1
+    int* matches; int* matchedL; int* matchedR; uint8_t* outliers;   // mode 2, in-out
+};
+void launchPredictMapPoints(const PredictArgs& a, cudaStream_t s, int* launches);
+
 // FeatureTracker::findOutliersR / findOutliersMono
 struct OutlierArgs {
     int mode;                  // 0 findOutliersR, 1 findOutliersMono

@@ -1352,6 +1352,100 @@ int gvs_project_mappoints(gvs_matcher* m, const double* pose_inv, double fx, dou
     return GVS_OK;
 }
 
+int gvs_predict_mappoints(gvs_matcher* m, int mode, const double* to_camera, const double* to_camera_r, double fx, double fy,
+                          double cx, double cy, int width, int height, int count, const uint8_t* valid, const double* world_pos,
+                          const float* max_scale_dist, const float* log_scale, const int32_t* n_scale_lev, float* pred_l,
+                          int32_t* scale_level_l, uint8_t* in_frame, float* pred_r, int32_t* scale_level_r, uint8_t* in_frame_r,
+                          uint8_t* keep, int32_t* matches, int32_t* matched_l, int n_left, int32_t* matched_r, int n_right,
+                          uint8_t* outliers) {
+    if (!m || !to_camera || count < 0 || mode < 0 || mode > 2) return fail(GVS_ERR_INVALID, "bad argument");
+    if (count == 0) return GVS_OK;
+    const bool two = mode != 1;
+    if (!world_pos || !max_scale_dist || !log_scale || !n_scale_lev || !pred_l || !scale_level_l || !in_frame) return fail(GVS_ERR_INVALID, "null array");
+    if (two && (!to_camera_r || !pred_r || !scale_level_r || !in_frame_r)) return fail(GVS_ERR_INVALID, "right-camera arrays missing");
+    if (mode != 2 && !keep) return fail(GVS_ERR_INVALID, "keep is required");
+    if (mode == 2) {
+        if (!matches || !matched_l || !matched_r || !outliers || n_left < 0 || n_right < 0) return fail(GVS_ERR_INVALID, "match arrays missing");
+        for (int i = 0; i < count; i++)
+            if (matches[2 * i] >= n_left || matches[2 * i + 1] >= n_right) return fail(GVS_ERR_INVALID, "match index outside matched_l / matched_r");
+    }
+    DeviceGuard deviceGuard(m->L->device);
+    cudaStream_t s = m->L->stream;
+    const size_t M = (size_t)count, NL = (size_t)std::max(n_left, 1), NR = (size_t)std::max(n_right, 1);
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    size_t o = 0;
+    auto take = [&](size_t bytes) { const size_t at = o; o += al(bytes); return at; };
+    const size_t oPose = take(256), oVa = take(M), oW = take(M * 32), oMs = take(M * 4), oLs = take(M * 4), oNl = take(M * 4),
+                 oPl = take(M * 8), oSl = take(M * 4), oIf = take(M), oPr = take(M * 8), oSr = take(M * 4), oIr = take(M), oKeep = take(M),
+                 oMt = take(M * 8), oML = take(NL * 4), oMR = take(NR * 4), oOut = take(M);
+    if (o > m->pjBytes) {
+        GVS_CUDA_OK(cudaStreamSynchronize(s));
+        cudaFree(m->pj); m->pj = nullptr; m->pjBytes = 0;
+        GVS_CUDA_OK(devAlloc(&m->pj, o));
+        m->pjBytes = o;
+    }
+    uint8_t* b = m->pj;
+    auto up = [&](size_t off, const void* src, size_t bytes) -> cudaError_t {
+        return src ? cudaMemcpyAsync(b + off, src, bytes, cudaMemcpyHostToDevice, s) : cudaSuccess;
+    };
+    GVS_CUDA_OK(up(oPose, to_camera, 128));
+    GVS_CUDA_OK(up(oPose + 128, two ? to_camera_r : nullptr, 128));
+    GVS_CUDA_OK(up(oVa, valid, M));
+    GVS_CUDA_OK(up(oW, world_pos, M * 32));
+    GVS_CUDA_OK(up(oMs, max_scale_dist, M * 4));
+    GVS_CUDA_OK(up(oLs, log_scale, M * 4));
+    GVS_CUDA_OK(up(oNl, n_scale_lev, M * 4));
+    GVS_CUDA_OK(up(oPl, pred_l, M * 8));
+    GVS_CUDA_OK(up(oSl, scale_level_l, M * 4));
+    GVS_CUDA_OK(up(oIf, in_frame, M));
+    if (two) {
+        GVS_CUDA_OK(up(oPr, pred_r, M * 8));
+        GVS_CUDA_OK(up(oSr, scale_level_r, M * 4));
+        GVS_CUDA_OK(up(oIr, in_frame_r, M));
+    }
+    if (mode == 2) {
+        GVS_CUDA_OK(up(oMt, matches, M * 8));
+        GVS_CUDA_OK(up(oML, matched_l, (size_t)n_left * 4));
+        GVS_CUDA_OK(up(oMR, matched_r, (size_t)n_right * 4));
+        GVS_CUDA_OK(up(oOut, outliers, M));
+    }
+    PredictArgs a{};
+    a.mode = mode; a.M = count;
+    a.toCamera = reinterpret_cast<double*>(b + oPose); a.toCameraR = reinterpret_cast<double*>(b + oPose + 128);
+    a.fx = fx; a.fy = fy; a.cx = cx; a.cy = cy; a.width = width; a.height = height;
+    a.valid = valid ? b + oVa : nullptr; a.wPos = reinterpret_cast<double*>(b + oW);
+    a.maxScaleDist = reinterpret_cast<float*>(b + oMs); a.logScale = reinterpret_cast<float*>(b + oLs); a.nScaleLev = reinterpret_cast<int*>(b + oNl);
+    a.predL = reinterpret_cast<float*>(b + oPl); a.scaleLevelL = reinterpret_cast<int*>(b + oSl); a.inFrame = b + oIf;
+    a.predR = reinterpret_cast<float*>(b + oPr); a.scaleLevelR = reinterpret_cast<int*>(b + oSr); a.inFrameR = b + oIr;
+    a.keep = b + oKeep;
+    a.matches = reinterpret_cast<int*>(b + oMt); a.matchedL = reinterpret_cast<int*>(b + oML); a.matchedR = reinterpret_cast<int*>(b + oMR);
+    a.outliers = b + oOut;
+    int launches = 0;
+    launchPredictMapPoints(a, s, &launches);
+    m->launchesTotal += launches;
+    auto down = [&](void* dst, size_t off, size_t bytes) -> cudaError_t {
+        return dst && bytes ? cudaMemcpyAsync(dst, b + off, bytes, cudaMemcpyDeviceToHost, s) : cudaSuccess;
+    };
+    GVS_CUDA_OK(down(pred_l, oPl, M * 8));
+    GVS_CUDA_OK(down(scale_level_l, oSl, M * 4));
+    GVS_CUDA_OK(down(in_frame, oIf, M));
+    if (two) {
+        GVS_CUDA_OK(down(pred_r, oPr, M * 8));
+        GVS_CUDA_OK(down(scale_level_r, oSr, M * 4));
+        GVS_CUDA_OK(down(in_frame_r, oIr, M));
+    }
+    if (mode != 2) GVS_CUDA_OK(down(keep, oKeep, M));
+    else {
+        GVS_CUDA_OK(down(matches, oMt, M * 8));
+        GVS_CUDA_OK(down(matched_l, oML, (size_t)n_left * 4));
+        GVS_CUDA_OK(down(matched_r, oMR, (size_t)n_right * 4));
+        GVS_CUDA_OK(down(outliers, oOut, M));
+    }
+    GVS_CUDA_OK(cudaStreamSynchronize(s));
+    GVS_CUDA_OK(cudaGetLastError());
+    return GVS_OK;
+}
+
 int gvs_find_outliers(gvs_matcher* m, int frame, int mode, const double* pose, const double* pose_r, double fx, double fy,
                       double cx, double cy, double thres, float close_dist, int count, const uint8_t* valid,
                       const double* world_pos, const uint8_t* in_frame, const uint8_t* in_frame_r, int32_t* matches,

@@ -428,27 +428,68 @@ void launchMedianDescriptor(const uint8_t* descs, const int* offsets, int P, int
 
 // FeatureTracker::worldToFrame + MapPoint::predictScale (src/FeatureTracker.cpp:685-741, src/Map.cpp:13-23), thread per map
 // point.  Double precision, explicit round-to-nearest operations in the reference's left-to-right order (no FMA).
+// one map point into one camera; returns worldToFrame's bool and updates pred / scaleLevel only when the point is in the frame
+__device__ __forceinline__ bool worldToFrameOne(const double* __restrict__ poseInv, const double* __restrict__ w, double fx, double fy,
+                                                double cx, double cy, int width, int height, float maxScaleDist, float logScale,
+                                                int nScaleLev, float* pred, int* scaleLevel) {
+    double pt[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+        pt[r] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(poseInv[4 * r], w[0]), __dmul_rn(poseInv[4 * r + 1], w[1])), __dmul_rn(poseInv[4 * r + 2], w[2])),
+                          __dmul_rn(poseInv[4 * r + 3], w[3]));
+    if (pt[2] <= 0.0) return false;
+    const double invZ = __ddiv_rn(1.0, pt[2]);
+    const double u = __dadd_rn(__dmul_rn(__dmul_rn(fx, pt[0]), invZ), cx), v = __dadd_rn(__dmul_rn(__dmul_rn(fy, pt[1]), invZ), cy);
+    if (u < 0 || v < 0 || u >= width || v >= height) return false;
+    const float dist = (float)__dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(pt[0], pt[0]), __dmul_rn(pt[1], pt[1])), __dmul_rn(pt[2], pt[2])));
+    const float dif = __fdiv_rn(maxScaleDist, dist);
+    int scale = (int)ceil(__ddiv_rn(log((double)dif), (double)logScale));
+    if (scale < 0) scale = 0; else if (scale >= nScaleLev) scale = nScaleLev - 1;
+    *scaleLevel = scale; pred[0] = (float)u; pred[1] = (float)v;
+    return true;
+}
+
 __global__ void world_to_frame_kernel(int M, const double* __restrict__ poseInv, double fx, double fy, double cx, double cy, int width,
                                       int height, const double* __restrict__ wPos, const float* __restrict__ maxScaleDist,
                                       const float* __restrict__ logScale, const int* __restrict__ nScaleLev, float* __restrict__ pred,
                                       int* __restrict__ scaleLevel, uint8_t* __restrict__ inFrame) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= M) return;
-    const double w0 = wPos[4 * i], w1 = wPos[4 * i + 1], w2 = wPos[4 * i + 2], w3 = wPos[4 * i + 3];
-    double pt[3];
-#pragma unroll
-    for (int r = 0; r < 3; r++)
-        pt[r] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(poseInv[4 * r], w0), __dmul_rn(poseInv[4 * r + 1], w1)), __dmul_rn(poseInv[4 * r + 2], w2)),
-                          __dmul_rn(poseInv[4 * r + 3], w3));
-    if (pt[2] <= 0.0) { inFrame[i] = 0; return; }
-    const double invZ = __ddiv_rn(1.0, pt[2]);
-    const double u = __dadd_rn(__dmul_rn(__dmul_rn(fx, pt[0]), invZ), cx), v = __dadd_rn(__dmul_rn(__dmul_rn(fy, pt[1]), invZ), cy);
-    if (u < 0 || v < 0 || u >= width || v >= height) { inFrame[i] = 0; return; }
-    const float dist = (float)__dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(pt[0], pt[0]), __dmul_rn(pt[1], pt[1])), __dmul_rn(pt[2], pt[2])));
-    const float dif = __fdiv_rn(maxScaleDist[i], dist);
-    int scale = (int)ceil(__ddiv_rn(log((double)dif), (double)logScale[i]));
-    if (scale < 0) scale = 0; else if (scale >= nScaleLev[i]) scale = nScaleLev[i] - 1;
-    scaleLevel[i] = scale; inFrame[i] = 1; pred[2 * i] = (float)u; pred[2 * i + 1] = (float)v;
+    inFrame[i] = worldToFrameOne(poseInv, wPos + 4 * (size_t)i, fx, fy, cx, cy, width, height, maxScaleDist[i], logScale[i], nScaleLev[i],
+                                 pred + 2 * (size_t)i, scaleLevel + i) ? 1 : 0;
+}
+
+// FeatureTracker::removeOutOfFrameMPs (src/FeatureTracker.cpp:910-940; mode 0), removeOutOfFrameMPsMono (:942-967; mode 1) and
+// PredictMPsPosition (:969-1013; mode 2), thread per active map point.  Every iteration of the reference's loops only touches its
+// own map point and, in mode 2, the matched-index slots of its own match (distinct matches own distinct slots; equal ones would
+// all write -1), so the loops are order independent.
+__global__ void predict_mappoints_kernel(const PredictArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.M) return;
+    if (a.mode != 2) a.keep[i] = 0;
+    if (a.valid && !a.valid[i]) return;        // if ( !mp ) continue;  (modes 0/1 also: if ( mp->GetIsOutlier() ) continue;)
+    const double* w = a.wPos + 4 * (size_t)i;
+    const bool c1 = worldToFrameOne(a.toCamera, w, a.fx, a.fy, a.cx, a.cy, a.width, a.height, a.maxScaleDist[i], a.logScale[i],
+                                    a.nScaleLev[i], a.predL + 2 * (size_t)i, a.scaleLevelL + i);
+    a.inFrame[i] = c1 ? 1 : 0;
+    bool c2 = true;
+    if (a.mode != 1) {
+        c2 = worldToFrameOne(a.toCameraR, w, a.fx, a.fy, a.cx, a.cy, a.width, a.height, a.maxScaleDist[i], a.logScale[i], a.nScaleLev[i],
+                             a.predR + 2 * (size_t)i, a.scaleLevelR + i);
+        a.inFrameR[i] = c2 ? 1 : 0;
+    }
+    if (a.mode != 2) { a.keep[i] = (c1 && c2) ? 1 : 0; return; }
+    const bool out = a.outliers[i] != 0;
+    if (out) a.outliers[i] = 0;
+    const int first = a.matches[2 * i], second = a.matches[2 * i + 1];
+    if ((!c1 || out) && first >= 0) { a.matchedL[first] = -1; a.matches[2 * i] = -1; }
+    if ((!c2 || out) && second >= 0) { a.matchedR[second] = -1; a.matches[2 * i + 1] = -1; }
+}
+
+void launchPredictMapPoints(const PredictArgs& a, cudaStream_t s, int* launches) {
+    if (a.M <= 0) return;
+    predict_mappoints_kernel<<<(a.M + 127) / 128, 128, 0, s>>>(a);
+    ++*launches;
 }
 
 void launchWorldToFrame(int M, const double* poseInv, double fx, double fy, double cx, double cy, int width, int height,

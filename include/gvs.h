@@ -235,6 +235,24 @@ int gvs_project_mappoints(gvs_matcher* fm, const double* pose_inv, double fx, do
                           int count, const double* world_pos, const float* max_scale_dist, const float* log_scale,
                           const int32_t* n_scale_lev, float* pred, int32_t* scale_level, uint8_t* in_frame);
 
+/* The worldToFrame loops of the tracking thread, for `count` active map points at once:
+ *   mode 0  FeatureTracker::removeOutOfFrameMPs     (src/FeatureTracker.cpp:910-940): both cameras, keep[i] = c1 && c2
+ *   mode 1  FeatureTracker::removeOutOfFrameMPsMono (:942-967): left camera only, keep[i] = c1
+ *   mode 2  FeatureTracker::PredictMPsPosition      (:969-1013): both cameras; a point that leaves a camera, or that is flagged in
+ *           outliers[], loses its match on that side (matched_l / matched_r slot and matches[i] set to -1), outliers[i] is reset
+ * to_camera = predNPose^-1, to_camera_r = (predNPose * extrinsics)^-1 (16 doubles row-major; the inverses stay on the host, :913-914).
+ * valid[i] = the reference does not `continue` for point i (mp != nullptr, and for modes 0/1 !mp->GetIsOutlier()); NULL = all.
+ * pred_l / scale_level_l / in_frame (and the _r arrays; NULL in mode 1) are MapPoint::predL / scaleLevelL / inFrame, in-out: only
+ * visited points are written, pred and scale level only when the point is in the frame (worldToFrame, :685-741).
+ * keep (modes 0/1, out): 1 = the point stays in activeMapPoints (the caller compacts the vector and calls setActive, :926-937).
+ * matches (count x 2), matched_l (n_left), matched_r (n_right), outliers (count): mode 2 only, in-out. */
+int gvs_predict_mappoints(gvs_matcher* fm, int mode, const double* to_camera, const double* to_camera_r, double fx, double fy,
+                          double cx, double cy, int width, int height, int count, const uint8_t* valid, const double* world_pos,
+                          const float* max_scale_dist, const float* log_scale, const int32_t* n_scale_lev, float* pred_l,
+                          int32_t* scale_level_l, uint8_t* in_frame, float* pred_r, int32_t* scale_level_r, uint8_t* in_frame_r,
+                          uint8_t* keep, int32_t* matches, int32_t* matched_l, int n_left, int32_t* matched_r, int n_right,
+                          uint8_t* outliers);
+
 /* FeatureTracker::findOutliersR (src/FeatureTracker.cpp:582-649; mode 0) and findOutliersMono (:651-684; mode 1) with
  * check2dError (:147-164), for the `count` active map points against frame `frame` of the last batch (the
  * outlier scoring that follows every pose estimate).  The frame's keys and stereo arrays are the device-resident ones, and the

@@ -978,6 +978,37 @@ void ora_find_outliers(int mode, const double* pose, const double* poseR, double
     counts[1] = nStereo;
 }
 
+// FeatureTracker::removeOutOfFrameMPs (src/FeatureTracker.cpp:910-940; mode 0), removeOutOfFrameMPsMono (:942-967; mode 1) and
+// PredictMPsPosition (:969-1013; mode 2) as sequential loops over ora_world_to_frame's single-point body.
+// valid[i] = the reference does not `continue` for point i.  Restated, not compiled from the reference (FeatureTracker.cpp needs GTSAM).
+void ora_predict_mappoints(int mode, const double* toCamera, const double* toCameraR, double fx, double fy, double cx, double cy, int width,
+                           int height, int M, const uint8_t* valid, const double* wPos, const float* maxScaleDist, const float* logScale,
+                           const int* nScaleLev, float* predL, int* scaleLevelL, uint8_t* inFrame, float* predR, int* scaleLevelR,
+                           uint8_t* inFrameR, uint8_t* keep, int* matches, int* matchedL, int* matchedR, uint8_t* outliers) {
+    for (int i = 0; i < M; i++) {
+        if (mode != 2) keep[i] = 0;
+        if (valid && !valid[i]) continue;
+        uint8_t c1 = 0, c2 = 1;
+        ora_world_to_frame(toCamera, fx, fy, cx, cy, width, height, 1, wPos + 4 * i, maxScaleDist + i, logScale + i, nScaleLev + i,
+                           predL + 2 * i, scaleLevelL + i, &c1);
+        inFrame[i] = c1;
+        if (mode != 1) {
+            ora_world_to_frame(toCameraR, fx, fy, cx, cy, width, height, 1, wPos + 4 * i, maxScaleDist + i, logScale + i, nScaleLev + i,
+                               predR + 2 * i, scaleLevelR + i, &c2);
+            inFrameR[i] = c2;
+        }
+        if (mode != 2) { keep[i] = c1 && c2; continue; }
+        int& first = matches[2 * i]; int& second = matches[2 * i + 1];
+        if (!c1 && first >= 0) { matchedL[first] = -1; first = -1; }
+        if (!c2 && second >= 0) { matchedR[second] = -1; second = -1; }
+        if (outliers[i]) {
+            outliers[i] = 0;
+            if (first >= 0) { matchedL[first] = -1; first = -1; }
+            if (second >= 0) { matchedR[second] = -1; second = -1; }
+        }
+    }
+}
+
 int ora_descriptor_distance(const uint8_t* a, const uint8_t* b) { return descriptorDistance(a, b); }
 
 // ---- primitive-level entry points (pinned one by one against cv2 in tests/test_oracle_vs_cv2.py)

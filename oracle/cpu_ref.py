@@ -200,6 +200,22 @@ def world_to_frame(poseInv, fx, fy, cx, cy, width, height, wPos, maxScaleDist, l
     return inF
 
 
+def predict_mappoints(mode, toCamera, toCameraR, fx, fy, cx, cy, width, height, valid, wPos, maxScaleDist, logScale, nScaleLev,
+                      predL, scaleLevelL, inFrame, predR=None, scaleLevelR=None, inFrameR=None, matches=None, matchedL=None,
+                      matchedR=None, outliers=None):
+    """removeOutOfFrameMPs (mode 0) / ...Mono (1) / PredictMPsPosition (2), reference src/FeatureTracker.cpp:910-1013; the in-out
+    arrays are modified in place; returns keep (modes 0/1) or None."""
+    c = lambda a, dt: None if a is None else np.ascontiguousarray(a, dt)
+    M = len(wPos)
+    keep = np.zeros(M, np.uint8)
+    k = [c(toCamera, np.float64), c(toCameraR, np.float64), c(valid, np.uint8), c(wPos, np.float64), c(maxScaleDist, np.float32),
+         c(logScale, np.float32), c(nScaleLev, np.int32)]
+    lib().ora_predict_mappoints(mode, _p(k[0]), _p(k[1]), C.c_double(fx), C.c_double(fy), C.c_double(cx), C.c_double(cy), width, height, M,
+                                _p(k[2]), _p(k[3]), _p(k[4]), _p(k[5]), _p(k[6]), _p(predL), _p(scaleLevelL), _p(inFrame), _p(predR),
+                                _p(scaleLevelR), _p(inFrameR), _p(keep), _p(matches), _p(matchedL), _p(matchedR), _p(outliers))
+    return keep if mode != 2 else None
+
+
 def find_outliers(mode, pose, poseR, fx, fy, cx, cy, thres, closeDist, invSigma, valid, wPos, inFrame, inFrameR, matches, outliers,
                   kl, kr, depth, close, rightIdxs, leftIdxs):
     """findOutliersR (mode 0) / findOutliersMono (mode 1), reference src/FeatureTracker.cpp:582-684; matches, outliers and the

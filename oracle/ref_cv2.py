@@ -732,6 +732,43 @@ def worldToFrame(wPos: np.ndarray, predPoseInv: np.ndarray, fx, fy, cx, cy, widt
     return ok
 
 
+def predictMapPoints(mode, toCamera, toCameraR, fx, fy, cx, cy, width, height, valid, wPos, maxScaleDist, logScale, nScaleLev,
+                     predL, scaleLevelL, inFrame, predR=None, scaleLevelR=None, inFrameR=None, matches=None, matchedL=None,
+                     matchedR=None, outliers=None):
+    """FeatureTracker::removeOutOfFrameMPs (src/FeatureTracker.cpp:910-940; mode 0), removeOutOfFrameMPsMono (:942-967; mode 1),
+    PredictMPsPosition (:969-1013; mode 2) on top of worldToFrame above; returns keep (modes 0/1)."""
+    M = len(wPos)
+    keep = np.zeros(M, np.uint8)
+    for i in range(M):
+        if valid is not None and not valid[i]:
+            continue
+        one = slice(i, i + 1)
+        c1 = bool(worldToFrame(wPos[one], toCamera, fx, fy, cx, cy, width, height, maxScaleDist[one], logScale[one], nScaleLev[one],
+                               predL[one], scaleLevelL[one], inFrame[one])[0])
+        c2 = True
+        if mode != 1:
+            c2 = bool(worldToFrame(wPos[one], toCameraR, fx, fy, cx, cy, width, height, maxScaleDist[one], logScale[one], nScaleLev[one],
+                                   predR[one], scaleLevelR[one], inFrameR[one])[0])
+        if mode != 2:
+            keep[i] = 1 if (c1 and c2) else 0
+            continue
+        if not c1 and matches[i][0] >= 0:
+            matchedL[matches[i][0]] = -1
+            matches[i][0] = -1
+        if not c2 and matches[i][1] >= 0:
+            matchedR[matches[i][1]] = -1
+            matches[i][1] = -1
+        if outliers[i]:
+            outliers[i] = 0
+            if matches[i][0] >= 0:
+                matchedL[matches[i][0]] = -1
+                matches[i][0] = -1
+            if matches[i][1] >= 0:
+                matchedR[matches[i][1]] = -1
+                matches[i][1] = -1
+    return keep
+
+
 def _check2dError(P, w, obs, fx, fy, cx, cy, thres, weight):
     """FeatureTracker::check2dError (src/FeatureTracker.cpp:147-164); returns (outlier, z)."""
     p = [((float(P[r, 0]) * w[0] + float(P[r, 1]) * w[1]) + float(P[r, 2]) * w[2]) + float(P[r, 3]) * w[3] for r in range(3)]

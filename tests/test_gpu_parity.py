@@ -441,6 +441,27 @@ def test_world_to_frame_projection():
     assert np.max(np.abs(pa - pb), initial=0) <= 1e-3 and np.array_equal(pa, pb)   # tolerance of the north star, and bit exact
 
 
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_predict_mappoints(mode):
+    """SURVEY 8(f) rank 3: FeatureTracker::removeOutOfFrameMPs / removeOutOfFrameMPsMono / PredictMPsPosition on the device against
+    the oracle's sequential loops (double precision projection bit exact, match bookkeeping exact)."""
+    from test_oracle_vs_cv2 import _predict_case, _run_predict
+    cam = (435.2047, 435.2047, 367.4517, 252.2008, 752, 480)
+    c = _predict_case(seed=9 + mode, M=20000, nl=2100, nr=2050)
+    feL, feR, fm = _handles(synth.CONFIGS["small"], 1)
+    ka, a = _run_predict(fm.predictMapPoints, mode, c, cam)
+    kb, b = _run_predict(cpu_ref.predict_mappoints, mode, c, cam)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    if mode != 2:
+        assert np.array_equal(ka, kb) and 0.05 < kb.mean() < 0.9
+    else:
+        assert (b["matches"] != c["matches"]).sum() > 500
+    with pytest.raises(gvs.GvsError):
+        bad = c["matches"].copy(); bad[0, 0] = 10 ** 6
+        _run_predict(fm.predictMapPoints, 2, dict(c, matches=bad), cam)
+
+
 @pytest.mark.parametrize("mode", [0, 1])
 def test_find_outliers(mode):
     """SURVEY 8(f) rank 3: FeatureTracker::findOutliersR / findOutliersMono on the device-resident frame against the oracle's

@@ -327,3 +327,52 @@ def test_find_outliers_cpp_matches_python_restatement(mode):
     if mode == 0:
         assert nSt > 20 and (b[1][:, 1] != c["matches"][:, 1]).sum() > 5           # stereo inliers and rejected partners
         assert (b[3][1] != st["close"].astype(np.uint8)).sum() > 0
+
+
+def _predict_case(seed=0, M=3000, nl=900, nr=880):
+    """Inputs for removeOutOfFrameMPs / PredictMPsPosition: the projection case above for both cameras plus match bookkeeping."""
+    rng = np.random.default_rng(seed)
+    Pinv, wPos, msd, ls, nlev = _projection_case(seed, M)
+    Tr = np.eye(4); Tr[0, 3] = -0.11
+    valid = (rng.random(M) < 0.9).astype(np.uint8)
+    matches = np.full((M, 2), -1, np.int32)
+    pick = rng.random(M) < 0.6
+    matches[pick, 0] = rng.permutation(max(nl, M))[:pick.sum()] % nl
+    pick = rng.random(M) < 0.5
+    matches[pick, 1] = rng.permutation(max(nr, M))[:pick.sum()] % nr
+    matchedL = np.full(nl, -1, np.int32); matchedR = np.full(nr, -1, np.int32)
+    for i in range(M):
+        if matches[i, 0] >= 0: matchedL[matches[i, 0]] = i
+        if matches[i, 1] >= 0: matchedR[matches[i, 1]] = i
+    outliers = (rng.random(M) < 0.15).astype(np.uint8)
+    return dict(toCamera=Pinv, toCameraR=Tr @ Pinv, wPos=wPos, msd=msd, ls=ls, nlev=nlev, valid=valid, matches=matches,
+                matchedL=matchedL, matchedR=matchedR, outliers=outliers)
+
+
+def _run_predict(fn, mode, c, cam):
+    M = len(c["wPos"])
+    st = dict(predL=np.full((M, 2), -7, np.float32), slL=np.full(M, -7, np.int32), inF=np.full(M, 7, np.uint8),
+              predR=np.full((M, 2), -7, np.float32), slR=np.full(M, -7, np.int32), inFR=np.full(M, 7, np.uint8),
+              matches=c["matches"].copy(), mL=c["matchedL"].copy(), mR=c["matchedR"].copy(), out=c["outliers"].copy())
+    two = mode != 1
+    keep = fn(mode, c["toCamera"], c["toCameraR"] if two else None, *cam, c["valid"], c["wPos"], c["msd"], c["ls"], c["nlev"],
+              st["predL"], st["slL"], st["inF"], st["predR"] if two else None, st["slR"] if two else None, st["inFR"] if two else None,
+              *( (st["matches"], st["mL"], st["mR"], st["out"]) if mode == 2 else (None, None, None, None) ))
+    return keep, st
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_predict_mappoints_cpp_matches_python_restatement(mode):
+    """removeOutOfFrameMPs / removeOutOfFrameMPsMono / PredictMPsPosition (src/FeatureTracker.cpp:910-1013),
+    C++ oracle vs the Python restatement."""
+    cam = (435.2047, 435.2047, 367.4517, 252.2008, 752, 480)
+    c = _predict_case(seed=4 + mode, M=1200)
+    ka, a = _run_predict(ref_cv2.predictMapPoints, mode, c, cam)
+    kb, b = _run_predict(cpu_ref.predict_mappoints, mode, c, cam)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    if mode != 2:
+        assert np.array_equal(ka, kb) and 0.05 < kb.mean() < 0.9 and (b["inF"] == 7).sum() > 20      # kept, dropped and unvisited points
+    else:
+        assert (b["matches"] != c["matches"]).sum() > 50 and b["out"].sum() == (c["outliers"] * (1 - c["valid"])).sum()
+        assert (b["mL"] != c["matchedL"]).sum() > 20 and (b["mR"] != c["matchedR"]).sum() > 20
