@@ -272,6 +272,35 @@ class FeatureMatcher {
         return nInliers;
     }
 
+    // FeatureTracker::removeOutOfFrameMPs (src/FeatureTracker.cpp:910-940) with the reference's arguments (plus the tracker's camera
+    // members).  Mat4 / MapPointT are the reference's Eigen::Matrix4d / MapPoint (fields wp via getWordPose4d(), maxScaleDist,
+    // lastObsKF->logScale / nScaleLev, predL/R, scaleLevelL/R, inFrame/R, GetIsOutlier(), setActive()).
+    template <class Mat4, class MapPointT>
+    void removeOutOfFrameMPs(const Mat4& predNPose, const Mat4& extrinsics, double fx, double fy, double cx, double cy, int width, int height,
+                             std::vector<MapPointT*>& activeMapPoints) {
+        const Mat4 toRCamera = (predNPose * extrinsics).inverse(), toCamera = predNPose.inverse();
+        std::vector<uint8_t> keep;
+        predictImpl(0, toCamera, &toRCamera, fx, fy, cx, cy, width, height, activeMapPoints, keep, nullptr, nullptr, nullptr, nullptr);
+        size_t j = 0;
+        for (size_t i = 0; i < activeMapPoints.size(); i++) {
+            MapPointT* mp = activeMapPoints[i];
+            if (!mp || mp->GetIsOutlier()) continue;
+            mp->setActive(keep[i] != 0);
+            if (keep[i]) activeMapPoints[j++] = mp;
+        }
+        activeMapPoints.resize(j);
+    }
+    // FeatureTracker::PredictMPsPosition (src/FeatureTracker.cpp:969-1013); the caller holds map->mapMutex like the reference
+    template <class Mat4, class MapPointT>
+    void PredictMPsPosition(const Mat4& predNPose, const Mat4& extrinsics, double fx, double fy, double cx, double cy, int width, int height,
+                            std::vector<MapPointT*>& activeMapPoints, std::vector<int>& matchedIdxsL, std::vector<int>& matchedIdxsR,
+                            std::vector<std::pair<int, int>>& matchesIdxs, std::vector<bool>& MPsOutliers) {
+        const Mat4 toRCamera = (predNPose * extrinsics).inverse(), toCamera = predNPose.inverse();
+        std::vector<uint8_t> keep;
+        predictImpl(2, toCamera, &toRCamera, fx, fy, cx, cy, width, height, activeMapPoints, keep, &matchesIdxs, &matchedIdxsL, &matchedIdxsR,
+                    &MPsOutliers);
+    }
+
     // MapPoint::calcDescriptor (src/Map.cpp:145-210) for one observation list: index of the chosen descriptor
     int medianDescriptor(const std::vector<cv::Mat>& vDescriptors) {
         const int N = (int)vDescriptors.size();
@@ -295,6 +324,47 @@ class FeatureMatcher {
     gvs_matcher* handle() const { return h_; }
 
   private:
+    template <class Mat4, class MapPointT>
+    void predictImpl(int mode, const Mat4& toCamera, const Mat4* toRCamera, double fx, double fy, double cx, double cy, int width, int height,
+                     std::vector<MapPointT*>& mps, std::vector<uint8_t>& keep, std::vector<std::pair<int, int>>* matchesIdxs,
+                     std::vector<int>* matchedIdxsL, std::vector<int>* matchedIdxsR, std::vector<bool>* MPsOutliers) {
+        const int M = (int)mps.size();
+        keep.assign(M, 0);
+        if (M == 0) return;
+        double tc[16], tr[16];
+        for (int r = 0; r < 4; r++)
+            for (int c = 0; c < 4; c++) { tc[4 * r + c] = toCamera(r, c); tr[4 * r + c] = toRCamera ? (*toRCamera)(r, c) : 0.0; }
+        std::vector<uint8_t> valid(M), inF(M), inFR(M), out(M);
+        std::vector<double> wp(4 * (size_t)M, 0.0);
+        std::vector<float> msd(M, 1.f), ls(M, 1.f), pl(2 * (size_t)M), pr(2 * (size_t)M);
+        std::vector<int32_t> nsl(M, 1), sl(M), sr(M);
+        for (int i = 0; i < M; i++) {
+            const MapPointT* mp = mps[i];
+            valid[i] = mp != nullptr && (mode == 2 || !mp->GetIsOutlier());
+            if (MPsOutliers) out[i] = (*MPsOutliers)[i];
+            if (!mp) continue;
+            const auto w = mp->getWordPose4d();
+            for (int c = 0; c < 4; c++) wp[4 * (size_t)i + c] = w(c);
+            msd[i] = mp->maxScaleDist; ls[i] = mp->lastObsKF->logScale; nsl[i] = mp->lastObsKF->nScaleLev;
+            pl[2 * i] = mp->predL.x; pl[2 * i + 1] = mp->predL.y; pr[2 * i] = mp->predR.x; pr[2 * i + 1] = mp->predR.y;
+            sl[i] = mp->scaleLevelL; sr[i] = mp->scaleLevelR; inF[i] = mp->inFrame; inFR[i] = mp->inFrameR;
+        }
+        const bool two = mode != 1;
+        gvsCheck(gvs_predict_mappoints(h_, mode, tc, two ? tr : nullptr, fx, fy, cx, cy, width, height, M, valid.data(), wp.data(), msd.data(),
+                                       ls.data(), nsl.data(), pl.data(), sl.data(), inF.data(), two ? pr.data() : nullptr,
+                                       two ? sr.data() : nullptr, two ? inFR.data() : nullptr, keep.data(),
+                                       matchesIdxs ? reinterpret_cast<int32_t*>(matchesIdxs->data()) : nullptr,
+                                       matchedIdxsL ? matchedIdxsL->data() : nullptr, matchedIdxsL ? (int)matchedIdxsL->size() : 0,
+                                       matchedIdxsR ? matchedIdxsR->data() : nullptr, matchedIdxsR ? (int)matchedIdxsR->size() : 0,
+                                       MPsOutliers ? out.data() : nullptr));
+        for (int i = 0; i < M; i++) {
+            MapPointT* mp = mps[i];
+            if (!valid[i]) continue;
+            mp->predL = cv::Point2f(pl[2 * i], pl[2 * i + 1]); mp->scaleLevelL = sl[i]; mp->inFrame = inF[i] != 0;
+            if (two) { mp->predR = cv::Point2f(pr[2 * i], pr[2 * i + 1]); mp->scaleLevelR = sr[i]; mp->inFrameR = inFR[i] != 0; }
+        }
+        if (MPsOutliers) for (int i = 0; i < M; i++) (*MPsOutliers)[i] = out[i] != 0;
+    }
     template <class Mat4, class MapPointT>
     int findOutliersImpl(int mode, const Mat4& estimPose, const Mat4* toCameraR, double fx, double fy, double cx, double cy, float closeDist,
                          std::vector<MapPointT*>& activeMapPoints, TrackedKeys* keys, std::vector<std::pair<int, int>>& matchesIdxs,

@@ -2,6 +2,7 @@
 // from two raw u8 files; prints counts and FNV-1a checksums that tests/test_gpu_adapter.py compares with the ctypes path.
 #include <cstdio>
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include "../../include/gvs_adapter.hpp"
 
@@ -20,10 +21,14 @@ struct Mat4 {
     Mat4 inverse() const { Mat4 m; for (int i = 0; i < 3; i++) m.t[i] = -t[i]; return m; }
     Mat4 operator*(const Mat4& o) const { Mat4 m; for (int i = 0; i < 3; i++) m.t[i] = t[i] + o.t[i]; return m; }
 };
+struct KeyFrameStub { float logScale; int nScaleLev; };
 struct MapPoint {
     cv::Mat desc; cv::Point2f predL, predR; int scaleLevelL = 0, scaleLevelR = 0; bool inFrame = true, inFrameR = true;
     Vec4 wp{{0, 0, 0, 1}};
+    float maxScaleDist = 30.f; const KeyFrameStub* lastObsKF = nullptr; bool isOutlier = false, isActive = true;
     Vec4 getWordPose4d() const { return wp; }
+    bool GetIsOutlier() const { return isOutlier; }
+    void setActive(bool a) { isActive = a; }
 };
 
 int main(int argc, char** argv) {
@@ -84,6 +89,29 @@ int main(int argc, char** argv) {
         for (size_t i = 0; i < outl.size(); i++) { nOut += outl[i]; nCleared += pairs[i].second < 0; }
         std::printf("outliers in %d stereo %d out %d ridx %016llx close %d\n", nIn, nStereo, nOut,
                     (unsigned long long)fnv(k.rightIdxs.data(), k.rightIdxs.size() * 4), (int)std::count(k.close.begin(), k.close.end(), true));
+        // FeatureTracker::PredictMPsPosition and removeOutOfFrameMPs through the adapter: every 7th point is moved far out of the
+        // frame, every 11th is flagged as an outlier (PredictMPsPosition) / is an outlier map point (removeOutOfFrameMPs)
+        const KeyFrameStub kf{(float)std::log((double)1.2f), nL};   // KeyFrame::logScale
+        for (size_t i = 0; i < store.size(); i++) {
+            store[i].lastObsKF = &kf;
+            if (i % 7 == 0) store[i].wp.v[0] += 1000.0;
+            pairs[i] = {(int)i, k.rightIdxs[i]};
+            outl[i] = i % 11 == 0;
+        }
+        std::fill(mL.begin(), mL.end(), -1); std::fill(mR.begin(), mR.end(), -1);
+        for (size_t i = 0; i < pairs.size(); i++) { mL[pairs[i].first] = (int)i; if (pairs[i].second >= 0) mR[pairs[i].second] = (int)i; }
+        fm.PredictMPsPosition(estimPose, extrinsics, fx, fx, cx, cy, w, h, mps, mL, mR, pairs, outl);
+        int inL = 0, inR = 0, scaleSum = 0;
+        for (auto& mp : store) { inL += mp.inFrame; inR += mp.inFrameR; scaleSum += mp.scaleLevelL + 3 * mp.scaleLevelR; }
+        std::printf("predict inL %d inR %d scale %d pairs %016llx mL %016llx mR %016llx\n", inL, inR, scaleSum,
+                    (unsigned long long)fnv(pairs.data(), pairs.size() * 8), (unsigned long long)fnv(mL.data(), mL.size() * 4),
+                    (unsigned long long)fnv(mR.data(), mR.size() * 4));
+        for (size_t i = 0; i < store.size(); i++) store[i].isOutlier = i % 11 == 0;
+        std::vector<MapPoint*> act = mps;
+        fm.removeOutOfFrameMPs(estimPose, extrinsics, fx, fx, cx, cy, w, h, act);
+        int active = 0;
+        for (auto& mp : store) active += mp.isActive;
+        std::printf("remove kept %zu active %d\n", act.size(), active);
     } catch (const std::exception& e) { std::fprintf(stderr, "%s\n", e.what()); return 1; }
     return 0;
 }

@@ -65,3 +65,27 @@ def test_cpp_adapter_matches_oracle(tmp_path):
                                      None, wp, None, None, m, out, kl, kr, *arr)
     assert (int(t[2]), int(t[4]), int(t[6])) == (nIn, nSt, int(out.sum())) and nSt > 0
     assert t[8] == fnv(arr[2].tobytes()) and int(t[10]) == int(arr[1].sum()) and (arr[2] != s["rightIdxs"]).sum() > 0
+    # PredictMPsPosition / removeOutOfFrameMPs through the adapter against the oracle's loops on the same inputs
+    import math
+    n = len(kl)
+    wp2 = wp.copy(); wp2[::7, 0] += 1000.0
+    m2 = np.stack([np.arange(n), arr[2]], 1).astype(np.int32)          # the stereo arrays as findOutliersR left them
+    mL = np.full(n, -1, np.int32); mR = np.full(len(kr), -1, np.int32)
+    for i in range(n):
+        mL[m2[i, 0]] = i
+        if m2[i, 1] >= 0:
+            mR[m2[i, 1]] = i
+    outl = (np.arange(n) % 11 == 0).astype(np.uint8)
+    msd = np.full(n, 30, np.float32); ls = np.full(n, np.float32(math.log(np.float32(1.2))), np.float32); nlev = np.full(n, cfg["n_levels"], np.int32)
+    # MapPoint state before the call: predL = the key itself, predR = the key, levels = octave, inFrame = inFrameR = true (driver set-up)
+    pl = np.stack([kl["x"], kl["y"]], 1).astype(np.float32); pr_ = pl.copy()
+    sl = kl["octave"].astype(np.int32).copy(); sr = sl.copy(); inF = np.ones(n, np.uint8); inFR = np.ones(n, np.uint8)
+    cam = (fx, fx, cx, cy, w, h)
+    cpu_ref.predict_mappoints(2, T, TR, *cam, None, wp2, msd, ls, nlev, pl, sl, inF, pr_, sr, inFR, m2, mL, mR, outl)
+    t = lines[5].split()
+    assert (int(t[2]), int(t[4]), int(t[6])) == (int(inF.sum()), int(inFR.sum()), int((sl + 3 * sr).sum()))
+    assert t[8] == fnv(m2.tobytes()) and t[10] == fnv(mL.tobytes()) and t[12] == fnv(mR.tobytes())
+    valid = (np.arange(n) % 11 != 0).astype(np.uint8)
+    keep = cpu_ref.predict_mappoints(0, T, TR, *cam, valid, wp2, msd, ls, nlev, pl, sl, inF, pr_, sr, inFR)
+    t = lines[6].split()
+    assert int(t[2]) == int(keep.sum()) and int(t[4]) == int(keep.sum()) + int((valid == 0).sum()) and 0 < keep.sum() < n
