@@ -123,6 +123,63 @@ def fuzz_matchers(rng, fm, oL, k, kl, dl, kr, dr, s, w, h, nL, tag):
     return bad
 
 
+def fuzz_tracker_loops(rng, fm, feL, k, kl, kr, s, w, h, tag):
+    """Random poses and map points through findOutliersR / findOutliersMono and removeOutOfFrameMPs / PredictMPsPosition (SURVEY 8(f)
+    rank 3) against the oracle's sequential loops; returns #mismatches.  Runs last: findOutliersR edits the frame's stereo arrays."""
+    nl, nr = len(kl), len(kr)
+    if nl < 20 or nr < 20:
+        return 0
+    bad = 0
+    M = int(rng.integers(1, 1500))
+    fx = float(rng.uniform(150, 900)); cx, cy = w / 2.0 + float(rng.normal(0, 5)), h / 2.0 + float(rng.normal(0, 5))
+    ang = float(rng.normal(0, 0.05))
+    T = np.eye(4); T[:3, :3] = [[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]]; T[:3, 3] = rng.normal(0, 0.3, 3)
+    Tr = np.eye(4); Tr[0, 3] = -float(rng.uniform(0.05, 0.6))
+    TR = Tr @ T
+    first = rng.integers(0, nl, M)
+    z = np.where(s["estimatedDepth"][first] > 0, s["estimatedDepth"][first], rng.uniform(0.5, 50, M)).astype(np.float64)
+    pc = np.stack([(kl["x"][first] - cx) / fx * z, (kl["y"][first] - cy) / fx * z, z, np.ones(M)], 1)
+    pc[:, :3] += rng.normal(0, 1, (M, 3)) * np.where(rng.random(M) < 0.7, 0.002, 0.2)[:, None] * z[:, None]
+    pc[rng.random(M) < 0.03, 2] *= -1
+    wPos = (np.linalg.inv(T) @ pc.T).T.copy()
+    matches = np.stack([first, np.where(rng.random(M) < 0.6, s["rightIdxs"][first], rng.integers(-1, nr, M))], 1).astype(np.int32)
+    matches[rng.random(M) < 0.15, 0] = -1
+    valid = (rng.random(M) < 0.95).astype(np.uint8); inF = (rng.random(M) < 0.95).astype(np.uint8); inFR = (rng.random(M) < 0.9).astype(np.uint8)
+    cam = (fx, fx, cx, cy); thres = float(rng.choice([5.991, 7.815, 20.0])); closeDist = float(np.float32(-Tr[0, 3]) * np.float32(40))
+    for mode in (1, 0):      # mono first: it leaves the stereo arrays alone
+        a = [matches.copy(), np.full(M, 7, np.uint8)]; b = [matches.copy(), np.full(M, 7, np.uint8)]
+        cur = [k.estimatedDepth.copy(), k.close.astype(np.uint8), k.rightIdxs.copy(), k.leftIdxs.copy()]
+        if mode == 0:
+            n1 = fm.findOutliersR(0, T, TR, *cam, thres, closeDist, valid, wPos, inF, inFR, a[0], a[1], keys=k)
+        else:
+            n1 = (fm.findOutliersMono(0, T, *cam, thres, valid, wPos, inF, a[0], a[1]), 0)
+        n2 = cpu_ref.find_outliers(mode, T, TR, *cam, thres, closeDist, feL.InvSigmaFactor, valid, wPos, inF, inFR, b[0], b[1], kl, kr, *cur)
+        same = tuple(n1) == tuple(n2) and all(np.array_equal(x, y) for x, y in zip(a, b))
+        if mode == 0:
+            same = same and all(np.array_equal(x, y) for x, y in zip((k.estimatedDepth, k.close, k.rightIdxs, k.leftIdxs), cur))
+        if not same:
+            bad += 1
+            print("MISMATCH findOutliers mode", mode, tag, f"M {M} n {n1}/{n2}", flush=True)
+    msd = rng.uniform(2, 80, M).astype(np.float32); ls = np.full(M, np.float32(np.log(np.float32(1.2))), np.float32); nlev = np.full(M, 8, np.int32)
+    mL = np.full(nl, -1, np.int32); mR = np.full(nr, -1, np.int32)
+    mt = matches.copy()
+    mL[mt[mt[:, 0] >= 0, 0]] = 3; mR[mt[mt[:, 1] >= 0, 1]] = 3
+    outl = (rng.random(M) < 0.2).astype(np.uint8)
+    for mode in (0, 1, 2):
+        def run(fn):
+            st = [np.full((M, 2), -7, np.float32), np.full(M, -7, np.int32), np.full(M, 7, np.uint8), np.full((M, 2), -7, np.float32),
+                  np.full(M, -7, np.int32), np.full(M, 7, np.uint8), mt.copy(), mL.copy(), mR.copy(), outl.copy()]
+            two = mode != 1
+            keep = fn(mode, T, TR if two else None, *cam, w, h, valid, wPos, msd, ls, nlev, st[0], st[1], st[2], st[3] if two else None,
+                      st[4] if two else None, st[5] if two else None, *(st[6:] if mode == 2 else (None, None, None, None)))
+            return ([] if keep is None else [keep]) + st
+        ra, rb = run(fm.predictMapPoints), run(cpu_ref.predict_mappoints)
+        if not all(np.array_equal(x, y) for x, y in zip(ra, rb)):
+            bad += 1
+            print("MISMATCH predictMapPoints mode", mode, tag, f"M {M}", flush=True)
+    return bad
+
+
 def main():
     iters = int(sys.argv[1]) if len(sys.argv) > 1 else 100
     rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
@@ -186,6 +243,7 @@ def main():
                     diagnose(feL, oL, nL, "L"); diagnose(feR, oR, nL, "R")
             elif f == 0:
                 bad += fuzz_matchers(rng, fm, oL, k, kl, dl, kr, dr, s, w, h, nL, tag)
+                bad += fuzz_tracker_loops(rng, fm, feL, k, kl, kr, s, w, h, tag)
         if ok2 and it % 10 == 0:
             print("ok", tag, f"keys {len(kl)}/{len(kr)} matches {(s['rightIdxs'] >= 0).sum()}", flush=True)
     print(f"{iters} cases, {bad} bad, {time.time() - t0:.0f} s")
