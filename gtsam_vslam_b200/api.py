@@ -31,11 +31,12 @@ SYMBOLS = [
     "gvs_debug_level_image", "gvs_debug_level_candidates", "gvs_debug_level_kept", "gvs_debug_select",
     "gvs_matcher_create", "gvs_matcher_destroy", "gvs_stereo_match_batch", "gvs_stereo_download",
     "gvs_assign_grids_batch", "gvs_grid_download", "gvs_track_stereo_batch_host",
-    "gvs_track_stereo_batch_resident", "gvs_matcher_sync", "gvs_matcher_set_stream", "gvs_match_projection", "gvs_descriptor_distance",
+    "gvs_track_stereo_batch_resident", "gvs_matcher_sync", "gvs_matcher_set_stream", "gvs_match_projection", "gvs_match_projection_batch",
+    "gvs_track_temporal_batch", "gvs_temporal_download", "gvs_descriptor_distance",
     "gvs_match_projection_lba", "gvs_median_descriptor", "gvs_project_mappoints", "gvs_find_outliers", "gvs_predict_mappoints", "gvs_extractor_enable_timing", "gvs_extractor_stage_times", "gvs_matcher_launch_count",
     "gvs_extractor_launch_count",
     "gvs_pipeline_create", "gvs_pipeline_destroy", "gvs_pipeline_submit", "gvs_pipeline_wait", "gvs_pipeline_download",
-    "gvs_pipeline_handles", "gvs_pipeline_release",
+    "gvs_pipeline_handles", "gvs_pipeline_release", "gvs_pipeline_submit_temporal", "gvs_pipeline_download_temporal",
 ]
 
 
@@ -55,6 +56,12 @@ class _MapPoints(C.Structure):
                 ("in_frame_r", C.c_void_p)]
 
 
+class _TemporalParams(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("rad", C.c_float), ("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
+                ("width", C.c_int32), ("height", C.c_int32), ("prev", C.c_void_p), ("pose_prev", C.c_void_p), ("to_camera", C.c_void_p),
+                ("to_camera_r", C.c_void_p)]
+
+
 class _LbaFrame(C.Structure):
     _fields_ = [("n_left", C.c_int32), ("n_right", C.c_int32), ("kp_left", C.c_void_p), ("desc_left", C.c_void_p),
                 ("kp_right", C.c_void_p), ("desc_right", C.c_void_p), ("left_idxs", C.c_void_p), ("right_idxs", C.c_void_p),
@@ -68,7 +75,8 @@ class _LbaPoints(C.Structure):
 
 class StageTimes(C.Structure):
     _fields_ = [("pyramid_ms", C.c_float), ("fast_ms", C.c_float), ("select_ms", C.c_float), ("blur_ms", C.c_float),
-                ("describe_ms", C.c_float), ("stereo_ms", C.c_float), ("grid_ms", C.c_float), ("launches", C.c_int32)]
+                ("describe_ms", C.c_float), ("stereo_ms", C.c_float), ("grid_ms", C.c_float), ("temporal_ms", C.c_float),
+                ("launches", C.c_int32)]
 
 
 _lib = None
@@ -115,6 +123,9 @@ def load_library() -> C.CDLL:
     lib.gvs_matcher_sync.argtypes = [vp]
     lib.gvs_matcher_set_stream.argtypes = [vp, vp]
     lib.gvs_match_projection.argtypes = [vp, i32, i32, C.POINTER(_MapPoints), f32, vp, vp, vp, C.POINTER(i32)]
+    lib.gvs_match_projection_batch.argtypes = [vp, i32, i32, i32, C.POINTER(_MapPoints), vp, f32, vp, vp, vp, vp]
+    lib.gvs_track_temporal_batch.argtypes = [vp, i32, C.POINTER(_TemporalParams)]
+    lib.gvs_temporal_download.argtypes = [vp, i32, i32] + [vp] * 8
     lib.gvs_descriptor_distance.argtypes = [vp, vp, vp, i32, vp]
     lib.gvs_match_projection_lba.argtypes = [vp, C.POINTER(_LbaFrame), C.POINTER(_LbaPoints), f32, vp, C.POINTER(i32)]
     lib.gvs_median_descriptor.argtypes = [vp, vp, vp, i32, vp]
@@ -130,6 +141,8 @@ def load_library() -> C.CDLL:
     lib.gvs_pipeline_create.argtypes = [C.POINTER(vp), C.POINTER(_Params), i32, i32, i32, i32, C.c_double, f32, i32]
     lib.gvs_pipeline_destroy.argtypes = [vp]
     lib.gvs_pipeline_submit.argtypes = [vp, vp, vp, C.c_size_t, i32, i32, C.POINTER(i64)]
+    lib.gvs_pipeline_submit_temporal.argtypes = [vp, vp, vp, C.c_size_t, i32, i32, C.POINTER(_TemporalParams), C.POINTER(i64)]
+    lib.gvs_pipeline_download_temporal.argtypes = [vp, i64, vp, vp, vp, vp]
     lib.gvs_pipeline_wait.argtypes = [vp, i64, vp, vp]
     lib.gvs_pipeline_download.argtypes = [vp, i64, vp, vp, i32, vp, vp, i32, vp, vp, vp, vp]
     lib.gvs_pipeline_handles.argtypes = [vp, i64, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
@@ -433,6 +446,65 @@ class FeatureMatcher:
     def matchByRadius(self, mps, frame, matchedIdxsL, matchesIdxs, rad):
         return self._project(frame, GVS_MATCH_RADIUS, mps, rad, matchedIdxsL, None, matchesIdxs)
 
+    def match_projection_batch(self, mode, first_frame, n_frames, mps, mp_offsets, rad, matchedL, matchedR, matches):
+        """matchByProjectionRPred / Mono / matchByRadius for frames [first_frame, first_frame + n_frames) in one call: frame f is
+        matched against map points [mp_offsets[f], mp_offsets[f+1]) of `mps`; matchedL / matchedR are dense over the frames' keys,
+        matches is (M, 2); all three in-out.  Returns the per-frame match counts."""
+        M = len(mps["desc"])
+        keep = []
+
+        def arr(key, dt):
+            v = mps.get(key)
+            if v is None:
+                return None
+            x = np.ascontiguousarray(v, dt)
+            keep.append(x)
+            return x.ctypes.data
+
+        s = _MapPoints(M, arr("desc", np.uint8), arr("predL", np.float32), arr("predR", np.float32),
+                       arr("scaleLevelL", np.int32), arr("scaleLevelR", np.int32), arr("inFrame", np.uint8),
+                       arr("inFrameR", np.uint8))
+        off = np.ascontiguousarray(mp_offsets, np.int32)
+        assert len(off) == n_frames + 1
+        assert matchedL.dtype == np.int32 and matches.dtype == np.int32 and matches.shape == (M, 2) and matches.flags.c_contiguous
+        n = np.zeros(n_frames, np.int32)
+        _check(self._lib.gvs_match_projection_batch(self.h, first_frame, n_frames, mode, C.byref(s), _p(off), float(rad), _p(matchedL),
+                                                    _p(matchedR) if matchedR is not None else None, _p(matches), _p(n)))
+        return n
+
+    def track_temporal_batch(self, n_frames, prev, posePrev, toCamera, toCameraR, fx, fy, cx, cy, width, height, rad, mode=0) -> None:
+        """Device-resident temporal tracking of the last stereo batch (include/gvs.h: gvs_track_temporal_batch): map points of
+        frame f from the stereo keys of frame prev[f] (initializeMap), removeOutOfFrameMPs, matchByProjectionRPred.  Asynchronous."""
+        c = lambda x, dt: np.ascontiguousarray(x, dt)
+        k = [c(prev, np.int32), c(posePrev, np.float64), c(toCamera, np.float64), c(toCameraR, np.float64)]
+        assert len(k[0]) == n_frames and k[1].size == 16 * n_frames and k[2].size == 16 * n_frames and k[3].size == 16 * n_frames
+        self._tkeep = k
+        p = _TemporalParams(int(mode), float(rad), float(fx), float(fy), float(cx), float(cy), int(width), int(height),
+                            k[0].ctypes.data, k[1].ctypes.data, k[2].ctypes.data, k[3].ctypes.data)
+        _check(self._lib.gvs_track_temporal_batch(self.h, n_frames, C.byref(p)))
+
+    def temporal_download(self, first: int, count: int, preds: bool = False):
+        """Results of track_temporal_batch for frames [first, first + count)."""
+        off = np.zeros(count + 1, np.int32); n = np.zeros(count, np.int32)
+        _check(self._lib.gvs_temporal_download(self.h, first, count, _p(off), None, None, _p(n), None, None, None, None))
+        M = int(off[-1])
+        _, _, nl = self._dense(self.feLeft, first, count)
+        _, _, nr = self._dense(self.feRight, first, count)
+        key = np.zeros(max(M, 1), np.int32); mt = np.zeros((max(M, 1), 2), np.int32)
+        mL = np.zeros(max(nl, 1), np.int32); mR = np.zeros(max(nr, 1), np.int32)
+        pL = np.zeros((max(M, 1), 2), np.float32) if preds else None
+        pR = np.zeros((max(M, 1), 2), np.float32) if preds else None
+        _check(self._lib.gvs_temporal_download(self.h, first, count, None, _p(key), _p(mt), None, _p(mL), _p(mR), _p(pL), _p(pR)))
+        out = dict(mp_offsets=off, mp_key=key[:M], matches=mt[:M], n_matches=n, matchedL=mL[:nl], matchedR=mR[:nr])
+        if preds:
+            out["predL"], out["predR"] = pL[:M], pR[:M]
+        return out
+
+    def temporal_download_into(self, first: int, count: int, off, key, mt, n) -> int:
+        """Throughput form: offsets / source keys / matches / counts into caller (pinned) arrays; returns the map point count."""
+        _check(self._lib.gvs_temporal_download(self.h, first, count, _p(off), _p(key), _p(mt), _p(n), None, None, None, None))
+        return int(off[count])
+
     # -- matchByProjectionRPredLBA (src/FeatureMatcher.cpp:66-252); flattened inputs, see include/gvs.h
     def matchByProjectionRPredLBA(self, pts: dict, kl, dl, kr, dr, leftIdxs, rightIdxs, unMatchedF, unMatchedFR, width, height, rad):
         c = lambda a, dt: np.ascontiguousarray(a, dt)
@@ -554,6 +626,22 @@ class StereoPipeline:
         t = C.c_int64(-1)
         _check(self._lib.gvs_pipeline_submit(self.h, _p(left), _p(right), w * h, w, n, C.byref(t)))
         return t.value
+
+    def submit_temporal(self, left: np.ndarray, right: np.ndarray, motion: dict, rad: float) -> int:
+        """submit() followed by the temporal tracking of the ticket's frames; motion = synth.sequence_motion-like dict with prev,
+        pose_prev, to_camera, to_camera_r (per frame of the ticket) and fx, fy, cx, cy."""
+        n, h, w = left.shape
+        c = lambda x, dt: np.ascontiguousarray(x, dt)
+        k = [c(motion["prev"], np.int32), c(motion["pose_prev"], np.float64), c(motion["to_camera"], np.float64), c(motion["to_camera_r"], np.float64)]
+        assert len(k[0]) == n
+        p = _TemporalParams(0, float(rad), float(motion["fx"]), float(motion["fy"]), float(motion["cx"]), float(motion["cy"]), w, h,
+                            k[0].ctypes.data, k[1].ctypes.data, k[2].ctypes.data, k[3].ctypes.data)
+        t = C.c_int64(-1)
+        _check(self._lib.gvs_pipeline_submit_temporal(self.h, _p(left), _p(right), w * h, w, n, C.byref(p), C.byref(t)))
+        return t.value
+
+    def download_temporal_into(self, ticket: int, off, key, mt, n) -> None:
+        _check(self._lib.gvs_pipeline_download_temporal(self.h, ticket, _p(off), _p(key), _p(mt), _p(n)))
 
     def wait(self, ticket: int, n_frames: int):
         offL = np.zeros(n_frames + 1, np.int32); offR = np.zeros(n_frames + 1, np.int32)

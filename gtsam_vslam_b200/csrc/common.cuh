@@ -190,7 +190,6 @@ struct ProjArgs {
     int* nMatches;
     int* status;
 };
-void launchProject(const ProjArgs& a, cudaStream_t s, int* launches);
 void launchProjectLBA(const ProjArgs& a, const float* lastL, const float* lastR, int* out, cudaStream_t s, int* launches);
 void launchMedianDescriptor(const uint8_t* descs, const int* offsets, int P, int* bestIdx, cudaStream_t s, int* launches);
 void launchWorldToFrame(int M, const double* poseInv, double fx, double fy, double cx, double cy, int width, int height,

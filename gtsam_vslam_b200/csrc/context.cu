@@ -9,6 +9,7 @@
 #include <mutex>
 
 #include "common.cuh"
+#include "handles.cuh"
 
 namespace gvs {
 
@@ -20,135 +21,11 @@ int fail(int code, const char* what, const char* detail) {
     return code;
 }
 
-// Entry points run on the handle's device and leave the caller's current device as they found it (a caller such as PyTorch
-// resolves "cuda" to the current device).
-struct DeviceGuard {
-    int prev = -1;
-    explicit DeviceGuard(int device) {
-        int cur = -1;
-        if (cudaGetDevice(&cur) == cudaSuccess && cur != device) prev = cur;
-        cudaSetDevice(device);
-    }
-    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
-    DeviceGuard(const DeviceGuard&) = delete;
-    DeviceGuard& operator=(const DeviceGuard&) = delete;
-};
-
 static inline int cvRoundF(float v) { return (int)lrintf(v); }
-
-template <typename T>
-static cudaError_t devAlloc(T** p, size_t count) {
-    *p = nullptr;
-    const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
-    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), bytes);
-    // debugging aid (compute-sanitizer's initcheck by other means): GVS_POISON=1 fills every fresh allocation with 0xA5 so that
-    // a kernel relying on cudaMalloc returning zeros shows up as a parity failure in the tests / tools/fuzz_parity.py
-    static const bool poison = getenv("GVS_POISON") != nullptr;
-    if (e == cudaSuccess && poison) { e = cudaMemset(*p, 0xA5, bytes); cudaDeviceSynchronize(); }  // (handles use non-blocking streams)
-    return e;
-}
 
 }  // namespace gvs
 
 using namespace gvs;
-
-struct gvs_extractor {
-    int device = 0;
-    gvs_extractor_params params{};
-    int width = 0, height = 0, maxImages = 0;
-    Geometry g{};
-    std::vector<float> scale, invScale, sigma, invSigma;
-    std::vector<int> patch, quota;
-    cudaStream_t ownStream = nullptr, stream = nullptr;
-    cudaStream_t auxStream = nullptr;  // blur runs here, concurrently with FAST + selection
-    cudaEvent_t doneEvent = nullptr, evPyr = nullptr, evBlur = nullptr;
-    // device
-    uint8_t* slab = nullptr;
-    uint8_t* blurSlab = nullptr;
-    uint8_t* tight = nullptr;   // staging for tightly packed host batches (one contiguous DMA, then repack)
-    size_t tightBytes = 0;
-    float* mapX = nullptr;      // rectification maps of cv::remap (optional, gvs_extractor_set_rectify_maps)
-    float* mapY = nullptr;
-    ResizeTap* taps = nullptr;
-    uint4* xWeights = nullptr;        // per group of 4 destination columns: a0 | a1 << 16 of each column
-    uint4* xSelectors = nullptr;      // ... PRMT selector (| 1 << 16 when the pair sits in the upper 8 bytes of the window)
-    unsigned short* xBase = nullptr;  // ... source offset of the window: sx of the first column (narrow levels) or the 4-byte aligned
-                                      //     start of the 12-byte window (other levels)
-    unsigned pyrNarrowMask = 0;       // bit l: every column group of level l spans at most 8 source bytes (pyr_down_kernel<true>)
-    FastItem* fastItems = nullptr;
-    int nFastItems = 0;
-    // CUDA graphs of the extraction pipeline for small batches (latency mode): one instantiated graph per batch size
-    std::map<int, cudaGraphExec_t> graphs;
-    std::map<int, int> graphLaunches;
-    BlurItem* blurItems = nullptr;
-    int nBlurItems = 0;
-    CandRec* recs = nullptr;
-    int* nCand = nullptr;
-    unsigned short* cellCnt = nullptr;
-    KeptKey* kept = nullptr;
-    int* keptCnt = nullptr;
-    int* imgOff = nullptr;
-    unsigned* orderedDbg = nullptr;
-    unsigned* sortedDbg = nullptr;
-    int* momentsDbg = nullptr;
-    uint8_t* selScratch = nullptr;
-    size_t selScratchPerCta = 0;
-    int selCtas = 0;
-    int* workCounter = nullptr;
-    int* status = nullptr;
-    gvs_keypoint* kps = nullptr;
-    uint8_t* desc = nullptr;
-    uint2* auxKey = nullptr;   // per key: stereo bucket row range + pt.y (compact copy for the matcher's scan)
-    int totalCap = 0;
-    // host (pinned)
-    int* hOff = nullptr;
-    int* hStatus = nullptr;
-    int lastN = 0;
-    bool pending = false;
-    bool blurValid = false;   // the blurred slab is only materialised on demand (parity tap)
-    int launches = 0;
-    int64_t launchesTotal = 0;
-    bool timing = false;
-    cudaEvent_t ev[8] = {};
-    gvs_stage_times times{};
-};
-
-struct gvs_matcher {
-    gvs_extractor* L = nullptr;
-    gvs_extractor* R = nullptr;
-    double fx = 0;
-    float baseline = 0;
-    int imageHeight = 0;
-    int* rightIdxs = nullptr;
-    int* leftIdxs = nullptr;
-    int* sadBest = nullptr;
-    void* sortScratch = nullptr;
-    float* depth = nullptr;
-    uint8_t* close = nullptr;
-    // grids
-    int* cellStartL = nullptr;
-    int* cellStartR = nullptr;
-    int* itemsL = nullptr;
-    int* itemsR = nullptr;
-    int maxCells = GVS_GRID_X * GVS_GRID_X;   // set at creation from the image shape
-    static constexpr int kMaxGridRows = 512;   // 64 x 512 cells: the counting sort of grid_assign_kernel keeps them in shared memory
-    int xGrids = 0, yGrids = 0;
-    float xMult = 0, yMult = 0;
-    bool gridsValid = false, stereoValid = false;
-    int lastFrames = 0;
-    cudaEvent_t evR = nullptr, evFork = nullptr, evJoin = nullptr, evHold = nullptr;
-    cudaStream_t callerStream = nullptr;  // optional: work is forked from / joined into this stream
-    // projection scratch (grown on demand)
-    uint8_t* pj = nullptr;
-    size_t pjBytes = 0;
-    unsigned* pool = nullptr;
-    int poolCap = 0;
-    int* pjStatus = nullptr;
-    int launches = 0;
-    int64_t launchesTotal = 0;
-    cudaEvent_t ev[4] = {};
-    float stereoMs = 0, gridMs = 0;
-};
 
 namespace {
 
@@ -380,11 +257,15 @@ int runExtract(gvs_extractor* fe, int n) {
     GVS_CUDA_OK(cudaEventRecord(fe->doneEvent, s));
     GVS_CUDA_OK(cudaGetLastError());
     fe->lastN = n;
+    ++fe->generation;
     fe->pending = true;
     fe->launchesTotal += fe->launches;
     return GVS_OK;
 }
 
+}  // namespace
+
+namespace gvs {
 int syncExtract(gvs_extractor* fe) {
     DeviceGuard deviceGuard(fe->device);
     GVS_CUDA_OK(cudaStreamSynchronize(fe->stream));
@@ -403,6 +284,9 @@ int syncExtract(gvs_extractor* fe) {
     if (st & kStatOutputOverflow) return fail(GVS_ERR_CAPACITY, "dense output overflow");
     return GVS_OK;
 }
+}  // namespace gvs
+
+namespace {
 
 int checkBatch(gvs_extractor* fe, int n) {
     if (!fe) return fail(GVS_ERR_INVALID, "null extractor");
@@ -412,10 +296,44 @@ int checkBatch(gvs_extractor* fe, int n) {
 
 }  // namespace
 
+namespace gvs {
+int joinRight(gvs_matcher* m) {  // make L's stream wait for R's last batch
+    if (m->R != m->L && m->R->stream != m->L->stream) {
+        GVS_CUDA_OK(cudaEventRecord(m->evR, m->R->stream));
+        GVS_CUDA_OK(cudaStreamWaitEvent(m->L->stream, m->evR, 0));
+    }
+    return GVS_OK;
+}
+
+// The matcher's kernels run on L's stream and read R's keys, descriptors and pyramid: whatever is queued on R's stream afterwards
+// (the next batch's upload and extraction) must wait for them.
+int holdRight(gvs_matcher* m) {
+    if (m->R != m->L && m->R->stream != m->L->stream) {
+        // (not while the caller captures L's stream into a graph: a fork that is never joined would invalidate the capture, and the
+        // caller's graph already orders whole batches)
+        cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(m->L->stream, &capturing) != cudaSuccess) { cudaGetLastError(); capturing = cudaStreamCaptureStatusNone; }
+        if (capturing != cudaStreamCaptureStatusNone) return GVS_OK;
+        GVS_CUDA_OK(cudaEventRecord(m->evHold, m->L->stream));
+        GVS_CUDA_OK(cudaStreamWaitEvent(m->R->stream, m->evHold, 0));
+    }
+    return GVS_OK;
+}
+
+int growScratch(gvs_matcher* m, size_t bytes) {
+    if (bytes <= m->pjBytes) return GVS_OK;
+    GVS_CUDA_OK(cudaStreamSynchronize(m->L->stream));
+    cudaFree(m->pj); m->pj = nullptr; m->pjBytes = 0;
+    GVS_CUDA_OK(devAlloc(&m->pj, bytes));
+    m->pjBytes = bytes;
+    return GVS_OK;
+}
+}  // namespace gvs
+
 extern "C" {
 
 const char* gvs_last_error(void) { return g_lastError.c_str(); }
-int gvs_version(void) { return 100; }
+int gvs_version(void) { return 200; }
 void gvs_default_params(gvs_extractor_params* p) {
     if (!p) return;
     p->n_features = 2000; p->n_levels = 8; p->im_scale = 1.2f; p->edge_threshold = 19; p->patch_size = 31;
@@ -840,6 +758,7 @@ int gvs_debug_select(gvs_extractor* fe, int level, int n, const int32_t* x, cons
     GVS_CUDA_OK(cudaStreamSynchronize(s));
     GVS_CUDA_OK(cudaGetLastError());
     fe->lastN = 0;  // the batch state of the handle is gone
+    ++fe->generation;
     if (st) return fail(GVS_ERR_CAPACITY, "selection overflow");
     *n_kept = cnt;
     if (cnt > cap) return fail(GVS_ERR_CAPACITY, "caller buffer too small");
@@ -886,6 +805,7 @@ int gvs_matcher_create(gvs_matcher** out, gvs_extractor* feL, gvs_extractor* feR
               cudaEventCreateWithFlags(&m->evJoin, cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&m->evHold, cudaEventDisableTiming) == cudaSuccess;
     for (auto& e : m->ev) ok = ok && cudaEventCreate(&e) == cudaSuccess;
+    for (auto& e : m->evT) ok = ok && cudaEventCreate(&e) == cudaSuccess;
     if (!ok) {
         int rc = fail(GVS_ERR_CUDA, "matcher allocation", cudaGetErrorString(cudaGetLastError()));
         gvs_matcher_destroy(m);
@@ -907,30 +827,15 @@ int gvs_matcher_destroy(gvs_matcher* m) {
     if (m->evJoin) cudaEventDestroy(m->evJoin);
     if (m->evHold) cudaEventDestroy(m->evHold);
     for (auto& e : m->ev) if (e) cudaEventDestroy(e);
+    for (auto& e : m->evT) if (e) cudaEventDestroy(e);
+    cudaFree(m->tFlag); cudaFree(m->tPredL); cudaFree(m->tPredR); cudaFree(m->tLvlL); cudaFree(m->tLvlR); cudaFree(m->tDescRow);
+    cudaFree(m->tWPos); cudaFree(m->tMaxScaleDist); cudaFree(m->tMpCnt); cudaFree(m->tMpOff); cudaFree(m->tMpSlot); cudaFree(m->tMpKey);
+    cudaFree(m->tMatchedL); cudaFree(m->tMatchedR); cudaFree(m->tMatches); cudaFree(m->tNMatches); cudaFree(m->tRecs);
+    cudaFree(m->tPoses); cudaFree(m->tPrev); cudaFree(m->tStatus);
+    if (m->hMpOff) cudaFreeHost(m->hMpOff);
+    if (m->hNMatches) cudaFreeHost(m->hNMatches);
+    if (m->hTStatus) cudaFreeHost(m->hTStatus);
     delete m;
-    return GVS_OK;
-}
-
-static int joinRight(gvs_matcher* m) {  // make L's stream wait for R's last batch
-    if (m->R != m->L && m->R->stream != m->L->stream) {
-        GVS_CUDA_OK(cudaEventRecord(m->evR, m->R->stream));
-        GVS_CUDA_OK(cudaStreamWaitEvent(m->L->stream, m->evR, 0));
-    }
-    return GVS_OK;
-}
-
-// The matcher's kernels run on L's stream and read R's keys, descriptors and pyramid: whatever is queued on R's stream afterwards
-// (the next batch's upload and extraction) must wait for them.
-static int holdRight(gvs_matcher* m) {
-    if (m->R != m->L && m->R->stream != m->L->stream) {
-        // (not while the caller captures L's stream into a graph: a fork that is never joined would invalidate the capture, and the
-        // caller's graph already orders whole batches)
-        cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
-        if (cudaStreamIsCapturing(m->L->stream, &capturing) != cudaSuccess) { cudaGetLastError(); capturing = cudaStreamCaptureStatusNone; }
-        if (capturing != cudaStreamCaptureStatusNone) return GVS_OK;
-        GVS_CUDA_OK(cudaEventRecord(m->evHold, m->L->stream));
-        GVS_CUDA_OK(cudaStreamWaitEvent(m->R->stream, m->evHold, 0));
-    }
     return GVS_OK;
 }
 
@@ -986,6 +891,7 @@ int gvs_stereo_match_batch(gvs_matcher* m, int n_frames) {
     m->launchesTotal += m->launches;
     m->stereoValid = true;
     m->lastFrames = n_frames;
+    m->stereoGenL = m->L->generation; m->stereoGenR = m->R->generation;
     return holdRight(m);
 }
 
@@ -998,15 +904,18 @@ int gvs_matcher_sync(gvs_matcher* m) {
     if (m->L->timing && m->stereoValid) {
         cudaEventElapsedTime(&m->stereoMs, m->ev[0], m->ev[1]);
         if (m->gridsValid) cudaEventElapsedTime(&m->gridMs, m->ev[2], m->ev[3]);
+        if (m->temporalFrames > 0 && m->temporalGen == m->L->generation) cudaEventElapsedTime(&m->temporalMs, m->evT[0], m->evT[1]);
         m->L->times.stereo_ms = m->stereoMs;
         m->L->times.grid_ms = m->gridMs;
+        m->L->times.temporal_ms = m->temporalMs;
     }
     return GVS_OK;
 }
 
 int gvs_stereo_download(gvs_matcher* m, int first, int count, int32_t* right_idxs, int32_t* left_idxs, float* depth, uint8_t* close) {
     if (!m) return fail(GVS_ERR_INVALID, "null matcher");
-    if (!m->stereoValid) return fail(GVS_ERR_STATE, "no stereo batch has been matched");
+    if (!m->stereoValid || m->stereoGenL != m->L->generation || m->stereoGenR != m->R->generation)
+        return fail(GVS_ERR_STATE, "no stereo batch has been matched for the current frames");
     if (first < 0 || count < 0 || first + count > m->lastFrames) return fail(GVS_ERR_INVALID, "frame range out of the last batch");
     int rc = gvs_matcher_sync(m);
     if (rc) return rc;
@@ -1053,13 +962,16 @@ int gvs_assign_grids_batch(gvs_matcher* m, int n_frames, int width, int height) 
     m->launchesTotal += launches;
     m->launches += launches;
     m->gridsValid = true;
+    m->gridFrames = n_frames;
+    m->gridGenL = m->L->generation; m->gridGenR = m->R->generation;
     if (m->lastFrames < n_frames) m->lastFrames = n_frames;
     return holdRight(m);
 }
 
 int gvs_grid_download(gvs_matcher* m, int frame, int side, int32_t* cell_start, int32_t* items, int* y_grids, float* x_mult, float* y_mult) {
     if (!m) return fail(GVS_ERR_INVALID, "null matcher");
-    if (!m->gridsValid) return fail(GVS_ERR_STATE, "grids have not been assigned");
+    if (!m->gridsValid || m->gridGenL != m->L->generation || (m->R != m->L && m->gridGenR != m->R->generation))
+        return fail(GVS_ERR_STATE, "grids have not been assigned for the current frames");
     gvs_extractor* fe = side ? m->R : m->L;
     if (frame < 0 || frame >= fe->lastN) return fail(GVS_ERR_INVALID, "bad frame");
     int rc = gvs_matcher_sync(m);
@@ -1112,105 +1024,6 @@ int gvs_track_stereo_batch_host(gvs_matcher* m, const uint8_t* left, const uint8
 int gvs_matcher_launch_count(gvs_matcher* m, int64_t* launches) {
     if (!m || !launches) return fail(GVS_ERR_INVALID, "null argument");
     *launches = m->launchesTotal;
-    return GVS_OK;
-}
-
-int gvs_match_projection(gvs_matcher* m, int frame, int mode, const gvs_mappoints* mps, float rad, int32_t* matched_l,
-                         int32_t* matched_r, int32_t* matches, int* n_matches) {
-    if (!m || !mps || !matched_l || !matches || !n_matches) return fail(GVS_ERR_INVALID, "null argument");
-    if (mode < 0 || mode > 2) return fail(GVS_ERR_INVALID, "bad mode");
-    if (!m->gridsValid) return fail(GVS_ERR_STATE, "call gvs_assign_grids_batch first");
-    if (mode == GVS_MATCH_STEREO_PRED && (!m->stereoValid || !matched_r || !mps->pred_r || !mps->scale_level_r))
-        return fail(GVS_ERR_STATE, "stereo-pred matching needs a stereo batch, matched_r, pred_r and scale_level_r");
-    if (frame < 0 || frame >= m->lastFrames) return fail(GVS_ERR_INVALID, "bad frame");
-    if (!mps->desc || !mps->pred_l || !mps->scale_level_l) return fail(GVS_ERR_INVALID, "map point arrays missing");
-    int rc = gvs_matcher_sync(m);
-    if (rc) return rc;
-    DeviceGuard deviceGuard(m->L->device);
-    cudaStream_t s = m->L->stream;
-    const int M = mps->count;
-    *n_matches = 0;
-    if (M <= 0) return GVS_OK;
-    const int oL = m->L->hOff[frame], NL = m->L->hOff[frame + 1] - oL;
-    const bool two = mode == GVS_MATCH_STEREO_PRED;
-    const int oR = two ? m->R->hOff[frame] : 0, NR = two ? m->R->hOff[frame + 1] - oR : 0;
-    for (int i = 0; i < M; i++) {
-        const int l = mps->scale_level_l[i];
-        if (l < 0 || l >= m->L->g.nLevels || (two && (mps->scale_level_r[i] < 0 || mps->scale_level_r[i] >= m->L->g.nLevels)))
-            return fail(GVS_ERR_INVALID, "map point scale level out of range");
-    }
-    // scratch layout
-    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
-    size_t o = 0;
-    const size_t oDesc = o; o += al((size_t)M * 32);
-    const size_t oPL = o; o += al((size_t)M * 8);
-    const size_t oPR = o; o += al((size_t)M * 8);
-    const size_t oLL = o; o += al((size_t)M * 4);
-    const size_t oLR = o; o += al((size_t)M * 4);
-    const size_t oIF = o; o += al((size_t)M);
-    const size_t oIR = o; o += al((size_t)M);
-    const size_t oML = o; o += al((size_t)std::max(NL, 1) * 4);
-    const size_t oMR = o; o += al((size_t)std::max(NR, 1) * 4);
-    const size_t oMt = o; o += al((size_t)M * 8);
-    const size_t oRec = o; o += al((size_t)M * 2 * 20);
-    const size_t oCnt = o; o += al(16);
-    if (o > m->pjBytes) {
-        cudaFree(m->pj); m->pj = nullptr; m->pjBytes = 0;
-        GVS_CUDA_OK(devAlloc(&m->pj, o));
-        m->pjBytes = o;
-    }
-    // candidate pools: every map point can list every key of its side at most once
-    const long long need = std::min<long long>((long long)M * std::max(NL, NR), (long long)1 << 28);
-    if (need > m->poolCap) {
-        cudaFree(m->pool); m->pool = nullptr; m->poolCap = 0;
-        GVS_CUDA_OK(devAlloc(&m->pool, (size_t)need * 2));
-        m->poolCap = (int)need;
-    }
-    uint8_t* b = m->pj;
-    auto up = [&](size_t off, const void* src, size_t bytes) -> cudaError_t {
-        return src ? cudaMemcpyAsync(b + off, src, bytes, cudaMemcpyHostToDevice, s) : cudaSuccess;
-    };
-    GVS_CUDA_OK(up(oDesc, mps->desc, (size_t)M * 32));
-    GVS_CUDA_OK(up(oPL, mps->pred_l, (size_t)M * 8));
-    GVS_CUDA_OK(up(oLL, mps->scale_level_l, (size_t)M * 4));
-    GVS_CUDA_OK(up(oIF, mps->in_frame, (size_t)M));
-    if (two) {
-        GVS_CUDA_OK(up(oPR, mps->pred_r, (size_t)M * 8));
-        GVS_CUDA_OK(up(oLR, mps->scale_level_r, (size_t)M * 4));
-        GVS_CUDA_OK(up(oIR, mps->in_frame_r, (size_t)M));
-        GVS_CUDA_OK(up(oMR, matched_r, (size_t)NR * 4));
-    }
-    GVS_CUDA_OK(up(oML, matched_l, (size_t)NL * 4));
-    GVS_CUDA_OK(up(oMt, matches, (size_t)M * 8));
-    GVS_CUDA_OK(cudaMemsetAsync(m->pjStatus, 0, 2 * sizeof(int), s));
-    ProjArgs a{};
-    a.mode = mode; a.M = M;
-    a.mpDesc = b + oDesc; a.predL = reinterpret_cast<float*>(b + oPL); a.predR = reinterpret_cast<float*>(b + oPR);
-    a.lvlL = reinterpret_cast<int*>(b + oLL); a.lvlR = reinterpret_cast<int*>(b + oLR);
-    a.inFrame = mps->in_frame ? b + oIF : nullptr; a.inFrameR = mps->in_frame_r ? b + oIR : nullptr;
-    a.kpL = m->L->kps + oL; a.descL = m->L->desc + (size_t)oL * 32; a.NL = NL;
-    a.kpR = two ? m->R->kps + oR : nullptr; a.descR = two ? m->R->desc + (size_t)oR * 32 : nullptr; a.NR = NR;
-    a.cellStartL = m->cellStartL + (size_t)frame * (m->maxCells + 1); a.itemsL = m->itemsL + oL;
-    a.cellStartR = two ? m->cellStartR + (size_t)frame * (m->maxCells + 1) : nullptr; a.itemsR = two ? m->itemsR + oR : nullptr;
-    a.leftIdxs = two ? m->leftIdxs + oR : nullptr; a.rightIdxs = two ? m->rightIdxs + oL : nullptr;
-    a.xGrids = m->xGrids; a.yGrids = m->yGrids; a.xMult = m->xMult; a.yMult = m->yMult; a.rad = rad;
-    for (int i = 0; i < kMaxLevels; i++) a.scalePyramid[i] = i < m->L->g.nLevels ? m->L->scale[i] : 1.f;
-    a.recs = b + oRec; a.poolTop = reinterpret_cast<int*>(b + oCnt);
-    a.candL = m->pool; a.candR = m->pool + m->poolCap; a.candCap = m->poolCap;
-    a.matchedL = reinterpret_cast<int*>(b + oML); a.matchedR = reinterpret_cast<int*>(b + oMR);
-    a.matches = reinterpret_cast<int*>(b + oMt); a.nMatches = m->pjStatus + 1; a.status = m->pjStatus;
-    int launches = 0;
-    launchProject(a, s, &launches);
-    m->launchesTotal += launches;
-    int st[2] = {0, 0};
-    GVS_CUDA_OK(cudaMemcpyAsync(matched_l, b + oML, (size_t)NL * 4, cudaMemcpyDeviceToHost, s));
-    if (two) GVS_CUDA_OK(cudaMemcpyAsync(matched_r, b + oMR, (size_t)NR * 4, cudaMemcpyDeviceToHost, s));
-    GVS_CUDA_OK(cudaMemcpyAsync(matches, b + oMt, (size_t)M * 8, cudaMemcpyDeviceToHost, s));
-    GVS_CUDA_OK(cudaMemcpyAsync(st, m->pjStatus, sizeof(st), cudaMemcpyDeviceToHost, s));
-    GVS_CUDA_OK(cudaStreamSynchronize(s));
-    GVS_CUDA_OK(cudaGetLastError());
-    if (st[0] & kStatProjOverflow) return fail(GVS_ERR_CAPACITY, "projection candidate pool overflow");
-    *n_matches = st[1];
     return GVS_OK;
 }
 
@@ -1453,7 +1266,8 @@ int gvs_find_outliers(gvs_matcher* m, int frame, int mode, const double* pose, c
                       int* n_inliers, int* n_stereo) {
     if (!m || !pose || !n_inliers || !n_stereo || count < 0) return fail(GVS_ERR_INVALID, "bad argument");
     if (mode != 0 && mode != 1) return fail(GVS_ERR_INVALID, "bad mode");
-    if (mode == 0 && (!pose_r || !m->stereoValid)) return fail(GVS_ERR_STATE, "findOutliersR needs toCameraR and a stereo batch");
+    if (mode == 0 && (!pose_r || !m->stereoValid || m->stereoGenL != m->L->generation || m->stereoGenR != m->R->generation))
+        return fail(GVS_ERR_STATE, "findOutliersR needs toCameraR and a stereo batch of the current frames");
     if (frame < 0 || frame >= m->L->lastN || (mode == 0 && frame >= m->lastFrames)) return fail(GVS_ERR_INVALID, "bad frame");
     *n_inliers = 0; *n_stereo = 0;
     int rc = gvs_matcher_sync(m);

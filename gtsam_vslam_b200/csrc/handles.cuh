@@ -1,0 +1,167 @@
+// Handle structures behind the opaque types of include/gvs.h, shared by the host-side translation units (context.cu: extractor
+// and per-frame matcher entry points; temporal.cu: batched temporal matching; multi.cu: multi-device front end).  Internal.
+#pragma once
+#include <algorithm>
+#include <cstdlib>
+#include <map>
+
+#include "common.cuh"
+
+namespace gvs {
+
+// Entry points run on the handle's device and leave the caller's current device as they found it (a caller such as PyTorch
+// resolves "cuda" to the current device).
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int device) {
+        int cur = -1;
+        if (cudaGetDevice(&cur) == cudaSuccess && cur != device) prev = cur;
+        cudaSetDevice(device);
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
+template <typename T>
+static cudaError_t devAlloc(T** p, size_t count) {
+    *p = nullptr;
+    const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), bytes);
+    // debugging aid (compute-sanitizer's initcheck by other means): GVS_POISON=1 fills every fresh allocation with 0xA5 so that
+    // a kernel relying on cudaMalloc returning zeros shows up as a parity failure in the tests / tools/fuzz_parity.py
+    static const bool poison = getenv("GVS_POISON") != nullptr;
+    if (e == cudaSuccess && poison) { e = cudaMemset(*p, 0xA5, bytes); cudaDeviceSynchronize(); }  // (handles use non-blocking streams)
+    return e;
+}
+
+}  // namespace gvs
+
+using namespace gvs;  // (internal header: the handle structs are global, their members are gvs:: types)
+
+struct gvs_extractor {
+    int device = 0;
+    gvs_extractor_params params{};
+    int width = 0, height = 0, maxImages = 0;
+    Geometry g{};
+    std::vector<float> scale, invScale, sigma, invSigma;
+    std::vector<int> patch, quota;
+    cudaStream_t ownStream = nullptr, stream = nullptr;
+    cudaStream_t auxStream = nullptr;  // blur runs here, concurrently with FAST + selection
+    cudaEvent_t doneEvent = nullptr, evPyr = nullptr, evBlur = nullptr;
+    // device
+    uint8_t* slab = nullptr;
+    uint8_t* blurSlab = nullptr;
+    uint8_t* tight = nullptr;   // staging for tightly packed host batches (one contiguous DMA, then repack)
+    size_t tightBytes = 0;
+    float* mapX = nullptr;      // rectification maps of cv::remap (optional, gvs_extractor_set_rectify_maps)
+    float* mapY = nullptr;
+    ResizeTap* taps = nullptr;
+    uint4* xWeights = nullptr;        // per group of 4 destination columns: a0 | a1 << 16 of each column
+    uint4* xSelectors = nullptr;      // ... PRMT selector (| 1 << 16 when the pair sits in the upper 8 bytes of the window)
+    unsigned short* xBase = nullptr;  // ... source offset of the window: sx of the first column (narrow levels) or the 4-byte aligned
+                                      //     start of the 12-byte window (other levels)
+    unsigned pyrNarrowMask = 0;       // bit l: every column group of level l spans at most 8 source bytes (pyr_down_kernel<true>)
+    FastItem* fastItems = nullptr;
+    int nFastItems = 0;
+    // CUDA graphs of the extraction pipeline for small batches (latency mode): one instantiated graph per batch size
+    std::map<int, cudaGraphExec_t> graphs;
+    std::map<int, int> graphLaunches;
+    BlurItem* blurItems = nullptr;
+    int nBlurItems = 0;
+    CandRec* recs = nullptr;
+    int* nCand = nullptr;
+    unsigned short* cellCnt = nullptr;
+    KeptKey* kept = nullptr;
+    int* keptCnt = nullptr;
+    int* imgOff = nullptr;
+    unsigned* orderedDbg = nullptr;
+    unsigned* sortedDbg = nullptr;
+    int* momentsDbg = nullptr;
+    uint8_t* selScratch = nullptr;
+    size_t selScratchPerCta = 0;
+    int selCtas = 0;
+    int* workCounter = nullptr;
+    int* status = nullptr;
+    gvs_keypoint* kps = nullptr;
+    uint8_t* desc = nullptr;
+    uint2* auxKey = nullptr;   // per key: stereo bucket row range + pt.y (compact copy for the matcher's scan)
+    int totalCap = 0;
+    // host (pinned)
+    int* hOff = nullptr;
+    int* hStatus = nullptr;
+    int lastN = 0;
+    uint64_t generation = 0;  // bumped by every batch that replaces the resident results (runExtract, gvs_debug_select)
+    bool pending = false;
+    bool blurValid = false;   // the blurred slab is only materialised on demand (parity tap)
+    int launches = 0;
+    int64_t launchesTotal = 0;
+    bool timing = false;
+    cudaEvent_t ev[8] = {};
+    gvs_stage_times times{};
+};
+
+struct gvs_matcher {
+    gvs_extractor* L = nullptr;
+    gvs_extractor* R = nullptr;
+    double fx = 0;
+    float baseline = 0;
+    int imageHeight = 0;
+    int* rightIdxs = nullptr;
+    int* leftIdxs = nullptr;
+    int* sadBest = nullptr;
+    void* sortScratch = nullptr;
+    float* depth = nullptr;
+    uint8_t* close = nullptr;
+    // grids
+    int* cellStartL = nullptr;
+    int* cellStartR = nullptr;
+    int* itemsL = nullptr;
+    int* itemsR = nullptr;
+    int maxCells = GVS_GRID_X * GVS_GRID_X;   // set at creation from the image shape
+    static constexpr int kMaxGridRows = 512;   // 64 x 512 cells: the counting sort of grid_assign_kernel keeps them in shared memory
+    int xGrids = 0, yGrids = 0;
+    float xMult = 0, yMult = 0;
+    bool gridsValid = false, stereoValid = false;
+    int lastFrames = 0, gridFrames = 0;
+    // the extractors' batch generations the stereo arrays / key grids were computed from: a call that combines them with the
+    // resident keys checks that nothing was re-extracted in between (GVS_ERR_STATE otherwise)
+    uint64_t stereoGenL = 0, stereoGenR = 0, gridGenL = 0, gridGenR = 0;
+    // batched temporal tracking (temporal.cu), allocated on first use
+    uint8_t* tFlag = nullptr;
+    float* tPredL = nullptr; float* tPredR = nullptr;
+    int* tLvlL = nullptr; int* tLvlR = nullptr; int* tDescRow = nullptr;
+    double* tWPos = nullptr; float* tMaxScaleDist = nullptr;
+    int* tMpCnt = nullptr; int* tMpOff = nullptr; int* tMpSlot = nullptr; int* tMpKey = nullptr;
+    int* tMatchedL = nullptr; int* tMatchedR = nullptr; int* tMatches = nullptr; int* tNMatches = nullptr;
+    uint8_t* tRecs = nullptr;
+    double* tPoses = nullptr; int* tPrev = nullptr; int* tStatus = nullptr;
+    std::vector<uint8_t> tStage;   // pageable staging of the per-frame poses / predecessor list
+    int* hMpOff = nullptr; int* hNMatches = nullptr; int* hTStatus = nullptr;   // pinned
+    int temporalFrames = 0;
+    uint64_t temporalGen = 0;
+    cudaEvent_t evT[2] = {};
+    float temporalMs = 0;
+    cudaEvent_t evR = nullptr, evFork = nullptr, evJoin = nullptr, evHold = nullptr;
+    cudaStream_t callerStream = nullptr;  // optional: work is forked from / joined into this stream
+    // projection scratch (grown on demand)
+    uint8_t* pj = nullptr;
+    size_t pjBytes = 0;
+    unsigned* pool = nullptr;
+    int poolCap = 0;
+    int* pjStatus = nullptr;
+    int launches = 0;
+    int64_t launchesTotal = 0;
+    cudaEvent_t ev[4] = {};
+    float stereoMs = 0, gridMs = 0;
+};
+
+namespace gvs {
+// context.cu
+int syncExtract(gvs_extractor* fe);                 // wait for the handle's last batch, surface device-side status bits
+int joinRight(gvs_matcher* m);                      // L's stream waits for R's last batch
+int holdRight(gvs_matcher* m);                      // R's stream waits for the matcher work queued on L's stream
+int growScratch(gvs_matcher* m, size_t bytes);      // m->pj of at least `bytes` (synchronises when it has to reallocate)
+// temporal.cu
+int checkResident(gvs_matcher* m, bool needStereo, int frame0, int nFrames);   // grids / stereo arrays belong to the current batch
+}  // namespace gvs

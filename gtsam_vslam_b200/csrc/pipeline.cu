@@ -75,6 +75,30 @@ int gvs_pipeline_submit(gvs_pipeline* p, const uint8_t* left, const uint8_t* rig
     return GVS_OK;
 }
 
+int gvs_pipeline_submit_temporal(gvs_pipeline* p, const uint8_t* left, const uint8_t* right, size_t image_stride, int row_stride,
+                                 int n_frames, const gvs_temporal_params* temporal, int64_t* ticket) {
+    if (!temporal) return gvs_pipeline_submit(p, left, right, image_stride, row_stride, n_frames, ticket);
+    if (!p || !left || !right || !ticket) return fail(GVS_ERR_INVALID, "null argument");
+    if (n_frames < 1 || n_frames > p->framesPerSlot) return fail(GVS_ERR_INVALID, "n_frames out of range for a slot");
+    gvs_pipeline::Slot& s = p->slots[(size_t)(p->next % (int64_t)p->slots.size())];
+    if (s.ticket >= 0) return fail(GVS_ERR_STATE, "pipeline full: release the oldest ticket first");
+    int rc = gvs_track_stereo_batch_host(s.m, left, right, image_stride, row_stride, n_frames, p->width, p->height);
+    if (!rc) rc = gvs_track_temporal_batch(s.m, n_frames, temporal);
+    if (rc) return rc;
+    s.ticket = p->next++; s.n = n_frames; s.done = false;
+    *ticket = s.ticket;
+    return GVS_OK;
+}
+
+int gvs_pipeline_download_temporal(gvs_pipeline* p, int64_t ticket, int32_t* mp_offsets, int32_t* mp_key, int32_t* matches,
+                                   int32_t* n_matches) {
+    gvs_pipeline::Slot* s = slotOf(p, ticket);
+    if (!s) return fail(GVS_ERR_INVALID, "unknown or released ticket");
+    int rc = 0;
+    if (!s->done && (rc = gvs_pipeline_wait(p, ticket, nullptr, nullptr))) return rc;
+    return gvs_temporal_download(s->m, 0, s->n, mp_offsets, mp_key, matches, n_matches, nullptr, nullptr, nullptr, nullptr);
+}
+
 int gvs_pipeline_wait(gvs_pipeline* p, int64_t ticket, int32_t* left_offsets, int32_t* right_offsets) {
     gvs_pipeline::Slot* s = slotOf(p, ticket);
     if (!s) return fail(GVS_ERR_INVALID, "unknown or released ticket");

@@ -1,22 +1,12 @@
-// K10 proj_match: windowed, projection-guided descriptor matching of map points against one frame.
-// Replaces FeatureMatcher::getMatchIdxs (reference src/FeatureMatcher.cpp:13-64), matchByProjectionRPred
-// (:254-389), matchByProjectionMono (:391-456) and matchByRadius (:458-526).
-//
-// The reference is greedy over map points in index order: a key point matched by map point j is skipped by
-// every later map point.  Two phases keep that order while doing the heavy work in parallel:
-//
-// phase 1 (proj_candidates, one warp per (map point, side)): enumerate the grid window in the reference's
-//   order (grid row, grid column, insertion order = one contiguous CSR range per grid row), apply the octave
-//   and |dx|,|dy| < radius tests (and the pixel-parallax test of matchByRadius), compute the 256-bit Hamming
-//   distances with __popc, and store the ordered list {idx, dist, level}.  It also reduces the list to the
-//   only three candidates the best/second-best rule can depend on (App. A.9): the first minimum p, the first
-//   minimum of the prefix [0,p) and the first minimum of the suffix (p,end).
-// phase 2 (proj_resolve, one CTA per call): walks the map points in order, 32 at a time.  If none of a map
-//   point's three deciding candidates is already matched, the phase-1 result stands (skipping any other
-//   candidate cannot change best, second or their levels); otherwise a warp rescans the stored list with the
-//   skip test.  Map points of a chunk that do not touch each other's deciding candidates are committed together (see the
-//   kernel).  matchedIdxsL/R live in shared memory for the duration of the walk.
+// Map-point side kernels of the matcher (everything here works on caller-provided arrays of ONE call):
+//   * FeatureMatcher::matchByProjectionRPredLBA (reference src/FeatureMatcher.cpp:66-252): proj_candidates_kernel (ordered
+//     candidate lists of a stored key frame, reduced to the three deciding candidates of SURVEY App. A.9) + lba_resolve_kernel;
+//   * MapPoint::calcDescriptor (src/Map.cpp:145-210), FeatureTracker::worldToFrame / removeOutOfFrameMPs / PredictMPsPosition /
+//     findOutliersR / findOutliersMono (src/FeatureTracker.cpp:582-1013), FeatureMatcher::DescriptorDistance (:710-726).
+// The batched projection matchers against the device-resident frames (matchByProjectionRPred / Mono / matchByRadius) live in
+// temporal.cu.
 #include "common.cuh"
+#include "mappoint_math.cuh"
 
 namespace gvs {
 
@@ -168,164 +158,6 @@ __device__ __forceinline__ Decision decide(unsigned eBest, unsigned ePre, unsign
     return d;
 }
 
-// phase 2.  The reference walks the map points in index order; map point i only depends on an earlier one j if j takes a key
-// that is one of i's (at most six) deciding candidates.  A CTA of 32 warps handles 32 map points at a time: every warp
-// computes the tentative decision of its map point against the current matched arrays (rescanning its stored list when a
-// deciding candidate is already taken), then warp 0 finds the longest prefix of the chunk in which no map point is affected by
-// an earlier one of the same chunk, commits it, and the rest is re-evaluated.  The first pending map point is always safe,
-// so every round makes progress; without conflicts a chunk costs one round.
-constexpr int kResolveWarps = 32;
-
-__global__ void __launch_bounds__(32 * kResolveWarps)
-proj_resolve_kernel(const ProjArgs a, const ProjRec* __restrict__ recs) {
-    extern __shared__ int sMatched[];  // NL + NR
-    __shared__ int sDec[kResolveWarps][6];                     // key ids of the deciding candidates (left 0..2, right 3..5), -1 = none
-    __shared__ int sTakeL[kResolveWarps], sTakeR[kResolveWarps];   // keys the map point marks if accepted (-1 = none)
-    __shared__ int sOut0[kResolveWarps], sOut1[kResolveWarps];     // its matchesIdxs pair
-    __shared__ int sAccept[kResolveWarps];
-    __shared__ int sDone, sTotal;
-    int* mL = sMatched;
-    int* mR = sMatched + a.NL;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool stereo = a.mode == GVS_MATCH_STEREO_PRED;
-    for (int i = tid; i < a.NL; i += blockDim.x) mL[i] = a.matchedL[i];
-    if (stereo) for (int i = tid; i < a.NR; i += blockDim.x) mR[i] = a.matchedR[i];
-    if (tid == 0) sTotal = 0;
-    const int nSides = stereo ? 2 : 1;
-    auto taken = [&](unsigned e, const int* m) { return e != kNone && m[candIdx(e)] >= 0; };
-    auto keyOf = [&](unsigned e) { return e == kNone ? -1 : candIdx(e); };
-    for (int base = 0; base < a.M; base += kResolveWarps) {
-        const int chunk = min(kResolveWarps, a.M - base);
-        __syncthreads();
-        if (tid == 0) sDone = 0;
-        bool first = true;
-        while (true) {
-            __syncthreads();
-            const int done = sDone;
-            if (done >= chunk) break;
-            // ---- (A) tentative decisions of the pending map points whose inputs changed
-            if (warp >= done && warp < chunk) {
-                bool redo = first;
-                if (!first) {
-#pragma unroll
-                    for (int q = 0; q < 6; q++) {
-                        const int kq = sDec[warp][q];
-                        if (kq >= 0 && (q < 3 ? mL[kq] : mR[kq]) >= 0) redo = true;
-                    }
-                }
-                if (redo) {
-                    const int mp = base + warp;
-                    const bool skipMP = a.mode != GVS_MATCH_RADIUS && (a.matches[2 * mp] >= 0 || a.matches[2 * mp + 1] >= 0);
-                    int accept = 0, takeL = -1, takeR = -1, out0 = -1, out1 = -1;
-                    unsigned eb = kNone, ep = kNone, es = kNone, rb = kNone, rp = kNone, rs = kNone;
-                    if (!skipMP) {
-                        const ProjRec rl = recs[mp * nSides];
-                        eb = rl.eBest; ep = rl.ePre; es = rl.eSuf;
-                        if (taken(eb, mL) || taken(ep, mL) || taken(es, mL)) reduceList(a.candL + rl.start, rl.len, mL, lane, eb, ep, es);
-                        Decision d = decide(eb, ep, es);
-                        bool right = false;
-                        int bestIdxR = -1;
-                        if (stereo) {
-                            const ProjRec rr = recs[mp * nSides + 1];
-                            rb = rr.eBest; rp = rr.ePre; rs = rr.eSuf;
-                            if (taken(rb, mR) || taken(rp, mR) || taken(rs, mR)) reduceList(a.candR + rr.start, rr.len, mR, lane, rb, rp, rs);
-                            const Decision dr = decide(rb, rp, rs);
-                            bestIdxR = dr.bestIdx;
-                            if (d.bestDist > dr.bestDist) {
-                                d.bestDist = dr.bestDist; d.secDist = dr.secDist; d.bestLev = dr.bestLev; d.bestLev2 = dr.bestLev2;
-                                right = true;
-                            }
-                        }
-                        bool ok;
-                        if (a.mode == GVS_MATCH_MONO) {
-                            // (ratioProj + 0.1) * secDist is evaluated in double (float + double), threshold 100 + 50
-                            const double thr = ((double)0.8f + 0.1) * (double)d.secDist;
-                            ok = d.bestDist <= 150 && !(d.bestLev == d.bestLev2 && (double)d.bestDist >= thr) &&
-                                 (d.bestLev != d.bestLev2 || (double)d.bestDist < thr);
-                        } else {
-                            const float thr = __fmul_rn(0.8f, (float)d.secDist);
-                            ok = d.bestDist <= 100 && !(d.bestLev == d.bestLev2 && (float)d.bestDist >= thr) &&
-                                 (d.bestLev != d.bestLev2 || (float)d.bestDist < thr);
-                        }
-                        if (ok) {
-                            accept = 1;
-                            if (!stereo) { takeL = d.bestIdx; out0 = d.bestIdx; }
-                            else if (right) {
-                                takeR = bestIdxR; out1 = bestIdxR;
-                                const int li = a.leftIdxs[bestIdxR];
-                                if (li >= 0) { out0 = li; takeL = li; }
-                            } else {
-                                takeL = d.bestIdx; out0 = d.bestIdx;
-                                const int ri = a.rightIdxs[d.bestIdx];
-                                if (ri >= 0) { out1 = ri; takeR = ri; }
-                            }
-                        }
-                    }
-                    if (lane == 0) {
-                        sDec[warp][0] = keyOf(eb); sDec[warp][1] = keyOf(ep); sDec[warp][2] = keyOf(es);
-                        sDec[warp][3] = keyOf(rb); sDec[warp][4] = keyOf(rp); sDec[warp][5] = keyOf(rs);
-                        sAccept[warp] = accept; sTakeL[warp] = takeL; sTakeR[warp] = takeR; sOut0[warp] = out0; sOut1[warp] = out1;
-                    }
-                }
-            }
-            first = false;
-            __syncthreads();
-            // ---- (B) warp 0, lane = map point of the chunk: longest safe prefix, commit
-            if (warp == 0) {
-                bool unsafe = false;
-                int dl0 = -1, dl1 = -1, dl2 = -1, dr0 = -1, dr1 = -1, dr2 = -1;
-                if (lane < chunk) { dl0 = sDec[lane][0]; dl1 = sDec[lane][1]; dl2 = sDec[lane][2]; dr0 = sDec[lane][3]; dr1 = sDec[lane][4]; dr2 = sDec[lane][5]; }
-                for (int j = done; j < chunk - 1; j++) {
-                    if (!sAccept[j]) continue;   // (uniform)
-                    const int tl = sTakeL[j], tr = sTakeR[j];
-                    if (lane > j && lane < chunk) {
-                        if (tl >= 0 && (tl == dl0 || tl == dl1 || tl == dl2)) unsafe = true;
-                        if (tr >= 0 && (tr == dr0 || tr == dr1 || tr == dr2)) unsafe = true;
-                    }
-                }
-                const unsigned um = __ballot_sync(0xffffffffu, unsafe);
-                const int upto = um ? __ffs(um) - 1 : chunk;     // lanes [done, upto) are final
-                const bool mine = lane >= done && lane < upto && sAccept[lane];
-                const int i = base + lane;
-                // several committed map points may mark the same key (a stereo partner): the last one in index order wins
-                const int tl = mine ? sTakeL[lane] : -1, tr = mine ? sTakeR[lane] : -1;
-                const unsigned pl = __match_any_sync(0xffffffffu, tl >= 0 ? tl : -1 - lane);
-                const unsigned pr = __match_any_sync(0xffffffffu, tr >= 0 ? tr : -1 - lane);
-                if (tl >= 0 && (31 - __clz(pl)) == lane) mL[tl] = i;
-                if (tr >= 0 && (31 - __clz(pr)) == lane) mR[tr] = i;
-                if (mine) {
-                    if (a.mode != GVS_MATCH_STEREO_PRED) a.matches[2 * i] = sOut0[lane];
-                    else {
-                        if (sOut0[lane] >= 0) a.matches[2 * i] = sOut0[lane];
-                        if (sOut1[lane] >= 0) a.matches[2 * i + 1] = sOut1[lane];
-                    }
-                }
-                const int nAcc = __popc(__ballot_sync(0xffffffffu, mine));
-                if (lane == 0) { sTotal += nAcc; sDone = upto; }
-            }
-        }
-    }
-    __syncthreads();
-    for (int i = tid; i < a.NL; i += blockDim.x) a.matchedL[i] = mL[i];
-    if (stereo) for (int i = tid; i < a.NR; i += blockDim.x) a.matchedR[i] = mR[i];
-    if (tid == 0) *a.nMatches = sTotal;
-}
-
-void launchProject(const ProjArgs& a, cudaStream_t s, int* launches) {
-    ProjRec* recs = reinterpret_cast<ProjRec*>(a.recs);
-    cudaMemsetAsync(a.poolTop, 0, 2 * sizeof(int), s);
-    if (a.M <= 0) { cudaMemsetAsync(a.nMatches, 0, sizeof(int), s); return; }
-    const int nSides = a.mode == GVS_MATCH_STEREO_PRED ? 2 : 1;
-    const int warps = a.M * nSides;
-    proj_candidates_kernel<<<(warps + 7) / 8, 256, 0, s>>>(a, recs);
-    ++*launches;
-    const size_t sm = (size_t)(a.NL + a.NR) * sizeof(int);
-    static size_t cfg[64];
-    ensureDynamicSmem(proj_resolve_kernel, sm + 4096, cfg);   // (+ the kernel's static shared memory counts against the 48 KB default)
-    proj_resolve_kernel<<<1, 32 * kResolveWarps, sm, s>>>(a, recs);
-    ++*launches;
-}
-
 // FeatureMatcher::matchByProjectionRPredLBA decision (src/FeatureMatcher.cpp:191-249), one thread per candidate point.
 // Left branch quirk (:132-136): a later second-best takes the *best* key's level.
 __global__ void lba_resolve_kernel(const ProjArgs a, const ProjRec* __restrict__ recs, const float* __restrict__ lastL,
@@ -426,29 +258,6 @@ void launchMedianDescriptor(const uint8_t* descs, const int* offsets, int P, int
     ++*launches;
 }
 
-// FeatureTracker::worldToFrame + MapPoint::predictScale (src/FeatureTracker.cpp:685-741, src/Map.cpp:13-23), thread per map
-// point.  Double precision, explicit round-to-nearest operations in the reference's left-to-right order (no FMA).
-// one map point into one camera; returns worldToFrame's bool and updates pred / scaleLevel only when the point is in the frame
-__device__ __forceinline__ bool worldToFrameOne(const double* __restrict__ poseInv, const double* __restrict__ w, double fx, double fy,
-                                                double cx, double cy, int width, int height, float maxScaleDist, float logScale,
-                                                int nScaleLev, float* pred, int* scaleLevel) {
-    double pt[3];
-#pragma unroll
-    for (int r = 0; r < 3; r++)
-        pt[r] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(poseInv[4 * r], w[0]), __dmul_rn(poseInv[4 * r + 1], w[1])), __dmul_rn(poseInv[4 * r + 2], w[2])),
-                          __dmul_rn(poseInv[4 * r + 3], w[3]));
-    if (pt[2] <= 0.0) return false;
-    const double invZ = __ddiv_rn(1.0, pt[2]);
-    const double u = __dadd_rn(__dmul_rn(__dmul_rn(fx, pt[0]), invZ), cx), v = __dadd_rn(__dmul_rn(__dmul_rn(fy, pt[1]), invZ), cy);
-    if (u < 0 || v < 0 || u >= width || v >= height) return false;
-    const float dist = (float)__dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(pt[0], pt[0]), __dmul_rn(pt[1], pt[1])), __dmul_rn(pt[2], pt[2])));
-    const float dif = __fdiv_rn(maxScaleDist, dist);
-    int scale = (int)ceil(__ddiv_rn(log((double)dif), (double)logScale));
-    if (scale < 0) scale = 0; else if (scale >= nScaleLev) scale = nScaleLev - 1;
-    *scaleLevel = scale; pred[0] = (float)u; pred[1] = (float)v;
-    return true;
-}
-
 __global__ void world_to_frame_kernel(int M, const double* __restrict__ poseInv, double fx, double fy, double cx, double cy, int width,
                                       int height, const double* __restrict__ wPos, const float* __restrict__ maxScaleDist,
                                       const float* __restrict__ logScale, const int* __restrict__ nScaleLev, float* __restrict__ pred,
@@ -509,13 +318,6 @@ void launchWorldToFrame(int M, const double* poseInv, double fx, double fy, doub
 // original `close` and records, per left key, the smallest match index that would clear it (atomicMin); pass 2 counts a
 // stereo inlier only before that index and applies the clearing at that index.  Double precision, explicit round-to-nearest
 // operations in the reference's left-to-right order (no FMA), like world_to_frame_kernel.
-__device__ __forceinline__ void mulPose(const double* __restrict__ P, const double* __restrict__ w, double (&pt)[3]) {
-#pragma unroll
-    for (int r = 0; r < 3; r++)
-        pt[r] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P[4 * r], w[0]), __dmul_rn(P[4 * r + 1], w[1])), __dmul_rn(P[4 * r + 2], w[2])),
-                          __dmul_rn(P[4 * r + 3], w[3]));
-}
-
 // FeatureTracker::check2dError, :147-164
 __device__ __forceinline__ bool check2dError(const double (&p)[3], float ox, float oy, double fx, double fy, double cx, double cy,
                                              double thres, double weight) {

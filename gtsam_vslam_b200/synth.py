@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["stereo_pair", "stereo_batch", "shifted_sequence", "CONFIGS"]
+__all__ = ["stereo_pair", "stereo_batch", "shifted_sequence", "stereo_sequence", "sequence_motion", "CONFIGS"]
 
 # FE params follow reference config/config_kitti_00.yaml:48-55, config/config_MH_01.yaml:101-108,
 # include/FeatureExtractor.h:80 (defaults, mono) ; camera values :20,:45 / :33,:98.
@@ -94,3 +94,48 @@ def shifted_sequence(width: int, height: int, n_frames: int, seed: int = 0, step
     for k in range(n_frames):
         out[k] = _noisy_u8(rng, c[step[1] * k: step[1] * k + height, step[0] * k: step[0] * k + width])
     return out
+
+
+def stereo_sequence(width: int, height: int, disparity: int, n_frames: int, seed: int = 0, step=(2, 1)):
+    """Temporal stereo sequence: frame k is the crop of one big canvas at offset step*k (left) and step*k + (disparity, 0) (right),
+    i.e. a fronto-parallel plane at depth fx*b/disparity seen by a camera that translates by step pixels per frame.  Two
+    (n_frames, H, W) uint8 arrays.  Bounded canvas: the walk turns around every 64 frames so that long batches stay small."""
+    rng = np.random.default_rng(seed)
+    span = 64
+    cw = width + step[0] * span + disparity + 32
+    ch = height + step[1] * span + 32
+    c = _canvas(rng, ch, cw, (cw * ch) // 90)
+    L = np.empty((n_frames, height, width), np.uint8)
+    R = np.empty_like(L)
+    for k in range(n_frames):
+        ox, oy = sequence_offset(k, step, span)
+        L[k] = _noisy_u8(rng, c[oy: oy + height, ox: ox + width])
+        R[k] = _noisy_u8(rng, c[oy: oy + height, ox + disparity: ox + disparity + width])
+    return L, R
+
+
+def sequence_offset(k: int, step=(2, 1), span: int = 64):
+    """Canvas offset of frame k of stereo_sequence: a triangle wave of period 2*span."""
+    m = k % (2 * span)
+    t = m if m <= span else 2 * span - m
+    return step[0] * t, step[1] * t
+
+
+def sequence_motion(cfg: dict, n_frames: int, prev, step=(2, 1), span: int = 64):
+    """Camera poses that explain stereo_sequence: pose_k = translation of offset_k * z0 / f, z0 = fx * baseline / disparity
+    (identity rotation, fy = fx, principal point at the image centre).  Returns dict(fx, fy, cx, cy, extrinsics, pose (n,4,4),
+    pose_prev, to_camera, to_camera_r (n,4,4) for the given predecessor list)."""
+    fx = float(cfg["fx"]); b = float(cfg["baseline"]); d = float(cfg["disparity"])
+    z0 = fx * b / d
+    pose = np.tile(np.eye(4), (n_frames, 1, 1))
+    for k in range(n_frames):
+        ox, oy = sequence_offset(k, step, span)
+        pose[k, 0, 3] = ox * z0 / fx
+        pose[k, 1, 3] = oy * z0 / fx
+    ext = np.eye(4); ext[0, 3] = b
+    prev = np.asarray(prev, np.int32)
+    pose_prev = np.stack([pose[p] if p >= 0 else np.eye(4) for p in prev])
+    to_cam = np.stack([np.linalg.inv(pose[k]) for k in range(n_frames)])
+    to_cam_r = np.stack([np.linalg.inv(pose[k] @ ext) for k in range(n_frames)])
+    return dict(fx=fx, fy=fx, cx=cfg["width"] / 2.0, cy=cfg["height"] / 2.0, extrinsics=ext, pose=pose, pose_prev=pose_prev,
+                to_camera=to_cam, to_camera_r=to_cam_r, prev=prev)

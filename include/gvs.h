@@ -193,9 +193,49 @@ typedef enum gvs_match_mode {
  * in-out exactly as in the reference (callers pre-fill them with -1 or with earlier matches).  For
  * GVS_MATCH_RADIUS matches[i][0] receives the matched key index (the reference appends (KeyFrame*, idx)
  * to keyframeIdxMatchs[i], :522).  *n_matches = the reference's return value.  Requires
- * gvs_assign_grids_batch (and gvs_stereo_match_batch for mode 0). */
+ * gvs_assign_grids_batch (and gvs_stereo_match_batch for mode 0) on the extractors' current batch: GVS_ERR_STATE otherwise.
+ * A scale level outside [0, n_levels) is GVS_ERR_INVALID (the reference indexes scalePyramid unchecked). */
 int gvs_match_projection(gvs_matcher* fm, int frame, int mode, const gvs_mappoints* mps, float rad, int32_t* matched_l,
                          int32_t* matched_r, int32_t* matches, int* n_matches);
+
+/* The same call for frames [first_frame, first_frame + n_frames) at once (two launches for the whole batch, no host loop):
+ * frame first_frame + f is matched against the map points [mp_offsets[f], mp_offsets[f + 1]) of `mps` (mp_offsets[0] = 0,
+ * mp_offsets[n_frames] = mps->count).  matched_l / matched_r are dense over the frames' keys (like gvs_extract_download of the
+ * same range), matches is mps->count x 2, n_matches has n_frames entries (the reference's return value per frame).
+ * Reference call sites: src/FeatureTracker.cpp:1205,1239 (stereo), :1400-1416 (mono), :1518 (radius). */
+int gvs_match_projection_batch(gvs_matcher* fm, int first_frame, int n_frames, int mode, const gvs_mappoints* mps,
+                               const int32_t* mp_offsets, float rad, int32_t* matched_l, int32_t* matched_r, int32_t* matches,
+                               int32_t* n_matches);
+
+/* Temporal tracking of consecutive stereo frames, device resident end to end (the timed step of bench.py: extract + stereo +
+ * temporal match).  For every frame f of the last batch with prev[f] >= 0 the call replays, on the device,
+ *   FeatureTracker::initializeMap's point creation (src/FeatureTracker.cpp:89-112) with MapPoint::update (src/Map.cpp:61-104):
+ *     one map point per left key of frame prev[f] with estimatedDepth > 0, wp = pose_prev[f] * ((x-cx)z/fx, (y-cy)z/fy, z, 1),
+ *     desc = its descriptor row, maxScaleDist = |wp - t(pose_prev[f])| * scalePyramid[octave];
+ *   FeatureTracker::removeOutOfFrameMPs (:910-940) -> worldToFrame (:685-741) -> MapPoint::predictScale (src/Map.cpp:13-23):
+ *     both projections with to_camera[f] / to_camera_r[f]; points that leave either camera are dropped, order kept;
+ *   FeatureMatcher::matchByProjectionRPred (src/FeatureMatcher.cpp:254-389) of the surviving points against frame f with radius
+ *     `rad`, on fresh matchedIdxsL / matchedIdxsR / matchesIdxs (:1176-1178).
+ * Frames are independent of each other (a frame only reads the stereo results of prev[f]), so the whole batch is a handful of
+ * launches.  Asynchronous (the parameter arrays are free again when the call returns); requires gvs_track_stereo_batch_* (or
+ * stereo + grids) on the current batch. */
+typedef struct gvs_temporal_params {
+    int32_t mode;              /* GVS_MATCH_STEREO_PRED */
+    float rad;                 /* 10 after the first frame, 120 at curFrame == 1 (src/FeatureTracker.cpp:1189-1192) */
+    double fx, fy, cx, cy;     /* FeatureTracker::fx .. cy = zedPtr->mCameraLeft intrinsics (src/FeatureTracker.cpp:23) */
+    int32_t width, height;     /* zedPtr->mWidth / mHeight (worldToFrame's bounds test) */
+    const int32_t* prev;       /* n_frames: index of the frame whose stereo keys become frame f's map points, -1 = none */
+    const double* pose_prev;   /* n_frames x 16, row-major: zedPtr->mCameraPose.pose when frame prev[f] was tracked */
+    const double* to_camera;   /* n_frames x 16: predNPose^-1 of frame f (:914) */
+    const double* to_camera_r; /* n_frames x 16: (predNPose * extrinsics)^-1 (:913) */
+} gvs_temporal_params;
+int gvs_track_temporal_batch(gvs_matcher* fm, int n_frames, const gvs_temporal_params* params);
+/* Results for frames [first, first + count) (waits for the batch).  mp_offsets (count + 1, relative to the first frame of the
+ * range): frame f's map points; mp_key: the left key of frame prev[f] each map point was created from (= activeMapPoints after
+ * removeOutOfFrameMPs, in order); matches (x 2) / n_matches (count) / matched_l / matched_r as in gvs_match_projection_batch;
+ * pred_l / pred_r (x 2 floats): MapPoint::predL / predR (parity taps).  Any pointer may be NULL. */
+int gvs_temporal_download(gvs_matcher* fm, int first, int count, int32_t* mp_offsets, int32_t* mp_key, int32_t* matches,
+                          int32_t* n_matches, int32_t* matched_l, int32_t* matched_r, float* pred_l, float* pred_r);
 
 /* FeatureMatcher::matchByProjectionRPredLBA, src/FeatureMatcher.cpp:66-252 (LocalMapper::findNewPoints,
  * src/OptimizationBA.cpp:367).  newKF is any stored key frame, so its keys come from the host: */
@@ -298,6 +338,10 @@ int gvs_pipeline_destroy(gvs_pipeline* p);
  * gvs_pipeline_wait returns).  GVS_ERR_STATE if that slot still holds an unreleased ticket. */
 int gvs_pipeline_submit(gvs_pipeline* p, const uint8_t* left, const uint8_t* right, size_t image_stride, int row_stride,
                         int n_frames, int64_t* ticket);
+/* The same followed by gvs_track_temporal_batch(temporal) on the ticket's frames (prev[] indexes frames of the ticket);
+ * temporal == NULL is gvs_pipeline_submit.  The parameter arrays are free again when the call returns. */
+int gvs_pipeline_submit_temporal(gvs_pipeline* p, const uint8_t* left, const uint8_t* right, size_t image_stride, int row_stride,
+                                 int n_frames, const gvs_temporal_params* temporal, int64_t* ticket);
 /* Blocks until the ticket is computed; offsets (n_frames + 1 entries each, may be NULL) as gvs_extract_offsets.  Device-side
  * failures of the ticket (GVS_ERR_CAPACITY ...) are returned here. */
 int gvs_pipeline_wait(gvs_pipeline* p, int64_t ticket, int32_t* left_offsets, int32_t* right_offsets);
@@ -305,6 +349,9 @@ int gvs_pipeline_wait(gvs_pipeline* p, int64_t ticket, int32_t* left_offsets, in
 int gvs_pipeline_download(gvs_pipeline* p, int64_t ticket, gvs_keypoint* kp_left, uint8_t* desc_left, int cap_left,
                           gvs_keypoint* kp_right, uint8_t* desc_right, int cap_right, int32_t* right_idxs, int32_t* left_idxs,
                           float* estimated_depth, uint8_t* close);
+/* Temporal results of all frames of the ticket (as gvs_temporal_download over the whole ticket). */
+int gvs_pipeline_download_temporal(gvs_pipeline* p, int64_t ticket, int32_t* mp_offsets, int32_t* mp_key, int32_t* matches,
+                                   int32_t* n_matches);
 /* The slot's handles, e.g. for gvs_match_projection / gvs_grid_download against the ticket's frames (valid until release). */
 int gvs_pipeline_handles(gvs_pipeline* p, int64_t ticket, gvs_extractor** fe_left, gvs_extractor** fe_right, gvs_matcher** fm);
 int gvs_pipeline_release(gvs_pipeline* p, int64_t ticket);
@@ -313,7 +360,7 @@ int gvs_pipeline_release(gvs_pipeline* p, int64_t ticket);
 
 /* Launch counters and device timings of the last batch, for bench.py (gpu_launches, per-stage ms). */
 typedef struct gvs_stage_times {
-    float pyramid_ms, fast_ms, select_ms, blur_ms, describe_ms, stereo_ms, grid_ms;
+    float pyramid_ms, fast_ms, select_ms, blur_ms, describe_ms, stereo_ms, grid_ms, temporal_ms;
     int32_t launches;
 } gvs_stage_times;
 int gvs_extractor_enable_timing(gvs_extractor* fe, int on);

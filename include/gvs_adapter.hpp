@@ -230,7 +230,8 @@ class FeatureMatcher {
             const double px = wPos(0) - toFindPose(0, 3), py = wPos(1) - toFindPose(1, 3), pz = wPos(2) - toFindPose(2, 3);
             const float dist = (float)std::sqrt(px * px + py * py + pz * pz);
             const float dif = maxDistsScale[i] / dist;
-            int predScale = (int)std::ceil(std::log(dif) / lastKF->logScale);
+            // the reference's unqualified log(dif) on a float (src/FeatureMatcher.cpp:91) is ::log(double) under <cmath>: double arithmetic, as in gvs.h
+            int predScale = (int)std::ceil(std::log((double)dif) / (double)lastKF->logScale);
             if (predScale < 0) predScale = 0; else if (predScale >= lastKF->nScaleLev) predScale = lastKF->nScaleLev - 1;
             ps[i] = predScale;
             pl[2 * i] = predPoints[i].first.x; pl[2 * i + 1] = predPoints[i].first.y;

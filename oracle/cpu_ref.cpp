@@ -915,7 +915,8 @@ void ora_world_to_frame(const double* poseInv, double fx, double fy, double cx, 
         if (u < 0 || v < 0 || u >= width || v >= height) { inFrame[i] = 0; continue; }
         const float dist = (float)std::sqrt(pt[0] * pt[0] + pt[1] * pt[1] + pt[2] * pt[2]);
         const float dif = maxScaleDist[i] / dist;
-        int scale = (int)std::ceil(std::log(dif) / logScale[i]);
+        // unqualified `log(dif)` on a float (src/Map.cpp:16) binds to ::log(double) when only <cmath> is in scope
+        int scale = (int)std::ceil(std::log((double)dif) / (double)logScale[i]);
         if (scale < 0) scale = 0; else if (scale >= nScaleLev[i]) scale = nScaleLev[i] - 1;
         scaleLevel[i] = scale; inFrame[i] = 1; pred[2 * i] = (float)u; pred[2 * i + 1] = (float)v;
     }
@@ -1009,6 +1010,44 @@ void ora_predict_mappoints(int mode, const double* toCamera, const double* toCam
     }
 }
 
+// The map points the tracker holds for frame f when they all come from the stereo keys of one earlier frame (temporal
+// matching of consecutive frames), as the reference builds and filters them:
+//   FeatureTracker::initializeMap (src/FeatureTracker.cpp:89-112): one point per left key with estimatedDepth > 0,
+//     p = pose * ((x - cx) * zp / fx, (y - cy) * zp / fy, zp, 1)  (double);
+//   MapPoint::update (src/Map.cpp:61-104): dist = |wp3d - kF->pose.t| (float), maxScaleDist = dist * kF->scaleFactor[octave of the left key];
+//   FeatureTracker::removeOutOfFrameMPs (:910-940): worldToFrame into both cameras, a point stays iff both succeed.
+// Outputs, one entry per surviving point in order: mpKey (source key), predL / predR, scaleLevelL / R, wPos (4 doubles), maxScaleDist.
+// Returns the number of surviving points.  Restated (FeatureTracker.cpp needs GTSAM); 4x4 products row by row, no contraction.
+int ora_temporal_mappoints(const KeyPoint* kl, int NL, const float* depth, const double* posePrev, const double* toCamera,
+                           const double* toCameraR, double fx, double fy, double cx, double cy, int width, int height,
+                           const float* scalePyramid, int nLevels, float logScale, int* mpKey, float* predL, float* predR, int* lvlL,
+                           int* lvlR, double* wPos, float* maxScaleDist) {
+    int M = 0;
+    for (int i = 0; i < NL; i++) {
+        if (!(depth[i] > 0)) continue;
+        const double zp = (double)depth[i];
+        const double c[4] = {(double)(((double)kl[i].x - cx) * zp / fx), (double)(((double)kl[i].y - cy) * zp / fy), zp, 1.0};
+        double w[4];
+        for (int r = 0; r < 4; r++) w[r] = ((posePrev[4 * r] * c[0] + posePrev[4 * r + 1] * c[1]) + posePrev[4 * r + 2] * c[2]) + posePrev[4 * r + 3] * c[3];
+        const double ex = w[0] - posePrev[3], ey = w[1] - posePrev[7], ez = w[2] - posePrev[11];
+        const float dist = (float)std::sqrt(ex * ex + ey * ey + ez * ez);
+        const float msd = dist * scalePyramid[kl[i].octave];
+        const int nl = nLevels;
+        float pl[2] = {0, 0}, pr[2] = {0, 0};
+        int ll = 0, lr = 0;
+        uint8_t c1 = 0, c2 = 0;
+        ora_world_to_frame(toCamera, fx, fy, cx, cy, width, height, 1, w, &msd, &logScale, &nl, pl, &ll, &c1);
+        ora_world_to_frame(toCameraR, fx, fy, cx, cy, width, height, 1, w, &msd, &logScale, &nl, pr, &lr, &c2);
+        if (!(c1 && c2)) continue;
+        mpKey[M] = i; predL[2 * M] = pl[0]; predL[2 * M + 1] = pl[1]; predR[2 * M] = pr[0]; predR[2 * M + 1] = pr[1];
+        lvlL[M] = ll; lvlR[M] = lr;
+        if (wPos) for (int r = 0; r < 4; r++) wPos[4 * M + r] = w[r];
+        if (maxScaleDist) maxScaleDist[M] = msd;
+        M++;
+    }
+    return M;
+}
+
 int ora_descriptor_distance(const uint8_t* a, const uint8_t* b) { return descriptorDistance(a, b); }
 
 // ---- primitive-level entry points (pinned one by one against cv2 in tests/test_oracle_vs_cv2.py)
@@ -1026,42 +1065,84 @@ int ora_fast_detect(const uint8_t* img, int w, int h, int threshold, int* xs, in
     return (int)out.size();
 }
 
-// ---- CPU baseline: F stereo frames (extract L, extract R, stereo match, two grids = FeatureTracker.cpp:56-70).
+// ---- CPU baseline: F stereo frames (extract L, extract R, stereo match, two grids = FeatureTracker.cpp:56-70), then, when `prev`
+// is given, the temporal step of bench.py (map points of frame f from the stereo keys of frame prev[f], matchByProjectionRPred
+// on fresh index arrays, src/FeatureTracker.cpp:1176-1205).
 // shape 0 = "reference-shaped": frames in sequence, 2 extraction threads per frame + serial matcher (2 cores).
 // shape 1 = frame-parallel over `threads` workers (each worker runs L, R, match serially).
 // Returns total matched pairs (so the work cannot be optimised away); nKeysOut[f] = left keypoints of frame f.
-long ora_stereo_frames(int nF, int nL, float s, int edge, int patch, int maxF, int minF, double fx, float baseline,
-                       const uint8_t* L, const uint8_t* R, int frames, int w, int h, int shape, int threads,
-                       int* nKeysOut) {
+long ora_track_frames(int nF, int nL, float s, int edge, int patch, int maxF, int minF, double fx, float baseline,
+                      const uint8_t* L, const uint8_t* R, int frames, int w, int h, int shape, int threads, int* nKeysOut,
+                      const int* prev, const double* posePrev, const double* toCamera, const double* toCameraR, double cfx, double cfy,
+                      double ccx, double ccy, float rad, int* nTemporalOut) {
     std::atomic<long> total{0};
+    struct FrameKeys { std::vector<KeyPoint> kl, kr; std::vector<uint8_t> dl, dr; std::vector<int> ridx, lidx; std::vector<float> dep; };
+    std::vector<FrameKeys> all(prev ? frames : 0);
     auto one = [&](int f, bool twoThreads) {
         Extractor feL(nF, nL, s, edge, patch, maxF, minF), feR(nF, nL, s, edge, patch, maxF, minF);
-        std::vector<KeyPoint> kl, kr; std::vector<uint8_t> dl, dr;
+        FrameKeys local;
+        FrameKeys& k = prev ? all[f] : local;
         const uint8_t* li = L + (size_t)f * w * h; const uint8_t* ri = R + (size_t)f * w * h;
         int nl = 0, nr = 0;
         if (twoThreads) {
-            std::thread a([&] { nl = feL.extract(li, w, h, w, kl, dl); });
-            std::thread b([&] { nr = feR.extract(ri, w, h, w, kr, dr); });
+            std::thread a([&] { nl = feL.extract(li, w, h, w, k.kl, k.dl); });
+            std::thread b([&] { nr = feR.extract(ri, w, h, w, k.kr, k.dr); });
             a.join(); b.join();
-        } else { nl = feL.extract(li, w, h, w, kl, dl); nr = feR.extract(ri, w, h, w, kr, dr); }
-        std::vector<int> ridx(nl), lidx(nr); std::vector<float> dep(nl); std::vector<uint8_t> cl(nl);
-        stereoMatch(feL, feR, fx, baseline, h, kl.data(), dl.data(), nl, kr.data(), dr.data(), nr, ridx.data(),
-                    lidx.data(), dep.data(), cl.data(), nullptr);
-        Grid g1 = assignKeysToGrids(kl.data(), nl, w, h), g2 = assignKeysToGrids(kr.data(), nr, w, h);
+        } else { nl = feL.extract(li, w, h, w, k.kl, k.dl); nr = feR.extract(ri, w, h, w, k.kr, k.dr); }
+        k.ridx.resize(nl); k.lidx.resize(nr); k.dep.resize(nl);
+        std::vector<uint8_t> cl(nl);
+        stereoMatch(feL, feR, fx, baseline, h, k.kl.data(), k.dl.data(), nl, k.kr.data(), k.dr.data(), nr, k.ridx.data(),
+                    k.lidx.data(), k.dep.data(), cl.data(), nullptr);
+        Grid g1 = assignKeysToGrids(k.kl.data(), nl, w, h), g2 = assignKeysToGrids(k.kr.data(), nr, w, h);
         long m = 0;
-        for (int v : ridx) m += v >= 0;
+        for (int v : k.ridx) m += v >= 0;
         total += m + (g1.items.size() + g2.items.size() == (size_t)(nl + nr) ? 0 : 1);
         if (nKeysOut) nKeysOut[f] = nl;
     };
-    if (shape == 0) { for (int f = 0; f < frames; f++) one(f, true); }
-    else {
+    auto temporal = [&](int f) {
+        if (nTemporalOut) nTemporalOut[f] = 0;
+        const int p = prev[f];
+        if (p < 0) return;
+        Extractor fe(nF, nL, s, edge, patch, maxF, minF);
+        const FrameKeys& pk = all[p];
+        const FrameKeys& k = all[f];
+        const int np = (int)pk.kl.size(), cap = std::max(np, 1);
+        std::vector<int> key(cap), ll(cap), lr(cap);
+        std::vector<float> pl(2 * cap), pr(2 * cap);
+        const int M = ora_temporal_mappoints(pk.kl.data(), np, pk.dep.data(), posePrev + 16 * f, toCamera + 16 * f, toCameraR + 16 * f, cfx, cfy,
+                                             ccx, ccy, w, h, fe.scalePyramid.data(), nL, (float)std::log((double)s), key.data(), pl.data(),
+                                             pr.data(), ll.data(), lr.data(), nullptr, nullptr);
+        std::vector<uint8_t> desc((size_t)std::max(M, 1) * 32), in(std::max(M, 1), 1);
+        for (int i = 0; i < M; i++) std::memcpy(&desc[(size_t)i * 32], &pk.dl[(size_t)key[i] * 32], 32);
+        std::vector<int> mL(std::max<size_t>(k.kl.size(), 1), -1), mR(std::max<size_t>(k.kr.size(), 1), -1), mt(2 * (size_t)std::max(M, 1), -1);
+        const int n = ora_match_projection(&fe, 0, M, desc.data(), pl.data(), pr.data(), ll.data(), lr.data(), in.data(), in.data(), k.kl.data(),
+                                           k.dl.data(), (int)k.kl.size(), k.kr.data(), k.dr.data(), (int)k.kr.size(), k.lidx.data(), k.ridx.data(),
+                                           w, h, rad, mL.data(), mR.data(), mt.data());
+        total += n;
+        if (nTemporalOut) nTemporalOut[f] = n;
+    };
+    auto parallel = [&](auto&& fn) {
         std::atomic<int> next{0};
         std::vector<std::thread> pool;
         for (int t = 0; t < std::max(1, threads); t++)
-            pool.emplace_back([&] { for (int f; (f = next++) < frames;) one(f, false); });
+            pool.emplace_back([&] { for (int f; (f = next++) < frames;) fn(f); });
         for (auto& t : pool) t.join();
+    };
+    if (shape == 0) {
+        for (int f = 0; f < frames; f++) one(f, true);
+        if (prev) for (int f = 0; f < frames; f++) temporal(f);
+    } else {
+        parallel([&](int f) { one(f, false); });
+        if (prev) parallel(temporal);
     }
     return total.load();
+}
+
+long ora_stereo_frames(int nF, int nL, float s, int edge, int patch, int maxF, int minF, double fx, float baseline,
+                       const uint8_t* L, const uint8_t* R, int frames, int w, int h, int shape, int threads,
+                       int* nKeysOut) {
+    return ora_track_frames(nF, nL, s, edge, patch, maxF, minF, fx, baseline, L, R, frames, w, h, shape, threads, nKeysOut, nullptr, nullptr,
+                            nullptr, nullptr, 0, 0, 0, 0, 0.f, nullptr);
 }
 
 }  // extern "C"

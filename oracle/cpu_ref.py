@@ -233,6 +233,26 @@ def find_outliers(mode, pose, poseR, fx, fy, cx, cy, thres, closeDist, invSigma,
     return int(cnt[0]), int(cnt[1])
 
 
+def temporal_mappoints(fe: Extractor, kl, depth, posePrev, toCamera, toCameraR, fx, fy, cx, cy, width, height):
+    """Map points of a frame made from the stereo keys of its predecessor: initializeMap's point creation + MapPoint::update +
+    removeOutOfFrameMPs (reference src/FeatureTracker.cpp:89-112, src/Map.cpp:61-104, src/FeatureTracker.cpp:910-940)."""
+    c = lambda a, dt: np.ascontiguousarray(a, dt)
+    kl = np.ascontiguousarray(kl)
+    n = len(kl)
+    key = np.zeros(max(n, 1), np.int32); pL = np.zeros((max(n, 1), 2), np.float32); pR = np.zeros((max(n, 1), 2), np.float32)
+    lL = np.zeros(max(n, 1), np.int32); lR = np.zeros(max(n, 1), np.int32)
+    wp = np.zeros((max(n, 1), 4), np.float64); msd = np.zeros(max(n, 1), np.float32)
+    imScale = np.float32(fe.params[2])
+    logScale = np.float32(np.log(np.float64(imScale)))
+    lib().ora_temporal_mappoints.restype = C.c_int
+    M = lib().ora_temporal_mappoints(_p(kl), n, _p(c(depth, np.float32)), _p(c(posePrev, np.float64)), _p(c(toCamera, np.float64)),
+                                     _p(c(toCameraR, np.float64)), C.c_double(fx), C.c_double(fy), C.c_double(cx), C.c_double(cy),
+                                     width, height, _p(fe.scalePyramid), fe.nLevels, C.c_float(logScale), _p(key), _p(pL), _p(pR),
+                                     _p(lL), _p(lR), _p(wp), _p(msd))
+    return dict(key=key[:M].copy(), predL=pL[:M].copy(), predR=pR[:M].copy(), scaleLevelL=lL[:M].copy(), scaleLevelR=lR[:M].copy(),
+                wPos=wp[:M].copy(), maxScaleDist=msd[:M].copy(), logScale=logScale)
+
+
 def stereo_frames(params, fx, baseline, L: np.ndarray, R: np.ndarray, shape: int, threads: int):
     """CPU baseline: run F stereo frames; returns (total matches, per-frame left key counts)."""
     L = np.ascontiguousarray(L, np.uint8); R = np.ascontiguousarray(R, np.uint8)
@@ -242,3 +262,24 @@ def stereo_frames(params, fx, baseline, L: np.ndarray, R: np.ndarray, shape: int
     tot = lib().ora_stereo_frames(nF, nL, C.c_float(s), e, p, mx, mn, C.c_double(fx), C.c_float(baseline),
                                   _p(L), _p(R), F, w, h, shape, threads, _p(nk))
     return tot, nk
+
+
+def track_frames(params, fx, baseline, L: np.ndarray, R: np.ndarray, shape: int, threads: int, motion: dict | None = None, rad: float = 10.0):
+    """CPU baseline (restatement): extract + stereo (+ temporal matching against frame motion["prev"][f] when `motion` =
+    gtsam_vslam_b200.synth.sequence_motion(...) is given).  Returns (total matches, left key counts, temporal match counts)."""
+    L = np.ascontiguousarray(L, np.uint8); R = np.ascontiguousarray(R, np.uint8)
+    F, h, w = L.shape
+    nk = np.zeros(F, np.int32); nt = np.zeros(F, np.int32)
+    nF, nL, s, e, p, mx, mn = params
+    lib().ora_track_frames.restype = C.c_long
+    c = lambda a, dt: np.ascontiguousarray(a, dt)
+    if motion is None:
+        extra = [None, None, None, None, C.c_double(0), C.c_double(0), C.c_double(0), C.c_double(0), C.c_float(0), None]
+        keep = []
+    else:
+        keep = [c(motion["prev"], np.int32), c(motion["pose_prev"], np.float64), c(motion["to_camera"], np.float64), c(motion["to_camera_r"], np.float64)]
+        extra = [_p(a) for a in keep] + [C.c_double(motion["fx"]), C.c_double(motion["fy"]), C.c_double(motion["cx"]), C.c_double(motion["cy"]),
+                                         C.c_float(rad), _p(nt)]
+    tot = lib().ora_track_frames(nF, nL, C.c_float(s), e, p, mx, mn, C.c_double(fx), C.c_float(baseline),
+                                 _p(L), _p(R), F, w, h, shape, threads, _p(nk), *extra)
+    return tot, nk, nt

@@ -239,3 +239,24 @@ def stereo_frames(params, fx, baseline, L: np.ndarray, R: np.ndarray, shape: int
     tot = lib().ref_stereo_frames(nF, nL, C.c_float(s), e, p, mx, mn, C.c_double(fx), C.c_float(baseline),
                                   _p(L), _p(R), F, w, h, shape, threads, _p(nk))
     return tot, nk
+
+
+def track_frames(params, fx, baseline, L: np.ndarray, R: np.ndarray, shape: int, threads: int, motion: dict | None = None, rad: float = 10.0):
+    """CPU baseline on the compiled reference: extract + stereo (+ temporal matching against frame motion["prev"][f] when `motion`
+    = gtsam_vslam_b200.synth.sequence_motion(...) is given).  Returns (total matches, left key counts, temporal match counts)."""
+    L = np.ascontiguousarray(L, np.uint8); R = np.ascontiguousarray(R, np.uint8)
+    F, h, w = L.shape
+    nk = np.zeros(F, np.int32); nt = np.zeros(F, np.int32)
+    nF, nL, s, e, p, mx, mn = params
+    lib().ref_track_frames.restype = C.c_long
+    c = lambda a, dt: np.ascontiguousarray(a, dt)
+    if motion is None:
+        extra = [None, None, None, None, C.c_double(0), C.c_double(0), C.c_double(0), C.c_double(0), C.c_float(0), None]
+        keep = []
+    else:
+        keep = [c(motion["prev"], np.int32), c(motion["pose_prev"], np.float64), c(motion["to_camera"], np.float64), c(motion["to_camera_r"], np.float64)]
+        extra = [_p(a) for a in keep] + [C.c_double(motion["fx"]), C.c_double(motion["fy"]), C.c_double(motion["cx"]), C.c_double(motion["cy"]),
+                                         C.c_float(rad), _p(nt)]
+    tot = lib().ref_track_frames(nF, nL, C.c_float(s), e, p, mx, mn, C.c_double(fx), C.c_float(baseline),
+                                 _p(L), _p(R), F, w, h, shape, threads, _p(nk), *extra)
+    return tot, nk, nt

@@ -22,6 +22,10 @@ float ora_fast_atan2(float y, float x);
 void ora_sort_idx_desc(const float* key, int n, int* idx);
 int ora_fast_detect(const uint8_t* img, int w, int h, int threshold, int* xs, int* ys, int* scores, int cap);
 int ora_assign_grid(const void* kps, int n, int width, int height, int* start, int* items, float* xMult, float* yMult);
+int ora_temporal_mappoints(const void* kl, int NL, const float* depth, const double* posePrev, const double* toCamera,
+                           const double* toCameraR, double fx, double fy, double cx, double cy, int width, int height,
+                           const float* scalePyramid, int nLevels, float logScale, int* mpKey, float* predL, float* predR, int* lvlL,
+                           int* lvlR, double* wPos, float* maxScaleDist);
 }
 
 namespace {
@@ -249,52 +253,102 @@ int ref_match_lba(void* h, int M, const uint8_t* mpDesc, const float* predL, con
     return n;
 }
 
-// CPU baseline on the reference's own code: F stereo frames = extractKeysNew x2 + findStereoMatchesORB2R (+ the two key
-// grids through the restated assignKeysToGrids of liboracle.so: FeatureTracker.cpp is not compiled), i.e.
-// FeatureTracker::extractORBAndStereoMatch (src/FeatureTracker.cpp:56-70).  Same contract as ora_stereo_frames:
+// CPU baseline on the reference's own code.  Per frame: extractKeysNew x2 + findStereoMatchesORB2R + the two key grids (through
+// the restated assignKeysToGrids of liboracle.so: FeatureTracker.cpp is not compiled), i.e. FeatureTracker::extractORBAndStereoMatch
+// (src/FeatureTracker.cpp:56-70); then, when `prev` is given, the temporal step of bench.py: the map points of frame f from the
+// stereo keys of frame prev[f] (ora_temporal_mappoints: initializeMap / MapPoint::update / removeOutOfFrameMPs restated) matched
+// with the reference's own matchByProjectionRPred(rad) on fresh index arrays (src/FeatureTracker.cpp:1176-1205).
 // shape 0 = reference-shaped (frames in sequence, two extraction threads per frame, serial matcher), shape 1 = frame-parallel
 // over `threads` workers.  Uses whatever hook table is installed (default: restated scalar primitives, thread safe).
-long ref_stereo_frames(int nF, int nL, float s, int edge, int patch, int maxF, int minF, double fx, float baseline,
-                       const uint8_t* L, const uint8_t* R, int frames, int w, int h, int shape, int threads, int* nKeysOut) {
+// Returns stereo matches + temporal matches (so the work cannot be optimised away).
+long ref_track_frames(int nF, int nL, float s, int edge, int patch, int maxF, int minF, double fx, float baseline,
+                      const uint8_t* L, const uint8_t* R, int frames, int w, int h, int shape, int threads, int* nKeysOut,
+                      const int* prev, const double* posePrev, const double* toCamera, const double* toCameraR, double cfx, double cfy,
+                      double ccx, double ccy, float rad, int* nTemporalOut) {
     std::atomic<long> total{0};
+    std::vector<TrackedKeys> all(prev ? frames : 0);
     auto one = [&](int f, bool twoThreads) {
         ExtractorPtr feL = std::make_shared<FeatureExtractor>(nF, nL, s, edge, patch, maxF, minF);
         ExtractorPtr feR = std::make_shared<FeatureExtractor>(nF, nL, s, edge, patch, maxF, minF);
         Matcher* m = (Matcher*)ref_matcher_create(&feL, &feR, fx, baseline, h);
         cv::Mat li(h, w, CV_8UC1, (void*)(L + (size_t)f * w * h)), ri(h, w, CV_8UC1, (void*)(R + (size_t)f * w * h));
-        TrackedKeys keys;
-        std::vector<cv::KeyPoint> rightKeys;
-        cv::Mat rightDesc;
+        TrackedKeys local;
+        TrackedKeys& keys = prev ? all[f] : local;
         if (twoThreads) {
             std::thread a([&] { feL->extractKeysNew(li, keys.keyPoints, keys.Desc); });
-            std::thread b([&] { feR->extractKeysNew(ri, rightKeys, rightDesc); });
+            std::thread b([&] { feR->extractKeysNew(ri, keys.rightKeyPoints, keys.rightDesc); });
             a.join(); b.join();
         } else {
             feL->extractKeysNew(li, keys.keyPoints, keys.Desc);
-            feR->extractKeysNew(ri, rightKeys, rightDesc);
+            feR->extractKeysNew(ri, keys.rightKeyPoints, keys.rightDesc);
         }
-        m->fm->findStereoMatchesORB2R(li, ri, rightDesc, rightKeys, keys);
-        const int nl = (int)keys.keyPoints.size(), nr = (int)rightKeys.size();
-        std::vector<int> start(64 * (64 * h / w + 2) + 1), items(std::max(1, std::max(nl, nr)));
+        m->fm->findStereoMatchesORB2R(li, ri, keys.rightDesc, keys.rightKeyPoints, keys);
+        const int nl = (int)keys.keyPoints.size(), nr = (int)keys.rightKeyPoints.size();
+        const int yGrids = (int)std::ceil(64.f / ((float)w / (float)h));
+        std::vector<int> start(64 * (yGrids + 1) + 1), items(std::max(1, std::max(nl, nr)));
         float xm, ym;
         ora_assign_grid(keys.keyPoints.data(), nl, w, h, start.data(), items.data(), &xm, &ym);
-        ora_assign_grid(rightKeys.data(), nr, w, h, start.data(), items.data(), &xm, &ym);
+        if (prev) keys.lkeyGrid = gridFromCsr(start.data(), items.data(), yGrids, 64);
+        ora_assign_grid(keys.rightKeyPoints.data(), nr, w, h, start.data(), items.data(), &xm, &ym);
+        if (prev) { keys.rkeyGrid = gridFromCsr(start.data(), items.data(), yGrids, 64); keys.xGrids = 64; keys.yGrids = yGrids; keys.xMult = xm; keys.yMult = ym; }
         long matched = 0;
         for (int v : keys.rightIdxs) matched += v >= 0;
         total += matched;
         if (nKeysOut) nKeysOut[f] = nl;
         ref_matcher_destroy(m);
     };
-    if (shape == 0) {
-        for (int f = 0; f < frames; f++) one(f, true);
-    } else {
+    auto temporal = [&](int f) {
+        if (nTemporalOut) nTemporalOut[f] = 0;
+        const int p = prev[f];
+        if (p < 0) return;
+        ExtractorPtr feL = std::make_shared<FeatureExtractor>(nF, nL, s, edge, patch, maxF, minF);
+        Matcher* m = (Matcher*)ref_matcher_create(&feL, &feL, fx, baseline, h);
+        const TrackedKeys& pk = all[p];
+        TrackedKeys& keys = all[f];
+        const int np = (int)pk.keyPoints.size();
+        std::vector<int> key(std::max(np, 1)), ll(std::max(np, 1)), lr(std::max(np, 1));
+        std::vector<float> pl(2 * std::max(np, 1)), pr(2 * std::max(np, 1));
+        const float logScale = (float)std::log((double)s);
+        const int M = ora_temporal_mappoints(pk.keyPoints.data(), np, pk.estimatedDepth.data(), posePrev + 16 * f, toCamera + 16 * f,
+                                             toCameraR + 16 * f, cfx, cfy, ccx, ccy, w, h, feL->scalePyramid.data(), nL, logScale, key.data(),
+                                             pl.data(), pr.data(), ll.data(), lr.data(), nullptr, nullptr);
+        std::vector<MapPoint*> mps(M);
+        cv::KeyPoint obs;
+        for (int i = 0; i < M; ++i) {
+            MapPoint* mp = new MapPoint(Eigen::Vector4d(0, 0, 0, 1), pk.Desc.row(key[i]), obs, 0, (unsigned long)i);
+            mp->predL = cv::Point2f(pl[2 * i], pl[2 * i + 1]); mp->predR = cv::Point2f(pr[2 * i], pr[2 * i + 1]);
+            mp->scaleLevelL = ll[i]; mp->scaleLevelR = lr[i]; mp->inFrame = true; mp->inFrameR = true;
+            mps[i] = mp;
+        }
+        std::vector<int> mL(keys.keyPoints.size(), -1), mR(keys.rightKeyPoints.size(), -1);
+        std::vector<std::pair<int, int>> pairs(M, std::make_pair(-1, -1));
+        const int n = m->fm->matchByProjectionRPred(mps, keys, mL, mR, pairs, rad);
+        for (MapPoint* mp : mps) delete mp;
+        total += n;
+        if (nTemporalOut) nTemporalOut[f] = n;
+        ref_matcher_destroy(m);
+    };
+    auto parallel = [&](auto&& fn) {
         std::atomic<int> next{0};
         std::vector<std::thread> pool;
         for (int t = 0; t < std::max(1, threads); t++)
-            pool.emplace_back([&] { for (int f; (f = next++) < frames;) one(f, false); });
+            pool.emplace_back([&] { for (int f; (f = next++) < frames;) fn(f); });
         for (auto& t : pool) t.join();
+    };
+    if (shape == 0) {
+        for (int f = 0; f < frames; f++) one(f, true);
+        if (prev) for (int f = 0; f < frames; f++) temporal(f);
+    } else {
+        parallel([&](int f) { one(f, false); });
+        if (prev) parallel(temporal);
     }
     return total.load();
+}
+
+long ref_stereo_frames(int nF, int nL, float s, int edge, int patch, int maxF, int minF, double fx, float baseline,
+                       const uint8_t* L, const uint8_t* R, int frames, int w, int h, int shape, int threads, int* nKeysOut) {
+    return ref_track_frames(nF, nL, s, edge, patch, maxF, minF, fx, baseline, L, R, frames, w, h, shape, threads, nKeysOut, nullptr, nullptr,
+                            nullptr, nullptr, 0, 0, 0, 0, 0.f, nullptr);
 }
 
 int ref_descriptor_distance(const uint8_t* a, const uint8_t* b) {
