@@ -268,9 +268,10 @@ class FeatureExtractor:
         _check(self._lib.gvs_extractor_sync(self.h))
 
     def offsets(self, n: int) -> np.ndarray:
-        off = np.zeros(n + 1, np.int32)
+        """Dense key offsets of the first n images of the last batch (n + 1 entries)."""
+        off = np.zeros(self.max_images + 1, np.int32)   # the C call writes one entry per image of the last batch, plus one
         _check(self._lib.gvs_extract_offsets(self.h, _p(off)))
-        return off
+        return off[:n + 1].copy()
 
     def download(self, first: int, count: int, total: int):
         kp = np.zeros(max(total, 1), KEYPOINT_DTYPE)

@@ -225,7 +225,9 @@ static void invalidateGraphs(gvs_extractor* fe) {
 // size is captured once into a CUDA graph and replayed.  All kernel arguments are fixed per handle and batch size.
 constexpr int kGraphMaxImages = 8;
 
-int runExtract(gvs_extractor* fe, int n) {
+// rerun = the same resident input is processed again (a parity tap was switched on): the results are the same, so the batch
+// generation, which the matcher compares, stays
+int runExtract(gvs_extractor* fe, int n, bool rerun = false) {
     cudaStream_t s = fe->stream;
     static const bool noGraph = getenv("GVS_NO_GRAPH") != nullptr;
     // (a caller's stream that is itself being captured takes the plain launches: they become part of the caller's graph)
@@ -257,7 +259,7 @@ int runExtract(gvs_extractor* fe, int n) {
     GVS_CUDA_OK(cudaEventRecord(fe->doneEvent, s));
     GVS_CUDA_OK(cudaGetLastError());
     fe->lastN = n;
-    ++fe->generation;
+    if (!rerun) ++fe->generation;
     fe->pending = true;
     fe->launchesTotal += fe->launches;
     return GVS_OK;
@@ -686,7 +688,7 @@ int gvs_debug_level_candidates(gvs_extractor* fe, int image, int level, int32_t*
         GVS_CUDA_OK(cudaStreamSynchronize(fe->stream));
         GVS_CUDA_OK(devAlloc(&fe->orderedDbg, (size_t)fe->maxImages * fe->g.candPerImage));
         invalidateGraphs(fe);
-        int rc = runExtract(fe, fe->lastN);
+        int rc = runExtract(fe, fe->lastN, true);
         if (rc) return rc;
     }
     int rc = syncExtract(fe);
@@ -788,7 +790,7 @@ int gvs_matcher_create(gvs_matcher** out, gvs_extractor* feL, gvs_extractor* feR
     if (image_height < 1) return fail(GVS_ERR_INVALID, "bad image_height");
     DeviceGuard deviceGuard(feL->device);
     gvs_matcher* m = new gvs_matcher();
-    m->L = feL; m->R = feR; m->fx = fx; m->baseline = baseline; m->imageHeight = image_height;
+    m->L = feL; m->R = feR; m->device = feL->device; m->fx = fx; m->baseline = baseline; m->imageHeight = image_height;
     {   // key grid: 64 columns, ceil(64 / (w/h)) rows (src/FeatureTracker.cpp:30-34); sized for this handle's image shape
         const int yG = (int)std::ceil((float)GVS_GRID_X / ((float)feL->width / (float)feL->height));
         if (yG > gvs_matcher::kMaxGridRows) { delete m; return fail(GVS_ERR_INVALID, "image taller than 8x its width is not supported"); }
@@ -817,8 +819,10 @@ int gvs_matcher_create(gvs_matcher** out, gvs_extractor* feL, gvs_extractor* feR
 
 int gvs_matcher_destroy(gvs_matcher* m) {
     if (!m) return GVS_OK;
-    DeviceGuard deviceGuard(m->L->device);
-    cudaStreamSynchronize(m->L->stream);
+    // (the extractors may be gone already when handles are torn down in arbitrary order, e.g. at interpreter exit: only the
+    // matcher's own state is touched here)
+    DeviceGuard deviceGuard(m->device);
+    cudaDeviceSynchronize();
     cudaFree(m->rightIdxs); cudaFree(m->leftIdxs); cudaFree(m->sadBest); cudaFree(m->sortScratch); cudaFree(m->depth); cudaFree(m->close);
     cudaFree(m->cellStartL); cudaFree(m->cellStartR); cudaFree(m->itemsL); cudaFree(m->itemsR); cudaFree(m->pj);
     cudaFree(m->pool); cudaFree(m->pjStatus);

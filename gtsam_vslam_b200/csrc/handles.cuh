@@ -104,6 +104,7 @@ struct gvs_extractor {
 struct gvs_matcher {
     gvs_extractor* L = nullptr;
     gvs_extractor* R = nullptr;
+    int device = 0;
     double fx = 0;
     float baseline = 0;
     int imageHeight = 0;

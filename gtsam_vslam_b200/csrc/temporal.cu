@@ -7,15 +7,19 @@
 //
 // The reference matcher is greedy over map points in index order.  Two phases keep that order:
 //   phase 1 (projb_candidates_kernel, one warp per (frame, map point, side)): walks the key-grid window in the reference's
-//     order (grid row, then one contiguous CSR range per row) and reduces the ordered candidate list to the only three
-//     candidates the best / second-best rule can depend on (App. A.9): the first minimum p, the first minimum of the prefix
-//     [0, p) and the first minimum of the suffix (p, end).  Nothing is stored per candidate: the window is enumerated twice
-//     (the second pass hits L1), so there is no candidate pool and no capacity to overflow.  Keys that are matched before the
-//     call (in-out matchedIdxs) are skipped here already: entries only ever change from -1 to >= 0 during a call.
+//     order (grid row, then one contiguous CSR range per row; the rows' ranges are fetched by different lanes and the window is
+//     flattened so that a typical window is ONE round of 32 lanes) and keeps the four smallest keys (dist << 20 | position in
+//     the candidate list).  The best / second-best rule (src/FeatureMatcher.cpp:281-302, strict <) only ever depends on the TWO
+//     smallest keys of the list: the best is the first occurrence of the minimum, and the second best is the smallest key among
+//     the others (a prefix element with the second's distance would have the smaller key, so "prefix minimum unless the suffix
+//     is strictly smaller" of SURVEY App. A.9 is the same rule).  Four are kept so that phase 2 can drop candidates that get
+//     matched in the meantime.  Nothing is stored per candidate: no candidate pool, no capacity to overflow.  Keys that are
+//     matched before the call (in-out matchedIdxs) are skipped here already: entries only change from -1 to >= 0 during a call.
 //   phase 2 (projb_resolve_kernel, one CTA of 32 warps per frame): walks the frame's map points in order, 32 at a time.  A map
-//     point whose three deciding candidates are all still free keeps its phase-1 result; otherwise its warp enumerates the
-//     window again with the skip test.  The longest prefix of the chunk in which no map point takes a deciding candidate of
-//     a later one is committed; the rest is re-evaluated.  matchedIdxsL/R of the frame live in shared memory during the walk.
+//     point decides from the first two of its stored candidates that are still free; if fewer than two are left of a list that
+//     was longer than four, its warp enumerates the window again with the skip test.  The longest prefix of the chunk in which
+//     no map point takes a deciding candidate of a later one is committed; the rest is re-evaluated.  matchedIdxsL/R of the
+//     frame live in shared memory during the walk.
 #include <cmath>
 #include <cstring>
 
@@ -31,7 +35,8 @@ __device__ __forceinline__ int tDist(unsigned e) { return (int)((e >> 16) & 0x1f
 __device__ __forceinline__ int tLev(unsigned e) { return (int)((e >> 25) & 0xf); }
 constexpr unsigned kNoCand = 0xffffffffu;
 
-struct TRec { unsigned eBest, ePre, eSuf; };   // per (map point, side)
+constexpr int kTopK = 4;
+struct TRec { unsigned e[kTopK]; int n; };   // per (map point, side): the kTopK smallest keys' entries in key order, n = list length
 
 struct ProjBatchArgs {
     int mode;                  // gvs_match_mode
@@ -99,90 +104,89 @@ struct TSide {
     const int* items;
 };
 
-// One warp: the ordered candidate list of a window reduced to (eBest, ePre, eSuf).  `skip` (optional) = matchedIdxs of the side,
-// indexed by key: entries >= 0 are not candidates (src/FeatureMatcher.cpp:283,323,418,485).
+// One warp: the ordered candidate list of a window reduced to its kTopK smallest keys (entries in key order) and its length.
+// `skip` (optional) = matchedIdxs of the side, indexed by key: entries >= 0 are not candidates (src/FeatureMatcher.cpp:283,323,
+// 418,485).
 __device__ void tScanWindow(const TSide& sd, const TWindow& w, int xGrids, const uint4& q0, const uint4& q1, const int* skip,
-                            bool radiusMode, int lane, unsigned& eBest, unsigned& ePre, unsigned& eSuf) {
-    eBest = ePre = eSuf = kNoCand;
+                            bool radiusMode, int lane, TRec& rec) {
+#pragma unroll
+    for (int i = 0; i < kTopK; i++) rec.e[i] = kNoCand;
+    rec.n = 0;
     if (!w.ok) return;
     unsigned lt;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt));
-    auto passes = [&](int idx) -> int {
-        const gvs_keypoint* k = sd.kps + idx;
-        const int oct = k->octave;
-        if (oct > w.lvl + 1 || oct < w.lvl - 1) return -1;
-        if (skip && skip[idx] >= 0) return -1;
-        const float kx = k->x, ky = k->y;
-        const float dx = __fsub_rn(kx, w.trackX), dy = __fsub_rn(ky, w.trackY);
-        if (!(fabsf(dx) < w.radius && fabsf(dy) < w.radius)) return -1;
-        if (radiusMode) {  // Converter::checkPixelParallax (include/Conversions.h:140-144)
-            const double ex = (double)w.trackX - (double)kx, ey = (double)w.trackY - (double)ky;
-            if (!(sqrt(ex * ex + ey * ey) > 10.0)) return -1;
-        }
-        return oct;
-    };
-    auto dist256 = [&](int idx) -> int {
-        const uint4* dk = reinterpret_cast<const uint4*>(sd.descs + (size_t)idx * 32);
-        const uint4 k0 = __ldg(dk), k1 = __ldg(dk + 1);
-        return __popc(q0.x ^ k0.x) + __popc(q0.y ^ k0.y) + __popc(q0.z ^ k0.z) + __popc(q0.w ^ k0.w) +
-               __popc(q1.x ^ k1.x) + __popc(q1.y ^ k1.y) + __popc(q1.z ^ k1.z) + __popc(q1.w ^ k1.w);
-    };
-    // pass 1: first minimum (key = dist << 20 | position in the list)
-    unsigned kb = kNoCand, eb = kNoCand;
+    unsigned k[kTopK], e[kTopK];   // this lane's smallest keys, ascending
+#pragma unroll
+    for (int i = 0; i < kTopK; i++) { k[i] = kNoCand; e[i] = kNoCand; }
     int run = 0;
-    for (int row = w.minY; row <= w.maxY; row++) {
-        const int p0 = sd.cellStart[row * xGrids + w.minX], p1 = sd.cellStart[row * xGrids + w.maxX + 1];
-        for (int base = p0; base < p1; base += 32) {
-            const int p = base + lane;
-            int idx = -1, lev = -1;
-            if (p < p1) { idx = sd.items[p]; lev = passes(idx); }
-            const unsigned m = __ballot_sync(0xffffffffu, lev >= 0);
-            if (lev >= 0) {
-                const int d = dist256(idx);
-                const unsigned key = ((unsigned)d << 20) | (unsigned)(run + __popc(m & lt));
-                if (key < kb) { kb = key; eb = tPack(idx, d, lev); }
-            }
-            run += __popc(m);
+    for (int row0 = w.minY; row0 <= w.maxY; row0 += 32) {
+        // lane r owns grid row row0 + r: its CSR range [p0, p1) and the exclusive prefix of the lengths
+        const int nRows = min(32, w.maxY - row0 + 1);
+        int p0 = 0, len = 0;
+        if (lane < nRows) {
+            p0 = sd.cellStart[(row0 + lane) * xGrids + w.minX];
+            len = sd.cellStart[(row0 + lane) * xGrids + w.maxX + 1] - p0;
         }
-    }
-    if (run == 0) return;
-    const unsigned kbAll = tWarpMin(kb);
-    {
-        const unsigned owner = __ballot_sync(0xffffffffu, kb == kbAll);
-        eBest = __shfl_sync(0xffffffffu, eb, __ffs(owner) - 1);
-    }
-    if (run == 1) return;
-    // pass 2: first minimum of the prefix [0, p) and of the suffix (p, end)
-    const int pBest = (int)(kbAll & 0xfffff);
-    unsigned kp = kNoCand, ep = kNoCand, ks = kNoCand, es = kNoCand;
-    run = 0;
-    for (int row = w.minY; row <= w.maxY; row++) {
-        const int p0 = sd.cellStart[row * xGrids + w.minX], p1 = sd.cellStart[row * xGrids + w.maxX + 1];
-        for (int base = p0; base < p1; base += 32) {
-            const int p = base + lane;
+        int incl = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        for (int base = 0; base < total; base += 32) {
+            const int s = base + lane;
+            // row of flattened slot s = number of rows whose inclusive prefix is <= s
+            int r = 0;
+            for (int j = 0; j < nRows; j++) r += __shfl_sync(0xffffffffu, incl, j) <= s;
+            r = min(r, nRows - 1);
+            const int rp0 = __shfl_sync(0xffffffffu, p0, r), rex = __shfl_sync(0xffffffffu, incl - len, r);
             int idx = -1, lev = -1;
-            if (p < p1) { idx = sd.items[p]; lev = passes(idx); }
+            float kx = 0.f, ky = 0.f;
+            if (s < total) {
+                idx = sd.items[rp0 + (s - rex)];
+                const gvs_keypoint* kp = sd.kps + idx;
+                lev = kp->octave;
+                kx = kp->x; ky = kp->y;
+                if (lev > w.lvl + 1 || lev < w.lvl - 1) lev = -1;
+                else if (skip && skip[idx] >= 0) lev = -1;
+                else {
+                    const float dx = __fsub_rn(kx, w.trackX), dy = __fsub_rn(ky, w.trackY);
+                    if (!(fabsf(dx) < w.radius && fabsf(dy) < w.radius)) lev = -1;
+                    else if (radiusMode) {  // Converter::checkPixelParallax (include/Conversions.h:140-144)
+                        const double ex = (double)w.trackX - (double)kx, ey = (double)w.trackY - (double)ky;
+                        if (!(sqrt(ex * ex + ey * ey) > 10.0)) lev = -1;
+                    }
+                }
+            }
             const unsigned m = __ballot_sync(0xffffffffu, lev >= 0);
             if (lev >= 0) {
-                const int pos = run + __popc(m & lt);
-                if (pos != pBest) {
-                    const int d = dist256(idx);
-                    const unsigned key = ((unsigned)d << 20) | (unsigned)pos;
-                    if (pos < pBest) { if (key < kp) { kp = key; ep = tPack(idx, d, lev); } }
-                    else if (key < ks) { ks = key; es = tPack(idx, d, lev); }
+                const uint4* dk = reinterpret_cast<const uint4*>(sd.descs + (size_t)idx * 32);
+                const uint4 k0 = __ldg(dk), k1 = __ldg(dk + 1);
+                const int d = __popc(q0.x ^ k0.x) + __popc(q0.y ^ k0.y) + __popc(q0.z ^ k0.z) + __popc(q0.w ^ k0.w) +
+                              __popc(q1.x ^ k1.x) + __popc(q1.y ^ k1.y) + __popc(q1.z ^ k1.z) + __popc(q1.w ^ k1.w);
+                unsigned key = ((unsigned)d << 20) | (unsigned)(run + __popc(m & lt));
+                unsigned ent = tPack(idx, d, lev);
+                // insert into the lane's ascending list
+#pragma unroll
+                for (int i = 0; i < kTopK; i++) {
+                    if (key < k[i]) { const unsigned tk = k[i], te = e[i]; k[i] = key; e[i] = ent; key = tk; ent = te; }
                 }
             }
             run += __popc(m);
         }
     }
-    const unsigned kpAll = tWarpMin(kp), ksAll = tWarpMin(ks);
-    if (kpAll != kNoCand) {
-        const unsigned owner = __ballot_sync(0xffffffffu, kp == kpAll);
-        ePre = __shfl_sync(0xffffffffu, ep, __ffs(owner) - 1);
-    }
-    if (ksAll != kNoCand) {
-        const unsigned owner = __ballot_sync(0xffffffffu, ks == ksAll);
-        eSuf = __shfl_sync(0xffffffffu, es, __ffs(owner) - 1);
+    rec.n = run;
+    if (run == 0) return;
+    // the kTopK smallest keys of the warp, in order: repeated warp minimum, the owner advances its list
+#pragma unroll
+    for (int i = 0; i < kTopK; i++) {
+        const unsigned g = tWarpMin(k[0]);
+        if (g == kNoCand) break;
+        const int owner = __ffs(__ballot_sync(0xffffffffu, k[0] == g)) - 1;
+        rec.e[i] = __shfl_sync(0xffffffffu, e[0], owner);
+        if (lane == owner) {
+#pragma unroll
+            for (int j = 0; j + 1 < kTopK; j++) { k[j] = k[j + 1]; e[j] = e[j + 1]; }
+            k[kTopK - 1] = kNoCand; e[kTopK - 1] = kNoCand;
+        }
     }
 }
 
@@ -228,178 +232,184 @@ projb_candidates_kernel(const ProjBatchArgs a) {
     const int* skipR = stereo ? a.matchedR + (a.offR[frame] - a.offR[a.frame0]) : nullptr;
     for (int wi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); wi < M * nSides; wi += warpsPerRow) {
         const int mpi = mp0 + wi / nSides, side = wi - (wi / nSides) * nSides;
-        TRec rec{kNoCand, kNoCand, kNoCand};
+        TRec rec;
+#pragma unroll
+        for (int i = 0; i < kTopK; i++) rec.e[i] = kNoCand;
+        rec.n = 0;
         // a map point that is matched already is skipped by the walk (:262,:399); matchByRadius has no such test
         const bool skipMP = a.mode != GVS_MATCH_RADIUS && (a.matches[2 * (size_t)mpi] >= 0 || a.matches[2 * (size_t)mpi + 1] >= 0);
         if (!skipMP) {
             const TTask t = tMakeTask(a, frame, mpi, side, a.status);
-            tScanWindow(t.sd, t.w, a.xGrids, t.q0, t.q1, side ? skipR : skipL, a.mode == GVS_MATCH_RADIUS, lane, rec.eBest, rec.ePre, rec.eSuf);
+            tScanWindow(t.sd, t.w, a.xGrids, t.q0, t.q1, side ? skipR : skipL, a.mode == GVS_MATCH_RADIUS, lane, rec);
         }
         if (lane == 0) a.recs[2 * (size_t)mpi + side] = rec;
     }
 }
 
 struct TDecision { int bestDist, bestIdx, bestLev, bestLev2, secDist; };
-__device__ __forceinline__ TDecision tDecide(unsigned eBest, unsigned ePre, unsigned eSuf) {
+// best = smallest remaining key, second best = second smallest (see the header of this file)
+__device__ __forceinline__ TDecision tDecide(unsigned e1, unsigned e2) {
     TDecision d{256, -1, -1, -1, 256};
-    if (eBest == kNoCand) return d;
-    d.bestDist = tDist(eBest); d.bestIdx = tIdx(eBest); d.bestLev = tLev(eBest);
-    if (ePre != kNoCand) { d.secDist = tDist(ePre); d.bestLev2 = tLev(ePre); }
-    if (eSuf != kNoCand && tDist(eSuf) < d.secDist) { d.secDist = tDist(eSuf); d.bestLev2 = tLev(eSuf); }
+    if (e1 == kNoCand) return d;
+    d.bestDist = tDist(e1); d.bestIdx = tIdx(e1); d.bestLev = tLev(e1);
+    if (e2 != kNoCand) { d.secDist = tDist(e2); d.bestLev2 = tLev(e2); }
     return d;
 }
+// the first two stored candidates that are still free; false = the stored list cannot answer (it was truncated and fewer than
+// two of its entries are left): enumerate the window again
+__device__ __forceinline__ bool tFirstTwo(const TRec& r, const int* matched, unsigned& e1, unsigned& e2) {
+    e1 = e2 = kNoCand;
+#pragma unroll
+    for (int i = 0; i < kTopK; i++) {
+        const unsigned e = r.e[i];
+        if (e == kNoCand || matched[tIdx(e)] >= 0) continue;
+        if (e1 == kNoCand) e1 = e; else if (e2 == kNoCand) e2 = e;
+    }
+    return e2 != kNoCand || r.n <= kTopK;
+}
 
-constexpr int kTResolveWarps = 32;
-
-__global__ void __launch_bounds__(32 * kTResolveWarps)
+// phase 2: ONE WARP per frame, lane = map point of the current chunk of 32.  Deciding from the stored candidates is a few
+// shared-memory look-ups per map point, so a thread per map point is enough; only the rare re-enumeration of a window is done
+// by the whole warp.  The walk is serial per frame (that is the reference's semantics), frames run in parallel.
+__global__ void __launch_bounds__(32)
 projb_resolve_kernel(const ProjBatchArgs a) {
     extern __shared__ int sMatched[];  // capL + capR
-    __shared__ int sDec[kTResolveWarps][6];                          // key ids of the deciding candidates (left 0..2, right 3..5), -1 = none
-    __shared__ int sTakeL[kTResolveWarps], sTakeR[kTResolveWarps];   // keys the map point marks if accepted (-1 = none)
-    __shared__ int sOut0[kTResolveWarps], sOut1[kTResolveWarps];     // its matchesIdxs pair
-    __shared__ int sAccept[kTResolveWarps];
-    __shared__ int sDone, sTotal;
     const int f = blockIdx.x, frame = a.frame0 + f;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lane = threadIdx.x;
     const bool stereo = a.mode == GVS_MATCH_STEREO_PRED;
     const int mp0 = a.mpOff[f], M = a.mpOff[f + 1] - mp0;
     const int oL = a.offL[frame], NL = a.offL[frame + 1] - oL;
     const int oR = stereo ? a.offR[frame] : 0, NR = stereo ? a.offR[frame + 1] - oR : 0;
-    if (M <= 0) { if (tid == 0) a.nMatches[f] = 0; return; }
-    if (NL > a.capL || NR > a.capR) { if (tid == 0) { atomicOr(a.status, kStatOutputOverflow); a.nMatches[f] = 0; } return; }
+    if (M <= 0) { if (lane == 0) a.nMatches[f] = 0; return; }
+    if (NL > a.capL || NR > a.capR) { if (lane == 0) { atomicOr(a.status, kStatOutputOverflow); a.nMatches[f] = 0; } return; }
     int* mL = sMatched;
     int* mR = sMatched + a.capL;
     int* gML = a.matchedL + (oL - a.offL[a.frame0]);
     int* gMR = stereo ? a.matchedR + (oR - a.offR[a.frame0]) : nullptr;
-    for (int i = tid; i < NL; i += blockDim.x) mL[i] = gML[i];
-    for (int i = tid; i < NR; i += blockDim.x) mR[i] = gMR[i];
-    if (tid == 0) sTotal = 0;
+    for (int i = lane; i < NL; i += 32) mL[i] = gML[i];
+    for (int i = lane; i < NR; i += 32) mR[i] = gMR[i];
+    __syncwarp();
     const int* leftIdxs = stereo ? a.leftIdxs + oR : nullptr;
     const int* rightIdxs = stereo ? a.rightIdxs + oL : nullptr;
-    auto taken = [&](unsigned e, const int* m) { return e != kNoCand && m[tIdx(e)] >= 0; };
+    const bool radiusMode = a.mode == GVS_MATCH_RADIUS;
     auto keyOf = [&](unsigned e) { return e == kNoCand ? -1 : tIdx(e); };
-    for (int base = 0; base < M; base += kTResolveWarps) {
-        const int chunk = min(kTResolveWarps, M - base);
-        __syncthreads();
-        if (tid == 0) sDone = 0;
-        bool first = true;
-        while (true) {
-            __syncthreads();
-            const int done = sDone;
-            if (done >= chunk) break;
-            // ---- (A) tentative decisions of the pending map points whose inputs changed
-            if (warp >= done && warp < chunk) {
-                bool redo = first;
-                if (!first) {
+    int total = 0;
+    for (int base = 0; base < M; base += 32) {
+        const int chunk = min(32, M - base);
+        const int mpi = mp0 + base + lane;
+        TRec rl, rr;
 #pragma unroll
-                    for (int q = 0; q < 6; q++) {
-                        const int kq = sDec[warp][q];
-                        if (kq >= 0 && (q < 3 ? mL[kq] : mR[kq]) >= 0) redo = true;
+        for (int i = 0; i < kTopK; i++) { rl.e[i] = kNoCand; rr.e[i] = kNoCand; }
+        rl.n = 0; rr.n = 0;
+        bool skipMP = true;
+        if (lane < chunk) {
+            // a map point that is matched already is skipped by the walk (:262,:399); matchByRadius has no such test
+            skipMP = !radiusMode && (a.matches[2 * (size_t)mpi] >= 0 || a.matches[2 * (size_t)mpi + 1] >= 0);
+            rl = a.recs[2 * (size_t)mpi];
+            if (stereo) rr = a.recs[2 * (size_t)mpi + 1];
+        }
+        int done = 0;
+        while (done < chunk) {
+            const bool pend = lane >= done && lane < chunk && !skipMP;
+            // ---- (A) tentative decision of every pending map point against the current matched arrays
+            unsigned l1 = kNoCand, l2 = kNoCand, r1 = kNoCand, r2 = kNoCand;
+            bool needL = false, needR = false;
+            if (pend) {
+                needL = !tFirstTwo(rl, mL, l1, l2);
+                if (stereo) needR = !tFirstTwo(rr, mR, r1, r2);
+            }
+            for (unsigned nm = __ballot_sync(0xffffffffu, needL); nm; nm &= nm - 1) {   // rare: the stored list ran dry
+                const int src = __ffs(nm) - 1;
+                const TTask t = tMakeTask(a, frame, mp0 + base + src, 0, a.status);
+                TRec fresh;
+                tScanWindow(t.sd, t.w, a.xGrids, t.q0, t.q1, mL, radiusMode, lane, fresh);
+                if (lane == src) { rl = fresh; l1 = fresh.e[0]; l2 = fresh.e[1]; }
+            }
+            for (unsigned nm = __ballot_sync(0xffffffffu, needR); nm; nm &= nm - 1) {
+                const int src = __ffs(nm) - 1;
+                const TTask t = tMakeTask(a, frame, mp0 + base + src, 1, a.status);
+                TRec fresh;
+                tScanWindow(t.sd, t.w, a.xGrids, t.q0, t.q1, mR, false, lane, fresh);
+                if (lane == src) { rr = fresh; r1 = fresh.e[0]; r2 = fresh.e[1]; }
+            }
+            int accept = 0, takeL = -1, takeR = -1, out0 = -1, out1 = -1;
+            if (pend) {
+                TDecision d = tDecide(l1, l2);
+                bool right = false;
+                int bestIdxR = -1;
+                if (stereo) {
+                    const TDecision dr = tDecide(r1, r2);
+                    bestIdxR = dr.bestIdx;
+                    if (d.bestDist > dr.bestDist) {   // :353-360
+                        d.bestDist = dr.bestDist; d.secDist = dr.secDist; d.bestLev = dr.bestLev; d.bestLev2 = dr.bestLev2;
+                        right = true;
                     }
                 }
-                if (redo) {
-                    const int mpi = mp0 + base + warp;
-                    const bool skipMP = a.mode != GVS_MATCH_RADIUS && (a.matches[2 * (size_t)mpi] >= 0 || a.matches[2 * (size_t)mpi + 1] >= 0);
-                    int accept = 0, takeL = -1, takeR = -1, out0 = -1, out1 = -1;
-                    unsigned eb = kNoCand, ep = kNoCand, es = kNoCand, rb = kNoCand, rp = kNoCand, rs = kNoCand;
-                    if (!skipMP) {
-                        const TRec rl = a.recs[2 * (size_t)mpi];
-                        eb = rl.eBest; ep = rl.ePre; es = rl.eSuf;
-                        if (taken(eb, mL) || taken(ep, mL) || taken(es, mL)) {
-                            const TTask t = tMakeTask(a, frame, mpi, 0, a.status);
-                            tScanWindow(t.sd, t.w, a.xGrids, t.q0, t.q1, mL, a.mode == GVS_MATCH_RADIUS, lane, eb, ep, es);
-                        }
-                        TDecision d = tDecide(eb, ep, es);
-                        bool right = false;
-                        int bestIdxR = -1;
-                        if (stereo) {
-                            const TRec rr = a.recs[2 * (size_t)mpi + 1];
-                            rb = rr.eBest; rp = rr.ePre; rs = rr.eSuf;
-                            if (taken(rb, mR) || taken(rp, mR) || taken(rs, mR)) {
-                                const TTask t = tMakeTask(a, frame, mpi, 1, a.status);
-                                tScanWindow(t.sd, t.w, a.xGrids, t.q0, t.q1, mR, false, lane, rb, rp, rs);
-                            }
-                            const TDecision dr = tDecide(rb, rp, rs);
-                            bestIdxR = dr.bestIdx;
-                            if (d.bestDist > dr.bestDist) {
-                                d.bestDist = dr.bestDist; d.secDist = dr.secDist; d.bestLev = dr.bestLev; d.bestLev2 = dr.bestLev2;
-                                right = true;
-                            }
-                        }
-                        bool ok;
-                        if (a.mode == GVS_MATCH_MONO) {
-                            // (ratioProj + 0.1) * secDist is evaluated in double (float + double), threshold 100 + 50 (:442-447)
-                            const double thr = ((double)0.8f + 0.1) * (double)d.secDist;
-                            ok = d.bestDist <= 150 && !(d.bestLev == d.bestLev2 && (double)d.bestDist >= thr) &&
-                                 (d.bestLev != d.bestLev2 || (double)d.bestDist < thr);
-                        } else {
-                            const float thr = __fmul_rn(0.8f, (float)d.secDist);
-                            ok = d.bestDist <= 100 && !(d.bestLev == d.bestLev2 && (float)d.bestDist >= thr) &&
-                                 (d.bestLev != d.bestLev2 || (float)d.bestDist < thr);
-                        }
-                        if (ok) {
-                            accept = 1;
-                            if (!stereo) { takeL = d.bestIdx; out0 = d.bestIdx; }
-                            else if (right) {
-                                takeR = bestIdxR; out1 = bestIdxR;
-                                const int li = leftIdxs[bestIdxR];
-                                if (li >= 0) { out0 = li; takeL = li; }
-                            } else {
-                                takeL = d.bestIdx; out0 = d.bestIdx;
-                                const int ri = rightIdxs[d.bestIdx];
-                                if (ri >= 0) { out1 = ri; takeR = ri; }
-                            }
-                        }
-                    }
-                    if (lane == 0) {
-                        sDec[warp][0] = keyOf(eb); sDec[warp][1] = keyOf(ep); sDec[warp][2] = keyOf(es);
-                        sDec[warp][3] = keyOf(rb); sDec[warp][4] = keyOf(rp); sDec[warp][5] = keyOf(rs);
-                        sAccept[warp] = accept; sTakeL[warp] = takeL; sTakeR[warp] = takeR; sOut0[warp] = out0; sOut1[warp] = out1;
+                bool ok;
+                if (a.mode == GVS_MATCH_MONO) {
+                    // (ratioProj + 0.1) * secDist is evaluated in double (float + double), threshold 100 + 50 (:442-447)
+                    const double thr = ((double)0.8f + 0.1) * (double)d.secDist;
+                    ok = d.bestDist <= 150 && !(d.bestLev == d.bestLev2 && (double)d.bestDist >= thr) &&
+                         (d.bestLev != d.bestLev2 || (double)d.bestDist < thr);
+                } else {
+                    const float thr = __fmul_rn(0.8f, (float)d.secDist);
+                    ok = d.bestDist <= 100 && !(d.bestLev == d.bestLev2 && (float)d.bestDist >= thr) &&
+                         (d.bestLev != d.bestLev2 || (float)d.bestDist < thr);
+                }
+                if (ok) {
+                    accept = 1;
+                    if (!stereo) { takeL = d.bestIdx; out0 = d.bestIdx; }
+                    else if (right) {
+                        takeR = bestIdxR; out1 = bestIdxR;
+                        const int li = leftIdxs[bestIdxR];
+                        if (li >= 0) { out0 = li; takeL = li; }
+                    } else {
+                        takeL = d.bestIdx; out0 = d.bestIdx;
+                        const int ri = rightIdxs[d.bestIdx];
+                        if (ri >= 0) { out1 = ri; takeR = ri; }
                     }
                 }
             }
-            first = false;
-            __syncthreads();
-            // ---- (B) warp 0, lane = map point of the chunk: longest safe prefix, commit
-            if (warp == 0) {
-                bool unsafe = false;
-                int dl0 = -1, dl1 = -1, dl2 = -1, dr0 = -1, dr1 = -1, dr2 = -1;
-                if (lane < chunk) { dl0 = sDec[lane][0]; dl1 = sDec[lane][1]; dl2 = sDec[lane][2]; dr0 = sDec[lane][3]; dr1 = sDec[lane][4]; dr2 = sDec[lane][5]; }
-                for (int j = done; j < chunk - 1; j++) {
-                    if (!sAccept[j]) continue;   // (uniform)
-                    const int tl = sTakeL[j], tr = sTakeR[j];
-                    if (lane > j && lane < chunk) {
-                        if (tl >= 0 && (tl == dl0 || tl == dl1 || tl == dl2)) unsafe = true;
-                        if (tr >= 0 && (tr == dr0 || tr == dr1 || tr == dr2)) unsafe = true;
-                    }
+            // ---- (B) longest prefix of the pending lanes in which nobody takes a deciding candidate of a later lane
+            const int dl0 = keyOf(l1), dl1 = keyOf(l2), dr0 = keyOf(r1), dr1 = keyOf(r2);
+            bool unsafe = false;
+            unsigned accMask = __ballot_sync(0xffffffffu, accept != 0);
+            accMask &= ~0u << done;
+            for (unsigned am = accMask; am; am &= am - 1) {
+                const int j = __ffs(am) - 1;
+                const int tl = __shfl_sync(0xffffffffu, takeL, j), tr = __shfl_sync(0xffffffffu, takeR, j);
+                if (lane > j && pend) {
+                    if (tl >= 0 && (tl == dl0 || tl == dl1)) unsafe = true;
+                    if (tr >= 0 && (tr == dr0 || tr == dr1)) unsafe = true;
                 }
-                const unsigned um = __ballot_sync(0xffffffffu, unsafe);
-                const int upto = um ? __ffs(um) - 1 : chunk;     // lanes [done, upto) are final
-                const bool mine = lane >= done && lane < upto && sAccept[lane];
-                const int i = base + lane;                       // the reference's map point index inside the frame
-                // several committed map points may mark the same key (a stereo partner): the last one in index order wins
-                const int tl = mine ? sTakeL[lane] : -1, tr = mine ? sTakeR[lane] : -1;
-                const unsigned pl = __match_any_sync(0xffffffffu, tl >= 0 ? tl : -1 - lane);
-                const unsigned pr = __match_any_sync(0xffffffffu, tr >= 0 ? tr : -1 - lane);
-                if (tl >= 0 && (31 - __clz(pl)) == lane) mL[tl] = i;
-                if (tr >= 0 && (31 - __clz(pr)) == lane) mR[tr] = i;
-                if (mine) {
-                    int* mt = a.matches + 2 * (size_t)(mp0 + i);
-                    if (!stereo) mt[0] = sOut0[lane];
-                    else {
-                        if (sOut0[lane] >= 0) mt[0] = sOut0[lane];
-                        if (sOut1[lane] >= 0) mt[1] = sOut1[lane];
-                    }
-                }
-                const int nAcc = __popc(__ballot_sync(0xffffffffu, mine));
-                if (lane == 0) { sTotal += nAcc; sDone = upto; }
             }
+            const unsigned um = __ballot_sync(0xffffffffu, unsafe);
+            const int upto = um ? __ffs(um) - 1 : chunk;     // lanes [done, upto) are final
+            const bool mine = lane >= done && lane < upto && accept;
+            const int i = base + lane;                       // the reference's map point index inside the frame
+            // several committed map points may mark the same key (a stereo partner): the last one in index order wins
+            const int tl = mine ? takeL : -1, tr = mine ? takeR : -1;
+            const unsigned pl = __match_any_sync(0xffffffffu, tl >= 0 ? tl : -1 - lane);
+            const unsigned pr = __match_any_sync(0xffffffffu, tr >= 0 ? tr : -1 - lane);
+            if (tl >= 0 && (31 - __clz(pl)) == lane) mL[tl] = i;
+            if (tr >= 0 && (31 - __clz(pr)) == lane) mR[tr] = i;
+            if (mine) {
+                int* mt = a.matches + 2 * (size_t)mpi;
+                if (!stereo) mt[0] = out0;
+                else {
+                    if (out0 >= 0) mt[0] = out0;
+                    if (out1 >= 0) mt[1] = out1;
+                }
+            }
+            total += __popc(__ballot_sync(0xffffffffu, mine));
+            done = upto;
+            __syncwarp();
         }
     }
-    __syncthreads();
-    for (int i = tid; i < NL; i += blockDim.x) gML[i] = mL[i];
-    for (int i = tid; i < NR; i += blockDim.x) gMR[i] = mR[i];
-    if (tid == 0) a.nMatches[f] = sTotal;
+    __syncwarp();
+    for (int i = lane; i < NL; i += 32) gML[i] = mL[i];
+    for (int i = lane; i < NR; i += 32) gMR[i] = mR[i];
+    if (lane == 0) a.nMatches[f] = total;
 }
 
 static void launchProjectBatch(const ProjBatchArgs& a, int maxMpPerFrame, cudaStream_t s, int* launches) {
@@ -411,8 +421,8 @@ static void launchProjectBatch(const ProjBatchArgs& a, int maxMpPerFrame, cudaSt
     ++*launches;
     const size_t sm = (size_t)(a.capL + a.capR) * sizeof(int);
     static size_t cfg[64];
-    ensureDynamicSmem(projb_resolve_kernel, sm + 4096, cfg);   // (+ the kernel's static shared memory counts against the 48 KB default)
-    projb_resolve_kernel<<<a.nFrames, 32 * kTResolveWarps, sm, s>>>(a);
+    ensureDynamicSmem(projb_resolve_kernel, sm, cfg);
+    projb_resolve_kernel<<<a.nFrames, 32, sm, s>>>(a);
     ++*launches;
 }
 
