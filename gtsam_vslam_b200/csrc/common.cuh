@@ -1,5 +1,6 @@
 // Shared declarations of the sm_100a frontend kernels (internal; the public surface is include/gvs.h).
 #pragma once
+#include <cuda.h>   // CUtensorMap (type only: the encoder is fetched through cudaGetDriverEntryPoint, libcuda is not linked)
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -56,7 +57,7 @@ struct FastItem {
 };
 
 // Resize tables entry for one destination column / row (cv::resize INTER_LINEAR fixed point, 11 bits).
-struct ResizeTap {
+struct alignas(8) ResizeTap {   // (row taps are fetched with one 8-byte load: {ofs | a0 << 16, a1 | pad << 16})
     short ofs, a0, a1, pad;
 };
 
@@ -92,9 +93,37 @@ inline void ensureDynamicSmem(K kernel, size_t bytes, size_t* cache /* [64] zero
 
 struct StageTimer;
 
+// ---- fused pyramid (pyramid.cu): a CTA owns a tile of the coarsest level of a group of consecutive levels and produces that
+// tile and the regions of the finer levels of the group it depends on from ONE TMA load of the group's base level.
+constexpr int kPyrMaxFuse = 4;      // output levels per fused group
+constexpr int kPyrMaxGroups = 4;    // (3 + 4 + 4 covers the 11 output levels of a 12-level pyramid)
+struct PyrSpan {                    // one tile column (or tile row) of a group; index 0 = base level, k = base + k
+    short lo[kPyrMaxFuse + 1];      // first computed (base level: loaded) column / row
+    short hi[kPyrMaxFuse + 1];      // one past the last computed
+    short ownLo[kPyrMaxFuse + 1];   // the part this tile writes to global memory: [ownLo, ownHi)
+    short ownHi[kPyrMaxFuse + 1];
+    unsigned magic[kPyrMaxFuse + 1]; // column spans: 2^32 / (number of 4-column groups of the level's region) + 1
+};
+struct PyrGroup {
+    int base, nOut;                 // levels base+1 .. base+nOut are produced from level base
+    int nTx, nTy;                   // tiles
+    int spanX, spanY;               // first entries of the group in the span table
+    int boxW, boxH;                 // TMA box of the base level (bytes x rows)
+    int bufOff[kPyrMaxFuse];        // shared-memory offsets of the level buffers (0 = base level box)
+    int bufPitch[kPyrMaxFuse];
+    int smemBytes;
+};
+struct PyrPlan {
+    int nGroups;                    // 0 = the fused path is not available for this geometry (legacy kernels run)
+    PyrGroup grp[kPyrMaxGroups];
+};
+
 // ---- kernel launchers (one translation unit each) -------------------------------------------------
 void launchPyramid(const Geometry& g, uint8_t* slab, const ResizeTap* taps, const uint4* xw, const uint4* xs,
                    const unsigned short* xbase, unsigned narrowMask, int nImages, cudaStream_t s, int* launches);
+void launchPyramidFused(const Geometry& g, uint8_t* slab, const ResizeTap* taps, const uint4* xw, const uint4* xs,
+                        const unsigned short* xbase, const PyrPlan& plan, const PyrSpan* spans, const CUtensorMap* baseMaps /* per group, host */,
+                        int nImages, cudaStream_t s, int* launches);
 void launchPrepare(const Geometry& g, const uint8_t* src, int channels, const float* mapx, const float* mapy, uint8_t* slab,
                    int nImages, cudaStream_t s, int* launches);
 void launchRepack(const Geometry& g, const uint8_t* tight, uint8_t* slab, int nImages, cudaStream_t s, int* launches);

@@ -170,11 +170,130 @@ void buildTaps(const gvs_extractor* fe, std::vector<ResizeTap>& taps, int nTaps)
     }
 }
 
+// cuTensorMapEncodeTiled through the runtime (libcuda is not linked): nullptr when the driver does not offer it
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn tensorMapEncoder() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+        }
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// u8 tile map over pyramid level `level` of every image slot: (x bytes, y rows, image)
+bool encodeLevelMap(const gvs_extractor* fe, int level, int boxW, int boxH, CUtensorMap* out) {
+    EncodeTiledFn enc = tensorMapEncoder();
+    if (!enc) return false;
+    const LevelGeom& lv = fe->g.lv[level];
+    const cuuint64_t dims[3] = {(cuuint64_t)lv.pitch, (cuuint64_t)lv.h, (cuuint64_t)fe->maxImages};
+    const cuuint64_t strides[2] = {(cuuint64_t)lv.pitch, (cuuint64_t)fe->g.slabBytes};
+    const cuuint32_t box[3] = {(cuuint32_t)boxW, (cuuint32_t)boxH, 1u}, es[3] = {1u, 1u, 1u};
+    return enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, fe->slab + lv.off, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// Plan of the fused pyramid (pyramid.cu: pyr_fused_kernel).  Groups of consecutive levels; per group the tiles of its coarsest
+// level and, walking the resize tables backwards, the regions of the finer levels every tile depends on.  Returns false (legacy
+// per-level kernels) when the geometry does not fit: a level that is not "narrow" (scale factor above ~1.75), a halo that does
+// not cover the neighbour's first column, or a region larger than a TMA box.
+bool buildPyrPlan(gvs_extractor* fe, const std::vector<ResizeTap>& taps, std::vector<PyrSpan>& spans) {
+    const Geometry& g = fe->g;
+    PyrPlan& P = fe->pyrPlan;
+    P.nGroups = 0;
+    spans.clear();
+    const int L = g.nLevels;
+    if (L < 2 || getenv("GVS_NO_FUSED_PYR")) return false;
+    for (int l = 1; l < L; l++)
+        if (!((fe->pyrNarrowMask >> l) & 1u)) return false;
+    auto up = [](int v, int a) { return (v + a - 1) / a * a; };
+    int base = 0;
+    while (base < L - 1) {
+        if (P.nGroups == kPyrMaxGroups) { P.nGroups = 0; return false; }
+        const bool first = base == 0;
+        const int nOut = std::min(first ? 3 : kPyrMaxFuse, L - 1 - base), top = base + nOut;
+        PyrGroup G{};
+        G.base = base; G.nOut = nOut;
+        int TW = first ? 128 : 64, TH = first ? 64 : 32;   // tile of the group's coarsest level (measured: larger tiles amortise the TMA wait)
+        if (const char* e = getenv("GVS_PYR_TILE")) {        // tuning knob: "TWa,THa,TWb,THb"
+            int v[4] = {TW, TH, 64, 32};
+            if (sscanf(e, "%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3]) >= 2) { TW = first ? v[0] : v[2]; TH = first ? v[1] : v[3]; }
+            TW = std::max(TW & ~3, 4); TH = std::max(TH, 2);
+        }
+        for (;; TW = std::max(TW / 2, 4), TH = std::max(TH / 2, 2)) {
+            auto build = [&](bool isX, int T, std::vector<PyrSpan>& out) -> bool {
+                out.clear();
+                const int dimTop = isX ? g.lv[top].w : g.lv[top].h, n = (dimTop + T - 1) / T;
+                for (int i = 0; i < n; i++) {
+                    PyrSpan sp{};
+                    sp.lo[nOut] = (short)(i * T); sp.hi[nOut] = (short)std::min(i * T + T, dimTop);
+                    for (int k = nOut - 1; k >= 0; k--) {   // level base + k feeds level base + k + 1
+                        const LevelGeom& D = g.lv[base + k + 1];
+                        const int tab = isX ? D.tabX : D.tabY, dimSrc = isX ? g.lv[base + k].w : g.lv[base + k].h;
+                        int lo = taps[tab + sp.lo[k + 1]].ofs, hi = taps[tab + sp.hi[k + 1] - 1].pad + 1;
+                        if (isX) lo &= k == 0 ? ~15 : ~3;
+                        if (i == n - 1 && k > 0) hi = dimSrc;   // the last tile of a produced level runs to its end
+                        sp.lo[k] = (short)lo; sp.hi[k] = (short)std::min(hi, dimSrc);
+                    }
+                    out.push_back(sp);
+                }
+                for (int k = 1; k <= nOut; k++) {
+                    const int dim = isX ? g.lv[base + k].w : g.lv[base + k].h;
+                    for (int i = 0; i < n; i++) {
+                        PyrSpan& sp = out[i];
+                        const unsigned nG = (unsigned)((sp.hi[k] - sp.lo[k] + 3) >> 2);
+                        sp.magic[k] = nG > 1 ? 0xffffffffu / nG + 1u : 0u;
+                        sp.ownLo[k] = (short)(i == 0 ? 0 : sp.lo[k]);
+                        sp.ownHi[k] = (short)(i == n - 1 ? dim : out[i + 1].lo[k]);
+                        if (i == 0 && sp.lo[k] != 0) return false;
+                        if (sp.ownHi[k] > sp.hi[k] || sp.ownHi[k] < sp.ownLo[k]) return false;           // the halo must reach the neighbour's first column
+                        if (isX && ((sp.ownLo[k] & 3) || (i < n - 1 && (sp.ownHi[k] & 3)))) return false;   // whole 4-px store groups
+                        if (i == n - 1 && sp.hi[k] != dim) return false;
+                    }
+                }
+                return true;
+            };
+            std::vector<PyrSpan> sx, sy;
+            if (!build(true, TW, sx) || !build(false, TH, sy)) return false;
+            int wMax[kPyrMaxFuse + 1] = {}, hMax[kPyrMaxFuse + 1] = {};
+            for (const PyrSpan& sp : sx) for (int k = 0; k <= nOut; k++) wMax[k] = std::max(wMax[k], sp.hi[k] - sp.lo[k]);
+            for (const PyrSpan& sp : sy) for (int k = 0; k <= nOut; k++) hMax[k] = std::max(hMax[k], sp.hi[k] - sp.lo[k]);
+            G.boxW = up(wMax[0] + 16, 16); G.boxH = hMax[0];
+            if ((G.boxW > 256 || G.boxH > 256) && (TW > 4 || TH > 2)) continue;   // smaller tiles
+            if (G.boxW > 256 || G.boxH > 256) return false;
+            // two shared-memory regions used in turn: level k is read while level k + 1 is written, level k - 1 is dead by then
+            G.bufPitch[0] = G.boxW;
+            int size[2] = {up(G.boxW * G.boxH + 16, 128), 0};
+            for (int k = 1; k < nOut; k++) {
+                G.bufPitch[k] = up(wMax[k] + 16, 4);
+                size[k & 1] = std::max(size[k & 1], up(G.bufPitch[k] * hMax[k] + 16, 128));
+            }
+            for (int k = 0; k < nOut; k++) G.bufOff[k] = (k & 1) ? size[0] : 0;
+            const int off = size[0] + size[1];
+            G.smemBytes = off + 16;
+            if (G.smemBytes > 96 * 1024) return false;
+            G.nTx = (int)sx.size(); G.nTy = (int)sy.size();
+            G.spanX = (int)spans.size(); spans.insert(spans.end(), sx.begin(), sx.end());
+            G.spanY = (int)spans.size(); spans.insert(spans.end(), sy.begin(), sy.end());
+            break;
+        }
+        if (!encodeLevelMap(fe, base, G.boxW, G.boxH, &fe->pyrMaps[P.nGroups])) { P.nGroups = 0; return false; }
+        P.grp[P.nGroups++] = G;
+        base = top;
+    }
+    return true;
+}
+
 void destroyExtractor(gvs_extractor* fe) {
     if (!fe) return;
     DeviceGuard deviceGuard(fe->device);
     if (fe->ownStream) cudaStreamSynchronize(fe->ownStream);
-    cudaFree(fe->slab); cudaFree(fe->blurSlab); cudaFree(fe->tight); cudaFree(fe->mapX); cudaFree(fe->mapY); cudaFree(fe->xWeights); cudaFree(fe->xSelectors); cudaFree(fe->xBase); cudaFree(fe->taps); cudaFree(fe->fastItems); cudaFree(fe->blurItems);
+    cudaFree(fe->slab); cudaFree(fe->blurSlab); cudaFree(fe->tight); cudaFree(fe->mapX); cudaFree(fe->mapY); cudaFree(fe->xWeights); cudaFree(fe->xSelectors); cudaFree(fe->xBase); cudaFree(fe->pyrSpans); cudaFree(fe->taps); cudaFree(fe->fastItems); cudaFree(fe->blurItems);
     cudaFree(fe->recs); cudaFree(fe->nCand); cudaFree(fe->cellCnt); cudaFree(fe->kept); cudaFree(fe->keptCnt);
     cudaFree(fe->imgOff); cudaFree(fe->orderedDbg); cudaFree(fe->sortedDbg); cudaFree(fe->momentsDbg); cudaFree(fe->selScratch);
     cudaFree(fe->workCounter); cudaFree(fe->status); cudaFree(fe->kps); cudaFree(fe->desc); cudaFree(fe->auxKey);
@@ -197,7 +316,10 @@ static int enqueueExtract(gvs_extractor* fe, int n, cudaStream_t s) {
     const bool T = fe->timing;
     GVS_CUDA_OK(cudaMemsetAsync(fe->status, 0, sizeof(int), s));
     if (T) cudaEventRecord(fe->ev[0], s);
-    launchPyramid(g, fe->slab, fe->taps, fe->xWeights, fe->xSelectors, fe->xBase, fe->pyrNarrowMask, n, s, &fe->launches);
+    if (fe->pyrPlan.nGroups > 0)
+        launchPyramidFused(g, fe->slab, fe->taps, fe->xWeights, fe->xSelectors, fe->xBase, fe->pyrPlan, fe->pyrSpans, fe->pyrMaps, n, s, &fe->launches);
+    else
+        launchPyramid(g, fe->slab, fe->taps, fe->xWeights, fe->xSelectors, fe->xBase, fe->pyrNarrowMask, n, s, &fe->launches);
     if (T) cudaEventRecord(fe->ev[1], s);
     launchFast(g, fe->slab, fe->fastItems, fe->nFastItems, n, fe->recs, fe->nCand, fe->cellCnt, fe->status, s, &fe->launches);
     if (T) cudaEventRecord(fe->ev[2], s);
@@ -427,6 +549,11 @@ int gvs_extractor_create(gvs_extractor** out, const gvs_extractor_params* params
         GVS_TRY(cudaMemcpy(fe->xWeights, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
         GVS_TRY(cudaMemcpy(fe->xSelectors, sl.data(), sl.size() * 4, cudaMemcpyHostToDevice));
         GVS_TRY(cudaMemcpy(fe->xBase, base.data(), base.size() * 2, cudaMemcpyHostToDevice));
+        std::vector<PyrSpan> spans;
+        if (buildPyrPlan(fe, taps, spans)) {
+            GVS_TRY(devAlloc(&fe->pyrSpans, spans.size()));
+            GVS_TRY(cudaMemcpy(fe->pyrSpans, spans.data(), spans.size() * sizeof(PyrSpan), cudaMemcpyHostToDevice));
+        }
     }
     {
         std::vector<FastItem> items;

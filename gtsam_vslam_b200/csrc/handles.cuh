@@ -61,6 +61,9 @@ struct gvs_extractor {
     uint4* xSelectors = nullptr;      // ... PRMT selector (| 1 << 16 when the pair sits in the upper 8 bytes of the window)
     unsigned short* xBase = nullptr;  // ... source offset of the window: sx of the first column (narrow levels) or the 4-byte aligned
                                       //     start of the 12-byte window (other levels)
+    PyrPlan pyrPlan{};                // fused pyramid (nGroups == 0: legacy per-level kernels)
+    PyrSpan* pyrSpans = nullptr;
+    alignas(64) CUtensorMap pyrMaps[kPyrMaxGroups];   // TMA tile maps of the groups' base levels
     unsigned pyrNarrowMask = 0;       // bit l: every column group of level l spans at most 8 source bytes (pyr_down_kernel<true>)
     FastItem* fastItems = nullptr;
     int nFastItems = 0;

@@ -8,6 +8,9 @@
 // Coefficients are precomputed on the host exactly as cv::resize does (float32 rounding) and read from a
 // small table that stays in L1/L2.  HBM-bound: reads level l-1 once (neighbouring threads share rows
 // through L1), writes level l once with 4-byte coalesced stores.
+#include <algorithm>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace gvs {
@@ -93,6 +96,156 @@ pyr_down_kernel(const __grid_constant__ Geometry g, uint8_t* __restrict__ slab, 
         for (int i = 0; i < 4; i++) hB1[i] = hA1[i];
     } else hrow(t1.pad, hB1);
     blend(hB0, hB1, t1, dy + 1);
+}
+
+// ---- fused pyramid -----------------------------------------------------------------------------------------------------
+// The level chain is sequential (level l is a resize of level l-1), but it is local: a tile of level l+3 depends on a slightly
+// larger tile of level l+2, ... of level l.  A CTA owns a tile of the coarsest level of a group (host plan: PyrGroup / PyrSpan),
+// fetches the region of the group's base level it depends on with ONE TMA tile load (cp.async.bulk.tensor, halo included,
+// out-of-image parts zero filled and never read) and produces the regions of the group's levels one after the other in shared
+// memory with the arithmetic of pyr_down_kernel<true>; every level's pixels are written to global memory by exactly one tile
+// (the "own" ranges partition the level).  HBM traffic per image: the base levels once + every produced level once (the
+// un-fused chain re-reads every intermediate level), 2-3 launches instead of nLevels - 1, and no exposed global-load latency
+// in the inner loop.
+__device__ __forceinline__ unsigned smemAddr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbarInit(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbarExpectTx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarWait(unsigned bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+// one 3-D tile (x bytes, y rows, z image) of a tensor map into shared memory; completion is signalled on the mbarrier
+__device__ __forceinline__ void tmaLoadTile3d(unsigned dst, const CUtensorMap* map, int x, int y, int z, unsigned bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
+}
+
+constexpr int kPyrMaxThreads = 512;
+__global__ void __launch_bounds__(kPyrMaxThreads)
+pyr_fused_kernel(const __grid_constant__ Geometry g, const __grid_constant__ CUtensorMap baseMap, const __grid_constant__ PyrGroup G,
+                 uint8_t* __restrict__ slab, const ResizeTap* __restrict__ taps, const uint4* __restrict__ xw,
+                 const uint4* __restrict__ xs, const unsigned short* __restrict__ xbase, const PyrSpan* __restrict__ spans) {
+    extern __shared__ __align__(128) uint8_t sm[];
+    __shared__ __align__(8) unsigned long long barrier;
+    const int tid = threadIdx.x, img = blockIdx.y;
+    const int ty = blockIdx.x / G.nTx, tx = blockIdx.x - ty * G.nTx;
+    __shared__ PyrSpan SX, SY;   // (indexed by the level inside the group: shared memory, not registers)
+    if (tid < (int)(sizeof(PyrSpan) / sizeof(short))) {
+        reinterpret_cast<short*>(&SX)[tid] = reinterpret_cast<const short*>(spans + G.spanX + tx)[tid];
+        reinterpret_cast<short*>(&SY)[tid] = reinterpret_cast<const short*>(spans + G.spanY + ty)[tid];
+    }
+    static_assert(sizeof(PyrSpan) / sizeof(short) <= 256, "one thread per 16-bit word of a span");
+    const unsigned bar = smemAddr(&barrier);
+    if (tid == 0) {
+        const short* gx = reinterpret_cast<const short*>(spans + G.spanX + tx);
+        const short* gy = reinterpret_cast<const short*>(spans + G.spanY + ty);
+        mbarInit(bar, 1);
+        mbarExpectTx(bar, (unsigned)(G.boxW * G.boxH));
+        tmaLoadTile3d(smemAddr(sm), &baseMap, gx[0], gy[0], img, bar);   // PyrSpan::lo[0]
+    }
+    __syncthreads();      // (the barrier is initialised before anybody polls it)
+    mbarWait(bar, 0);
+    for (int k = 1; k <= G.nOut; k++) {
+        const int level = G.base + k;
+        const LevelGeom& D = g.lv[level];
+        const uint8_t* sbuf = sm + G.bufOff[k - 1];
+        const int sPitch = G.bufPitch[k - 1], sX0 = SX.lo[k - 1], sY0 = SY.lo[k - 1];
+        uint8_t* dbuf = k < G.nOut ? sm + G.bufOff[k] : nullptr;
+        const int dPitch = k < G.nOut ? G.bufPitch[k] : 0;
+        const int cLo = SX.lo[k], cHi = SX.hi[k], rLo = SY.lo[k], rHi = SY.hi[k];
+        const int oxLo = SX.ownLo[k], oxHi = SX.ownHi[k], oyLo = SY.ownLo[k], oyHi = SY.ownHi[k];
+        uint8_t* dst = levelPtr(slab, g, img, level);
+        // thread = one group of 4 destination columns (its column tables stay in registers) and every nStripes-th row of the
+        // region.  Both source rows of a destination row are interpolated on the spot: no dependence between the rows of a
+        // thread, no reuse bookkeeping -- the inner loop is straight-line code on shared memory.
+        const int nGx = (cHi - cLo + 3) >> 2, nRows = rHi - rLo;
+        const int nStripes = max((int)blockDim.x / nGx, 1);   // stripes of row pairs
+        const unsigned magic = SX.magic[k];   // stripe = tid / nGx = umulhi(tid, magic) (host: 2^32 / nGx + 1)
+        const int stripe = nGx > 1 ? (int)__umulhi((unsigned)tid, magic) : tid, gx = tid - stripe * nGx;
+        if (stripe < nStripes) {
+            const int dx0 = cLo + 4 * gx;
+            const int gi = (D.tabX + dx0) >> 2;
+            const unsigned base = xbase[gi];
+            const unsigned sh = (base & 3u) * 8u;
+            const uint4 wv = __ldg(xw + gi), sv = __ldg(xs + gi);
+            const uint8_t* s0 = sbuf + ((int)(base & ~3u) - sX0) - sY0 * sPitch;
+            uint8_t* d0 = dbuf ? dbuf + (dx0 - cLo) - rLo * dPitch : nullptr;
+            uint8_t* g0 = dst + dx0;
+            const bool ownX = dx0 >= oxLo && dx0 < oxHi;
+            const int dp = D.pitch;
+            const uint2* ty = reinterpret_cast<const uint2*>(taps + D.tabY);   // {ofs | a0 << 16, a1 | pad << 16}: one 8-byte load
+            auto hrow = [&](int row, unsigned& h0, unsigned& h1, unsigned& h2, unsigned& h3) {
+                const unsigned* r = reinterpret_cast<const unsigned*>(s0 + row * sPitch);
+                const unsigned p0 = r[0], p1 = r[1], p2 = r[2];
+                const unsigned lo = __funnelshift_r(p0, p1, sh), hi = __funnelshift_r(p1, p2, sh);
+                h0 = __dp2a_lo(wv.x, __byte_perm(lo, hi, sv.x), 0u) >> 4;
+                h1 = __dp2a_lo(wv.y, __byte_perm(lo, hi, sv.y), 0u) >> 4;
+                h2 = __dp2a_lo(wv.z, __byte_perm(lo, hi, sv.z), 0u) >> 4;
+                h3 = __dp2a_lo(wv.w, __byte_perm(lo, hi, sv.w), 0u) >> 4;
+            };
+            // vertical blend of 4 pixels: (hi(b0*u) + hi(b1*v) + 2) >> 2 per pixel; the four 10-bit sums are packed into 16-bit
+            // lanes first so that two shifts and one PRMT (bytes 0 and 2 of each word) finish all four
+            auto blend = [&](unsigned b0, unsigned b1, unsigned u0, unsigned u1, unsigned u2, unsigned u3, unsigned v0, unsigned v1,
+                             unsigned v2, unsigned v3) {
+                const unsigned s0 = __umulhi(b0, u0) + 2u + __umulhi(b1, v0), s1 = __umulhi(b0, u1) + 2u + __umulhi(b1, v1);
+                const unsigned s2 = __umulhi(b0, u2) + 2u + __umulhi(b1, v2), s3 = __umulhi(b0, u3) + 2u + __umulhi(b1, v3);
+                const unsigned p01 = __byte_perm(s0, s1, 0x5410) >> 2, p23 = __byte_perm(s2, s3, 0x5410) >> 2;
+                return __byte_perm(p01, p23, 0x6420);
+            };
+            // thread rows: pairs (y, y + 1) of consecutive destination rows, every nStripes-th pair: the second row usually shares
+            // its upper source row with the first one's lower row (uniform across the warps of a stripe)
+            const int y0 = rLo + 2 * stripe;
+            uint8_t* dptr = d0 ? d0 + y0 * dPitch : nullptr;        // running pointers: one add per pair
+            uint8_t* gptr = g0 + (size_t)y0 * dp;
+            const int dStep = 2 * nStripes * dPitch, gStep = 2 * nStripes * dp;
+            for (int y = y0; y < rHi; y += 2 * nStripes, dptr += dStep, gptr += gStep) {
+                const uint2 t = __ldg(ty + y);
+                const int rA = (int)(t.x & 0xffffu), rB = (int)(t.y >> 16);
+                unsigned a0, a1, a2, a3, c0, c1, c2, c3;
+                hrow(rA, a0, a1, a2, a3);
+                hrow(rB, c0, c1, c2, c3);
+                const unsigned w0 = blend(t.x & 0xffff0000u, t.y << 16, a0, a1, a2, a3, c0, c1, c2, c3);
+                if (d0) *reinterpret_cast<unsigned*>(dptr) = w0;
+                if (ownX && y >= oyLo && y < oyHi) *reinterpret_cast<unsigned*>(gptr) = w0;
+                if (y + 1 >= rHi) break;
+                const uint2 t2 = __ldg(ty + y + 1);
+                const int rC = (int)(t2.x & 0xffffu), rD = (int)(t2.y >> 16);
+                unsigned e0, e1, e2, e3, f0, f1, f2, f3;
+                if (rC == rB) { e0 = c0; e1 = c1; e2 = c2; e3 = c3; }
+                else if (rC == rA) { e0 = a0; e1 = a1; e2 = a2; e3 = a3; }
+                else hrow(rC, e0, e1, e2, e3);
+                if (rD == rC) { f0 = e0; f1 = e1; f2 = e2; f3 = e3; }
+                else if (rD == rB) { f0 = c0; f1 = c1; f2 = c2; f3 = c3; }
+                else hrow(rD, f0, f1, f2, f3);
+                const unsigned w1 = blend(t2.x & 0xffff0000u, t2.y << 16, e0, e1, e2, e3, f0, f1, f2, f3);
+                if (d0) *reinterpret_cast<unsigned*>(dptr + dPitch) = w1;
+                if (ownX && y + 1 >= oyLo && y + 1 < oyHi) *reinterpret_cast<unsigned*>(gptr + dp) = w1;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+void launchPyramidFused(const Geometry& g, uint8_t* slab, const ResizeTap* taps, const uint4* xw, const uint4* xs,
+                        const unsigned short* xbase, const PyrPlan& plan, const PyrSpan* spans, const CUtensorMap* baseMaps,
+                        int nImages, cudaStream_t s, int* launches) {
+    static size_t cfg[64];
+    for (int i = 0; i < plan.nGroups; i++) {
+        const PyrGroup& G = plan.grp[i];
+        ensureDynamicSmem(pyr_fused_kernel, (size_t)G.smemBytes, cfg);
+        static const int threads = [] { const char* e = getenv("GVS_PYR_THREADS"); const int v = e ? atoi(e) : 256; return std::min(std::max(v & ~31, 64), kPyrMaxThreads); }();
+        pyr_fused_kernel<<<dim3(G.nTx * G.nTy, nImages), threads, G.smemBytes, s>>>(g, baseMaps[i], G, slab, taps, xw, xs, xbase, spans);
+        ++*launches;
+    }
 }
 
 // Tightly packed host batches arrive with one contiguous DMA (about 55 GB/s over PCIe Gen5, against about 8 GB/s for a
