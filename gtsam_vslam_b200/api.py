@@ -25,7 +25,7 @@ GVS_MATCH_STEREO_PRED, GVS_MATCH_MONO, GVS_MATCH_RADIUS = 0, 1, 2
 # every symbol include/gvs.h declares (tests check that the library exports all of them)
 SYMBOLS = [
     "gvs_last_error", "gvs_version", "gvs_default_params", "gvs_device_count",
-    "gvs_extractor_create", "gvs_extractor_destroy", "gvs_extractor_tables", "gvs_extractor_level_size",
+    "gvs_extractor_create", "gvs_extractor_destroy", "gvs_extractor_tables", "gvs_tables_from_params", "gvs_extractor_level_size",
     "gvs_extract", "gvs_extract_batch_host", "gvs_extractor_input", "gvs_extract_batch_resident",
     "gvs_extractor_sync", "gvs_extractor_set_rectify_maps", "gvs_extract_batch_host_raw", "gvs_extract_offsets", "gvs_extract_download", "gvs_extractor_set_stream",
     "gvs_debug_level_image", "gvs_debug_level_candidates", "gvs_debug_level_kept", "gvs_debug_select",
@@ -97,6 +97,7 @@ def load_library() -> C.CDLL:
     lib.gvs_extractor_create.argtypes = [C.POINTER(vp), C.POINTER(_Params), i32, i32, i32, i32]
     lib.gvs_extractor_destroy.argtypes = [vp]
     lib.gvs_extractor_tables.argtypes = [vp] + [vp] * 6
+    lib.gvs_tables_from_params.argtypes = [C.POINTER(_Params)] + [vp] * 6
     lib.gvs_extractor_level_size.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32)]
     lib.gvs_extract.argtypes = [vp, vp, i32, i32, i32, vp, vp, i32, C.POINTER(i32)]
     lib.gvs_extract_batch_host.argtypes = [vp, vp, C.c_size_t, i32, i32]

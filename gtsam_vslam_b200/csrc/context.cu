@@ -29,6 +29,25 @@ using namespace gvs;
 
 namespace {
 
+// FeatureExtractor::FeatureExtractor, the tables that depend on the constructor arguments only (src/FeatureExtractor.cpp:622-659)
+void buildTables(const gvs_extractor_params& p, std::vector<float>& scale, std::vector<float>& invScale, std::vector<float>& sigma,
+                 std::vector<float>& invSigma, std::vector<int>& patch, std::vector<int>& quota) {
+    const int L = p.n_levels;
+    scale.assign(L, 1.f); invScale.assign(L, 1.f); sigma.assign(L, 1.f); invSigma.assign(L, 1.f);
+    patch.assign(L, p.patch_size); quota.assign(L, 0);
+    for (int i = 1; i < L; i++) {
+        scale[i] = scale[i - 1] * p.im_scale;
+        patch[i] = (int)(p.patch_size * scale[i]);
+        sigma[i] = scale[i] * scale[i];
+    }
+    for (int i = 0; i < L; i++) { invScale[i] = 1.0f / scale[i]; invSigma[i] = 1.0f / sigma[i]; }
+    const float factor = 1.0f / p.im_scale;
+    float nd = p.n_features * (1 - factor) / (1 - (float)std::pow((double)factor, (double)L));
+    int sum = 0;
+    for (int l = 0; l < L - 1; l++) { quota[l] = cvRoundF(nd); sum += quota[l]; nd *= factor; }
+    quota[L - 1] = std::max(p.n_features - sum, 0);
+}
+
 int buildGeometry(gvs_extractor* fe) {
     const gvs_extractor_params& p = fe->params;
     const int L = p.n_levels;
@@ -40,23 +59,8 @@ int buildGeometry(gvs_extractor* fe) {
     g.tMin = p.min_fast_threshold;
     g.tMax = p.max_fast_threshold;
     g.edge = p.edge_threshold;
-    // ---- tables, float32 cumulative (src/FeatureExtractor.cpp:622-644)
-    fe->scale.assign(L, 1.f); fe->invScale.assign(L, 1.f); fe->sigma.assign(L, 1.f); fe->invSigma.assign(L, 1.f);
-    fe->patch.assign(L, p.patch_size); fe->quota.assign(L, 0);
-    for (int i = 1; i < L; i++) {
-        fe->scale[i] = fe->scale[i - 1] * p.im_scale;
-        fe->patch[i] = (int)(p.patch_size * fe->scale[i]);
-        fe->sigma[i] = fe->scale[i] * fe->scale[i];
-    }
-    for (int i = 0; i < L; i++) { fe->invScale[i] = 1.0f / fe->scale[i]; fe->invSigma[i] = 1.0f / fe->sigma[i]; }
-    // ---- per-level quota (:648-659)
-    {
-        const float factor = 1.0f / p.im_scale;
-        float nd = p.n_features * (1 - factor) / (1 - (float)std::pow((double)factor, (double)L));
-        int sum = 0;
-        for (int l = 0; l < L - 1; l++) { fe->quota[l] = cvRoundF(nd); sum += fe->quota[l]; nd *= factor; }
-        fe->quota[L - 1] = std::max(p.n_features - sum, 0);
-    }
+    // ---- tables, float32 cumulative (src/FeatureExtractor.cpp:622-644) and per-level quota (:648-659)
+    buildTables(p, fe->scale, fe->invScale, fe->sigma, fe->invSigma, fe->patch, fe->quota);
     // ---- umax (:666-680)
     {
         const int hp = kHalfPatch;
@@ -620,6 +624,25 @@ int gvs_extractor_tables(const gvs_extractor* fe, float* scale, float* inv_scale
         if (inv_sigma) inv_sigma[i] = fe->invSigma[i];
         if (scaled_patch) scaled_patch[i] = fe->patch[i];
         if (feature_per_level) feature_per_level[i] = fe->quota[i];
+    }
+    return GVS_OK;
+}
+
+int gvs_tables_from_params(const gvs_extractor_params* params, float* scale, float* inv_scale, float* sigma, float* inv_sigma,
+                           int32_t* scaled_patch, int32_t* feature_per_level) {
+    if (!params) return fail(GVS_ERR_INVALID, "null argument");
+    if (params->n_levels < 1 || params->n_levels > kMaxLevels) return fail(GVS_ERR_INVALID, "n_levels must be in [1, 12]");
+    if (params->n_features < 2 || params->im_scale <= 1.0f) return fail(GVS_ERR_INVALID, "bad n_features / im_scale");
+    std::vector<float> sc, isc, sg, isg;
+    std::vector<int> pt, qt;
+    buildTables(*params, sc, isc, sg, isg, pt, qt);
+    for (int i = 0; i < params->n_levels; i++) {
+        if (scale) scale[i] = sc[i];
+        if (inv_scale) inv_scale[i] = isc[i];
+        if (sigma) sigma[i] = sg[i];
+        if (inv_sigma) inv_sigma[i] = isg[i];
+        if (scaled_patch) scaled_patch[i] = pt[i];
+        if (feature_per_level) feature_per_level[i] = qt[i];
     }
     return GVS_OK;
 }

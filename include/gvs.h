@@ -79,6 +79,10 @@ int gvs_extractor_destroy(gvs_extractor* fe);
  * src/FeatureTracker.cpp:75-79).  Each array has n_levels entries; any pointer may be NULL. */
 int gvs_extractor_tables(const gvs_extractor* fe, float* scale_pyramid, float* scale_inv_pyramid, float* sigma_factor,
                          float* inv_sigma_factor, int32_t* scaled_patch_size, int32_t* feature_per_level);
+/* The same tables from the constructor arguments alone (no handle, no device: they do not depend on the image size), for
+ * callers that must publish them before the first image arrives (KeyFrame copies them at once, src/FeatureTracker.cpp:75-79). */
+int gvs_tables_from_params(const gvs_extractor_params* params, float* scale_pyramid, float* scale_inv_pyramid, float* sigma_factor,
+                           float* inv_sigma_factor, int32_t* scaled_patch_size, int32_t* feature_per_level);
 /* imagePyramid[level].cols / .rows (computePyramid, src/FeatureExtractor.cpp:346-347) */
 int gvs_extractor_level_size(const gvs_extractor* fe, int level, int* width, int* height);
 

@@ -4,10 +4,11 @@
 // A maintainer of gtsam-vSLAM replaces include/FeatureExtractor.h + src/FeatureExtractor.cpp and
 // include/FeatureMatcher.h + src/FeatureMatcher.cpp by this header and links libgvs.so;
 // System, FeatureTracker, KeyFrame, Map and LocalMapper compile against it unchanged apart from the two
-// constructor calls that now also pass the image size.
+// constructor calls.  The constructors keep the reference's argument lists (include/FeatureExtractor.h:80,
+// include/FeatureMatcher.h:40): the device handles are created lazily from the size of the first image.
 //
 //   reference                                                       here
-//   FeatureExtractor::FeatureExtractor   src/FeatureExtractor.cpp:620   FeatureExtractor(..., width, height)
+//   FeatureExtractor::FeatureExtractor   src/FeatureExtractor.cpp:620   FeatureExtractor(nfeatures = 2000, ..., minFastThreshold = 7)
 //   FeatureExtractor::extractKeysNew     src/FeatureExtractor.cpp:481   extractKeysNew(image, keypoints, descriptors)
 //   public tables                        include/FeatureExtractor.h:71  scalePyramid, scaleInvPyramid, sigmaFactor, ...
 //   FeatureMatcher::findStereoMatchesORB2R src/FeatureMatcher.cpp:528   findStereoMatchesORB2R(lImage, rImage, rightDesc, rightKeys, keysLeft)
@@ -23,6 +24,7 @@
 // Error behaviour: the reference returns void and never reports errors; here a failing C-ABI call throws
 // std::runtime_error with gvs_last_error() (there is no CPU fallback to fall through to).
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <memory>
@@ -39,6 +41,12 @@
 #include "gvs.h"
 
 namespace GTSAM_VIOSLAM {
+
+#ifdef GVS_HAVE_OPENCV
+#define GVS_CV_8U CV_8U
+#else
+#define GVS_CV_8U cv::CV_8U
+#endif
 
 static_assert(sizeof(cv::KeyPoint) == sizeof(gvs_keypoint), "cv::KeyPoint must be the 28-byte POD the ABI copies");
 
@@ -70,47 +78,107 @@ class FeatureExtractor {
     const int edgeThreshold, patchSize;
     const int halfPatchSize{15};
     const int maxFastThreshold, minFastThreshold;
+    // include/FeatureExtractor.h:71.  The pyramid lives on the device (only findStereoMatchesORB2R reads it, src/FeatureMatcher.cpp:
+    // 606-623, and that runs on the device too); set mirrorImagePyramid to have extractKeysNew copy the levels back into this member.
+    std::vector<cv::Mat> imagePyramid;
+    bool mirrorImagePyramid = false;
     std::vector<int> scaledPatchSize, featurePerLevel;
     std::vector<float> scalePyramid, scaleInvPyramid, sigmaFactor, InvSigmaFactor;
-    // imagePyramid stays on the device: only findStereoMatchesORB2R reads it (src/FeatureMatcher.cpp:606-623)
 
-    FeatureExtractor(int _nfeatures, int _nLevels, float _imScale, int _edgeThreshold, int _patchSize, int _maxFastThreshold,
-                     int _minFastThreshold, int width, int height, int device = 0)
+    // include/FeatureExtractor.h:80: the reference's seven arguments and defaults (src/System.cpp:31,56-57).  The device handle is
+    // created by the first call that sees an image (the reference also learns the image size per call, src/FeatureExtractor.cpp:347).
+    FeatureExtractor(const int _nfeatures = 2000, const int _nLevels = 8, const float _imScale = 1.2f, const int _edgeThreshold = 19,
+                     const int _patchSize = 31, const int _maxFastThreshold = 20, const int _minFastThreshold = 7)
         : nFeatures(_nfeatures), nLevels(_nLevels), imScale(_imScale), edgeThreshold(_edgeThreshold), patchSize(_patchSize),
-          maxFastThreshold(_maxFastThreshold), minFastThreshold(_minFastThreshold), width_(width), height_(height) {
-        gvs_extractor_params p{_nfeatures, _nLevels, _imScale, _edgeThreshold, _patchSize, _maxFastThreshold, _minFastThreshold};
-        gvsCheck(gvs_extractor_create(&h_, &p, width, height, 1, device));
+          maxFastThreshold(_maxFastThreshold), minFastThreshold(_minFastThreshold) {
+        const gvs_extractor_params p = params();
         scalePyramid.resize(nLevels); scaleInvPyramid.resize(nLevels); sigmaFactor.resize(nLevels); InvSigmaFactor.resize(nLevels);
         scaledPatchSize.resize(nLevels); featurePerLevel.resize(nLevels);
-        gvsCheck(gvs_extractor_tables(h_, scalePyramid.data(), scaleInvPyramid.data(), sigmaFactor.data(), InvSigmaFactor.data(),
-                                      scaledPatchSize.data(), featurePerLevel.data()));
+        gvsCheck(gvs_tables_from_params(&p, scalePyramid.data(), scaleInvPyramid.data(), sigmaFactor.data(), InvSigmaFactor.data(),
+                                        scaledPatchSize.data(), featurePerLevel.data()));
     }
-    FeatureExtractor(int width, int height) : FeatureExtractor(2000, 8, 1.2f, 19, 31, 20, 7, width, height) {}
     ~FeatureExtractor() { gvs_extractor_destroy(h_); }
     FeatureExtractor(const FeatureExtractor&) = delete;
     FeatureExtractor& operator=(const FeatureExtractor&) = delete;
 
     // src/FeatureExtractor.cpp:481-533.  Zero keypoints leaves both outputs untouched (:498-499).
     void extractKeysNew(cv::Mat& image, std::vector<cv::KeyPoint>& keypoints, cv::Mat& descriptors) {
+        ensure(image.cols, image.rows);
         const int cap = 2 * nFeatures + 64 * (int)nLevels;
         std::vector<cv::KeyPoint> k(cap);
-        cv::Mat d(cap, 32, cv::CV_8U);
+        cv::Mat d(cap, 32, GVS_CV_8U);
         int n = 0;
         gvsCheck(gvs_extract(h_, image.data, image.cols, image.rows, (int)image.step, reinterpret_cast<gvs_keypoint*>(k.data()),
                              d.data, cap, &n));
+        if (mirrorImagePyramid) fetchImagePyramid();
         if (n <= 0) return;
         k.resize(n);
         keypoints = std::move(k);
-        descriptors = cv::Mat(n, 32, cv::CV_8U);
+        descriptors = cv::Mat(n, 32, GVS_CV_8U);
         std::memcpy(descriptors.data, d.data, (size_t)n * 32);
+    }
+    // FeatureExtractor::computePyramid (src/FeatureExtractor.cpp:342-366): the levels of `image` in imagePyramid (the device runs
+    // its whole per-image pipeline; the levels are what is copied back)
+    void computePyramid(const cv::Mat& image) {
+        ensure(image.cols, image.rows);
+        gvsCheck(gvs_extract_batch_host(h_, image.data, (size_t)image.step * image.rows, (int)image.step, 1));
+        fetchImagePyramid();
+    }
+    // imagePyramid[level] of the last image, copied from the device (a parity tap: it waits for the stream)
+    void fetchImagePyramid() {
+        imagePyramid.resize(nLevels);
+        for (size_t l = 0; l < nLevels; l++) {
+            int w = 0, h = 0;
+            gvsCheck(gvs_extractor_level_size(h_, (int)l, &w, &h));
+            imagePyramid[l] = cv::Mat(h, w, GVS_CV_8U);
+            gvsCheck(gvs_debug_level_image(h_, 0, (int)l, 0, imagePyramid[l].data));
+        }
+    }
+    // FeatureExtractor::ssc (src/FeatureExtractor.cpp:368-468) as the extractor itself calls it (:612): tolerance 0.1, (cols, rows)
+    // = a pyramid level's size and numRetPoints = that level's featurePerLevel.  The selection stage of the device pipeline is run
+    // on the given points (pt = level coordinates, response = FAST score); other argument combinations are not on the path and
+    // throw std::invalid_argument.
+    std::vector<cv::KeyPoint> ssc(std::vector<cv::KeyPoint> keyPoints, int numRetPoints, float tolerance, int cols, int rows) {
+        if (!h_) throw std::logic_error("FeatureExtractor::ssc: no image has been seen yet (the level sizes are unknown)");
+        int level = -1;
+        for (size_t l = 0; l < nLevels && level < 0; l++) {
+            int w = 0, h = 0;
+            gvsCheck(gvs_extractor_level_size(h_, (int)l, &w, &h));
+            if (w == cols && h == rows && featurePerLevel[l] == numRetPoints) level = (int)l;
+        }
+        if (level < 0 || tolerance != 0.1f) throw std::invalid_argument("FeatureExtractor::ssc: only the extractor's own per-level calls run on the device");
+        const int n = (int)keyPoints.size();
+        std::vector<int32_t> x(n), y(n), sc(n), kept(n + 1);
+        for (int i = 0; i < n; i++) { x[i] = (int)keyPoints[i].pt.x; y[i] = (int)keyPoints[i].pt.y; sc[i] = (int)keyPoints[i].response; }
+        int nk = 0;
+        gvsCheck(gvs_debug_select(h_, level, n, x.data(), y.data(), sc.data(), nullptr, kept.data(), n + 1, &nk));
+        std::vector<cv::KeyPoint> out(nk);
+        for (int i = 0; i < nk; i++) out[i] = keyPoints[kept[i]];
+        return out;
+    }
+
+    // device handle for images of this size (created on first use; the size of a camera does not change)
+    gvs_extractor* ensure(int width, int height) {
+        if (!h_) {
+            const gvs_extractor_params p = params();
+            gvsCheck(gvs_extractor_create(&h_, &p, width, height, 1, device));
+            width_ = width; height_ = height;
+        } else if (width != width_ || height != height_) {
+            throw std::invalid_argument("FeatureExtractor: image size differs from the first image's");
+        }
+        return h_;
     }
     gvs_extractor* handle() const { return h_; }
     int width() const { return width_; }
     int height() const { return height_; }
+    int device = 0;   // CUDA device of the lazily created handle
 
   private:
+    gvs_extractor_params params() const {
+        return gvs_extractor_params{nFeatures, (int32_t)nLevels, imScale, edgeThreshold, patchSize, maxFastThreshold, minFastThreshold};
+    }
     gvs_extractor* h_ = nullptr;
-    int width_, height_;
+    int width_ = 0, height_ = 0;
 };
 
 class FeatureMatcher {
@@ -119,12 +187,17 @@ class FeatureMatcher {
     std::shared_ptr<FeatureExtractor> feLeft, feRight;
     const int imageHeight;
 
-    // zedptr is reduced to the values the path reads: mCameraLeft->fx (double), mBaseline (float) (include/Camera.h:72,86)
+    // include/FeatureMatcher.h:40 (src/System.cpp:32,58, src/FeatureTracker.cpp:23): StereoCameraT is the reference's StereoCamera;
+    // the path reads zedptr->mCameraLeft->fx (double, include/Camera.h:72) and zedptr->mBaseline (float, :86).
+    template <class StereoCameraT>
+    FeatureMatcher(std::shared_ptr<StereoCameraT> _zed, std::shared_ptr<FeatureExtractor> _feLeft, std::shared_ptr<FeatureExtractor> _feRight,
+                   const int _imageHeight = 360)
+        : feLeft(std::move(_feLeft)), feRight(std::move(_feRight)), imageHeight(_imageHeight), fx_(_zed->mCameraLeft->fx),
+          baseline_(_zed->mBaseline) {}
+    // the same with the two camera values spelled out
     FeatureMatcher(double fx, float baseline, std::shared_ptr<FeatureExtractor> _feLeft, std::shared_ptr<FeatureExtractor> _feRight,
                    int _imageHeight = 360)
-        : feLeft(std::move(_feLeft)), feRight(std::move(_feRight)), imageHeight(_imageHeight) {
-        gvsCheck(gvs_matcher_create(&h_, feLeft->handle(), feRight ? feRight->handle() : nullptr, fx, baseline, _imageHeight));
-    }
+        : feLeft(std::move(_feLeft)), feRight(std::move(_feRight)), imageHeight(_imageHeight), fx_(fx), baseline_(baseline) {}
     ~FeatureMatcher() { gvs_matcher_destroy(h_); }
     FeatureMatcher(const FeatureMatcher&) = delete;
     FeatureMatcher& operator=(const FeatureMatcher&) = delete;
@@ -132,8 +205,14 @@ class FeatureMatcher {
     // src/FeatureMatcher.cpp:528-708.  The images and rightDesc/rightKeys arguments are kept for signature parity: the
     // device already holds the pyramids, keys and descriptors of the two extractKeysNew calls that precede this call.
     void findStereoMatchesORB2R(const cv::Mat&, const cv::Mat&, const cv::Mat&, std::vector<cv::KeyPoint>& rightKeys, TrackedKeys& keysLeft) {
-        gvsCheck(gvs_stereo_match_batch(h_, 1));
-        const size_t nl = keysLeft.keyPoints.size(), nr = rightKeys.size();
+        gvsCheck(gvs_stereo_match_batch(ensureHandle(), 1));
+        // (sized from the device's own key counts: the caller's vectors may be stale when an extraction returned no keys)
+        int offL[2] = {0, 0}, offR[2] = {0, 0};
+        gvsCheck(gvs_extract_offsets(feLeft->handle(), offL));
+        gvsCheck(gvs_extract_offsets(feRight->handle(), offR));
+        const size_t nl = (size_t)offL[1], nr = (size_t)offR[1];
+        if (nl != keysLeft.keyPoints.size() || nr != rightKeys.size())
+            throw std::logic_error("findStereoMatchesORB2R: keysLeft / rightKeys are not the keys of the last extractKeysNew calls");
         keysLeft.rightIdxs.assign(nl, -1); keysLeft.leftIdxs.assign(nr, -1); keysLeft.estimatedDepth.assign(nl, -1.0f);
         std::vector<uint8_t> cl(nl + 1);
         gvsCheck(gvs_stereo_download(h_, 0, 1, keysLeft.rightIdxs.data(), keysLeft.leftIdxs.data(), keysLeft.estimatedDepth.data(), cl.data()));
@@ -143,7 +222,7 @@ class FeatureMatcher {
 
     // FeatureTracker::assignKeysToGrids for both sides (src/FeatureTracker.cpp:28-54, :67-68)
     void assignKeysToGrids(TrackedKeys& keysLeft, int width, int height) {
-        gvsCheck(gvs_assign_grids_batch(h_, 1, width, height));
+        gvsCheck(gvs_assign_grids_batch(ensureHandle(), 1, width, height));
         for (int side = 0; side < 2; side++) {
             const size_t n = side ? keysLeft.rightKeyPoints.size() : keysLeft.keyPoints.size();
             int yg = 0;
@@ -162,8 +241,9 @@ class FeatureMatcher {
     // FeatureTracker::extractORBAndStereoMatch (src/FeatureTracker.cpp:56-70): the two extractions run concurrently on the
     // two handles' streams (the reference uses two std::threads), then stereo matching and both grids.
     void extractORBAndStereoMatch(cv::Mat& leftIm, cv::Mat& rightIm, TrackedKeys& keysLeft) {
-        gvsCheck(gvs_extract_batch_host(feLeft->handle(), leftIm.data, leftIm.step * leftIm.rows, (int)leftIm.step, 1));
-        gvsCheck(gvs_extract_batch_host(feRight->handle(), rightIm.data, rightIm.step * rightIm.rows, (int)rightIm.step, 1));
+        gvsCheck(gvs_extract_batch_host(feLeft->ensure(leftIm.cols, leftIm.rows), leftIm.data, leftIm.step * leftIm.rows, (int)leftIm.step, 1));
+        gvsCheck(gvs_extract_batch_host(feRight->ensure(rightIm.cols, rightIm.rows), rightIm.data, rightIm.step * rightIm.rows, (int)rightIm.step, 1));
+        keysLeft.keyPoints.clear(); keysLeft.rightKeyPoints.clear();   // (a frame without keys must not keep the previous frame's)
         fetch(*feLeft, keysLeft.keyPoints, keysLeft.Desc);
         fetch(*feRight, keysLeft.rightKeyPoints, keysLeft.rightDesc);
         findStereoMatchesORB2R(leftIm, rightIm, keysLeft.rightDesc, keysLeft.rightKeyPoints, keysLeft);
@@ -182,10 +262,12 @@ class FeatureMatcher {
                               std::vector<std::pair<int, int>>& matchesIdxs, const float rad) {
         return project(GVS_MATCH_MONO, activeMapPoints, keysLeft, matchedIdxsL, nullptr, matchesIdxs, rad);
     }
-    // src/FeatureMatcher.cpp:458-526: matches[i].first receives the index matched by lastKeys.keyPoints[i] (or stays -1); the
-    // caller appends (actKeyFrame, idx) to keyframeIdxMatchs[i] as :522 does.  actKeys must be the last extracted frame.
-    int matchByRadius(TrackedKeys& lastKeys, TrackedKeys& actKeys, std::vector<int>& matchedIdxsL, std::vector<std::pair<int, int>>& matches,
-                      const float rad) {
+    // src/FeatureMatcher.cpp:458-526 with the reference's seven arguments (call site src/FeatureTracker.cpp:1518): matchedIdxsL is
+    // in-out, (actKeyFrame, idx) is appended to keyframeIdxMatchs[i] for every matched key i of lastKeys (:522) and matchesIdxs is
+    // not touched (the reference never reads or writes it in this function).  actKeys must be the last extracted frame.
+    template <class KeyFrameT>
+    int matchByRadius(TrackedKeys& lastKeys, TrackedKeys& actKeys, std::vector<int>& matchedIdxsL, std::vector<std::pair<int, int>>& matchesIdxs,
+                      const float rad, std::vector<std::vector<std::pair<KeyFrameT*, int>>>& keyframeIdxMatchs, KeyFrameT* actKeyFrame) {
         const int M = (int)lastKeys.keyPoints.size();
         std::vector<float> pred(2 * (size_t)M);
         std::vector<int32_t> lvl(M);
@@ -195,12 +277,44 @@ class FeatureMatcher {
             std::memcpy(&desc[(size_t)i * 32], lastKeys.Desc.ptr(i), 32);
         }
         gvs_mappoints mp{M, desc.data(), pred.data(), nullptr, lvl.data(), nullptr, nullptr, nullptr};
-        matches.assign(M, std::make_pair(-1, -1));
+        std::vector<std::pair<int, int>> found(M, std::make_pair(-1, -1));
         int n = 0;
-        (void)actKeys;
-        gvsCheck(gvs_match_projection(h_, 0, GVS_MATCH_RADIUS, &mp, rad, matchedIdxsL.data(), nullptr,
-                                      reinterpret_cast<int32_t*>(matches.data()), &n));
+        (void)actKeys; (void)matchesIdxs;
+        gvsCheck(gvs_match_projection(ensureHandle(), 0, GVS_MATCH_RADIUS, &mp, rad, matchedIdxsL.data(), nullptr,
+                                      reinterpret_cast<int32_t*>(found.data()), &n));
+        for (int i = 0; i < M; i++)
+            if (found[i].first >= 0) keyframeIdxMatchs[i].emplace_back(std::make_pair(actKeyFrame, found[i].first));
         return n;
+    }
+
+    // FeatureMatcher::getMatchIdxs (src/FeatureMatcher.cpp:13-64) and destributeRightKeys (:728-752): public helpers of the
+    // reference class that nothing outside FeatureMatcher.cpp calls.  They only index the CALLER'S host containers (the key
+    // grids / key vectors of a TrackedKeys); the device matchers never use them (they enumerate the same windows / buckets in
+    // their kernels).  Kept so that code written against the reference header still compiles.
+    void getMatchIdxs(const cv::Point2f& predP, std::vector<int>& idxs, const TrackedKeys& keysLeft, const int predictedScale, const float radius,
+                      bool right) const {
+        const float trackX = predP.x, trackY = predP.y;
+        const int minX = std::max(0, (int)std::floor((trackX - radius) * keysLeft.xMult));
+        const int maxX = std::min(keysLeft.xGrids - 1, (int)std::ceil((trackX + radius) * keysLeft.xMult));
+        const int minY = std::max(0, (int)std::floor((trackY - radius) * keysLeft.yMult));
+        const int maxY = std::min(keysLeft.yGrids - 1, (int)std::ceil((trackY + radius) * keysLeft.yMult));
+        if (minX >= keysLeft.xGrids || minY >= keysLeft.yGrids || maxX < 0 || maxY < 0) return;
+        for (int row = minY; row <= maxY; row++)
+            for (int col = minX; col <= maxX; col++)
+                for (int idx : (right ? keysLeft.rkeyGrid : keysLeft.lkeyGrid)[row][col]) {
+                    const cv::KeyPoint& k = right ? keysLeft.rightKeyPoints[idx] : keysLeft.keyPoints[idx];
+                    if (k.octave > predictedScale + 1 || k.octave < predictedScale - 1) continue;
+                    if (std::fabs(k.pt.x - trackX) < radius && std::fabs(k.pt.y - trackY) < radius) idxs.push_back(idx);
+                }
+    }
+    void destributeRightKeys(const std::vector<cv::KeyPoint>& rightKeys, std::vector<std::vector<int>>& indexes) const {
+        indexes.assign(imageHeight, std::vector<int>());
+        for (size_t i = 0; i < rightKeys.size(); i++) {
+            const float y = rightKeys[i].pt.y, r = 2.0f * feLeft->scalePyramid[rightKeys[i].octave];
+            const int mx = (int)std::ceil(y + r), mn = (int)std::floor(y - r);
+            for (int p = mn; p <= mx; p++)
+                if (p >= 0 && p < imageHeight) indexes[p].push_back((int)i);
+        }
     }
 
     // src/FeatureMatcher.cpp:66-252 (LocalMapper::findNewPoints, src/OptimizationBA.cpp:367).  KeyFrameT / the Eigen types are
@@ -247,7 +361,7 @@ class FeatureMatcher {
         gvs_lba_points p{M, desc.data(), pl.data(), pr.data(), ps.data(), ll.data(), lr.data()};
         std::vector<int32_t> out(2 * (size_t)M);
         int n = 0;
-        gvsCheck(gvs_match_projection_lba(h_, &f, &p, rad, out.data(), &n));
+        gvsCheck(gvs_match_projection_lba(ensureHandle(), &f, &p, rad, out.data(), &n));
         for (int i = 0; i < M; i++)
             if (out[2 * i] != -2) matchedIdxs[i].emplace_back(std::make_pair(newKF, std::make_pair(out[2 * i], out[2 * i + 1])));
         return n;
@@ -310,7 +424,7 @@ class FeatureMatcher {
         for (int i = 0; i < N; i++) std::memcpy(&d[(size_t)i * 32], vDescriptors[i].ptr(0), 32);
         const int32_t off[2] = {0, N};
         int32_t best = -1;
-        gvsCheck(gvs_median_descriptor(h_, d.data(), off, 1, &best));
+        gvsCheck(gvs_median_descriptor(ensureHandle(), d.data(), off, 1, &best));
         return best;
     }
 
@@ -321,6 +435,15 @@ class FeatureMatcher {
         int d = 0;
         for (int i = 0; i < 8; i++) d += __builtin_popcount(pa[i] ^ pb[i]);  // one 32-byte pair: not worth a launch
         return d;
+    }
+    // the device handle (created when both extractors have seen an image: the matcher reads their resident results)
+    gvs_matcher* ensureHandle() {
+        if (!h_) {
+            if (!feLeft || !feLeft->handle() || (feRight && !feRight->handle()))
+                throw std::logic_error("FeatureMatcher: extract an image with both extractors first");
+            gvsCheck(gvs_matcher_create(&h_, feLeft->handle(), feRight ? feRight->handle() : nullptr, fx_, baseline_, imageHeight));
+        }
+        return h_;
     }
     gvs_matcher* handle() const { return h_; }
 
@@ -351,7 +474,7 @@ class FeatureMatcher {
             sl[i] = mp->scaleLevelL; sr[i] = mp->scaleLevelR; inF[i] = mp->inFrame; inFR[i] = mp->inFrameR;
         }
         const bool two = mode != 1;
-        gvsCheck(gvs_predict_mappoints(h_, mode, tc, two ? tr : nullptr, fx, fy, cx, cy, width, height, M, valid.data(), wp.data(), msd.data(),
+        gvsCheck(gvs_predict_mappoints(ensureHandle(), mode, tc, two ? tr : nullptr, fx, fy, cx, cy, width, height, M, valid.data(), wp.data(), msd.data(),
                                        ls.data(), nsl.data(), pl.data(), sl.data(), inF.data(), two ? pr.data() : nullptr,
                                        two ? sr.data() : nullptr, two ? inFR.data() : nullptr, keep.data(),
                                        matchesIdxs ? reinterpret_cast<int32_t*>(matchesIdxs->data()) : nullptr,
@@ -388,7 +511,7 @@ class FeatureMatcher {
         std::vector<uint8_t> close8;
         if (keys) close8.assign(keys->close.begin(), keys->close.end());
         int nIn = 0, nStereo = 0;
-        gvsCheck(gvs_find_outliers(h_, 0, mode, pose, toCameraR ? poseR : nullptr, fx, fy, cx, cy, thres, closeDist, M, valid.data(), wp.data(),
+        gvsCheck(gvs_find_outliers(ensureHandle(), 0, mode, pose, toCameraR ? poseR : nullptr, fx, fy, cx, cy, thres, closeDist, M, valid.data(), wp.data(),
                                    inF.data(), mode == 0 ? inFR.data() : nullptr, reinterpret_cast<int32_t*>(matchesIdxs.data()), out.data(),
                                    keys ? keys->estimatedDepth.data() : nullptr, keys ? close8.data() : nullptr,
                                    keys ? keys->rightIdxs.data() : nullptr, keys ? keys->leftIdxs.data() : nullptr, &nIn, &nStereo));
@@ -403,7 +526,7 @@ class FeatureMatcher {
         const int n = off[1];
         if (n <= 0) return;
         k.assign(n, cv::KeyPoint());
-        d = cv::Mat(n, 32, cv::CV_8U);
+        d = cv::Mat(n, 32, GVS_CV_8U);
         gvsCheck(gvs_extract_download(fe.handle(), 0, 1, reinterpret_cast<gvs_keypoint*>(k.data()), d.data, n));
     }
     template <class MapPointT>
@@ -415,6 +538,9 @@ class FeatureMatcher {
         std::vector<uint8_t> inl(M), inr(M), desc((size_t)M * 32);
         for (int i = 0; i < M; i++) {
             const MapPointT* mp = mps[i];
+            // the reference skips an already matched point before it touches mp (:259-263), so a null entry there is harmless:
+            // its slot stays zero / out of frame (an unmatched null entry is a null dereference in the reference as well)
+            if (!mp && (matches[i].first >= 0 || matches[i].second >= 0)) continue;
             pl[2 * i] = mp->predL.x; pl[2 * i + 1] = mp->predL.y; pr[2 * i] = mp->predR.x; pr[2 * i + 1] = mp->predR.y;
             ll[i] = mp->scaleLevelL; lr[i] = mp->scaleLevelR; inl[i] = mp->inFrame; inr[i] = mp->inFrameR;
             std::memcpy(&desc[(size_t)i * 32], mp->desc.ptr(0), 32);
@@ -422,11 +548,13 @@ class FeatureMatcher {
         gvs_mappoints s{M, desc.data(), pl.data(), pr.data(), ll.data(), lr.data(), inl.data(), inr.data()};
         static_assert(sizeof(std::pair<int, int>) == 8, "pair<int,int> must be two packed ints");
         int n = 0;
-        gvsCheck(gvs_match_projection(h_, 0, mode, &s, rad, mL.data(), mR ? mR->data() : nullptr,
+        gvsCheck(gvs_match_projection(ensureHandle(), 0, mode, &s, rad, mL.data(), mR ? mR->data() : nullptr,
                                       reinterpret_cast<int32_t*>(matches.data()), &n));
         return n;
     }
     gvs_matcher* h_ = nullptr;
+    double fx_ = 0;
+    float baseline_ = 0;
 };
 
 }  // namespace GTSAM_VIOSLAM

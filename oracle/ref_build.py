@@ -260,3 +260,93 @@ def track_frames(params, fx, baseline, L: np.ndarray, R: np.ndarray, shape: int,
     tot = lib().ref_track_frames(nF, nL, C.c_float(s), e, p, mx, mn, C.c_double(fx), C.c_float(baseline),
                                  _p(L), _p(R), F, w, h, shape, threads, _p(nk), *extra)
     return tot, nk, nt
+
+
+class RefTracker:
+    """The reference's FeatureTracker object (src/FeatureTracker.cpp:23) for the functions of it that oracle/slice_reference.py
+    compiles from the reference source: assignKeysToGrids, initializeMap, check2dError, findOutliersR / Mono, worldToFrame,
+    removeOutOfFrameMPs / Mono, PredictMPsPosition -- and, through them, MapPoint (src/Map.cpp, compiled whole)."""
+
+    def __init__(self, feL: RefExtractor, feR: RefExtractor, fx, fy, cx, cy, baseline, width, height, extrinsics=None):
+        self.feL, self.feR = feL, feR
+        ext = np.ascontiguousarray(np.eye(4) if extrinsics is None else extrinsics, np.float64)
+        lib().ref_tracker_create.restype = C.c_void_p
+        lib().ref_tracker_destroy.argtypes = [C.c_void_p]
+        self.h = C.c_void_p(lib().ref_tracker_create(feL.h, feR.h, C.c_double(fx), C.c_double(fy), C.c_double(cx), C.c_double(cy),
+                                                     C.c_float(baseline), int(width), int(height), _p(ext)))
+
+    def __del__(self):
+        try:
+            lib().ref_tracker_destroy(self.h)
+        except Exception:
+            pass
+
+    def cameras(self, predNPose):
+        """(toCamera, toCameraR) = (predNPose^-1, (predNPose * extrinsics)^-1) with this build's arithmetic (:913-914)."""
+        a = np.zeros((4, 4)); b = np.zeros((4, 4))
+        lib().ref_tracker_cameras(self.h, _p(np.ascontiguousarray(predNPose, np.float64)), _p(a), _p(b))
+        return a, b
+
+    def outlier_cameras(self, estimPose):
+        """toCameraR = (estimPose^-1 * extrinsics)^-1 (:584-585)."""
+        a = np.zeros((4, 4))
+        lib().ref_outlier_cameras(self.h, _p(np.ascontiguousarray(estimPose, np.float64)), _p(a))
+        return a
+
+    def assign_grid(self, kps, width: int, height: int):
+        """FeatureTracker::assignKeysToGrids (:28-54) in CSR form (same dict as oracle.cpu_ref.assign_grid)."""
+        kps = np.ascontiguousarray(kps)
+        n = len(kps)
+        start = np.zeros(64 * 513 + 1, np.int32); items = np.zeros(max(n, 1), np.int32)
+        xm, ym = C.c_float(), C.c_float()
+        yg = lib().ref_assign_grid(self.h, _p(kps), n, width, height, _p(start), _p(items), C.byref(xm), C.byref(ym))
+        return dict(xGrids=64, yGrids=yg, xMult=xm.value, yMult=ym.value, start=start[:yg * 64 + 1].copy(), items=items[:n].copy())
+
+    def predict_mappoints(self, mode, currCamPose, predNPose, valid, wPos, maxScaleDist, logScale, nScaleLev, predL, scaleLevelL, inFrame,
+                          predR=None, scaleLevelR=None, inFrameR=None, matches=None, matchedL=None, matchedR=None, outliers=None):
+        """removeOutOfFrameMPs (0) / ...Mono (1) / PredictMPsPosition (2) of the reference; in-out arrays in place; keep or None."""
+        c = lambda a, dt: None if a is None else np.ascontiguousarray(a, dt)
+        M = len(wPos)
+        keep = np.zeros(M, np.uint8)
+        k = [c(currCamPose, np.float64), c(predNPose, np.float64), c(valid, np.uint8), c(wPos, np.float64), c(maxScaleDist, np.float32),
+             c(logScale, np.float32), c(nScaleLev, np.int32)]
+        lib().ref_predict_mappoints(self.h, mode, _p(k[0]), _p(k[1]), M, _p(k[2]), _p(k[3]), _p(k[4]), _p(k[5]), _p(k[6]), _p(predL),
+                                    _p(scaleLevelL), _p(inFrame), _p(predR), _p(scaleLevelR), _p(inFrameR), _p(keep), _p(matches),
+                                    _p(matchedL), 0 if matchedL is None else len(matchedL), _p(matchedR),
+                                    0 if matchedR is None else len(matchedR), _p(outliers))
+        return keep if mode != 2 else None
+
+    def find_outliers(self, mode, estimPose, thres, valid, wPos, inFrame, inFrameR, matches, outliers, kl, kr, depth, close, rightIdxs,
+                      leftIdxs):
+        """findOutliersR (0) / findOutliersMono (1) of the reference; returns (nInliers increments, nStereo)."""
+        c = lambda a, dt: None if a is None else np.ascontiguousarray(a, dt)
+        cnt = np.zeros(2, np.int32)
+        keep = [c(estimPose, np.float64), c(valid, np.uint8), c(wPos, np.float64), c(inFrame, np.uint8), c(inFrameR, np.uint8),
+                np.ascontiguousarray(kl), None if kr is None else np.ascontiguousarray(kr)]
+        lib().ref_find_outliers(self.h, mode, _p(keep[0]), C.c_double(thres), len(matches), _p(keep[1]), _p(keep[2]), _p(keep[3]), _p(keep[4]),
+                                _p(matches), _p(outliers), _p(keep[5]), len(kl), _p(keep[6]), 0 if kr is None else len(kr), _p(depth),
+                                _p(close), _p(rightIdxs), _p(leftIdxs), _p(cnt))
+        return int(cnt[0]), int(cnt[1])
+
+    def temporal_mappoints(self, kl, dl, kr, dr, rightIdxs, depth, posePrev, predNPose):
+        """initializeMap (:72-123, MapPoint::update / calcDescriptor inside) on a frame's stereo keys, then removeOutOfFrameMPs."""
+        c = lambda a, dt: np.ascontiguousarray(a, dt)
+        kl = np.ascontiguousarray(kl); kr = np.ascontiguousarray(kr)
+        n = max(len(kl), 1)
+        key = np.zeros(n, np.int32); pL = np.zeros((n, 2), np.float32); pR = np.zeros((n, 2), np.float32)
+        lL = np.zeros(n, np.int32); lR = np.zeros(n, np.int32); wp = np.zeros((n, 4)); msd = np.zeros(n, np.float32)
+        desc = np.zeros((n, 32), np.uint8)
+        keep = [c(dl, np.uint8), c(dr, np.uint8), c(rightIdxs, np.int32), c(depth, np.float32), c(posePrev, np.float64), c(predNPose, np.float64)]
+        M = lib().ref_temporal_mappoints(self.h, _p(kl), _p(keep[0]), len(kl), _p(kr), _p(keep[1]), len(kr), _p(keep[2]), _p(keep[3]),
+                                         _p(keep[4]), _p(keep[5]), _p(key), _p(pL), _p(pR), _p(lL), _p(lR), _p(wp), _p(msd), _p(desc))
+        return dict(key=key[:M].copy(), predL=pL[:M].copy(), predR=pR[:M].copy(), scaleLevelL=lL[:M].copy(), scaleLevelR=lR[:M].copy(),
+                    wPos=wp[:M].copy(), maxScaleDist=msd[:M].copy(), desc=desc[:M].copy())
+
+
+def median_descriptor(descs: np.ndarray):
+    """MapPoint::calcDescriptor (src/Map.cpp:145-210) on one observation list: (order in which the reference visits the
+    observations, the 32 bytes it keeps)."""
+    descs = np.ascontiguousarray(descs, np.uint8).reshape(-1, 32)
+    order = np.zeros(max(len(descs), 1), np.int32); chosen = np.zeros(32, np.uint8)
+    lib().ref_median_descriptor(_p(descs), len(descs), _p(order), _p(chosen))
+    return order[:len(descs)].copy(), chosen

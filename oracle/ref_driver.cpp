@@ -3,15 +3,18 @@
 // C entry points around the reference's OWN FeatureExtractor and FeatureMatcher (compiled unmodified from
 // /root/reference/src/FeatureExtractor.cpp and src/FeatureMatcher.cpp against oracle/shim, see oracle/Makefile target
 // `ref`), so that python tests can run them next to the restatement (oracle/cpu_ref.cpp) and generate golden vectors.
-// Only objects and members the reference declares public are touched.  The reference's Map.cpp / KeyFrame.cpp /
-// Camera.cpp are not on the path and not compiled; the few constructors of their classes that this driver needs in order
-// to hand objects to the matcher are defined at the bottom of this file as plain member initialisations.
+// Only objects and members the reference declares public are touched.  Also compiled into the library: the reference's
+// src/Map.cpp (unmodified, whole) and the functions of src/FeatureTracker.cpp listed in oracle/slice_reference.py (bodies copied by
+// line range into a generated file at build time; the whole file needs GTSAM).  KeyFrame.cpp / Camera.cpp are not on the path
+// and not compiled; the three constructors of their classes that this driver needs in order to hand objects to the reference
+// code are defined at the bottom of this file as plain member initialisations.
 #include <atomic>
 #include <cstring>
 #include <thread>
 #include <vector>
 
-#include "FeatureMatcher.h"   // reference header: pulls Settings.h, Camera.h, Map.h, KeyFrame.h, FeatureExtractor.h
+#include "FeatureTracker.h"   // reference header (with oracle/shim/gtsam/navigation/ImuBias.h standing in for GTSAM): pulls
+                              // FeatureMatcher.h, Settings.h, Camera.h, Map.h, KeyFrame.h, FeatureExtractor.h, Conversions.h
 #include "ref_hooks.h"
 
 // default primitives: the cv2-pinned restatements exported by liboracle.so (oracle/cpu_ref.cpp)
@@ -357,17 +360,244 @@ int ref_descriptor_distance(const uint8_t* a, const uint8_t* b) {
 
 }  // extern "C"
 
+
+// ---- FeatureTracker functions next to the path (reference src/FeatureTracker.cpp, bodies compiled from the reference source by
+// oracle/slice_reference.py) and MapPoint (src/Map.cpp, compiled whole) ------------------------------------------------------
+namespace {
+Eigen::Matrix4d mat4(const double* rowMajor) {
+    Eigen::Matrix4d m;
+    for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) m(r, c) = rowMajor[4 * r + c];
+    return m;
+}
+void mat4Out(const Eigen::Matrix4d& m, double* rowMajor) {
+    for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) rowMajor[4 * r + c] = m(r, c);
+}
+struct Tracker {
+    std::shared_ptr<StereoCamera> zed;
+    ExtractorPtr feL, feR;
+    std::shared_ptr<Map> map;
+    std::unique_ptr<FeatureTracker> ft;
+};
+// a key frame that carries what MapPoint::predictScale reads (lastObsKF->logScale / nScaleLev)
+KeyFrame* scaleKF(float logScale, int nScaleLev) {
+    cv::Mat none;
+    KeyFrame* kf = new KeyFrame(Eigen::Matrix4d::Identity(), none, none, 0, 0);
+    kf->logScale = logScale; kf->nScaleLev = nScaleLev;
+    return kf;
+}
+}  // namespace
+
+extern "C" {
+
+// FeatureTracker::FeatureTracker (src/FeatureTracker.cpp:23) on a camera described by the values the functions below read
+void* ref_tracker_create(void* feL, void* feR, double fx, double fy, double cx, double cy, float baseline, int width, int height,
+                         const double* extrinsics) {
+    Tracker* t = new Tracker;
+    t->zed = std::make_shared<StereoCamera>();
+    t->zed->mBaseline = baseline; t->zed->mWidth = width; t->zed->mHeight = height;
+    t->zed->mCameraLeft = std::make_shared<Camera>(nullptr, std::string());
+    t->zed->mCameraLeft->fx = fx; t->zed->mCameraLeft->fy = fy; t->zed->mCameraLeft->cx = cx; t->zed->mCameraLeft->cy = cy;
+    if (extrinsics) t->zed->extrinsics = mat4(extrinsics);
+    t->feL = *(ExtractorPtr*)feL; t->feR = *(ExtractorPtr*)feR;
+    t->map = std::make_shared<Map>();
+    t->ft.reset(new FeatureTracker(t->zed, t->feL, t->feR, t->map));
+    return t;
+}
+void ref_tracker_destroy(void* h) { delete (Tracker*)h; }
+
+// the matrices the reference derives from its pose arguments, with the arithmetic of THIS build (mini-Eigen inverse): tests give
+// exactly these to the CUDA entry points, whose callers compute them on the host as well (include/gvs.h)
+void ref_tracker_cameras(void* h, const double* predNPose, double* toCamera, double* toCameraR) {   // :913-914, :972-973
+    Tracker* t = (Tracker*)h;
+    const Eigen::Matrix4d P = mat4(predNPose);
+    mat4Out(P.inverse(), toCamera);
+    mat4Out((P * t->zed->extrinsics).inverse(), toCameraR);
+}
+void ref_outlier_cameras(void* h, const double* estimPose, double* toCameraR) {   // :584-585
+    Tracker* t = (Tracker*)h;
+    const Eigen::Matrix4d E = mat4(estimPose);
+    mat4Out((E.inverse() * t->zed->extrinsics).inverse(), toCameraR);
+}
+
+// FeatureTracker::assignKeysToGrids (:28-54), CSR out (start: yGrids * 64 + 1 entries); returns yGrids
+int ref_assign_grid(void* h, const void* kps, int n, int width, int height, int* start, int* items, float* xMult, float* yMult) {
+    Tracker* t = (Tracker*)h;
+    TrackedKeys keys;
+    std::vector<cv::KeyPoint> k = keyVector(kps, n);
+    std::vector<std::vector<std::vector<int>>> grid;
+    t->ft->assignKeysToGrids(keys, k, grid, width, height);
+    int run = 0;
+    for (int r = 0; r < keys.yGrids; ++r)
+        for (int c = 0; c < keys.xGrids; ++c) {
+            start[r * keys.xGrids + c] = run;
+            for (int v : grid[r][c]) items[run++] = v;
+        }
+    start[keys.yGrids * keys.xGrids] = run;
+    *xMult = keys.xMult; *yMult = keys.yMult;
+    return keys.yGrids;
+}
+
+// removeOutOfFrameMPs (:910-940; mode 0), removeOutOfFrameMPsMono (:942-967; mode 1), PredictMPsPosition (:969-1013; mode 2) on map
+// points rebuilt from flat arrays (same contract as ora_predict_mappoints, but the POSE predNPose goes in: the reference inverts
+// it itself).  valid[i] == 0 stands for a null entry (mode 2) / an outlier map point (modes 0/1).
+void ref_predict_mappoints(void* h, int mode, const double* currCamPose, const double* predNPose, int M, const uint8_t* valid,
+                           const double* wPos, const float* maxScaleDist, const float* logScale, const int* nScaleLev, float* predL,
+                           int* scaleLevelL, uint8_t* inFrame, float* predR, int* scaleLevelR, uint8_t* inFrameR, uint8_t* keep, int* matches,
+                           int* matchedL, int nL, int* matchedR, int nR, uint8_t* outliers) {
+    Tracker* t = (Tracker*)h;
+    std::vector<MapPoint*> mps(M, nullptr), all;
+    std::vector<KeyFrame*> kfs;
+    cv::KeyPoint obs;
+    cv::Mat d(1, 32, CV_8U);
+    for (int i = 0; i < M; ++i) {
+        const bool ok = !valid || valid[i];
+        if (mode == 2 && !ok) continue;   // null entry
+        MapPoint* mp = new MapPoint(Eigen::Vector4d(wPos[4 * i], wPos[4 * i + 1], wPos[4 * i + 2], wPos[4 * i + 3]), d, obs, 0, (unsigned long)i);
+        KeyFrame* kf = scaleKF(logScale[i], nScaleLev[i]);
+        kfs.push_back(kf);
+        mp->lastObsKF = kf; mp->maxScaleDist = maxScaleDist[i];
+        mp->predL = cv::Point2f(predL[2 * i], predL[2 * i + 1]); mp->scaleLevelL = scaleLevelL[i]; mp->inFrame = inFrame[i] != 0;
+        if (mode != 1) { mp->predR = cv::Point2f(predR[2 * i], predR[2 * i + 1]); mp->scaleLevelR = scaleLevelR[i]; mp->inFrameR = inFrameR[i] != 0; }
+        if (!ok) mp->SetIsOutlier(true);
+        mps[i] = mp; all.push_back(mp);
+    }
+    const Eigen::Matrix4d C = mat4(currCamPose), P = mat4(predNPose);
+    if (mode == 2) {
+        std::vector<int> mL(matchedL, matchedL + nL), mR(matchedR, matchedR + nR);
+        std::vector<std::pair<int, int>> pairs(M);
+        std::vector<bool> out(M);
+        for (int i = 0; i < M; ++i) { pairs[i] = {matches[2 * i], matches[2 * i + 1]}; out[i] = outliers[i] != 0; }
+        t->ft->PredictMPsPosition(C, P, mps, mL, mR, pairs, out);
+        std::memcpy(matchedL, mL.data(), (size_t)nL * sizeof(int)); std::memcpy(matchedR, mR.data(), (size_t)nR * sizeof(int));
+        for (int i = 0; i < M; ++i) { matches[2 * i] = pairs[i].first; matches[2 * i + 1] = pairs[i].second; outliers[i] = out[i]; }
+    } else {
+        std::vector<MapPoint*> act = mps;
+        if (mode == 0) t->ft->removeOutOfFrameMPs(C, P, act); else t->ft->removeOutOfFrameMPsMono(C, P, act);
+        for (int i = 0; i < M; ++i) keep[i] = 0;
+        for (MapPoint* mp : act) keep[mp->idx] = 1;
+    }
+    for (int i = 0; i < M; ++i) {
+        MapPoint* mp = mps[i];
+        if (!mp) continue;
+        predL[2 * i] = mp->predL.x; predL[2 * i + 1] = mp->predL.y; scaleLevelL[i] = mp->scaleLevelL; inFrame[i] = mp->inFrame;
+        if (mode != 1) { predR[2 * i] = mp->predR.x; predR[2 * i + 1] = mp->predR.y; scaleLevelR[i] = mp->scaleLevelR; inFrameR[i] = mp->inFrameR; }
+    }
+    for (MapPoint* mp : all) delete mp;
+    for (KeyFrame* kf : kfs) delete kf;
+}
+
+// findOutliersR (:582-649; mode 0) / findOutliersMono (:651-684; mode 1) with check2dError (:147-164); same contract as
+// ora_find_outliers except that the reference computes toCameraR from estimPose and the extrinsics itself
+void ref_find_outliers(void* h, int mode, const double* estimPose, double thres, int M, const uint8_t* valid, const double* wPos,
+                       const uint8_t* inFrame, const uint8_t* inFrameR, int* matches, uint8_t* outliers, const void* kl, int NL,
+                       const void* kr, int NR, float* depth, uint8_t* close, int* rightIdxs, int* leftIdxs, int* counts) {
+    Tracker* t = (Tracker*)h;
+    TrackedKeys keys;
+    keys.keyPoints = keyVector(kl, NL);
+    if (kr) keys.rightKeyPoints = keyVector(kr, NR);
+    if (mode == 0) {
+        keys.estimatedDepth.assign(depth, depth + NL); keys.rightIdxs.assign(rightIdxs, rightIdxs + NL); keys.leftIdxs.assign(leftIdxs, leftIdxs + NR);
+        keys.close.resize(NL);
+        for (int i = 0; i < NL; ++i) keys.close[i] = close[i] != 0;
+    }
+    std::vector<MapPoint*> mps(M, nullptr);
+    cv::KeyPoint obs;
+    cv::Mat d(1, 32, CV_8U);
+    for (int i = 0; i < M; ++i) {
+        if (valid && !valid[i]) continue;
+        MapPoint* mp = new MapPoint(Eigen::Vector4d(wPos[4 * i], wPos[4 * i + 1], wPos[4 * i + 2], wPos[4 * i + 3]), d, obs, 0, (unsigned long)i);
+        mp->inFrame = inFrame ? inFrame[i] != 0 : true; mp->inFrameR = inFrameR ? inFrameR[i] != 0 : true;
+        mps[i] = mp;
+    }
+    std::vector<std::pair<int, int>> pairs(M);
+    std::vector<bool> out(M);
+    for (int i = 0; i < M; ++i) { pairs[i] = {matches[2 * i], matches[2 * i + 1]}; out[i] = outliers[i] != 0; }
+    std::vector<float> weights;
+    int nInliers = 0, nStereo = 0;
+    const Eigen::Matrix4d E = mat4(estimPose);
+    if (mode == 0) nStereo = t->ft->findOutliersR(E, mps, keys, pairs, thres, out, weights, nInliers);
+    else t->ft->findOutliersMono(E, mps, keys, pairs, thres, out, weights, nInliers);
+    for (int i = 0; i < M; ++i) { matches[2 * i] = pairs[i].first; matches[2 * i + 1] = pairs[i].second; outliers[i] = out[i]; }
+    if (mode == 0) {
+        for (int i = 0; i < NL; ++i) { depth[i] = keys.estimatedDepth[i]; close[i] = keys.close[i]; rightIdxs[i] = keys.rightIdxs[i]; }
+        for (int i = 0; i < NR; ++i) leftIdxs[i] = keys.leftIdxs[i];
+    }
+    counts[0] = nInliers; counts[1] = nStereo;
+    for (MapPoint* mp : mps) delete mp;
+}
+
+// The map points of the temporal step, built by the reference itself: FeatureTracker::initializeMap (:72-123) on the stereo keys of
+// a frame tracked at camera pose posePrev (MapPoint::MapPoint / MapPoint::update / MapPoint::calcDescriptor of src/Map.cpp run inside),
+// then FeatureTracker::removeOutOfFrameMPs (:910-940) with predNPose.  Outputs per surviving point, in order: source key, predL/R,
+// scaleLevelL/R, world position, maxScaleDist, descriptor.  Returns their number.
+int ref_temporal_mappoints(void* h, const void* kl, const uint8_t* dl, int NL, const void* kr, const uint8_t* dr, int NR,
+                           const int* rightIdxs, const float* depth, const double* posePrev, const double* predNPose, int* mpKey,
+                           float* predL, float* predR, int* lvlL, int* lvlR, double* wPos, float* maxScaleDist, uint8_t* desc) {
+    Tracker* t = (Tracker*)h;
+    // a fresh tracker state per call: initializeMap appends to the map
+    Tracker fresh;
+    fresh.zed = std::make_shared<StereoCamera>(*t->zed);
+    fresh.zed->mCameraPose.pose = mat4(posePrev);
+    fresh.feL = t->feL; fresh.feR = t->feR; fresh.map = std::make_shared<Map>();
+    fresh.ft.reset(new FeatureTracker(fresh.zed, fresh.feL, fresh.feR, fresh.map));
+    TrackedKeys keys;
+    keys.keyPoints = keyVector(kl, NL); keys.Desc = descMat(dl, NL);
+    keys.rightKeyPoints = keyVector(kr, NR); keys.rightDesc = descMat(dr, NR);
+    keys.rightIdxs.assign(rightIdxs, rightIdxs + NL); keys.estimatedDepth.assign(depth, depth + NL);
+    keys.leftIdxs.assign(NR, -1); keys.close.assign(NL, false);
+    fresh.ft->initializeMap(keys);
+    std::vector<MapPoint*> all = fresh.map->activeMapPoints;
+    KeyFrame* kf = all.empty() ? nullptr : all[0]->lastObsKF;
+    fresh.ft->removeOutOfFrameMPs(mat4(posePrev), mat4(predNPose), fresh.map->activeMapPoints);
+    int M = 0;
+    for (MapPoint* mp : fresh.map->activeMapPoints) {
+        mpKey[M] = mp->kFMatches[kf].first;
+        predL[2 * M] = mp->predL.x; predL[2 * M + 1] = mp->predL.y; predR[2 * M] = mp->predR.x; predR[2 * M + 1] = mp->predR.y;
+        lvlL[M] = mp->scaleLevelL; lvlR[M] = mp->scaleLevelR;
+        if (wPos) for (int c = 0; c < 4; ++c) wPos[4 * M + c] = mp->wp(c);
+        if (maxScaleDist) maxScaleDist[M] = mp->maxScaleDist;
+        if (desc) std::memcpy(desc + (size_t)M * 32, mp->desc.ptr(0), 32);
+        ++M;
+    }
+    for (MapPoint* mp : all) delete mp;
+    for (auto& kv : fresh.map->keyFrames) delete kv.second;
+    return M;
+}
+
+// MapPoint::calcDescriptor (src/Map.cpp:145-210) for one map point observed by n key frames (one left descriptor each).  The
+// reference walks an unordered_map<KeyFrame*, ...>: order[] receives the order in which it visits the observations (ties are
+// resolved by that order), chosen[] the 32 bytes it picks.
+void ref_median_descriptor(const uint8_t* descs, int n, int* order, uint8_t* chosen) {
+    cv::KeyPoint obs;
+    MapPoint mp(Eigen::Vector4d(0, 0, 0, 1), descMat(descs, n ? 1 : 0), obs, 0, 0);
+    std::vector<KeyFrame*> kfs(n);
+    cv::Mat none;
+    for (int i = 0; i < n; ++i) {
+        kfs[i] = new KeyFrame(Eigen::Matrix4d::Identity(), none, none, i, i);
+        kfs[i]->keys.Desc = descMat(descs + (size_t)i * 32, 1);
+        mp.kFMatches.insert({kfs[i], {0, -1}});
+    }
+    {
+        std::unordered_map<KeyFrame*, std::pair<int, int>> observations = mp.kFMatches;   // the copy the reference iterates (:150)
+        int k = 0;
+        for (auto& kv : observations) order[k++] = (int)kv.first->numb;
+    }
+    mp.calcDescriptor();
+    std::memcpy(chosen, mp.desc.ptr(0), 32);
+    for (KeyFrame* kf : kfs) delete kf;
+}
+
+}  // extern "C"
+
 // ---- link stubs -----------------------------------------------------------------------------------------------------
-// Constructors that the reference defines in files which are not on the path (src/Map.cpp, src/KeyFrame.cpp,
-// src/Camera.cpp) and which this driver needs to create the objects the matcher reads.  They only initialise members; no
+// Constructors that the reference defines in files which are not on the path (src/KeyFrame.cpp, src/Camera.cpp) and which this driver needs to create the objects the matcher reads.  They only initialise members; no
 // behaviour of the reference is restated here.
 namespace GTSAM_VIOSLAM {
 CameraPose::CameraPose(Eigen::Matrix4d _pose, std::chrono::time_point<std::chrono::high_resolution_clock> _timestamp)
     : pose(_pose), timestamp(_timestamp) {}
 Camera::Camera(std::shared_ptr<ConfigFile> configFile, const std::string&) : mConfigFile(configFile) {}
-MapPoint::MapPoint(const Eigen::Vector4d& p, const cv::Mat& _desc, const cv::KeyPoint& obsK, const unsigned long _kdx,
-                   const unsigned long _idx)
-    : wp(p), lastObsL(obsK), lastObsKF(nullptr), desc(_desc), kdx(_kdx), idx(_idx) {}
+// src/Camera.cpp:22-25; referenced by MapPoint::updatePos (src/Map.cpp:224), which nothing here calls
+Eigen::Matrix4d CameraPose::getInvPose() const { return poseInverse; }
 KeyFrame::KeyFrame(Eigen::Matrix4d _pose, cv::Mat& _leftIm, cv::Mat& rLIm, const int _numb, const int _frameIdx)
     : pose(_pose), leftIm(_leftIm), rLeftIm(rLIm), numb(_numb), frameIdx(_frameIdx) {}
 }  // namespace GTSAM_VIOSLAM

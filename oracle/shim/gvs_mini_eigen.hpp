@@ -1,6 +1,8 @@
 // oracle/shim/gvs_mini_eigen.hpp — TEST INFRASTRUCTURE ONLY.  Fixed-size double matrices with the few operations the
 // reference's matcher uses: construction from coefficients, (i,j) / (i) access, block<R,C>(i,j) read views and
-// assignment, +, -, *, norm(), Identity(), Zero(), inverse() for 4x4 rigid transforms is NOT provided (unused here).
+// assignment, +, -, *, norm(), Identity(), Zero(), and inverse() of square matrices (Gauss-Jordan with partial pivoting in
+// double: correct to rounding, not bit-identical to Eigen's cofactor kernels -- tests therefore hand the SAME inverted
+// matrices to both sides, see ref_mat4_inverse in oracle/ref_driver.cpp).
 #pragma once
 #include <cmath>
 #include <cstdlib>
@@ -70,6 +72,26 @@ public:
     Matrix<T, R, K> operator*(const Matrix<T, C, K>& o) const {
         Matrix<T, R, K> m;
         for (int r = 0; r < R; ++r) for (int k = 0; k < K; ++k) { T s = T(0); for (int c = 0; c < C; ++c) s += (*this)(r, c) * o(c, k); m(r, k) = s; }
+        return m;
+    }
+    Matrix inverse() const {
+        static_assert(R == C, "inverse of a square matrix");
+        T a[R][2 * R];
+        for (int r = 0; r < R; ++r) for (int c = 0; c < R; ++c) { a[r][c] = (*this)(r, c); a[r][R + c] = r == c ? T(1) : T(0); }
+        for (int p = 0; p < R; ++p) {
+            int best = p;
+            for (int r = p + 1; r < R; ++r) if (std::fabs(a[r][p]) > std::fabs(a[best][p])) best = r;
+            if (best != p) for (int c = 0; c < 2 * R; ++c) { const T t = a[p][c]; a[p][c] = a[best][c]; a[best][c] = t; }
+            const T d = a[p][p];
+            for (int c = 0; c < 2 * R; ++c) a[p][c] /= d;
+            for (int r = 0; r < R; ++r) {
+                if (r == p) continue;
+                const T f = a[r][p];
+                if (f != T(0)) for (int c = 0; c < 2 * R; ++c) a[r][c] -= f * a[p][c];
+            }
+        }
+        Matrix m;
+        for (int r = 0; r < R; ++r) for (int c = 0; c < R; ++c) m(r, c) = a[r][R + c];
         return m;
     }
     T trace() const { T s = T(0); for (int i = 0; i < (R < C ? R : C); ++i) s += (*this)(i, i); return s; }

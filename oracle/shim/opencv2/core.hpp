@@ -194,6 +194,17 @@ public:
     void create(Size s, int type) { create(s.height, s.width, type); }
     void release() { owner_.reset(); data = nullptr; rows = cols = 0; step = 0; }
 
+    // cv::Mat::push_back(const Mat&): appends the rows of m (same type and width; an empty matrix adopts them)
+    void push_back(const Mat& m) {
+        if (m.empty()) return;
+        GVS_SHIM_REQUIRE(empty() || (m.cols == cols && m.flags == flags), "push_back: type / width mismatch");
+        Mat out(rows + m.rows, m.cols, m.flags);
+        const size_t rb = (size_t)m.cols * m.elemSize();
+        for (int y = 0; y < rows; ++y) std::memcpy(out.ptr(y), ptr(y), rb);
+        for (int y = 0; y < m.rows; ++y) std::memcpy(out.ptr(rows + y), m.ptr(y), rb);
+        *this = out;
+    }
+
     uchar* ptr(int r = 0) { return data + (size_t)r * step; }
     const uchar* ptr(int r = 0) const { return data + (size_t)r * step; }
     template <class T> T* ptr(int r = 0) { return (T*)(data + (size_t)r * step); }

@@ -22,6 +22,9 @@ struct Mat4 {
     Mat4 operator*(const Mat4& o) const { Mat4 m; for (int i = 0; i < 3; i++) m.t[i] = t[i] + o.t[i]; return m; }
 };
 struct KeyFrameStub { float logScale; int nScaleLev; };
+// stand-ins for the reference's StereoCamera / Camera (include/Camera.h:72,86): the members the matcher constructor reads
+struct CameraStub { double fx = 0; };
+struct StereoCameraStub { std::shared_ptr<CameraStub> mCameraLeft; float mBaseline = 0; };
 struct MapPoint {
     cv::Mat desc; cv::Point2f predL, predR; int scaleLevelL = 0, scaleLevelR = 0; bool inFrame = true, inFrameR = true;
     Vec4 wp{{0, 0, 0, 1}};
@@ -38,9 +41,14 @@ int main(int argc, char** argv) {
     FILE* f = std::fopen(argv[1], "rb"); if (!f || std::fread(L.data, 1, (size_t)w * h, f) != (size_t)w * h) return 3; std::fclose(f);
     f = std::fopen(argv[2], "rb"); if (!f || std::fread(R.data, 1, (size_t)w * h, f) != (size_t)w * h) return 3; std::fclose(f);
     try {
-        auto feL = std::make_shared<FeatureExtractor>(nF, nL, 1.2f, 19, 31, 20, 7, w, h);
-        auto feR = std::make_shared<FeatureExtractor>(nF, nL, 1.2f, 19, 31, 20, 7, w, h);
-        FeatureMatcher fm(200.0, 0.1f, feL, feR, h);
+        // exactly the reference's argument lists: include/FeatureExtractor.h:80 (src/System.cpp:56-57), include/FeatureMatcher.h:40
+        // (src/FeatureTracker.cpp:23); the default constructor of src/System.cpp:31 is exercised below
+        auto feL = std::make_shared<FeatureExtractor>(nF, nL, 1.2f, 19, 31, 20, 7);
+        auto feR = std::make_shared<FeatureExtractor>(nF, nL, 1.2f, 19, 31, 20, 7);
+        auto zed = std::make_shared<StereoCameraStub>();
+        zed->mCameraLeft = std::make_shared<CameraStub>(); zed->mCameraLeft->fx = 200.0; zed->mBaseline = 0.1f;
+        if ((int)feL->scalePyramid.size() != nL || feL->featurePerLevel.empty()) return 4;   // tables are public before the first image
+        FeatureMatcher fm(zed, feL, feR, h);
         TrackedKeys k;
         fm.extractORBAndStereoMatch(L, R, k);
         int matches = 0;
@@ -112,6 +120,36 @@ int main(int argc, char** argv) {
         int active = 0;
         for (auto& mp : store) active += mp.isActive;
         std::printf("remove kept %zu active %d\n", act.size(), active);
+        // matchByRadius with the reference's seven arguments (include/FeatureMatcher.h:63, call site src/FeatureTracker.cpp:1518):
+        // the right keys of this frame against its left keys; matchedIdxsL is in-out, matchesIdxs stays untouched
+        fm.extractORBAndStereoMatch(L, R, k);
+        TrackedKeys last;
+        last.keyPoints = k.rightKeyPoints; last.Desc = k.rightDesc.clone();
+        std::vector<int> mRad(k.keyPoints.size(), -1);
+        std::vector<std::pair<int, int>> untouched(last.keyPoints.size(), {-7, -7});
+        std::vector<std::vector<std::pair<KeyFrameStub*, int>>> kfMatches(last.keyPoints.size());
+        KeyFrameStub actKF{0.f, nL};
+        const int nRad = fm.matchByRadius(last, k, mRad, untouched, 120.0f, kfMatches, &actKF);
+        int appended = 0, same = 1;
+        std::vector<int> radIdx(last.keyPoints.size(), -1);
+        for (size_t i = 0; i < kfMatches.size(); i++) { appended += (int)kfMatches[i].size(); if (!kfMatches[i].empty()) { radIdx[i] = kfMatches[i].back().second; same &= kfMatches[i].back().first == &actKF; } }
+        for (auto& p : untouched) same &= p.first == -7 && p.second == -7;
+        std::printf("radius %d appended %d ok %d idx %016llx mL %016llx\n", nRad, appended, same, (unsigned long long)fnv(radIdx.data(), radIdx.size() * 4),
+                    (unsigned long long)fnv(mRad.data(), mRad.size() * 4));
+        // the default constructor (src/System.cpp:31: mono, 2000 features, 8 levels), imagePyramid mirror, the public ssc helper
+        auto feM = std::make_shared<FeatureExtractor>();
+        feM->mirrorImagePyramid = true;
+        std::vector<cv::KeyPoint> km; cv::Mat dm;
+        feM->extractKeysNew(L, km, dm);
+        uint64_t ph = 1469598103934665603ull;
+        for (auto& m : feM->imagePyramid) ph = fnv(m.data, (size_t)m.rows * m.cols, ph);
+        std::printf("default %zu levels %zu pyr %016llx l1 %dx%d\n", km.size(), feM->imagePyramid.size(), (unsigned long long)ph,
+                    feM->imagePyramid[1].cols, feM->imagePyramid[1].rows);
+        FeatureMatcher fmMono(zed, feM, feM);   // src/System.cpp:32
+        std::vector<cv::KeyPoint> grid;
+        for (int y = 20; y < h - 20; y += 5) for (int x = 20; x < w - 20; x += 5) { cv::KeyPoint q; q.pt = cv::Point2f((float)x, (float)y); q.response = (float)(1 + (x * 7 + y * 13) % 200); grid.push_back(q); }
+        std::vector<cv::KeyPoint> keptS = feM->ssc(grid, feM->featurePerLevel[0], 0.1f, w, h);
+        std::printf("ssc %zu of %zu quota %d %016llx\n", keptS.size(), grid.size(), feM->featurePerLevel[0], (unsigned long long)fnv(keptS.data(), keptS.size() * sizeof(cv::KeyPoint)));
     } catch (const std::exception& e) { std::fprintf(stderr, "%s\n", e.what()); return 1; }
     return 0;
 }

@@ -89,3 +89,27 @@ def test_cpp_adapter_matches_oracle(tmp_path):
     keep = cpu_ref.predict_mappoints(0, T, TR, *cam, valid, wp2, msd, ls, nlev, pl, sl, inF, pr_, sr, inFR)
     t = lines[6].split()
     assert int(t[2]) == int(keep.sum()) and int(t[4]) == int(keep.sum()) + int((valid == 0).sum()) and 0 < keep.sum() < n
+    # matchByRadius with the reference's seven arguments: right keys of the frame against its left keys (rad 120)
+    t = lines[7].split()
+    mps = dict(desc=dr, predL=np.stack([kr["x"], kr["y"]], 1).astype(np.float32), scaleLevelL=kr["octave"].astype(np.int32))
+    oL = np.full(len(kl), -1, np.int32); ot = np.full((len(kr), 2), -1, np.int32)
+    on = cpu_ref.match_projection(cpu_ref.Extractor(**args), 2, mps, kl, dl, None, None, None, None, w, h, 120.0, oL, None, ot)
+    assert int(t[1]) == on and int(t[3]) == on and int(t[5]) == 1
+    assert t[7] == fnv(ot[:, 0].astype(np.int32).tobytes()) and t[9] == fnv(oL.tobytes())
+    # default constructor (2000 features, 8 levels) + imagePyramid mirror + public ssc helper
+    t = lines[8].split()
+    oM = cpu_ref.Extractor()
+    km, dm = oM.extractKeysNew(L)
+    pyr = b"".join(oM.level_image(l).tobytes() for l in range(8))
+    assert int(t[1]) == len(km) and int(t[3]) == 8 and t[5] == fnv(pyr)
+    lw, lh = oM.level_image(1).shape[1], oM.level_image(1).shape[0]
+    assert t[7] == f"{lw}x{lh}"
+    t = lines[9].split()
+    gx, gy = np.meshgrid(np.arange(20, w - 20, 5), np.arange(20, h - 20, 5))
+    gx = gx.ravel().astype(np.int32); gy = gy.ravel().astype(np.int32)
+    resp = (1 + (gx * 7 + gy * 13) % 200).astype(np.float32)
+    _, kept = oM.ssc(int(oM.featurePerLevel[0]), w, h, gx, gy, resp)
+    assert int(t[1]) == len(kept) and int(t[3]) == len(gx) and int(t[5]) == int(oM.featurePerLevel[0])
+    kk = np.zeros(len(kept), gvs.KEYPOINT_DTYPE)
+    kk["x"] = gx[kept]; kk["y"] = gy[kept]; kk["response"] = resp[kept]; kk["angle"] = -1; kk["class_id"] = -1
+    assert t[6] == fnv(kk.tobytes())
