@@ -37,6 +37,7 @@ SYMBOLS = [
     "gvs_extractor_launch_count",
     "gvs_pipeline_create", "gvs_pipeline_destroy", "gvs_pipeline_submit", "gvs_pipeline_wait", "gvs_pipeline_download",
     "gvs_pipeline_handles", "gvs_pipeline_release", "gvs_pipeline_submit_temporal", "gvs_pipeline_download_temporal",
+    "gvs_multi_create", "gvs_multi_destroy", "gvs_multi_device_count", "gvs_multi_track_stereo",
 ]
 
 
@@ -148,6 +149,11 @@ def load_library() -> C.CDLL:
     lib.gvs_pipeline_download.argtypes = [vp, i64, vp, vp, i32, vp, vp, i32, vp, vp, vp, vp]
     lib.gvs_pipeline_handles.argtypes = [vp, i64, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     lib.gvs_pipeline_release.argtypes = [vp, i64]
+    lib.gvs_multi_create.argtypes = [C.POINTER(vp), C.POINTER(_Params), i32, i32, i32, C.c_double, f32, vp, i32]
+    lib.gvs_multi_destroy.argtypes = [vp]
+    lib.gvs_multi_device_count.argtypes = [vp]
+    lib.gvs_multi_track_stereo.argtypes = [vp, vp, vp, C.c_size_t, i32, i32, C.POINTER(_TemporalParams), vp, vp, vp, vp, i32, vp, vp, i32,
+                                           vp, vp, vp, vp, vp, vp, vp, i32, vp]
     _lib = lib
     return lib
 
@@ -679,6 +685,62 @@ class StereoPipeline:
             _check(fn(hnd, C.byref(v)))
             tot += v.value
         return tot
+
+
+class MultiGpuTracker:
+    """gvs_multi (include/gvs.h): one process, one handle set and one host thread per device, frames split into
+    contiguous ranges over the devices, results gathered on the host into dense arrays."""
+
+    def __init__(self, fx: float, baseline: float, devices, *, width: int, height: int, frames_per_device: int, nFeatures=2000, nLevels=8,
+                 imScale=1.2, edgeThreshold=19, patchSize=31, maxFastThreshold=20, minFastThreshold=7):
+        self._lib = load_library()
+        self.width, self.height, self.frames_per_device = int(width), int(height), int(frames_per_device)
+        self.devices = np.ascontiguousarray(devices, np.int32)
+        p = _Params(int(nFeatures), int(nLevels), float(imScale), int(edgeThreshold), int(patchSize), int(maxFastThreshold), int(minFastThreshold))
+        self.cap_per_image = 2 * int(nFeatures) + 64 * int(nLevels)
+        self.h = C.c_void_p()
+        _check(self._lib.gvs_multi_create(C.byref(self.h), C.byref(p), self.width, self.height, self.frames_per_device, float(fx),
+                                          float(baseline), _p(self.devices), len(self.devices)))
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self._lib.gvs_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def track_stereo(self, left: np.ndarray, right: np.ndarray, motion: dict | None = None, rad: float = 10.0):
+        """All frames over all devices; returns a dict of dense arrays with global offsets (and the temporal results when `motion`,
+        a synth.sequence_motion-like dict, is given)."""
+        assert left.shape == right.shape and left.dtype == np.uint8 and left.flags.c_contiguous and right.flags.c_contiguous
+        n, h, w = left.shape
+        cap = n * self.cap_per_image
+        offL = np.zeros(n + 1, np.int32); offR = np.zeros(n + 1, np.int32)
+        kl = np.zeros(cap, KEYPOINT_DTYPE); kr = np.zeros(cap, KEYPOINT_DTYPE)
+        dl = np.zeros((cap, 32), np.uint8); dr = np.zeros((cap, 32), np.uint8)
+        ri = np.zeros(cap, np.int32); li = np.zeros(cap, np.int32); de = np.zeros(cap, np.float32); cl = np.zeros(cap, np.uint8)
+        tp = None
+        mo = mk = mt = nm = None
+        keep = []
+        if motion is not None:
+            c = lambda x, dt: np.ascontiguousarray(x, dt)
+            keep = [c(motion["prev"], np.int32), c(motion["pose_prev"], np.float64), c(motion["to_camera"], np.float64), c(motion["to_camera_r"], np.float64)]
+            tp = C.byref(_TemporalParams(0, float(rad), float(motion["fx"]), float(motion["fy"]), float(motion["cx"]), float(motion["cy"]), w, h,
+                                         keep[0].ctypes.data, keep[1].ctypes.data, keep[2].ctypes.data, keep[3].ctypes.data))
+            mo = np.zeros(n + 1, np.int32); mk = np.zeros(cap, np.int32); mt = np.zeros((cap, 2), np.int32); nm = np.zeros(n, np.int32)
+        _check(self._lib.gvs_multi_track_stereo(self.h, _p(left), _p(right), h * w, w, n, tp, _p(offL), _p(offR), _p(kl), _p(dl), cap, _p(kr), _p(dr),
+                                                cap, _p(ri), _p(li), _p(de), _p(cl), _p(mo), _p(mk), _p(mt), cap, _p(nm)))
+        nl, nr = int(offL[-1]), int(offR[-1])
+        out = dict(offL=offL, offR=offR, kpL=kl[:nl], descL=dl[:nl], kpR=kr[:nr], descR=dr[:nr], rightIdxs=ri[:nl], leftIdxs=li[:nr],
+                   estimatedDepth=de[:nl], close=cl[:nl].astype(bool))
+        if motion is not None:
+            M = int(mo[-1])
+            out.update(mp_offsets=mo, mp_key=mk[:M], matches=mt[:M], n_matches=nm)
+        return out
 
 
 def extractORBAndStereoMatch(fm: FeatureMatcher, leftIm: np.ndarray, rightIm: np.ndarray) -> TrackedKeys:

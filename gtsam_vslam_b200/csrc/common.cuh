@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -78,14 +79,18 @@ typedef unsigned KeptKey;
 
 int fail(int code, const char* what, const char* detail = nullptr);
 
-// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remember the largest request per (kernel, device)
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remember the largest request per (kernel, device).  Handles
+// are driven from several host threads (two extractors, gvs_multi workers), so the cache is guarded and only ever grows.
+std::mutex& smemAttrMutex();
 template <typename K>
 inline void ensureDynamicSmem(K kernel, size_t bytes, size_t* cache /* [64] zero-initialised, one per call site */) {
+    // (opt in from 40 KB: a kernel's static shared memory counts against the 48 KB default as well)
+    if (bytes <= 40 * 1024) return;
     int dev = 0;
     cudaGetDevice(&dev);
     dev &= 63;
-    // (opt in from 40 KB: a kernel's static shared memory counts against the 48 KB default as well)
-    if (bytes > 40 * 1024 && cache[dev] < bytes) {
+    std::lock_guard<std::mutex> lock(smemAttrMutex());
+    if (cache[dev] < bytes) {
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
         cache[dev] = bytes;
     }

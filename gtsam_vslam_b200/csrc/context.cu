@@ -21,6 +21,11 @@ int fail(int code, const char* what, const char* detail) {
     return code;
 }
 
+std::mutex& smemAttrMutex() {
+    static std::mutex m;
+    return m;
+}
+
 static inline int cvRoundF(float v) { return (int)lrintf(v); }
 
 }  // namespace gvs
@@ -436,6 +441,11 @@ int joinRight(gvs_matcher* m) {  // make L's stream wait for R's last batch
 // The matcher's kernels run on L's stream and read R's keys, descriptors and pyramid: whatever is queued on R's stream afterwards
 // (the next batch's upload and extraction) must wait for them.
 int holdRight(gvs_matcher* m) {
+    {   // remember the end of the matcher's own work for gvs_matcher_destroy
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(m->L->stream, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusNone; }
+        if (cap == cudaStreamCaptureStatusNone) GVS_CUDA_OK(cudaEventRecord(m->evLast, m->L->stream));
+    }
     if (m->R != m->L && m->R->stream != m->L->stream) {
         // (not while the caller captures L's stream into a graph: a fork that is never joined would invalidate the capture, and the
         // caller's graph already orders whole batches)
@@ -603,7 +613,9 @@ int gvs_extractor_create(gvs_extractor** out, const gvs_extractor_params* params
     *fe->hStatus = 0;
     std::memset(fe->hOff, 0, sizeof(int) * (B + 1));
     // the initialising memsets above ran on the legacy default stream, which the handle's non-blocking streams do not wait for
-    GVS_TRY(cudaDeviceSynchronize());
+    // (only the legacy stream, not the device: another host thread may be capturing its handle's stream into a CUDA graph, and a
+    // device-wide synchronisation is not permitted then -- found by tests/test_gpu_multi.py)
+    GVS_TRY(cudaStreamSynchronize(cudaStreamLegacy));
 #undef GVS_TRY
     *out = fe;
     return GVS_OK;
@@ -955,7 +967,8 @@ int gvs_matcher_create(gvs_matcher** out, gvs_extractor* feL, gvs_extractor* feR
               devAlloc(&m->pjStatus, 2) == cudaSuccess && cudaEventCreateWithFlags(&m->evR, cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&m->evFork, cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&m->evJoin, cudaEventDisableTiming) == cudaSuccess &&
-              cudaEventCreateWithFlags(&m->evHold, cudaEventDisableTiming) == cudaSuccess;
+              cudaEventCreateWithFlags(&m->evHold, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&m->evLast, cudaEventDisableTiming) == cudaSuccess;
     for (auto& e : m->ev) ok = ok && cudaEventCreate(&e) == cudaSuccess;
     for (auto& e : m->evT) ok = ok && cudaEventCreate(&e) == cudaSuccess;
     if (!ok) {
@@ -972,7 +985,7 @@ int gvs_matcher_destroy(gvs_matcher* m) {
     // (the extractors may be gone already when handles are torn down in arbitrary order, e.g. at interpreter exit: only the
     // matcher's own state is touched here)
     DeviceGuard deviceGuard(m->device);
-    cudaDeviceSynchronize();
+    if (m->evLast) cudaEventSynchronize(m->evLast);   // the matcher's last enqueued work (no device-wide synchronisation: see gvs_extractor_create)
     cudaFree(m->rightIdxs); cudaFree(m->leftIdxs); cudaFree(m->sadBest); cudaFree(m->sortScratch); cudaFree(m->depth); cudaFree(m->close);
     cudaFree(m->cellStartL); cudaFree(m->cellStartR); cudaFree(m->itemsL); cudaFree(m->itemsR); cudaFree(m->pj);
     cudaFree(m->pool); cudaFree(m->pjStatus);
@@ -980,6 +993,7 @@ int gvs_matcher_destroy(gvs_matcher* m) {
     if (m->evFork) cudaEventDestroy(m->evFork);
     if (m->evJoin) cudaEventDestroy(m->evJoin);
     if (m->evHold) cudaEventDestroy(m->evHold);
+    if (m->evLast) cudaEventDestroy(m->evLast);
     for (auto& e : m->ev) if (e) cudaEventDestroy(e);
     for (auto& e : m->evT) if (e) cudaEventDestroy(e);
     cudaFree(m->tFlag); cudaFree(m->tPredL); cudaFree(m->tPredR); cudaFree(m->tLvlL); cudaFree(m->tLvlR); cudaFree(m->tDescRow);

@@ -31,7 +31,7 @@ static cudaError_t devAlloc(T** p, size_t count) {
     // debugging aid (compute-sanitizer's initcheck by other means): GVS_POISON=1 fills every fresh allocation with 0xA5 so that
     // a kernel relying on cudaMalloc returning zeros shows up as a parity failure in the tests / tools/fuzz_parity.py
     static const bool poison = getenv("GVS_POISON") != nullptr;
-    if (e == cudaSuccess && poison) { e = cudaMemset(*p, 0xA5, bytes); cudaDeviceSynchronize(); }  // (handles use non-blocking streams)
+    if (e == cudaSuccess && poison) { e = cudaMemset(*p, 0xA5, bytes); cudaStreamSynchronize(cudaStreamLegacy); }  // (handles use non-blocking streams)
     return e;
 }
 
@@ -146,7 +146,7 @@ struct gvs_matcher {
     uint64_t temporalGen = 0;
     cudaEvent_t evT[2] = {};
     float temporalMs = 0;
-    cudaEvent_t evR = nullptr, evFork = nullptr, evJoin = nullptr, evHold = nullptr;
+    cudaEvent_t evR = nullptr, evFork = nullptr, evJoin = nullptr, evHold = nullptr, evLast = nullptr;
     cudaStream_t callerStream = nullptr;  // optional: work is forked from / joined into this stream
     // projection scratch (grown on demand)
     uint8_t* pj = nullptr;

@@ -12,8 +12,15 @@
  *    (void returns, unchecked indexing); conditions that are UB there are GVS_ERR_* here.
  *  - there is NO CPU fallback: without a CUDA device every compute call fails with GVS_ERR_CUDA.
  *  - a gvs_extractor is one FeatureExtractor instance with `max_images` image slots, so that a batch of
- *    independent frames runs as one set of launches.  Handles own their CUDA stream; two handles may be
- *    driven from two host threads concurrently (as reference src/FeatureTracker.cpp:58-61 does).
+ *    independent frames runs as one set of launches.  Handles own their CUDA stream.
+ *  - threads: different handles may be driven from different host threads concurrently (the reference runs its two
+ *    extractors on two std::threads, src/FeatureTracker.cpp:58-61; gvs_multi drives one handle set per thread).  One
+ *    handle is not re-entrant, and a gvs_matcher shares the streams and the resident results of the two extractors it
+ *    was created on: calls on a matcher and on its extractors must come from one thread at a time.  A second matcher
+ *    over the same extractors (the reference wires FeatureTracker::fm and System::mFeatureMatcher that way) is only
+ *    safe for the calls that do not touch the resident frame: gvs_match_projection_lba, gvs_median_descriptor,
+ *    gvs_descriptor_distance, gvs_project_mappoints, gvs_predict_mappoints -- and only while no other thread is inside
+ *    a call on the same extractors; give a thread of its own (LocalMapper) its own extractor pair instead.
  *  - results of the last extract stay resident on the device (pyramids, keypoints, descriptors) and are what
  *    the matcher calls read, exactly like FeatureMatcher reads feLeft->imagePyramid (src/FeatureMatcher.cpp:606).
  */
@@ -359,6 +366,27 @@ int gvs_pipeline_download_temporal(gvs_pipeline* p, int64_t ticket, int32_t* mp_
 /* The slot's handles, e.g. for gvs_match_projection / gvs_grid_download against the ticket's frames (valid until release). */
 int gvs_pipeline_handles(gvs_pipeline* p, int64_t ticket, gvs_extractor** fe_left, gvs_extractor** fe_right, gvs_matcher** fm);
 int gvs_pipeline_release(gvs_pipeline* p, int64_t ticket);
+
+/* ---- several GPUs in one process ----------------------------------------------------------------------
+ * Stereo frames are independent: a batch of n_frames is cut into contiguous ranges [g*n/G, (g+1)*n/G) over the G devices of the
+ * handle; every device has its own handle set and is driven by its own host thread; results are gathered on the host into the
+ * caller's dense arrays (offsets are global over the batch).  No collective and no peer access on the data path.  A device may
+ * be named more than once (two handle sets on one GPU). */
+typedef struct gvs_multi gvs_multi;
+int gvs_multi_create(gvs_multi** out, const gvs_extractor_params* params, int width, int height, int frames_per_device, double fx,
+                     float baseline, const int* devices, int n_devices);
+int gvs_multi_destroy(gvs_multi* p);
+int gvs_multi_device_count(const gvs_multi* p);
+/* FeatureTracker::extractORBAndStereoMatch (src/FeatureTracker.cpp:56-70) for n_frames host frames over all devices, followed by
+ * gvs_track_temporal_batch when `temporal` is given (prev[] indexes frames of the whole batch; a frame and its predecessor must
+ * fall on the same device: GVS_ERR_INVALID otherwise).  left_offsets / right_offsets (n_frames + 1) and, with temporal,
+ * mp_offsets (n_frames + 1) / n_matches (n_frames) are required; any other output may be NULL.  cap_* are the capacities of the
+ * caller's key / map point arrays.  Blocks until everything is on the host. */
+int gvs_multi_track_stereo(gvs_multi* p, const uint8_t* left, const uint8_t* right, size_t image_stride, int row_stride, int n_frames,
+                           const gvs_temporal_params* temporal, int32_t* left_offsets, int32_t* right_offsets, gvs_keypoint* kp_left,
+                           uint8_t* desc_left, int cap_left, gvs_keypoint* kp_right, uint8_t* desc_right, int cap_right,
+                           int32_t* right_idxs, int32_t* left_idxs, float* estimated_depth, uint8_t* close, int32_t* mp_offsets,
+                           int32_t* mp_key, int32_t* matches, int cap_mp, int32_t* n_matches);
 
 /* ------------------------------------------------------------------ measurement --------------------- */
 

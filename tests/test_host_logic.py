@@ -79,3 +79,41 @@ def test_bench_reference_arm_prints_contract_line():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["metric"] == bench.METRIC and line["value"] > 0
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_multi_device_sharding_rule_world_size_2_gloo(tmp_path):
+    """gvs_multi / bench.py shard a batch into contiguous ranges [g*n/G, (g+1)*n/G); two gloo ranks that each take the range of
+    their rank cover the batch exactly once and a host gather restores the batch order (the rule csrc/multi.cu implements)."""
+    script = tmp_path / "w2.py"
+    script.write_text(r'''
+import json, sys
+import torch, torch.distributed as dist
+dist.init_process_group("gloo")
+r, G = dist.get_rank(), dist.get_world_size()
+n = 7
+first = [g * n // G for g in range(G + 1)]
+mine = torch.full((n,), -1, dtype=torch.int64)
+mine[first[r]:first[r + 1]] = torch.arange(first[r], first[r + 1]) * 10 + r     # "results" of the rank's frames
+out = [torch.zeros(n, dtype=torch.int64) for _ in range(G)]
+dist.all_gather(out, mine)                                                       # host gather
+merged = torch.stack(out).max(0).values
+if r == 0:
+    print(json.dumps({"merged": merged.tolist(), "first": first}))
+dist.destroy_process_group()
+''')
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29533", str(script)], capture_output=True, text=True, env=env, timeout=240)
+    assert out.returncode == 0, out.stderr[-2000:]
+    res = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert res["first"] == [0, 3, 7]
+    assert res["merged"] == [0, 10, 20, 31, 41, 51, 61]
+
+
+def test_multi_entry_point_fails_loudly_without_a_device():
+    import gtsam_vslam_b200 as gvs
+    if gvs.device_count() > 0:
+        return
+    import pytest
+    with pytest.raises(gvs.GvsError):
+        gvs.MultiGpuTracker(400.0, 0.1, [0, 1], width=320, height=240, frames_per_device=2, nFeatures=300, nLevels=4)
