@@ -28,7 +28,7 @@ SYMBOLS = [
     "gvs_extractor_create", "gvs_extractor_destroy", "gvs_extractor_tables", "gvs_tables_from_params", "gvs_extractor_level_size",
     "gvs_extract", "gvs_extract_batch_host", "gvs_extractor_input", "gvs_extract_batch_resident",
     "gvs_extractor_sync", "gvs_extractor_set_rectify_maps", "gvs_extract_batch_host_raw", "gvs_extract_offsets", "gvs_extract_download", "gvs_extractor_set_stream",
-    "gvs_debug_level_image", "gvs_debug_level_candidates", "gvs_debug_level_kept", "gvs_debug_select",
+    "gvs_debug_level_image", "gvs_debug_level_candidates", "gvs_debug_level_kept", "gvs_debug_select", "gvs_debug_check_guards",
     "gvs_matcher_create", "gvs_matcher_destroy", "gvs_stereo_match_batch", "gvs_stereo_download",
     "gvs_assign_grids_batch", "gvs_grid_download", "gvs_track_stereo_batch_host",
     "gvs_track_stereo_batch_resident", "gvs_matcher_sync", "gvs_matcher_set_stream", "gvs_match_projection", "gvs_match_projection_batch",
@@ -165,6 +165,13 @@ def _check(rc: int) -> None:
 
 def _p(a):
     return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def check_guards():
+    """(overwritten guard tails, buffers checked) -- GVS_GUARD=1 debugging aid, see include/gvs.h."""
+    n = C.c_int(0)
+    bad = load_library().gvs_debug_check_guards(C.byref(n))
+    return bad, n.value
 
 
 def device_count() -> int:

@@ -26,6 +26,21 @@ std::mutex& smemAttrMutex() {
     return m;
 }
 
+static std::mutex g_guardMutex;
+static std::vector<std::pair<void*, size_t>> g_guards;   // GVS_GUARD=1: (allocation, payload bytes) of the live buffers
+void guardRegister(void* p, size_t bytes) {
+    std::lock_guard<std::mutex> lock(g_guardMutex);
+    g_guards.emplace_back(p, bytes);
+}
+
+void guardForget(void* p) {
+    static const bool guard = getenv("GVS_GUARD") != nullptr;
+    if (!guard) return;
+    std::lock_guard<std::mutex> lock(g_guardMutex);
+    for (auto& g : g_guards)
+        if (g.first == p) { g = g_guards.back(); g_guards.pop_back(); break; }
+}
+
 static inline int cvRoundF(float v) { return (int)lrintf(v); }
 
 }  // namespace gvs
@@ -302,10 +317,10 @@ void destroyExtractor(gvs_extractor* fe) {
     if (!fe) return;
     DeviceGuard deviceGuard(fe->device);
     if (fe->ownStream) cudaStreamSynchronize(fe->ownStream);
-    cudaFree(fe->slab); cudaFree(fe->blurSlab); cudaFree(fe->tight); cudaFree(fe->mapX); cudaFree(fe->mapY); cudaFree(fe->xWeights); cudaFree(fe->xSelectors); cudaFree(fe->xBase); cudaFree(fe->pyrSpans); cudaFree(fe->taps); cudaFree(fe->fastItems); cudaFree(fe->blurItems);
-    cudaFree(fe->recs); cudaFree(fe->nCand); cudaFree(fe->cellCnt); cudaFree(fe->kept); cudaFree(fe->keptCnt);
-    cudaFree(fe->imgOff); cudaFree(fe->orderedDbg); cudaFree(fe->sortedDbg); cudaFree(fe->momentsDbg); cudaFree(fe->selScratch);
-    cudaFree(fe->workCounter); cudaFree(fe->status); cudaFree(fe->kps); cudaFree(fe->desc); cudaFree(fe->auxKey);
+    devFree(fe->slab); devFree(fe->blurSlab); devFree(fe->tight); devFree(fe->mapX); devFree(fe->mapY); devFree(fe->xWeights); devFree(fe->xSelectors); devFree(fe->xBase); devFree(fe->pyrSpans); devFree(fe->taps); devFree(fe->fastItems); devFree(fe->blurItems);
+    devFree(fe->recs); devFree(fe->nCand); devFree(fe->cellCnt); devFree(fe->kept); devFree(fe->keptCnt);
+    devFree(fe->imgOff); devFree(fe->orderedDbg); devFree(fe->sortedDbg); devFree(fe->momentsDbg); devFree(fe->selScratch);
+    devFree(fe->workCounter); devFree(fe->status); devFree(fe->kps); devFree(fe->desc); devFree(fe->auxKey);
     if (fe->hOff) cudaFreeHost(fe->hOff);
     if (fe->hStatus) cudaFreeHost(fe->hStatus);
     for (auto& kv : fe->graphs) cudaGraphExecDestroy(kv.second);
@@ -461,7 +476,7 @@ int holdRight(gvs_matcher* m) {
 int growScratch(gvs_matcher* m, size_t bytes) {
     if (bytes <= m->pjBytes) return GVS_OK;
     GVS_CUDA_OK(cudaStreamSynchronize(m->L->stream));
-    cudaFree(m->pj); m->pj = nullptr; m->pjBytes = 0;
+    devFree(m->pj); m->pj = nullptr; m->pjBytes = 0;
     GVS_CUDA_OK(devAlloc(&m->pj, bytes));
     m->pjBytes = bytes;
     return GVS_OK;
@@ -481,6 +496,26 @@ int gvs_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
+}
+
+int gvs_debug_check_guards(int* n_checked) {
+    std::lock_guard<std::mutex> lock(g_guardMutex);
+    if (n_checked) *n_checked = (int)g_guards.size();
+    std::vector<uint8_t> tail(kGuardBytes);
+    int bad = 0;
+    for (auto& g : g_guards) {
+        if (cudaMemcpy(tail.data(), static_cast<uint8_t*>(g.first) + g.second, kGuardBytes, cudaMemcpyDeviceToHost) != cudaSuccess) {
+            cudaGetLastError();
+            continue;
+        }
+        for (size_t i = 0; i < kGuardBytes; i++)
+            if (tail[i] != 0xC3) {
+                ++bad;
+                std::fprintf(stderr, "gvs guard: %zu-byte device buffer %p overwritten at +%zu past its end\n", g.second, g.first, i);
+                break;
+            }
+    }
+    return bad;
 }
 
 int gvs_extractor_create(gvs_extractor** out, const gvs_extractor_params* params, int width, int height, int max_images,
@@ -700,7 +735,7 @@ int gvs_extract_batch_host(gvs_extractor* fe, const uint8_t* images, size_t imag
         const size_t need = (size_t)fe->maxImages * fe->width * fe->height + 16;
         if (fe->tightBytes < need) {
             GVS_CUDA_OK(cudaStreamSynchronize(fe->stream));
-            cudaFree(fe->tight); fe->tight = nullptr; fe->tightBytes = 0;
+            devFree(fe->tight); fe->tight = nullptr; fe->tightBytes = 0;
             GVS_CUDA_OK(devAlloc(&fe->tight, need));
             fe->tightBytes = need;
         }
@@ -721,7 +756,7 @@ int gvs_extractor_set_rectify_maps(gvs_extractor* fe, const float* map_x, const 
     DeviceGuard deviceGuard(fe->device);
     GVS_CUDA_OK(cudaStreamSynchronize(fe->stream));
     if (!map_x || !map_y) {
-        cudaFree(fe->mapX); cudaFree(fe->mapY);
+        devFree(fe->mapX); devFree(fe->mapY);
         fe->mapX = fe->mapY = nullptr;
         return GVS_OK;
     }
@@ -742,7 +777,7 @@ int gvs_extract_batch_host_raw(gvs_extractor* fe, const uint8_t* images, int cha
     const size_t need = (size_t)fe->maxImages * fe->width * fe->height * 3 + 16;
     if (fe->tightBytes < need) {
         GVS_CUDA_OK(cudaStreamSynchronize(fe->stream));
-        cudaFree(fe->tight); fe->tight = nullptr; fe->tightBytes = 0;
+        devFree(fe->tight); fe->tight = nullptr; fe->tightBytes = 0;
         GVS_CUDA_OK(devAlloc(&fe->tight, need));
         fe->tightBytes = need;
     }
@@ -986,9 +1021,9 @@ int gvs_matcher_destroy(gvs_matcher* m) {
     // matcher's own state is touched here)
     DeviceGuard deviceGuard(m->device);
     if (m->evLast) cudaEventSynchronize(m->evLast);   // the matcher's last enqueued work (no device-wide synchronisation: see gvs_extractor_create)
-    cudaFree(m->rightIdxs); cudaFree(m->leftIdxs); cudaFree(m->sadBest); cudaFree(m->sortScratch); cudaFree(m->depth); cudaFree(m->close);
-    cudaFree(m->cellStartL); cudaFree(m->cellStartR); cudaFree(m->itemsL); cudaFree(m->itemsR); cudaFree(m->pj);
-    cudaFree(m->pool); cudaFree(m->pjStatus);
+    devFree(m->rightIdxs); devFree(m->leftIdxs); devFree(m->sadBest); devFree(m->sortScratch); devFree(m->depth); devFree(m->close);
+    devFree(m->cellStartL); devFree(m->cellStartR); devFree(m->itemsL); devFree(m->itemsR); devFree(m->pj);
+    devFree(m->pool); devFree(m->pjStatus);
     if (m->evR) cudaEventDestroy(m->evR);
     if (m->evFork) cudaEventDestroy(m->evFork);
     if (m->evJoin) cudaEventDestroy(m->evJoin);
@@ -996,10 +1031,10 @@ int gvs_matcher_destroy(gvs_matcher* m) {
     if (m->evLast) cudaEventDestroy(m->evLast);
     for (auto& e : m->ev) if (e) cudaEventDestroy(e);
     for (auto& e : m->evT) if (e) cudaEventDestroy(e);
-    cudaFree(m->tFlag); cudaFree(m->tPredL); cudaFree(m->tPredR); cudaFree(m->tLvlL); cudaFree(m->tLvlR); cudaFree(m->tDescRow);
-    cudaFree(m->tWPos); cudaFree(m->tMaxScaleDist); cudaFree(m->tMpCnt); cudaFree(m->tMpOff); cudaFree(m->tMpSlot); cudaFree(m->tMpKey);
-    cudaFree(m->tMatchedL); cudaFree(m->tMatchedR); cudaFree(m->tMatches); cudaFree(m->tNMatches); cudaFree(m->tRecs);
-    cudaFree(m->tPoses); cudaFree(m->tPrev); cudaFree(m->tStatus);
+    devFree(m->tFlag); devFree(m->tPredL); devFree(m->tPredR); devFree(m->tLvlL); devFree(m->tLvlR); devFree(m->tDescRow);
+    devFree(m->tWPos); devFree(m->tMaxScaleDist); devFree(m->tMpCnt); devFree(m->tMpOff); devFree(m->tMpSlot); devFree(m->tMpKey);
+    devFree(m->tMatchedL); devFree(m->tMatchedR); devFree(m->tMatches); devFree(m->tNMatches); devFree(m->tRecs);
+    devFree(m->tPoses); devFree(m->tPrev); devFree(m->tStatus);
     if (m->hMpOff) cudaFreeHost(m->hMpOff);
     if (m->hNMatches) cudaFreeHost(m->hNMatches);
     if (m->hTStatus) cudaFreeHost(m->hTStatus);
@@ -1226,14 +1261,14 @@ int gvs_match_projection_lba(gvs_matcher* m, const gvs_lba_frame* kf, const gvs_
                  oCSR = take((size_t)(m->maxCells + 1) * 4), oItL = take((size_t)NL * 4), oItR = take((size_t)NR * 4), oOff = take(32);
     if (o > m->pjBytes) {
         GVS_CUDA_OK(cudaStreamSynchronize(s));
-        cudaFree(m->pj); m->pj = nullptr; m->pjBytes = 0;
+        devFree(m->pj); m->pj = nullptr; m->pjBytes = 0;
         GVS_CUDA_OK(devAlloc(&m->pj, o));
         m->pjBytes = o;
     }
     const long long need = std::min<long long>((long long)M * std::max(std::max(NL, NR), 1), (long long)1 << 28);
     if (need > m->poolCap) {
         GVS_CUDA_OK(cudaStreamSynchronize(s));
-        cudaFree(m->pool); m->pool = nullptr; m->poolCap = 0;
+        devFree(m->pool); m->pool = nullptr; m->poolCap = 0;
         GVS_CUDA_OK(devAlloc(&m->pool, (size_t)need * 2));
         m->poolCap = (int)need;
     }
@@ -1308,7 +1343,7 @@ int gvs_project_mappoints(gvs_matcher* m, const double* pose_inv, double fx, dou
                  oSl = oPr + al(M * 8), oIf = oSl + al(M * 4), total = oIf + al(M);
     if (total > m->pjBytes) {
         GVS_CUDA_OK(cudaStreamSynchronize(s));
-        cudaFree(m->pj); m->pj = nullptr; m->pjBytes = 0;
+        devFree(m->pj); m->pj = nullptr; m->pjBytes = 0;
         GVS_CUDA_OK(devAlloc(&m->pj, total));
         m->pjBytes = total;
     }
@@ -1361,7 +1396,7 @@ int gvs_predict_mappoints(gvs_matcher* m, int mode, const double* to_camera, con
                  oMt = take(M * 8), oML = take(NL * 4), oMR = take(NR * 4), oOut = take(M);
     if (o > m->pjBytes) {
         GVS_CUDA_OK(cudaStreamSynchronize(s));
-        cudaFree(m->pj); m->pj = nullptr; m->pjBytes = 0;
+        devFree(m->pj); m->pj = nullptr; m->pjBytes = 0;
         GVS_CUDA_OK(devAlloc(&m->pj, o));
         m->pjBytes = o;
     }
@@ -1456,7 +1491,7 @@ int gvs_find_outliers(gvs_matcher* m, int frame, int mode, const double* pose, c
                      oMt = oIr + al(M), oOut = oMt + al(M * 8), oAct = oOut + al(M), oFc = oAct + al(M * 4),
                      oCnt = oFc + al((size_t)std::max(NL, 1) * 4), total = oCnt + al(16);
         if (total > m->pjBytes) {
-            cudaFree(m->pj); m->pj = nullptr; m->pjBytes = 0;
+            devFree(m->pj); m->pj = nullptr; m->pjBytes = 0;
             GVS_CUDA_OK(devAlloc(&m->pj, total));
             m->pjBytes = total;
         }
@@ -1527,7 +1562,7 @@ int gvs_median_descriptor(gvs_matcher* m, const uint8_t* descs, const int32_t* o
     int launches = 0;
     if (e == cudaSuccess) { launchMedianDescriptor(dd, doff, n_points, dbest, s, &launches); e = cudaMemcpyAsync(best_idx, dbest, sizeof(int) * n_points, cudaMemcpyDeviceToHost, s); }
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-    cudaFree(dd); cudaFree(doff); cudaFree(dbest);
+    devFree(dd); devFree(doff); devFree(dbest);
     m->launchesTotal += launches;
     if (e != cudaSuccess) return fail(GVS_ERR_CUDA, "gvs_median_descriptor", cudaGetErrorString(e));
     return GVS_OK;
@@ -1548,7 +1583,7 @@ int gvs_descriptor_distance(gvs_matcher* m, const uint8_t* a, const uint8_t* b, 
     int launches = 0;
     if (e == cudaSuccess) { launchHamming(da, db, n, dd, s, &launches); e = cudaMemcpyAsync(dist, dd, sizeof(int) * n, cudaMemcpyDeviceToHost, s); }
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-    cudaFree(da); cudaFree(db); cudaFree(dd);
+    devFree(da); devFree(db); devFree(dd);
     m->launchesTotal += launches;
     if (e != cudaSuccess) return fail(GVS_ERR_CUDA, "gvs_descriptor_distance", cudaGetErrorString(e));
     return GVS_OK;

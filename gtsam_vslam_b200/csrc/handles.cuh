@@ -23,15 +23,24 @@ struct DeviceGuard {
     DeviceGuard& operator=(const DeviceGuard&) = delete;
 };
 
+// Debugging aids for device memory (compute-sanitizer is not available on the GPU pool this was developed on):
+//   GVS_POISON=1  every fresh allocation is filled with 0xA5, so that a kernel relying on cudaMalloc returning zeros shows up as a
+//                 parity failure in the tests / tools/fuzz_parity.py (initcheck by other means);
+//   GVS_GUARD=1   every allocation gets a 256-byte tail filled with 0xC3 and is registered; gvs_debug_check_guards() (gvs.h)
+//                 verifies all tails: an out-of-bounds write past the end of a buffer is reported with the buffer's size.
+constexpr size_t kGuardBytes = 256;
+void guardRegister(void* p, size_t bytes);
+void guardForget(void* p);
+inline cudaError_t devFree(void* p) { if (p) guardForget(p); return cudaFree(p); }
 template <typename T>
 static cudaError_t devAlloc(T** p, size_t count) {
     *p = nullptr;
     const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
-    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), bytes);
-    // debugging aid (compute-sanitizer's initcheck by other means): GVS_POISON=1 fills every fresh allocation with 0xA5 so that
-    // a kernel relying on cudaMalloc returning zeros shows up as a parity failure in the tests / tools/fuzz_parity.py
-    static const bool poison = getenv("GVS_POISON") != nullptr;
-    if (e == cudaSuccess && poison) { e = cudaMemset(*p, 0xA5, bytes); cudaStreamSynchronize(cudaStreamLegacy); }  // (handles use non-blocking streams)
+    static const bool poison = getenv("GVS_POISON") != nullptr, guard = getenv("GVS_GUARD") != nullptr;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), bytes + (guard ? kGuardBytes : 0));
+    if (e == cudaSuccess && poison) e = cudaMemset(*p, 0xA5, bytes);
+    if (e == cudaSuccess && guard) { e = cudaMemset(reinterpret_cast<uint8_t*>(*p) + bytes, 0xC3, kGuardBytes); guardRegister(*p, bytes); }
+    if (e == cudaSuccess && (poison || guard)) cudaStreamSynchronize(cudaStreamLegacy);   // (handles use non-blocking streams)
     return e;
 }
 

@@ -134,6 +134,11 @@ int gvs_debug_level_candidates(gvs_extractor* fe, int image, int level, int32_t*
 /* Keys of a level after ssc (:609-613) in output order, with the integer moments of computeOrientation. */
 int gvs_debug_level_kept(gvs_extractor* fe, int image, int level, int32_t* x, int32_t* y, int32_t* score, int cap, int* n);
 
+/* Debugging aid (compute-sanitizer by other means): with GVS_GUARD=1 in the environment every device buffer of the library carries
+ * a guard tail; returns how many tails have been overwritten (0 = no write past the end of any buffer) and the number checked.
+ * Call it before destroying the handles of interest.  Without GVS_GUARD it checks nothing (*n_checked = 0). */
+int gvs_debug_check_guards(int* n_checked);
+
 /* Run the selection stage alone (ordering + cv::sortIdx emulation + ssc, src/FeatureExtractor.cpp:368-468) on a
  * caller-made candidate list of pyramid level `level` (n candidates in emission order, x/y inside the level,
  * score in [1,254]).  Outputs: sorted_idx (n entries, may be NULL) = the permutation cv::sortIdx(SORT_DESCENDING)

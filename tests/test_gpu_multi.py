@@ -108,3 +108,18 @@ def test_handles_driven_from_concurrent_host_threads():
     assert not errors, errors
     assert np.array_equal(results["L"][0], want["offL"]) and np.array_equal(results["L"][1], want["kpL"]) and np.array_equal(results["L"][2], want["descL"])
     assert np.array_equal(results["R"][0], want["offR"]) and np.array_equal(results["R"][1], want["kpR"]) and np.array_equal(results["R"][2], want["descR"])
+
+
+def test_guard_tails_and_poisoned_allocations():
+    """compute-sanitizer is closed on the GPU pool: every device buffer gets a guard tail (GVS_GUARD) and a poison fill
+    (GVS_POISON), the whole step / pipeline / multi-device front end runs (tools/sanitize_target.py, bit-exact smoke included) and
+    no tail may have been overwritten."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, GVS_GUARD="1", GVS_POISON="1")
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "sanitize_target.py")], capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
+    line = [l for l in out.stdout.splitlines() if l.startswith("guard tails:")][0]
+    assert line.startswith("guard tails: 0 overwritten of ") and int(line.split()[5]) > 100, line
