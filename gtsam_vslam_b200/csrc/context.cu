@@ -982,8 +982,15 @@ int gvs_matcher_create(gvs_matcher** out, gvs_extractor* feL, gvs_extractor* feR
     *out = nullptr;
     if (!feR) feR = feL;  // mono: System::InitializeMonocular passes the left extractor twice (src/System.cpp:32)
     if (feL->device != feR->device) return fail(GVS_ERR_INVALID, "extractors live on different devices");
-    if (feL->g.nLevels != feR->g.nLevels || feL->width != feR->width || feL->height != feR->height)
-        return fail(GVS_ERR_INVALID, "left and right extractors differ in geometry");
+    // the stereo and projection kernels index both pyramids and both key sets with the LEFT handle's geometry and scale tables
+    if (feL->g.nLevels != feR->g.nLevels || feL->width != feR->width || feL->height != feR->height ||
+        feL->params.im_scale != feR->params.im_scale || feL->params.edge_threshold != feR->params.edge_threshold ||
+        feL->params.patch_size != feR->params.patch_size || feL->g.slabBytes != feR->g.slabBytes)
+        return fail(GVS_ERR_INVALID, "left and right extractors differ in geometry (size, levels, scale factor, edge threshold)");
+    for (int l = 0; l < feL->g.nLevels; l++)
+        if (feL->g.lv[l].w != feR->g.lv[l].w || feL->g.lv[l].h != feR->g.lv[l].h || feL->g.lv[l].pitch != feR->g.lv[l].pitch ||
+            feL->g.lv[l].off != feR->g.lv[l].off)
+            return fail(GVS_ERR_INVALID, "left and right extractors differ in pyramid layout");
     if (image_height < 1) return fail(GVS_ERR_INVALID, "bad image_height");
     DeviceGuard deviceGuard(feL->device);
     gvs_matcher* m = new gvs_matcher();
@@ -1003,7 +1010,8 @@ int gvs_matcher_create(gvs_matcher** out, gvs_extractor* feL, gvs_extractor* feR
               cudaEventCreateWithFlags(&m->evFork, cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&m->evJoin, cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&m->evHold, cudaEventDisableTiming) == cudaSuccess &&
-              cudaEventCreateWithFlags(&m->evLast, cudaEventDisableTiming) == cudaSuccess;
+              cudaEventCreateWithFlags(&m->evLast, cudaEventDisableTiming) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&m->ownStream, cudaStreamNonBlocking) == cudaSuccess;
     for (auto& e : m->ev) ok = ok && cudaEventCreate(&e) == cudaSuccess;
     for (auto& e : m->evT) ok = ok && cudaEventCreate(&e) == cudaSuccess;
     if (!ok) {
@@ -1020,7 +1028,9 @@ int gvs_matcher_destroy(gvs_matcher* m) {
     // (the extractors may be gone already when handles are torn down in arbitrary order, e.g. at interpreter exit: only the
     // matcher's own state is touched here)
     DeviceGuard deviceGuard(m->device);
-    if (m->evLast) cudaEventSynchronize(m->evLast);   // the matcher's last enqueued work (no device-wide synchronisation: see gvs_extractor_create)
+    if (m->evLast) cudaEventSynchronize(m->evLast);
+    if (m->ownStream) { cudaStreamSynchronize(m->ownStream); cudaStreamDestroy(m->ownStream); }
+    devFree(m->pjOwn);   // the matcher's last enqueued work (no device-wide synchronisation: see gvs_extractor_create)
     devFree(m->rightIdxs); devFree(m->leftIdxs); devFree(m->sadBest); devFree(m->sortScratch); devFree(m->depth); devFree(m->close);
     devFree(m->cellStartL); devFree(m->cellStartR); devFree(m->itemsL); devFree(m->itemsR); devFree(m->pj);
     devFree(m->pool); devFree(m->pjStatus);
@@ -1245,7 +1255,7 @@ int gvs_match_projection_lba(gvs_matcher* m, const gvs_lba_frame* kf, const gvs_
     for (int i = 0; i < M; i++)
         if (pts->pred_scale[i] < 0 || pts->pred_scale[i] >= m->L->g.nLevels) return fail(GVS_ERR_INVALID, "pred_scale out of range");
     DeviceGuard deviceGuard(m->L->device);
-    cudaStream_t s = m->L->stream;
+    cudaStream_t s = m->ownStream;   // (does not read the resident frame: the matcher's own stream and scratch)
     const float imageRatio = (float)kf->width / (float)kf->height;
     const int xGrids = GVS_GRID_X, yGrids = (int)std::ceil((float)xGrids / imageRatio);
     if (xGrids * yGrids > m->maxCells) return fail(GVS_ERR_INVALID, "key grid larger than the one this matcher was created for (image shape differs from the extractors')");
@@ -1259,11 +1269,11 @@ int gvs_match_projection_lba(gvs_matcher* m, const gvs_lba_frame* kf, const gvs_
                  oDL = take((size_t)NL * 32), oDR = take((size_t)NR * 32), oLI = take((size_t)NR * 4), oRI = take((size_t)NL * 4),
                  oUF = take((size_t)NL * 4), oUR = take((size_t)NR * 4), oCSL = take((size_t)(m->maxCells + 1) * 4),
                  oCSR = take((size_t)(m->maxCells + 1) * 4), oItL = take((size_t)NL * 4), oItR = take((size_t)NR * 4), oOff = take(32);
-    if (o > m->pjBytes) {
+    if (o > m->pjOwnBytes) {
         GVS_CUDA_OK(cudaStreamSynchronize(s));
-        devFree(m->pj); m->pj = nullptr; m->pjBytes = 0;
-        GVS_CUDA_OK(devAlloc(&m->pj, o));
-        m->pjBytes = o;
+        devFree(m->pjOwn); m->pjOwn = nullptr; m->pjOwnBytes = 0;
+        GVS_CUDA_OK(devAlloc(&m->pjOwn, o));
+        m->pjOwnBytes = o;
     }
     const long long need = std::min<long long>((long long)M * std::max(std::max(NL, NR), 1), (long long)1 << 28);
     if (need > m->poolCap) {
@@ -1272,7 +1282,7 @@ int gvs_match_projection_lba(gvs_matcher* m, const gvs_lba_frame* kf, const gvs_
         GVS_CUDA_OK(devAlloc(&m->pool, (size_t)need * 2));
         m->poolCap = (int)need;
     }
-    uint8_t* b = m->pj;
+    uint8_t* b = m->pjOwn;
     std::vector<uint8_t> inL(M), inR(M);
     for (int i = 0; i < M; i++) {
         inL[i] = pts->pred_l[2 * i] > 0 && pts->pred_l[2 * i + 1] > 0;   // :104
@@ -1336,18 +1346,18 @@ int gvs_project_mappoints(gvs_matcher* m, const double* pose_inv, double fx, dou
     if (count == 0) return GVS_OK;
     if (!world_pos || !max_scale_dist || !log_scale || !n_scale_lev || !pred || !scale_level || !in_frame) return fail(GVS_ERR_INVALID, "null array");
     DeviceGuard deviceGuard(m->L->device);
-    cudaStream_t s = m->L->stream;
+    cudaStream_t s = m->ownStream;   // (does not read the resident frame: the matcher's own stream and scratch)
     const size_t M = (size_t)count;
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
     const size_t oPose = 0, oW = al(128), oMs = oW + al(M * 32), oLs = oMs + al(M * 4), oNl = oLs + al(M * 4), oPr = oNl + al(M * 4),
                  oSl = oPr + al(M * 8), oIf = oSl + al(M * 4), total = oIf + al(M);
-    if (total > m->pjBytes) {
+    if (total > m->pjOwnBytes) {
         GVS_CUDA_OK(cudaStreamSynchronize(s));
-        devFree(m->pj); m->pj = nullptr; m->pjBytes = 0;
-        GVS_CUDA_OK(devAlloc(&m->pj, total));
-        m->pjBytes = total;
+        devFree(m->pjOwn); m->pjOwn = nullptr; m->pjOwnBytes = 0;
+        GVS_CUDA_OK(devAlloc(&m->pjOwn, total));
+        m->pjOwnBytes = total;
     }
-    uint8_t* b = m->pj;
+    uint8_t* b = m->pjOwn;
     GVS_CUDA_OK(cudaMemcpyAsync(b + oPose, pose_inv, 128, cudaMemcpyHostToDevice, s));
     GVS_CUDA_OK(cudaMemcpyAsync(b + oW, world_pos, M * 32, cudaMemcpyHostToDevice, s));
     GVS_CUDA_OK(cudaMemcpyAsync(b + oMs, max_scale_dist, M * 4, cudaMemcpyHostToDevice, s));
@@ -1386,7 +1396,7 @@ int gvs_predict_mappoints(gvs_matcher* m, int mode, const double* to_camera, con
             if (matches[2 * i] >= n_left || matches[2 * i + 1] >= n_right) return fail(GVS_ERR_INVALID, "match index outside matched_l / matched_r");
     }
     DeviceGuard deviceGuard(m->L->device);
-    cudaStream_t s = m->L->stream;
+    cudaStream_t s = m->ownStream;   // (does not read the resident frame: the matcher's own stream and scratch)
     const size_t M = (size_t)count, NL = (size_t)std::max(n_left, 1), NR = (size_t)std::max(n_right, 1);
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
     size_t o = 0;
@@ -1394,13 +1404,13 @@ int gvs_predict_mappoints(gvs_matcher* m, int mode, const double* to_camera, con
     const size_t oPose = take(256), oVa = take(M), oW = take(M * 32), oMs = take(M * 4), oLs = take(M * 4), oNl = take(M * 4),
                  oPl = take(M * 8), oSl = take(M * 4), oIf = take(M), oPr = take(M * 8), oSr = take(M * 4), oIr = take(M), oKeep = take(M),
                  oMt = take(M * 8), oML = take(NL * 4), oMR = take(NR * 4), oOut = take(M);
-    if (o > m->pjBytes) {
+    if (o > m->pjOwnBytes) {
         GVS_CUDA_OK(cudaStreamSynchronize(s));
-        devFree(m->pj); m->pj = nullptr; m->pjBytes = 0;
-        GVS_CUDA_OK(devAlloc(&m->pj, o));
-        m->pjBytes = o;
+        devFree(m->pjOwn); m->pjOwn = nullptr; m->pjOwnBytes = 0;
+        GVS_CUDA_OK(devAlloc(&m->pjOwn, o));
+        m->pjOwnBytes = o;
     }
-    uint8_t* b = m->pj;
+    uint8_t* b = m->pjOwn;
     auto up = [&](size_t off, const void* src, size_t bytes) -> cudaError_t {
         return src ? cudaMemcpyAsync(b + off, src, bytes, cudaMemcpyHostToDevice, s) : cudaSuccess;
     };
@@ -1552,7 +1562,7 @@ int gvs_median_descriptor(gvs_matcher* m, const uint8_t* descs, const int32_t* o
     for (int p = 0; p < n_points; p++)
         if (offsets[p + 1] < offsets[p] || offsets[p + 1] - offsets[p] > 65535) return fail(GVS_ERR_INVALID, "bad offsets");
     DeviceGuard deviceGuard(m->L->device);
-    cudaStream_t s = m->L->stream;
+    cudaStream_t s = m->ownStream;   // (does not read the resident frame: the matcher's own stream and scratch)
     uint8_t* dd = nullptr; int* doff = nullptr; int* dbest = nullptr;
     cudaError_t e = devAlloc(&dd, (size_t)std::max(total, 1) * 32);
     if (e == cudaSuccess) e = devAlloc(&doff, (size_t)n_points + 1);
@@ -1572,7 +1582,7 @@ int gvs_descriptor_distance(gvs_matcher* m, const uint8_t* a, const uint8_t* b, 
     if (!m || !a || !b || !dist || n < 0) return fail(GVS_ERR_INVALID, "bad argument");
     if (n == 0) return GVS_OK;
     DeviceGuard deviceGuard(m->L->device);
-    cudaStream_t s = m->L->stream;
+    cudaStream_t s = m->ownStream;   // (does not read the resident frame: the matcher's own stream and scratch)
     uint8_t *da = nullptr, *db = nullptr;
     int* dd = nullptr;
     cudaError_t e = devAlloc(&da, (size_t)n * 32);

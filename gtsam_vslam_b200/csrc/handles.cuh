@@ -160,6 +160,12 @@ struct gvs_matcher {
     // projection scratch (grown on demand)
     uint8_t* pj = nullptr;
     size_t pjBytes = 0;
+    // the calls that do not read the resident frame (LBA matcher, calcDescriptor, DescriptorDistance, worldToFrame loops) run on the
+    // matcher's own stream with their own scratch: a second matcher over the same extractors may serve another host thread
+    // (System::mFeatureMatcher in LocalMapper) without touching the tracker's streams
+    cudaStream_t ownStream = nullptr;
+    uint8_t* pjOwn = nullptr;
+    size_t pjOwnBytes = 0;
     unsigned* pool = nullptr;
     int poolCap = 0;
     int* pjStatus = nullptr;

@@ -123,3 +123,48 @@ def test_guard_tails_and_poisoned_allocations():
     assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
     line = [l for l in out.stdout.splitlines() if l.startswith("guard tails:")][0]
     assert line.startswith("guard tails: 0 overwritten of ") and int(line.split()[5]) > 100, line
+
+
+def test_second_matcher_on_the_same_extractors_from_another_thread(golden_dir):
+    """The reference wires two FeatureMatcher objects over one extractor pair: FeatureTracker::fm (tracking thread) and
+    System::mFeatureMatcher (LocalMapper thread: matchByProjectionRPredLBA, src/OptimizationBA.cpp:367).  The calls that do not read
+    the resident frame run on the matcher's own stream and scratch, so the second matcher is safe next to a tracking loop."""
+    import os
+    cfg = synth.CONFIGS["small"]
+    w, h = cfg["width"], cfg["height"]
+    L, R = synth.stereo_batch(w, h, cfg["disparity"], range(90, 92))
+    args = dict(nFeatures=cfg["n_features"], nLevels=cfg["n_levels"], width=w, height=h, max_images=2)
+    feL, feR = gvs.FeatureExtractor(**args), gvs.FeatureExtractor(**args)
+    fmTrack = gvs.FeatureMatcher(cfg["fx"], cfg["baseline"], feL, feR, h)
+    fmMap = gvs.FeatureMatcher(cfg["fx"], cfg["baseline"], feL, feR, h)
+    g = np.load(os.path.join(golden_dir, "small_s0.npz")); p = np.load(os.path.join(golden_dir, "small_s0_lba.npz"))
+    pts = {k[3:]: p[k] for k in p.files if k.startswith("pt_")}
+    want_n, want_out = int(p["lba_15_n"]), p["lba_15_out"]
+    errors, first = [], {}
+
+    def tracker():
+        try:
+            for i in range(30):
+                fmTrack.track_stereo_batch(L, R)
+                ri, li, de, cl = fmTrack.stereo_download(0, 2)
+                if i == 0:
+                    first["ri"] = ri.copy()
+                assert np.array_equal(ri, first["ri"])
+        except Exception as e:  # noqa: BLE001
+            errors.append(("tracker", e))
+
+    def mapper():
+        try:
+            for _ in range(30):
+                n, out = fmMap.matchByProjectionRPredLBA(pts, g["kpL"], g["descL"], g["kpR"], g["descR"], g["leftIdxs"], g["rightIdxs"],
+                                                         p["unF"], p["unFR"], w, h, 15.0)
+                assert n == want_n and np.array_equal(out, want_out)
+        except Exception as e:  # noqa: BLE001
+            errors.append(("mapper", e))
+
+    ts = [threading.Thread(target=tracker), threading.Thread(target=mapper)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors
