@@ -6,18 +6,18 @@
 // worldToFrame :685-741 -> MapPoint::predictScale src/Map.cpp:13-23).
 //
 // The reference matcher is greedy over map points in index order.  Two phases keep that order:
-//   phase 1 (projb_candidates_kernel, one warp per (frame, map point, side)): walks the key-grid window in the reference's
-//     order (grid row, then one contiguous CSR range per row; the rows' ranges are fetched by different lanes and the window is
-//     flattened so that a typical window is ONE round of 32 lanes) and keeps the four smallest keys (dist << 20 | position in
-//     the candidate list).  The best / second-best rule (src/FeatureMatcher.cpp:281-302, strict <) only ever depends on the TWO
-//     smallest keys of the list: the best is the first occurrence of the minimum, and the second best is the smallest key among
-//     the others (a prefix element with the second's distance would have the smaller key, so "prefix minimum unless the suffix
-//     is strictly smaller" of SURVEY App. A.9 is the same rule).  Four are kept so that phase 2 can drop candidates that get
-//     matched in the meantime.  Nothing is stored per candidate: no candidate pool, no capacity to overflow.  Keys that are
-//     matched before the call (in-out matchedIdxs) are skipped here already: entries only change from -1 to >= 0 during a call.
+//   phase 1 (projb_candidates_kernel, one THREAD per (frame, map point, side), the frame's key grid and keys staged in shared
+//     memory per CTA): walks the key-grid window in the reference's order (grid row, then one contiguous CSR range per row) and
+//     keeps the four smallest keys (dist << 20 | position in the candidate list).  The best / second-best rule
+//     (src/FeatureMatcher.cpp:281-302, strict <) only ever depends on the TWO smallest keys of the list: the best is the first
+//     occurrence of the minimum, and the second best is the smallest key among the others (a prefix element with the second's
+//     distance would have the smaller key, so "prefix minimum unless the suffix is strictly smaller" of SURVEY App. A.9 is the
+//     same rule).  Four are kept so that phase 2 can drop candidates that get matched in the meantime.  Nothing is stored per
+//     candidate: no candidate pool, no capacity to overflow.  Keys that are matched before the call (in-out matchedIdxs) are
+//     skipped here already: entries only change from -1 to >= 0 during a call.
 //   phase 2 (projb_resolve_kernel, one CTA of 32 warps per frame): walks the frame's map points in order, 32 at a time.  A map
 //     point decides from the first two of its stored candidates that are still free; if fewer than two are left of a list that
-//     was longer than four, its warp enumerates the window again with the skip test.  The longest prefix of the chunk in which
+//     was longer than four, its lane walks the window again with the skip test.  The longest prefix of the chunk in which
 //     no map point takes a deciding candidate of a later one is committed; the rest is re-evaluated.  matchedIdxsL/R of the
 //     frame live in shared memory during the walk.
 #include <cmath>
@@ -72,12 +72,6 @@ struct ProjBatchArgs {
     int capL, capR;            // shared-memory capacity of the resolve kernel (keys per frame and side)
 };
 
-__device__ __forceinline__ unsigned tWarpMin(unsigned v) {
-#pragma unroll
-    for (int o = 16; o; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
-
 struct TWindow {
     int minX, maxX, minY, maxY, lvl;
     float trackX, trackY, radius;
@@ -98,99 +92,59 @@ __device__ __forceinline__ TWindow tWindow(const ProjBatchArgs& a, float trackX,
 }
 
 struct TSide {
-    const gvs_keypoint* kps;   // of the frame
+    const char* kp;            // keys of the frame: x, y as floats at +0 / +4, the octave at +octOfs, kpStride bytes apart
+    int kpStride, octOfs;      // (28, 20: gvs_keypoint in global memory; 12, 8: the staged copy in shared memory)
     const uint8_t* descs;
     const int* cellStart;
     const int* items;
 };
+struct TKey3 { float x, y; int octave; };   // staged key
 
-// One warp: the ordered candidate list of a window reduced to its kTopK smallest keys (entries in key order) and its length.
-// `skip` (optional) = matchedIdxs of the side, indexed by key: entries >= 0 are not candidates (src/FeatureMatcher.cpp:283,323,
-// 418,485).
-__device__ void tScanWindow(const TSide& sd, const TWindow& w, int xGrids, const uint4& q0, const uint4& q1, const int* skip,
-                            bool radiusMode, int lane, TRec& rec) {
+// One THREAD: the ordered candidate list of a window (grid rows top to bottom, one contiguous CSR range per row) reduced to its
+// kTopK smallest keys (entries in key order) and its length.  `skip` (optional) = matchedIdxs of the side, indexed by key: entries
+// >= 0 are not candidates (src/FeatureMatcher.cpp:283,323,418,485).  A window holds a few dozen keys at the tracking radii, so a
+// thread per (map point, side) keeps 32 independent walks of a warp in flight where a warp per walk would keep one.
+__device__ __forceinline__ void tScanLane(const TSide& sd, const TWindow& w, int xGrids, const uint4& q0, const uint4& q1, const int* skip,
+                                          bool radiusMode, TRec& rec) {
+    unsigned k[kTopK];
 #pragma unroll
-    for (int i = 0; i < kTopK; i++) rec.e[i] = kNoCand;
+    for (int i = 0; i < kTopK; i++) { k[i] = kNoCand; rec.e[i] = kNoCand; }
     rec.n = 0;
     if (!w.ok) return;
-    unsigned lt;
-    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt));
-    unsigned k[kTopK], e[kTopK];   // this lane's smallest keys, ascending
-#pragma unroll
-    for (int i = 0; i < kTopK; i++) { k[i] = kNoCand; e[i] = kNoCand; }
     int run = 0;
-    for (int row0 = w.minY; row0 <= w.maxY; row0 += 32) {
-        // lane r owns grid row row0 + r: its CSR range [p0, p1) and the exclusive prefix of the lengths
-        const int nRows = min(32, w.maxY - row0 + 1);
-        int p0 = 0, len = 0;
-        if (lane < nRows) {
-            p0 = sd.cellStart[(row0 + lane) * xGrids + w.minX];
-            len = sd.cellStart[(row0 + lane) * xGrids + w.maxX + 1] - p0;
-        }
-        int incl = len;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        for (int base = 0; base < total; base += 32) {
-            const int s = base + lane;
-            // row of flattened slot s = number of rows whose inclusive prefix is <= s
-            int r = 0;
-            for (int j = 0; j < nRows; j++) r += __shfl_sync(0xffffffffu, incl, j) <= s;
-            r = min(r, nRows - 1);
-            const int rp0 = __shfl_sync(0xffffffffu, p0, r), rex = __shfl_sync(0xffffffffu, incl - len, r);
-            int idx = -1, lev = -1;
-            float kx = 0.f, ky = 0.f;
-            if (s < total) {
-                idx = sd.items[rp0 + (s - rex)];
-                const gvs_keypoint* kp = sd.kps + idx;
-                lev = kp->octave;
-                kx = kp->x; ky = kp->y;
-                if (lev > w.lvl + 1 || lev < w.lvl - 1) lev = -1;
-                else if (skip && skip[idx] >= 0) lev = -1;
-                else {
-                    const float dx = __fsub_rn(kx, w.trackX), dy = __fsub_rn(ky, w.trackY);
-                    if (!(fabsf(dx) < w.radius && fabsf(dy) < w.radius)) lev = -1;
-                    else if (radiusMode) {  // Converter::checkPixelParallax (include/Conversions.h:140-144)
-                        const double ex = (double)w.trackX - (double)kx, ey = (double)w.trackY - (double)ky;
-                        if (!(sqrt(ex * ex + ey * ey) > 10.0)) lev = -1;
-                    }
-                }
+    for (int row = w.minY; row <= w.maxY; row++) {
+        const int p0 = sd.cellStart[row * xGrids + w.minX], p1 = sd.cellStart[row * xGrids + w.maxX + 1];
+        for (int p = p0; p < p1; p++) {
+            const int idx = sd.items[p];
+            const char* kp = sd.kp + (size_t)idx * sd.kpStride;
+            const int lev = *reinterpret_cast<const int*>(kp + sd.octOfs);
+            if (lev > w.lvl + 1 || lev < w.lvl - 1) continue;
+            if (skip && skip[idx] >= 0) continue;
+            const float kx = *reinterpret_cast<const float*>(kp), ky = *reinterpret_cast<const float*>(kp + 4);
+            const float dx = __fsub_rn(kx, w.trackX), dy = __fsub_rn(ky, w.trackY);
+            if (!(fabsf(dx) < w.radius && fabsf(dy) < w.radius)) continue;
+            if (radiusMode) {  // Converter::checkPixelParallax (include/Conversions.h:140-144)
+                const double ex = (double)w.trackX - (double)kx, ey = (double)w.trackY - (double)ky;
+                if (!(sqrt(ex * ex + ey * ey) > 10.0)) continue;
             }
-            const unsigned m = __ballot_sync(0xffffffffu, lev >= 0);
-            if (lev >= 0) {
-                const uint4* dk = reinterpret_cast<const uint4*>(sd.descs + (size_t)idx * 32);
-                const uint4 k0 = __ldg(dk), k1 = __ldg(dk + 1);
-                const int d = __popc(q0.x ^ k0.x) + __popc(q0.y ^ k0.y) + __popc(q0.z ^ k0.z) + __popc(q0.w ^ k0.w) +
-                              __popc(q1.x ^ k1.x) + __popc(q1.y ^ k1.y) + __popc(q1.z ^ k1.z) + __popc(q1.w ^ k1.w);
-                unsigned key = ((unsigned)d << 20) | (unsigned)(run + __popc(m & lt));
-                unsigned ent = tPack(idx, d, lev);
-                // insert into the lane's ascending list
+            const uint4* dk = reinterpret_cast<const uint4*>(sd.descs + (size_t)idx * 32);
+            const uint4 k0 = __ldg(dk), k1 = __ldg(dk + 1);
+            const int d = __popc(q0.x ^ k0.x) + __popc(q0.y ^ k0.y) + __popc(q0.z ^ k0.z) + __popc(q0.w ^ k0.w) +
+                          __popc(q1.x ^ k1.x) + __popc(q1.y ^ k1.y) + __popc(q1.z ^ k1.z) + __popc(q1.w ^ k1.w);
+            unsigned key = ((unsigned)d << 20) | (unsigned)run, ent = tPack(idx, d, lev);
+            ++run;
+            if (key < k[kTopK - 1]) {   // insert into the ascending list
 #pragma unroll
                 for (int i = 0; i < kTopK; i++) {
-                    if (key < k[i]) { const unsigned tk = k[i], te = e[i]; k[i] = key; e[i] = ent; key = tk; ent = te; }
+                    if (key < k[i]) { const unsigned tk = k[i], te = rec.e[i]; k[i] = key; rec.e[i] = ent; key = tk; ent = te; }
                 }
             }
-            run += __popc(m);
         }
     }
     rec.n = run;
-    if (run == 0) return;
-    // the kTopK smallest keys of the warp, in order: repeated warp minimum, the owner advances its list
-#pragma unroll
-    for (int i = 0; i < kTopK; i++) {
-        const unsigned g = tWarpMin(k[0]);
-        if (g == kNoCand) break;
-        const int owner = __ffs(__ballot_sync(0xffffffffu, k[0] == g)) - 1;
-        rec.e[i] = __shfl_sync(0xffffffffu, e[0], owner);
-        if (lane == owner) {
-#pragma unroll
-            for (int j = 0; j + 1 < kTopK; j++) { k[j] = k[j + 1]; e[j] = e[j + 1]; }
-            k[kTopK - 1] = kNoCand; e[kTopK - 1] = kNoCand;
-        }
-    }
 }
 
-// everything a warp needs to scan one (map point, side) of frame `frame`
+// everything a thread needs to scan one (map point, side) of frame `frame`
 struct TTask {
     TSide sd;
     TWindow w;
@@ -210,7 +164,8 @@ __device__ __forceinline__ TTask tMakeTask(const ProjBatchArgs& a, int frame, in
                                                     : (side ? (a.inFrameR ? a.inFrameR[j] != 0 : true) : (a.inFrame ? a.inFrame[j] != 0 : true));
     t.w = tWindow(a, pred[0], pred[1], lvl, inFrame);
     const int o = side ? a.offR[frame] : a.offL[frame];
-    t.sd.kps = (side ? a.kpR : a.kpL) + o;
+    t.sd.kp = reinterpret_cast<const char*>((side ? a.kpR : a.kpL) + o);
+    t.sd.kpStride = (int)sizeof(gvs_keypoint); t.sd.octOfs = 20;
     t.sd.descs = (side ? a.descR : a.descL) + (size_t)o * 32;
     t.sd.cellStart = (side ? a.cellStartR : a.cellStartL) + (size_t)frame * (a.maxCells + 1);
     t.sd.items = (side ? a.itemsR : a.itemsL) + o;
@@ -220,30 +175,74 @@ __device__ __forceinline__ TTask tMakeTask(const ProjBatchArgs& a, int frame, in
     return t;
 }
 
-__global__ void __launch_bounds__(256)
-projb_candidates_kernel(const ProjBatchArgs a) {
-    const int f = blockIdx.y, frame = a.frame0 + f;
-    const int lane = threadIdx.x & 31;
+// phase 1.  CTA = (slice of 256 map points of a frame, frame, side), thread = one window walk.  Every walk of the CTA reads the same
+// key grid, keys and matched flags, so they are staged in shared memory once (cellStart, items, {x, y, octave}, matchedIdxs: 20 bytes
+// per key + 4 per grid cell); a walk then only goes to global memory for its map point and for the descriptors of the candidates
+// that pass the window test.  STAGED = false (frames with more keys than the shared memory holds): the same walk on global memory.
+constexpr int kCandThreads = 256;
+template <bool STAGED>
+__global__ void __launch_bounds__(kCandThreads)
+projb_candidates_kernel(const ProjBatchArgs a, int capKeys) {
+    extern __shared__ __align__(16) uint8_t tsm[];
+    const int f = blockIdx.y, frame = a.frame0 + f, side = blockIdx.z;
+    const int tid = threadIdx.x;
     const int mp0 = a.mpOff[f], M = a.mpOff[f + 1] - mp0;
-    const bool stereo = a.mode == GVS_MATCH_STEREO_PRED;
-    const int nSides = stereo ? 2 : 1;
-    const int warpsPerRow = gridDim.x * (blockDim.x >> 5);
-    const int* skipL = a.matchedL + (a.offL[frame] - a.offL[a.frame0]);
-    const int* skipR = stereo ? a.matchedR + (a.offR[frame] - a.offR[a.frame0]) : nullptr;
-    for (int wi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); wi < M * nSides; wi += warpsPerRow) {
-        const int mpi = mp0 + wi / nSides, side = wi - (wi / nSides) * nSides;
-        TRec rec;
-#pragma unroll
-        for (int i = 0; i < kTopK; i++) rec.e[i] = kNoCand;
-        rec.n = 0;
-        // a map point that is matched already is skipped by the walk (:262,:399); matchByRadius has no such test
-        const bool skipMP = a.mode != GVS_MATCH_RADIUS && (a.matches[2 * (size_t)mpi] >= 0 || a.matches[2 * (size_t)mpi + 1] >= 0);
-        if (!skipMP) {
-            const TTask t = tMakeTask(a, frame, mpi, side, a.status);
-            tScanWindow(t.sd, t.w, a.xGrids, t.q0, t.q1, side ? skipR : skipL, a.mode == GVS_MATCH_RADIUS, lane, rec);
+    const int i0 = blockIdx.x * kCandThreads;
+    if (i0 >= M) return;
+    const int o = side ? a.offR[frame] : a.offL[frame], N = (side ? a.offR[frame + 1] : a.offL[frame + 1]) - o;
+    const int* gSkip = (side ? a.matchedR + (a.offR[frame] - a.offR[a.frame0]) : a.matchedL + (a.offL[frame] - a.offL[a.frame0]));
+    TSide sd;
+    sd.descs = (side ? a.descR : a.descL) + (size_t)o * 32;
+    const int* gCell = (side ? a.cellStartR : a.cellStartL) + (size_t)frame * (a.maxCells + 1);
+    const int* gItems = (side ? a.itemsR : a.itemsL) + o;
+    const gvs_keypoint* gKp = (side ? a.kpR : a.kpL) + o;
+    const int* skip = gSkip;
+    if (STAGED && N <= capKeys) {
+        const int nCells = a.xGrids * a.yGrids + 1;
+        int* sCell = reinterpret_cast<int*>(tsm);
+        int* sItems = sCell + ((nCells + 3) & ~3);
+        int* sSkip = sItems + capKeys;
+        TKey3* sKp = reinterpret_cast<TKey3*>(sSkip + capKeys);
+        for (int i = tid; i < nCells; i += kCandThreads) sCell[i] = gCell[i];
+        for (int i = tid; i < N; i += kCandThreads) {
+            sItems[i] = gItems[i];
+            sSkip[i] = gSkip[i];
+            const gvs_keypoint k = gKp[i];
+            sKp[i] = TKey3{k.x, k.y, k.octave};
         }
-        if (lane == 0) a.recs[2 * (size_t)mpi + side] = rec;
+        __syncthreads();
+        sd.kp = reinterpret_cast<const char*>(sKp); sd.kpStride = (int)sizeof(TKey3); sd.octOfs = 8;
+        sd.cellStart = sCell; sd.items = sItems; skip = sSkip;
+    } else {
+        sd.kp = reinterpret_cast<const char*>(gKp); sd.kpStride = (int)sizeof(gvs_keypoint); sd.octOfs = 20;
+        sd.cellStart = gCell; sd.items = gItems;
     }
+    const int i = i0 + tid;
+    if (i >= M) return;
+    const int mpi = mp0 + i;
+    const bool radiusMode = a.mode == GVS_MATCH_RADIUS;
+    TRec rec;
+#pragma unroll
+    for (int q = 0; q < kTopK; q++) rec.e[q] = kNoCand;
+    rec.n = 0;
+    // a map point that is matched already is skipped by the walk (:262,:399); matchByRadius has no such test
+    const bool skipMP = !radiusMode && (a.matches[2 * (size_t)mpi] >= 0 || a.matches[2 * (size_t)mpi + 1] >= 0);
+    if (!skipMP) {
+        const int j = a.mpSlot ? a.mpSlot[mpi] : mpi;
+        const float* pred = (side ? a.predR : a.predL) + 2 * (size_t)j;
+        int lvl = side ? a.lvlR[j] : a.lvlL[j];
+        if (lvl < 0 || lvl >= a.nLevels) {   // the reference indexes scalePyramid unchecked: reported as GVS_ERR_INVALID
+            atomicOr(a.status, kStatProjOverflow);
+            lvl = min(max(lvl, 0), a.nLevels - 1);
+        }
+        const bool inFrame = radiusMode ? true : (side ? (a.inFrameR ? a.inFrameR[j] != 0 : true) : (a.inFrame ? a.inFrame[j] != 0 : true));
+        const TWindow w = tWindow(a, pred[0], pred[1], lvl, inFrame);
+        const int row = a.mpDescRow ? a.mpDescRow[j] : j;
+        const uint4* dq = reinterpret_cast<const uint4*>(a.mpDesc + (size_t)row * 32);
+        const uint4 q0 = __ldg(dq), q1 = __ldg(dq + 1);
+        tScanLane(sd, w, a.xGrids, q0, q1, skip, radiusMode, rec);
+    }
+    a.recs[2 * (size_t)mpi + side] = rec;
 }
 
 struct TDecision { int bestDist, bestIdx, bestLev, bestLev2, secDist; };
@@ -318,19 +317,15 @@ projb_resolve_kernel(const ProjBatchArgs a) {
                 needL = !tFirstTwo(rl, mL, l1, l2);
                 if (stereo) needR = !tFirstTwo(rr, mR, r1, r2);
             }
-            for (unsigned nm = __ballot_sync(0xffffffffu, needL); nm; nm &= nm - 1) {   // rare: the stored list ran dry
-                const int src = __ffs(nm) - 1;
-                const TTask t = tMakeTask(a, frame, mp0 + base + src, 0, a.status);
-                TRec fresh;
-                tScanWindow(t.sd, t.w, a.xGrids, t.q0, t.q1, mL, radiusMode, lane, fresh);
-                if (lane == src) { rl = fresh; l1 = fresh.e[0]; l2 = fresh.e[1]; }
+            if (needL) {   // rare: the stored list ran dry
+                const TTask t = tMakeTask(a, frame, mpi, 0, a.status);
+                tScanLane(t.sd, t.w, a.xGrids, t.q0, t.q1, mL, radiusMode, rl);
+                l1 = rl.e[0]; l2 = rl.e[1];
             }
-            for (unsigned nm = __ballot_sync(0xffffffffu, needR); nm; nm &= nm - 1) {
-                const int src = __ffs(nm) - 1;
-                const TTask t = tMakeTask(a, frame, mp0 + base + src, 1, a.status);
-                TRec fresh;
-                tScanWindow(t.sd, t.w, a.xGrids, t.q0, t.q1, mR, false, lane, fresh);
-                if (lane == src) { rr = fresh; r1 = fresh.e[0]; r2 = fresh.e[1]; }
+            if (needR) {
+                const TTask t = tMakeTask(a, frame, mpi, 1, a.status);
+                tScanLane(t.sd, t.w, a.xGrids, t.q0, t.q1, mR, false, rr);
+                r1 = rr.e[0]; r2 = rr.e[1];
             }
             int accept = 0, takeL = -1, takeR = -1, out0 = -1, out1 = -1;
             if (pend) {
@@ -415,13 +410,19 @@ projb_resolve_kernel(const ProjBatchArgs a) {
 static void launchProjectBatch(const ProjBatchArgs& a, int maxMpPerFrame, cudaStream_t s, int* launches) {
     if (a.nFrames <= 0) return;
     const int nSides = a.mode == GVS_MATCH_STEREO_PRED ? 2 : 1;
-    int gx = (maxMpPerFrame * nSides + 8 * 4 - 1) / (8 * 4);   // about 4 (map point, side) tasks per warp at full fill
-    gx = std::min(std::max(gx, 1), 256);
-    projb_candidates_kernel<<<dim3(gx, a.nFrames), 256, 0, s>>>(a);
+    const int nSlices = std::max((maxMpPerFrame + kCandThreads - 1) / kCandThreads, 1);
+    const int capKeys = std::max(a.capL, a.capR), nCells = a.xGrids * a.yGrids + 1;
+    const size_t stage = (size_t)((nCells + 3) & ~3) * 4 + (size_t)capKeys * (4 + 4 + sizeof(TKey3)) + 16;
+    static size_t cfgA[64], cfgB[64];
+    if (stage <= 160 * 1024) {
+        ensureDynamicSmem(projb_candidates_kernel<true>, stage, cfgA);
+        projb_candidates_kernel<true><<<dim3(nSlices, a.nFrames, nSides), kCandThreads, stage, s>>>(a, capKeys);
+    } else {
+        projb_candidates_kernel<false><<<dim3(nSlices, a.nFrames, nSides), kCandThreads, 0, s>>>(a, capKeys);
+    }
     ++*launches;
     const size_t sm = (size_t)(a.capL + a.capR) * sizeof(int);
-    static size_t cfg[64];
-    ensureDynamicSmem(projb_resolve_kernel, sm, cfg);
+    ensureDynamicSmem(projb_resolve_kernel, sm, cfgB);
     projb_resolve_kernel<<<a.nFrames, 32, sm, s>>>(a);
     ++*launches;
 }
