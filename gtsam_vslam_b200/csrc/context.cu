@@ -345,7 +345,8 @@ static int enqueueExtract(gvs_extractor* fe, int n, cudaStream_t s) {
     else
         launchPyramid(g, fe->slab, fe->taps, fe->xWeights, fe->xSelectors, fe->xBase, fe->pyrNarrowMask, n, s, &fe->launches);
     if (T) cudaEventRecord(fe->ev[1], s);
-    launchFast(g, fe->slab, fe->fastItems, fe->nFastItems, n, fe->recs, fe->nCand, fe->cellCnt, fe->status, s, &fe->launches);
+    launchFast(g, fe->slab, fe->fastItems, fe->nFastItems, n, fe->recs, fe->nCand, fe->cellCnt, fe->status, fe->fastTma ? fe->fastMaps : nullptr, s,
+               &fe->launches);
     if (T) cudaEventRecord(fe->ev[2], s);
     launchSelect(g, n, fe->recs, fe->nCand, fe->cellCnt, fe->kept, fe->keptCnt, fe->orderedDbg, nullptr, fe->selScratch,
                  fe->selScratchPerCta, fe->selCtas, fe->workCounter, fe->status, s, &fe->launches);
@@ -617,6 +618,11 @@ int gvs_extractor_create(gvs_extractor** out, const gvs_extractor_params* params
                 }
         }
         fe->nFastItems = (int)items.size();
+        {   // TMA tile maps of every level for the FAST kernel's tile staging (box = the largest strip tile with its 3-px halo)
+            int bw = 0, bh = 0;
+            fe->fastTma = !getenv("GVS_NO_FAST_TMA") && fastTmaBox(fe->g, &bw, &bh);
+            for (int l = 0; l < g.nLevels && fe->fastTma; l++) fe->fastTma = encodeLevelMap(fe, l, bw, bh, &fe->fastMaps[l]);
+        }
         GVS_TRY(devAlloc(&fe->fastItems, items.size()));
         if (!items.empty()) GVS_TRY(cudaMemcpy(fe->fastItems, items.data(), items.size() * sizeof(FastItem), cudaMemcpyHostToDevice));
         std::vector<BlurItem> bi;

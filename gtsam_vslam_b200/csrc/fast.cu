@@ -27,7 +27,12 @@
 //      buffer; K3/K4 (select.cu) restores the reference's emission order from (cell, rank).
 //   Pass 0 runs 2a-3 at maxFastThreshold on every cell; pass 1 redoes the cells that listed no key at minFastThreshold.
 // Bound: integer ALU, not HBM: see DESIGN.md.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace gvs {
 
@@ -41,19 +46,24 @@ struct FastSmemLayout {
     int tileWords, tileRows;    // image tile: words per row, rows
     int scoreWords, scoreRows;  // score tile: words per row (1 zero word each side), rows (1 zero row each side)
     int listCap;                // entries per cell list
-    int tileOff, scoreOff, listOff, maskOff, queueOff, queueCap, total;
+    int tileOff, tile2Off, scoreOff, listOff, maskOff, queueOff, queueCap, total;
 };
 
-__host__ __device__ inline FastSmemLayout fastLayout(int maxGW, int maxGH) {
+// tma: the tile is filled by TMA box loads (row pitch a multiple of 16 bytes, buffers 128-byte aligned) into TWO buffers, so that the
+// next strip's tile arrives while the current one is processed
+__host__ __device__ inline FastSmemLayout fastLayout(int maxGW, int maxGH, bool tma = false) {
     FastSmemLayout L;
     const int maxUnits = (kFastCellsPerItem * maxGW + 3 + 3) / 4 + 1;  // unit words covering [X0, X1)
-    L.tileWords = maxUnits + 2;
+    // (a TMA box starts at a 16-byte aligned x -- the copy faults otherwise -- so up to 3 words of lead-in are fetched with the tile)
+    L.tileWords = tma ? (maxUnits + 2 + 3 + 3) & ~3 : maxUnits + 2;
     L.tileRows = maxGH + 6;
     L.scoreWords = maxUnits + 2;
     L.scoreRows = maxGH + 2;
     L.listCap = ((maxGW + 1) / 2) * ((maxGH + 1) / 2);
     L.tileOff = 0;
-    L.scoreOff = L.tileOff + L.tileWords * L.tileRows * 4;
+    const int tileBytes = tma ? (L.tileWords * L.tileRows * 4 + 127) & ~127 : L.tileWords * L.tileRows * 4;
+    L.tile2Off = L.tileOff + tileBytes;
+    L.scoreOff = tma ? L.tile2Off + tileBytes : L.tile2Off;
     L.maskOff = L.scoreOff + L.scoreWords * L.scoreRows * 4;
     L.listOff = ((L.maskOff + maxUnits * 12 + 15) / 16) * 16;
     L.queueOff = L.listOff + kFastCellsPerItem * L.listCap * 4;
@@ -124,47 +134,93 @@ __device__ __forceinline__ unsigned scorePair(const unsigned (&W)[7][3], int tMi
 #ifndef GVS_FAST_CTAS
 #define GVS_FAST_CTAS 3
 #endif
-__global__ void __launch_bounds__(256, GVS_FAST_CTAS)
-fast_cells_kernel(const __grid_constant__ Geometry g, const uint8_t* __restrict__ slab,
-                  const FastItem* __restrict__ items, int maxGW, int maxGH, CandRec* __restrict__ recs,
-                  int* __restrict__ nCand, unsigned short* __restrict__ cellCnt, int* __restrict__ status) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    __shared__ int sCnt[kFastCellsPerItem], sBase[kFastCellsPerItem];
 
-    const FastItem it = items[blockIdx.x];
-    const int img = blockIdx.y;
+// geometry of one work item (a strip of cells of one cell row)
+struct FastStrip {
+    int level, y0, y1, X0, X1, xu, nW, rows, cols, gW;
+};
+__device__ __forceinline__ FastStrip fastStrip(const Geometry& g, const FastItem& it) {
+    FastStrip s;
     const LevelGeom& lv = g.lv[it.level];
-    const FastSmemLayout L = fastLayout(maxGW, maxGH);
-    unsigned* tile = reinterpret_cast<unsigned*>(smem + L.tileOff);
+    const int edge = g.edge;  // (edgeThreshold - fastEdge) + 3: first tested pixel of the first cell
+    s.level = it.level;
+    s.y0 = edge + it.iR * lv.gridH; s.y1 = min(s.y0 + lv.gridH, lv.h - edge);
+    s.X0 = edge + it.iC0 * lv.gridW; s.X1 = min(s.X0 + it.nC * lv.gridW, lv.w - edge);
+    s.rows = s.y1 - s.y0; s.cols = s.X1 - s.X0;
+    s.gW = lv.gridW;
+    // unit words: 4-px aligned words covering [X0, X1); tile word 0 is the word left of unit 0
+    s.xu = s.X0 & ~3;                 // x of unit 0
+    // number of unit words; at least 2: i / 1 has no 32-bit magic number, and a narrow last cell can leave a single word (the
+    // extra word lies inside the row -- X1 <= w - edge -- and is fully masked out)
+    s.nW = max((s.X1 - s.xu + 3) >> 2, 2);
+    return s;
+}
+
+// USE_TMA: a CTA takes itemsPerCta consecutive strips of one image; the (rows+6) x (cols+8) tile of strip k+1 is fetched by one TMA
+// box load (cp.async.bulk.tensor) into the second tile buffer while strip k is processed.  Otherwise (no tensor-map encoder, or a
+// strip wider than a TMA box) every thread stages its share of the tile with 4-byte loads.
+struct FastMaps { CUtensorMap m[kMaxLevels]; };
+
+template <bool USE_TMA>
+__global__ void __launch_bounds__(256, GVS_FAST_CTAS)
+fast_cells_kernel(const __grid_constant__ Geometry g, const __grid_constant__ FastMaps maps /* TMA tile map per level */, const uint8_t* __restrict__ slab,
+                  const FastItem* __restrict__ items, int nItems, int itemsPerCta, int maxGW, int maxGH, CandRec* __restrict__ recs,
+                  int* __restrict__ nCand, unsigned short* __restrict__ cellCnt, int* __restrict__ status) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ int sCnt[kFastCellsPerItem], sBase[kFastCellsPerItem];
+    __shared__ __align__(8) unsigned long long sBar[2];
+
+    const int img = blockIdx.y;
+    const FastSmemLayout L = fastLayout(maxGW, maxGH, USE_TMA);
     unsigned* score = reinterpret_cast<unsigned*>(smem + L.scoreOff);
     unsigned* masks = reinterpret_cast<unsigned*>(smem + L.maskOff);  // per unit: in-range, has-left, has-right byte masks
     unsigned* lists = reinterpret_cast<unsigned*>(smem + L.listOff);
-
-    const int edge = g.edge;  // (edgeThreshold - fastEdge) + 3: first tested pixel of the first cell
-    const int y0 = edge + it.iR * lv.gridH, y1 = min(y0 + lv.gridH, lv.h - edge);
-    const int X0 = edge + it.iC0 * lv.gridW, X1 = min(X0 + it.nC * lv.gridW, lv.w - edge);
     const int tid = threadIdx.x;
+    const int first = blockIdx.x * itemsPerCta, last = min(first + itemsPerCta, nItems);
+    // one TMA box load of the tile of strip `idx` into buffer `buf` (x from xu - 4, y from y0 - 3); issued by thread 0
+    auto issue = [&](int idx, int buf) {
+        const FastStrip n = fastStrip(g, items[idx]);
+        if (n.rows <= 0 || n.cols <= 0) return;
+        const unsigned bar = smemAddr(&sBar[buf]);
+        mbarExpectTx(bar, (unsigned)(L.tileWords * 4 * L.tileRows));
+        const unsigned dst = smemAddr(smem + (buf ? L.tile2Off : L.tileOff));
+        const int x = (n.xu - 4) & ~15, y = n.y0 - 3;   // x: multiple of 16 bytes (tma_probe.cu); the strip's tile starts ((xu - 4) & 15) / 4 words in
+        tmaLoadTile3d(dst, &maps.m[n.level], x, y, img, bar);
+    };
+    if (USE_TMA) {
+        if (tid == 0) {
+            mbarInit(smemAddr(&sBar[0]), 1);
+            mbarInit(smemAddr(&sBar[1]), 1);
+            if (first < last) issue(first, 0);
+        }
+        __syncthreads();   // (the barriers are initialised before anybody polls them)
+    }
+    unsigned used0 = 0, used1 = 0;   // loads consumed per buffer (their mbarrier phase)
+    for (int idx = first; idx < last; idx++) {
+    const int buf = USE_TMA ? (idx - first) & 1 : 0;
+    const FastItem it = items[idx];
+    const LevelGeom& lv = g.lv[it.level];
+    const FastStrip S = fastStrip(g, it);
+    const int y0 = S.y0, X0 = S.X0, rows = S.rows, cols = S.cols, gW = S.gW, xu = S.xu, nW = S.nW;
+    if (USE_TMA && tid == 0 && idx + 1 < last) issue(idx + 1, buf ^ 1);   // (buffer buf^1 was last read by strip idx-1, which ended with a CTA barrier)
     if (tid < kFastCellsPerItem) sCnt[tid] = 0;
-    const int rows = y1 - y0, cols = X1 - X0;
     if (rows <= 0 || cols <= 0) {  // empty strip: still publish zero counts for its cells
         if (tid < it.nC) cellCnt[(size_t)img * g.cellsPerImage + lv.cellBase + it.iR * lv.nCols + it.iC0 + tid] = 0;
-        return;
+        __syncthreads();
+        continue;
     }
-    const int gW = lv.gridW;
-    // unit words: 4-px aligned words covering [X0, X1); tile word 0 is the word left of unit 0
-    const int xu = X0 & ~3;                 // x of unit 0
-    // number of unit words; at least 2: i / 1 has no 32-bit magic number, and a narrow last cell can leave a single word (the
-    // extra word lies inside the row -- X1 <= w - edge -- and is fully masked out)
-    const int nW = max((X1 - xu + 3) >> 2, 2);
+    unsigned* tile = reinterpret_cast<unsigned*>(smem + (buf ? L.tile2Off : L.tileOff)) + (USE_TMA ? ((xu - 4) & 15) >> 2 : 0);
     const int tw = nW + 2, th = rows + 6;   // tile words per row / rows
     // i / d = umulhi(i, 2^32 / d + 1) for the small i used here (d >= 2)
     const unsigned magicT = 0xffffffffu / (unsigned)tw + 1u, magicU = 0xffffffffu / (unsigned)nW + 1u;
 
     // ---- 1. stage the image tile (x from xu-4, y from y0-3), zero the score tile, build the per-unit byte masks
-    const uint8_t* src = levelPtr(slab, g, img, it.level) + (size_t)(y0 - 3) * lv.pitch + (xu - 4);
-    for (int i = tid; i < tw * th; i += 256) {
-        const int r = (int)__umulhi((unsigned)i, magicT), c = i - r * tw;
-        tile[r * L.tileWords + c] = __ldg(reinterpret_cast<const unsigned*>(src + (size_t)r * lv.pitch) + c);
+    if (!USE_TMA) {
+        const uint8_t* src = levelPtr(slab, g, img, it.level) + (size_t)(y0 - 3) * lv.pitch + (xu - 4);
+        for (int i = tid; i < tw * th; i += 256) {
+            const int r = (int)__umulhi((unsigned)i, magicT), c = i - r * tw;
+            tile[r * L.tileWords + c] = __ldg(reinterpret_cast<const unsigned*>(src + (size_t)r * lv.pitch) + c);
+        }
     }
     for (int i = tid; i < L.scoreWords * (rows + 2); i += 256) score[i] = 0;
     for (int j = tid; j < nW; j += 256) {
@@ -180,6 +236,10 @@ fast_cells_kernel(const __grid_constant__ Geometry g, const uint8_t* __restrict_
             if (lx + 1 < cx1) hasR |= 0xffu << (8 * b);
         }
         masks[3 * j] = inr; masks[3 * j + 1] = hasL; masks[3 * j + 2] = hasR;
+    }
+    if (USE_TMA) {
+        mbarWait(smemAddr(&sBar[buf]), (buf ? used1 : used0) & 1u);
+        if (buf) used1++; else used0++;
     }
     __syncthreads();
 
@@ -339,20 +399,40 @@ fast_cells_kernel(const __grid_constant__ Geometry g, const uint8_t* __restrict_
         rec.w1 = (unsigned)(it.iR * lv.nCols + it.iC0 + c) | ((unsigned)rank << 16);
         out[slot] = rec;
     }
+    __syncthreads();   // the next strip reuses the score tile, the masks, the lists and the counters
+    }   // strips of this CTA
+}
+
+// box of the TMA tile loads (bytes x rows), or false when a strip does not fit a TMA box (256 x 256)
+bool fastTmaBox(const Geometry& g, int* boxW, int* boxH) {
+    int maxGW = 0, maxGH = 0;
+    for (int l = 0; l < g.nLevels; l++) { maxGW = std::max(maxGW, g.lv[l].gridW); maxGH = std::max(maxGH, g.lv[l].gridH); }
+    const FastSmemLayout L = fastLayout(maxGW, maxGH, true);
+    *boxW = L.tileWords * 4; *boxH = L.tileRows;
+    return *boxW <= 256 && *boxH <= 256 && L.total <= 200 * 1024;
 }
 
 void launchFast(const Geometry& g, const uint8_t* slab, const FastItem* items, int nItems, int nImages, CandRec* recs,
-                int* nCand, unsigned short* cellCnt, int* status, cudaStream_t s, int* launches) {
+                int* nCand, unsigned short* cellCnt, int* status, const CUtensorMap* levelMaps, cudaStream_t s, int* launches) {
     int maxGW = 0, maxGH = 0;
     for (int l = 0; l < g.nLevels; l++) { maxGW = std::max(maxGW, g.lv[l].gridW); maxGH = std::max(maxGH, g.lv[l].gridH); }
-    const FastSmemLayout L = fastLayout(maxGW, maxGH);
-    static size_t cfg[64];
-    ensureDynamicSmem(fast_cells_kernel, (size_t)L.total, cfg);
     cudaMemsetAsync(nCand, 0, sizeof(int) * (size_t)nImages * kMaxLevels, s);
-    if (nItems > 0) {
-        fast_cells_kernel<<<dim3(nItems, nImages), 256, L.total, s>>>(g, slab, items, maxGW, maxGH, recs, nCand, cellCnt, status);
-        ++*launches;
+    if (nItems <= 0) return;
+    static size_t cfgA[64], cfgB[64];
+    static const int perCta = [] { const char* e = getenv("GVS_FAST_ITEMS"); const int v = e ? atoi(e) : 3; return std::min(std::max(v, 1), 64); }();
+    FastMaps pm{};
+    if (levelMaps) {
+        const FastSmemLayout L = fastLayout(maxGW, maxGH, true);
+        memcpy(pm.m, levelMaps, sizeof(CUtensorMap) * (size_t)g.nLevels);
+        ensureDynamicSmem(fast_cells_kernel<true>, (size_t)L.total, cfgA);
+        fast_cells_kernel<true><<<dim3((nItems + perCta - 1) / perCta, nImages), 256, L.total, s>>>(g, pm, slab, items, nItems, perCta, maxGW, maxGH, recs,
+                                                                                                 nCand, cellCnt, status);
+    } else {
+        const FastSmemLayout L = fastLayout(maxGW, maxGH, false);
+        ensureDynamicSmem(fast_cells_kernel<false>, (size_t)L.total, cfgB);
+        fast_cells_kernel<false><<<dim3(nItems, nImages), 256, L.total, s>>>(g, pm, slab, items, nItems, 1, maxGW, maxGH, recs, nCand, cellCnt, status);
     }
+    ++*launches;
 }
 
 }  // namespace gvs

@@ -74,6 +74,8 @@ struct gvs_extractor {
     PyrSpan* pyrSpans = nullptr;
     alignas(64) CUtensorMap pyrMaps[kPyrMaxGroups];   // TMA tile maps of the groups' base levels
     unsigned pyrNarrowMask = 0;       // bit l: every column group of level l spans at most 8 source bytes (pyr_down_kernel<true>)
+    alignas(64) CUtensorMap fastMaps[kMaxLevels];   // TMA tile maps of the levels for the FAST kernel
+    bool fastTma = false;
     FastItem* fastItems = nullptr;
     int nFastItems = 0;
     // CUDA graphs of the extraction pipeline for small batches (latency mode): one instantiated graph per batch size
