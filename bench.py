@@ -449,6 +449,7 @@ def main():
     if also == "auto":
         also = "kitti4096,hires" if world > 1 else ""
     others = {}
+    tma = arm.feL.tma_stages()
     del arm
     torch.cuda.empty_cache()
     for name in [a for a in also.split(",") if a]:
@@ -494,6 +495,7 @@ def main():
                        f"{chunks} slots, a ticket is collected when its slot is needed again) -> keypoints, descriptors, stereo arrays and temporal "
                        f"matches back in pinned host memory; wall clock around all {e2e_steps} steps including the final drain"},
         "gpu_launches": int(n_launch),
+        "tma_stages": {"pyramid": bool(tma & 1), "fast": bool(tma & 2)},
         "stage_ms": {k: round(v, 4) for k, v in stage_acc.items()},
         "stage_ms_note": f"per step, left+right, each kernel alone on one stream (sum {serial_ms:.3f} ms); the timed region overlaps "
                          "the two sides on separate streams",

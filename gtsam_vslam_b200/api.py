@@ -28,7 +28,7 @@ SYMBOLS = [
     "gvs_extractor_create", "gvs_extractor_destroy", "gvs_extractor_tables", "gvs_tables_from_params", "gvs_extractor_level_size",
     "gvs_extract", "gvs_extract_batch_host", "gvs_extractor_input", "gvs_extract_batch_resident",
     "gvs_extractor_sync", "gvs_extractor_set_rectify_maps", "gvs_extract_batch_host_raw", "gvs_extract_offsets", "gvs_extract_download", "gvs_extractor_set_stream",
-    "gvs_debug_level_image", "gvs_debug_level_candidates", "gvs_debug_level_kept", "gvs_debug_select", "gvs_debug_check_guards",
+    "gvs_debug_level_image", "gvs_debug_level_candidates", "gvs_debug_level_kept", "gvs_debug_select", "gvs_debug_check_guards", "gvs_extractor_tma_stages",
     "gvs_matcher_create", "gvs_matcher_destroy", "gvs_stereo_match_batch", "gvs_stereo_download",
     "gvs_assign_grids_batch", "gvs_grid_download", "gvs_track_stereo_batch_host",
     "gvs_track_stereo_batch_resident", "gvs_matcher_sync", "gvs_matcher_set_stream", "gvs_match_projection", "gvs_match_projection_batch",
@@ -97,6 +97,7 @@ def load_library() -> C.CDLL:
     vp, i32, f32 = C.c_void_p, C.c_int, C.c_float
     lib.gvs_extractor_create.argtypes = [C.POINTER(vp), C.POINTER(_Params), i32, i32, i32, i32]
     lib.gvs_extractor_destroy.argtypes = [vp]
+    lib.gvs_extractor_tma_stages.argtypes = [vp]
     lib.gvs_extractor_tables.argtypes = [vp] + [vp] * 6
     lib.gvs_tables_from_params.argtypes = [C.POINTER(_Params)] + [vp] * 6
     lib.gvs_extractor_level_size.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32)]
@@ -280,6 +281,10 @@ class FeatureExtractor:
 
     def sync(self) -> None:
         _check(self._lib.gvs_extractor_sync(self.h))
+
+    def tma_stages(self) -> int:
+        """bit 0: the fused pyramid kernel, bit 1: the FAST kernel stage their tiles with TMA box loads (include/gvs.h)."""
+        return int(self._lib.gvs_extractor_tma_stages(self.h))
 
     def offsets(self, n: int) -> np.ndarray:
         """Dense key offsets of the first n images of the last batch (n + 1 entries)."""

@@ -135,7 +135,7 @@ void launchRepack(const Geometry& g, const uint8_t* tight, uint8_t* slab, int nI
 // levelMaps: TMA tile maps of the pyramid levels with the box of fastTmaBox (HOST array of nLevels entries, passed to the kernel as a parameter), or nullptr
 void launchFast(const Geometry& g, const uint8_t* slab, const FastItem* items, int nItems, int nImages, CandRec* recs,
                 int* nCand, unsigned short* cellCnt, int* status, const CUtensorMap* levelMaps, cudaStream_t s, int* launches);
-bool fastTmaBox(const Geometry& g, int* boxW, int* boxH);
+bool fastTmaBox(const Geometry& g, int* boxWords, int* boxH);
 void launchSelect(const Geometry& g, int nImages, const CandRec* recs, const int* nCand, const unsigned short* cellCnt,
                   KeptKey* kept, int* keptCnt, unsigned* orderedDbg, unsigned* sortedDbg, uint8_t* scratch,
                   size_t scratchPerCta, int nCtas, int* workCounter, int* status, cudaStream_t s, int* launches);

@@ -210,15 +210,16 @@ EncodeTiledFn tensorMapEncoder() {
     return fn;
 }
 
-// u8 tile map over pyramid level `level` of every image slot: (x bytes, y rows, image)
-bool encodeLevelMap(const gvs_extractor* fe, int level, int boxW, int boxH, CUtensorMap* out) {
+// tile map over pyramid level `level` of every image slot: (x, y rows, image); x counts bytes, or 32-bit words with `words`
+// (a box dimension is limited to 256 elements)
+bool encodeLevelMap(const gvs_extractor* fe, int level, int boxW, int boxH, CUtensorMap* out, bool words = false) {
     EncodeTiledFn enc = tensorMapEncoder();
     if (!enc) return false;
     const LevelGeom& lv = fe->g.lv[level];
-    const cuuint64_t dims[3] = {(cuuint64_t)lv.pitch, (cuuint64_t)lv.h, (cuuint64_t)fe->maxImages};
+    const cuuint64_t dims[3] = {(cuuint64_t)(words ? lv.pitch / 4 : lv.pitch), (cuuint64_t)lv.h, (cuuint64_t)fe->maxImages};
     const cuuint64_t strides[2] = {(cuuint64_t)lv.pitch, (cuuint64_t)fe->g.slabBytes};
     const cuuint32_t box[3] = {(cuuint32_t)boxW, (cuuint32_t)boxH, 1u}, es[3] = {1u, 1u, 1u};
-    return enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, fe->slab + lv.off, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    return enc(out, words ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, fe->slab + lv.off, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -499,6 +500,11 @@ int gvs_device_count(void) {
     return n;
 }
 
+int gvs_extractor_tma_stages(const gvs_extractor* fe) {
+    if (!fe) return fail(GVS_ERR_INVALID, "null handle");
+    return (fe->pyrPlan.nGroups > 0 ? 1 : 0) | (fe->fastTma ? 2 : 0);
+}
+
 int gvs_debug_check_guards(int* n_checked) {
     std::lock_guard<std::mutex> lock(g_guardMutex);
     if (n_checked) *n_checked = (int)g_guards.size();
@@ -621,7 +627,7 @@ int gvs_extractor_create(gvs_extractor** out, const gvs_extractor_params* params
         {   // TMA tile maps of every level for the FAST kernel's tile staging (box = the largest strip tile with its 3-px halo)
             int bw = 0, bh = 0;
             fe->fastTma = !getenv("GVS_NO_FAST_TMA") && fastTmaBox(fe->g, &bw, &bh);
-            for (int l = 0; l < g.nLevels && fe->fastTma; l++) fe->fastTma = encodeLevelMap(fe, l, bw, bh, &fe->fastMaps[l]);
+            for (int l = 0; l < g.nLevels && fe->fastTma; l++) fe->fastTma = encodeLevelMap(fe, l, bw, bh, &fe->fastMaps[l], true);
         }
         GVS_TRY(devAlloc(&fe->fastItems, items.size()));
         if (!items.empty()) GVS_TRY(cudaMemcpy(fe->fastItems, items.data(), items.size() * sizeof(FastItem), cudaMemcpyHostToDevice));

@@ -28,6 +28,7 @@
 //   Pass 0 runs 2a-3 at maxFastThreshold on every cell; pass 1 redoes the cells that listed no key at minFastThreshold.
 // Bound: integer ALU, not HBM: see DESIGN.md.
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 
@@ -51,11 +52,14 @@ struct FastSmemLayout {
 
 // tma: the tile is filled by TMA box loads (row pitch a multiple of 16 bytes, buffers 128-byte aligned) into TWO buffers, so that the
 // next strip's tile arrives while the current one is processed
-__host__ __device__ inline FastSmemLayout fastLayout(int maxGW, int maxGH, bool tma = false) {
+// maxSW: width in pixels of the widest strip (cells of a strip x cell pitch of its level), maxGW / maxGH: largest cell pitch
+__host__ __device__ inline FastSmemLayout fastLayout(int maxSW, int maxGW, int maxGH, bool tma = false, bool twoTiles = false) {
     FastSmemLayout L;
-    const int maxUnits = (kFastCellsPerItem * maxGW + 3 + 3) / 4 + 1;  // unit words covering [X0, X1)
+    const int maxUnits = (maxSW + 3 + 3) / 4 + 1;  // unit words covering [X0, X1)
     // (a TMA box starts at a 16-byte aligned x -- the copy faults otherwise -- so up to 3 words of lead-in are fetched with the tile)
-    L.tileWords = tma ? (maxUnits + 2 + 3 + 3) & ~3 : maxUnits + 2;
+    // and the row pitch is an odd multiple of 16 bytes: corners line up vertically, and a pitch of 0 mod 32 words would put the same
+    // column of every row into one bank
+    L.tileWords = tma ? ((maxUnits + 2 + 3 + 3) & ~3) | 4 : maxUnits + 2;
     L.tileRows = maxGH + 6;
     L.scoreWords = maxUnits + 2;
     L.scoreRows = maxGH + 2;
@@ -63,7 +67,8 @@ __host__ __device__ inline FastSmemLayout fastLayout(int maxGW, int maxGH, bool 
     L.tileOff = 0;
     const int tileBytes = tma ? (L.tileWords * L.tileRows * 4 + 127) & ~127 : L.tileWords * L.tileRows * 4;
     L.tile2Off = L.tileOff + tileBytes;
-    L.scoreOff = tma ? L.tile2Off + tileBytes : L.tile2Off;
+    if (!(tma && twoTiles)) L.tile2Off = L.tileOff;   // one buffer: a CTA that takes a single strip has nothing to prefetch
+    L.scoreOff = L.tile2Off + tileBytes;
     L.maskOff = L.scoreOff + L.scoreWords * L.scoreRows * 4;
     L.listOff = ((L.maskOff + maxUnits * 12 + 15) / 16) * 16;
     L.queueOff = L.listOff + kFastCellsPerItem * L.listCap * 4;
@@ -164,14 +169,14 @@ struct FastMaps { CUtensorMap m[kMaxLevels]; };
 template <bool USE_TMA>
 __global__ void __launch_bounds__(256, GVS_FAST_CTAS)
 fast_cells_kernel(const __grid_constant__ Geometry g, const __grid_constant__ FastMaps maps /* TMA tile map per level */, const uint8_t* __restrict__ slab,
-                  const FastItem* __restrict__ items, int nItems, int itemsPerCta, int maxGW, int maxGH, CandRec* __restrict__ recs,
+                  const FastItem* __restrict__ items, int nItems, int itemsPerCta, int maxSW, int maxGW, int maxGH, CandRec* __restrict__ recs,
                   int* __restrict__ nCand, unsigned short* __restrict__ cellCnt, int* __restrict__ status) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ int sCnt[kFastCellsPerItem], sBase[kFastCellsPerItem];
     __shared__ __align__(8) unsigned long long sBar[2];
 
     const int img = blockIdx.y;
-    const FastSmemLayout L = fastLayout(maxGW, maxGH, USE_TMA);
+    const FastSmemLayout L = fastLayout(maxSW, maxGW, maxGH, USE_TMA, itemsPerCta > 1);
     unsigned* score = reinterpret_cast<unsigned*>(smem + L.scoreOff);
     unsigned* masks = reinterpret_cast<unsigned*>(smem + L.maskOff);  // per unit: in-range, has-left, has-right byte masks
     unsigned* lists = reinterpret_cast<unsigned*>(smem + L.listOff);
@@ -184,8 +189,9 @@ fast_cells_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Fa
         const unsigned bar = smemAddr(&sBar[buf]);
         mbarExpectTx(bar, (unsigned)(L.tileWords * 4 * L.tileRows));
         const unsigned dst = smemAddr(smem + (buf ? L.tile2Off : L.tileOff));
-        const int x = (n.xu - 4) & ~15, y = n.y0 - 3;   // x: multiple of 16 bytes (tma_probe.cu); the strip's tile starts ((xu - 4) & 15) / 4 words in
-        tmaLoadTile3d(dst, &maps.m[n.level], x, y, img, bar);
+        // the maps have 32-bit elements (a box may be 256 of them wide); x must be a multiple of 16 bytes (tools/tma_probe.cu), so
+        // the box starts up to 3 words left of the strip's tile
+        tmaLoadTile3d(dst, &maps.m[n.level], ((n.xu - 4) & ~15) >> 2, n.y0 - 3, img, bar);
     };
     if (USE_TMA) {
         if (tid == 0) {
@@ -237,8 +243,8 @@ fast_cells_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Fa
         }
         masks[3 * j] = inr; masks[3 * j + 1] = hasL; masks[3 * j + 2] = hasR;
     }
-    if (USE_TMA) {
-        mbarWait(smemAddr(&sBar[buf]), (buf ? used1 : used0) & 1u);
+    if (USE_TMA) {   // one thread polls the tile's mbarrier (a polling warp takes issue slots from the CTAs that compute); the CTA
+        if (tid == 0) mbarWait(smemAddr(&sBar[buf]), (buf ? used1 : used0) & 1u);   // barrier below passes the arrival on
         if (buf) used1++; else used0++;
     }
     __syncthreads();
@@ -403,34 +409,52 @@ fast_cells_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Fa
     }   // strips of this CTA
 }
 
-// box of the TMA tile loads (bytes x rows), or false when a strip does not fit a TMA box (256 x 256)
-bool fastTmaBox(const Geometry& g, int* boxW, int* boxH) {
-    int maxGW = 0, maxGH = 0;
-    for (int l = 0; l < g.nLevels; l++) { maxGW = std::max(maxGW, g.lv[l].gridW); maxGH = std::max(maxGH, g.lv[l].gridH); }
-    const FastSmemLayout L = fastLayout(maxGW, maxGH, true);
-    *boxW = L.tileWords * 4; *boxH = L.tileRows;
-    return *boxW <= 256 && *boxH <= 256 && L.total <= 200 * 1024;
+// box of the TMA tile loads (32-bit words x rows), or false when a strip does not fit a TMA box (256 x 256 elements)
+struct FastDims { int maxSW, maxGW, maxGH; };
+static FastDims fastDims(const Geometry& g) {
+    FastDims d{0, 0, 0};
+    for (int l = 0; l < g.nLevels; l++) {
+        const LevelGeom& lv = g.lv[l];
+        d.maxGW = std::max(d.maxGW, lv.gridW); d.maxGH = std::max(d.maxGH, lv.gridH);
+        if (lv.nCols <= 0) continue;
+        const int nStrips = (lv.nCols + kFastCellsPerItem - 1) / kFastCellsPerItem;   // the cut of gvs_extractor_create
+        d.maxSW = std::max(d.maxSW, ((lv.nCols + nStrips - 1) / nStrips) * lv.gridW);
+    }
+    return d;
+}
+
+bool fastTmaBox(const Geometry& g, int* boxWords, int* boxH) {
+    const FastDims d = fastDims(g);
+    const FastSmemLayout L = fastLayout(d.maxSW, d.maxGW, d.maxGH, true, true);
+    *boxWords = L.tileWords; *boxH = L.tileRows;
+    return *boxWords <= 256 && *boxH <= 256 && L.total <= 200 * 1024;
 }
 
 void launchFast(const Geometry& g, const uint8_t* slab, const FastItem* items, int nItems, int nImages, CandRec* recs,
                 int* nCand, unsigned short* cellCnt, int* status, const CUtensorMap* levelMaps, cudaStream_t s, int* launches) {
-    int maxGW = 0, maxGH = 0;
-    for (int l = 0; l < g.nLevels; l++) { maxGW = std::max(maxGW, g.lv[l].gridW); maxGH = std::max(maxGH, g.lv[l].gridH); }
+    const FastDims d = fastDims(g);
     cudaMemsetAsync(nCand, 0, sizeof(int) * (size_t)nImages * kMaxLevels, s);
     if (nItems <= 0) return;
     static size_t cfgA[64], cfgB[64];
-    static const int perCta = [] { const char* e = getenv("GVS_FAST_ITEMS"); const int v = e ? atoi(e) : 3; return std::min(std::max(v, 1), 64); }();
+    static const int perCta = [] { const char* e = getenv("GVS_FAST_ITEMS"); const int v = e ? atoi(e) : 1; return std::min(std::max(v, 1), 64); }();
     FastMaps pm{};
     if (levelMaps) {
-        const FastSmemLayout L = fastLayout(maxGW, maxGH, true);
+        const FastSmemLayout L = fastLayout(d.maxSW, d.maxGW, d.maxGH, true, perCta > 1);
         memcpy(pm.m, levelMaps, sizeof(CUtensorMap) * (size_t)g.nLevels);
+        int dv = 0;
+        cudaGetDevice(&dv);
+        static std::atomic<bool> carved[64];
+        if (!carved[dv & 63].exchange(true))   // (first launch on this device)
+            // two tile buffers per CTA: ask for the largest shared-memory carve-out so that as many CTAs fit as with one buffer
+            // (the kernel reads global memory through TMA only, it has no use for L1)
+            cudaFuncSetAttribute(fast_cells_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         ensureDynamicSmem(fast_cells_kernel<true>, (size_t)L.total, cfgA);
-        fast_cells_kernel<true><<<dim3((nItems + perCta - 1) / perCta, nImages), 256, L.total, s>>>(g, pm, slab, items, nItems, perCta, maxGW, maxGH, recs,
+        fast_cells_kernel<true><<<dim3((nItems + perCta - 1) / perCta, nImages), 256, L.total, s>>>(g, pm, slab, items, nItems, perCta, d.maxSW, d.maxGW, d.maxGH, recs,
                                                                                                  nCand, cellCnt, status);
     } else {
-        const FastSmemLayout L = fastLayout(maxGW, maxGH, false);
+        const FastSmemLayout L = fastLayout(d.maxSW, d.maxGW, d.maxGH, false);
         ensureDynamicSmem(fast_cells_kernel<false>, (size_t)L.total, cfgB);
-        fast_cells_kernel<false><<<dim3(nItems, nImages), 256, L.total, s>>>(g, pm, slab, items, nItems, 1, maxGW, maxGH, recs, nCand, cellCnt, status);
+        fast_cells_kernel<false><<<dim3(nItems, nImages), 256, L.total, s>>>(g, pm, slab, items, nItems, 1, d.maxSW, d.maxGW, d.maxGH, recs, nCand, cellCnt, status);
     }
     ++*launches;
 }

@@ -9,7 +9,8 @@
 //     Right keys are stored level by level, so only the levels octL-1..octL+1 are scanned.
 //   * the reference's "u" test uses pt.y (sic): yL - fx <= yR <= yL.
 //   * Hamming distance: 8 x __popc on 32-bit words, warp-shuffle argmin on (dist << 20 | j).
-//   * SAD refinement on the unblurred level octL of both pyramids: 22 lanes = 11 shifts x 2 row halves,
+//   * SAD refinement on the unblurred level octL of both pyramids: 22 lanes = 11 shifts x 2 row halves, a patch row = 3 words
+//     compared four bytes at a time (VABSDIFF4 with accumulate);
 //     skipped shifts keep 0.0 (App. B.3); float32 parabola and depth with explicit round-to-nearest ops.
 //   * leftIdxs[j] is last-writer-wins in left-index order (App. B.4) = atomicMax over the accepted left indices.
 // stereo_finalize: one CTA per frame; bitonic sorts of (depth, idx) and (SAD, idx) give the lowest floor(1%)
@@ -22,6 +23,15 @@ namespace gvs {
 __device__ __forceinline__ int hamming256(const uint4& a0, const uint4& a1, const uint4& b0, const uint4& b1) {
     return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
            __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+// the 11 bytes at p as three words (the last one holds 3 bytes): 4 aligned word loads + funnel shifts.  The rows are padded
+// (pitch a multiple of 64, 256 spare bytes behind the last slab), so the aligned words around the patch are always readable.
+__device__ __forceinline__ void patchRow(const uint8_t* p, unsigned& w0, unsigned& w1, unsigned& w2) {
+    const unsigned sh = ((unsigned)(size_t)p & 3u) * 8u;
+    const unsigned* q = reinterpret_cast<const unsigned*>(p - ((size_t)p & 3u));
+    const unsigned a0 = __ldg(q), a1 = __ldg(q + 1), a2 = __ldg(q + 2), a3 = __ldg(q + 3);
+    w0 = __funnelshift_r(a0, a1, sh); w1 = __funnelshift_r(a1, a2, sh); w2 = __funnelshift_r(a2, a3, sh) & 0x00ffffffu;
 }
 
 __global__ void __launch_bounds__(256)
@@ -82,11 +92,12 @@ stereo_match_kernel(const __grid_constant__ Geometry g, const StereoArgs a) {
                 const bool skip = startW < 0 || endW >= lv.w;
                 if (lane < 22 && !skip) {
                     const int rEnd = half ? 11 : 6;
+                    // 11 pixels of a row = 3 words cut out of 4 aligned ones; |l - r| summed four bytes at a time (VABSDIFF4)
                     for (int r = half * 6; r < rEnd; r++) {
-                        const uint8_t* pl = imL + (size_t)(scvL - 5 + r) * lv.pitch + (scuL - 5);
-                        const uint8_t* pr = imR + (size_t)(scvL - 5 + r) * lv.pitch + startW;
-#pragma unroll
-                        for (int c = 0; c < 11; c++) part += abs((int)pl[c] - (int)pr[c]);
+                        unsigned l0, l1, l2, r0, r1, r2;
+                        patchRow(imL + (size_t)(scvL - 5 + r) * lv.pitch + (scuL - 5), l0, l1, l2);
+                        patchRow(imR + (size_t)(scvL - 5 + r) * lv.pitch + startW, r0, r1, r2);
+                        part += (int)__vsadu4(l0, r0) + (int)__vsadu4(l1, r1) + (int)__vsadu4(l2, r2);
                     }
                 }
                 part += __shfl_down_sync(0xffffffffu, part, 11);  // lanes 0..10 now hold the full SAD of shift s

@@ -125,6 +125,11 @@ int gvs_extract_download(gvs_extractor* fe, int first, int count, gvs_keypoint* 
  * handle's own stream. */
 int gvs_extractor_set_stream(gvs_extractor* fe, void* cuda_stream);
 
+/* Which stages of this handle stage their tiles with TMA box loads (cp.async.bulk.tensor): bit 0 = the fused pyramid kernel,
+ * bit 1 = the FAST kernel.  0 when the driver offers no tensor-map encoder or the geometry does not fit a TMA box (the kernels
+ * then stage with ordinary loads; same results).  Negative on a null handle. */
+int gvs_extractor_tma_stages(const gvs_extractor* fe);
+
 /* Parity taps (tests only; they stall the stream).  imagePyramid[level] / its blurred clone
  * (src/FeatureExtractor.cpp:512-515), tightly packed w*h bytes. */
 int gvs_debug_level_image(gvs_extractor* fe, int image, int level, int blurred, uint8_t* out);

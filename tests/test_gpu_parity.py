@@ -615,3 +615,28 @@ def test_frame_pipeline_tickets_and_slots():
     with pytest.raises(gvs.GvsError):           # more frames than a slot holds
         pipe.submit(*synth.stereo_batch(w, h, cfg["disparity"], [1, 2, 3]))
     pipe.close()
+
+
+@pytest.mark.parametrize("cfgname", ["euroc", "kitti", "hires", "small"])
+def test_tma_staging_is_active_and_changes_nothing(cfgname, monkeypatch):
+    """The fused pyramid and the FAST kernel stage their tiles with TMA box loads on the BASELINE shapes; the same handles
+    built with the ordinary-load kernels (GVS_NO_FUSED_PYR / GVS_NO_FAST_TMA, read when a handle is created) give
+    byte-identical keys and descriptors."""
+    cfg = synth.CONFIGS[cfgname]
+    w, h = cfg["width"], cfg["height"]
+    n = 3
+    imgs = np.ascontiguousarray(synth.stereo_batch(w, h, cfg["disparity"], range(40, 40 + n))[0])
+    args = dict(nFeatures=cfg["n_features"], nLevels=cfg["n_levels"], width=w, height=h, max_images=n)
+
+    def run():
+        fe = gvs.FeatureExtractor(**args)
+        fe.extract_batch(imgs); fe.sync()
+        off = fe.offsets(n)
+        kp, desc = fe.download(0, n, int(off[n]))
+        return fe.tma_stages(), off.tobytes() + kp.tobytes() + desc.tobytes()
+
+    stages, with_tma = run()
+    assert stages == 3, f"TMA staging not active on {cfgname}: {stages}"
+    monkeypatch.setenv("GVS_NO_FUSED_PYR", "1"); monkeypatch.setenv("GVS_NO_FAST_TMA", "1")
+    stages, without = run()
+    assert stages == 0 and without == with_tma
