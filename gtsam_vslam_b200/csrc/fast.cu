@@ -258,10 +258,13 @@ fast_cells_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Fa
     const int lane = tid & 31, warp = tid >> 5;
     const unsigned ltMask = (1u << lane) - 1u;
     const int nUnits = nW * rows;
-    // Every warp owns a contiguous share of the unit words and private queue regions for it, so that compaction needs no
+    // Every warp owns a share of the unit words (at most `chunk`) and private queue regions for it, so that compaction needs no
     // shared counters or atomics and phase 2b follows 2a without a CTA barrier.
     const int chunk = (((nUnits + kFastWarps - 1) / kFastWarps) + 31) & ~31;
-    const int u0 = min(warp * chunk, nUnits), u1 = min(u0 + chunk, nUnits);
+    // Ownership is interleaved -- warp w takes the 32-unit groups w, w + 8, w + 16, ... -- so that corner-dense parts of the strip are
+    // spread over all warps (the barriers between the phases wait for the slowest warp).
+    const int u0 = warp * 32, u1 = nUnits;
+    constexpr int uStep = kFastWarps * 32;
     unsigned short* q0 = queue + warp * chunk;                 // pair 0 of a unit / phase 3: units with a non-zero score
     unsigned short* q1 = queue + L.queueCap + warp * chunk;    // pair 1 of a unit
     unsigned redo = 0;  // pass 1: bit c = cell c of the strip is redone
@@ -286,7 +289,7 @@ fast_cells_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Fa
         const unsigned kT = (unsigned)max(127 - T, 0) * 0x01010101u;
         auto gt = [&](unsigned d) { return ((d & 0x7f7f7f7fu) + kT) | d; };
         int n0 = 0, n1 = 0;
-        for (int base = u0; base < u1; base += 32) {
+        for (int base = u0; base < u1; base += uStep) {
             const int i = base + lane;
             unsigned f = 0;  // bit 7 of byte b: pixel b of the unit passes the pre-test
             if (i < u1) {
@@ -329,7 +332,7 @@ fast_cells_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Fa
         // ---- 3. strict local maxima inside each cell, four pixels at a time -> per-cell lists.  The warp first compacts the
         // unit words of its share that hold a non-zero score (about a third on textured images) and tests only those.
         int nz = 0;
-        for (int base = u0; base < u1; base += 32) {
+        for (int base = u0; base < u1; base += uStep) {
             const int i = base + lane;
             bool any = false;
             if (i < u1) {
@@ -405,7 +408,7 @@ fast_cells_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Fa
         rec.w1 = (unsigned)(it.iR * lv.nCols + it.iC0 + c) | ((unsigned)rank << 16);
         out[slot] = rec;
     }
-    __syncthreads();   // the next strip reuses the score tile, the masks, the lists and the counters
+    if (idx + 1 < last) __syncthreads();   // the next strip reuses the score tile, the masks, the lists and the counters
     }   // strips of this CTA
 }
 
