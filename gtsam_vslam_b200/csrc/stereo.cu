@@ -16,6 +16,9 @@
 // stereo_finalize: one CTA per frame; bitonic sorts of (depth, idx) and (SAD, idx) give the lowest floor(1%)
 //   depths and the median SAD; both outlier passes are then order independent.
 // Bound: integer pipe / L2 latency; the HBM traffic of this stage is negligible (descriptors + keypoints).
+#include <algorithm>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace gvs {
@@ -35,17 +38,19 @@ __device__ __forceinline__ void patchRow(const uint8_t* p, unsigned& w0, unsigne
 }
 
 __global__ void __launch_bounds__(256)
-stereo_match_kernel(const __grid_constant__ Geometry g, const StereoArgs a) {
+stereo_match_kernel(const __grid_constant__ Geometry g, const StereoArgs a, int auxCap) {
     const int frame = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const int offL = a.offL[frame], nL = a.offL[frame + 1] - offL;
     const int offR = a.offR[frame], nR = a.offR[frame + 1] - offR;
     __shared__ int sLvlStart[kMaxLevels + 1];
+    extern __shared__ uint2 sAux[];   // the frame's right keys: bucket rows [mn, mx] and pt.y (8 B each), scanned once per left key
     if (threadIdx.x == 0) {
         int run = 0;
         for (int l = 0; l < kMaxLevels; l++) { sLvlStart[l] = run; run += l < g.nLevels ? a.keptCntR[frame * kMaxLevels + l] : 0; }
         sLvlStart[kMaxLevels] = run;
     }
+    for (int j = threadIdx.x; j < min(nR, auxCap); j += blockDim.x) sAux[j] = __ldg(a.auxR + offR + j);
     __syncthreads();
     const float maxD = (float)a.fx;
     const int warpsPerGrid = gridDim.x * (blockDim.x >> 5);
@@ -64,7 +69,7 @@ stereo_match_kernel(const __grid_constant__ Geometry g, const StereoArgs a) {
             const int j0 = sLvlStart[max(octL - 1, 0)], j1 = sLvlStart[min(octL + 2, kMaxLevels)];
             unsigned best = 0xffffffffu;
             for (int j = j0 + lane; j < min(j1, nR); j += 32) {
-                const uint2 ar = __ldg(a.auxR + offR + j);  // bucket rows [mn, mx] of this right key, and its pt.y
+                const uint2 ar = j < auxCap ? sAux[j] : __ldg(a.auxR + offR + j);  // bucket rows [mn, mx] of this right key, and its pt.y
                 const int mn = (int)(ar.x & 0xffffu), mx = (int)(ar.x >> 16);
                 if (yKey < mn || yKey > mx) continue;
                 const float yR = __uint_as_float(ar.y);
@@ -220,9 +225,14 @@ stereo_finalize_kernel(const StereoArgs a, int sortCap, unsigned long long* __re
 void launchStereo(const Geometry& g, const StereoArgs& a, int nFrames, int maxKeysPerImage, cudaStream_t s, int* launches) {
     if (nFrames <= 0) return;
     const int warpsPerCta = 8;
-    int gx = (maxKeysPerImage / 2 + 4 * warpsPerCta - 1) / (4 * warpsPerCta);  // ~4 left keys per warp at typical fill
+    static const int keysPerWarp = [] { const char* e = getenv("GVS_STEREO_KEYS"); return e ? std::max(atoi(e), 1) : 8; }();
+    int gx = (maxKeysPerImage / 2 + keysPerWarp * warpsPerCta - 1) / (keysPerWarp * warpsPerCta);  // left keys per warp at typical fill
     if (gx < 1) gx = 1;
-    stereo_match_kernel<<<dim3(gx, nFrames), 32 * warpsPerCta, 0, s>>>(g, a);
+    // every CTA keeps the 8-byte row / y records of the frame's right keys in shared memory (the per-left-key scan runs over them)
+    const int auxCap = std::min(maxKeysPerImage, 5120);   // (40 KB; the records of further keys are read from global memory)
+    static size_t cfgAux[64];
+    ensureDynamicSmem(stereo_match_kernel, (size_t)auxCap * sizeof(uint2), cfgAux);
+    stereo_match_kernel<<<dim3(gx, nFrames), 32 * warpsPerCta, (size_t)auxCap * sizeof(uint2), s>>>(g, a, auxCap);
     ++*launches;
     int n2 = 1;
     while (n2 < maxKeysPerImage) n2 <<= 1;

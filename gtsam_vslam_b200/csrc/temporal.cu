@@ -15,7 +15,7 @@
 //     same rule).  Four are kept so that phase 2 can drop candidates that get matched in the meantime.  Nothing is stored per
 //     candidate: no candidate pool, no capacity to overflow.  Keys that are matched before the call (in-out matchedIdxs) are
 //     skipped here already: entries only change from -1 to >= 0 during a call.
-//   phase 2 (projb_resolve_kernel, one CTA of 32 warps per frame): walks the frame's map points in order, 32 at a time.  A map
+//   phase 2 (projb_resolve_kernel, one warp per frame, lane = map point): walks the frame's map points in order, 32 at a time.  A map
 //     point decides from the first two of its stored candidates that are still free; if fewer than two are left of a list that
 //     was longer than four, its lane walks the window again with the skip test.  The longest prefix of the chunk in which
 //     no map point takes a deciding candidate of a later one is committed; the rest is re-evaluated.  matchedIdxsL/R of the

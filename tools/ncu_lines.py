@@ -12,7 +12,10 @@ for r in rows:
     if not r: continue
     if r[0] == 'Function Name': cur = r[1]; hdr = None; continue
     if r[0] == 'File Path': continue
-    if r[0] == 'Line No': hdr = r; ii = hdr.index('Instructions Executed'); si = hdr.index('# Samples'); continue
+    if r[0] == 'Line No':
+        hdr = r if 'Instructions Executed' in r and '# Samples' in r else None
+        if hdr: ii = hdr.index('Instructions Executed'); si = hdr.index('# Samples')
+        continue
     if hdr is None or cur is None or want not in cur: continue
     if r[0] != '-' and r[0] != '':
         curline = r[0]; agg[curline][2] = r[1].strip()[:120]
