@@ -28,7 +28,6 @@
 //   Pass 0 runs 2a-3 at maxFastThreshold on every cell; pass 1 redoes the cells that listed no key at minFastThreshold.
 // Bound: integer ALU, not HBM: see DESIGN.md.
 #include <algorithm>
-#include <atomic>
 #include <cstdlib>
 #include <cstring>
 
@@ -47,13 +46,14 @@ struct FastSmemLayout {
     int tileWords, tileRows;    // image tile: words per row, rows
     int scoreWords, scoreRows;  // score tile: words per row (1 zero word each side), rows (1 zero row each side)
     int listCap;                // entries per cell list
-    int tileOff, tile2Off, scoreOff, listOff, maskOff, queueOff, queueCap, total;
+    int tileOff, scoreOff, listOff, maskOff, queueOff, queueCap, total;
 };
 
-// tma: the tile is filled by TMA box loads (row pitch a multiple of 16 bytes, buffers 128-byte aligned) into TWO buffers, so that the
-// next strip's tile arrives while the current one is processed
+// tma: the tile is filled by TMA box loads (row pitch a multiple of 16 bytes, buffer 128-byte aligned).  ONE buffer: a second one
+// costs a CTA per SM (measured: 2.11 ms against 1.91 with one), so the next strip's tile is requested when the current strip has
+// read its tile for the last time -- it arrives while the strip finds its local maxima and writes its records
 // maxSW: width in pixels of the widest strip (cells of a strip x cell pitch of its level), maxGW / maxGH: largest cell pitch
-__host__ __device__ inline FastSmemLayout fastLayout(int maxSW, int maxGW, int maxGH, bool tma = false, bool twoTiles = false) {
+__host__ __device__ inline FastSmemLayout fastLayout(int maxSW, int maxGW, int maxGH, bool tma = false) {
     FastSmemLayout L;
     const int maxUnits = (maxSW + 3 + 3) / 4 + 1;  // unit words covering [X0, X1)
     // (a TMA box starts at a 16-byte aligned x -- the copy faults otherwise -- so up to 3 words of lead-in are fetched with the tile)
@@ -66,9 +66,7 @@ __host__ __device__ inline FastSmemLayout fastLayout(int maxSW, int maxGW, int m
     L.listCap = ((maxGW + 1) / 2) * ((maxGH + 1) / 2);
     L.tileOff = 0;
     const int tileBytes = tma ? (L.tileWords * L.tileRows * 4 + 127) & ~127 : L.tileWords * L.tileRows * 4;
-    L.tile2Off = L.tileOff + tileBytes;
-    if (!(tma && twoTiles)) L.tile2Off = L.tileOff;   // one buffer: a CTA that takes a single strip has nothing to prefetch
-    L.scoreOff = L.tile2Off + tileBytes;
+    L.scoreOff = L.tileOff + tileBytes;
     L.maskOff = L.scoreOff + L.scoreWords * L.scoreRows * 4;
     L.listOff = ((L.maskOff + maxUnits * 12 + 15) / 16) * 16;
     L.queueOff = L.listOff + kFastCellsPerItem * L.listCap * 4;
@@ -173,49 +171,46 @@ fast_cells_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Fa
                   int* __restrict__ nCand, unsigned short* __restrict__ cellCnt, int* __restrict__ status) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ int sCnt[kFastCellsPerItem], sBase[kFastCellsPerItem];
-    __shared__ __align__(8) unsigned long long sBar[2];
+    __shared__ __align__(8) unsigned long long sBar;
 
     const int img = blockIdx.y;
-    const FastSmemLayout L = fastLayout(maxSW, maxGW, maxGH, USE_TMA, itemsPerCta > 1);
+    const FastSmemLayout L = fastLayout(maxSW, maxGW, maxGH, USE_TMA);
     unsigned* score = reinterpret_cast<unsigned*>(smem + L.scoreOff);
     unsigned* masks = reinterpret_cast<unsigned*>(smem + L.maskOff);  // per unit: in-range, has-left, has-right byte masks
     unsigned* lists = reinterpret_cast<unsigned*>(smem + L.listOff);
     const int tid = threadIdx.x;
     const int first = blockIdx.x * itemsPerCta, last = min(first + itemsPerCta, nItems);
-    // one TMA box load of the tile of strip `idx` into buffer `buf` (x from xu - 4, y from y0 - 3); issued by thread 0
-    auto issue = [&](int idx, int buf) {
+    // one TMA box load of the tile of strip `idx` (x from xu - 4, y from y0 - 3); issued by thread 0
+    auto issue = [&](int idx) {
         const FastStrip n = fastStrip(g, items[idx]);
         if (n.rows <= 0 || n.cols <= 0) return;
-        const unsigned bar = smemAddr(&sBar[buf]);
+        const unsigned bar = smemAddr(&sBar);
         mbarExpectTx(bar, (unsigned)(L.tileWords * 4 * L.tileRows));
-        const unsigned dst = smemAddr(smem + (buf ? L.tile2Off : L.tileOff));
         // the maps have 32-bit elements (a box may be 256 of them wide); x must be a multiple of 16 bytes (tools/tma_probe.cu), so
         // the box starts up to 3 words left of the strip's tile
-        tmaLoadTile3d(dst, &maps.m[n.level], ((n.xu - 4) & ~15) >> 2, n.y0 - 3, img, bar);
+        tmaLoadTile3d(smemAddr(smem + L.tileOff), &maps.m[n.level], ((n.xu - 4) & ~15) >> 2, n.y0 - 3, img, bar);
     };
     if (USE_TMA) {
         if (tid == 0) {
-            mbarInit(smemAddr(&sBar[0]), 1);
-            mbarInit(smemAddr(&sBar[1]), 1);
-            if (first < last) issue(first, 0);
+            mbarInit(smemAddr(&sBar), 1);
+            if (first < last) issue(first);
         }
-        __syncthreads();   // (the barriers are initialised before anybody polls them)
+        __syncthreads();   // (the barrier is initialised before anybody polls it)
     }
-    unsigned used0 = 0, used1 = 0;   // loads consumed per buffer (their mbarrier phase)
+    unsigned used = 0;   // tile loads consumed so far (the mbarrier's phase)
     for (int idx = first; idx < last; idx++) {
-    const int buf = USE_TMA ? (idx - first) & 1 : 0;
     const FastItem it = items[idx];
     const LevelGeom& lv = g.lv[it.level];
     const FastStrip S = fastStrip(g, it);
     const int y0 = S.y0, X0 = S.X0, rows = S.rows, cols = S.cols, gW = S.gW, xu = S.xu, nW = S.nW;
-    if (USE_TMA && tid == 0 && idx + 1 < last) issue(idx + 1, buf ^ 1);   // (buffer buf^1 was last read by strip idx-1, which ended with a CTA barrier)
     if (tid < kFastCellsPerItem) sCnt[tid] = 0;
     if (rows <= 0 || cols <= 0) {  // empty strip: still publish zero counts for its cells
         if (tid < it.nC) cellCnt[(size_t)img * g.cellsPerImage + lv.cellBase + it.iR * lv.nCols + it.iC0 + tid] = 0;
+        if (USE_TMA && tid == 0 && idx + 1 < last) issue(idx + 1);   // (nothing of this strip is in the tile buffer)
         __syncthreads();
         continue;
     }
-    unsigned* tile = reinterpret_cast<unsigned*>(smem + (buf ? L.tile2Off : L.tileOff)) + (USE_TMA ? ((xu - 4) & 15) >> 2 : 0);
+    unsigned* tile = reinterpret_cast<unsigned*>(smem + L.tileOff) + (USE_TMA ? ((xu - 4) & 15) >> 2 : 0);
     const int tw = nW + 2, th = rows + 6;   // tile words per row / rows
     // i / d = umulhi(i, 2^32 / d + 1) for the small i used here (d >= 2)
     const unsigned magicT = 0xffffffffu / (unsigned)tw + 1u, magicU = 0xffffffffu / (unsigned)nW + 1u;
@@ -244,8 +239,8 @@ fast_cells_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Fa
         masks[3 * j] = inr; masks[3 * j + 1] = hasL; masks[3 * j + 2] = hasR;
     }
     if (USE_TMA) {   // one thread polls the tile's mbarrier (a polling warp takes issue slots from the CTAs that compute); the CTA
-        if (tid == 0) mbarWait(smemAddr(&sBar[buf]), (buf ? used1 : used0) & 1u);   // barrier below passes the arrival on
-        if (buf) used1++; else used0++;
+        if (tid == 0) mbarWait(smemAddr(&sBar), used & 1u);   // barrier below passes the arrival on
+        used++;
     }
     __syncthreads();
 
@@ -376,6 +371,9 @@ fast_cells_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Fa
         for (int c = 0; c < it.nC; c++) redo |= (sCnt[c] == 0 ? 1u : 0u) << c;   // same value in every thread
         if (!redo) break;
     }
+    // the tile has been read for the last time (every warp is past its exact scores): request the next strip's tile into the same
+    // buffer; it arrives while this strip writes its records
+    if (USE_TMA && tid == 0 && idx + 1 < last) issue(idx + 1);
 
     // ---- 4. reserve, rank inside the cell (row-major), write: every listed key is emitted (the lists already hold exactly the
     // keys of the threshold that applies to their cell)
@@ -428,7 +426,7 @@ static FastDims fastDims(const Geometry& g) {
 
 bool fastTmaBox(const Geometry& g, int* boxWords, int* boxH) {
     const FastDims d = fastDims(g);
-    const FastSmemLayout L = fastLayout(d.maxSW, d.maxGW, d.maxGH, true, true);
+    const FastSmemLayout L = fastLayout(d.maxSW, d.maxGW, d.maxGH, true);
     *boxWords = L.tileWords; *boxH = L.tileRows;
     return *boxWords <= 256 && *boxH <= 256 && L.total <= 200 * 1024;
 }
@@ -439,18 +437,14 @@ void launchFast(const Geometry& g, const uint8_t* slab, const FastItem* items, i
     cudaMemsetAsync(nCand, 0, sizeof(int) * (size_t)nImages * kMaxLevels, s);
     if (nItems <= 0) return;
     static size_t cfgA[64], cfgB[64];
+    // strips per CTA (a CTA that takes several requests the next strip's tile while it writes the current strip's records).  Measured
+    // on 256 EuRoC frames: 1 strip 1.89 ms, 2: 1.90, 3: 1.92, 4: 1.92, 8: 1.98 -- many short CTAs schedule better than few long
+    // ones and four CTAs per SM already hide the tile latency, so the default is 1
     static const int perCta = [] { const char* e = getenv("GVS_FAST_ITEMS"); const int v = e ? atoi(e) : 1; return std::min(std::max(v, 1), 64); }();
     FastMaps pm{};
     if (levelMaps) {
-        const FastSmemLayout L = fastLayout(d.maxSW, d.maxGW, d.maxGH, true, perCta > 1);
+        const FastSmemLayout L = fastLayout(d.maxSW, d.maxGW, d.maxGH, true);
         memcpy(pm.m, levelMaps, sizeof(CUtensorMap) * (size_t)g.nLevels);
-        int dv = 0;
-        cudaGetDevice(&dv);
-        static std::atomic<bool> carved[64];
-        if (!carved[dv & 63].exchange(true))   // (first launch on this device)
-            // two tile buffers per CTA: ask for the largest shared-memory carve-out so that as many CTAs fit as with one buffer
-            // (the kernel reads global memory through TMA only, it has no use for L1)
-            cudaFuncSetAttribute(fast_cells_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         ensureDynamicSmem(fast_cells_kernel<true>, (size_t)L.total, cfgA);
         fast_cells_kernel<true><<<dim3((nItems + perCta - 1) / perCta, nImages), 256, L.total, s>>>(g, pm, slab, items, nItems, perCta, d.maxSW, d.maxGW, d.maxGH, recs,
                                                                                                  nCand, cellCnt, status);
