@@ -226,6 +226,8 @@ struct ProjArgs {
     int* nMatches;
     int* status;
 };
+// stored candidate lists (wide search windows): one argument block per frame, in device memory and on the host
+void launchProjectWide(const ProjArgs* frames, const ProjArgs* hostFrames, int nFrames, cudaStream_t s, int* launches);
 void launchProjectLBA(const ProjArgs& a, const float* lastL, const float* lastR, int* out, cudaStream_t s, int* launches);
 void launchMedianDescriptor(const uint8_t* descs, const int* offsets, int P, int* bestIdx, cudaStream_t s, int* launches);
 void launchWorldToFrame(int M, const double* poseInv, double fx, double fy, double cx, double cy, int width, int height,

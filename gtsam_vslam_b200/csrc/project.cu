@@ -5,6 +5,8 @@
 //     findOutliersR / findOutliersMono (src/FeatureTracker.cpp:582-1013), FeatureMatcher::DescriptorDistance (:710-726).
 // The batched projection matchers against the device-resident frames (matchByProjectionRPred / Mono / matchByRadius) live in
 // temporal.cu.
+#include <algorithm>
+
 #include "common.cuh"
 #include "mappoint_math.cuh"
 
@@ -58,8 +60,7 @@ __device__ void reduceList(const unsigned* list, int len, const int* matched, in
     eSuf = ks == kNone ? kNone : list[ks & 0xfffff];
 }
 
-__global__ void __launch_bounds__(256)
-proj_candidates_kernel(const ProjArgs a, ProjRec* __restrict__ recs) {
+__device__ __forceinline__ void projCandidatesBody(const ProjArgs& a, ProjRec* __restrict__ recs) {
     const int lane = threadIdx.x & 31;
     const int nSides = (a.mode == GVS_MATCH_STEREO_PRED || a.mode == kModeLBA) ? 2 : 1;
     const int warpsPerGrid = gridDim.x * (blockDim.x >> 5);
@@ -148,6 +149,16 @@ proj_candidates_kernel(const ProjArgs a, ProjRec* __restrict__ recs) {
     }
 }
 
+__global__ void __launch_bounds__(256)
+proj_candidates_kernel(const ProjArgs a, ProjRec* __restrict__ recs) { projCandidatesBody(a, recs); }
+// one grid row per frame, the frames' arguments in device memory
+__global__ void __launch_bounds__(256)
+proj_candidates_frames_kernel(const ProjArgs* __restrict__ frames) {
+    const ProjArgs& a = frames[blockIdx.y];
+    if ((int)blockIdx.x * 8 >= 2 * a.M) return;
+    projCandidatesBody(a, reinterpret_cast<ProjRec*>(a.recs));
+}
+
 struct Decision { int bestDist, bestIdx, bestLev, bestLev2, secDist; };
 __device__ __forceinline__ Decision decide(unsigned eBest, unsigned ePre, unsigned eSuf) {
     Decision d{256, -1, -1, -1, 256};
@@ -156,6 +167,168 @@ __device__ __forceinline__ Decision decide(unsigned eBest, unsigned ePre, unsign
     if (ePre != kNone) { d.secDist = candDist(ePre); d.bestLev2 = candLev(ePre); }
     if (eSuf != kNone && candDist(eSuf) < d.secDist) { d.secDist = candDist(eSuf); d.bestLev2 = candLev(eSuf); }
     return d;
+}
+
+// Wide windows (gvs_match_projection_batch with a search radius that covers a large part of the image: hundreds of candidates per
+// map point): the candidate lists are stored (proj_candidates_kernel above) and phase 2 works on the stored lists.
+// phase 2.  The reference walks the map points in index order; map point i only depends on an earlier one j if j takes a key
+// that is one of i's (at most six) deciding candidates.  A CTA of 32 warps handles 32 map points at a time: every warp
+// computes the tentative decision of its map point against the current matched arrays (rescanning its stored list when a
+// deciding candidate is already taken), then warp 0 finds the longest prefix of the chunk in which no map point is affected by
+// an earlier one of the same chunk, commits it, and the rest is re-evaluated.  The first pending map point is always safe,
+// so every round makes progress; without conflicts a chunk costs one round.
+constexpr int kResolveWarps = 32;
+
+__global__ void __launch_bounds__(32 * kResolveWarps)
+proj_resolve_frames_kernel(const ProjArgs* __restrict__ frames) {
+    const ProjArgs& a = frames[blockIdx.x];
+    const ProjRec* __restrict__ recs = reinterpret_cast<const ProjRec*>(a.recs);
+    extern __shared__ int sMatched[];  // NL + NR
+    __shared__ int sDec[kResolveWarps][6];                     // key ids of the deciding candidates (left 0..2, right 3..5), -1 = none
+    __shared__ int sTakeL[kResolveWarps], sTakeR[kResolveWarps];   // keys the map point marks if accepted (-1 = none)
+    __shared__ int sOut0[kResolveWarps], sOut1[kResolveWarps];     // its matchesIdxs pair
+    __shared__ int sAccept[kResolveWarps];
+    __shared__ int sDone, sTotal;
+    int* mL = sMatched;
+    int* mR = sMatched + a.NL;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool stereo = a.mode == GVS_MATCH_STEREO_PRED;
+    for (int i = tid; i < a.NL; i += blockDim.x) mL[i] = a.matchedL[i];
+    if (stereo) for (int i = tid; i < a.NR; i += blockDim.x) mR[i] = a.matchedR[i];
+    if (tid == 0) sTotal = 0;
+    const int nSides = stereo ? 2 : 1;
+    auto taken = [&](unsigned e, const int* m) { return e != kNone && m[candIdx(e)] >= 0; };
+    auto keyOf = [&](unsigned e) { return e == kNone ? -1 : candIdx(e); };
+    for (int base = 0; base < a.M; base += kResolveWarps) {
+        const int chunk = min(kResolveWarps, a.M - base);
+        __syncthreads();
+        if (tid == 0) sDone = 0;
+        bool first = true;
+        while (true) {
+            __syncthreads();
+            const int done = sDone;
+            if (done >= chunk) break;
+            // ---- (A) tentative decisions of the pending map points whose inputs changed
+            if (warp >= done && warp < chunk) {
+                bool redo = first;
+                if (!first) {
+#pragma unroll
+                    for (int q = 0; q < 6; q++) {
+                        const int kq = sDec[warp][q];
+                        if (kq >= 0 && (q < 3 ? mL[kq] : mR[kq]) >= 0) redo = true;
+                    }
+                }
+                if (redo) {
+                    const int mp = base + warp;
+                    const bool skipMP = a.mode != GVS_MATCH_RADIUS && (a.matches[2 * mp] >= 0 || a.matches[2 * mp + 1] >= 0);
+                    int accept = 0, takeL = -1, takeR = -1, out0 = -1, out1 = -1;
+                    unsigned eb = kNone, ep = kNone, es = kNone, rb = kNone, rp = kNone, rs = kNone;
+                    if (!skipMP) {
+                        const ProjRec rl = recs[mp * nSides];
+                        eb = rl.eBest; ep = rl.ePre; es = rl.eSuf;
+                        if (taken(eb, mL) || taken(ep, mL) || taken(es, mL)) reduceList(a.candL + rl.start, rl.len, mL, lane, eb, ep, es);
+                        Decision d = decide(eb, ep, es);
+                        bool right = false;
+                        int bestIdxR = -1;
+                        if (stereo) {
+                            const ProjRec rr = recs[mp * nSides + 1];
+                            rb = rr.eBest; rp = rr.ePre; rs = rr.eSuf;
+                            if (taken(rb, mR) || taken(rp, mR) || taken(rs, mR)) reduceList(a.candR + rr.start, rr.len, mR, lane, rb, rp, rs);
+                            const Decision dr = decide(rb, rp, rs);
+                            bestIdxR = dr.bestIdx;
+                            if (d.bestDist > dr.bestDist) {
+                                d.bestDist = dr.bestDist; d.secDist = dr.secDist; d.bestLev = dr.bestLev; d.bestLev2 = dr.bestLev2;
+                                right = true;
+                            }
+                        }
+                        bool ok;
+                        if (a.mode == GVS_MATCH_MONO) {
+                            // (ratioProj + 0.1) * secDist is evaluated in double (float + double), threshold 100 + 50
+                            const double thr = ((double)0.8f + 0.1) * (double)d.secDist;
+                            ok = d.bestDist <= 150 && !(d.bestLev == d.bestLev2 && (double)d.bestDist >= thr) &&
+                                 (d.bestLev != d.bestLev2 || (double)d.bestDist < thr);
+                        } else {
+                            const float thr = __fmul_rn(0.8f, (float)d.secDist);
+                            ok = d.bestDist <= 100 && !(d.bestLev == d.bestLev2 && (float)d.bestDist >= thr) &&
+                                 (d.bestLev != d.bestLev2 || (float)d.bestDist < thr);
+                        }
+                        if (ok) {
+                            accept = 1;
+                            if (!stereo) { takeL = d.bestIdx; out0 = d.bestIdx; }
+                            else if (right) {
+                                takeR = bestIdxR; out1 = bestIdxR;
+                                const int li = a.leftIdxs[bestIdxR];
+                                if (li >= 0) { out0 = li; takeL = li; }
+                            } else {
+                                takeL = d.bestIdx; out0 = d.bestIdx;
+                                const int ri = a.rightIdxs[d.bestIdx];
+                                if (ri >= 0) { out1 = ri; takeR = ri; }
+                            }
+                        }
+                    }
+                    if (lane == 0) {
+                        sDec[warp][0] = keyOf(eb); sDec[warp][1] = keyOf(ep); sDec[warp][2] = keyOf(es);
+                        sDec[warp][3] = keyOf(rb); sDec[warp][4] = keyOf(rp); sDec[warp][5] = keyOf(rs);
+                        sAccept[warp] = accept; sTakeL[warp] = takeL; sTakeR[warp] = takeR; sOut0[warp] = out0; sOut1[warp] = out1;
+                    }
+                }
+            }
+            first = false;
+            __syncthreads();
+            // ---- (B) warp 0, lane = map point of the chunk: longest safe prefix, commit
+            if (warp == 0) {
+                bool unsafe = false;
+                int dl0 = -1, dl1 = -1, dl2 = -1, dr0 = -1, dr1 = -1, dr2 = -1;
+                if (lane < chunk) { dl0 = sDec[lane][0]; dl1 = sDec[lane][1]; dl2 = sDec[lane][2]; dr0 = sDec[lane][3]; dr1 = sDec[lane][4]; dr2 = sDec[lane][5]; }
+                for (int j = done; j < chunk - 1; j++) {
+                    if (!sAccept[j]) continue;   // (uniform)
+                    const int tl = sTakeL[j], tr = sTakeR[j];
+                    if (lane > j && lane < chunk) {
+                        if (tl >= 0 && (tl == dl0 || tl == dl1 || tl == dl2)) unsafe = true;
+                        if (tr >= 0 && (tr == dr0 || tr == dr1 || tr == dr2)) unsafe = true;
+                    }
+                }
+                const unsigned um = __ballot_sync(0xffffffffu, unsafe);
+                const int upto = um ? __ffs(um) - 1 : chunk;     // lanes [done, upto) are final
+                const bool mine = lane >= done && lane < upto && sAccept[lane];
+                const int i = base + lane;
+                // several committed map points may mark the same key (a stereo partner): the last one in index order wins
+                const int tl = mine ? sTakeL[lane] : -1, tr = mine ? sTakeR[lane] : -1;
+                const unsigned pl = __match_any_sync(0xffffffffu, tl >= 0 ? tl : -1 - lane);
+                const unsigned pr = __match_any_sync(0xffffffffu, tr >= 0 ? tr : -1 - lane);
+                if (tl >= 0 && (31 - __clz(pl)) == lane) mL[tl] = i;
+                if (tr >= 0 && (31 - __clz(pr)) == lane) mR[tr] = i;
+                if (mine) {
+                    if (a.mode != GVS_MATCH_STEREO_PRED) a.matches[2 * i] = sOut0[lane];
+                    else {
+                        if (sOut0[lane] >= 0) a.matches[2 * i] = sOut0[lane];
+                        if (sOut1[lane] >= 0) a.matches[2 * i + 1] = sOut1[lane];
+                    }
+                }
+                const int nAcc = __popc(__ballot_sync(0xffffffffu, mine));
+                if (lane == 0) { sTotal += nAcc; sDone = upto; }
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < a.NL; i += blockDim.x) a.matchedL[i] = mL[i];
+    if (stereo) for (int i = tid; i < a.NR; i += blockDim.x) a.matchedR[i] = mR[i];
+    if (tid == 0) *a.nMatches = sTotal;
+}
+
+// frames: nFrames argument blocks in device memory (host copy in hostFrames for the launch geometry); every frame has its own
+// pool counters (poolTop), pool regions (candL / candR / candCap), recs and nMatches
+void launchProjectWide(const ProjArgs* frames, const ProjArgs* hostFrames, int nFrames, cudaStream_t s, int* launches) {
+    int maxM = 0, maxKeys = 0;
+    for (int f = 0; f < nFrames; f++) { maxM = std::max(maxM, hostFrames[f].M); maxKeys = std::max(maxKeys, hostFrames[f].NL + hostFrames[f].NR); }
+    if (maxM <= 0) return;
+    proj_candidates_frames_kernel<<<dim3((2 * maxM + 7) / 8, nFrames), 256, 0, s>>>(frames);
+    ++*launches;
+    const size_t sm = (size_t)maxKeys * sizeof(int);
+    static size_t cfg[64];
+    ensureDynamicSmem(proj_resolve_frames_kernel, sm + 4096, cfg);   // (+ the kernel's static shared memory counts against the 48 KB default)
+    proj_resolve_frames_kernel<<<nFrames, 32 * kResolveWarps, sm, s>>>(frames);
+    ++*launches;
 }
 
 // FeatureMatcher::matchByProjectionRPredLBA decision (src/FeatureMatcher.cpp:191-249), one thread per candidate point.

@@ -21,7 +21,9 @@
 //     no map point takes a deciding candidate of a later one is committed; the rest is re-evaluated.  matchedIdxsL/R of the
 //     frame live in shared memory during the walk.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "handles.cuh"
 #include "mappoint_math.cuh"
@@ -272,7 +274,7 @@ __device__ __forceinline__ bool tFirstTwo(const TRec& r, const int* matched, uns
 // by the whole warp.  The walk is serial per frame (that is the reference's semantics), frames run in parallel.
 __global__ void __launch_bounds__(32)
 projb_resolve_kernel(const ProjBatchArgs a) {
-    extern __shared__ int sMatched[];  // capL + capR
+    extern __shared__ int sMatched[];  // 2 x (capL + capR)
     const int f = blockIdx.x, frame = a.frame0 + f;
     const int lane = threadIdx.x;
     const bool stereo = a.mode == GVS_MATCH_STEREO_PRED;
@@ -283,30 +285,43 @@ projb_resolve_kernel(const ProjBatchArgs a) {
     if (NL > a.capL || NR > a.capR) { if (lane == 0) { atomicOr(a.status, kStatOutputOverflow); a.nMatches[f] = 0; } return; }
     int* mL = sMatched;
     int* mR = sMatched + a.capL;
+    int* tL = sMatched + a.capL + a.capR;   // per key: the first lane of the current round that wants to mark it (kNoLane = nobody)
+    int* tR = tL + a.capL;
+    constexpr int kNoLane = 0x7fffffff;
     int* gML = a.matchedL + (oL - a.offL[a.frame0]);
     int* gMR = stereo ? a.matchedR + (oR - a.offR[a.frame0]) : nullptr;
-    for (int i = lane; i < NL; i += 32) mL[i] = gML[i];
-    for (int i = lane; i < NR; i += 32) mR[i] = gMR[i];
+    for (int i = lane; i < NL; i += 32) { mL[i] = gML[i]; tL[i] = kNoLane; }
+    for (int i = lane; i < NR; i += 32) { mR[i] = gMR[i]; tR[i] = kNoLane; }
     __syncwarp();
     const int* leftIdxs = stereo ? a.leftIdxs + oR : nullptr;
     const int* rightIdxs = stereo ? a.rightIdxs + oL : nullptr;
     const bool radiusMode = a.mode == GVS_MATCH_RADIUS;
     auto keyOf = [&](unsigned e) { return e == kNoCand ? -1 : tIdx(e); };
     int total = 0;
-    for (int base = 0; base < M; base += 32) {
-        const int chunk = min(32, M - base);
-        const int mpi = mp0 + base + lane;
-        TRec rl, rr;
+    // the records of a chunk are requested one chunk ahead: the walk is a serial chain per frame and a chunk is only a few hundred
+    // cycles of work, less than one trip to L2
+    auto loadChunk = [&](int base, TRec& rl, TRec& rr, bool& skipMP) {
 #pragma unroll
         for (int i = 0; i < kTopK; i++) { rl.e[i] = kNoCand; rr.e[i] = kNoCand; }
         rl.n = 0; rr.n = 0;
-        bool skipMP = true;
-        if (lane < chunk) {
+        skipMP = true;
+        if (base + lane < M) {
+            const int mpi = mp0 + base + lane;
             // a map point that is matched already is skipped by the walk (:262,:399); matchByRadius has no such test
             skipMP = !radiusMode && (a.matches[2 * (size_t)mpi] >= 0 || a.matches[2 * (size_t)mpi + 1] >= 0);
             rl = a.recs[2 * (size_t)mpi];
             if (stereo) rr = a.recs[2 * (size_t)mpi + 1];
         }
+    };
+    TRec nrl, nrr;
+    bool nskip;
+    loadChunk(0, nrl, nrr, nskip);
+    for (int base = 0; base < M; base += 32) {
+        const int chunk = min(32, M - base);
+        const int mpi = mp0 + base + lane;
+        TRec rl = nrl, rr = nrr;
+        const bool skipMP = nskip;
+        loadChunk(base + 32, nrl, nrr, nskip);   // (matches[] of a later chunk is not written by this one: every lane writes its own map point)
         int done = 0;
         while (done < chunk) {
             const bool pend = lane >= done && lane < chunk && !skipMP;
@@ -365,18 +380,25 @@ projb_resolve_kernel(const ProjBatchArgs a) {
                     }
                 }
             }
-            // ---- (B) longest prefix of the pending lanes in which nobody takes a deciding candidate of a later lane
+            // ---- (B) longest prefix of the pending lanes in which nobody takes a deciding candidate of a later lane: every accepting
+            // lane leaves its lane number on the keys it would mark (minimum wins), every pending lane looks at its deciding keys
             const int dl0 = keyOf(l1), dl1 = keyOf(l2), dr0 = keyOf(r1), dr1 = keyOf(r2);
+            if (accept) {
+                if (takeL >= 0) atomicMin(&tL[takeL], lane);
+                if (takeR >= 0) atomicMin(&tR[takeR], lane);
+            }
+            __syncwarp();
             bool unsafe = false;
-            unsigned accMask = __ballot_sync(0xffffffffu, accept != 0);
-            accMask &= ~0u << done;
-            for (unsigned am = accMask; am; am &= am - 1) {
-                const int j = __ffs(am) - 1;
-                const int tl = __shfl_sync(0xffffffffu, takeL, j), tr = __shfl_sync(0xffffffffu, takeR, j);
-                if (lane > j && pend) {
-                    if (tl >= 0 && (tl == dl0 || tl == dl1)) unsafe = true;
-                    if (tr >= 0 && (tr == dr0 || tr == dr1)) unsafe = true;
-                }
+            if (pend) {
+                if (dl0 >= 0 && tL[dl0] < lane) unsafe = true;
+                if (dl1 >= 0 && tL[dl1] < lane) unsafe = true;
+                if (dr0 >= 0 && tR[dr0] < lane) unsafe = true;
+                if (dr1 >= 0 && tR[dr1] < lane) unsafe = true;
+            }
+            __syncwarp();
+            if (accept) {
+                if (takeL >= 0) tL[takeL] = kNoLane;
+                if (takeR >= 0) tR[takeR] = kNoLane;
             }
             const unsigned um = __ballot_sync(0xffffffffu, unsafe);
             const int upto = um ? __ffs(um) - 1 : chunk;     // lanes [done, upto) are final
@@ -421,7 +443,7 @@ static void launchProjectBatch(const ProjBatchArgs& a, int maxMpPerFrame, cudaSt
         projb_candidates_kernel<false><<<dim3(nSlices, a.nFrames, nSides), kCandThreads, 0, s>>>(a, capKeys);
     }
     ++*launches;
-    const size_t sm = (size_t)(a.capL + a.capR) * sizeof(int);
+    const size_t sm = 2 * (size_t)(a.capL + a.capR) * sizeof(int);   // matched flags + the round's tentative marks
     ensureDynamicSmem(projb_resolve_kernel, sm, cfgB);
     projb_resolve_kernel<<<a.nFrames, 32, sm, s>>>(a);
     ++*launches;
@@ -646,8 +668,44 @@ int gvs_match_projection_batch(gvs_matcher* m, int first_frame, int n_frames, in
                  oLR = take((size_t)M * 4), oIF = take(M), oIR = take(M), oML = take((size_t)NL * 4), oMR = take((size_t)NR * 4),
                  oMt = take((size_t)M * 8), oRec = take((size_t)M * 2 * sizeof(TRec)), oOff = take((size_t)(n_frames + 1) * 4),
                  oCnt = take((size_t)n_frames * 4), oSt = take(16);
+    // A search radius that covers a large part of the image (matchByProjectionMono with rad 1200, BASELINE config 4: hundreds of
+    // candidates per map point and most keys contested) goes to the stored-list kernels of project.cu: a thread per window and a
+    // re-enumeration per conflict (temporal.cu) are built for the tracking radii, where a window holds a few dozen keys.
+    bool wide = false;
+    size_t poolNeed = 0;
+    {
+        const float r = rad * m->L->scale[std::min(2, m->L->g.nLevels - 1)];
+        const float wx = std::min((float)m->xGrids, 2.f * r * m->xMult + 2.f), wy = std::min((float)m->yGrids, 2.f * r * m->yMult + 2.f);
+        const float keysPerFrame = (float)NL / (float)n_frames;
+        wide = keysPerFrame * 0.5f * (wx * wy) / ((float)m->xGrids * (float)m->yGrids) > 128.f;
+        // a handful of frames (the per-frame call of the tracking thread): the stored-list resolve spends 32 warps on a frame where
+        // the other spends one -- measured on one EuRoC frame, 1937 map points, rad 10: 0.53 ms against 0.91 ms host to host
+        if (n_frames <= 4) wide = true;
+        if (const char* e = getenv("GVS_PROJ_WIDE")) wide = atoi(e) != 0;   // (tests drive both paths)
+        if (wide)
+            for (int f = 0; f < n_frames; f++) {
+                const int frame = first_frame + f;
+                const int nl = m->L->hOff[frame + 1] - m->L->hOff[frame], nr = two ? m->R->hOff[frame + 1] - m->R->hOff[frame] : 0;
+                poolNeed += 2 * (size_t)(mp_offsets[f + 1] - mp_offsets[f]) * (size_t)std::max(std::max(nl, nr), 1);
+            }
+        if (poolNeed > ((size_t)1 << 30)) { wide = false; poolNeed = 0; }   // (4 GB of lists: take the other path)
+    }
+    const size_t oFr = take(wide ? (size_t)n_frames * sizeof(ProjArgs) : 4), oPT = take(wide ? (size_t)n_frames * 8 : 4);
     rc = growScratch(m, o);
     if (rc) return rc;
+    if (wide) {
+        for (int i = 0; i < M; i++) {
+            const int l = mps->scale_level_l[i];
+            if (l < 0 || l >= m->L->g.nLevels || (two && (mps->scale_level_r[i] < 0 || mps->scale_level_r[i] >= m->L->g.nLevels)))
+                return fail(GVS_ERR_INVALID, "map point scale level out of range");
+        }
+        if (poolNeed > (size_t)m->poolCap * 2) {
+            GVS_CUDA_OK(cudaStreamSynchronize(s));
+            devFree(m->pool); m->pool = nullptr; m->poolCap = 0;
+            GVS_CUDA_OK(devAlloc(&m->pool, poolNeed));
+            m->poolCap = (int)(poolNeed / 2);
+        }
+    }
     uint8_t* b = m->pj;
     auto up = [&](size_t off, const void* src, size_t bytes) -> cudaError_t {
         return (src && bytes) ? cudaMemcpyAsync(b + off, src, bytes, cudaMemcpyHostToDevice, s) : cudaSuccess;
@@ -677,7 +735,42 @@ int gvs_match_projection_batch(gvs_matcher* m, int first_frame, int n_frames, in
     a.matchedL = reinterpret_cast<int*>(b + oML); a.matchedR = reinterpret_cast<int*>(b + oMR);
     a.matches = reinterpret_cast<int*>(b + oMt); a.nMatches = reinterpret_cast<int*>(b + oCnt); a.status = reinterpret_cast<int*>(b + oSt);
     int launches = 0;
-    launchProjectBatch(a, maxMp, s, &launches);
+    if (wide) {
+        // stored candidate lists (project.cu): one argument block per frame; pool regions of M_f x max(NL_f, NR_f) entries per side
+        static_assert(sizeof(TRec) == 20, "the stored-list records of project.cu (ProjRec, 20 bytes) reuse the TRec scratch region");
+        std::vector<ProjArgs> fr((size_t)n_frames);
+        size_t poolAt = 0;
+        for (int f = 0; f < n_frames; f++) {
+            const int frame = first_frame + f, mp0 = mp_offsets[f], Mf = mp_offsets[f + 1] - mp0;
+            const int fl = m->L->hOff[frame], nl = m->L->hOff[frame + 1] - fl;
+            const int fr0 = two ? m->R->hOff[frame] : 0, nr = two ? m->R->hOff[frame + 1] - fr0 : 0;
+            ProjArgs& q = fr[(size_t)f];
+            q = ProjArgs{};
+            q.mode = mode; q.M = Mf;
+            q.mpDesc = b + oDesc + (size_t)mp0 * 32; q.predL = a.predL + 2 * (size_t)mp0; q.predR = a.predR + 2 * (size_t)mp0;
+            q.lvlL = a.lvlL + mp0; q.lvlR = a.lvlR + mp0;
+            q.inFrame = a.inFrame ? a.inFrame + mp0 : nullptr; q.inFrameR = a.inFrameR ? a.inFrameR + mp0 : nullptr;
+            q.kpL = m->L->kps + fl; q.descL = m->L->desc + (size_t)fl * 32; q.NL = nl;
+            q.kpR = two ? m->R->kps + fr0 : nullptr; q.descR = two ? m->R->desc + (size_t)fr0 * 32 : nullptr; q.NR = nr;
+            q.cellStartL = m->cellStartL + (size_t)frame * (m->maxCells + 1); q.itemsL = m->itemsL + fl;
+            q.cellStartR = two ? m->cellStartR + (size_t)frame * (m->maxCells + 1) : nullptr; q.itemsR = two ? m->itemsR + fr0 : nullptr;
+            q.leftIdxs = two ? m->leftIdxs + fr0 : nullptr; q.rightIdxs = two ? m->rightIdxs + fl : nullptr;
+            q.xGrids = a.xGrids; q.yGrids = a.yGrids; q.xMult = a.xMult; q.yMult = a.yMult; q.rad = rad;
+            for (int i = 0; i < kMaxLevels; i++) q.scalePyramid[i] = a.scalePyramid[i];
+            q.recs = b + oRec + (size_t)mp0 * 2 * sizeof(TRec);
+            q.poolTop = reinterpret_cast<int*>(b + oPT) + 2 * f;
+            const size_t cap = (size_t)Mf * (size_t)std::max(std::max(nl, nr), 1);
+            q.candL = m->pool + poolAt; q.candR = m->pool + poolAt + cap; q.candCap = (int)cap;
+            poolAt += 2 * cap;
+            q.matchedL = a.matchedL + (fl - oL); q.matchedR = two ? a.matchedR + (fr0 - oR) : nullptr;
+            q.matches = a.matches + 2 * (size_t)mp0; q.nMatches = a.nMatches + f; q.status = a.status + 2;
+        }
+        GVS_CUDA_OK(cudaMemcpyAsync(b + oFr, fr.data(), fr.size() * sizeof(ProjArgs), cudaMemcpyHostToDevice, s));   // (pageable: staged before the call returns)
+        GVS_CUDA_OK(cudaMemsetAsync(b + oPT, 0, (size_t)n_frames * 8, s));
+        launchProjectWide(reinterpret_cast<const ProjArgs*>(b + oFr), fr.data(), n_frames, s, &launches);
+    } else {
+        launchProjectBatch(a, maxMp, s, &launches);
+    }
     m->launchesTotal += launches;
     int st = 0;
     GVS_CUDA_OK(cudaMemcpyAsync(matched_l, b + oML, (size_t)NL * 4, cudaMemcpyDeviceToHost, s));

@@ -61,10 +61,15 @@ def _synthetic_mappoints(rng, kprev, shift, noise, with_right_from=None):
     return mps
 
 
+@pytest.mark.parametrize("path", ["auto", "windows", "lists"])
 @pytest.mark.parametrize("cfgname", ["euroc", "kitti"])
-def test_match_projection_batch_against_reference(cfgname):
+def test_match_projection_batch_against_reference(cfgname, path, monkeypatch):
     """RPred (rad 10 / 40 / 120), Mono (rad 1200), Radius (rad 120) for a batch of frames in ONE call each, with pre-filled in-out
-    arrays, against the reference matcher run frame by frame."""
+    arrays, against the reference matcher run frame by frame.  The call has two device paths -- a thread per search window with the
+    four best keys kept (tracking radii) and stored candidate lists (radii that cover much of the image); `path` forces one of them
+    (GVS_PROJ_WIDE, read per call) or leaves the choice to the library: all three must agree with the reference."""
+    if path != "auto":
+        monkeypatch.setenv("GVS_PROJ_WIDE", "1" if path == "lists" else "0")
     cfg = synth.CONFIGS[cfgname]
     w, h = cfg["width"], cfg["height"]
     F = 4
