@@ -376,6 +376,7 @@ constexpr int kGraphMaxImages = 8;
 // rerun = the same resident input is processed again (a parity tap was switched on): the results are the same, so the batch
 // generation, which the matcher compares, stays
 int runExtract(gvs_extractor* fe, int n, bool rerun = false) {
+    NvtxScope nvtx("gvs:extract");
     cudaStream_t s = fe->stream;
     static const bool noGraph = getenv("GVS_NO_GRAPH") != nullptr;
     // (a caller's stream that is itself being captured takes the plain launches: they become part of the caller's graph)
@@ -1085,6 +1086,7 @@ int gvs_matcher_set_stream(gvs_matcher* m, void* cuda_stream) {
 }
 
 int gvs_stereo_match_batch(gvs_matcher* m, int n_frames) {
+    NvtxScope nvtx("gvs:stereo_match");
     if (!m) return fail(GVS_ERR_INVALID, "null matcher");
     if (n_frames < 1 || n_frames > m->L->lastN || n_frames > m->R->lastN) return fail(GVS_ERR_STATE, "extract both sides first");
     DeviceGuard deviceGuard(m->L->device);
@@ -1158,6 +1160,7 @@ int gvs_stereo_download(gvs_matcher* m, int first, int count, int32_t* right_idx
 }
 
 int gvs_assign_grids_batch(gvs_matcher* m, int n_frames, int width, int height) {
+    NvtxScope nvtx("gvs:assign_grids");
     if (!m) return fail(GVS_ERR_INVALID, "null matcher");
     if (n_frames < 1 || n_frames > m->L->lastN) return fail(GVS_ERR_STATE, "extract first");
     if (width < 1 || height < 1) return fail(GVS_ERR_INVALID, "bad size");
@@ -1212,6 +1215,7 @@ int gvs_grid_download(gvs_matcher* m, int frame, int side, int32_t* cell_start, 
 }
 
 int gvs_track_stereo_batch_resident(gvs_matcher* m, int n_frames, int width, int height) {
+    NvtxScope nvtx("gvs:track_stereo_batch");
     if (!m) return fail(GVS_ERR_INVALID, "null matcher");
     if (m->R == m->L) return fail(GVS_ERR_STATE, "stereo tracking needs two extractors");
     DeviceGuard deviceGuard(m->L->device);
@@ -1230,6 +1234,7 @@ int gvs_track_stereo_batch_resident(gvs_matcher* m, int n_frames, int width, int
 
 int gvs_track_stereo_batch_host(gvs_matcher* m, const uint8_t* left, const uint8_t* right, size_t image_stride, int row_stride,
                                 int n_frames, int width, int height) {
+    NvtxScope nvtx("gvs:track_stereo_batch_host");
     if (!m) return fail(GVS_ERR_INVALID, "null matcher");
     if (m->R == m->L) return fail(GVS_ERR_STATE, "stereo tracking needs two extractors");
     DeviceGuard deviceGuard(m->L->device);

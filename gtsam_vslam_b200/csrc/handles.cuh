@@ -6,11 +6,20 @@
 #include <map>
 
 #include "common.cuh"
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX: ranges show up in nsys / ncu timelines, a no-op without a tool attached
 
 namespace gvs {
 
 // Entry points run on the handle's device and leave the caller's current device as they found it (a caller such as PyTorch
 // resolves "cuda" to the current device).
+// NVTX range for the duration of a C ABI call (tracing)
+struct NvtxScope {
+    explicit NvtxScope(const char* name) { nvtxRangePushA(name); }
+    ~NvtxScope() { nvtxRangePop(); }
+    NvtxScope(const NvtxScope&) = delete;
+    NvtxScope& operator=(const NvtxScope&) = delete;
+};
+
 struct DeviceGuard {
     int prev = -1;
     explicit DeviceGuard(int device) {

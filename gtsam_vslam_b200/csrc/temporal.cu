@@ -639,6 +639,7 @@ extern "C" {
 
 int gvs_match_projection_batch(gvs_matcher* m, int first_frame, int n_frames, int mode, const gvs_mappoints* mps, const int32_t* mp_offsets,
                                float rad, int32_t* matched_l, int32_t* matched_r, int32_t* matches, int32_t* n_matches) {
+    NvtxScope nvtx("gvs:match_projection_batch");
     if (!m || !mps || !mp_offsets || !matched_l || !matches || !n_matches) return fail(GVS_ERR_INVALID, "null argument");
     if (mode < 0 || mode > 2) return fail(GVS_ERR_INVALID, "bad mode");
     const bool two = mode == GVS_MATCH_STEREO_PRED;
@@ -796,6 +797,7 @@ int gvs_match_projection(gvs_matcher* m, int frame, int mode, const gvs_mappoint
 }
 
 int gvs_track_temporal_batch(gvs_matcher* m, int n_frames, const gvs_temporal_params* tp) {
+    NvtxScope nvtx("gvs:track_temporal_batch");
     if (!m || !tp || !tp->prev || !tp->pose_prev || !tp->to_camera || !tp->to_camera_r) return fail(GVS_ERR_INVALID, "null argument");
     if (m->R == m->L) return fail(GVS_ERR_STATE, "stereo temporal tracking needs two extractors");
     int rc = checkResident(m, true, 0, n_frames);
