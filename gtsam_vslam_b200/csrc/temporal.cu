@@ -272,6 +272,9 @@ __device__ __forceinline__ bool tFirstTwo(const TRec& r, const int* matched, uns
 // phase 2: ONE WARP per frame, lane = map point of the current chunk of 32.  Deciding from the stored candidates is a few
 // shared-memory look-ups per map point, so a thread per map point is enough; only the rare re-enumeration of a window is done
 // by the whole warp.  The walk is serial per frame (that is the reference's semantics), frames run in parallel.
+// MARKS: the round's tentative marks live in shared memory next to the matched flags (frames of up to ~14 k keys per side); without
+// them (very large key counts: the flags alone fill the shared memory) conflicts are found by comparing lanes pairwise.
+template <bool MARKS>
 __global__ void __launch_bounds__(32)
 projb_resolve_kernel(const ProjBatchArgs a) {
     extern __shared__ int sMatched[];  // 2 x (capL + capR)
@@ -290,8 +293,8 @@ projb_resolve_kernel(const ProjBatchArgs a) {
     constexpr int kNoLane = 0x7fffffff;
     int* gML = a.matchedL + (oL - a.offL[a.frame0]);
     int* gMR = stereo ? a.matchedR + (oR - a.offR[a.frame0]) : nullptr;
-    for (int i = lane; i < NL; i += 32) { mL[i] = gML[i]; tL[i] = kNoLane; }
-    for (int i = lane; i < NR; i += 32) { mR[i] = gMR[i]; tR[i] = kNoLane; }
+    for (int i = lane; i < NL; i += 32) { mL[i] = gML[i]; if (MARKS) tL[i] = kNoLane; }
+    for (int i = lane; i < NR; i += 32) { mR[i] = gMR[i]; if (MARKS) tR[i] = kNoLane; }
     __syncwarp();
     const int* leftIdxs = stereo ? a.leftIdxs + oR : nullptr;
     const int* rightIdxs = stereo ? a.rightIdxs + oL : nullptr;
@@ -383,22 +386,35 @@ projb_resolve_kernel(const ProjBatchArgs a) {
             // ---- (B) longest prefix of the pending lanes in which nobody takes a deciding candidate of a later lane: every accepting
             // lane leaves its lane number on the keys it would mark (minimum wins), every pending lane looks at its deciding keys
             const int dl0 = keyOf(l1), dl1 = keyOf(l2), dr0 = keyOf(r1), dr1 = keyOf(r2);
-            if (accept) {
-                if (takeL >= 0) atomicMin(&tL[takeL], lane);
-                if (takeR >= 0) atomicMin(&tR[takeR], lane);
-            }
-            __syncwarp();
             bool unsafe = false;
-            if (pend) {
-                if (dl0 >= 0 && tL[dl0] < lane) unsafe = true;
-                if (dl1 >= 0 && tL[dl1] < lane) unsafe = true;
-                if (dr0 >= 0 && tR[dr0] < lane) unsafe = true;
-                if (dr1 >= 0 && tR[dr1] < lane) unsafe = true;
-            }
-            __syncwarp();
-            if (accept) {
-                if (takeL >= 0) tL[takeL] = kNoLane;
-                if (takeR >= 0) tR[takeR] = kNoLane;
+            if (MARKS) {
+                if (accept) {
+                    if (takeL >= 0) atomicMin(&tL[takeL], lane);
+                    if (takeR >= 0) atomicMin(&tR[takeR], lane);
+                }
+                __syncwarp();
+                if (pend) {
+                    if (dl0 >= 0 && tL[dl0] < lane) unsafe = true;
+                    if (dl1 >= 0 && tL[dl1] < lane) unsafe = true;
+                    if (dr0 >= 0 && tR[dr0] < lane) unsafe = true;
+                    if (dr1 >= 0 && tR[dr1] < lane) unsafe = true;
+                }
+                __syncwarp();
+                if (accept) {
+                    if (takeL >= 0) tL[takeL] = kNoLane;
+                    if (takeR >= 0) tR[takeR] = kNoLane;
+                }
+            } else {
+                unsigned accMask = __ballot_sync(0xffffffffu, accept != 0);
+                accMask &= ~0u << done;
+                for (unsigned am = accMask; am; am &= am - 1) {
+                    const int j = __ffs(am) - 1;
+                    const int tl = __shfl_sync(0xffffffffu, takeL, j), tr = __shfl_sync(0xffffffffu, takeR, j);
+                    if (lane > j && pend) {
+                        if (tl >= 0 && (tl == dl0 || tl == dl1)) unsafe = true;
+                        if (tr >= 0 && (tr == dr0 || tr == dr1)) unsafe = true;
+                    }
+                }
             }
             const unsigned um = __ballot_sync(0xffffffffu, unsafe);
             const int upto = um ? __ffs(um) - 1 : chunk;     // lanes [done, upto) are final
@@ -443,9 +459,15 @@ static void launchProjectBatch(const ProjBatchArgs& a, int maxMpPerFrame, cudaSt
         projb_candidates_kernel<false><<<dim3(nSlices, a.nFrames, nSides), kCandThreads, 0, s>>>(a, capKeys);
     }
     ++*launches;
-    const size_t sm = 2 * (size_t)(a.capL + a.capR) * sizeof(int);   // matched flags + the round's tentative marks
-    ensureDynamicSmem(projb_resolve_kernel, sm, cfgB);
-    projb_resolve_kernel<<<a.nFrames, 32, sm, s>>>(a);
+    const size_t flags = (size_t)(a.capL + a.capR) * sizeof(int);   // matched flags (+ as much again for the round's tentative marks)
+    static size_t cfgC[64];
+    if (2 * flags <= 200 * 1024) {
+        ensureDynamicSmem(projb_resolve_kernel<true>, 2 * flags, cfgB);
+        projb_resolve_kernel<true><<<a.nFrames, 32, 2 * flags, s>>>(a);
+    } else {
+        ensureDynamicSmem(projb_resolve_kernel<false>, flags, cfgC);
+        projb_resolve_kernel<false><<<a.nFrames, 32, flags, s>>>(a);
+    }
     ++*launches;
 }
 
