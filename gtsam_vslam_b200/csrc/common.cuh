@@ -187,6 +187,7 @@ struct GridArgs {
     int maxCells;
 };
 void launchGrid(const GridArgs& a, int nImages, cudaStream_t s, int* launches);
+void launchGrid2(const GridArgs& a, const GridArgs* b, int nImages, cudaStream_t s, int* launches);
 
 struct ProjArgs {
     int mode;           // gvs_match_mode

@@ -1180,9 +1180,11 @@ int gvs_assign_grids_batch(gvs_matcher* m, int n_frames, int width, int height) 
     GridArgs a{};
     a.xGrids = m->xGrids; a.yGrids = m->yGrids; a.xMult = m->xMult; a.yMult = m->yMult; a.maxCells = m->maxCells;
     a.kps = m->L->kps; a.off = m->L->imgOff; a.cellStart = m->cellStartL; a.items = m->itemsL;
-    launchGrid(a, n_frames, s, &launches);
     if (m->R != m->L && n_frames <= m->R->lastN) {
-        a.kps = m->R->kps; a.off = m->R->imgOff; a.cellStart = m->cellStartR; a.items = m->itemsR;
+        GridArgs r = a;
+        r.kps = m->R->kps; r.off = m->R->imgOff; r.cellStart = m->cellStartR; r.items = m->itemsR;
+        launchGrid2(a, &r, n_frames, s, &launches);
+    } else {
         launchGrid(a, n_frames, s, &launches);
     }
     if (m->L->timing) cudaEventRecord(m->ev[3], s);

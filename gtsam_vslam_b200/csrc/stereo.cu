@@ -249,8 +249,9 @@ void launchStereo(const Geometry& g, const StereoArgs& a, int nFrames, int maxKe
 // One warp per image: bin = cvRound(pt * mult) clamped (src/FeatureTracker.cpp:40-49); CSR with insertion
 // (= index) order inside a cell: counting pass, exclusive scan, stable fill in chunks of 32 keys.
 __global__ void __launch_bounds__(32)
-grid_assign_kernel(const GridArgs a) {
+grid_assign_kernel(const GridArgs a0, const GridArgs a1) {   // blockIdx.y = side (the grids of both sides in one launch)
     extern __shared__ int sCell[];  // xGrids * yGrids + 1
+    const GridArgs& a = blockIdx.y ? a1 : a0;
     const int img = blockIdx.x, lane = threadIdx.x;
     const int off = a.off[img], n = a.off[img + 1] - off;
     const int nCells = a.xGrids * a.yGrids;
@@ -295,12 +296,15 @@ grid_assign_kernel(const GridArgs a) {
     }
 }
 
-void launchGrid(const GridArgs& a, int nImages, cudaStream_t s, int* launches) {
+void launchGrid(const GridArgs& a, int nImages, cudaStream_t s, int* launches) { launchGrid2(a, nullptr, nImages, s, launches); }
+
+// b != nullptr: the grids of a second set of keys (the right images) in the same launch
+void launchGrid2(const GridArgs& a, const GridArgs* b, int nImages, cudaStream_t s, int* launches) {
     if (nImages <= 0) return;
     const size_t sm = ((size_t)a.xGrids * a.yGrids + 1) * sizeof(int);
     static size_t cfg[64];
     ensureDynamicSmem(grid_assign_kernel, sm, cfg);
-    grid_assign_kernel<<<nImages, 32, sm, s>>>(a);
+    grid_assign_kernel<<<dim3(nImages, b ? 2 : 1), 32, sm, s>>>(a, b ? *b : a);
     ++*launches;
 }
 
