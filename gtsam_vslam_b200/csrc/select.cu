@@ -42,6 +42,7 @@ template <typename IdxT>
 struct SelArrays {
     uint8_t* key;    // [n]   score, emission order
     unsigned* xy;    // [n]   x | y << 12 | score << 24, emission order
+    unsigned* sxy;   // [n]   the same in sorted order (global-memory class only, nullptr otherwise)
     IdxT* idx;       // [n]   permutation
     IdxT* tmp;       // [n]   scratch / sorted order
     int* cellOff;    // [cells + 1]
@@ -489,14 +490,88 @@ __device__ int sscPassWarp(const unsigned* xy, const IdxT* sorted, int n, int wi
     return cnt;
 }
 
+// sorted == nullptr: xy is already in sorted order (the global-memory class gathers it once after the sort, so that a pass streams
+// it instead of chasing sorted -> xy through L2).  kU chunks of 32 points are loaded per outer step (kU = 4 for the global class:
+// four independent loads in flight; 1 for the shared-memory class, where look-ahead only costs registers).
+template <typename IdxT, int kU>
+__device__ int sscPassStream(const unsigned* xy, const IdxT* sorted, int n, int width, int ncc, int ncr, unsigned* bitmap,
+                           IdxT* list, int listCap, int lane, int limit) {
+    const int pitch = ncc + 4;
+    const int bmWords = (pitch * (ncr + 4) + 31) >> 5;
+    for (int i = lane; i < bmWords; i += 32) bitmap[i] = 0;
+    __syncwarp();
+    // floor(v / width) = umulhi(v + 1, floor((2^32 - 1) / width)) for every width >= 1 while (v + 1) * width < 2^32
+    // (round-down magic number; unlike the round-up form it also exists for width 1)
+    const unsigned magic = 0xffffffffu / (unsigned)width;
+    int cnt = 0;
+    const int coverOff2 = ((lane & 7) - 2) * pitch - 2;
+    for (int base0 = 0; base0 < n; base0 += 32 * kU) {
+        unsigned q4[kU];
+#pragma unroll
+        for (int u = 0; u < kU; u++) {
+            const int i = base0 + 32 * u + lane;
+            q4[u] = i < n ? (sorted ? xy[sorted[i]] : xy[i]) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < kU; u++) {
+            const int base = base0 + 32 * u;
+            if (base >= n) break;
+            const int i = base + lane;
+            int row = 0, col = 0, bit = 0;
+            bool active = false;
+            if (i < n) {
+                const unsigned q = q4[u];
+                col = (int)__umulhi(2 * (q & 0xfff) + 1, magic);
+                row = (int)__umulhi(2 * ((q >> 12) & 0xfff) + 1, magic);
+                bit = (row + 2) * pitch + col + 2;
+                active = !((bitmap[bit >> 5] >> (bit & 31)) & 1);
+            }
+            unsigned mask = __ballot_sync(0xffffffffu, active);
+            const int rc = (row << 16) | col;
+            // Two uncovered lanes per step: the first one (f1) is always kept; the second one (f2) is kept in the same step unless
+            // f1 covers it, which every lane can tell from the two shuffled cells.  Lanes 0..4 / 8..12 set the two 5 x 5 blocks.
+            while (mask) {
+                const int f1 = __ffs(mask) - 1;
+                const unsigned rest = mask & (mask - 1);
+                const int f2 = rest ? __ffs(rest) - 1 : f1;
+                const int c1 = __shfl_sync(0xffffffffu, rc, f1), c2 = __shfl_sync(0xffffffffu, rc, f2);
+                const int r1 = c1 >> 16, q1 = c1 & 0xffff, r2 = c2 >> 16, q2 = c2 & 0xffff;
+                const bool both = rest != 0 && !((unsigned)(r2 - r1 + 2) <= 4u && (unsigned)(q2 - q1 + 2) <= 4u);
+                const bool second = lane >= 8;
+                if ((lane & 7) < 5 && lane < 16 && (!second || both)) {
+                    const int sbit = ((second ? r2 : r1) + 2) * pitch + (second ? q2 : q1) + 2 + coverOff2, sh = sbit & 31;
+                    atomicOr(&bitmap[sbit >> 5], 0x1fu << sh);
+                    if (sh > 27) atomicOr(&bitmap[(sbit >> 5) + 1], 0x1fu >> (32 - sh));
+                } else if (lane == 5) { if (cnt < listCap) list[cnt] = (IdxT)(base + f1); }
+                else if (lane == 13 && both) { if (cnt + 1 < listCap) list[cnt + 1] = (IdxT)(base + f2); }
+                cnt += both ? 2 : 1;
+                if ((unsigned)(row - r1 + 2) <= 4u && (unsigned)(col - q1 + 2) <= 4u) active = false;
+                if (both && (unsigned)(row - r2 + 2) <= 4u && (unsigned)(col - q2 + 2) <= 4u) active = false;
+                mask = __ballot_sync(0xffffffffu, active);
+            }
+            __syncwarp();
+            if (cnt > limit) return limit + 1;
+        }
+    }
+    return cnt;
+}
+
+// the pass of the shared-memory class (kU == 1) or of the global-memory class
+template <typename IdxT, int kU>
+__device__ __forceinline__ int sscPass(const unsigned* xy, const IdxT* sorted, int n, int width, int ncc, int ncr, unsigned* bitmap,
+                                       IdxT* list, int listCap, int lane, int limit) {
+    if (kU == 1) return sscPassWarp<IdxT>(xy, sorted, n, width, ncc, ncr, bitmap, list, listCap, lane, limit);
+    return sscPassStream<IdxT, kU>(xy, sorted, n, width, ncc, ncr, bitmap, list, listCap, lane, limit);
+}
+
 // The reference's binary search over the width.  The widths it can visit form a binary tree; three levels of
 // the tree (7 nodes) are evaluated speculatively by 7 warps at once, then the path is walked with the counts.
 // Returns the kept count; `outList` (shared, listCap entries) receives the kept sorted-positions.
 constexpr int kSscBitmapWords = 384;  // per-warp shared bitmap: 12288 cells (keeps the CTA at 3 per SM)
 constexpr size_t kSscListSmemBudget = 16 * 1024;  // 7 kept lists of u16: in shared memory up to this size (quota <= ~550 per level)
 __host__ __device__ inline size_t sscListScratchBytes(int listCap) { return ((size_t)kSscWarps * listCap * 4 + 255) & ~(size_t)255; }
-template <typename IdxT>
-__device__ int sscSearch(const SelArrays<IdxT>& A, SelShared& S, const IdxT* sorted, int n, const LevelGeom& lv,
+template <typename IdxT, int kU>
+__device__ int sscSearch(const SelArrays<IdxT>& A, SelShared& S, const unsigned* xy, const IdxT* sorted, int n, const LevelGeom& lv,
                          unsigned* bitmaps, IdxT* lists, int listCap, unsigned* globalBitmap, const IdxT** outList) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int K = lv.quota, cols = lv.w, rows = lv.h;
@@ -524,10 +599,10 @@ __device__ int sscSearch(const SelArrays<IdxT>& A, SelShared& S, const IdxT* sor
             int c = -1;
             if (rootFits) {
                 if (valid && fits(warp))
-                    c = sscPassWarp(A.xy, sorted, n, nw[warp], (2 * cols) / nw[warp] + 1, (2 * rows) / nw[warp] + 1,
+                    c = sscPass<IdxT, kU>(xy, sorted, n, nw[warp], (2 * cols) / nw[warp] + 1, (2 * rows) / nw[warp] + 1,
                                     bitmaps + warp * kSscBitmapWords, lists + warp * listCap, listCap, lane, lv.kmax);
             } else if (warp == 0) {  // tiny width: one pass, bitmap in global scratch
-                c = sscPassWarp(A.xy, sorted, n, nw[0], (2 * cols) / nw[0] + 1, (2 * rows) / nw[0] + 1, globalBitmap, lists,
+                c = sscPass<IdxT, kU>(xy, sorted, n, nw[0], (2 * cols) / nw[0] + 1, (2 * rows) / nw[0] + 1, globalBitmap, lists,
                                 listCap, lane, lv.kmax);
             }
             if (lane == 0) S.wA[warp] = c;
@@ -554,7 +629,7 @@ __device__ int sscSearch(const SelArrays<IdxT>& A, SelShared& S, const IdxT* sor
                 const int ncc = (2 * cols) / w + 1, ncr = (2 * rows) / w + 1;
                 const bool fitsSmem = sscBitmapCells(cols, rows, w) <= kSscBitmapWords * 32;
                 if (warp == 0) {
-                    const int c = sscPassWarp(A.xy, sorted, n, w, ncc, ncr, fitsSmem ? bitmaps : globalBitmap, lists, listCap, lane,
+                    const int c = sscPass<IdxT, kU>(xy, sorted, n, w, ncc, ncr, fitsSmem ? bitmaps : globalBitmap, lists, listCap, lane,
                                               0x7fffffff);
                     if (lane == 0) S.wA[0] = c;
                 }
@@ -604,6 +679,7 @@ select_kernel(const __grid_constant__ Geometry g, int nImages, const CandRec* __
             A.idx = reinterpret_cast<IdxT*>(p); p += (size_t)kSmallMax * sizeof(IdxT);
             A.tmp = reinterpret_cast<IdxT*>(p); p += (size_t)kSmallMax * sizeof(IdxT);
             A.key = p;
+            A.sxy = nullptr;
             A.globalBitmap = reinterpret_cast<unsigned*>(myScratch);
         } else {
             // global class: all per-candidate arrays and the segment frontiers live in global scratch
@@ -613,6 +689,7 @@ select_kernel(const __grid_constant__ Geometry g, int nImages, const CandRec* __
             A.tmp = reinterpret_cast<IdxT*>(q); q += (size_t)nMaxGlobal * sizeof(IdxT);
             A.seg = reinterpret_cast<int*>(q); A.segCap = nMaxGlobal / 17 + 2; q += (size_t)2 * 3 * A.segCap * 4;
             A.key = q; q += ((size_t)nMaxGlobal + 15) & ~(size_t)15;
+            A.sxy = reinterpret_cast<unsigned*>(q); q += (size_t)nMaxGlobal * 4;
             A.globalBitmap = reinterpret_cast<unsigned*>(q);
             A.hist = reinterpret_cast<int*>(A.bitmaps);  // the union holds only hist during the sort
         }
@@ -680,10 +757,15 @@ select_kernel(const __grid_constant__ Geometry g, int nImages, const CandRec* __
         // ---- (c) ssc binary search (src/FeatureExtractor.cpp:396-461)
         const IdxT* res = nullptr;
         GVS_PROF_DECL2
-        int count = sscSearch<IdxT>(A, S, sorted, n, lv, A.bitmaps, reinterpret_cast<IdxT*>(A.lists), A.listCap, A.globalBitmap, &res);
+        if (!kSmall) {   // coordinates in sorted order: the passes stream them (one gather here instead of one per pass and point)
+            for (int i = tid; i < n; i += kSelThreads) A.sxy[i] = A.xy[sorted[i]];
+            __syncthreads();
+        }
+        int count = sscSearch<IdxT, kSmall ? 1 : 4>(A, S, kSmall ? A.xy : A.sxy, kSmall ? sorted : nullptr, n, lv, A.bitmaps,
+                                                    reinterpret_cast<IdxT*>(A.lists), A.listCap, A.globalBitmap, &res);
         GVS_PROF(4);
         if (count > lv.keptCap || count > A.listCap) { if (tid == 0) atomicOr(status, kStatKeptOverflow); count = min(lv.keptCap, A.listCap); }
-        for (int i = tid; i < count; i += kSelThreads) keptOut[i] = A.xy[sorted[res[i]]];
+        for (int i = tid; i < count; i += kSelThreads) keptOut[i] = kSmall ? A.xy[sorted[res[i]]] : A.sxy[res[i]];
         if (tid == 0) *keptCntOut = count;
         GVS_PROF(5);
 #ifdef GVS_SEL_PROFILE
@@ -717,7 +799,7 @@ size_t selectScratchBytes(const Geometry& g) {
     // global class arrays (xy, idx, tmp, seg frontiers, key) + the fallback SSC bitmap for width 1:
     // (2h+1) x (2w+1) cells, one bit each
     const size_t nMax = (size_t)std::max(maxCandCap(g), kSmallMax);
-    size_t b = nMax * (4 + 4 + 4) + (size_t)2 * 3 * (nMax / 17 + 2) * 4 + ((nMax + 15) & ~(size_t)15);
+    size_t b = nMax * (4 + 4 + 4 + 4) + (size_t)2 * 3 * (nMax / 17 + 2) * 4 + ((nMax + 15) & ~(size_t)15);   // xy, idx, tmp, sxy, seg, key
     b += ((size_t)sscBitmapCells(g.lv[0].w, g.lv[0].h, 1) + 31) / 32 * 4 + 16;
     b = (b + 255) & ~(size_t)255;
     return b + sscListScratchBytes(maxListCap(g));   // tail: the SSC kept lists when they do not fit shared memory
