@@ -272,7 +272,7 @@ class Arm:
         self.feL.set_stream(None); self.feR.set_stream(None)
         return acc
 
-    def make_e2e(self, chunks):
+    def make_e2e(self, chunks, slots=0):
         """End to end through the public API the way a throughput caller uses it: gvs_pipeline (include/gvs.h; api.StereoPipeline)
         with `chunks` slots, the batch cut into `chunks` tickets.  A ticket is collected when its slot is needed again, so the
         upload of the next tickets (also the next step's) overlaps the kernels and downloads in flight."""
@@ -282,15 +282,16 @@ class Arm:
         while F % chunks:
             chunks -= 1
         Fc = F // chunks
+        slots = max(slots, chunks) if slots else chunks   # tickets in flight (>= tickets per step: the queue may run into the next step)
         pin = lambda n, dt: torch.empty(n, dtype=dt).pin_memory().numpy()
-        pipe = gvs.StereoPipeline(cfg["fx"], cfg["baseline"], width=w, height=h, frames_per_slot=Fc, n_slots=chunks,
+        pipe = gvs.StereoPipeline(cfg["fx"], cfg["baseline"], width=w, height=h, frames_per_slot=Fc, n_slots=slots,
                                   nFeatures=cfg["n_features"], nLevels=cfg["n_levels"], device=self.local)
         cap = Fc * self.feL.cap_per_image
         bufs = [dict(kl=pin(cap * 28, torch.uint8).view(gvs.KEYPOINT_DTYPE), kr=pin(cap * 28, torch.uint8).view(gvs.KEYPOINT_DTYPE),
                      dl=pin(cap * 32, torch.uint8), dr=pin(cap * 32, torch.uint8), ri=pin(cap, torch.int32),
                      li=pin(cap, torch.int32), de=pin(cap, torch.float32), cl=pin(cap, torch.uint8),
                      to=pin(Fc + 1, torch.int32), tk=pin(cap, torch.int32), tm=pin(cap * 2, torch.int32), tn=pin(Fc, torch.int32))
-                for _ in range(chunks)]
+                for _ in range(slots)]
         npL, npR = self.hL.numpy(), self.hR.numpy()
         motions = [None if self.args.no_temporal else motion_slice(self.mo, c * Fc, (c + 1) * Fc) for c in range(chunks)]
 
@@ -301,7 +302,7 @@ class Arm:
             def collect():
                 nonlocal nbytes, tl, tr, ts, tt
                 t = pending.pop(0)
-                b = bufs[t % chunks]
+                b = bufs[t % slots]
                 offL, offR = pipe.wait(t, Fc)
                 nl, nr = int(offL[-1]), int(offR[-1])
                 pipe.download_into(t, b["kl"], b["dl"], b["kr"], b["dr"], b["ri"], b["li"], b["de"], b["cl"])
@@ -316,7 +317,7 @@ class Arm:
 
             for _ in range(steps):
                 for c in range(chunks):
-                    if len(pending) == chunks:
+                    if len(pending) == slots:
                         collect()
                     if motions[c] is None:
                         pending.append(pipe.submit(npL[c * Fc:(c + 1) * Fc], npR[c * Fc:(c + 1) * Fc]))
@@ -355,7 +356,8 @@ def main():
     ap.add_argument("--no-temporal", action="store_true", help="extract + stereo + grids only (round-1 step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sustained", action="store_true")
-    ap.add_argument("--e2e-chunks", type=int, default=4, help="sub-batches pipelined through separate handles in the end-to-end leg")
+    ap.add_argument("--e2e-chunks", type=int, default=2, help="sub-batches (tickets) per step in the end-to-end leg")
+    ap.add_argument("--e2e-slots", type=int, default=4, help="pipeline slots = tickets in flight (at least one per ticket of a step; measured on 256 EuRoC frames: 2 tickets of 128 frames over 4 slots 48.4 k frames/s, 4 over 4: 45.4 k, 4 over 8: 46.3 k, 2 over 6: 41.9 k)")
     ap.add_argument("--also", default="auto", help="extra workloads reported in 'other_workloads' (comma list of kitti4096,hires; auto = both when "
                                                    "--gpus > 1, none otherwise)")
     args = ap.parse_args()
@@ -430,7 +432,7 @@ def main():
     serial_ms = sum(stage_acc.values())
 
     # ---- end to end through the public API: pinned host images in, all results back on the host
-    run_e2e, chunks, Fc = arm.make_e2e(args.e2e_chunks)
+    run_e2e, chunks, Fc = arm.make_e2e(args.e2e_chunks, args.e2e_slots)
     run_e2e(2)
     barrier()
     t0 = time.perf_counter()
@@ -492,7 +494,7 @@ def main():
                                  "how": "the same H2D + D2H bytes per step as bare pinned cudaMemcpyAsync on two streams, no kernels, all ranks "
                                         "at the same time (max over ranks): what the host link gives at this N"},
                 "how": f"pinned host images -> gvs_pipeline_submit_temporal / wait / download ({chunks} tickets of {Fc} frames per step streamed over "
-                       f"{chunks} slots, a ticket is collected when its slot is needed again) -> keypoints, descriptors, stereo arrays and temporal "
+                       f"{max(args.e2e_slots, chunks) if args.e2e_slots else chunks} slots, a ticket is collected when its slot is needed again) -> keypoints, descriptors, stereo arrays and temporal "
                        f"matches back in pinned host memory; wall clock around all {e2e_steps} steps including the final drain"},
         "gpu_launches": int(n_launch),
         "tma_stages": {"pyramid": bool(tma & 1), "fast": bool(tma & 2)},
