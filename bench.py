@@ -357,7 +357,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sustained", action="store_true")
     ap.add_argument("--e2e-chunks", type=int, default=2, help="sub-batches (tickets) per step in the end-to-end leg")
-    ap.add_argument("--e2e-slots", type=int, default=4, help="pipeline slots = tickets in flight (at least one per ticket of a step; measured on 256 EuRoC frames: 2 tickets of 128 frames over 4 slots 48.4 k frames/s, 4 over 4: 45.4 k, 4 over 8: 46.3 k, 2 over 6: 41.9 k)")
+    ap.add_argument("--e2e-slots", type=int, default=6, help="pipeline slots = tickets in flight (at least one per ticket of a step; measured on 256 EuRoC frames, tickets per step / slots: 2/6 48.9 k frames/s, 1/4 48.9 k, 3/6 48.6 k, 2/4 48.1 k, 1/3 47.7 k, 2/8 46.7 k, 4/4 45.4 k, 1/2 40.9 k)")
     ap.add_argument("--also", default="auto", help="extra workloads reported in 'other_workloads' (comma list of kitti4096,hires; auto = both when "
                                                    "--gpus > 1, none otherwise)")
     args = ap.parse_args()
@@ -433,7 +433,7 @@ def main():
 
     # ---- end to end through the public API: pinned host images in, all results back on the host
     run_e2e, chunks, Fc = arm.make_e2e(args.e2e_chunks, args.e2e_slots)
-    run_e2e(2)
+    run_e2e(2 + (max(args.e2e_slots, chunks) + chunks - 1) // chunks)   # warm-up: every slot has been used (first use allocates)
     barrier()
     t0 = time.perf_counter()
     e2e_steps = max(args.steps, 3)
