@@ -440,7 +440,7 @@ void launchFast(const Geometry& g, const uint8_t* slab, const FastItem* items, i
     // strips per CTA (a CTA that takes several requests the next strip's tile while it writes the current strip's records).  Measured
     // on 256 EuRoC frames: 1 strip 1.89 ms, 2: 1.90, 3: 1.92, 4: 1.92, 8: 1.98 -- many short CTAs schedule better than few long
     // ones and four CTAs per SM already hide the tile latency, so the default is 1
-    static const int perCta = [] { const char* e = getenv("GVS_FAST_ITEMS"); const int v = e ? atoi(e) : 1; return std::min(std::max(v, 1), 64); }();
+    const int perCta = [] { const char* e = getenv("GVS_FAST_ITEMS"); const int v = e ? atoi(e) : 1; return std::min(std::max(v, 1), 64); }();   // (read per launch: tests switch it)
     FastMaps pm{};
     if (levelMaps) {
         const FastSmemLayout L = fastLayout(d.maxSW, d.maxGW, d.maxGH, true);

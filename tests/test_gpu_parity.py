@@ -640,3 +640,25 @@ def test_tma_staging_is_active_and_changes_nothing(cfgname, monkeypatch):
     monkeypatch.setenv("GVS_NO_FUSED_PYR", "1"); monkeypatch.setenv("GVS_NO_FAST_TMA", "1")
     stages, without = run()
     assert stages == 0 and without == with_tma
+
+
+@pytest.mark.parametrize("cfgname", ["euroc", "small"])
+def test_fast_several_strips_per_cta(cfgname, monkeypatch):
+    """GVS_FAST_ITEMS > 1: a CTA of the FAST kernel walks several strips and requests the next strip's tile (TMA) while it writes the
+    current strip's records.  Not the default (it measures slower), but it must give the same bytes."""
+    cfg = synth.CONFIGS[cfgname]
+    w, h = cfg["width"], cfg["height"]
+    n = 9   # (more than 8 images: smaller batches replay a captured graph, which would keep the first setting)
+    imgs = np.ascontiguousarray(synth.stereo_batch(w, h, cfg["disparity"], range(70, 70 + n))[0])
+    fe = gvs.FeatureExtractor(nFeatures=cfg["n_features"], nLevels=cfg["n_levels"], width=w, height=h, max_images=n)
+
+    def run():
+        fe.extract_batch(imgs); fe.sync()
+        off = fe.offsets(n)
+        kp, desc = fe.download(0, n, int(off[n]))
+        return off.tobytes() + kp.tobytes() + desc.tobytes()
+
+    ref = run()
+    for k in ("2", "3", "7"):
+        monkeypatch.setenv("GVS_FAST_ITEMS", k)
+        assert run() == ref, k
