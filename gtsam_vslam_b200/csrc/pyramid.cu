@@ -131,8 +131,8 @@ pyr_fused_kernel(const __grid_constant__ Geometry g, const __grid_constant__ CUt
         mbarExpectTx(bar, (unsigned)(G.boxW * G.boxH));
         tmaLoadTile3d(smemAddr(sm), &baseMap, gx[0], gy[0], img, bar);   // PyrSpan::lo[0]
     }
-    __syncthreads();      // (the barrier is initialised before anybody polls it)
-    mbarWait(bar, 0);
+    if (tid == 0) mbarWait(bar, 0);   // one thread polls (a polling warp takes issue slots from the CTAs that compute) ...
+    __syncthreads();                  // ... and the CTA barrier passes the arrival on
     for (int k = 1; k <= G.nOut; k++) {
         const int level = G.base + k;
         const LevelGeom& D = g.lv[level];
