@@ -163,6 +163,10 @@ struct StereoArgs {
     const int* keptCntL;  // per image per level counts (nImages x kMaxLevels)
     const int* keptCntR;
     const uint2* auxR; // per right key: bucket row range (mn | mx << 16) and pt.y, written by the descriptor kernel
+    int* rowStart;             // per frame (imageHeight + 1): CSR over image rows of the right keys whose bucket range holds the row
+    unsigned short* rowItems;  // per frame rowItemsStride entries: right key indices (inside the frame), row by row
+    int rowItemsStride;
+    int bucketRows;            // rows that have a bucket: min(imageHeight of the matcher, image height)
     int* rightIdxs;   // dense, left offsets
     int* leftIdxs;    // dense, right offsets
     float* depth;

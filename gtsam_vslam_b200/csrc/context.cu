@@ -1046,6 +1046,7 @@ int gvs_matcher_destroy(gvs_matcher* m) {
     devFree(m->pjOwn);   // the matcher's last enqueued work (no device-wide synchronisation: see gvs_extractor_create)
     devFree(m->rightIdxs); devFree(m->leftIdxs); devFree(m->sadBest); devFree(m->sortScratch); devFree(m->depth); devFree(m->close);
     devFree(m->cellStartL); devFree(m->cellStartR); devFree(m->itemsL); devFree(m->itemsR); devFree(m->pj);
+    devFree(m->rowStart); devFree(m->rowItems);
     devFree(m->pool); devFree(m->pjStatus);
     if (m->evR) cudaEventDestroy(m->evR);
     if (m->evFork) cudaEventDestroy(m->evFork);
@@ -1097,6 +1098,16 @@ int gvs_stereo_match_batch(gvs_matcher* m, int n_frames) {
     a.slabL = m->L->slab; a.slabR = m->R->slab; a.kpL = m->L->kps; a.kpR = m->R->kps; a.descL = m->L->desc; a.descR = m->R->desc;
     a.offL = m->L->imgOff; a.offR = m->R->imgOff; a.keptCntL = m->L->keptCnt; a.keptCntR = m->R->keptCnt;
     a.auxR = m->R->auxKey;
+    if (!m->rowStart) {   // first stereo match of this matcher: the row buckets of the right keys
+        // a key lies in the buckets of rows floor(y - r) .. ceil(y + r), r = 2 * scalePyramid[octave] (src/FeatureMatcher.cpp:741-744)
+        const int dup = 2 * (int)std::ceil(2.0 * (double)m->R->scale[m->R->g.nLevels - 1]) + 3;
+        const size_t B = (size_t)std::min(m->L->maxImages, m->R->maxImages);
+        m->rowItemsStride = m->R->g.keptPerImage * dup;
+        GVS_CUDA_OK(devAlloc(&m->rowStart, B * (size_t)(std::min(m->imageHeight, m->L->height) + 1)));
+        GVS_CUDA_OK(devAlloc(&m->rowItems, B * (size_t)m->rowItemsStride));
+    }
+    a.rowStart = m->rowStart; a.rowItems = m->rowItems; a.rowItemsStride = m->rowItemsStride;
+    a.bucketRows = std::min(m->imageHeight, m->L->height);   // (a left key's row is below both)
     a.rightIdxs = m->rightIdxs; a.leftIdxs = m->leftIdxs; a.depth = m->depth; a.close = m->close; a.sadBest = m->sadBest;
     a.fx = m->fx; a.baseline = m->baseline; a.imageHeight = m->imageHeight; a.closeNumber = 40; a.thDist = 75;
     {

@@ -178,6 +178,9 @@ struct gvs_matcher {
     uint8_t* pjOwn = nullptr;
     size_t pjOwnBytes = 0;
     unsigned* pool = nullptr;
+    int* rowStart = nullptr;               // stereo row buckets (destributeRightKeys), see stereo.cu
+    unsigned short* rowItems = nullptr;
+    int rowItemsStride = 0;
     int poolCap = 0;
     int* pjStatus = nullptr;
     int launches = 0;

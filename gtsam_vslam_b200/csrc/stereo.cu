@@ -3,10 +3,10 @@
 // :728-752) and FeatureTracker::assignKeysToGrids (src/FeatureTracker.cpp:28-54) for a batch of frames.
 //
 // stereo_match: one warp per left key.
-//   * the row buckets of destributeRightKeys are never materialised: right key j is in bucket[yKeyL] iff
-//     floor(yKeyR - r) <= yKeyL <= ceil(yKeyR + r), r = 2*scalePyramid[octR] (float32), and buckets hold
-//     indices in ascending order, so "first minimum in bucket order" is the minimum of (distance, j).
-//     Right keys are stored level by level, so only the levels octL-1..octL+1 are scanned.
+//   * the row buckets of destributeRightKeys are built per frame by row_bucket_kernel (CSR over image rows): right key j is in
+//     bucket[yKeyL] iff floor(yKeyR - r) <= yKeyL <= ceil(yKeyR + r), r = 2*scalePyramid[octR] (float32); the reference's buckets
+//     hold indices in ascending order, so its "first minimum in bucket order" is the minimum of (distance, j), whatever the order
+//     here.  Right keys are stored level by level, so the level test octL-1..octL+1 is a range test on j.
 //   * the reference's "u" test uses pt.y (sic): yL - fx <= yR <= yL.
 //   * Hamming distance: 8 x __popc on 32-bit words, warp-shuffle argmin on (dist << 20 | j).
 //   * SAD refinement on the unblurred level octL of both pyramids: 22 lanes = 11 shifts x 2 row halves, a patch row = 3 words
@@ -37,20 +37,67 @@ __device__ __forceinline__ void patchRow(const uint8_t* p, unsigned& w0, unsigne
     w0 = __funnelshift_r(a0, a1, sh); w1 = __funnelshift_r(a1, a2, sh); w2 = __funnelshift_r(a2, a3, sh) & 0x00ffffffu;
 }
 
+// destributeRightKeys (src/FeatureMatcher.cpp:728-752) for a batch: per frame a CSR over image rows, row r listing the right keys
+// whose bucket range [mn, mx] (written by the descriptor kernel) holds r.  The order inside a row is arbitrary: the match takes the
+// minimum of (distance, key index), which does not depend on it.  One CTA per frame; counters, scan and cursors in shared memory.
 __global__ void __launch_bounds__(256)
-stereo_match_kernel(const __grid_constant__ Geometry g, const StereoArgs a, int auxCap) {
+row_bucket_kernel(const StereoArgs a) {
+    extern __shared__ int sRow[];   // bucketRows + 1
+    __shared__ int sWarp[8];
+    const int frame = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int offR = a.offR[frame], nR = a.offR[frame + 1] - offR;
+    const int H = a.bucketRows;
+    for (int r = tid; r <= H; r += 256) sRow[r] = 0;
+    __syncthreads();
+    for (int j = tid; j < nR; j += 256) {
+        const unsigned rg = a.auxR[offR + j].x;
+        const int mn = (int)(rg & 0xffffu), mx = min((int)(rg >> 16), H - 1);
+        for (int r = mn; r <= mx; r++) atomicAdd(&sRow[r], 1);
+    }
+    __syncthreads();
+    // exclusive scan over the rows: thread t owns rows [t * per, (t + 1) * per)
+    const int per = (H + 255) / 256;
+    const int r0 = min(tid * per, H), r1 = min(r0 + per, H);
+    int sum = 0;
+    for (int r = r0; r < r1; r++) sum += sRow[r];
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) sWarp[warp] = incl;
+    __syncthreads();
+    int base = incl - sum;
+    for (int w = 0; w < warp; w++) base += sWarp[w];
+    int total = 0;
+    for (int w = 0; w < 8; w++) total += sWarp[w];
+    for (int r = r0; r < r1; r++) { const int c = sRow[r]; sRow[r] = base; base += c; }
+    if (tid == 0) sRow[H] = total;
+    __syncthreads();
+    int* rs = a.rowStart + (size_t)frame * (H + 1);
+    for (int r = tid; r <= H; r += 256) rs[r] = sRow[r];
+    __syncthreads();
+    unsigned short* items = a.rowItems + (size_t)frame * a.rowItemsStride;
+    for (int j = tid; j < nR; j += 256) {
+        const unsigned rg = a.auxR[offR + j].x;
+        const int mn = (int)(rg & 0xffffu), mx = min((int)(rg >> 16), H - 1);
+        for (int r = mn; r <= mx; r++) {
+            const int p = atomicAdd(&sRow[r], 1);
+            if (p < a.rowItemsStride) items[p] = (unsigned short)j;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+stereo_match_kernel(const __grid_constant__ Geometry g, const StereoArgs a) {
     const int frame = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const int offL = a.offL[frame], nL = a.offL[frame + 1] - offL;
     const int offR = a.offR[frame], nR = a.offR[frame + 1] - offR;
     __shared__ int sLvlStart[kMaxLevels + 1];
-    extern __shared__ uint2 sAux[];   // the frame's right keys: bucket rows [mn, mx] and pt.y (8 B each), scanned once per left key
     if (threadIdx.x == 0) {
         int run = 0;
         for (int l = 0; l < kMaxLevels; l++) { sLvlStart[l] = run; run += l < g.nLevels ? a.keptCntR[frame * kMaxLevels + l] : 0; }
         sLvlStart[kMaxLevels] = run;
     }
-    for (int j = threadIdx.x; j < min(nR, auxCap); j += blockDim.x) sAux[j] = __ldg(a.auxR + offR + j);
     __syncthreads();
     const float maxD = (float)a.fx;
     const int warpsPerGrid = gridDim.x * (blockDim.x >> 5);
@@ -63,16 +110,19 @@ stereo_match_kernel(const __grid_constant__ Geometry g, const StereoArgs a, int 
         const float uL = kl.y;
         const int octL = kl.octave;
         const float minU = __fsub_rn(uL, maxD), maxU = uL;
-        if (!(maxU < 0.f) && yKey >= 0 && yKey < a.imageHeight) {
+        if (!(maxU < 0.f) && yKey >= 0 && yKey < a.imageHeight && yKey < a.bucketRows) {   // (bucketRows = min(imageHeight, image rows))
             const uint4* dl = reinterpret_cast<const uint4*>(a.descL + (size_t)(offL + i) * 32);
             const uint4 l0 = __ldg(dl), l1 = __ldg(dl + 1);
             const int j0 = sLvlStart[max(octL - 1, 0)], j1 = sLvlStart[min(octL + 2, kMaxLevels)];
             unsigned best = 0xffffffffu;
-            for (int j = j0 + lane; j < min(j1, nR); j += 32) {
-                const uint2 ar = j < auxCap ? sAux[j] : __ldg(a.auxR + offR + j);  // bucket rows [mn, mx] of this right key, and its pt.y
-                const int mn = (int)(ar.x & 0xffffu), mx = (int)(ar.x >> 16);
-                if (yKey < mn || yKey > mx) continue;
-                const float yR = __uint_as_float(ar.y);
+            // the row bucket of yKey: right keys j with mn_j <= yKey <= mx_j; of these the levels octL-1 .. octL+1 (key ranges j0 .. j1)
+            const int* rs = a.rowStart + (size_t)frame * (a.bucketRows + 1);
+            const unsigned short* items = a.rowItems + (size_t)frame * a.rowItemsStride;
+            const int p1 = min(rs[yKey + 1], a.rowItemsStride);
+            for (int p = rs[yKey] + lane; p < p1; p += 32) {
+                const int j = items[p];
+                if (j < j0 || j >= j1) continue;
+                const float yR = __uint_as_float(__ldg(&a.auxR[offR + j].y));
                 if (!(yR >= minU && yR <= maxU)) continue;
                 const uint4* dr = reinterpret_cast<const uint4*>(a.descR + (size_t)(offR + j) * 32);
                 const int dist = hamming256(l0, l1, __ldg(dr), __ldg(dr + 1));
@@ -228,11 +278,13 @@ void launchStereo(const Geometry& g, const StereoArgs& a, int nFrames, int maxKe
     static const int keysPerWarp = [] { const char* e = getenv("GVS_STEREO_KEYS"); return e ? std::max(atoi(e), 1) : 8; }();
     int gx = (maxKeysPerImage / 2 + keysPerWarp * warpsPerCta - 1) / (keysPerWarp * warpsPerCta);  // left keys per warp at typical fill
     if (gx < 1) gx = 1;
-    // every CTA keeps the 8-byte row / y records of the frame's right keys in shared memory (the per-left-key scan runs over them)
-    const int auxCap = std::min(maxKeysPerImage, 5120);   // (40 KB; the records of further keys are read from global memory)
-    static size_t cfgAux[64];
-    ensureDynamicSmem(stereo_match_kernel, (size_t)auxCap * sizeof(uint2), cfgAux);
-    stereo_match_kernel<<<dim3(gx, nFrames), 32 * warpsPerCta, (size_t)auxCap * sizeof(uint2), s>>>(g, a, auxCap);
+    // the row buckets of the right keys first (one CTA per frame)
+    static size_t cfgRow[64];
+    const size_t rowSm = ((size_t)a.bucketRows + 1) * sizeof(int);
+    ensureDynamicSmem(row_bucket_kernel, rowSm, cfgRow);
+    row_bucket_kernel<<<nFrames, 256, rowSm, s>>>(a);
+    ++*launches;
+    stereo_match_kernel<<<dim3(gx, nFrames), 32 * warpsPerCta, 0, s>>>(g, a);
     ++*launches;
     int n2 = 1;
     while (n2 < maxKeysPerImage) n2 <<= 1;
