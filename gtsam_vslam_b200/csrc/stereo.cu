@@ -212,49 +212,110 @@ __device__ void bitonicSort(unsigned long long* k, int n) {
     __syncthreads();
 }
 
+// The two outlier passes of findStereoMatchesORB2R (src/FeatureMatcher.cpp:655-706) need the floor(1 %) smallest (depth, index)
+// pairs of the frame's matches and the median SAD, not sorted arrays: the first is a handful of block-wide arg-min rounds (a bitonic
+// sort when the frame has more than kMinRounds * 100 matches), the second a two-level radix select on the 15-bit SAD.
+constexpr int kMinRounds = 16;
+
+__device__ __forceinline__ unsigned long long warpMin64(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o);
+        v = w < v ? w : v;
+    }
+    return v;
+}
+
 __global__ void __launch_bounds__(256)
 stereo_finalize_kernel(const StereoArgs a, int sortCap, unsigned long long* __restrict__ gKeys) {
     extern __shared__ unsigned long long smKeys[];
     // sort keys live in shared memory when the per-image key capacity fits, in global scratch otherwise (very large nFeatures)
     unsigned long long* sKeys = gKeys ? gKeys + (size_t)blockIdx.x * sortCap : smKeys;
-    __shared__ int sCount;
+    __shared__ int sCount, sHist[256], sSel[2];
+    __shared__ unsigned long long sWarpMin[8];
     __shared__ float sMed;
-    const int frame = blockIdx.x, tid = threadIdx.x;
+    const int frame = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int offL = a.offL[frame], nL = a.offL[frame + 1] - offL;
     const int offR = a.offR[frame];
+    int mine = 0;
+    for (int i = tid; i < nL; i += blockDim.x) mine += a.rightIdxs[offL + i] >= 0;
     if (tid == 0) sCount = 0;
     __syncthreads();
-    // pass A: (depth, idx) ascending -> lowest floor(1%) depths
-    for (int i = tid; i < nL; i += blockDim.x)
-        if (a.rightIdxs[offL + i] >= 0) {
-            const int s = atomicAdd(&sCount, 1);
-            if (s < sortCap) sKeys[s] = ((unsigned long long)__float_as_uint(a.depth[offL + i]) << 32) | (unsigned)i;
-        }
+    if (mine) atomicAdd(&sCount, mine);
     __syncthreads();
-    const int V = min(sCount, sortCap);
+    const int V = sCount;   // matched left keys of the frame
     if (V <= 0) return;
-    int n2 = 1;
-    while (n2 < V) n2 <<= 1;
-    for (int i = V + tid; i < n2; i += blockDim.x) sKeys[i] = ~0ull;
-    bitonicSort(sKeys, n2);
+    // ---- pass A: the floor(1 %) smallest (depth, idx) are dropped.  They are marked through the close[] byte (2 = "drop"; close is
+    // rewritten below) and applied after pass B has read the SADs: the two passes commute.
     const int endDe = (int)floor((double)V * 0.01);
-    // The left keys pass A removes are marked through the close[] byte (2 = "drop"; close is rewritten below) and applied after
-    // pass B has read the SADs: the two passes commute.
-    __syncthreads();
-    for (int i = tid; i < endDe; i += blockDim.x) a.close[offL + (int)(sKeys[i] & 0xffffffffu)] = 2;
-    __syncthreads();
-    if (tid == 0) sCount = 0;
-    __syncthreads();
-    for (int i = tid; i < nL; i += blockDim.x)
-        if (a.rightIdxs[offL + i] >= 0) {
-            const int s = atomicAdd(&sCount, 1);
-            if (s < sortCap) sKeys[s] = ((unsigned long long)(unsigned)a.sadBest[offL + i] << 32) | (unsigned)i;
+    if (endDe <= kMinRounds) {
+        unsigned long long last = 0;
+        for (int r = 0; r < endDe; r++) {
+            unsigned long long best = ~0ull;
+            for (int i = tid; i < nL; i += blockDim.x) {
+                if (a.rightIdxs[offL + i] < 0) continue;
+                const unsigned long long k = ((unsigned long long)__float_as_uint(a.depth[offL + i]) << 32) | (unsigned)i;
+                if ((r == 0 || k > last) && k < best) best = k;   // (keys are distinct: the index is part of them)
+            }
+            best = warpMin64(best);
+            if (lane == 0) sWarpMin[warp] = best;
+            __syncthreads();
+            best = sWarpMin[0];
+#pragma unroll
+            for (int w = 1; w < 8; w++) best = sWarpMin[w] < best ? sWarpMin[w] : best;
+            last = best;
+            if (tid == 0) a.close[offL + (int)(last & 0xffffffffu)] = 2;
+            __syncthreads();
         }
-    __syncthreads();
-    for (int i = V + tid; i < n2; i += blockDim.x) sKeys[i] = ~0ull;
-    bitonicSort(sKeys, n2);
+    } else {
+        if (tid == 0) sCount = 0;
+        __syncthreads();
+        for (int i = tid; i < nL; i += blockDim.x)
+            if (a.rightIdxs[offL + i] >= 0) {
+                const int s = atomicAdd(&sCount, 1);
+                if (s < sortCap) sKeys[s] = ((unsigned long long)__float_as_uint(a.depth[offL + i]) << 32) | (unsigned)i;
+            }
+        __syncthreads();
+        const int Vs = min(V, sortCap);
+        int n2 = 1;
+        while (n2 < Vs) n2 <<= 1;
+        for (int i = Vs + tid; i < n2; i += blockDim.x) sKeys[i] = ~0ull;
+        bitonicSort(sKeys, n2);
+        for (int i = tid; i < min(endDe, Vs); i += blockDim.x) a.close[offL + (int)(sKeys[i] & 0xffffffffu)] = 2;
+    }
+    // ---- pass B: the median SAD = element V / 2 of the ascending (SAD, idx) order; only its SAD is used.  SAD <= 11 * 11 * 255 < 2^15:
+    // bits 14..7 pick one of 256 bins, bits 6..0 one of 128 inside it.
+    int target = V / 2, prefix = 0;
+    for (int level = 0; level < 2; level++) {
+        __syncthreads();
+        sHist[tid] = 0;
+        __syncthreads();
+        for (int i = tid; i < nL; i += blockDim.x) {
+            if (a.rightIdxs[offL + i] < 0) continue;
+            const int v = a.sadBest[offL + i];
+            if (level == 0) atomicAdd(&sHist[min(v >> 7, 255)], 1);
+            else if (min(v >> 7, 255) == prefix) atomicAdd(&sHist[v & 127], 1);
+        }
+        __syncthreads();
+        if (warp == 0) {   // the bin that holds rank `target`: 8 bins per lane, warp scan
+            int c[8], sum = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) { c[k] = sHist[8 * lane + k]; sum += c[k]; }
+            int incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            int run = incl - sum;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                if (target >= run && target < run + c[k]) { sSel[0] = 8 * lane + k; sSel[1] = target - run; }
+                run += c[k];
+            }
+        }
+        __syncthreads();
+        if (level == 0) { prefix = sSel[0]; target = sSel[1]; }
+    }
     if (tid == 0) {
-        const int medianD = (int)(sKeys[V / 2] >> 32);
+        const int medianD = (prefix << 7) | sSel[0];
         sMed = __fmul_rn((float)medianD, __fmul_rn(1.5f, 1.4f));
     }
     __syncthreads();

@@ -219,10 +219,11 @@ projb_candidates_kernel(const ProjBatchArgs a, int capKeys) {
         sd.kp = reinterpret_cast<const char*>(gKp); sd.kpStride = (int)sizeof(gvs_keypoint); sd.octOfs = 20;
         sd.cellStart = gCell; sd.items = gItems;
     }
-    const int i = i0 + tid;
-    if (i >= M) return;
-    const int mpi = mp0 + i;
     const bool radiusMode = a.mode == GVS_MATCH_RADIUS;
+    // the CTA's slices of 256 map points: blockIdx.x, blockIdx.x + gridDim.x, ... (large batches run one CTA per frame and side, so
+    // that the frame is staged once; small ones spread a frame over several CTAs)
+    for (int i = i0 + tid; i < M; i += gridDim.x * kCandThreads) {
+    const int mpi = mp0 + i;
     TRec rec;
 #pragma unroll
     for (int q = 0; q < kTopK; q++) rec.e[q] = kNoCand;
@@ -245,6 +246,7 @@ projb_candidates_kernel(const ProjBatchArgs a, int capKeys) {
         tScanLane(sd, w, a.xGrids, q0, q1, skip, radiusMode, rec);
     }
     a.recs[2 * (size_t)mpi + side] = rec;
+    }
 }
 
 struct TDecision { int bestDist, bestIdx, bestLev, bestLev2, secDist; };
@@ -448,7 +450,9 @@ projb_resolve_kernel(const ProjBatchArgs a) {
 static void launchProjectBatch(const ProjBatchArgs& a, int maxMpPerFrame, cudaStream_t s, int* launches) {
     if (a.nFrames <= 0) return;
     const int nSides = a.mode == GVS_MATCH_STEREO_PRED ? 2 : 1;
-    const int nSlices = std::max((maxMpPerFrame + kCandThreads - 1) / kCandThreads, 1);
+    // CTAs per (frame, side): enough of them to fill the GPU (148 SMs x ~4 CTAs), at most one per 256 map points
+    const int maxSlices = std::max((maxMpPerFrame + kCandThreads - 1) / kCandThreads, 1);
+    const int nSlices = std::min(maxSlices, std::max(1, (592 + a.nFrames * nSides - 1) / (a.nFrames * nSides)));
     const int capKeys = std::max(a.capL, a.capR), nCells = a.xGrids * a.yGrids + 1;
     const size_t stage = (size_t)((nCells + 3) & ~3) * 4 + (size_t)capKeys * (4 + 4 + sizeof(TKey3)) + 16;
     static size_t cfgA[64], cfgB[64];
