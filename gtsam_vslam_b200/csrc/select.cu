@@ -35,6 +35,7 @@ namespace gvs {
 constexpr int kSelThreads = 256;
 constexpr int kSelWarps = kSelThreads / 32;
 constexpr int kSmallMax = 6144;    // problems with n <= kSmallMax run entirely in shared memory
+constexpr int kBigKeySmem = 64 * 1024;  // global-memory class: the 8-bit keys of a problem of up to this many candidates stay in shared memory
 constexpr int kBigSeg = 1024;      // segments at least this long are partitioned by the whole CTA
 constexpr int kSscWarps = 7;       // widths evaluated speculatively per super-round
 
@@ -657,6 +658,7 @@ select_kernel(const __grid_constant__ Geometry g, int nImages, const CandRec* __
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     SelArrays<IdxT> A;
+    size_t bigKeyOff = 0;
     uint8_t* myScratch = scratch + (size_t)blockIdx.x * scratchPerCta;
     {
         // shared layout: cellOff | union(sort: seg + hist ; ssc: bitmaps + lists) | [small only] xy | idx | tmp | key
@@ -674,6 +676,7 @@ select_kernel(const __grid_constant__ Geometry g, int nImages, const CandRec* __
         A.listCap = listCap;
         const size_t unionBytes = segBytes + histBytes > bmBytes + listBytes ? segBytes + histBytes : bmBytes + listBytes;
         p += (unionBytes + 15) & ~15;
+        bigKeyOff = (size_t)(p - smem);
         if (kSmall) {
             A.xy = reinterpret_cast<unsigned*>(p); p += (size_t)kSmallMax * 4;
             A.idx = reinterpret_cast<IdxT*>(p); p += (size_t)kSmallMax * sizeof(IdxT);
@@ -688,13 +691,15 @@ select_kernel(const __grid_constant__ Geometry g, int nImages, const CandRec* __
             A.idx = reinterpret_cast<IdxT*>(q); q += (size_t)nMaxGlobal * sizeof(IdxT);
             A.tmp = reinterpret_cast<IdxT*>(q); q += (size_t)nMaxGlobal * sizeof(IdxT);
             A.seg = reinterpret_cast<int*>(q); A.segCap = nMaxGlobal / 17 + 2; q += (size_t)2 * 3 * A.segCap * 4;
-            A.key = q; q += ((size_t)nMaxGlobal + 15) & ~(size_t)15;
+            A.key = q; q += ((size_t)nMaxGlobal + 15) & ~(size_t)15;   // (problems above kBigKeySmem candidates; smaller ones: shared, below)
             A.sxy = reinterpret_cast<unsigned*>(q); q += (size_t)nMaxGlobal * 4;
             A.globalBitmap = reinterpret_cast<unsigned*>(q);
             A.hist = reinterpret_cast<int*>(A.bitmaps);  // the union holds only hist during the sort
         }
     }
 
+    uint8_t* const keyGlobal = A.key;
+    uint8_t* const keyShared = kSmall ? A.key : smem + bigKeyOff;   // (global class: behind cellOff and the union)
     const int nProb = nImages * g.nLevels;
     while (true) {
         __syncthreads();
@@ -707,6 +712,7 @@ select_kernel(const __grid_constant__ Geometry g, int nImages, const CandRec* __
         int n = nCand[img * kMaxLevels + level];
         if (n > lv.candCap) n = lv.candCap;  // overflow already flagged by the FAST kernel
         if ((n <= kSmallMax) != kSmall) continue;
+        if (!kSmall) A.key = n <= kBigKeySmem ? keyShared : keyGlobal;   // the partition passes mostly read keys
         int* keptCntOut = keptCnt + img * kMaxLevels + level;
         KeptKey* keptOut = kept + (size_t)img * g.keptPerImage + lv.keptOff;
         if (n == 0) { if (tid == 0) *keptCntOut = 0; continue; }
@@ -780,6 +786,7 @@ static size_t selectSmemBytes(bool small, int maxCells, int segCap, int listCap 
     size_t u = std::max(segBytes + histBytes, (size_t)kSscWarps * kSscBitmapWords * 4 + (size_t)kSscWarps * listCap * (small ? 2 : 4));
     b += (u + 15) & ~(size_t)15;
     if (small) b += (size_t)kSmallMax * (4 + 2 + 2 + 1);
+    else b += kBigKeySmem;
     return b;
 }
 
