@@ -12,7 +12,7 @@ if [ "${1:-bench}" = full ]; then
 # one step of our kernels at 64 frames (about 25 kernel launches per step: skip the three warm-up steps)
 python bench.py --frames 64 --steps 1 --warmup 3 --no-cpu-baseline --no-sustained > /dev/null 2>&1 || { echo "bench failed without ncu"; exit 1; }
 timeout 600 ncu --set full --clock-control none --import-source on \
-    -k regex:'pyr_fused|pyr_down|fast_cells|select_kernel|offsets_kernel|describe_fused|stereo_|grid_assign|tmp_|projb_' -s 75 -c 26 -f -o $O/full \
+    -k regex:'pyr_fused|pyr_down|fast_cells|select_kernel|offsets_kernel|describe_fused|row_bucket|stereo_|grid_assign|tmp_|projb_' -s 75 -c 26 -f -o $O/full \
     python bench.py --frames 64 --steps 1 --warmup 3 --no-cpu-baseline --no-sustained > $O/ncu_full.log 2>&1; echo "ncu full rc=$?"
 exit 0
 fi
