@@ -2,7 +2,7 @@
 """bench.py -- stereo frames/s of the frontend hot path: extract L + extract R + stereo match + key grids + temporal match.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload euroc|kitti|hires|small|mono]
-                    [--frames F] [--no-temporal] [--also kitti4096,hires]
+                    [--frames F] [--no-temporal] [--also kitti4096,hires] [--e2e-chunks C] [--e2e-slots S]
 
 A step = one pass of the hot path over one batch of F synthetic stereo frames per GPU (default workload: BASELINE.json
 configs[1], EuRoC MH_01-shaped 752x480 stereo, nFeatures 1000, F = 256 consecutive frames of a synthetic sequence).  The
@@ -15,7 +15,7 @@ data path; the only collective is the timing reduction).  Prints ONE JSON line o
   value     whole-job frames/s with the batch already resident in HBM (CUDA events, max over ranks), exactly K steps
   sustained the same loop repeated for >= 2 s (clocks sampled over that region)
   e2e       the same through the public API with pinned HOST images in and keypoints / descriptors / stereo arrays /
-            temporal matches back on the host inside the timed region
+            temporal matches back on the host inside the timed region (gvs_pipeline: C tickets per step over S slots)
   roofline  the dominant extraction kernel against the measured HBM peak (MEASURED_PEAKS.json), algorithmic bytes per
             SURVEY.md section 8(d); alu_roofline: the same kernel against the integer-ALU issue rate that actually bounds it
   cpu_baseline / --impl reference: the reference's own FeatureExtractor.cpp / FeatureMatcher.cpp (oracle/_ref, compiled
