@@ -509,7 +509,9 @@ def main():
                              "integer ALU pipe instead: see alu_roofline",
                      "pyramid": {"achieved": st_bytes["pyramid"] * 2 * F / (stage_acc["pyramid"] * 1e-3) / 1e9 if stage_acc["pyramid"] > 0 else None,
                                  "frac": st_bytes["pyramid"] * 2 * F / (stage_acc["pyramid"] * 1e-3) / 1e9 / peak if stage_acc["pyramid"] > 0 else None,
-                                 "ms_per_step": stage_acc["pyramid"]},
+                                 "ms_per_step": stage_acc["pyramid"],
+                                 "traffic_per_side": prof.get("pyramid"),   # DRAM bytes of the fused launches of ONE side (ncu, profiles/traffic.json)
+                                 "algorithmic_bytes_per_side": int(st_bytes["pyramid"] * F)},
                      "step": {"achieved": b_frame * F / (dev_ms * 1e-3) / 1e9, "frac": b_frame * F / (dev_ms * 1e-3) / 1e9 / peak,
                               "bytes_per_stereo_frame": b_frame}},
         "alu_roofline": alu_roofline(cfg, F, stage_acc["fast"] / 2, (clocks or {}).get("sm_mhz") or sm_max, prof.get("fast_alu_thread_instr_per_pixel")),
