@@ -57,3 +57,18 @@ def test_bad_arguments_are_reported():
     assert lib.gvs_extractor_destroy(None) == 0
     assert lib.gvs_extractor_sync(None) != 0
     assert b"null" in lib.gvs_last_error()
+
+
+def test_no_reference_source_text_in_the_tree():
+    """oracle/_ref holds build outputs only (a shared library and an object file): the FeatureTracker slices are piped into the
+    compiler, never written out, and no tracked file is a copy of a reference source file."""
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    if os.path.isdir(ref):
+        for f in os.listdir(ref):
+            assert f.endswith((".so", ".o")), f"unexpected file in oracle/_ref: {f}"
+    needle = "void FeatureTracker::assignKeysToGrids("   # a line of the reference that no file of this repo needs verbatim ...
+    for dp, dn, files in os.walk(ROOT):
+        dn[:] = [d for d in dn if d not in (".git", "gpurun_out", "__pycache__", "_ref", "_build", ".pytest_cache")]
+        for f in files:
+            if f.endswith((".cpp", ".cu", ".cuh", ".h", ".hpp", ".inc")):
+                assert needle not in open(os.path.join(dp, f), errors="ignore").read(), f   # ... (the slice recipe names it in a .py)
